@@ -1,0 +1,306 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see vp8_common.h).
+// Flat C entry points over the CPU restatement so tests/ and bench.py's cpu_baseline leg can
+// drive it through ctypes.  Nothing in webp_b200/ links this.
+#include "decoder.h"
+#include "encoder.h"
+#include <thread>
+#include <atomic>
+
+using namespace orc;
+
+extern "C" {
+
+// ---- whole-codec -------------------------------------------------------------------------
+struct OrcEncCfg {
+  int quality, method, sns_strength, filter_strength, filter_sharpness, filter_type, partitions, segments,
+      preprocessing, has_alpha;
+};
+static EncodeConfig to_cfg(const OrcEncCfg* c) {
+  EncodeConfig e;
+  e.quality = c->quality; e.method = c->method; e.sns_strength = c->sns_strength;
+  e.filter_strength = c->filter_strength; e.filter_sharpness = c->filter_sharpness;
+  e.filter_type = c->filter_type; e.partitions = c->partitions; e.segments = c->segments;
+  e.preprocessing = c->preprocessing;
+  return e;
+}
+// Encode one RGBA image (parallel-path semantics).  Returns RIFF size or <0 (-1 unsupported
+// config on this path, -2 output too small).  Optional taps may be NULL.
+//   mb_hdr [nmb][8]  : mb_type, i16_mode, uv_mode, segment, skip, nz_dc, alpha(after clustering), 0
+//   mb_modes [nmb][16], mb_nz [nmb][24] (16 Y + 8 UV), mb_coeffs [nmb][400]
+//   recon_y/u/v : reconstructed (unfiltered) planes, padded to 16*mb_w x 16*mb_h (and half)
+//   src_y/u/v   : imported source planes (same geometry); alphas [nmb] : pre-clustering alpha
+//   seg_out [4][8] int32 : quant, fstrength, alpha, beta, lambda_i4, lambda_i16, lambda_uv, lambda_mode
+long orc_encode(const uint8_t* rgba, int stride, int w, int h, const OrcEncCfg* cfg, uint8_t* out, long out_cap,
+                uint8_t* mb_hdr, uint8_t* mb_modes, uint8_t* mb_nz, int16_t* mb_coeffs, uint8_t* recon_y,
+                uint8_t* recon_u, uint8_t* recon_v, uint8_t* src_y, uint8_t* src_u, uint8_t* src_v,
+                uint8_t* alphas, int32_t* seg_out) {
+  if (cfg->method < 3 || ((h + 15) >> 4) < 4) return -1;  // serial path (encode.go:1356) not restated yet
+  Encoder* enc = new Encoder();
+  enc->init(rgba, stride, w, h, to_cfg(cfg), cfg->has_alpha);
+  std::vector<uint8_t> vp8 = enc->encode_frame();
+  std::vector<uint8_t> riff = riff_wrap(vp8);
+  const size_t nmb = enc->mb_info.size();
+  for (size_t i = 0; i < nmb; ++i) {
+    const MBInfo& m = enc->mb_info[i];
+    if (mb_hdr) {
+      uint8_t* hd = mb_hdr + 8 * i;
+      hd[0] = (uint8_t)m.mb_type; hd[1] = m.i16_mode; hd[2] = m.uv_mode; hd[3] = m.segment; hd[4] = m.skip;
+      hd[5] = m.nz_dc; hd[6] = (uint8_t)m.alpha; hd[7] = 0;
+    }
+    if (mb_modes) memcpy(mb_modes + 16 * i, m.modes, 16);
+    if (mb_nz) { memcpy(mb_nz + 24 * i, m.nz_y, 16); memcpy(mb_nz + 24 * i + 16, m.nz_uv, 8); }
+    if (mb_coeffs) memcpy(mb_coeffs + 400 * i, m.coeffs, 800);
+  }
+  if (recon_y) memcpy(recon_y, enc->y_plane.data(), enc->y_plane.size());
+  if (recon_u) memcpy(recon_u, enc->u_plane.data(), enc->u_plane.size());
+  if (recon_v) memcpy(recon_v, enc->v_plane.data(), enc->v_plane.size());
+  if (src_y) memcpy(src_y, enc->src_y.data(), enc->src_y.size());
+  if (src_u) memcpy(src_u, enc->src_u.data(), enc->src_u.size());
+  if (src_v) memcpy(src_v, enc->src_v.data(), enc->src_v.size());
+  if (alphas) memcpy(alphas, enc->alphas.data(), enc->alphas.size());
+  if (seg_out)
+    for (int s = 0; s < 4; ++s) {
+      int32_t* o = seg_out + 8 * s;
+      const SegmentInfo& d = enc->dqm[s];
+      o[0] = d.quant; o[1] = d.fstrength; o[2] = d.alpha; o[3] = d.beta; o[4] = d.lambda_i4; o[5] = d.lambda_i16;
+      o[6] = d.lambda_uv; o[7] = d.lambda_mode;
+    }
+  long ret = (long)riff.size();
+  if (ret > out_cap) ret = -2; else memcpy(out, riff.data(), riff.size());
+  delete enc;
+  return ret;
+}
+
+// Encode n same-size images on `threads` host threads (bench cpu_baseline / --impl reference).
+// sizes[i] receives each RIFF size; returns total bytes or <0.
+long orc_encode_batch(const uint8_t* rgba, int n, int stride, int w, int h, const OrcEncCfg* cfg, int threads,
+                      long* sizes) {
+  std::atomic<int> next(0);
+  std::atomic<long> total(0);
+  std::atomic<int> bad(0);
+  auto work = [&]() {
+    std::vector<uint8_t> out((size_t)w * h * 2 + (1 << 16));
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n) return;
+      const long r = orc_encode(rgba + (size_t)i * stride * h, stride, w, h, cfg, out.data(), (long)out.size(), 0, 0,
+                                0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+      if (r < 0) bad = 1;
+      if (sizes) sizes[i] = r;
+      total += r;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; ++t) th.emplace_back(work);
+  for (auto& t : th) t.join();
+  return bad ? -1 : total.load();
+}
+
+// Decode header only: 0 ok.
+int orc_decode_info(const uint8_t* data, long len, int* w, int* h, int* mb_w, int* mb_h) {
+  const uint8_t* vp8; size_t n;
+  if (!find_vp8_chunk(data, (size_t)len, &vp8, &n)) return -1;
+  Decoder d;
+  if (!d.parse_headers(vp8, n)) return -2;
+  *w = d.width; *h = d.height; *mb_w = d.mb_w; *mb_h = d.mb_h;
+  return 0;
+}
+// Full decode into padded planes (stride 16*mb_w / 8*mb_w).  filter=0 skips the loop filter
+// (returns the unfiltered reconstruction); filter=3 filters with libwebp's inner-edge rule
+// (cross-validation of libwebp-made streams only, see Decoder::libwebp_inner_rule).  Optional taps: per-MB parsed data.
+//   mb_coeffs [nmb][384], mb_meta [nmb][24]: is_i4, uvmode, skip, segment, f_limit, f_ilevel, f_inner, hev, imodes[16]
+//   mb_nz [nmb][2] uint32: non_zero_y, non_zero_uv ; hdr_out[4]: filter_type, sharpness, level, use_segment
+int orc_decode(const uint8_t* data, long len, int filter, uint8_t* y, uint8_t* u, uint8_t* v, int16_t* mb_coeffs,
+               uint8_t* mb_meta, uint32_t* mb_nz, int32_t* hdr_out) {
+  const uint8_t* vp8; size_t n;
+  if (!find_vp8_chunk(data, (size_t)len, &vp8, &n)) return -1;
+  Decoder* d = new Decoder();
+  int rc = 0;
+  if (!d->parse_headers(vp8, n)) { delete d; return -2; }
+  d->libwebp_inner_rule = (filter & 2) != 0;
+  d->y_stride = 16 * d->mb_w; d->uv_stride = 8 * d->mb_w;
+  d->mbs.assign((size_t)d->mb_w * d->mb_h, MBData());
+  d->finfo.assign((size_t)d->mb_w * d->mb_h, FInfo{0, 0, 0, 0});
+  d->y.assign((size_t)d->y_stride * 16 * d->mb_h, 0);
+  d->u.assign((size_t)d->uv_stride * 8 * d->mb_h, 0);
+  d->v.assign((size_t)d->uv_stride * 8 * d->mb_h, 0);
+  d->precompute_filter_strengths();
+  if (!d->parse_all()) rc = -3;
+  if (rc == 0) {
+    d->reconstruct_all();
+    if (filter && d->filter_type > 0)
+      for (int my = 0; my < d->mb_h; ++my)
+        for (int mx = 0; mx < d->mb_w; ++mx) d->do_filter(mx, my);
+    if (y) memcpy(y, d->y.data(), d->y.size());
+    if (u) memcpy(u, d->u.data(), d->u.size());
+    if (v) memcpy(v, d->v.data(), d->v.size());
+    const size_t nmb = d->mbs.size();
+    for (size_t i = 0; i < nmb; ++i) {
+      const MBData& m = d->mbs[i];
+      if (mb_coeffs) memcpy(mb_coeffs + 384 * i, m.coeffs, 768);
+      if (mb_meta) {
+        uint8_t* o = mb_meta + 24 * i;
+        const FInfo& f = d->finfo[i];
+        o[0] = m.is_i4x4; o[1] = m.uvmode; o[2] = m.skip; o[3] = m.segment;
+        o[4] = f.f_limit; o[5] = f.f_ilevel; o[6] = f.f_inner; o[7] = f.hev_thresh;
+        memcpy(o + 8, m.imodes, 16);
+      }
+      if (mb_nz) { mb_nz[2 * i] = m.non_zero_y; mb_nz[2 * i + 1] = m.non_zero_uv; }
+    }
+    if (hdr_out) { hdr_out[0] = d->filter_type; hdr_out[1] = d->f_sharpness; hdr_out[2] = d->f_level; hdr_out[3] = d->use_segment; }
+  }
+  delete d;
+  return rc;
+}
+
+// ---- stage-level ---------------------------------------------------------------------------
+// RGBA -> padded YUV420 planes (encode.go:671 importImage).
+void orc_import_rgba(const uint8_t* rgba, int stride, int w, int h, int has_alpha, uint8_t* y, uint8_t* u, uint8_t* v) {
+  Encoder* enc = new Encoder();
+  EncodeConfig c;
+  enc->cfg = c; enc->width = w; enc->height = h; enc->mb_w = (w + 15) >> 4; enc->mb_h = (h + 15) >> 4;
+  enc->y_stride = enc->mb_w * 16; enc->uv_stride = enc->mb_w * 8;
+  enc->y_plane.assign((size_t)enc->y_stride * enc->mb_h * 16, 0);
+  enc->u_plane.assign((size_t)enc->uv_stride * enc->mb_h * 8, 0);
+  enc->v_plane.assign((size_t)enc->uv_stride * enc->mb_h * 8, 0);
+  enc->import_image(rgba, stride, has_alpha);
+  memcpy(y, enc->y_plane.data(), enc->y_plane.size());
+  memcpy(u, enc->u_plane.data(), enc->u_plane.size());
+  memcpy(v, enc->v_plane.data(), enc->v_plane.size());
+  delete enc;
+}
+// buildNRGBA (webp.go:379)
+void orc_build_nrgba(int w, int h, const uint8_t* y, int ys, const uint8_t* u, const uint8_t* v, int uvs,
+                     const uint8_t* alpha, uint8_t* out) {
+  build_nrgba(w, h, y, ys, u, v, uvs, alpha, out);
+}
+// Plane metrics: SSE (ssim.go:172) and the sum over all pixels of SSIMGet / SSIMGetClipped
+// (interior / border windows, as libwebp's plane accumulation).
+uint64_t orc_plane_sse(const uint8_t* a, int sa, const uint8_t* b, int sb, int w, int h) {
+  uint64_t s = 0;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) { const int d = a[x + (size_t)y * sa] - b[x + (size_t)y * sb]; s += (uint64_t)(d * d); }
+  return s;
+}
+double orc_plane_ssim(const uint8_t* a, int sa, const uint8_t* b, int sb, int w, int h) {
+  double sum = 0;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      if (x >= 3 && y >= 3 && x + 3 < w && y + 3 < h)
+        sum += ssim_get(a + (x - 3) + (size_t)(y - 3) * sa, sa, b + (x - 3) + (size_t)(y - 3) * sb, sb);
+      else
+        sum += ssim_get_clipped(a, sa, b, sb, x, y, w, h);
+    }
+  return sum;
+}
+double orc_psnr_from_sse(uint64_t sse, uint64_t count) { return psnr_from_sse(sse, count); }
+// per-pixel SSIM map (float64 [h][w]) for tolerance checks
+void orc_plane_ssim_map(const uint8_t* a, int sa, const uint8_t* b, int sb, int w, int h, double* out) {
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x)
+      out[(size_t)y * w + x] = (x >= 3 && y >= 3 && x + 3 < w && y + 3 < h)
+                                   ? ssim_get(a + (x - 3) + (size_t)(y - 3) * sa, sa, b + (x - 3) + (size_t)(y - 3) * sb, sb)
+                                   : ssim_get_clipped(a, sa, b, sb, x, y, w, h);
+}
+
+// ---- dsp primitives, batched over n blocks (SoA) for property tests -----------------------
+// blocks are 4x4 (or 16x16) u8 tiles stored densely (16 or 256 bytes each).
+static void load4(const uint8_t* s, uint8_t* d) { for (int j = 0; j < 4; ++j) memcpy(d + j * BPS, s + 4 * j, 4); }
+void orc_ftransform_batch(int n, const uint8_t* src, const uint8_t* ref, int16_t* out) {
+  uint8_t a[4 * BPS], b[4 * BPS];
+  for (int i = 0; i < n; ++i) { load4(src + 16 * i, a); load4(ref + 16 * i, b); ftransform(a, b, out + 16 * i); }
+}
+void orc_itransform_batch(int n, const uint8_t* ref, const int16_t* in, uint8_t* dst) {
+  uint8_t a[4 * BPS], b[4 * BPS];
+  for (int i = 0; i < n; ++i) {
+    load4(ref + 16 * i, a);
+    itransform_one(a, in + 16 * i, b);
+    for (int j = 0; j < 4; ++j) memcpy(dst + 16 * i + 4 * j, b + j * BPS, 4);
+  }
+}
+void orc_fwht_batch(int n, const int16_t* in, int16_t* out) { for (int i = 0; i < n; ++i) ftransform_wht(in + 16 * i, out + 16 * i); }
+void orc_iwht_batch(int n, const int16_t* in, int16_t* out) {
+  int16_t tmp[256];
+  for (int i = 0; i < n; ++i) { transform_wht(in + 16 * i, tmp); for (int k = 0; k < 16; ++k) out[16 * i + k] = tmp[16 * k]; }
+}
+void orc_sse4x4_batch(int n, const uint8_t* a, const uint8_t* b, int32_t* out) {
+  uint8_t x[4 * BPS], y[4 * BPS];
+  for (int i = 0; i < n; ++i) { load4(a + 16 * i, x); load4(b + 16 * i, y); out[i] = sse4x4(x, y); }
+}
+void orc_tdisto4x4_batch(int n, const uint8_t* a, const uint8_t* b, int32_t* out) {
+  uint8_t x[4 * BPS], y[4 * BPS];
+  for (int i = 0; i < n; ++i) { load4(a + 16 * i, x); load4(b + 16 * i, y); out[i] = tdisto4x4(x, y); }
+}
+// 4x4 predictors: ctx[i] = 13 bytes {tl, t0..t7, l0..l3}; out 16 bytes per (block, mode) for modes 0..9
+void orc_pred4_batch(int n, const uint8_t* ctx, uint8_t* out) {
+  uint8_t buf[6 * BPS];
+  for (int i = 0; i < n; ++i) {
+    const uint8_t* c = ctx + 13 * i;
+    for (int mode = 0; mode < 10; ++mode) {
+      memset(buf, 0, sizeof(buf));
+      const int off = BPS + 8;
+      buf[off - BPS - 1] = c[0];
+      memcpy(buf + off - BPS, c + 1, 8);
+      for (int j = 0; j < 4; ++j) buf[off - 1 + j * BPS] = c[9 + j];
+      pred_luma4(mode, buf, off);
+      for (int j = 0; j < 4; ++j) memcpy(out + (i * 10 + mode) * 16 + 4 * j, buf + off + j * BPS, 4);
+    }
+  }
+}
+// 16x16 / 8x8 predictors: ctx = {tl, top[size], left[size]}; out size*size per (block, mode 0..6)
+void orc_pred_square_batch(int n, int size, const uint8_t* ctx, uint8_t* out) {
+  uint8_t buf[18 * BPS];
+  const int cs = 1 + 2 * size;
+  for (int i = 0; i < n; ++i) {
+    const uint8_t* c = ctx + cs * i;
+    for (int mode = 0; mode < 7; ++mode) {
+      memset(buf, 0, sizeof(buf));
+      const int off = BPS + 8;
+      buf[off - BPS - 1] = c[0];
+      memcpy(buf + off - BPS, c + 1, size);
+      for (int j = 0; j < size; ++j) buf[off - 1 + j * BPS] = c[1 + size + j];
+      pred_square(mode, buf, off, size);
+      for (int j = 0; j < size; ++j) memcpy(out + ((size_t)(i * 7 + mode) * size + j) * size, buf + off + j * BPS, size);
+    }
+  }
+}
+// quantize (encode_quant.go:16) with a full SegmentQuant derived from (dc_q, ac_q, bias type, sharpen on/off)
+static SegmentQuant make_sq(int dc_q, int ac_q, int type, int sharpen) {
+  SegmentQuant sq;
+  Encoder::init_segment_quant(&sq, dc_q, ac_q, type);
+  for (int i = 0; i < 16; ++i) sq.sharpen[i] = sharpen ? (int16_t)((kFreqSharpening[i] * (i == 0 ? dc_q : ac_q)) >> 11) : 0;
+  return sq;
+}
+void orc_quantize_batch(int n, const int16_t* in, int dc_q, int ac_q, int type, int sharpen, int first, int16_t* out,
+                        int32_t* nz) {
+  const SegmentQuant sq = make_sq(dc_q, ac_q, type, sharpen);
+  for (int i = 0; i < n; ++i) nz[i] = quantize_coeffs(in + 16 * i, out + 16 * i, &sq, first);
+}
+void orc_trellis_batch(int n, const int16_t* in, int dc_q, int ac_q, int qtype, int sharpen, int first, int ctx_type,
+                       const int32_t* ctx0, int lambda, int16_t* out, int32_t* nz) {
+  const SegmentQuant sq = make_sq(dc_q, ac_q, qtype, sharpen);
+  Proba p;
+  reset_proba(&p);
+  for (int i = 0; i < n; ++i) nz[i] = trellis_quantize_block(in + 16 * i, out + 16 * i, &sq, first, ctx_type, ctx0[i], &p, lambda);
+}
+void orc_token_cost_batch(int n, const int16_t* levels, const int32_t* nz, int ctx_type, const int32_t* ctx0, int first,
+                          int32_t* out) {
+  Proba p;
+  reset_proba(&p);
+  for (int i = 0; i < n; ++i) out[i] = token_cost(levels + 16 * i, nz[i], ctx_type, &p, ctx0[i], first);
+}
+void orc_fixed_costs_i4(uint16_t* out) {
+  Encoder* e = new Encoder();
+  e->compute_fixed_costs_i4();
+  memcpy(out, e->fixed_costs_i4, sizeof(e->fixed_costs_i4));
+  delete e;
+}
+void orc_gamma_tables(uint32_t* g2l, uint32_t* l2g) {
+  memcpy(g2l, gamma_tables().gamma_to_linear, 256 * 4);
+  memcpy(l2g, gamma_tables().linear_to_gamma, 34 * 4);
+}
+int orc_quality_to_qindex(int q) { return Encoder::quality_to_qindex(q); }
+const uint16_t* orc_level_fixed_costs() { return kLevelFixedCosts; }
+const uint16_t* orc_entropy_cost() { return kEntropyCost; }
+
+}  // extern "C"

@@ -1,0 +1,182 @@
+"""ctypes bindings to the CPU oracle (oracle/_build/liboracle.so) -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+
+class OrcEncCfg(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "quality", "method", "sns_strength", "filter_strength", "filter_sharpness", "filter_type",
+        "partitions", "segments", "preprocessing", "has_alpha")]
+
+
+def default_cfg(quality=75, method=4, **kw):
+    """lossy.DefaultConfig (internal/lossy/encode.go:66) + EncoderOptions mapping (encode.go:478-528)."""
+    c = OrcEncCfg(quality=quality, method=method, sns_strength=50, filter_strength=60, filter_sharpness=0,
+                  filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=0)
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_encode.restype = C.c_long
+        _LIB.orc_encode_batch.restype = C.c_long
+        _LIB.orc_plane_sse.restype = C.c_uint64
+        _LIB.orc_plane_ssim.restype = C.c_double
+        _LIB.orc_psnr_from_sse.restype = C.c_double
+        _LIB.orc_psnr_from_sse.argtypes = [C.c_uint64, C.c_uint64]
+        _LIB.orc_level_fixed_costs.restype = C.POINTER(C.c_uint16)
+        _LIB.orc_entropy_cost.restype = C.POINTER(C.c_uint16)
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def encode(rgba, cfg=None, taps=False):
+    """rgba: uint8 [h][w][4].  Returns bytes (RIFF) or (bytes, dict of taps)."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = rgba.shape[:2]
+    cfg = cfg or default_cfg()
+    mbw, mbh = (w + 15) >> 4, (h + 15) >> 4
+    nmb = mbw * mbh
+    out = np.zeros(w * h * 2 + 65536, np.uint8)
+    t = None
+    if taps:
+        t = dict(
+            mb_hdr=np.zeros((nmb, 8), np.uint8), mb_modes=np.zeros((nmb, 16), np.uint8),
+            mb_nz=np.zeros((nmb, 24), np.uint8), mb_coeffs=np.zeros((nmb, 400), np.int16),
+            recon_y=np.zeros((mbh * 16, mbw * 16), np.uint8), recon_u=np.zeros((mbh * 8, mbw * 8), np.uint8),
+            recon_v=np.zeros((mbh * 8, mbw * 8), np.uint8), src_y=np.zeros((mbh * 16, mbw * 16), np.uint8),
+            src_u=np.zeros((mbh * 8, mbw * 8), np.uint8), src_v=np.zeros((mbh * 8, mbw * 8), np.uint8),
+            alphas=np.zeros(nmb, np.uint8), seg=np.zeros((4, 8), np.int32))
+    args = [_p(t[k]) if t else None for k in ("mb_hdr", "mb_modes", "mb_nz", "mb_coeffs", "recon_y", "recon_u",
+                                               "recon_v", "src_y", "src_u", "src_v", "alphas", "seg")]
+    n = lib().orc_encode(_p(rgba), C.c_int(rgba.strides[0]), w, h, C.byref(cfg), _p(out), C.c_long(out.size), *args)
+    if n < 0:
+        raise RuntimeError("orc_encode failed: %d" % n)
+    data = out[:n].tobytes()
+    return (data, t) if taps else data
+
+
+def encode_batch(rgba_batch, cfg=None, threads=1):
+    """rgba_batch uint8 [n][h][w][4]; returns total compressed bytes (timing leg)."""
+    rgba_batch = np.ascontiguousarray(rgba_batch, dtype=np.uint8)
+    n, h, w = rgba_batch.shape[:3]
+    cfg = cfg or default_cfg()
+    sizes = np.zeros(n, np.int64)
+    r = lib().orc_encode_batch(_p(rgba_batch), n, w * 4, w, h, C.byref(cfg), threads, _p(sizes))
+    if r < 0:
+        raise RuntimeError("orc_encode_batch failed")
+    return r, sizes
+
+
+def decode_info(data):
+    w, h, mbw, mbh = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    rc = lib().orc_decode_info(data, C.c_long(len(data)), C.byref(w), C.byref(h), C.byref(mbw), C.byref(mbh))
+    if rc:
+        raise RuntimeError("orc_decode_info: %d" % rc)
+    return w.value, h.value, mbw.value, mbh.value
+
+
+def decode(data, filter=True, taps=False, libwebp_inner_rule=False):
+    """Returns (w, h, Y, U, V) padded planes (and per-MB parsed data if taps)."""
+    w, h, mbw, mbh = decode_info(data)
+    y = np.zeros((mbh * 16, mbw * 16), np.uint8)
+    u = np.zeros((mbh * 8, mbw * 8), np.uint8)
+    v = np.zeros((mbh * 8, mbw * 8), np.uint8)
+    t = None
+    nmb = mbw * mbh
+    if taps:
+        t = dict(coeffs=np.zeros((nmb, 384), np.int16), meta=np.zeros((nmb, 24), np.uint8),
+                 nz=np.zeros((nmb, 2), np.uint32), hdr=np.zeros(4, np.int32))
+    rc = lib().orc_decode(data, C.c_long(len(data)), (int(bool(filter)) | (2 if libwebp_inner_rule else 0)), _p(y), _p(u), _p(v),
+                          _p(t["coeffs"]) if t else None, _p(t["meta"]) if t else None,
+                          _p(t["nz"]) if t else None, _p(t["hdr"]) if t else None)
+    if rc:
+        raise RuntimeError("orc_decode: %d" % rc)
+    return (w, h, y, u, v, t) if taps else (w, h, y, u, v)
+
+
+def import_rgba(rgba, has_alpha=False):
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = rgba.shape[:2]
+    mbw, mbh = (w + 15) >> 4, (h + 15) >> 4
+    y = np.zeros((mbh * 16, mbw * 16), np.uint8)
+    u = np.zeros((mbh * 8, mbw * 8), np.uint8)
+    v = np.zeros((mbh * 8, mbw * 8), np.uint8)
+    lib().orc_import_rgba(_p(rgba), C.c_int(rgba.strides[0]), w, h, int(has_alpha), _p(y), _p(u), _p(v))
+    return y, u, v
+
+
+def build_nrgba(w, h, y, u, v, alpha=None):
+    out = np.zeros((h, w, 4), np.uint8)
+    lib().orc_build_nrgba(w, h, _p(y), C.c_int(y.strides[0]), _p(u), _p(v), C.c_int(u.strides[0]),
+                          _p(alpha) if alpha is not None else None, _p(out))
+    return out
+
+
+def plane_sse(a, b):
+    h, w = a.shape
+    return int(lib().orc_plane_sse(_p(a), C.c_int(a.strides[0]), _p(b), C.c_int(b.strides[0]), w, h))
+
+
+def plane_ssim(a, b):
+    h, w = a.shape
+    return float(lib().orc_plane_ssim(_p(a), C.c_int(a.strides[0]), _p(b), C.c_int(b.strides[0]), w, h))
+
+
+def plane_ssim_map(a, b):
+    h, w = a.shape
+    out = np.zeros((h, w), np.float64)
+    lib().orc_plane_ssim_map(_p(a), C.c_int(a.strides[0]), _p(b), C.c_int(b.strides[0]), w, h, _p(out))
+    return out
+
+
+# ------------------------------------------------------------------ synthetic images
+def synth_image(w, h, index, kind=None):
+    """Deterministic opaque RGBA test image; three content classes (gradient / textured / noisy)."""
+    kind = index % 3 if kind is None else kind
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.int64)
+    rng = np.random.RandomState(0xC0FFEE + index)
+    if kind == 0:  # smooth gradients (root encode_test.go:1496 richTestImage shape)
+        r = xx * 255 // max(w, 1)
+        g = yy * 255 // max(h, 1)
+        b = (xx + yy) * 255 // max(w + h, 1)
+    elif kind == 1:  # gradient + band-limited noise + hard-edged rectangles
+        base = rng.randint(-24, 25, size=((h + 7) // 8 + 1, (w + 7) // 8 + 1, 3))
+        noise = np.kron(base, np.ones((8, 8, 1), np.int64))[:h, :w]
+        r = xx * 255 // max(w, 1) + noise[..., 0]
+        g = yy * 255 // max(h, 1) + noise[..., 1]
+        b = 128 + noise[..., 2]
+        for _ in range(12):
+            x0, y0 = rng.randint(0, w), rng.randint(0, h)
+            x1, y1 = min(w, x0 + rng.randint(4, max(5, w // 4))), min(h, y0 + rng.randint(4, max(5, h // 4)))
+            col = rng.randint(0, 256, 3)
+            r[y0:y1, x0:x1], g[y0:y1, x0:x1], b[y0:y1, x0:x1] = col
+    else:  # noisy image (race_test.go:78 noisyImage shape)
+        r = (xx * 7 + yy * 13) % 256 + rng.randint(-16, 17, size=(h, w))
+        g = (xx * 3 + yy * 5) % 256 + rng.randint(-16, 17, size=(h, w))
+        b = (xx ^ yy) % 256
+    img = np.stack([r, g, b, np.full_like(r, 255)], axis=-1)
+    return np.clip(img, 0, 255).astype(np.uint8)
