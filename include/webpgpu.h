@@ -1,0 +1,147 @@
+/* webpgpu.h -- C ABI of the B200 (sm_100a) VP8 lossy pixel pipeline.
+ *
+ * Drop-in boundary for deepteams/webp: these are the entry points a `//go:build cuda && cgo`
+ * file in internal/dsp and internal/lossy binds (see INTEGRATION.md for the cgo stubs).
+ * Plain pointers and sizes only; no exceptions cross the boundary; no caller pointer is
+ * retained after a call returns (cgo rule).  Every function returns 0 on success or a
+ * negative wgpu_status; wgpu_last_error(ctx) gives the message.  One ctx == one GPU; calls on
+ * one ctx are serialised by the library, different ctxs are independent.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   wgpu_encode_batch        lossy.NewEncoder + (*VP8Encoder).EncodeFrame   internal/lossy/encode.go:452,1324
+ *                            (called from encodeLossyWithAlpha, encode.go:472-546) + writeRIFFSimple encode.go:968
+ *   wgpu_decode_batch        lossy.DecodeFrame (+ buildYCbCr / buildNRGBA)    internal/lossy/decode.go:209, webp.go:351,379
+ *   wgpu_import_rgba         (*VP8Encoder).importImage                       internal/lossy/encode.go:671
+ *   wgpu_upsample_nrgba      buildNRGBA / dsp.UpsampleLinePairNRGBA           webp.go:379, internal/dsp/upsample.go:130
+ *   wgpu_plane_metrics       dsp.SSE / SSIMGet / SSIMGetClipped / PSNRFromSSE internal/dsp/ssim.go:116-181
+ *   wgpu_dsp_*_batch         the per-block operator surface                  internal/dsp/dsp.go:12-37,
+ *                            FTransformDirect/ITransformDirect/SSE4x4Direct/TDisto4x4/PredLuma4Direct,
+ *                            lossy.QuantizeCoeffs, lossy.TrellisQuantizeBlock  internal/lossy/encode_quant.go:16, encode_trellis.go:23
+ */
+#ifndef WEBPGPU_H_
+#define WEBPGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wgpu_ctx wgpu_ctx;
+
+typedef enum {
+  WGPU_OK = 0,
+  WGPU_ERR_INVALID = -1,     /* bad argument / option out of range (validateConfig, encode.go:259) */
+  WGPU_ERR_UNSUPPORTED = -2, /* configuration routed to a reference path not built yet (serial path) */
+  WGPU_ERR_CUDA = -3,        /* CUDA runtime failure; there is NO CPU fallback */
+  WGPU_ERR_NOMEM = -4,
+  WGPU_ERR_BITSTREAM = -5,   /* malformed VP8/RIFF input */
+  WGPU_ERR_TOO_SMALL = -6    /* caller output buffer too small */
+} wgpu_status;
+
+/* lossy.EncodeConfig (internal/lossy/encode.go:46-63) after the EncoderOptions mapping of
+ * encode.go:478-528; defaults = lossy.DefaultConfig (encode.go:66-86). */
+typedef struct {
+  int quality;          /* 0..100 */
+  int method;           /* 0..6; 3..6 supported (parallel path), <3 -> WGPU_ERR_UNSUPPORTED */
+  int sns_strength;     /* 0..100, default 50 */
+  int filter_strength;  /* 0..100, default 60 */
+  int filter_sharpness; /* 0..7 */
+  int filter_type;      /* 0 simple, 1 strong */
+  int partitions;       /* 0..3 (log2) */
+  int segments;         /* 1..4 */
+  int preprocessing;    /* bit0: segment smoothing */
+  int has_alpha;        /* 0: opaque input (alpha bytes ignored) */
+} wgpu_enc_options;
+
+void wgpu_enc_options_default(wgpu_enc_options* o, int quality);
+
+/* ---- context ------------------------------------------------------------------------- */
+int wgpu_ctx_create(int device_ordinal, wgpu_ctx** out);
+void wgpu_ctx_destroy(wgpu_ctx* ctx);
+const char* wgpu_last_error(const wgpu_ctx* ctx); /* ctx may be NULL: last create error */
+int wgpu_sync(wgpu_ctx* ctx);
+/* host worker threads used for bitstream serialisation / parsing (0 = hardware concurrency) */
+int wgpu_set_host_threads(wgpu_ctx* ctx, int n);
+/* pinned host staging (device image-batch allocator; internal/pool analogue) */
+void* wgpu_host_alloc(wgpu_ctx* ctx, size_t bytes);
+void wgpu_host_free(wgpu_ctx* ctx, void* p);
+
+/* ---- encoder: whole job --------------------------------------------------------------- */
+/* Encode n same-size RGBA images (4 B/px, `stride` bytes per row, image i at rgba + i*image_stride).
+ * out receives n RIFF/WebP files, file i at out + i*out_stride, length out_sizes[i].
+ * Output bytes are identical to the reference's webp.Encode on its parallel path
+ * (Method>=3, single pass, GOMAXPROCS>1, height>48). */
+int wgpu_encode_batch(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int height, int stride,
+                      size_t image_stride, const wgpu_enc_options* opt, uint8_t* out, size_t out_stride,
+                      size_t* out_sizes);
+
+/* Staged form of the same job (used by bench.py to separate H2D / device / host time):
+ *   upload  : host RGBA -> HBM (async on the ctx stream)
+ *   device  : import + analysis + segmentation + wavefront mode search, results stay in HBM
+ *   finish  : D2H of per-MB modes/levels + host token/probability/bool coding -> RIFF bytes */
+int wgpu_enc_upload(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int height, int stride, size_t image_stride);
+int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt);
+int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_sizes);
+
+/* Debug/parity taps of the last wgpu_enc_device call (any pointer may be NULL).  Layouts as the
+ * oracle's taps: mb_hdr [nmb][8] = {mb_type,i16_mode,uv_mode,segment,skip,nz_dc,0,0}, mb_modes [nmb][16],
+ * mb_nz [nmb][24], mb_coeffs [nmb][400] int16, planes padded to 16*mb_w x 16*mb_h (chroma half). */
+int wgpu_enc_fetch(wgpu_ctx* ctx, int image, uint8_t* mb_hdr, uint8_t* mb_modes, uint8_t* mb_nz, int16_t* mb_coeffs,
+                   uint8_t* recon_y, uint8_t* recon_u, uint8_t* recon_v, uint8_t* src_y, uint8_t* src_u,
+                   uint8_t* src_v, uint8_t* alphas);
+
+/* ---- decoder: whole job --------------------------------------------------------------- */
+/* Header probe (webp.DecodeConfig): dimensions of a RIFF/WebP or raw VP8 lossy stream. */
+int wgpu_decode_info(const uint8_t* data, size_t len, int* width, int* height);
+/* Decode n lossy streams of identical dimensions.  Host parses headers/modes/tokens (bool
+ * decoder), the GPU reconstructs (predict + inverse transform, wavefront), loop-filters and
+ * optionally converts.  Planes are written with stride 16*mb_w (luma) / 8*mb_w (chroma),
+ * plane i at y + i*y_plane_stride etc.  nrgba (optional) gets width*height*4 bytes per image
+ * with buildNRGBA semantics (webp.go:379) and A=255. */
+int wgpu_decode_batch(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* lens, int n, uint8_t* y,
+                      uint8_t* u, uint8_t* v, size_t y_plane_stride, size_t uv_plane_stride, uint8_t* nrgba,
+                      size_t nrgba_image_stride);
+
+/* ---- stage-level entry points (host buffers in/out) ------------------------------------ */
+int wgpu_import_rgba(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int height, int stride,
+                     size_t image_stride, int has_alpha, uint8_t* y, uint8_t* u, uint8_t* v);
+int wgpu_upsample_nrgba(wgpu_ctx* ctx, int n, int width, int height, const uint8_t* y, int y_stride,
+                        const uint8_t* u, const uint8_t* v, int uv_stride, size_t y_plane_stride,
+                        size_t uv_plane_stride, const uint8_t* alpha, uint8_t* nrgba);
+/* per plane pair: sse[i] (u64) and ssim_sum[i] (f64, sum over all pixels of SSIMGet/SSIMGetClipped) */
+int wgpu_plane_metrics(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int width, int height, int stride,
+                       size_t plane_stride, uint64_t* sse, double* ssim_sum);
+double wgpu_psnr_from_sse(uint64_t sse, uint64_t count);
+
+/* ---- per-block dsp operator surface, batched (n blocks, dense 4x4 tiles of 16 bytes) ---- */
+int wgpu_dsp_ftransform_batch(wgpu_ctx* ctx, int n, const uint8_t* src, const uint8_t* ref, int16_t* out);
+int wgpu_dsp_itransform_batch(wgpu_ctx* ctx, int n, const uint8_t* ref, const int16_t* in, uint8_t* dst);
+int wgpu_dsp_fwht_batch(wgpu_ctx* ctx, int n, const int16_t* in, int16_t* out);
+int wgpu_dsp_iwht_batch(wgpu_ctx* ctx, int n, const int16_t* in, int16_t* out);
+int wgpu_dsp_sse4x4_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int32_t* out);
+int wgpu_dsp_tdisto4x4_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int32_t* out);
+/* ctx13[i] = {tl, t0..t7, l0..l3}; out[(i*10+mode)*16..] for the ten B_* modes */
+int wgpu_dsp_pred4_batch(wgpu_ctx* ctx, int n, const uint8_t* ctx13, uint8_t* out);
+/* quantizer derived as initSegmentQuant(dc_q, ac_q, type) (+ Y1 sharpening when sharpen!=0) */
+int wgpu_dsp_quantize_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, int ac_q, int type, int sharpen,
+                            int first, int16_t* out, int32_t* nz);
+int wgpu_dsp_trellis_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, int ac_q, int qtype, int sharpen,
+                           int first, int ctx_type, const int32_t* ctx0, int lambda, int16_t* out, int32_t* nz);
+int wgpu_dsp_token_cost_batch(wgpu_ctx* ctx, int n, const int16_t* levels, const int32_t* nz, int ctx_type,
+                              const int32_t* ctx0, int first, int32_t* out);
+
+/* ---- measurement helpers (device timing on the library's own stream) -------------------- */
+int wgpu_timer_begin(wgpu_ctx* ctx);           /* records a CUDA event on the ctx stream */
+int wgpu_timer_end(wgpu_ctx* ctx, float* ms);   /* records + synchronises, returns elapsed ms */
+/* Number of kernels this library launched on ctx since creation (for bench.py gpu_launches). */
+uint64_t wgpu_launch_count(const wgpu_ctx* ctx);
+/* Timed device-only repetitions of one stage over data already uploaded by wgpu_enc_upload /
+ * decoded data; used for roofline numbers.  stage: 0 import, 1 analysis, 2 mode search (all waves). */
+int wgpu_enc_stage_time(wgpu_ctx* ctx, const wgpu_enc_options* opt, int stage, int reps, float* ms_per_rep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEBPGPU_H_ */

@@ -1,0 +1,208 @@
+"""GPU parity, pipeline level: import, analysis, mode search + serialisation (WebP bytes), decoder
+reconstruction + loop filter, fancy upsampler, SSE/SSIM -- all through the C ABI, bit-exact against the oracle
+(SSIM within 1e-6 relative, BASELINE.json north_star)."""
+import ctypes as C
+import io
+import os
+
+import numpy as np
+import pytest
+
+import webp_b200
+from webp_b200 import dsp, native
+
+pytestmark = pytest.mark.gpu
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+def _opts(**kw):
+    o = webp_b200.DefaultOptions()
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def _ocfg(oracle, o):
+    c = webp_b200.webp.lossy_config(o)
+    return oracle.default_cfg(**{f: getattr(c, f) for f, _ in c._fields_})
+
+
+def _fetch(ctx, i, w, h):
+    mbw, mbh = (w + 15) >> 4, (h + 15) >> 4
+    nmb = mbw * mbh
+    t = dict(mb_hdr=np.zeros((nmb, 8), np.uint8), mb_modes=np.zeros((nmb, 16), np.uint8), mb_nz=np.zeros((nmb, 24), np.uint8),
+             mb_coeffs=np.zeros((nmb, 400), np.int16), recon_y=np.zeros((mbh * 16, mbw * 16), np.uint8),
+             recon_u=np.zeros((mbh * 8, mbw * 8), np.uint8), recon_v=np.zeros((mbh * 8, mbw * 8), np.uint8),
+             src_y=np.zeros((mbh * 16, mbw * 16), np.uint8), src_u=np.zeros((mbh * 8, mbw * 8), np.uint8),
+             src_v=np.zeros((mbh * 8, mbw * 8), np.uint8), alphas=np.zeros(nmb, np.uint8))
+    ctx.check(native.lib().wgpu_enc_fetch(ctx.handle, i, *[t[k].ctypes.data for k in (
+        "mb_hdr", "mb_modes", "mb_nz", "mb_coeffs", "recon_y", "recon_u", "recon_v", "src_y", "src_u", "src_v", "alphas")]))
+    return t
+
+
+def first_diff(name, got, exp):
+    if np.array_equal(got, exp):
+        return None
+    idx = np.argwhere(got != exp)
+    return "%s: %d mismatches, first at %s got %s exp %s" % (name, len(idx), idx[0].tolist(), got[tuple(idx[0])], exp[tuple(idx[0])])
+
+
+@pytest.mark.parametrize("w,h,has_alpha", [(64, 64, 0), (130, 71, 0), (33, 49, 0), (1536, 1024, 0), (96, 80, 1)])
+def test_import_rgba(oracle, gpu_ctx, w, h, has_alpha):
+    imgs = np.stack([oracle.synth_image(w, h, i) for i in range(3)])
+    if has_alpha:
+        rng = np.random.RandomState(9)
+        imgs[..., 3] = rng.randint(0, 256, imgs.shape[:3])
+        imgs[0, :16, :16, 3] = 0
+    y, u, v = dsp.ImportRGBA(imgs, bool(has_alpha), gpu_ctx)
+    for i in range(3):
+        ey, eu, ev = oracle.import_rgba(imgs[i], bool(has_alpha))
+        assert np.array_equal(y[i], ey) and np.array_equal(u[i], eu) and np.array_equal(v[i], ev)
+
+
+ENC_CASES = [
+    (128, 96, [0, 1, 2], {}),
+    (100, 70, [1, 2], {}),
+    (256, 192, [1], dict(Segments=1)),
+    (128, 96, [1, 2], dict(Method=3)),
+    (128, 96, [1, 2], dict(Method=6, Quality=40)),
+    (128, 96, [1, 2], dict(Quality=95, SNSStrength=0)),
+    (128, 96, [2], dict(Quality=5)),
+    (128, 96, [1, 2], dict(FilterType=0, FilterSharpness=5, FilterStrength=80, Preprocessing=1)),
+    (128, 128, [2], dict(Partitions=2, Quality=90)),
+    (128, 128, [1], dict(Partitions=3)),
+    (768, 576, [1], {}),
+]
+
+
+@pytest.mark.parametrize("w,h,idxs,kw", ENC_CASES)
+def test_encode_bytes_and_decisions(oracle, gpu_ctx, w, h, idxs, kw):
+    o = _opts(**kw)
+    imgs = np.stack([oracle.synth_image(w, h, i) for i in idxs])
+    files = webp_b200.EncodeBatch(imgs, o, gpu_ctx)
+    for k, i in enumerate(idxs):
+        exp, t = oracle.encode(imgs[k], _ocfg(oracle, o), taps=True)
+        g = _fetch(gpu_ctx, k, w, h)
+        errs = [first_diff("alphas", g["alphas"], t["alphas"]),
+                first_diff("segment", g["mb_hdr"][:, 3], t["mb_hdr"][:, 3]),
+                first_diff("mb_type", g["mb_hdr"][:, 0], t["mb_hdr"][:, 0]),
+                first_diff("hdr", g["mb_hdr"][:, :6], t["mb_hdr"][:, :6]),
+                first_diff("modes", g["mb_modes"], t["mb_modes"]),
+                first_diff("nz", g["mb_nz"], t["mb_nz"]),
+                first_diff("coeffs", g["mb_coeffs"], t["mb_coeffs"]),
+                first_diff("recon_y", g["recon_y"][:h, :w], t["recon_y"][:h, :w])]
+        errs = [e for e in errs if e]
+        assert not errs, "image %d: %s" % (i, "; ".join(errs))
+        assert files[k] == exp, "image %d: bitstream differs (%d vs %d bytes)" % (i, len(files[k]), len(exp))
+
+
+def test_encode_test_png(oracle, gpu_ctx):
+    # BASELINE.json configs[0]: testdata/test.png q75 m4 (768x576 RGBA, all opaque)
+    from PIL import Image
+    img = np.array(Image.open(os.path.join(DATA, "test.png")).convert("RGBA"))
+    buf = io.BytesIO()
+    webp_b200.Encode(buf, img, webp_b200.DefaultOptions(), gpu_ctx)
+    assert buf.getvalue() == oracle.encode(img)
+
+
+def test_encode_rejections(gpu_ctx):
+    img = np.full((64, 64, 4), 255, np.uint8)
+    with pytest.raises(native.WebPGPUError) as e:
+        webp_b200.EncodeBatch(img[None], _opts(Method=2), gpu_ctx)
+    assert e.value.code == native.ERR_UNSUPPORTED
+    with pytest.raises(native.WebPGPUError) as e:
+        webp_b200.EncodeBatch(img[None, :40], _opts(), gpu_ctx)
+    assert e.value.code == native.ERR_UNSUPPORTED
+    with pytest.raises(webp_b200.WebPError):
+        webp_b200.EncodeBatch(img[None], _opts(Lossless=True), gpu_ctx)
+
+
+DEC_CASES = [(128, 96, {}), (100, 70, {}), (130, 71, dict(segments=1)), (128, 96, dict(filter_type=0, segments=1)),
+             (128, 96, dict(filter_strength=0)), (160, 112, dict(filter_sharpness=6, segments=1, filter_strength=100)),
+             (128, 128, dict(partitions=2, quality=90)), (768, 576, dict(segments=1)), (64, 64, dict(quality=10))]
+
+
+@pytest.mark.parametrize("w,h,kw", DEC_CASES)
+def test_decode_planes_and_nrgba(oracle, gpu_ctx, w, h, kw):
+    streams = [oracle.encode(oracle.synth_image(w, h, i), oracle.default_cfg(**kw)) for i in (2, 1, 0)]
+    gw, gh, y, u, v, rgba = webp_b200.webp.decode_padded(streams, nrgba=True, ctx=gpu_ctx)
+    assert (gw, gh) == (w, h)
+    for i, s in enumerate(streams):
+        _, _, ey, eu, ev = oracle.decode(s)
+        errs = [first_diff("y", y[i], ey), first_diff("u", u[i], eu), first_diff("v", v[i], ev),
+                first_diff("nrgba", rgba[i], oracle.build_nrgba(w, h, ey, eu, ev))]
+        errs = [e for e in errs if e]
+        assert not errs, "stream %d: %s" % (i, "; ".join(errs))
+
+
+def test_decode_reference_fixtures_and_foreign_stream(oracle, gpu_ctx):
+    for name in ("blue_16x16_lossy.webp", "red_4x4_lossy.webp"):
+        data = open(os.path.join(DATA, name), "rb").read()
+        w, h, y, u, v, rgba = webp_b200.webp.decode_padded([data], nrgba=True, ctx=gpu_ctx)
+        _, _, ey, eu, ev = oracle.decode(data)
+        assert np.array_equal(y[0], ey) and np.array_equal(u[0], eu) and np.array_equal(v[0], ev)
+        assert np.array_equal(rgba[0], oracle.build_nrgba(w, h, ey, eu, ev))
+    img = webp_b200.Decode(io.BytesIO(open(os.path.join(DATA, "blue_16x16_lossy.webp"), "rb").read()), gpu_ctx)
+    assert img.Y.shape == (16, 16) and img.Cb.shape == (8, 8)
+    from PIL import Image
+    buf = io.BytesIO()
+    Image.fromarray(oracle.synth_image(200, 120, 1)[..., :3]).save(buf, "WEBP", quality=60, method=4)
+    data = buf.getvalue()
+    w, h, y, u, v, _ = webp_b200.webp.decode_padded([data], ctx=gpu_ctx)
+    _, _, ey, eu, ev = oracle.decode(data)
+    assert np.array_equal(y[0], ey) and np.array_equal(u[0], eu) and np.array_equal(v[0], ev)
+
+
+def test_decode_errors(gpu_ctx, oracle):
+    data = oracle.encode(oracle.synth_image(64, 64, 1))
+    with pytest.raises(native.WebPGPUError) as e:
+        webp_b200.webp.decode_padded([data[:len(data) // 2]], ctx=gpu_ctx)
+    assert e.value.code == native.ERR_BITSTREAM
+    other = oracle.encode(oracle.synth_image(80, 64, 1))
+    with pytest.raises(native.WebPGPUError):
+        webp_b200.webp.decode_padded([data, other], ctx=gpu_ctx)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 2), (5, 3), (16, 16), (33, 49), (130, 71), (1536, 1024)])
+def test_upsample_nrgba(oracle, gpu_ctx, w, h):
+    rng = np.random.RandomState(w * 31 + h)
+    n = 2
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    y = rng.randint(0, 256, (n, h, w)).astype(np.uint8)
+    u = rng.randint(0, 256, (n, ch, cw)).astype(np.uint8)
+    v = rng.randint(0, 256, (n, ch, cw)).astype(np.uint8)
+    a = rng.randint(0, 256, (n, h, w)).astype(np.uint8)
+    got = dsp.UpsampleNRGBA(y, u, v, w, h, None, gpu_ctx)
+    got_a = dsp.UpsampleNRGBA(y, u, v, w, h, a, gpu_ctx)
+    for i in range(n):
+        assert np.array_equal(got[i], oracle.build_nrgba(w, h, y[i], u[i], v[i]))
+        assert np.array_equal(got_a[i], oracle.build_nrgba(w, h, y[i], u[i], v[i], a[i]))
+
+
+@pytest.mark.parametrize("w,h", [(7, 7), (8, 3), (40, 56), (130, 71), (1536, 1024)])
+def test_plane_metrics(oracle, gpu_ctx, w, h):
+    rng = np.random.RandomState(w + h)
+    a = rng.randint(0, 256, (2, h, w)).astype(np.uint8)
+    b = np.clip(a.astype(np.int32) + rng.randint(-12, 13, a.shape), 0, 255).astype(np.uint8)
+    b[1] = a[1]
+    sse, ssim = dsp.PlaneMetrics(a, b, gpu_ctx)
+    for i in range(2):
+        assert int(sse[i]) == oracle.plane_sse(a[i], b[i])
+        exp = oracle.plane_ssim(a[i], b[i])
+        assert abs(ssim[i] - exp) <= 1e-6 * abs(exp)  # north_star tolerance: 1e-6 relative
+        assert dsp.PSNRFromSSE(sse[i], w * h) == oracle.lib().orc_psnr_from_sse(int(sse[i]), w * h)
+
+
+def test_round_trip_at_full_size(oracle, gpu_ctx):
+    """BASELINE configs[1]/[2] shape: 1536x1024 q75 m4 -> own decoder -> libwebp-identical planes; size-independent
+    properties: GPU decode of GPU bytes == encoder's own reconstruction (filter off), PSNR >= 30 dB."""
+    imgs = np.stack([oracle.synth_image(1536, 1024, i) for i in (0, 1)])
+    o = _opts(FilterStrength=0)
+    files = webp_b200.EncodeBatch(imgs, o, gpu_ctx)
+    g = [_fetch(gpu_ctx, k, 1536, 1024) for k in range(2)]
+    _, _, y, u, v, _ = webp_b200.webp.decode_padded(files, ctx=gpu_ctx)
+    for k in range(2):
+        assert np.array_equal(y[k], g[k]["recon_y"]) and np.array_equal(u[k], g[k]["recon_u"]) and np.array_equal(v[k], g[k]["recon_v"])
+        sse, _ = dsp.PlaneMetrics(g[k]["src_y"][None], y[k][None], gpu_ctx)
+        assert dsp.PSNRFromSSE(sse[0], 1536 * 1024) >= 30.0
+    assert files[1] == oracle.encode(imgs[1], _ocfg(oracle, o))

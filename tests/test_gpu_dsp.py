@@ -1,0 +1,95 @@
+"""GPU parity, operator surface: every batched dsp entry point vs the oracle on the same seeded inputs, bit-exact.
+Pattern and input ranges follow internal/dsp/simd_test.go (pixels 0..255, coefficients +-1000 / +-2048, WHT +-256)."""
+import numpy as np
+import pytest
+
+from webp_b200 import dsp
+
+pytestmark = pytest.mark.gpu
+N = 20000
+
+
+def _p(a):
+    return a.ctypes.data
+
+
+def test_ftransform(oracle, gpu_ctx):
+    rng = np.random.RandomState(1)
+    src = rng.randint(0, 256, (N, 16)).astype(np.uint8); ref = rng.randint(0, 256, (N, 16)).astype(np.uint8)
+    src[:100] = 255; ref[:100] = 0; src[100:200] = 0; ref[100:200] = 255
+    exp = np.zeros((N, 16), np.int16)
+    oracle.lib().orc_ftransform_batch(N, _p(src), _p(ref), _p(exp))
+    assert np.array_equal(dsp.FTransformBatch(src, ref, gpu_ctx), exp)
+
+
+@pytest.mark.parametrize("amp", [1000, 2048, 32000])
+def test_itransform(oracle, gpu_ctx, amp):
+    rng = np.random.RandomState(2)
+    ref = rng.randint(0, 256, (N, 16)).astype(np.uint8)
+    co = rng.randint(-amp, amp + 1, (N, 16)).astype(np.int16)
+    co[: N // 4, 2:] = 0  # AC3-shaped and DC-only blocks
+    co[: N // 8, 1:] = 0
+    exp = np.zeros((N, 16), np.uint8)
+    oracle.lib().orc_itransform_batch(N, _p(ref), _p(co), _p(exp))
+    assert np.array_equal(dsp.ITransformBatch(ref, co, gpu_ctx), exp)
+
+
+def test_wht(oracle, gpu_ctx):
+    rng = np.random.RandomState(3)
+    a = rng.randint(-2040, 2041, (N, 16)).astype(np.int16)
+    exp = np.zeros((N, 16), np.int16)
+    oracle.lib().orc_fwht_batch(N, _p(a), _p(exp))
+    assert np.array_equal(dsp.FTransformWHTBatch(a, gpu_ctx), exp)
+    b = rng.randint(-20000, 20001, (N, 16)).astype(np.int16)
+    oracle.lib().orc_iwht_batch(N, _p(b), _p(exp))
+    assert np.array_equal(dsp.TransformWHTBatch(b, gpu_ctx), exp)
+
+
+def test_sse_tdisto(oracle, gpu_ctx):
+    rng = np.random.RandomState(4)
+    a = rng.randint(0, 256, (N, 16)).astype(np.uint8); b = rng.randint(0, 256, (N, 16)).astype(np.uint8)
+    exp = np.zeros(N, np.int32)
+    oracle.lib().orc_sse4x4_batch(N, _p(a), _p(b), _p(exp))
+    assert np.array_equal(dsp.SSE4x4Batch(a, b, gpu_ctx), exp)
+    oracle.lib().orc_tdisto4x4_batch(N, _p(a), _p(b), _p(exp))
+    assert np.array_equal(dsp.TDisto4x4Batch(a, b, gpu_ctx), exp)
+
+
+def test_pred4_all_modes(oracle, gpu_ctx):
+    rng = np.random.RandomState(5)
+    c = rng.randint(0, 256, (N, 13)).astype(np.uint8)
+    c[:50] = 0; c[50:100] = 255
+    exp = np.zeros((N, 10, 16), np.uint8)
+    oracle.lib().orc_pred4_batch(N, _p(c), _p(exp))
+    assert np.array_equal(dsp.PredLuma4Batch(c, gpu_ctx), exp)
+
+
+@pytest.mark.parametrize("dc_q,ac_q,qtype,sharpen,first", [(24, 30, 0, 1, 0), (24, 30, 0, 1, 1), (48, 46, 1, 0, 0), (21, 27, 2, 0, 0),
+                                                             (4, 4, 0, 1, 0), (157, 284, 0, 1, 1)])
+def test_quantize(oracle, gpu_ctx, dc_q, ac_q, qtype, sharpen, first):
+    rng = np.random.RandomState(6)
+    a = rng.randint(-2048, 2049, (N, 16)).astype(np.int16)
+    a[: N // 2] = rng.randint(-64, 65, (N // 2, 16))
+    exp = np.zeros((N, 16), np.int16); enz = np.zeros(N, np.int32)
+    oracle.lib().orc_quantize_batch(N, _p(a), dc_q, ac_q, qtype, sharpen, first, _p(exp), _p(enz))
+    got, nz = dsp.QuantizeCoeffsBatch(a, dc_q, ac_q, qtype, sharpen, first, gpu_ctx)
+    assert np.array_equal(got, exp) and np.array_equal(nz, enz)
+
+
+@pytest.mark.parametrize("dc_q,ac_q,first,ctx_type,lam", [(24, 30, 0, 3, 787), (24, 30, 1, 0, 529), (8, 9, 0, 3, 70), (100, 120, 1, 0, 9000)])
+def test_trellis_and_token_cost(oracle, gpu_ctx, dc_q, ac_q, first, ctx_type, lam):
+    rng = np.random.RandomState(7)
+    n = 8000
+    a = rng.randint(-2048, 2049, (n, 16)).astype(np.int16)
+    a[: n // 2] = (rng.randn(n // 2, 16) * 40).astype(np.int16)
+    a[: n // 8] = (rng.randn(n // 8, 16) * 6).astype(np.int16)
+    if first:
+        a[:, 0] = 0
+    c0 = rng.randint(0, 3, n).astype(np.int32)
+    exp = np.zeros((n, 16), np.int16); enz = np.zeros(n, np.int32)
+    oracle.lib().orc_trellis_batch(n, _p(a), dc_q, ac_q, 0, 1, first, ctx_type, _p(c0), lam, _p(exp), _p(enz))
+    got, nz = dsp.TrellisQuantizeBlockBatch(a, dc_q, ac_q, 0, 1, first, ctx_type, c0, lam, gpu_ctx)
+    assert np.array_equal(got, exp) and np.array_equal(nz, enz)
+    ecost = np.zeros(n, np.int32)
+    oracle.lib().orc_token_cost_batch(n, _p(exp), _p(enz), ctx_type, _p(c0), first, _p(ecost))
+    assert np.array_equal(dsp.TokenCostForCoeffsBatch(exp, enz, ctx_type, c0, first, gpu_ctx), ecost)

@@ -1,0 +1,115 @@
+"""CPU suite: pins the oracle (oracle/, a C++ restatement of the reference) against the reference's own
+fixtures, its analytic anchors and libwebp 1.6.0 as an independent normative decoder."""
+import io
+import os
+
+import numpy as np
+import pytest
+
+import libwebp_ref as W
+
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+needs_libwebp = pytest.mark.skipif(W.lib() is None, reason="Pillow's libwebp not present")
+
+
+def _crop(w, h, y, u, v):
+    return y[:h, :w], u[:(h + 1) // 2, :(w + 1) // 2], v[:(h + 1) // 2, :(w + 1) // 2]
+
+
+def test_quality_to_qindex_anchors(oracle):
+    # internal/lossy/encode_test.go:63-80 pins Q0->127, Q100->0, Q50 in [38,39]; SURVEY 9.7 adds the rest
+    q = oracle.lib().orc_quality_to_qindex
+    assert q(0) == 127 and q(100) == 0 and q(50) in (38, 39)
+    assert [q(x) for x in (50, 65, 70, 75, 80, 90)] == [38, 30, 28, 26, 19, 9]
+
+
+def test_segment_params_q75(oracle):
+    # base q-index 26 -> LambdaI4=21, LambdaMode=7 (1 segment so no SNS modulation of q)
+    img = oracle.synth_image(64, 64, 0)
+    _, t = oracle.encode(img, oracle.default_cfg(segments=1, sns_strength=0), taps=True)
+    quant, fstrength, alpha, beta, l_i4, l_i16, l_uv, l_mode = t["seg"][0]
+    assert quant == 26 and l_i4 == 21 and l_mode == 7
+
+
+@needs_libwebp
+@pytest.mark.parametrize("name,centre", [("blue_16x16_lossy.webp", (1, 128, 255)), ("red_4x4_lossy.webp", None)])
+def test_reference_decode_fixtures(oracle, name, centre):
+    # webp_test.go:148-188 fixtures; the comment at :178 quotes dwebp's centre pixel (1,128,255)
+    data = open(os.path.join(DATA, name), "rb").read()
+    w, h, y, u, v = oracle.decode(data)
+    lw, lh, ly, lu, lv = W.decode_yuv(data)
+    assert (w, h) == (lw, lh)
+    cy, cu, cv = _crop(w, h, y, u, v)
+    assert np.array_equal(cy, ly) and np.array_equal(cu, lu) and np.array_equal(cv, lv)
+    rgba = oracle.build_nrgba(w, h, y, u, v)
+    assert np.array_equal(rgba, W.decode_rgba(data))
+    if centre:
+        assert tuple(rgba[h // 2, w // 2, :3]) == centre
+
+
+@needs_libwebp
+@pytest.mark.parametrize("w,h,kind", [(64, 64, 0), (96, 80, 1), (130, 71, 2), (33, 49, 1)])
+def test_import_matches_libwebp(oracle, w, h, kind):
+    img = oracle.synth_image(w, h, 7, kind)
+    y, u, v = oracle.import_rgba(img)
+    ly, lu, lv = W.import_rgba_yuv(img)
+    cy, cu, cv = _crop(w, h, y, u, v)
+    assert np.array_equal(cy, ly) and np.array_equal(cu, lu) and np.array_equal(cv, lv)
+
+
+@needs_libwebp
+@pytest.mark.parametrize("w,h,idx,kw", [
+    (128, 96, 0, {}), (128, 96, 1, {}), (160, 112, 2, {}), (100, 70, 1, {}),
+    (128, 96, 1, dict(segments=1)), (128, 96, 2, dict(filter_type=0)), (128, 96, 1, dict(method=3)),
+    (128, 96, 2, dict(method=6, quality=40)), (128, 96, 1, dict(filter_sharpness=5, filter_strength=80)),
+    (128, 128, 2, dict(partitions=2, quality=90)), (128, 96, 2, dict(quality=95)),
+])
+def test_oracle_stream_decodes_identically_in_libwebp(oracle, w, h, idx, kw):
+    """Every oracle-encoded stream must decode in libwebp to exactly what the oracle's decoder produces,
+    and the unfiltered reconstruction the oracle's encoder kept must equal its decoder's (filter off)."""
+    img = oracle.synth_image(w, h, idx)
+    data, t = oracle.encode(img, oracle.default_cfg(**kw), taps=True)
+    ow, oh, y, u, v = oracle.decode(data)
+    assert (ow, oh) == (w, h)
+    lw, lh, ly, lu, lv = W.decode_yuv(data)
+    cy, cu, cv = _crop(w, h, y, u, v)
+    assert np.array_equal(cy, ly) and np.array_equal(cu, lu) and np.array_equal(cv, lv)
+    assert np.array_equal(oracle.build_nrgba(w, h, y, u, v), W.decode_rgba(data))
+    _, _, ry, ru, rv = oracle.decode(data, filter=False)
+    assert np.array_equal(ry[:h, :w], t["recon_y"][:h, :w])
+    assert np.array_equal(ru[:(h + 1) // 2, :(w + 1) // 2], t["recon_u"][:(h + 1) // 2, :(w + 1) // 2])
+    assert np.array_equal(rv[:(h + 1) // 2, :(w + 1) // 2], t["recon_v"][:(h + 1) // 2, :(w + 1) // 2])
+
+
+@needs_libwebp
+def test_libwebp_encoded_stream_decodes_identically(oracle):
+    # a foreign encoder exercises decoder paths the reference encoder never emits (lf deltas, other modes)
+    from PIL import Image
+    img = oracle.synth_image(200, 120, 1)
+    buf = io.BytesIO()
+    Image.fromarray(img[..., :3]).save(buf, "WEBP", quality=60, method=4)
+    data = buf.getvalue()
+    w, h, y, u, v = oracle.decode(data, libwebp_inner_rule=True)
+    lw, lh, ly, lu, lv = W.decode_yuv(data)
+    cy, cu, cv = _crop(w, h, y, u, v)
+    assert np.array_equal(cy, ly) and np.array_equal(cu, lu) and np.array_equal(cv, lv)
+
+
+def test_encode_is_deterministic_and_psnr(oracle):
+    # race_test.go:33-73 (bytes.Equal run-vs-run) and the >= 30 dB round-trip threshold of encode_test.go
+    img = oracle.synth_image(192, 128, 1)
+    a, b = oracle.encode(img), oracle.encode(img)
+    assert a == b
+    w, h, y, u, v = oracle.decode(a)
+    sy, _, _ = oracle.import_rgba(img)
+    sse = oracle.plane_sse(np.ascontiguousarray(sy[:h, :w]), np.ascontiguousarray(y[:h, :w]))
+    assert oracle.lib().orc_psnr_from_sse(sse, w * h) >= 30.0
+
+
+def test_ssim_identity_and_psnr(oracle):
+    rng = np.random.RandomState(3)
+    a = rng.randint(0, 256, (40, 56)).astype(np.uint8)
+    assert oracle.plane_ssim(a, a) == pytest.approx(40 * 56, rel=1e-12)
+    assert oracle.lib().orc_psnr_from_sse(0, 100) == 99.0
+    b = a.copy(); b[0, 0] ^= 1
+    assert oracle.plane_sse(a, b) == 1

@@ -1,0 +1,38 @@
+"""In-tree build of libwebpgpu.so (the C-ABI shared library of include/webpgpu.h) for sm_100a.
+
+nvcc cross-compiles without a GPU; the built .so is git-ignored but travels with gpurun snapshots.
+"""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT_DIR, "libwebpgpu.so")
+SOURCES = ["webpgpu.cu"]
+HEADERS = ["vp8_dev.cuh", "enc_kernels.cuh", "dec_kernels.cuh", "misc_kernels.cuh", "host_enc.h", "host_dec.h",
+           "vp8_tables.inc", os.path.join("..", "..", "include", "webpgpu.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build_native(force=False, verbose=False):
+    """Compile webp_b200/csrc/webpgpu.cu -> webp_b200/_build/libwebpgpu.so.  Returns the path."""
+    if not force and not _stale():
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_native(force=True, verbose=True))

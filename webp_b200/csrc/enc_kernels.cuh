@@ -1,0 +1,919 @@
+// Encoder kernels (sm_100a): RGBA import, analysis, and the wavefront mode-search kernel.
+//
+// Mode search restates the reference's per-macroblock pipeline on its parallel path
+// (internal/lossy/encode_parallel.go:293-335): import -> prediction context -> pickBestMode
+// (I16 RD / I4 RD with SSE pre-screen and trellis / UV RD) -> residuals -> reconstruct -> export.
+// Scheduling is B200-first: macroblock (x, y) of every image in the batch runs in wave
+// t = x + 2y (left / top / top-right dependency), one launch per wave, G lanes of a
+// warp per macroblock, block rows staged in shared memory in the reference's BPS=32 work-buffer
+// layout (internal/lossy/constants.go:66-75).
+#pragma once
+#include "vp8_dev.cuh"
+
+namespace wg {
+
+enum { BPS = 32, YUV_SIZE = BPS * 17 + BPS * 9, Y_OFF = BPS + 8, U_OFF = Y_OFF + BPS * 16 + BPS, V_OFF = U_OFF + 16 };
+
+struct ImageParams {  // per image, written by the host after segmentation
+  SegParams seg[4];
+};
+
+struct EncKernelParams {
+  const uint8_t* src_y; const uint8_t* src_u; const uint8_t* src_v;  // padded source planes [n][..]
+  uint8_t* rec_y; uint8_t* rec_u; uint8_t* rec_v;                    // padded reconstruction planes
+  const uint8_t* segment;       // [n][nmb]
+  const ImageParams* img;       // [n]
+  uint32_t* ctx;                // [n][nmb] packed NZ context (see pack_ctx)
+  uint8_t* out_hdr;             // [n][nmb][48]: mb_type,i16,uv,segment,skip,nz_dc,0,0, modes[16], nz[24]
+  int16_t* out_coeffs;          // [n][nmb][400]
+  const uint16_t* i4_costs;     // [10][10][10]
+  const uint16_t* ecost; const uint16_t* lfc; const uint16_t* lcodes; const uint8_t* proba;  // global tables
+  int n_images, width, height, mb_w, mb_h;
+  int method, max_i4_modes;
+  size_t y_plane, uv_plane;     // bytes per image plane
+};
+
+// ctx word: bits 0-7 out_t (4 Y, 2 U, 2 V), 8-15 out_l, 16 top-DC carry, 17 left-DC carry
+__device__ __forceinline__ uint32_t pack_ctx(uint32_t out_t, uint32_t out_l, int top_dc, int left_dc) {
+  return (out_t & 0xff) | ((out_l & 0xff) << 8) | ((uint32_t)top_dc << 16) | ((uint32_t)left_dc << 17);
+}
+
+struct I4Cand {
+  unsigned long long score;
+  int disto, rate, nz, mode;
+  int16_t lev[16];
+  uint8_t rec[16];
+};
+struct MBShared {
+  uint8_t in[YUV_SIZE];
+  uint8_t out[YUV_SIZE];
+  uint8_t out2[YUV_SIZE];
+  int16_t lev[24][16];
+  int dc[16];
+  int dcrec[16];
+  int nz[24];
+  int sse[10];
+  I4Cand cand[3];
+  int misc[8];
+};
+
+template <int G>
+__device__ __forceinline__ int grp_sum(int v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ int grp_and(int v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v &= __shfl_xor_sync(0xffffffffu, v, o, G);
+  return v;
+}
+
+__device__ __forceinline__ void load4x4(const uint8_t* p, int* d) {  // p 4-byte aligned, stride BPS
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(p + j * BPS);
+    d[4 * j + 0] = w & 0xff;
+    d[4 * j + 1] = (w >> 8) & 0xff;
+    d[4 * j + 2] = (w >> 16) & 0xff;
+    d[4 * j + 3] = w >> 24;
+  }
+}
+__device__ __forceinline__ void store4x4(uint8_t* p, const int* d) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint32_t*>(p + j * BPS) =
+        (uint32_t)d[4 * j] | ((uint32_t)d[4 * j + 1] << 8) | ((uint32_t)d[4 * j + 2] << 16) | ((uint32_t)d[4 * j + 3] << 24);
+}
+__device__ __forceinline__ void load_pred4_ctx(const uint8_t* p, int* e) {  // p = block origin in a BPS buffer
+  e[0] = p[-BPS - 1];
+  const uint32_t a = *reinterpret_cast<const uint32_t*>(p - BPS), b = *reinterpret_cast<const uint32_t*>(p - BPS + 4);
+  e[1] = a & 0xff; e[2] = (a >> 8) & 0xff; e[3] = (a >> 16) & 0xff; e[4] = a >> 24;
+  e[5] = b & 0xff; e[6] = (b >> 8) & 0xff; e[7] = (b >> 16) & 0xff; e[8] = b >> 24;
+  e[9] = p[-1]; e[10] = p[-1 + BPS]; e[11] = p[-1 + 2 * BPS]; e[12] = p[-1 + 3 * BPS];
+}
+
+// checkMode (internal/lossy/decode_frame.go:6)
+__device__ __forceinline__ int check_mode(int mx, int my, int mode) {
+  if (mode == 0) {
+    if (mx == 0) return my == 0 ? 6 : 5;
+    if (my == 0) return 4;
+  }
+  return mode;
+}
+// Cooperative square predictor into buf at off (predict_lossy.go:27-181); modes 0..6.
+template <int G>
+__device__ __forceinline__ void pred_square_coop(int gl, int mode, uint8_t* buf, int off, int size) {
+  uint8_t* d = buf + off;
+  const int words_per_row = size >> 2;
+  const int nwords = size * words_per_row;
+  int dcv = 128;
+  if (mode == 0 || mode == 4 || mode == 5) {
+    int s = 0;
+    if (mode != 4) for (int i = 0; i < size; ++i) s += d[i - BPS];
+    if (mode != 5) for (int i = 0; i < size; ++i) s += d[-1 + i * BPS];
+    const int shift = (size == 16) ? 4 : 3;
+    dcv = (mode == 0) ? (s + size) >> (shift + 1) : (s + (size >> 1)) >> shift;
+  }
+  const int tl = d[-1 - BPS];
+  for (int w = gl; w < nwords; w += G) {
+    const int j = w / words_per_row, i0 = (w % words_per_row) * 4;
+    uint32_t v;
+    if (mode == 1) {
+      const int base = d[-1 + j * BPS] - tl;
+      v = (uint32_t)clip8(base + d[i0 - BPS]) | ((uint32_t)clip8(base + d[i0 + 1 - BPS]) << 8) |
+          ((uint32_t)clip8(base + d[i0 + 2 - BPS]) << 16) | ((uint32_t)clip8(base + d[i0 + 3 - BPS]) << 24);
+    } else if (mode == 2) {
+      v = *reinterpret_cast<const uint32_t*>(d + i0 - BPS);
+    } else if (mode == 3) {
+      v = (uint32_t)d[-1 + j * BPS] * 0x01010101u;
+    } else {
+      v = (uint32_t)dcv * 0x01010101u;
+    }
+    *reinterpret_cast<uint32_t*>(d + i0 + j * BPS) = v;
+  }
+}
+
+__device__ __forceinline__ bool needs_top4(int m) { return m == 1 || m == 2 || m == 4 || m == 5 || m == 6 || m == 7 || m == 8; }
+__device__ __forceinline__ bool needs_left4(int m) { return m == 1 || m == 3 || m == 4 || m == 8 || m == 9; }
+
+// modeFixedCost16 / modeFixedCostUV (internal/lossy/encode_analysis.go:1481,1485)
+__device__ __forceinline__ int kModeFixedCost16(int m) { return m == 0 ? 663 : (m == 2 ? 872 : 919); }
+__device__ __forceinline__ int kModeFixedCostUV(int m) { return m == 0 ? 302 : (m == 1 ? 984 : (m == 2 ? 439 : 642)); }
+
+__device__ __forceinline__ unsigned long long rd_score(int disto, int rate, int lambda) {
+  return (unsigned long long)(long long)rate * (unsigned long long)(long long)lambda + 256ull * (unsigned long long)(long long)disto;
+}
+
+// One wave of the mode search.  Grid: ceil(tasks / (WARPS * 32/G)) CTAs of WARPS warps.
+template <int G, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) encode_wave_kernel(const EncKernelParams P, int wave) {
+  constexpr int MPW = 32 / G;  // macroblocks per warp
+  __shared__ uint16_t s_ecost[256];
+  __shared__ uint16_t s_lfc[2048];
+  __shared__ uint16_t s_lcodes[136];
+  __shared__ uint8_t s_proba[1056];
+  __shared__ uint16_t s_i4cost[1000];
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  MBShared* s_mb = reinterpret_cast<MBShared*>(s_dyn);  // [WARPS * MPW]
+  for (int i = threadIdx.x; i < 256; i += WARPS * 32) s_ecost[i] = P.ecost[i];
+  for (int i = threadIdx.x; i < 2048; i += WARPS * 32) s_lfc[i] = P.lfc[i];
+  for (int i = threadIdx.x; i < 134; i += WARPS * 32) s_lcodes[i] = P.lcodes[i];
+  for (int i = threadIdx.x; i < 1056; i += WARPS * 32) s_proba[i] = P.proba[i];
+  for (int i = threadIdx.x; i < 1000; i += WARPS * 32) s_i4cost[i] = P.i4_costs[i];
+  __syncthreads();
+  CostTabs T;
+  T.ecost = s_ecost; T.lfc = s_lfc; T.lcodes = s_lcodes; T.proba = s_proba;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / G, gl = lane % G;
+  // rows on this wave: x = wave - 2y in [0, mb_w)
+  const int y_lo = max(0, (wave - (P.mb_w - 1) + 1) >> 1), y_hi = min(P.mb_h - 1, wave >> 1);
+  const int rows = y_hi - y_lo + 1;
+  const long long total = (long long)rows * P.n_images;
+  const long long task = ((long long)blockIdx.x * WARPS + warp) * MPW + g;
+  const bool active = task < total;
+  const int img = active ? (int)(task / rows) : 0;
+  const int my = active ? y_lo + (int)(task % rows) : 0;
+  const int mx = active ? wave - 2 * my : 0;
+  const int nmb = P.mb_w * P.mb_h;
+  const int mb_idx = my * P.mb_w + mx;
+  MBShared& S = s_mb[warp * MPW + g];
+
+  const int y_stride = P.mb_w * 16, uv_stride = P.mb_w * 8;
+  const uint8_t* src_y = P.src_y + (size_t)img * P.y_plane;
+  const uint8_t* src_u = P.src_u + (size_t)img * P.uv_plane;
+  const uint8_t* src_v = P.src_v + (size_t)img * P.uv_plane;
+  uint8_t* rec_y = P.rec_y + (size_t)img * P.y_plane;
+  uint8_t* rec_u = P.rec_u + (size_t)img * P.uv_plane;
+  uint8_t* rec_v = P.rec_v + (size_t)img * P.uv_plane;
+  uint32_t* ctxw = P.ctx + (size_t)img * nmb;
+  uint8_t* hdr = P.out_hdr + ((size_t)img * nmb + mb_idx) * 48;
+  int16_t* oc = P.out_coeffs + ((size_t)img * nmb + mb_idx) * 400;
+  const int segment = active ? P.segment[(size_t)img * nmb + mb_idx] : 0;
+  const SegParams& seg = P.img[img].seg[segment];
+  const bool trellis = P.method >= 4;
+
+  // ---- 1. import source MB with edge replication (encode_iterator.go:145) + 2. prediction context
+  if (active) {
+    const int x0 = mx * 16, y0 = my * 16;
+    const int ww = min(16, P.width - x0), hh = min(16, P.height - y0);
+    for (int i = gl; i < 256; i += G) {
+      const int r = i >> 4, c = i & 15;
+      S.in[Y_OFF + r * BPS + c] = src_y[(size_t)(y0 + min(r, hh - 1)) * y_stride + x0 + min(c, ww - 1)];
+    }
+    const int uvw = (ww + 1) >> 1, uvh = (hh + 1) >> 1;
+    for (int i = gl; i < 128; i += G) {
+      const int pl = i >> 6, r = (i >> 3) & 7, c = i & 7;
+      const uint8_t* sp = pl ? src_v : src_u;
+      S.in[(pl ? V_OFF : U_OFF) + r * BPS + c] = sp[(size_t)(my * 8 + min(r, uvh - 1)) * uv_stride + mx * 8 + min(c, uvw - 1)];
+    }
+    // context from the reconstruction planes (full padded MBs are stored, so partial MBs are exact)
+    uint8_t* o = S.out;
+    for (int i = gl; i < 20; i += G) {  // top row 16 + top-right 4 (encode_parallel.go:461-487)
+      int v = 127;
+      if (my > 0) {
+        const int xx = (i < 16 || mx < P.mb_w - 1) ? x0 + i : x0 + 15;
+        v = rec_y[(size_t)(y0 - 1) * y_stride + xx];
+      }
+      o[Y_OFF - BPS + i] = (uint8_t)v;
+    }
+    for (int j = gl; j < 16; j += G) o[Y_OFF - 1 + j * BPS] = mx > 0 ? rec_y[(size_t)(y0 + j) * y_stride + x0 - 1] : 129;
+    for (int i = gl; i < 16; i += G) {
+      const int pl = i >> 3, c = i & 7;
+      const uint8_t* rp = pl ? rec_v : rec_u;
+      const int off = pl ? V_OFF : U_OFF;
+      o[off - BPS + c] = my > 0 ? rp[(size_t)(my * 8 - 1) * uv_stride + mx * 8 + c] : 127;
+      o[off - 1 + c * BPS] = mx > 0 ? rp[(size_t)(my * 8 + c) * uv_stride + mx * 8 - 1] : 129;
+    }
+    if (gl == 0) {
+      const bool both = mx > 0 && my > 0;
+      o[Y_OFF - BPS - 1] = both ? rec_y[(size_t)(y0 - 1) * y_stride + x0 - 1] : (my > 0 ? 129 : 127);
+      o[U_OFF - BPS - 1] = both ? rec_u[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1] : (my > 0 ? 129 : 127);
+      o[V_OFF - BPS - 1] = both ? rec_v[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1] : (my > 0 ? 129 : 127);
+    }
+  }
+  __syncwarp();
+  if (active) {  // replicate top-right under rows 3, 7, 11 (encode_parallel.go:489-495)
+    for (int i = gl; i < 12; i += G) {
+      const int r = 1 + i / 4, c = i & 3;
+      S.out[Y_OFF - BPS + 16 + r * 4 * BPS + c] = S.out[Y_OFF - BPS + 16 + c];
+    }
+  }
+  // neighbour contexts
+  uint32_t top_nz = 0, left_nz = 0;
+  int top_nz_dc = 0, left_nz_dc = 0;
+  int top_modes[4] = {0, 0, 0, 0}, left_modes[4] = {0, 0, 0, 0};
+  if (active) {
+    if (my > 0) {
+      const uint32_t cw = ctxw[mb_idx - P.mb_w];
+      top_nz = cw & 0xff;
+      top_nz_dc = (cw >> 16) & 1;
+      const uint8_t* th = hdr - (size_t)P.mb_w * 48;
+      if (th[0] == 1) { top_modes[0] = th[8 + 12]; top_modes[1] = th[8 + 13]; top_modes[2] = th[8 + 14]; top_modes[3] = th[8 + 15]; }
+    }
+    if (mx > 0) {
+      const uint32_t cw = ctxw[mb_idx - 1];
+      left_nz = (cw >> 8) & 0xff;
+      left_nz_dc = (cw >> 17) & 1;
+      const uint8_t* lh = hdr - 48;
+      if (lh[0] == 1) { left_modes[0] = lh[8 + 3]; left_modes[1] = lh[8 + 7]; left_modes[2] = lh[8 + 11]; left_modes[3] = lh[8 + 15]; }
+    }
+  }
+  __syncwarp();
+
+  // ---- 3a. I16 RD search (encode_parallel.go:624-735)
+  int best16 = 0, rate16 = 0, disto16 = 0;
+  {
+    unsigned long long best_score = ~0ull;
+    int src_flat = 0;
+    if (active) {  // isFlatSource16 (encode_analysis.go:358)
+      const int v0 = S.in[Y_OFF];
+      int ok = 1;
+      for (int i = gl; i < 256; i += G) ok &= (S.in[Y_OFF + (i >> 4) * BPS + (i & 15)] == v0);
+      src_flat = ok;
+    }
+    src_flat = grp_and<G>(src_flat);
+    if (active) for (int i = gl; i < U_OFF / 4; i += G) reinterpret_cast<uint32_t*>(S.out2)[i] = reinterpret_cast<const uint32_t*>(S.out)[i];
+    __syncwarp();
+    const int dc_ctx = min(top_nz_dc + left_nz_dc, 2);
+    for (int mode = 0; mode < 4; ++mode) {
+      const bool allowed = active && !((mode == 2 && my == 0) || (mode == 3 && mx == 0) || (mode == 1 && (mx == 0 || my == 0)));
+      if (allowed) pred_square_coop<G>(gl, check_mode(mx, my, mode), S.out2, Y_OFF, 16);
+      __syncwarp();
+      if (allowed) {
+        for (int b = gl; b < 16; b += G) {
+          const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+          int s[16], p[16], c[16], q[16];
+          load4x4(S.in + off, s);
+          load4x4(S.out2 + off, p);
+          ftransform(s, p, c);
+          S.dc[b] = c[0];
+          c[0] = 0;
+          S.nz[b] = quantize_block(c, q, seg.y1, 1);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) S.lev[b][i] = (int16_t)q[i];
+        }
+      }
+      __syncwarp();
+      int rate = 0;
+      if (allowed) {
+        if (gl == 0) {  // WHT of the 16 DCs, quantise, cost, reconstruct DCs
+          int d[16], w[16], q[16], dq[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) d[i] = S.dc[i];
+          fwht(d, w);
+          const int nz_dc = quantize_block(w, q, seg.y2, 0);
+          rate += kModeFixedCost16(mode) + token_cost(q, nz_dc, 1, dc_ctx, 0, T);
+          dequant_block(q, dq, seg.y2);
+          iwht(dq, d);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) S.dcrec[i] = d[i];
+        }
+        for (int b = gl; b < 16; b += G) {
+          const int bx = b & 3, by = b >> 2;
+          const int l = bx > 0 ? (S.nz[b - 1] > 0) : ((left_nz >> by) & 1);
+          const int t = by > 0 ? (S.nz[b - 4] > 0) : ((top_nz >> bx) & 1);
+          int q[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) q[i] = S.lev[b][i];
+          rate += token_cost(q, S.nz[b], 0, l + t, 1, T);
+        }
+      }
+      __syncwarp();
+      int disto = 0, td = 0, any_ac = 0;
+      if (allowed) {
+        for (int b = gl; b < 16; b += G) {
+          const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+          int q[16], dq[16], p[16], r[16], s[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) q[i] = S.lev[b][i];
+          dequant_block(q, dq, seg.y1);
+          dq[0] = S.dcrec[b];
+          load4x4(S.out2 + off, p);
+          itransform(p, dq, r);
+          load4x4(S.in + off, s);
+          disto += sse16(s, r);
+          if (seg.tlambda_sd > 0) td += tdisto4x4(s, r);
+          any_ac |= (S.nz[b] > 0);
+        }
+      }
+      rate = grp_sum<G>(rate);
+      disto = grp_sum<G>(disto);
+      td = grp_sum<G>(td);
+      any_ac = grp_sum<G>(any_ac);
+      if (allowed) {
+        if (seg.tlambda_sd > 0) disto += (seg.tlambda_sd * td + 128) >> 8;
+        if (src_flat && any_ac == 0) disto *= 2;
+        const unsigned long long score = rd_score(disto, rate, seg.lambda_i16);
+        if (score < best_score) { best_score = score; best16 = mode; rate16 = rate; disto16 = disto; }
+      }
+      __syncwarp();
+    }
+  }
+  const unsigned long long score16 = rd_score(disto16, rate16, seg.lambda_mode);
+
+  // ---- 3b. I4 RD search (encode_parallel.go:738-1027)
+  unsigned long long score4 = ~0ull;
+  uint32_t i4_nzmask = 0;
+  {
+    if (active) for (int i = gl; i < YUV_SIZE / 4; i += G) reinterpret_cast<uint32_t*>(S.out2)[i] = reinterpret_cast<const uint32_t*>(S.out)[i];
+    __syncwarp();
+    int total_rate = 0, total_disto = 0, total_hdr = 0;
+    bool alive = active;
+    uint32_t nzmask = 0;   // bit b: block b has nz > 0
+    uint32_t modes_lo = 0, modes_hi = 0;  // 16 x 4-bit modes
+    for (int b = 0; b < 16; ++b) {
+      const int bx = b & 3, by = b >> 2;
+      const int off = Y_OFF + by * 4 * BPS + bx * 4;
+      auto get_mode = [&](int k) -> int { return (k < 8) ? (modes_lo >> (4 * k)) & 15 : (modes_hi >> (4 * (k - 8))) & 15; };
+      const int top_mode = by == 0 ? top_modes[bx] : get_mode(b - 4);
+      const int left_mode = bx == 0 ? left_modes[by] : get_mode(b - 1);
+      const bool has_top = my > 0 || by > 0, has_left = mx > 0 || bx > 0;
+      const int l = bx > 0 ? ((nzmask >> (b - 1)) & 1) : ((left_nz >> by) & 1);
+      const int t = by > 0 ? ((nzmask >> (b - 4)) & 1) : ((top_nz >> bx) & 1);
+      const int nz_ctx = l + t;
+      int e[13], s[16];
+      if (alive) {
+        load_pred4_ctx(S.out2 + off, e);
+        load4x4(S.in + off, s);
+        // pre-screen: prediction SSE of every eligible mode (encode_parallel.go:955-966)
+        for (int m = gl; m < 10; m += G) {
+          int v = 0x7fffffff;
+          if (!((!has_top && needs_top4(m)) || (!has_left && needs_left4(m)))) {
+            int p[16];
+            pred4(m, e, p);
+            v = sse16(s, p);
+          }
+          S.sse[m] = v;
+        }
+      }
+      __syncwarp();
+      int K = 0;
+      int cand_mode[3] = {0, 0, 0};
+      if (alive) {  // exact selection-sort emulation (encode_parallel.go:969-983); every lane redundantly
+        int cm[10], cs[10], n_c = 0;
+#pragma unroll
+        for (int m = 0; m < 10; ++m) {
+          const int v = S.sse[m];
+          if (v != 0x7fffffff) { cm[n_c] = m; cs[n_c] = v; n_c++; }
+        }
+        K = min(P.max_i4_modes, n_c);
+        for (int i = 0; i < K; ++i) {
+          int mi = i;
+          for (int j = i + 1; j < n_c; ++j) if (cs[j] < cs[mi]) mi = j;
+          if (mi != i) { const int tm = cm[i], ts = cs[i]; cm[i] = cm[mi]; cs[i] = cs[mi]; cm[mi] = tm; cs[mi] = ts; }
+          cand_mode[i] = cm[i];
+        }
+      }
+      // full RD on the K candidates, one lane each
+      if (alive) {
+        for (int k = gl; k < K; k += G) {
+          const int mode = cand_mode[k];
+          int p[16], c[16], q[16], dq[16], r[16];
+          pred4(mode, e, p);
+          ftransform(s, p, c);
+          const int nz = trellis ? trellis_block(c, q, seg.y1, 0, 3, nz_ctx, seg.tlambda_i4, T)
+                                 : quantize_block(c, q, seg.y1, 0);
+          dequant_block(q, dq, seg.y1);
+          itransform(p, dq, r);
+          int disto = sse16(s, r);
+          if (seg.tlambda_sd > 0) disto += (seg.tlambda_sd * tdisto4x4(s, r) + 128) >> 8;
+          int rate = 0;
+          if (mode > 0) {  // isFlat(levels, 1, 3)  (encode_analysis.go:374)
+            int cnt = 0;
+#pragma unroll
+            for (int i = 1; i < 16; ++i) cnt += (q[i] != 0);
+            if (cnt <= 3) rate = 140;
+          }
+          rate += token_cost(q, nz, 3, nz_ctx, 0, T);
+          rate += s_i4cost[(top_mode * 10 + left_mode) * 10 + mode];
+          I4Cand& C = S.cand[k];
+          C.score = rd_score(disto, rate, seg.lambda_i4);
+          C.disto = disto; C.rate = rate; C.nz = nz; C.mode = mode;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { C.lev[i] = (int16_t)q[i]; C.rec[i] = (uint8_t)r[i]; }
+        }
+      }
+      __syncwarp();
+      if (alive) {
+        unsigned long long bs = ~0ull;
+        int bk = 0;
+        for (int k = 0; k < K; ++k) {
+          const I4Cand& C = S.cand[k];
+          if (256ull * (unsigned long long)C.disto >= bs) continue;
+          if (C.score < bs) { bs = C.score; bk = k; }
+        }
+        const I4Cand& C = S.cand[bk];
+        const int bm = C.mode;
+        if (b < 8) modes_lo |= (uint32_t)bm << (4 * b); else modes_hi |= (uint32_t)bm << (4 * (b - 8));
+        total_rate += C.rate;
+        total_disto += C.disto;
+        total_hdr += s_i4cost[(top_mode * 10 + left_mode) * 10 + bm];
+        for (int i = gl; i < 16; i += G) oc[b * 16 + i] = C.lev[i];
+        if (gl == 0) hdr[24 + b] = (uint8_t)C.nz;
+        if (C.nz > 0) nzmask |= 1u << b;
+        if (rd_score(total_disto, total_rate + 211, seg.lambda_mode) >= score16 || total_hdr > 15000) {
+          alive = false;
+        } else {
+          for (int i = gl; i < 16; i += G) S.out2[off + (i >> 2) * BPS + (i & 3)] = C.rec[i];
+        }
+      }
+      __syncwarp();
+    }
+    if (alive) score4 = rd_score(total_disto, total_rate + 211, seg.lambda_mode);
+    i4_nzmask = nzmask;
+    // ---- decision (encode_parallel.go:572-592)
+    const bool use_i4 = active && score4 < score16;
+    if (active) {
+      if (use_i4) {
+        for (int i = gl; i < 64; i += G)
+          *reinterpret_cast<uint32_t*>(S.out + Y_OFF + (i >> 2) * BPS + (i & 3) * 4) =
+              *reinterpret_cast<const uint32_t*>(S.out2 + Y_OFF + (i >> 2) * BPS + (i & 3) * 4);
+        for (int i = gl; i < 16; i += G) hdr[8 + i] = (uint8_t)((i < 8) ? (modes_lo >> (4 * i)) & 15 : (modes_hi >> (4 * (i - 8))) & 15);
+      } else {
+        pred_square_coop<G>(gl, check_mode(mx, my, best16), S.out, Y_OFF, 16);
+        for (int i = gl; i < 16; i += G) hdr[8 + i] = 0;
+      }
+    }
+    __syncwarp();
+    S.misc[0] = use_i4;  // uniform within the group
+  }
+  __syncwarp();
+  const bool use_i4 = S.misc[0] != 0;
+
+  // ---- 3c. UV RD search (encode_parallel.go:1030-1116)
+  int best_uv = 0;
+  {
+    unsigned long long best_score = ~0ull;
+    if (active)
+      for (int i = gl; i < (YUV_SIZE - U_OFF) / 4; i += G)
+        reinterpret_cast<uint32_t*>(S.out2 + U_OFF)[i] = reinterpret_cast<const uint32_t*>(S.out + U_OFF)[i];
+    __syncwarp();
+    for (int mode = 0; mode < 4; ++mode) {
+      const bool allowed = active && !((mode == 2 && my == 0) || (mode == 3 && mx == 0) || (mode == 1 && (mx == 0 || my == 0)));
+      if (allowed) {
+        const int am = check_mode(mx, my, mode);
+        pred_square_coop<G>(gl, am, S.out2, U_OFF, 8);
+        pred_square_coop<G>(gl, am, S.out2, V_OFF, 8);
+      }
+      __syncwarp();
+      int disto = 0, ac_cnt = 0;
+      if (allowed) {
+        for (int b = gl; b < 8; b += G) {
+          const int off = ((b & 4) ? V_OFF : U_OFF) + ((b >> 1) & 1) * 4 * BPS + (b & 1) * 4;
+          int s[16], p[16], c[16], q[16], dq[16], r[16];
+          load4x4(S.in + off, s);
+          load4x4(S.out2 + off, p);
+          ftransform(s, p, c);
+          S.nz[16 + b] = quantize_block(c, q, seg.uv, 0);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) S.lev[16 + b][i] = (int16_t)q[i];
+#pragma unroll
+          for (int i = 1; i < 16; ++i) ac_cnt += (q[i] != 0);
+          dequant_block(q, dq, seg.uv);
+          itransform(p, dq, r);
+          disto += sse16(s, r);
+        }
+      }
+      __syncwarp();
+      int rate = 0;
+      if (allowed) {
+        for (int b = gl; b < 8; b += G) {
+          const int ch = b >> 2, bx = b & 1, by = (b >> 1) & 1;
+          const uint32_t tn = (top_nz >> (4 + 2 * ch)) & 3, ln = (left_nz >> (4 + 2 * ch)) & 3;
+          const int l = bx > 0 ? (S.nz[16 + b - 1] > 0) : ((ln >> by) & 1);
+          const int t = by > 0 ? (S.nz[16 + b - 2] > 0) : ((tn >> bx) & 1);
+          int q[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) q[i] = S.lev[16 + b][i];
+          rate += token_cost(q, S.nz[16 + b], 2, l + t, 0, T);
+        }
+      }
+      rate = grp_sum<G>(rate);
+      disto = grp_sum<G>(disto);
+      ac_cnt = grp_sum<G>(ac_cnt);
+      if (allowed) {
+        rate += kModeFixedCostUV(mode);
+        if (mode > 0 && ac_cnt <= 2) rate += 140 * 8;
+        const unsigned long long score = rd_score(disto, rate, seg.lambda_uv);
+        if (score < best_score) { best_score = score; best_uv = mode; }
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- 4. final residuals + 6. reconstruction (encode_parallel.go:1164-1407)
+  uint32_t nzy_flags = 0;  // 16 bits: Y block has nz>0 (i16: AC), bit 24: DC block
+  int nz_dc = 0;
+  if (active && !use_i4) {
+    // I16: forward transform all blocks against the cached prediction in S.out
+    for (int b = gl; b < 16; b += G) {
+      const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+      int s[16], p[16], c[16];
+      load4x4(S.in + off, s);
+      load4x4(S.out + off, p);
+      ftransform(s, p, c);
+      S.dc[b] = c[0];
+      c[0] = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) S.lev[b][i] = (int16_t)c[i];  // raw coefficients for now
+    }
+  }
+  __syncwarp();
+  if (!trellis) {
+    if (active && !use_i4)
+      for (int b = gl; b < 16; b += G) {
+        int c[16], q[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = S.lev[b][i];
+        S.nz[b] = quantize_block(c, q, seg.y1, 1);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) S.lev[b][i] = (int16_t)q[i];
+      }
+    __syncwarp();
+  } else {
+    // trellis with the NZ-context chain: anti-diagonal wavefront over the 16 blocks (7 steps)
+    for (int d = 0; d < 7; ++d) {
+      if (active && !use_i4) {
+        const int by_lo = max(0, d - 3), by_hi = min(3, d);
+        for (int k = gl; k <= by_hi - by_lo; k += G) {
+          const int by = by_lo + k, bx = d - by, b = by * 4 + bx;
+          const int l = bx > 0 ? (S.nz[b - 1] > 0) : ((left_nz >> by) & 1);
+          const int t = by > 0 ? (S.nz[b - 4] > 0) : ((top_nz >> bx) & 1);
+          int c[16], q[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) c[i] = S.lev[b][i];
+          S.nz[b] = trellis_block(c, q, seg.y1, 1, 0, l + t, seg.tlambda_i16, T);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) S.lev[b][i] = (int16_t)q[i];
+        }
+      }
+      __syncwarp();
+    }
+  }
+  if (active && !use_i4) {
+    if (gl == 0) {
+      int d[16], w[16], q[16], dq[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) d[i] = S.dc[i];
+      fwht(d, w);
+      const int n = quantize_block(w, q, seg.y2, 0);
+      S.misc[1] = n;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) oc[384 + i] = (int16_t)q[i];
+      dequant_block(q, dq, seg.y2);
+      iwht(dq, d);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) S.dcrec[i] = d[i];
+    }
+  }
+  __syncwarp();
+  if (active && !use_i4) {
+    nz_dc = S.misc[1];
+    for (int b = gl; b < 16; b += G) {
+      const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+      int q[16], dq[16], p[16], r[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { q[i] = S.lev[b][i]; oc[b * 16 + i] = (int16_t)q[i]; }
+      hdr[24 + b] = (uint8_t)S.nz[b];
+      dequant_block(q, dq, seg.y1);
+      dq[0] = S.dcrec[b];
+      load4x4(S.out + off, p);
+      itransform(p, dq, r);
+      store4x4(S.out + off, r);
+    }
+    for (int b = 0; b < 16; ++b) nzy_flags |= (uint32_t)(S.nz[b] > 0) << b;
+  }
+  if (active && use_i4) {
+    nzy_flags = i4_nzmask;
+    for (int i = gl; i < 16; i += G) oc[384 + i] = 0;  // no WHT block on I4 macroblocks
+  }
+  // UV: predict with the winner, transform, quantise, reconstruct
+  if (active) {
+    const int am = check_mode(mx, my, best_uv);
+    pred_square_coop<G>(gl, am, S.out, U_OFF, 8);
+    pred_square_coop<G>(gl, am, S.out, V_OFF, 8);
+  }
+  __syncwarp();
+  if (active) {
+    for (int b = gl; b < 8; b += G) {
+      const int off = ((b & 4) ? V_OFF : U_OFF) + ((b >> 1) & 1) * 4 * BPS + (b & 1) * 4;
+      int s[16], p[16], c[16], q[16], dq[16], r[16];
+      load4x4(S.in + off, s);
+      load4x4(S.out + off, p);
+      ftransform(s, p, c);
+      const int nz = quantize_block(c, q, seg.uv, 0);
+      S.nz[16 + b] = nz;
+      hdr[40 + b] = (uint8_t)nz;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) oc[(16 + b) * 16 + i] = (int16_t)q[i];
+      dequant_block(q, dq, seg.uv);
+      itransform(p, dq, r);
+      store4x4(S.out + off, r);
+    }
+  }
+  __syncwarp();
+
+  // ---- 7. export: reconstruction planes, header, NZ context (encode_parallel.go:341-428,1410-1496)
+  if (active) {
+    const int x0 = mx * 16, y0 = my * 16;
+    for (int i = gl; i < 64; i += G) {
+      const int r = i >> 2, c4 = (i & 3) * 4;
+      *reinterpret_cast<uint32_t*>(rec_y + (size_t)(y0 + r) * y_stride + x0 + c4) =
+          *reinterpret_cast<const uint32_t*>(S.out + Y_OFF + r * BPS + c4);
+    }
+    for (int i = gl; i < 32; i += G) {
+      const int pl = i >> 4, r = (i >> 1) & 7, c4 = (i & 1) * 4;
+      uint8_t* rp = pl ? rec_v : rec_u;
+      *reinterpret_cast<uint32_t*>(rp + (size_t)(my * 8 + r) * uv_stride + mx * 8 + c4) =
+          *reinterpret_cast<const uint32_t*>(S.out + (pl ? V_OFF : U_OFF) + r * BPS + c4);
+    }
+    if (gl == 0) {
+      uint32_t nzuv = 0;
+      for (int b = 0; b < 8; ++b) nzuv |= (uint32_t)(S.nz[16 + b] > 0) << b;
+      const bool i16 = !use_i4;
+      const int dcflag = nz_dc > 0;
+      const bool skip = (nzy_flags == 0) && (!i16 || !dcflag) && nzuv == 0;
+      hdr[0] = use_i4 ? 1 : 0;
+      hdr[1] = (uint8_t)(i16 ? best16 : 0);
+      hdr[2] = (uint8_t)best_uv;
+      hdr[3] = (uint8_t)segment;
+      hdr[4] = skip ? 1 : 0;
+      hdr[5] = (uint8_t)(i16 ? nz_dc : 0);
+      hdr[6] = 0; hdr[7] = 0;
+      // NZ context words (bottom row / right column flags)
+      const uint32_t out_t = ((nzy_flags >> 12) & 0xf) | (((nzuv >> 2) & 3) << 4) | (((nzuv >> 6) & 3) << 6);
+      const uint32_t yl = ((nzy_flags >> 3) & 1) | (((nzy_flags >> 7) & 1) << 1) | (((nzy_flags >> 11) & 1) << 2) | (((nzy_flags >> 15) & 1) << 3);
+      const uint32_t ul = ((nzuv >> 1) & 1) | (((nzuv >> 3) & 1) << 1);
+      const uint32_t vl = ((nzuv >> 5) & 1) | (((nzuv >> 7) & 1) << 1);
+      const uint32_t out_l = yl | (ul << 4) | (vl << 6);
+      const int tdc = i16 ? dcflag : top_nz_dc, ldc = i16 ? dcflag : left_nz_dc;
+      ctxw[mb_idx] = pack_ctx(out_t, out_l, tdc, ldc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// RGBA import (internal/lossy/encode.go:671-942 for *image.RGBA / *image.NRGBA sources):
+//   Y = RGBToY per pixel (internal/dsp/yuv.go:151); U,V from the gamma-domain 2x2 average
+//   (AccumulateRGBA yuv.go:486, LinearToGamma :237, ConvertRGBA32ToUV :553), alpha-weighted when any
+//   alpha in the 2x2 block is < 255; edges replicated out to the 16-pixel macroblock grid.
+// One thread = 4x2 source pixels: 2 x 128-bit loads, 2 x 32-bit Y stores, 16-bit U and V stores.
+struct ImportParams {
+  const uint8_t* rgba; size_t image_stride; int stride;  // device RGBA, `stride` bytes per row (multiple of 16)
+  int n, width, height, pad_w, pad_h, has_alpha;
+  uint8_t* y; uint8_t* u; uint8_t* v; size_t y_plane, uv_plane;
+  const uint16_t* gamma_to_linear;  // [256]  (yuv.go:193)
+  const uint16_t* linear_to_gamma;  // [34]   (yuv.go:205)
+};
+__device__ __forceinline__ int rgb_to_y(int r, int g, int b) { return (16839 * r + 33059 * g + 6420 * b + (1 << 15) + (16 << 16)) >> 16; }
+__device__ __forceinline__ int clip_uv(int uv) {  // VP8ClipUV with rounding = 1<<17 (yuv.go:138)
+  uv = (uv + (1 << 17) + (128 << 18)) >> 18;
+  return min(max(uv, 0), 255);
+}
+__device__ __forceinline__ int lin2gamma(uint32_t v, const uint16_t* l2g) {  // yuv.go:237, shift 0
+  const int tab_pos = min((int)(v >> 9), 31);
+  const int x = v & 511;
+  const int yv = l2g[tab_pos + 1] * x + l2g[tab_pos] * (512 - x);
+  return (yv + 64) >> 7;
+}
+__global__ void __launch_bounds__(256) import_rgba_kernel(const ImportParams P) {
+  __shared__ uint16_t s_g2l[256];
+  __shared__ uint16_t s_l2g[34];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_g2l[i] = P.gamma_to_linear[i];
+  if (threadIdx.x < 34) s_l2g[threadIdx.x] = P.linear_to_gamma[threadIdx.x];
+  __syncthreads();
+  const int qw = P.pad_w >> 2, qh = P.pad_h >> 1;
+  const long long per_img = (long long)qw * qh;
+  const long long total = per_img * P.n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(t / per_img);
+    const int rem = (int)(t - (long long)img * per_img);
+    const int cy = rem / qw, cx = rem - cy * qw;
+    const int x0 = cx * 4, y0 = cy * 2;
+    const uint8_t* base = P.rgba + (size_t)img * P.image_stride;
+    uint32_t px[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint8_t* row = base + (size_t)min(y0 + r, P.height - 1) * P.stride;
+      if (x0 + 3 < P.width) {
+        const uint4 q = *reinterpret_cast<const uint4*>(row + 4 * x0);
+        px[r][0] = q.x; px[r][1] = q.y; px[r][2] = q.z; px[r][3] = q.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) px[r][i] = *reinterpret_cast<const uint32_t*>(row + 4 * min(x0 + i, P.width - 1));
+      }
+    }
+    uint8_t* yp = P.y + (size_t)img * P.y_plane;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t p = px[r][i];
+        w |= (uint32_t)rgb_to_y(p & 0xff, (p >> 8) & 0xff, (p >> 16) & 0xff) << (8 * i);
+      }
+      *reinterpret_cast<uint32_t*>(yp + (size_t)(y0 + r) * P.pad_w + x0) = w;
+    }
+    uint32_t uu = 0, vv = 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t p0 = px[0][2 * k], p1 = px[0][2 * k + 1], p2 = px[1][2 * k], p3 = px[1][2 * k + 1];
+      uint32_t a0 = 255, a1 = 255, a2 = 255, a3 = 255;
+      if (P.has_alpha) { a0 = p0 >> 24; a1 = p1 >> 24; a2 = p2 >> 24; a3 = p3 >> 24; }
+      const uint32_t ta = a0 + a1 + a2 + a3;
+      int c[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const int sh = 8 * ch;
+        const uint32_t l0 = s_g2l[(p0 >> sh) & 0xff], l1 = s_g2l[(p1 >> sh) & 0xff];
+        const uint32_t l2 = s_g2l[(p2 >> sh) & 0xff], l3 = s_g2l[(p3 >> sh) & 0xff];
+        if (ta == 4 * 255 || ta == 0) {
+          c[ch] = lin2gamma(l0 + l1 + l2 + l3, s_l2g);
+        } else {  // LinearToGammaWeighted (yuv.go:466); kInvAlpha[a] = (1<<19)/a
+          const uint32_t sum = a0 * l0 + a1 * l1 + a2 * l2 + a3 * l3;
+          c[ch] = lin2gamma((sum * ((1u << 19) / ta)) >> (19 - 2), s_l2g);
+        }
+        c[ch] &= 0xffff;
+      }
+      uu |= (uint32_t)clip_uv(-9719 * c[0] - 19081 * c[1] + 28800 * c[2]) << (8 * k);
+      vv |= (uint32_t)clip_uv(28800 * c[0] - 24116 * c[1] - 4684 * c[2]) << (8 * k);
+    }
+    const size_t uvo = (size_t)img * P.uv_plane + (size_t)cy * (P.pad_w >> 1) + (x0 >> 1);
+    *reinterpret_cast<uint16_t*>(P.u + uvo) = (uint16_t)uu;
+    *reinterpret_cast<uint16_t*>(P.v + uvo) = (uint16_t)vv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Analysis (internal/lossy/encode_analysis.go:245-728): per macroblock, DC and TM 16x16 predictions built
+// from SOURCE pixels, 16 forward transforms each, histogram of min(|c|>>3, 31), alpha = 510*last/max;
+// chroma DC-only.  mixed = 255 - ((3*luma + uv + 2) >> 2).  16 lanes per macroblock, one 4x4 block per lane.
+struct AnalysisParams {
+  const uint8_t* y; const uint8_t* u; const uint8_t* v; size_t y_plane, uv_plane;
+  int n, mb_w, mb_h;
+  uint8_t* alpha;     // [n][nmb] mixed alpha
+  uint8_t* uv_alpha;  // [n][nmb] chroma alpha (host sums it for dq_uv_ac)
+};
+__device__ __forceinline__ int histo_alpha16(int* hist, int gl) {  // alpha from a 32-bin shared histogram, 16 lanes
+  const int c0 = hist[gl], c1 = hist[gl + 16];
+  int mx = max(c0, c1);
+  int last = c1 > 0 ? gl + 16 : (c0 > 0 ? gl : -1);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o, 16));
+    last = max(last, __shfl_xor_sync(0xffffffffu, last, o, 16));
+  }
+  if (last < 0) last = 1;
+  int alpha = 0;
+  if (mx > 1) alpha = 2 * 255 * last / mx;
+  return min(alpha, 255);
+}
+__device__ __forceinline__ void histo_add16(const int* c, int* hist) {
+#pragma unroll
+  for (int k = 0; k < 16; ++k) atomicAdd(&hist[min(abs(c[k]) >> 3, 31)], 1);
+}
+__global__ void __launch_bounds__(128) analysis_kernel(const AnalysisParams P) {
+  __shared__ int s_hist[8][32];
+  const int lane = threadIdx.x & 31, gl = lane & 15;
+  const int grp = threadIdx.x >> 4;  // 8 macroblocks per CTA
+  const int nmb = P.mb_w * P.mb_h;
+  const long long total = (long long)nmb * P.n;
+  const long long task = (long long)blockIdx.x * 8 + grp;
+  const bool active = task < total;
+  const int img = active ? (int)(task / nmb) : 0;
+  const int mb = active ? (int)(task - (long long)img * nmb) : 0;
+  const int my = mb / P.mb_w, mx = mb - my * P.mb_w;
+  const int ys = P.mb_w * 16, uvs = P.mb_w * 8;
+  const uint8_t* yp = P.y + (size_t)img * P.y_plane + (size_t)my * 16 * ys + mx * 16;
+  int* hist = s_hist[grp];
+  const int bx = gl & 3, by = gl >> 2;
+  int src[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(yp + (size_t)(by * 4 + j) * ys + bx * 4);
+    src[4 * j] = w & 0xff; src[4 * j + 1] = (w >> 8) & 0xff; src[4 * j + 2] = (w >> 16) & 0xff; src[4 * j + 3] = w >> 24;
+  }
+  // DC value from source neighbours (encode_analysis.go:455-500)
+  int s = 0;
+  if (my > 0) s += yp[-(ptrdiff_t)ys + gl];
+  if (mx > 0) s += yp[(size_t)gl * ys - 1];
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+  const int count = (my > 0 ? 16 : 0) + (mx > 0 ? 16 : 0);
+  const int dc_val = count > 0 ? (s + count / 2) / count : 128;
+  int best_alpha = 256;
+  int pred[16], c[16];
+  {
+    hist[gl] = 0; hist[gl + 16] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pred[i] = dc_val;
+    ftransform(src, pred, c);
+    histo_add16(c, hist);
+    __syncwarp();
+    best_alpha = min(best_alpha, histo_alpha16(hist, gl));
+    __syncwarp();
+  }
+  if (mx > 0 && my > 0) {  // uniform per 16-lane group; groups of a warp may diverge here, shuffles use width 16
+    hist[gl] = 0; hist[gl + 16] = 0;
+    const uint32_t tw = *reinterpret_cast<const uint32_t*>(yp - (ptrdiff_t)ys + bx * 4);
+    const int tl = yp[-(ptrdiff_t)ys - 1];
+    const int t[4] = {(int)(tw & 0xff), (int)((tw >> 8) & 0xff), (int)((tw >> 16) & 0xff), (int)(tw >> 24)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = yp[(size_t)(by * 4 + j) * ys - 1];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pred[4 * j + i] = clip8(t[i] + l - tl);
+    }
+    ftransform(src, pred, c);
+  }
+  __syncwarp();
+  if (mx > 0 && my > 0) histo_add16(c, hist);
+  __syncwarp();
+  {
+    const int a = histo_alpha16(hist, gl);  // for edge macroblocks this re-reads the DC histogram: same value
+    best_alpha = min(best_alpha, a);
+  }
+  __syncwarp();
+  const int luma_alpha = min(best_alpha, 255);
+  // chroma: lanes 0-7 read U neighbours, 8-15 V neighbours; lanes 0-3 transform U blocks, 4-7 V blocks
+  const int pl = gl >> 3, k = gl & 7;
+  const uint8_t* cp = (pl ? P.v : P.u) + (size_t)img * P.uv_plane + (size_t)my * 8 * uvs + mx * 8;
+  int cs = 0;
+  if (my > 0) cs += cp[-(ptrdiff_t)uvs + k];
+  if (mx > 0) cs += cp[(size_t)k * uvs - 1];
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o, 8);
+  const int ccount = (my > 0 ? 8 : 0) + (mx > 0 ? 8 : 0);
+  const int cdc = ccount > 0 ? (cs + ccount / 2) / ccount : 128;
+  const int dc_u = __shfl_sync(0xffffffffu, cdc, 0, 16), dc_v = __shfl_sync(0xffffffffu, cdc, 8, 16);
+  hist[gl] = 0; hist[gl + 16] = 0;
+  __syncwarp();
+  if (gl < 8) {
+    const int bpl = gl >> 2, bb = gl & 3;
+    const uint8_t* bp = (bpl ? P.v : P.u) + (size_t)img * P.uv_plane + (size_t)(my * 8 + (bb >> 1) * 4) * uvs + mx * 8 + (bb & 1) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(bp + (size_t)j * uvs);
+      src[4 * j] = w & 0xff; src[4 * j + 1] = (w >> 8) & 0xff; src[4 * j + 2] = (w >> 16) & 0xff; src[4 * j + 3] = w >> 24;
+    }
+    const int dv = bpl ? dc_v : dc_u;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pred[i] = dv;
+    ftransform(src, pred, c);
+    histo_add16(c, hist);
+  }
+  __syncwarp();
+  const int uv_alpha = histo_alpha16(hist, gl);
+  if (active && gl == 0) {
+    int mixed = 255 - ((3 * luma_alpha + uv_alpha + 2) >> 2);
+    mixed = min(max(mixed, 0), 255);
+    P.alpha[(size_t)img * nmb + mb] = (uint8_t)mixed;
+    P.uv_alpha[(size_t)img * nmb + mb] = (uint8_t)uv_alpha;
+  }
+}
+
+}  // namespace wg

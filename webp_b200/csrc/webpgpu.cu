@@ -1,0 +1,800 @@
+// libwebpgpu: C ABI (include/webpgpu.h) over the sm_100a kernels.  One wgpu_ctx == one GPU + one stream.
+// There is no CPU fallback anywhere in this file: every pixel stage is a kernel launch, and a missing /
+// failing CUDA device is an error (WGPU_ERR_CUDA), never a silent host path.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/webpgpu.h"
+#include "misc_kernels.cuh"
+#include "host_dec.h"
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool reserve(size_t n) {
+    if (n <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    if (cudaMalloc(&p, n) != cudaSuccess) return false;
+    cap = n;
+    return true;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool reserve(size_t n) {
+    if (n <= cap) return true;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    if (cudaMallocHost(&p, n) != cudaSuccess) return false;
+    cap = n;
+    return true;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+template <class F>
+void parallel_for(int n, int threads, F f) {
+  if (threads <= 1 || n <= 1) { for (int i = 0; i < n; ++i) f(i); return; }
+  if (threads > n) threads = n;
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  pool.reserve(threads);
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&]() { for (int i; (i = next.fetch_add(1)) < n;) f(i); });
+  for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+struct wgpu_ctx {
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int host_threads = 0;
+  std::mutex mu;
+  // constant tables
+  DevBuf t_ecost, t_lfc, t_lcodes, t_proba, t_i4cost, t_g2l, t_l2g;
+  // encoder state (device)
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, hdr, coeffs;
+  PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs;
+  int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
+  bool e_uploaded = false, e_done = false;
+  wgpu_enc_options e_opt;
+  std::vector<wgh::FramePlan> plans;
+  // decoder state
+  DevBuf d_coeffs, d_meta, d_ftype, dy, du, dv, d_nrgba, d_alpha;
+  PinBuf hd_coeffs, hd_meta, hd_ftype, hd_planes, hd_nrgba;
+  // metrics
+  DevBuf m_a, m_b, m_sse_part, m_ssim_part, m_sse, m_ssim;
+};
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+      return e_ == cudaErrorMemoryAllocation ? WGPU_ERR_NOMEM : WGPU_ERR_CUDA;                     \
+    }                                                                                              \
+  } while (0)
+#define RESERVE(buf, bytes)                                                                        \
+  do {                                                                                             \
+    if (!(buf).reserve(bytes)) { ctx->err = "out of memory reserving " #buf; cudaGetLastError(); return WGPU_ERR_NOMEM; } \
+  } while (0)
+#define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
+
+static int threads_of(const wgpu_ctx* ctx) {
+  int t = ctx->host_threads;
+  if (t <= 0) t = (int)std::thread::hardware_concurrency();
+  return t > 0 ? t : 1;
+}
+
+extern "C" {
+
+void wgpu_enc_options_default(wgpu_enc_options* o, int quality) {
+  // DefaultOptions (encode.go:196-214) mapped onto lossy.EncodeConfig (internal/lossy/encode.go:66-86)
+  o->quality = quality; o->method = 4; o->sns_strength = 50; o->filter_strength = 60; o->filter_sharpness = 0;
+  o->filter_type = 1; o->partitions = 0; o->segments = 4; o->preprocessing = 0; o->has_alpha = 0;
+}
+
+static int upload_table(wgpu_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+  RESERVE(b, bytes);
+  CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int wgpu_ctx_create(int device_ordinal, wgpu_ctx** out) {
+  if (!out) return WGPU_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                     " (libwebpgpu has no CPU fallback)";
+    cudaGetLastError();
+    return WGPU_ERR_CUDA;
+  }
+  if (device_ordinal < 0 || device_ordinal >= count) { g_create_error = "device ordinal out of range"; return WGPU_ERR_INVALID; }
+  wgpu_ctx* ctx = new wgpu_ctx();
+  ctx->dev = device_ordinal;
+  auto bail = [&](const char* what, cudaError_t ce) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ce); delete ctx; return WGPU_ERR_CUDA; };
+  if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  // tables
+  static uint16_t i4costs[1000];
+  wgh::compute_i4_costs(i4costs);
+  static uint16_t g2l[256], l2g[34];
+  for (int i = 0; i < 256; ++i) {  // yuv.go:193-215 (kGamma = 0.80, 12-bit linear, 32-entry interpolation table)
+    const double v = (double)i / 255.0;
+    g2l[i] = (uint16_t)((v <= 0 ? 0.0 : pow(v, 0.80)) * 4095.0 + 0.5);
+  }
+  for (int i = 0; i <= 32; ++i) {
+    const double v = (128.0 / 4095.0) * (double)i;
+    l2g[i] = (uint16_t)((v <= 0 ? 0.0 : pow(v, 1.0 / 0.80)) * 255.0 + 0.5);
+  }
+  l2g[33] = 255;
+  int rc = 0;
+  rc |= upload_table(ctx, ctx->t_ecost, wgh::kEntropyCost, sizeof(wgh::kEntropyCost));
+  rc |= upload_table(ctx, ctx->t_lfc, wgh::kLevelFixedCosts, sizeof(wgh::kLevelFixedCosts));
+  rc |= upload_table(ctx, ctx->t_lcodes, wgh::kLevelCodes, sizeof(wgh::kLevelCodes));
+  rc |= upload_table(ctx, ctx->t_proba, wgh::kCoeffsProba0, sizeof(wgh::kCoeffsProba0));
+  rc |= upload_table(ctx, ctx->t_i4cost, i4costs, sizeof(i4costs));
+  rc |= upload_table(ctx, ctx->t_g2l, g2l, sizeof(g2l));
+  rc |= upload_table(ctx, ctx->t_l2g, l2g, sizeof(l2g));
+  if (rc || cudaStreamSynchronize(ctx->stream) != cudaSuccess) { g_create_error = "table upload failed: " + ctx->err; delete ctx; return WGPU_ERR_CUDA; }
+  *out = ctx;
+  return WGPU_OK;
+}
+
+void wgpu_ctx_destroy(wgpu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->dev);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* db[] = {&ctx->t_ecost, &ctx->t_lfc, &ctx->t_lcodes, &ctx->t_proba, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
+                  &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
+                  &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
+                  &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
+                  &ctx->m_sse, &ctx->m_ssim};
+  for (DevBuf* b : db) b->release();
+  PinBuf* pb[] = {&ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
+                  &ctx->hd_meta, &ctx->hd_ftype, &ctx->hd_planes, &ctx->hd_nrgba};
+  for (PinBuf* b : pb) b->release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* wgpu_last_error(const wgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int wgpu_sync(wgpu_ctx* ctx) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WGPU_OK;
+}
+int wgpu_set_host_threads(wgpu_ctx* ctx, int n) {
+  if (!ctx || n < 0) return WGPU_ERR_INVALID;
+  ctx->host_threads = n;
+  return WGPU_OK;
+}
+void* wgpu_host_alloc(wgpu_ctx* ctx, size_t bytes) {
+  if (!ctx) return nullptr;
+  cudaSetDevice(ctx->dev);
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { ctx->err = "cudaMallocHost failed"; cudaGetLastError(); return nullptr; }
+  return p;
+}
+void wgpu_host_free(wgpu_ctx* ctx, void* p) {
+  if (ctx) cudaSetDevice(ctx->dev);
+  if (p) cudaFreeHost(p);
+}
+
+// ======================================================================================== encoder
+static int validate_enc_options(wgpu_ctx* ctx, const wgpu_enc_options* o, int width, int height) {
+  // validateConfig (encode.go:259-334)
+  if (!o) FAIL(WGPU_ERR_INVALID, "webp: nil options");
+  if (width <= 0 || height <= 0 || width > 16383 || height > 16383) FAIL(WGPU_ERR_INVALID, "webp: invalid image dimensions");
+  if (o->quality < 0 || o->quality > 100) FAIL(WGPU_ERR_INVALID, "webp: quality out of range [0, 100]");
+  if (o->method < 0 || o->method > 6) FAIL(WGPU_ERR_INVALID, "webp: method out of range [0, 6]");
+  if (o->sns_strength < 0 || o->sns_strength > 100) FAIL(WGPU_ERR_INVALID, "webp: sns strength out of range [0, 100]");
+  if (o->filter_strength < 0 || o->filter_strength > 100) FAIL(WGPU_ERR_INVALID, "webp: filter strength out of range [0, 100]");
+  if (o->filter_sharpness < 0 || o->filter_sharpness > 7) FAIL(WGPU_ERR_INVALID, "webp: filter sharpness out of range [0, 7]");
+  if (o->filter_type < 0 || o->filter_type > 1) FAIL(WGPU_ERR_INVALID, "webp: filter type out of range [0, 1]");
+  if (o->partitions < 0 || o->partitions > 3) FAIL(WGPU_ERR_INVALID, "webp: partitions out of range [0, 3]");
+  if (o->segments < 1 || o->segments > 4) FAIL(WGPU_ERR_INVALID, "webp: segments out of range [1, 4]");
+  // The GPU path restates the reference's row-parallel encoder (internal/lossy/encode.go:1356):
+  // Method >= 3, mbH >= 4, single pass.  The serial-path configurations are a later row of the scope table.
+  if (o->method < 3) FAIL(WGPU_ERR_UNSUPPORTED, "method < 3 takes the reference's serial path (not built yet)");
+  if (((height + 15) >> 4) < 4) FAIL(WGPU_ERR_UNSUPPORTED, "height <= 48 takes the reference's serial path (not built yet)");
+  return WGPU_OK;
+}
+
+int wgpu_enc_upload(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int height, int stride, size_t image_stride) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!rgba || n <= 0 || width <= 0 || height <= 0 || stride < 4 * width) FAIL(WGPU_ERR_INVALID, "webp: invalid input image");
+  if (width > 16383 || height > 16383) FAIL(WGPU_ERR_INVALID, "webp: invalid image dimensions");
+  CK(cudaSetDevice(ctx->dev));
+  const int dstride = (4 * width + 15) & ~15;
+  RESERVE(ctx->rgba, (size_t)n * height * dstride);
+  if (image_stride == (size_t)stride * height) {
+    CK(cudaMemcpy2DAsync(ctx->rgba.p, dstride, rgba, stride, (size_t)4 * width, (size_t)n * height, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    for (int i = 0; i < n; ++i)
+      CK(cudaMemcpy2DAsync(ctx->rgba.as<uint8_t>() + (size_t)i * height * dstride, dstride, rgba + (size_t)i * image_stride, stride,
+                           (size_t)4 * width, height, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ctx->e_n = n; ctx->e_w = width; ctx->e_h = height; ctx->e_mbw = (width + 15) >> 4; ctx->e_mbh = (height + 15) >> 4;
+  ctx->e_rgba_stride = dstride;
+  ctx->e_uploaded = true;
+  ctx->e_done = false;
+  return WGPU_OK;
+}
+
+namespace {
+constexpr int kEncG = 8, kEncWarps = 4;  // lanes per macroblock / warps per CTA of the mode-search kernel
+constexpr int kEncMBPerCTA = kEncWarps * (32 / kEncG);
+constexpr size_t kEncSmem = sizeof(wg::MBShared) * kEncMBPerCTA;
+
+int wave_rows(int wave, int mb_w, int mb_h) {
+  const int y_lo = std::max(0, (wave - (mb_w - 1) + 1) >> 1), y_hi = std::min(mb_h - 1, wave >> 1);
+  return y_hi - y_lo + 1;
+}
+}  // namespace
+
+static int enc_launch_import(wgpu_ctx* ctx) {
+  const int n = ctx->e_n, pad_w = ctx->e_mbw * 16, pad_h = ctx->e_mbh * 16;
+  wg::ImportParams ip;
+  ip.rgba = ctx->rgba.as<uint8_t>(); ip.image_stride = (size_t)ctx->e_h * ctx->e_rgba_stride; ip.stride = ctx->e_rgba_stride;
+  ip.n = n; ip.width = ctx->e_w; ip.height = ctx->e_h; ip.pad_w = pad_w; ip.pad_h = pad_h; ip.has_alpha = ctx->e_opt.has_alpha;
+  ip.y = ctx->sy.as<uint8_t>(); ip.u = ctx->su.as<uint8_t>(); ip.v = ctx->sv.as<uint8_t>();
+  ip.y_plane = (size_t)pad_w * pad_h; ip.uv_plane = ip.y_plane / 4;
+  ip.gamma_to_linear = ctx->t_g2l.as<uint16_t>(); ip.linear_to_gamma = ctx->t_l2g.as<uint16_t>();
+  const long long total = (long long)(pad_w / 4) * (pad_h / 2) * n;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
+  wg::import_rgba_kernel<<<blocks, 256, 0, ctx->stream>>>(ip);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return WGPU_OK;
+}
+static int enc_launch_analysis(wgpu_ctx* ctx) {
+  const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
+  wg::AnalysisParams ap;
+  ap.y = ctx->sy.as<uint8_t>(); ap.u = ctx->su.as<uint8_t>(); ap.v = ctx->sv.as<uint8_t>();
+  ap.y_plane = (size_t)nmb * 256; ap.uv_plane = (size_t)nmb * 64;
+  ap.n = n; ap.mb_w = ctx->e_mbw; ap.mb_h = ctx->e_mbh;
+  ap.alpha = ctx->alpha.as<uint8_t>(); ap.uv_alpha = ctx->uv_alpha.as<uint8_t>();
+  const long long total = (long long)nmb * n;
+  wg::analysis_kernel<<<(unsigned)((total + 7) / 8), 128, 0, ctx->stream>>>(ap);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return WGPU_OK;
+}
+static int enc_launch_waves(wgpu_ctx* ctx) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(wg::encode_wave_kernel<kEncG, kEncWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmem));
+    attr_set = true;
+  }
+  const int n = ctx->e_n, mbw = ctx->e_mbw, mbh = ctx->e_mbh, nmb = mbw * mbh;
+  wg::EncKernelParams P;
+  P.src_y = ctx->sy.as<uint8_t>(); P.src_u = ctx->su.as<uint8_t>(); P.src_v = ctx->sv.as<uint8_t>();
+  P.rec_y = ctx->ry.as<uint8_t>(); P.rec_u = ctx->ru.as<uint8_t>(); P.rec_v = ctx->rv.as<uint8_t>();
+  P.segment = ctx->segment.as<uint8_t>(); P.img = ctx->img_params.as<wg::ImageParams>();
+  P.ctx = ctx->ctxw.as<uint32_t>(); P.out_hdr = ctx->hdr.as<uint8_t>(); P.out_coeffs = ctx->coeffs.as<int16_t>();
+  P.i4_costs = ctx->t_i4cost.as<uint16_t>(); P.ecost = ctx->t_ecost.as<uint16_t>(); P.lfc = ctx->t_lfc.as<uint16_t>();
+  P.lcodes = ctx->t_lcodes.as<uint16_t>(); P.proba = ctx->t_proba.as<uint8_t>();
+  P.n_images = n; P.width = ctx->e_w; P.height = ctx->e_h; P.mb_w = mbw; P.mb_h = mbh;
+  P.method = ctx->e_opt.method;
+  P.max_i4_modes = ctx->e_opt.quality < 50 ? 2 : 3;  // getMaxI4RDModes (encode_parallel.go:931)
+  P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
+  const int waves = mbw + 2 * (mbh - 1);
+  for (int w = 0; w < waves; ++w) {
+    const long long tasks = (long long)wave_rows(w, mbw, mbh) * n;
+    const unsigned grid = (unsigned)((tasks + kEncMBPerCTA - 1) / kEncMBPerCTA);
+    wg::encode_wave_kernel<kEncG, kEncWarps><<<grid, kEncWarps * 32, kEncSmem, ctx->stream>>>(P, w);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  return WGPU_OK;
+}
+
+static int enc_reserve(wgpu_ctx* ctx) {
+  const size_t n = ctx->e_n, nmb = (size_t)ctx->e_mbw * ctx->e_mbh;
+  RESERVE(ctx->sy, n * nmb * 256); RESERVE(ctx->su, n * nmb * 64); RESERVE(ctx->sv, n * nmb * 64);
+  RESERVE(ctx->ry, n * nmb * 256); RESERVE(ctx->ru, n * nmb * 64); RESERVE(ctx->rv, n * nmb * 64);
+  RESERVE(ctx->alpha, n * nmb); RESERVE(ctx->uv_alpha, n * nmb); RESERVE(ctx->segment, n * nmb);
+  RESERVE(ctx->img_params, n * sizeof(wg::ImageParams));
+  RESERVE(ctx->ctxw, n * nmb * 4); RESERVE(ctx->hdr, n * nmb * 48); RESERVE(ctx->coeffs, n * nmb * 800);
+  RESERVE(ctx->h_alpha, n * nmb); RESERVE(ctx->h_uv_alpha, n * nmb); RESERVE(ctx->h_segment, n * nmb);
+  RESERVE(ctx->h_params, n * sizeof(wg::ImageParams));
+  return WGPU_OK;
+}
+
+int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->e_uploaded) FAIL(WGPU_ERR_INVALID, "wgpu_enc_device called before wgpu_enc_upload");
+  int rc = validate_enc_options(ctx, opt, ctx->e_w, ctx->e_h);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->dev));
+  ctx->e_opt = *opt;
+  ctx->e_done = false;
+  if ((rc = enc_reserve(ctx))) return rc;
+  const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
+  if ((rc = enc_launch_import(ctx))) return rc;
+  if ((rc = enc_launch_analysis(ctx))) return rc;
+  CK(cudaMemcpyAsync(ctx->h_alpha.p, ctx->alpha.p, (size_t)n * nmb, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_uv_alpha.p, ctx->uv_alpha.p, (size_t)n * nmb, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // host: segment clustering + quantiser / lambda setup (microseconds per image; float64 pow as in the reference)
+  ctx->plans.resize(n);
+  static_assert(sizeof(wgh::SegParams) == sizeof(wg::SegParams), "SegParams layout");
+  parallel_for(n, threads_of(ctx), [&](int i) {
+    const uint8_t* ua = ctx->h_uv_alpha.as<uint8_t>() + (size_t)i * nmb;
+    long long uv_sum = 0;
+    for (int k = 0; k < nmb; ++k) uv_sum += ua[k];
+    wgh::FramePlan& fp = ctx->plans[i];
+    wgh::plan_frame(&fp, ctx->e_opt, ctx->e_w, ctx->e_h, ctx->h_alpha.as<uint8_t>() + (size_t)i * nmb, uv_sum,
+                    ctx->h_segment.as<uint8_t>() + (size_t)i * nmb);
+    fp.num_parts = 1 << ctx->e_opt.partitions;
+    memcpy(ctx->h_params.as<uint8_t>() + (size_t)i * sizeof(wg::ImageParams), fp.dev, sizeof(wg::ImageParams));
+  });
+  CK(cudaMemcpyAsync(ctx->segment.p, ctx->h_segment.p, (size_t)n * nmb, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->img_params.p, ctx->h_params.p, (size_t)n * sizeof(wg::ImageParams), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = enc_launch_waves(ctx))) return rc;
+  ctx->e_done = true;
+  return WGPU_OK;
+}
+
+int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_sizes) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->e_done) FAIL(WGPU_ERR_INVALID, "wgpu_enc_finish called before wgpu_enc_device");
+  if (!out || !out_sizes) FAIL(WGPU_ERR_INVALID, "webp: nil writer");
+  CK(cudaSetDevice(ctx->dev));
+  const size_t n = ctx->e_n, nmb = (size_t)ctx->e_mbw * ctx->e_mbh;
+  RESERVE(ctx->h_hdr, n * nmb * 48);
+  RESERVE(ctx->h_coeffs, n * nmb * 800);
+  CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_coeffs.p, ctx->coeffs.p, n * nmb * 800, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::atomic<int> too_small(0);
+  parallel_for((int)n, threads_of(ctx), [&](int i) {
+    std::vector<uint8_t> riff;
+    riff.reserve(nmb * 64 + 4096);
+    wgh::serialize_frame(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
+                         ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, &riff);
+    out_sizes[i] = riff.size();
+    if (riff.size() > out_stride) { too_small.store(1); return; }
+    memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
+  });
+  if (too_small.load()) FAIL(WGPU_ERR_TOO_SMALL, "output buffer too small (out_sizes holds the required sizes)");
+  return WGPU_OK;
+}
+
+int wgpu_encode_batch(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int height, int stride, size_t image_stride,
+                      const wgpu_enc_options* opt, uint8_t* out, size_t out_stride, size_t* out_sizes) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  int rc = validate_enc_options(ctx, opt, width, height);
+  if (rc) return rc;
+  if ((rc = wgpu_enc_upload(ctx, rgba, n, width, height, stride, image_stride))) return rc;
+  if ((rc = wgpu_enc_device(ctx, opt))) return rc;
+  return wgpu_enc_finish(ctx, out, out_stride, out_sizes);
+}
+
+int wgpu_enc_fetch(wgpu_ctx* ctx, int image, uint8_t* mb_hdr, uint8_t* mb_modes, uint8_t* mb_nz, int16_t* mb_coeffs, uint8_t* recon_y,
+                   uint8_t* recon_u, uint8_t* recon_v, uint8_t* src_y, uint8_t* src_u, uint8_t* src_v, uint8_t* alphas) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->e_done || image < 0 || image >= ctx->e_n) FAIL(WGPU_ERR_INVALID, "wgpu_enc_fetch: no encoded batch / bad image index");
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t nmb = (size_t)ctx->e_mbw * ctx->e_mbh, i = image;
+  if (mb_hdr || mb_modes || mb_nz) {
+    std::vector<uint8_t> h(nmb * 48);
+    CK(cudaMemcpy(h.data(), ctx->hdr.as<uint8_t>() + i * nmb * 48, nmb * 48, cudaMemcpyDeviceToHost));
+    for (size_t k = 0; k < nmb; ++k) {
+      if (mb_hdr) memcpy(mb_hdr + 8 * k, &h[48 * k], 8);
+      if (mb_modes) memcpy(mb_modes + 16 * k, &h[48 * k + 8], 16);
+      if (mb_nz) memcpy(mb_nz + 24 * k, &h[48 * k + 24], 24);
+    }
+  }
+  if (mb_coeffs) CK(cudaMemcpy(mb_coeffs, ctx->coeffs.as<int16_t>() + i * nmb * 400, nmb * 800, cudaMemcpyDeviceToHost));
+  if (recon_y) CK(cudaMemcpy(recon_y, ctx->ry.as<uint8_t>() + i * nmb * 256, nmb * 256, cudaMemcpyDeviceToHost));
+  if (recon_u) CK(cudaMemcpy(recon_u, ctx->ru.as<uint8_t>() + i * nmb * 64, nmb * 64, cudaMemcpyDeviceToHost));
+  if (recon_v) CK(cudaMemcpy(recon_v, ctx->rv.as<uint8_t>() + i * nmb * 64, nmb * 64, cudaMemcpyDeviceToHost));
+  if (src_y) CK(cudaMemcpy(src_y, ctx->sy.as<uint8_t>() + i * nmb * 256, nmb * 256, cudaMemcpyDeviceToHost));
+  if (src_u) CK(cudaMemcpy(src_u, ctx->su.as<uint8_t>() + i * nmb * 64, nmb * 64, cudaMemcpyDeviceToHost));
+  if (src_v) CK(cudaMemcpy(src_v, ctx->sv.as<uint8_t>() + i * nmb * 64, nmb * 64, cudaMemcpyDeviceToHost));
+  if (alphas) CK(cudaMemcpy(alphas, ctx->alpha.as<uint8_t>() + i * nmb, nmb, cudaMemcpyDeviceToHost));
+  return WGPU_OK;
+}
+
+int wgpu_enc_stage_time(wgpu_ctx* ctx, const wgpu_enc_options* opt, int stage, int reps, float* ms_per_rep) {
+  if (!ctx || !ms_per_rep || reps <= 0) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->e_done) FAIL(WGPU_ERR_INVALID, "wgpu_enc_stage_time needs a completed wgpu_enc_device");
+  (void)opt;
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = 0;
+  for (int r = 0; r < reps && !rc; ++r) {
+    if (stage == 0) rc = enc_launch_import(ctx);
+    else if (stage == 1) rc = enc_launch_analysis(ctx);
+    else if (stage == 2) rc = enc_launch_waves(ctx);
+    else FAIL(WGPU_ERR_INVALID, "unknown stage");
+  }
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *ms_per_rep = ms / reps;
+  return WGPU_OK;
+}
+
+// ======================================================================================== decoder
+int wgpu_decode_info(const uint8_t* data, size_t len, int* width, int* height) {
+  if (!data || !width || !height) return WGPU_ERR_INVALID;
+  const uint8_t* vp8; size_t vlen; const char* err = nullptr;
+  if (!wgh::find_vp8(data, len, &vp8, &vlen)) return WGPU_ERR_BITSTREAM;
+  if (!wgh::peek_dims(vp8, vlen, width, height, &err)) return WGPU_ERR_BITSTREAM;
+  return WGPU_OK;
+}
+
+namespace {
+constexpr int kDecG = 8, kDecWarps = 4, kFiltWarps = 4;
+}
+
+static int dec_launch_recon(wgpu_ctx* ctx, const wg::DecKernelParams& P) {
+  const int waves = P.mb_w + 2 * (P.mb_h - 1);
+  const int per_cta = kDecWarps * (32 / kDecG);
+  for (int w = 0; w < waves; ++w) {
+    const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
+    wg::recon_wave_kernel<kDecG, kDecWarps><<<(unsigned)((tasks + per_cta - 1) / per_cta), kDecWarps * 32, 0, ctx->stream>>>(P, w);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  return WGPU_OK;
+}
+static int dec_launch_filter(wgpu_ctx* ctx, const wg::DecKernelParams& P) {
+  const int waves = P.mb_w + 2 * (P.mb_h - 1);
+  const int per_cta = kFiltWarps * 2;
+  for (int w = 0; w < waves; ++w) {
+    const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
+    wg::filter_wave_kernel<kFiltWarps><<<(unsigned)((tasks + per_cta - 1) / per_cta), kFiltWarps * 32, 0, ctx->stream>>>(P, w);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  return WGPU_OK;
+}
+static int launch_upsample(wgpu_ctx* ctx, int n, int width, int height, const uint8_t* y, int ys, const uint8_t* u, const uint8_t* v,
+                           int uvs, size_t y_plane, size_t uv_plane, const uint8_t* alpha, uint8_t* out) {
+  wg::UpsampleParams up;
+  up.y = y; up.u = u; up.v = v; up.alpha = alpha;
+  up.y_plane = y_plane; up.uv_plane = uv_plane; up.alpha_plane = (size_t)width * height; up.out_image = (size_t)width * height * 4;
+  up.y_stride = ys; up.uv_stride = uvs; up.width = width; up.height = height; up.n = n; up.out = out;
+  const long long total = (long long)((width + 3) / 4) * height * n;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
+  wg::upsample_nrgba_kernel<<<blocks, 256, 0, ctx->stream>>>(up);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return WGPU_OK;
+}
+
+int wgpu_decode_batch(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* lens, int n, uint8_t* y, uint8_t* u, uint8_t* v,
+                      size_t y_plane_stride, size_t uv_plane_stride, uint8_t* nrgba, size_t nrgba_image_stride) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!streams || !lens || n <= 0) FAIL(WGPU_ERR_INVALID, "webp: nil reader");
+  CK(cudaSetDevice(ctx->dev));
+  // dimensions from the first stream; every stream of the batch must match
+  const uint8_t* vp8; size_t vlen; const char* perr = nullptr;
+  int width = 0, height = 0;
+  if (!wgh::find_vp8(streams[0], lens[0], &vp8, &vlen) || !wgh::peek_dims(vp8, vlen, &width, &height, &perr))
+    FAIL(WGPU_ERR_BITSTREAM, perr ? perr : "webp: no VP8 chunk");
+  const int mbw = (width + 15) >> 4, mbh = (height + 15) >> 4;
+  const size_t nmb = (size_t)mbw * mbh;
+  const size_t yp = nmb * 256, uvp = nmb * 64;
+  if ((y && y_plane_stride < yp) || ((u || v) && uv_plane_stride < uvp)) FAIL(WGPU_ERR_TOO_SMALL, "plane stride smaller than the padded plane");
+  if (nrgba && nrgba_image_stride < (size_t)width * height * 4) FAIL(WGPU_ERR_TOO_SMALL, "nrgba image stride too small");
+  RESERVE(ctx->hd_coeffs, (size_t)n * nmb * 768);
+  RESERVE(ctx->hd_meta, (size_t)n * nmb * sizeof(wgh::MBMetaH));
+  RESERVE(ctx->hd_ftype, (size_t)n);
+  RESERVE(ctx->d_coeffs, (size_t)n * nmb * 768);
+  RESERVE(ctx->d_meta, (size_t)n * nmb * sizeof(wg::MBMeta));
+  RESERVE(ctx->d_ftype, (size_t)n);
+  RESERVE(ctx->dy, (size_t)n * yp); RESERVE(ctx->du, (size_t)n * uvp); RESERVE(ctx->dv, (size_t)n * uvp);
+  // host: boolean decoding of headers, modes and coefficient tokens (serial per image, parallel across images)
+  std::vector<wgh::DecFrame> frames(n);
+  std::atomic<int> bad(-1);
+  parallel_for(n, threads_of(ctx), [&](int i) {
+    const uint8_t* p; size_t pl;
+    wgh::DecFrame& F = frames[i];
+    if (!wgh::find_vp8(streams[i], lens[i], &p, &pl)) { F.err = "webp: no VP8 chunk"; bad.store(i); return; }
+    if (!wgh::parse_frame(p, pl, &F, ctx->hd_coeffs.as<int16_t>() + (size_t)i * nmb * 384, ctx->hd_meta.as<wgh::MBMetaH>() + (size_t)i * nmb,
+                          mbw, mbh)) { bad.store(i); return; }
+    if (F.width != width || F.height != height) { F.err = "batch decode needs identical dimensions"; bad.store(i); return; }
+    ctx->hd_ftype.as<uint8_t>()[i] = (uint8_t)F.filter_type;
+  });
+  if (bad.load() >= 0) FAIL(WGPU_ERR_BITSTREAM, std::string("image ") + std::to_string(bad.load()) + ": " + (frames[bad.load()].err ? frames[bad.load()].err : "parse error"));
+  CK(cudaMemcpyAsync(ctx->d_coeffs.p, ctx->hd_coeffs.p, (size_t)n * nmb * 768, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_meta.p, ctx->hd_meta.p, (size_t)n * nmb * sizeof(wg::MBMeta), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_ftype.p, ctx->hd_ftype.p, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  wg::DecKernelParams P;
+  P.coeffs = ctx->d_coeffs.as<int16_t>(); P.meta = ctx->d_meta.as<wg::MBMeta>();
+  P.y = ctx->dy.as<uint8_t>(); P.u = ctx->du.as<uint8_t>(); P.v = ctx->dv.as<uint8_t>();
+  P.y_plane = yp; P.uv_plane = uvp; P.filter_type = ctx->d_ftype.as<uint8_t>();
+  P.n_images = n; P.mb_w = mbw; P.mb_h = mbh;
+  int rc;
+  if ((rc = dec_launch_recon(ctx, P))) return rc;
+  bool any_filter = false;
+  for (int i = 0; i < n; ++i) any_filter |= frames[i].filter_type > 0;
+  if (any_filter && (rc = dec_launch_filter(ctx, P))) return rc;
+  if (nrgba) {
+    RESERVE(ctx->d_nrgba, (size_t)n * width * height * 4);
+    if ((rc = launch_upsample(ctx, n, width, height, P.y, mbw * 16, P.u, P.v, mbw * 8, yp, uvp, nullptr, ctx->d_nrgba.as<uint8_t>()))) return rc;
+  }
+  if (y) CK(cudaMemcpy2DAsync(y, y_plane_stride, P.y, yp, yp, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (u) CK(cudaMemcpy2DAsync(u, uv_plane_stride, P.u, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v) CK(cudaMemcpy2DAsync(v, uv_plane_stride, P.v, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nrgba) {
+    const size_t img = (size_t)width * height * 4;
+    CK(cudaMemcpy2DAsync(nrgba, nrgba_image_stride, ctx->d_nrgba.p, img, img, n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WGPU_OK;
+}
+
+// ======================================================================================== stage-level
+int wgpu_import_rgba(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int height, int stride, size_t image_stride, int has_alpha,
+                     uint8_t* y, uint8_t* u, uint8_t* v) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  int rc = wgpu_enc_upload(ctx, rgba, n, width, height, stride, image_stride);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  wgpu_enc_options_default(&ctx->e_opt, 75);
+  ctx->e_opt.has_alpha = has_alpha;
+  if ((rc = enc_reserve(ctx))) return rc;
+  if ((rc = enc_launch_import(ctx))) return rc;
+  const size_t nmb = (size_t)ctx->e_mbw * ctx->e_mbh;
+  if (y) CK(cudaMemcpyAsync(y, ctx->sy.p, (size_t)n * nmb * 256, cudaMemcpyDeviceToHost, ctx->stream));
+  if (u) CK(cudaMemcpyAsync(u, ctx->su.p, (size_t)n * nmb * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v) CK(cudaMemcpyAsync(v, ctx->sv.p, (size_t)n * nmb * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WGPU_OK;
+}
+
+int wgpu_upsample_nrgba(wgpu_ctx* ctx, int n, int width, int height, const uint8_t* y, int y_stride, const uint8_t* u, const uint8_t* v,
+                        int uv_stride, size_t y_plane_stride, size_t uv_plane_stride, const uint8_t* alpha, uint8_t* nrgba) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!y || !u || !v || !nrgba || n <= 0 || width <= 0 || height <= 0 || y_stride < width || uv_stride < (width + 1) / 2)
+    FAIL(WGPU_ERR_INVALID, "wgpu_upsample_nrgba: bad arguments");
+  CK(cudaSetDevice(ctx->dev));
+  const int ch = (height + 1) / 2;
+  const size_t ysz = (size_t)(n - 1) * y_plane_stride + (size_t)(height - 1) * y_stride + width;
+  const size_t csz = (size_t)(n - 1) * uv_plane_stride + (size_t)(ch - 1) * uv_stride + (width + 1) / 2;
+  RESERVE(ctx->dy, ysz); RESERVE(ctx->du, csz); RESERVE(ctx->dv, csz);
+  RESERVE(ctx->d_nrgba, (size_t)n * width * height * 4);
+  CK(cudaMemcpyAsync(ctx->dy.p, y, ysz, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->du.p, u, csz, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->dv.p, v, csz, cudaMemcpyHostToDevice, ctx->stream));
+  const uint8_t* d_alpha = nullptr;
+  if (alpha) {
+    RESERVE(ctx->d_alpha, (size_t)n * width * height);
+    CK(cudaMemcpyAsync(ctx->d_alpha.p, alpha, (size_t)n * width * height, cudaMemcpyHostToDevice, ctx->stream));
+    d_alpha = ctx->d_alpha.as<uint8_t>();
+  }
+  int rc = launch_upsample(ctx, n, width, height, ctx->dy.as<uint8_t>(), y_stride, ctx->du.as<uint8_t>(), ctx->dv.as<uint8_t>(), uv_stride,
+                           y_plane_stride, uv_plane_stride, d_alpha, ctx->d_nrgba.as<uint8_t>());
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(nrgba, ctx->d_nrgba.p, (size_t)n * width * height * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WGPU_OK;
+}
+
+static int launch_metrics(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int width, int height, int stride, size_t plane_stride) {
+  wg::MetricsParams mp;
+  mp.a = a; mp.b = b; mp.plane_stride = plane_stride; mp.stride = stride; mp.width = width; mp.height = height; mp.n = n;
+  mp.tiles_x = (width + 31) / 32; mp.tiles_y = (height + 7) / 8;
+  const int tiles = mp.tiles_x * mp.tiles_y;
+  RESERVE(ctx->m_sse_part, (size_t)n * tiles * 8); RESERVE(ctx->m_ssim_part, (size_t)n * tiles * 8);
+  RESERVE(ctx->m_sse, (size_t)n * 8); RESERVE(ctx->m_ssim, (size_t)n * 8);
+  mp.sse_part = ctx->m_sse_part.as<unsigned long long>(); mp.ssim_part = ctx->m_ssim_part.as<double>();
+  wg::metrics_kernel<<<(unsigned)(n * tiles), 256, 0, ctx->stream>>>(mp);
+  wg::metrics_reduce_kernel<<<n, 256, 0, ctx->stream>>>(mp.sse_part, mp.ssim_part, tiles, ctx->m_sse.as<unsigned long long>(), ctx->m_ssim.as<double>());
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  return WGPU_OK;
+}
+
+int wgpu_plane_metrics(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int width, int height, int stride, size_t plane_stride,
+                       uint64_t* sse, double* ssim_sum) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!a || !b || n <= 0 || width <= 0 || height <= 0 || stride < width) FAIL(WGPU_ERR_INVALID, "wgpu_plane_metrics: bad arguments");
+  CK(cudaSetDevice(ctx->dev));
+  const size_t sz = (size_t)(n - 1) * plane_stride + (size_t)(height - 1) * stride + width;
+  RESERVE(ctx->m_a, sz); RESERVE(ctx->m_b, sz);
+  CK(cudaMemcpyAsync(ctx->m_a.p, a, sz, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->m_b.p, b, sz, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = launch_metrics(ctx, n, ctx->m_a.as<uint8_t>(), ctx->m_b.as<uint8_t>(), width, height, stride, plane_stride);
+  if (rc) return rc;
+  if (sse) CK(cudaMemcpyAsync(sse, ctx->m_sse.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ssim_sum) CK(cudaMemcpyAsync(ssim_sum, ctx->m_ssim.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WGPU_OK;
+}
+
+double wgpu_psnr_from_sse(uint64_t sse, uint64_t count) {  // PSNRFromSSE (internal/dsp/ssim.go:163)
+  if (sse == 0 || count == 0) return 99.0;
+  return 10.0 * log10(255.0 * 255.0 / ((double)sse / (double)count));
+}
+
+// ======================================================================================== dsp batch surface
+namespace {
+struct Scratch {  // per-call device scratch for the per-block operator surface (parity-test entry points)
+  std::vector<void*> ptrs;
+  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+  void* get(size_t bytes) { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr; ptrs.push_back(p); return p; }
+};
+}  // namespace
+#define DSP_BEGIN                                                                      \
+  if (!ctx) return WGPU_ERR_INVALID;                                                   \
+  std::lock_guard<std::mutex> lk(ctx->mu);                                             \
+  if (n <= 0) FAIL(WGPU_ERR_INVALID, "dsp batch: n must be positive");                 \
+  CK(cudaSetDevice(ctx->dev));                                                         \
+  Scratch S;                                                                           \
+  const unsigned grid = (unsigned)((n + 127) / 128)
+#define DSP_IN(var, host, bytes)                                                        \
+  auto* var = reinterpret_cast<decltype(host)>(S.get(bytes));                           \
+  if (!var) FAIL(WGPU_ERR_NOMEM, "dsp batch: device allocation failed");                \
+  CK(cudaMemcpyAsync((void*)var, host, bytes, cudaMemcpyHostToDevice, ctx->stream))
+#define DSP_OUT(var, type, bytes)                                                       \
+  type* var = reinterpret_cast<type*>(S.get(bytes));                                    \
+  if (!var) FAIL(WGPU_ERR_NOMEM, "dsp batch: device allocation failed")
+#define DSP_END(dev, host, bytes)                                                       \
+  ctx->launches++;                                                                      \
+  CK(cudaGetLastError());                                                               \
+  CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream))
+#define DSP_SYNC CK(cudaStreamSynchronize(ctx->stream)); return WGPU_OK
+
+int wgpu_dsp_ftransform_batch(wgpu_ctx* ctx, int n, const uint8_t* src, const uint8_t* ref, int16_t* out) {
+  DSP_BEGIN;
+  DSP_IN(d_src, src, (size_t)n * 16); DSP_IN(d_ref, ref, (size_t)n * 16); DSP_OUT(d_out, int16_t, (size_t)n * 32);
+  wg::dsp_ftransform_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_src, d_ref, d_out);
+  DSP_END(d_out, out, (size_t)n * 32);
+  DSP_SYNC;
+}
+int wgpu_dsp_itransform_batch(wgpu_ctx* ctx, int n, const uint8_t* ref, const int16_t* in, uint8_t* dst) {
+  DSP_BEGIN;
+  DSP_IN(d_ref, ref, (size_t)n * 16); DSP_IN(d_in, in, (size_t)n * 32); DSP_OUT(d_out, uint8_t, (size_t)n * 16);
+  wg::dsp_itransform_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_ref, d_in, d_out);
+  DSP_END(d_out, dst, (size_t)n * 16);
+  DSP_SYNC;
+}
+int wgpu_dsp_fwht_batch(wgpu_ctx* ctx, int n, const int16_t* in, int16_t* out) {
+  DSP_BEGIN;
+  DSP_IN(d_in, in, (size_t)n * 32); DSP_OUT(d_out, int16_t, (size_t)n * 32);
+  wg::dsp_fwht_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_in, d_out);
+  DSP_END(d_out, out, (size_t)n * 32);
+  DSP_SYNC;
+}
+int wgpu_dsp_iwht_batch(wgpu_ctx* ctx, int n, const int16_t* in, int16_t* out) {
+  DSP_BEGIN;
+  DSP_IN(d_in, in, (size_t)n * 32); DSP_OUT(d_out, int16_t, (size_t)n * 32);
+  wg::dsp_iwht_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_in, d_out);
+  DSP_END(d_out, out, (size_t)n * 32);
+  DSP_SYNC;
+}
+int wgpu_dsp_sse4x4_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int32_t* out) {
+  DSP_BEGIN;
+  DSP_IN(d_a, a, (size_t)n * 16); DSP_IN(d_b, b, (size_t)n * 16); DSP_OUT(d_out, int32_t, (size_t)n * 4);
+  wg::dsp_sse4x4_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_a, d_b, d_out);
+  DSP_END(d_out, out, (size_t)n * 4);
+  DSP_SYNC;
+}
+int wgpu_dsp_tdisto4x4_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int32_t* out) {
+  DSP_BEGIN;
+  DSP_IN(d_a, a, (size_t)n * 16); DSP_IN(d_b, b, (size_t)n * 16); DSP_OUT(d_out, int32_t, (size_t)n * 4);
+  wg::dsp_tdisto4x4_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_a, d_b, d_out);
+  DSP_END(d_out, out, (size_t)n * 4);
+  DSP_SYNC;
+}
+int wgpu_dsp_pred4_batch(wgpu_ctx* ctx, int n, const uint8_t* ctx13, uint8_t* out) {
+  DSP_BEGIN;
+  (void)grid;
+  DSP_IN(d_c, ctx13, (size_t)n * 13); DSP_OUT(d_out, uint8_t, (size_t)n * 160);
+  wg::dsp_pred4_kernel<<<(unsigned)((n * 10 + 127) / 128), 128, 0, ctx->stream>>>(n * 10, d_c, d_out);
+  DSP_END(d_out, out, (size_t)n * 160);
+  DSP_SYNC;
+}
+static wg::SegQuant make_seg_quant(int dc_q, int ac_q, int type, int sharpen) {
+  wgh::SegQuant h;
+  wgh::expand_quant(&h, dc_q, ac_q, type);
+  static const int kSharp[16] = {0, 30, 60, 90, 30, 60, 90, 90, 60, 90, 90, 90, 90, 90, 90, 90};
+  if (sharpen) for (int i = 0; i < 16; ++i) h.sharpen[i] = (int16_t)((kSharp[i] * (i == 0 ? dc_q : ac_q)) >> 11);
+  wg::SegQuant d;
+  static_assert(sizeof(d) == sizeof(h), "SegQuant layout");
+  memcpy(&d, &h, sizeof(d));
+  return d;
+}
+static wg::TabPtrs tab_ptrs(const wgpu_ctx* ctx) {
+  wg::TabPtrs t;
+  t.ecost = ctx->t_ecost.as<uint16_t>(); t.lfc = ctx->t_lfc.as<uint16_t>(); t.lcodes = ctx->t_lcodes.as<uint16_t>();
+  t.proba = ctx->t_proba.as<uint8_t>();
+  return t;
+}
+int wgpu_dsp_quantize_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, int ac_q, int type, int sharpen, int first, int16_t* out,
+                            int32_t* nz) {
+  DSP_BEGIN;
+  if (dc_q <= 0 || ac_q <= 0 || type < 0 || type > 2) FAIL(WGPU_ERR_INVALID, "dsp quantize: bad quantiser");
+  DSP_IN(d_in, in, (size_t)n * 32); DSP_OUT(d_out, int16_t, (size_t)n * 32); DSP_OUT(d_nz, int32_t, (size_t)n * 4);
+  wg::dsp_quantize_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_in, make_seg_quant(dc_q, ac_q, type, sharpen), first, d_out, d_nz);
+  DSP_END(d_out, out, (size_t)n * 32);
+  CK(cudaMemcpyAsync(nz, d_nz, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DSP_SYNC;
+}
+int wgpu_dsp_trellis_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, int ac_q, int qtype, int sharpen, int first, int ctx_type,
+                           const int32_t* ctx0, int lambda, int16_t* out, int32_t* nz) {
+  DSP_BEGIN;
+  if (dc_q <= 0 || ac_q <= 0 || qtype < 0 || qtype > 2 || ctx_type < 0 || ctx_type > 3) FAIL(WGPU_ERR_INVALID, "dsp trellis: bad arguments");
+  DSP_IN(d_in, in, (size_t)n * 32); DSP_IN(d_ctx, ctx0, (size_t)n * 4);
+  DSP_OUT(d_out, int16_t, (size_t)n * 32); DSP_OUT(d_nz, int32_t, (size_t)n * 4);
+  wg::dsp_trellis_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_in, make_seg_quant(dc_q, ac_q, qtype, sharpen), first, ctx_type, d_ctx, lambda,
+                                                        tab_ptrs(ctx), d_out, d_nz);
+  DSP_END(d_out, out, (size_t)n * 32);
+  CK(cudaMemcpyAsync(nz, d_nz, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  DSP_SYNC;
+}
+int wgpu_dsp_token_cost_batch(wgpu_ctx* ctx, int n, const int16_t* levels, const int32_t* nz, int ctx_type, const int32_t* ctx0, int first,
+                              int32_t* out) {
+  DSP_BEGIN;
+  if (ctx_type < 0 || ctx_type > 3) FAIL(WGPU_ERR_INVALID, "dsp token cost: bad type");
+  DSP_IN(d_lv, levels, (size_t)n * 32); DSP_IN(d_nz, nz, (size_t)n * 4); DSP_IN(d_ctx, ctx0, (size_t)n * 4);
+  DSP_OUT(d_out, int32_t, (size_t)n * 4);
+  wg::dsp_token_cost_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_lv, d_nz, ctx_type, d_ctx, first, tab_ptrs(ctx), d_out);
+  DSP_END(d_out, out, (size_t)n * 4);
+  DSP_SYNC;
+}
+
+// ======================================================================================== measurement
+int wgpu_timer_begin(wgpu_ctx* ctx) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  return WGPU_OK;
+}
+int wgpu_timer_end(wgpu_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return WGPU_ERR_INVALID;
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return WGPU_OK;
+}
+uint64_t wgpu_launch_count(const wgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
