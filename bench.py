@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): lossy encode & decode Mpix/s, 1536x1024 q75 m4, batch of 256 images per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic images:
+  value : encode throughput with the RGBA batch already resident in HBM (import + analysis + host segment plan +
+          wavefront mode search; per-macroblock modes/levels left in HBM), CUDA events on the library's stream
+  e2e   : the same batch through the reference-facing call wgpu_encode_batch (webp.Encode's batch twin): pinned
+          host RGBA in, H2D, kernels, D2H of modes/levels, host token/bool coding, WebP files out
+  decode: the streams produced above through wgpu_dec_* / wgpu_decode_batch (host parse, recon + loop filter +
+          fancy upsampling on the GPU, NRGBA back to the host)
+Images shard across ranks with no collective (weak scaling: every rank encodes its own batch).
+--impl reference times the oracle (a C++ port of the reference's CPU path; no Go toolchain in this image) with all
+host threads on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1536, 1024
+ALG_BYTES_PER_PX = {"mode_search": 6.44, "import": 5.5, "analysis": 1.5, "recon": 4.66, "filter": 3.0, "upsample": 5.5}
+
+
+def measured_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference encoder, one image per thread on all host cores, bounded sample."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    from webp_b200.synth import synth_batch
+    cores = os.cpu_count() or 1
+    sample = max(cores, 8)  # images per step: >= one per thread, ~10-20 s per step on this workload
+    imgs = synth_batch(sample, W, H, distinct=min(sample, 24))
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        oracle_lib.encode_batch(imgs[:cores], threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_lib.encode_batch(imgs, threads=cores)
+    dt = time.perf_counter() - t0
+    v = sample * W * H * args.steps / dt / 1e6
+    line = {"impl": "reference", "metric": "lossy encode Mpix/s (1536x1024 q75 m4, bit-exact)", "value": v, "unit": "Mpix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+            "config": {"workload": "1536x1024 RGBA lossy encode q75 method 4 (reference parallel-path semantics)", "sample_images_per_step": sample},
+            "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                             "sample": "%d images of the 1536x1024 q75 m4 workload per step, one image per thread (C++ oracle, -O2)" % sample},
+            "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (BASELINE configs[1]: 256)")
+    ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    from webp_b200 import native
+    from webp_b200.synth import synth_batch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    L = native.lib()
+    ctx = native.Context(local)
+    n, K = args.batch, args.steps
+    px_step = n * W * H
+    # pinned host staging: input batch and output files
+    in_bytes = n * W * H * 4
+    cap = W * H  # per-file capacity (bytes)
+    h_in = L.wgpu_host_alloc(ctx.handle, in_bytes)
+    h_out = L.wgpu_host_alloc(ctx.handle, n * cap)
+    if not h_in or not h_out:
+        raise SystemExit("pinned allocation failed")
+    imgs = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_uint8)), shape=(n, H, W, 4))
+    imgs[:] = synth_batch(n, W, H, distinct=24, first_index=rank * 24)
+    out = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_uint8)), shape=(n, cap))
+    sizes = np.zeros(n, np.uint64)
+    opt = native.EncOptions()
+    L.wgpu_enc_options_default(opt, 75)
+
+    def encode_e2e():
+        ctx.check(L.wgpu_encode_batch(ctx.handle, h_in, n, W, H, W * 4, W * H * 4, C.byref(opt), h_out, cap, sizes.ctypes.data))
+
+    for _ in range(max(args.warmup, 3)):
+        encode_e2e()
+    clocks = ClockSampler(local)
+    clocks.start()
+    # ---- value: device-resident encode (inputs already in HBM)
+    ctx.check(L.wgpu_enc_upload(ctx.handle, h_in, n, W, H, W * 4, W * H * 4))
+    ctx.check(L.wgpu_sync(ctx.handle))
+    launches0 = ctx.launch_count()
+    ms = C.c_float()
+    barrier()
+    ctx.check(L.wgpu_timer_begin(ctx.handle))
+    for _ in range(K):
+        ctx.check(L.wgpu_enc_device(ctx.handle, C.byref(opt)))
+    ctx.check(L.wgpu_timer_end(ctx.handle, C.byref(ms)))
+    barrier()
+    dev_ms = max_over_ranks(ms.value)
+    launches = ctx.launch_count() - launches0
+    value = px_step * K * world / (dev_ms * 1e-3) / 1e6
+    # ---- e2e: host RGBA -> WebP files through the public batch call
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        encode_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = px_step * K * world / e2e_s / 1e6
+    nmb = ((W + 15) // 16) * ((H + 15) // 16)
+    h2d = in_bytes + n * nmb + n * 4 * 160  # RGBA + segment map + per-image segment parameters
+    d2h = 2 * n * nmb + n * nmb * (48 + 800)  # analysis alphas + per-MB header/levels
+    # ---- per-kernel device times for the roofline (CUDA events on the library's stream)
+    stage_ms = {}
+    for name, sid, reps in (("import", 0, 5), ("analysis", 1, 5), ("mode_search", 2, max(1, min(K, 3)))):
+        ctx.check(L.wgpu_enc_stage_time(ctx.handle, C.byref(opt), sid, reps, C.byref(ms)))
+        stage_ms[name] = ms.value
+    peak, peak_kind = measured_peak_gbs()
+    dom = "mode_search"
+    ach = ALG_BYTES_PER_PX[dom] * px_step / (stage_ms[dom] * 1e-3) / 1e9
+    waves = (W // 16) + 2 * (H // 16 - 1)
+    roofline = {"bound": "hbm", "kernel": "encode_wave_kernel (%d wave launches per step, timed together)" % waves, "achieved": ach,
+                "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "note": "integer-issue bound, not HBM bound: ~940 int-ops/px (SURVEY.md 8d) vs 6.44 algorithmic B/px; see DESIGN.md",
+                "stages_ms": stage_ms,
+                "stages_gbs": {k: ALG_BYTES_PER_PX[k] * px_step / (v * 1e-3) / 1e9 for k, v in stage_ms.items()}}
+    result = {"metric": "lossy encode & decode Mpix/s (1536x1024 q75 m4), bit-exact", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": K,
+              "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "u8/int32", "data": "synthetic",
+              "config": {"workload": "synthetic 1536x1024 RGBA lossy encode q75 method 4, batch of %d images per GPU (BASELINE configs[1])" % n,
+                         "batch_per_gpu": n, "l2": "inputs (%.0f MB RGBA per step) exceed the 126 MB L2" % (in_bytes / 1e6),
+                         "parallelism": "images sharded across %d GPU(s), no collective" % world},
+              "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / K * 1e3,
+                      "compressed_bytes_per_step": int(sizes.sum())},
+              "gpu_launches": int(launches), "roofline": roofline}
+    # ---- decode of the streams just produced (BASELINE configs[2])
+    if not args.no_decode:
+        files = [out[i, :int(sizes[i])].tobytes() for i in range(n)]
+        ptrs = (C.c_char_p * n)(*files)
+        lens = (C.c_size_t * n)(*[len(f) for f in files])
+        h_rgba = L.wgpu_host_alloc(ctx.handle, in_bytes)
+        for _ in range(2):
+            ctx.check(L.wgpu_decode_batch(ctx.handle, ptrs, lens, n, None, None, None, 0, 0, h_rgba, W * H * 4))
+        ctx.check(L.wgpu_dec_parse(ctx.handle, ptrs, lens, n, None, None))
+        ctx.check(L.wgpu_sync(ctx.handle))
+        l0 = ctx.launch_count()
+        barrier()
+        ctx.check(L.wgpu_timer_begin(ctx.handle))
+        for _ in range(K):
+            ctx.check(L.wgpu_dec_device(ctx.handle, 1))
+        ctx.check(L.wgpu_timer_end(ctx.handle, C.byref(ms)))
+        barrier()
+        dms = max_over_ranks(ms.value)
+        dl = ctx.launch_count() - l0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            ctx.check(L.wgpu_decode_batch(ctx.handle, ptrs, lens, n, None, None, None, 0, 0, h_rgba, W * H * 4))
+        barrier()
+        ds = max_over_ranks(time.perf_counter() - t0)
+        result["decode"] = {"value": px_step * K * world / (dms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": dms / K, "gpu_launches": int(dl),
+                            "e2e": {"value": px_step * K * world / ds / 1e6, "unit": "Mpix/s", "ms_per_step": ds / K * 1e3,
+                                    "h2d_bytes_per_step": n * nmb * (768 + 32), "d2h_bytes_per_step": in_bytes},
+                            "config": {"workload": "decode of the %d streams above -> recon + loop filter + fancy upsampling to NRGBA (BASELINE configs[2])" % n},
+                            "roofline": {"bound": "hbm", "kernel": "recon_wave + filter_wave + upsample_nrgba (whole device step)",
+                                         "achieved": (ALG_BYTES_PER_PX["recon"] + ALG_BYTES_PER_PX["filter"] + ALG_BYTES_PER_PX["upsample"]) * px_step / (dms / K * 1e-3) / 1e9,
+                                         "peak": peak, "unit": "GB/s"}}
+        result["decode"]["roofline"]["frac"] = result["decode"]["roofline"]["achieved"] / peak
+        L.wgpu_host_free(ctx.handle, h_rgba)
+    result["clocks"] = clocks.stop()
+    # ---- CPU baseline beside it: the oracle port on this box's host cores, bounded sample, rank 0 at N=1 only
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        cores = os.cpu_count() or 1
+        sample = max(cores, 8)
+        sub = np.ascontiguousarray(imgs[:sample] if sample <= n else synth_batch(sample, W, H))
+        t0 = time.perf_counter()
+        oracle_lib.encode_batch(sub, threads=cores)
+        dt = time.perf_counter() - t0
+        result["cpu_baseline"] = {"value": sample * W * H / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                                  "sample": "%d images of the same batch, one image per thread, %d threads (C++ oracle -O2; the Go reference cannot be built here)" % (sample, cores)}
+    L.wgpu_host_free(ctx.handle, h_in)
+    L.wgpu_host_free(ctx.handle, h_out)
+    if rank == 0:
+        print(json.dumps(result), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

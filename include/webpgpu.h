@@ -104,6 +104,15 @@ int wgpu_decode_batch(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t
                       uint8_t* u, uint8_t* v, size_t y_plane_stride, size_t uv_plane_stride, uint8_t* nrgba,
                       size_t nrgba_image_stride);
 
+/* Staged form of the same job (bench.py separates host parse + H2D / device / D2H):
+ *   parse  : host boolean decoding of every stream into per-macroblock coefficients + modes, then H2D
+ *   device : reconstruction waves, loop-filter waves, optional fancy upsampling; results stay in HBM
+ *   fetch  : D2H of planes and/or NRGBA (any pointer may be NULL) */
+int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* lens, int n, int* width, int* height);
+int wgpu_dec_device(wgpu_ctx* ctx, int want_nrgba);
+int wgpu_dec_fetch(wgpu_ctx* ctx, uint8_t* y, uint8_t* u, uint8_t* v, size_t y_plane_stride, size_t uv_plane_stride,
+                   uint8_t* nrgba, size_t nrgba_image_stride);
+
 /* ---- stage-level entry points (host buffers in/out) ------------------------------------ */
 int wgpu_import_rgba(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int height, int stride,
                      size_t image_stride, int has_alpha, uint8_t* y, uint8_t* u, uint8_t* v);

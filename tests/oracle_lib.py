@@ -154,29 +154,7 @@ def plane_ssim_map(a, b):
 
 
 # ------------------------------------------------------------------ synthetic images
-def synth_image(w, h, index, kind=None):
-    """Deterministic opaque RGBA test image; three content classes (gradient / textured / noisy)."""
-    kind = index % 3 if kind is None else kind
-    yy, xx = np.mgrid[0:h, 0:w].astype(np.int64)
-    rng = np.random.RandomState(0xC0FFEE + index)
-    if kind == 0:  # smooth gradients (root encode_test.go:1496 richTestImage shape)
-        r = xx * 255 // max(w, 1)
-        g = yy * 255 // max(h, 1)
-        b = (xx + yy) * 255 // max(w + h, 1)
-    elif kind == 1:  # gradient + band-limited noise + hard-edged rectangles
-        base = rng.randint(-24, 25, size=((h + 7) // 8 + 1, (w + 7) // 8 + 1, 3))
-        noise = np.kron(base, np.ones((8, 8, 1), np.int64))[:h, :w]
-        r = xx * 255 // max(w, 1) + noise[..., 0]
-        g = yy * 255 // max(h, 1) + noise[..., 1]
-        b = 128 + noise[..., 2]
-        for _ in range(12):
-            x0, y0 = rng.randint(0, w), rng.randint(0, h)
-            x1, y1 = min(w, x0 + rng.randint(4, max(5, w // 4))), min(h, y0 + rng.randint(4, max(5, h // 4)))
-            col = rng.randint(0, 256, 3)
-            r[y0:y1, x0:x1], g[y0:y1, x0:x1], b[y0:y1, x0:x1] = col
-    else:  # noisy image (race_test.go:78 noisyImage shape)
-        r = (xx * 7 + yy * 13) % 256 + rng.randint(-16, 17, size=(h, w))
-        g = (xx * 3 + yy * 5) % 256 + rng.randint(-16, 17, size=(h, w))
-        b = (xx ^ yy) % 256
-    img = np.stack([r, g, b, np.full_like(r, 255)], axis=-1)
-    return np.clip(img, 0, 255).astype(np.uint8)
+import sys as _sys
+if ROOT not in _sys.path:
+    _sys.path.insert(0, ROOT)
+from webp_b200.synth import synth_image  # noqa: E402,F401  (shared generator; pure numpy, no native code)

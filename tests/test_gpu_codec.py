@@ -117,14 +117,18 @@ def test_encode_rejections(gpu_ctx):
         webp_b200.EncodeBatch(img[None], _opts(Lossless=True), gpu_ctx)
 
 
-DEC_CASES = [(128, 96, {}), (100, 70, {}), (130, 71, dict(segments=1)), (128, 96, dict(filter_type=0, segments=1)),
-             (128, 96, dict(filter_strength=0)), (160, 112, dict(filter_sharpness=6, segments=1, filter_strength=100)),
-             (128, 128, dict(partitions=2, quality=90)), (768, 576, dict(segments=1)), (64, 64, dict(quality=10))]
+DEC_CASES = [(128, 96, (2, 1, 0), {}), (100, 70, (2, 1, 0), {}), (130, 71, (2, 1, 0), dict(segments=1)),
+             (128, 96, (2, 1, 0), dict(filter_type=0, segments=1)), (128, 96, (2, 1, 0), dict(filter_strength=0)),
+             (160, 112, (2, 1, 0), dict(filter_sharpness=6, segments=1, filter_strength=100)),
+             # multi-partition streams of images with skipped macroblocks are corrupt in the reference itself
+             # (encode_token.go:90 marks MB starts only for non-skipped MBs, DESIGN.md "reference quirks")
+             (128, 128, (2, 5, 8), dict(partitions=2, quality=90)), (128, 128, (2,), dict(partitions=3, quality=95)),
+             (768, 576, (2, 1, 0), dict(segments=1)), (64, 64, (2, 1, 0), dict(quality=10))]
 
 
-@pytest.mark.parametrize("w,h,kw", DEC_CASES)
-def test_decode_planes_and_nrgba(oracle, gpu_ctx, w, h, kw):
-    streams = [oracle.encode(oracle.synth_image(w, h, i), oracle.default_cfg(**kw)) for i in (2, 1, 0)]
+@pytest.mark.parametrize("w,h,idxs,kw", DEC_CASES)
+def test_decode_planes_and_nrgba(oracle, gpu_ctx, w, h, idxs, kw):
+    streams = [oracle.encode(oracle.synth_image(w, h, i), oracle.default_cfg(**kw)) for i in idxs]
     gw, gh, y, u, v, rgba = webp_b200.webp.decode_padded(streams, nrgba=True, ctx=gpu_ctx)
     assert (gw, gh) == (w, h)
     for i, s in enumerate(streams):
@@ -155,9 +159,13 @@ def test_decode_reference_fixtures_and_foreign_stream(oracle, gpu_ctx):
 
 def test_decode_errors(gpu_ctx, oracle):
     data = oracle.encode(oracle.synth_image(64, 64, 1))
-    with pytest.raises(native.WebPGPUError) as e:
+    with pytest.raises(webp_b200.WebPError):  # RIFF chunk longer than the file
         webp_b200.webp.decode_padded([data[:len(data) // 2]], ctx=gpu_ctx)
+    with pytest.raises(native.WebPGPUError) as e:  # raw VP8 frame cut in the token partition
+        webp_b200.webp.decode_padded([data[20:20 + (len(data) - 20) // 2]], ctx=gpu_ctx)
     assert e.value.code == native.ERR_BITSTREAM
+    with pytest.raises(RuntimeError):
+        oracle.decode(data[20:20 + (len(data) - 20) // 2])
     other = oracle.encode(oracle.synth_image(80, 64, 1))
     with pytest.raises(native.WebPGPUError):
         webp_b200.webp.decode_padded([data, other], ctx=gpu_ctx)

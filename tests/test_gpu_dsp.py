@@ -1,5 +1,7 @@
 """GPU parity, operator surface: every batched dsp entry point vs the oracle on the same seeded inputs, bit-exact.
 Pattern and input ranges follow internal/dsp/simd_test.go (pixels 0..255, coefficients +-1000 / +-2048, WHT +-256)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -10,7 +12,7 @@ N = 20000
 
 
 def _p(a):
-    return a.ctypes.data
+    return C.c_void_p(a.ctypes.data)
 
 
 def test_ftransform(oracle, gpu_ctx):

@@ -81,6 +81,8 @@ struct wgpu_ctx {
   // decoder state
   DevBuf d_coeffs, d_meta, d_ftype, dy, du, dv, d_nrgba, d_alpha;
   PinBuf hd_coeffs, hd_meta, hd_ftype, hd_planes, hd_nrgba;
+  int d_n = 0, d_w = 0, d_h = 0, d_mbw = 0, d_mbh = 0;
+  bool d_ready = false, d_any_filter = false, d_has_nrgba = false;
   // metrics
   DevBuf m_a, m_b, m_sse_part, m_ssim_part, m_sse, m_ssim;
 };
@@ -503,12 +505,12 @@ static int launch_upsample(wgpu_ctx* ctx, int n, int width, int height, const ui
   return WGPU_OK;
 }
 
-int wgpu_decode_batch(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* lens, int n, uint8_t* y, uint8_t* u, uint8_t* v,
-                      size_t y_plane_stride, size_t uv_plane_stride, uint8_t* nrgba, size_t nrgba_image_stride) {
+int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* lens, int n, int* width_out, int* height_out) {
   if (!ctx) return WGPU_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!streams || !lens || n <= 0) FAIL(WGPU_ERR_INVALID, "webp: nil reader");
   CK(cudaSetDevice(ctx->dev));
+  ctx->d_ready = false;
   // dimensions from the first stream; every stream of the batch must match
   const uint8_t* vp8; size_t vlen; const char* perr = nullptr;
   int width = 0, height = 0;
@@ -516,16 +518,13 @@ int wgpu_decode_batch(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t
     FAIL(WGPU_ERR_BITSTREAM, perr ? perr : "webp: no VP8 chunk");
   const int mbw = (width + 15) >> 4, mbh = (height + 15) >> 4;
   const size_t nmb = (size_t)mbw * mbh;
-  const size_t yp = nmb * 256, uvp = nmb * 64;
-  if ((y && y_plane_stride < yp) || ((u || v) && uv_plane_stride < uvp)) FAIL(WGPU_ERR_TOO_SMALL, "plane stride smaller than the padded plane");
-  if (nrgba && nrgba_image_stride < (size_t)width * height * 4) FAIL(WGPU_ERR_TOO_SMALL, "nrgba image stride too small");
   RESERVE(ctx->hd_coeffs, (size_t)n * nmb * 768);
   RESERVE(ctx->hd_meta, (size_t)n * nmb * sizeof(wgh::MBMetaH));
   RESERVE(ctx->hd_ftype, (size_t)n);
   RESERVE(ctx->d_coeffs, (size_t)n * nmb * 768);
   RESERVE(ctx->d_meta, (size_t)n * nmb * sizeof(wg::MBMeta));
   RESERVE(ctx->d_ftype, (size_t)n);
-  RESERVE(ctx->dy, (size_t)n * yp); RESERVE(ctx->du, (size_t)n * uvp); RESERVE(ctx->dv, (size_t)n * uvp);
+  RESERVE(ctx->dy, (size_t)n * nmb * 256); RESERVE(ctx->du, (size_t)n * nmb * 64); RESERVE(ctx->dv, (size_t)n * nmb * 64);
   // host: boolean decoding of headers, modes and coefficient tokens (serial per image, parallel across images)
   std::vector<wgh::DecFrame> frames(n);
   std::atomic<int> bad(-1);
@@ -542,29 +541,63 @@ int wgpu_decode_batch(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t
   CK(cudaMemcpyAsync(ctx->d_coeffs.p, ctx->hd_coeffs.p, (size_t)n * nmb * 768, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_meta.p, ctx->hd_meta.p, (size_t)n * nmb * sizeof(wg::MBMeta), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_ftype.p, ctx->hd_ftype.p, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->d_any_filter = false;
+  for (int i = 0; i < n; ++i) ctx->d_any_filter |= frames[i].filter_type > 0;
+  ctx->d_n = n; ctx->d_w = width; ctx->d_h = height; ctx->d_mbw = mbw; ctx->d_mbh = mbh;
+  ctx->d_ready = true;
+  if (width_out) *width_out = width;
+  if (height_out) *height_out = height;
+  return WGPU_OK;
+}
+
+int wgpu_dec_device(wgpu_ctx* ctx, int want_nrgba) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->d_ready) FAIL(WGPU_ERR_INVALID, "wgpu_dec_device called before wgpu_dec_parse");
+  CK(cudaSetDevice(ctx->dev));
+  const int n = ctx->d_n;
+  const size_t nmb = (size_t)ctx->d_mbw * ctx->d_mbh;
   wg::DecKernelParams P;
   P.coeffs = ctx->d_coeffs.as<int16_t>(); P.meta = ctx->d_meta.as<wg::MBMeta>();
   P.y = ctx->dy.as<uint8_t>(); P.u = ctx->du.as<uint8_t>(); P.v = ctx->dv.as<uint8_t>();
-  P.y_plane = yp; P.uv_plane = uvp; P.filter_type = ctx->d_ftype.as<uint8_t>();
-  P.n_images = n; P.mb_w = mbw; P.mb_h = mbh;
+  P.y_plane = nmb * 256; P.uv_plane = nmb * 64; P.filter_type = ctx->d_ftype.as<uint8_t>();
+  P.n_images = n; P.mb_w = ctx->d_mbw; P.mb_h = ctx->d_mbh;
   int rc;
   if ((rc = dec_launch_recon(ctx, P))) return rc;
-  bool any_filter = false;
-  for (int i = 0; i < n; ++i) any_filter |= frames[i].filter_type > 0;
-  if (any_filter && (rc = dec_launch_filter(ctx, P))) return rc;
-  if (nrgba) {
-    RESERVE(ctx->d_nrgba, (size_t)n * width * height * 4);
-    if ((rc = launch_upsample(ctx, n, width, height, P.y, mbw * 16, P.u, P.v, mbw * 8, yp, uvp, nullptr, ctx->d_nrgba.as<uint8_t>()))) return rc;
+  if (ctx->d_any_filter && (rc = dec_launch_filter(ctx, P))) return rc;
+  if (want_nrgba) {
+    RESERVE(ctx->d_nrgba, (size_t)n * ctx->d_w * ctx->d_h * 4);
+    if ((rc = launch_upsample(ctx, n, ctx->d_w, ctx->d_h, P.y, ctx->d_mbw * 16, P.u, P.v, ctx->d_mbw * 8, P.y_plane, P.uv_plane, nullptr,
+                              ctx->d_nrgba.as<uint8_t>()))) return rc;
   }
-  if (y) CK(cudaMemcpy2DAsync(y, y_plane_stride, P.y, yp, yp, n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (u) CK(cudaMemcpy2DAsync(u, uv_plane_stride, P.u, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (v) CK(cudaMemcpy2DAsync(v, uv_plane_stride, P.v, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (nrgba) {
-    const size_t img = (size_t)width * height * 4;
-    CK(cudaMemcpy2DAsync(nrgba, nrgba_image_stride, ctx->d_nrgba.p, img, img, n, cudaMemcpyDeviceToHost, ctx->stream));
-  }
+  ctx->d_has_nrgba = want_nrgba != 0;
+  return WGPU_OK;
+}
+
+int wgpu_dec_fetch(wgpu_ctx* ctx, uint8_t* y, uint8_t* u, uint8_t* v, size_t y_plane_stride, size_t uv_plane_stride, uint8_t* nrgba,
+                   size_t nrgba_image_stride) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->d_ready) FAIL(WGPU_ERR_INVALID, "wgpu_dec_fetch called before wgpu_dec_parse");
+  CK(cudaSetDevice(ctx->dev));
+  const int n = ctx->d_n;
+  const size_t nmb = (size_t)ctx->d_mbw * ctx->d_mbh, yp = nmb * 256, uvp = nmb * 64, img = (size_t)ctx->d_w * ctx->d_h * 4;
+  if ((y && y_plane_stride < yp) || ((u || v) && uv_plane_stride < uvp)) FAIL(WGPU_ERR_TOO_SMALL, "plane stride smaller than the padded plane");
+  if (nrgba && (!ctx->d_has_nrgba || nrgba_image_stride < img)) FAIL(WGPU_ERR_TOO_SMALL, "nrgba not produced or image stride too small");
+  if (y) CK(cudaMemcpy2DAsync(y, y_plane_stride, ctx->dy.p, yp, yp, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (u) CK(cudaMemcpy2DAsync(u, uv_plane_stride, ctx->du.p, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (v) CK(cudaMemcpy2DAsync(v, uv_plane_stride, ctx->dv.p, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nrgba) CK(cudaMemcpy2DAsync(nrgba, nrgba_image_stride, ctx->d_nrgba.p, img, img, n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return WGPU_OK;
+}
+
+int wgpu_decode_batch(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* lens, int n, uint8_t* y, uint8_t* u, uint8_t* v,
+                      size_t y_plane_stride, size_t uv_plane_stride, uint8_t* nrgba, size_t nrgba_image_stride) {
+  int rc = wgpu_dec_parse(ctx, streams, lens, n, nullptr, nullptr);
+  if (rc) return rc;
+  if ((rc = wgpu_dec_device(ctx, nrgba != nullptr))) return rc;
+  return wgpu_dec_fetch(ctx, y, u, v, y_plane_stride, uv_plane_stride, nrgba, nrgba_image_stride);
 }
 
 // ======================================================================================== stage-level

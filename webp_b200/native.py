@@ -61,6 +61,9 @@ def lib():
         L.wgpu_enc_fetch.argtypes = [vp, C.c_int] + [vp] * 11
         L.wgpu_decode_info.argtypes = [u8p, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.wgpu_decode_batch.argtypes = [vp, vp, vp, C.c_int, u8p, u8p, u8p, sz, sz, u8p, sz]
+        L.wgpu_dec_parse.argtypes = [vp, vp, vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.wgpu_dec_device.argtypes = [vp, C.c_int]
+        L.wgpu_dec_fetch.argtypes = [vp, u8p, u8p, u8p, sz, sz, u8p, sz]
         L.wgpu_import_rgba.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, sz, C.c_int, u8p, u8p, u8p]
         L.wgpu_upsample_nrgba.argtypes = [vp, C.c_int, C.c_int, C.c_int, u8p, C.c_int, u8p, u8p, C.c_int, sz, sz, u8p, u8p]
         L.wgpu_plane_metrics.argtypes = [vp, C.c_int, u8p, u8p, C.c_int, C.c_int, C.c_int, sz, vp, vp]
