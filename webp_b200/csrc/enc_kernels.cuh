@@ -27,7 +27,7 @@ struct EncKernelParams {
   uint8_t* out_hdr;             // [n][nmb][48]: mb_type,i16,uv,segment,skip,nz_dc,0,0, modes[16], nz[24]
   int16_t* out_coeffs;          // [n][nmb][400]
   const uint16_t* i4_costs;     // [10][10][10]
-  const uint16_t* ecost; const uint16_t* lfc; const uint16_t* lcodes; const uint8_t* proba;  // global tables
+  const uint16_t* lc; const uint16_t* eob; const uint16_t* lfc;  // folded cost tables (vp8_dev.cuh CostTabs), global
   int n_images, width, height, mb_w, mb_h;
   int method, max_i4_modes;
   size_t y_plane, uv_plane;     // bytes per image plane
@@ -45,7 +45,7 @@ struct I4Cand {
   uint8_t rec[16];
 };
 struct MBShared {
-  uint8_t in[YUV_SIZE];
+  uint8_t in[384];  // source macroblock, compact: Y 16x16 (stride 16), U 8x8 at 256, V 8x8 at 320 (stride 8)
   uint8_t out[YUV_SIZE];
   uint8_t out2[YUV_SIZE];
   int16_t lev[24][16];
@@ -79,6 +79,22 @@ __device__ __forceinline__ void load4x4(const uint8_t* p, int* d) {  // p 4-byte
     d[4 * j + 2] = (w >> 16) & 0xff;
     d[4 * j + 3] = w >> 24;
   }
+}
+template <int STRIDE>
+__device__ __forceinline__ void load4x4s(const uint8_t* p, int* d) {  // p 4-byte aligned, compact stride
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(p + j * STRIDE);
+    d[4 * j + 0] = w & 0xff;
+    d[4 * j + 1] = (w >> 8) & 0xff;
+    d[4 * j + 2] = (w >> 16) & 0xff;
+    d[4 * j + 3] = w >> 24;
+  }
+}
+// source block b of the compact MBShared::in: luma 0..15, chroma 16..23 (U 16..19, V 20..23)
+__device__ __forceinline__ void load_src_block(const uint8_t* in, int b, int* d) {
+  if (b < 16) load4x4s<16>(in + (b >> 2) * 64 + (b & 3) * 4, d);
+  else { const int k = b - 16; load4x4s<8>(in + 256 + (k >> 2) * 64 + ((k >> 1) & 1) * 32 + (k & 1) * 4, d); }
 }
 __device__ __forceinline__ void store4x4(uint8_t* p, const int* d) {
 #pragma unroll
@@ -147,24 +163,25 @@ __device__ __forceinline__ unsigned long long rd_score(int disto, int rate, int 
 }
 
 // One wave of the mode search.  Grid: ceil(tasks / (WARPS * 32/G)) CTAs of WARPS warps.
-template <int G, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) encode_wave_kernel(const EncKernelParams P, int wave) {
+template <int G, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const EncKernelParams P, int wave) {
   constexpr int MPW = 32 / G;  // macroblocks per warp
-  __shared__ uint16_t s_ecost[256];
-  __shared__ uint16_t s_lfc[2048];
-  __shared__ uint16_t s_lcodes[136];
-  __shared__ uint8_t s_proba[1056];
-  __shared__ uint16_t s_i4cost[1000];
+  __shared__ __align__(16) uint16_t s_lc[LC_SIZE];
+  __shared__ __align__(16) uint16_t s_lfc[2048];
+  __shared__ __align__(16) uint16_t s_i4cost[1000];
+  __shared__ __align__(16) uint16_t s_eob[EOB_SIZE];
   extern __shared__ __align__(16) unsigned char s_dyn[];
   MBShared* s_mb = reinterpret_cast<MBShared*>(s_dyn);  // [WARPS * MPW]
-  for (int i = threadIdx.x; i < 256; i += WARPS * 32) s_ecost[i] = P.ecost[i];
-  for (int i = threadIdx.x; i < 2048; i += WARPS * 32) s_lfc[i] = P.lfc[i];
-  for (int i = threadIdx.x; i < 134; i += WARPS * 32) s_lcodes[i] = P.lcodes[i];
-  for (int i = threadIdx.x; i < 1056; i += WARPS * 32) s_proba[i] = P.proba[i];
-  for (int i = threadIdx.x; i < 1000; i += WARPS * 32) s_i4cost[i] = P.i4_costs[i];
+  {
+    constexpr int NT = WARPS * 32;
+    for (int i = threadIdx.x; i < LC_SIZE / 8; i += NT) reinterpret_cast<uint4*>(s_lc)[i] = reinterpret_cast<const uint4*>(P.lc)[i];
+    for (int i = threadIdx.x; i < 2048 / 8; i += NT) reinterpret_cast<uint4*>(s_lfc)[i] = reinterpret_cast<const uint4*>(P.lfc)[i];
+    for (int i = threadIdx.x; i < 1000 / 8; i += NT) reinterpret_cast<uint4*>(s_i4cost)[i] = reinterpret_cast<const uint4*>(P.i4_costs)[i];
+    for (int i = threadIdx.x; i < EOB_SIZE / 8; i += NT) reinterpret_cast<uint4*>(s_eob)[i] = reinterpret_cast<const uint4*>(P.eob)[i];
+  }
   __syncthreads();
   CostTabs T;
-  T.ecost = s_ecost; T.lfc = s_lfc; T.lcodes = s_lcodes; T.proba = s_proba;
+  T.lc = s_lc; T.eob = s_eob; T.lfc = s_lfc;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / G, gl = lane % G;
@@ -201,13 +218,13 @@ __global__ void __launch_bounds__(WARPS * 32) encode_wave_kernel(const EncKernel
     const int ww = min(16, P.width - x0), hh = min(16, P.height - y0);
     for (int i = gl; i < 256; i += G) {
       const int r = i >> 4, c = i & 15;
-      S.in[Y_OFF + r * BPS + c] = src_y[(size_t)(y0 + min(r, hh - 1)) * y_stride + x0 + min(c, ww - 1)];
+      S.in[r * 16 + c] = src_y[(size_t)(y0 + min(r, hh - 1)) * y_stride + x0 + min(c, ww - 1)];
     }
     const int uvw = (ww + 1) >> 1, uvh = (hh + 1) >> 1;
     for (int i = gl; i < 128; i += G) {
       const int pl = i >> 6, r = (i >> 3) & 7, c = i & 7;
       const uint8_t* sp = pl ? src_v : src_u;
-      S.in[(pl ? V_OFF : U_OFF) + r * BPS + c] = sp[(size_t)(my * 8 + min(r, uvh - 1)) * uv_stride + mx * 8 + min(c, uvw - 1)];
+      S.in[256 + pl * 64 + r * 8 + c] = sp[(size_t)(my * 8 + min(r, uvh - 1)) * uv_stride + mx * 8 + min(c, uvw - 1)];
     }
     // context from the reconstruction planes (full padded MBs are stored, so partial MBs are exact)
     uint8_t* o = S.out;
@@ -269,9 +286,9 @@ __global__ void __launch_bounds__(WARPS * 32) encode_wave_kernel(const EncKernel
     unsigned long long best_score = ~0ull;
     int src_flat = 0;
     if (active) {  // isFlatSource16 (encode_analysis.go:358)
-      const int v0 = S.in[Y_OFF];
+      const int v0 = S.in[0];
       int ok = 1;
-      for (int i = gl; i < 256; i += G) ok &= (S.in[Y_OFF + (i >> 4) * BPS + (i & 15)] == v0);
+      for (int i = gl; i < 256; i += G) ok &= (S.in[i] == v0);
       src_flat = ok;
     }
     src_flat = grp_and<G>(src_flat);
@@ -286,7 +303,7 @@ __global__ void __launch_bounds__(WARPS * 32) encode_wave_kernel(const EncKernel
         for (int b = gl; b < 16; b += G) {
           const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
           int s[16], p[16], c[16], q[16];
-          load4x4(S.in + off, s);
+          load_src_block(S.in, b, s);
           load4x4(S.out2 + off, p);
           ftransform(s, p, c);
           S.dc[b] = c[0];
@@ -333,7 +350,7 @@ __global__ void __launch_bounds__(WARPS * 32) encode_wave_kernel(const EncKernel
           dq[0] = S.dcrec[b];
           load4x4(S.out2 + off, p);
           itransform(p, dq, r);
-          load4x4(S.in + off, s);
+          load_src_block(S.in, b, s);
           disto += sse16(s, r);
           if (seg.tlambda_sd > 0) td += tdisto4x4(s, r);
           any_ac |= (S.nz[b] > 0);
@@ -377,7 +394,7 @@ __global__ void __launch_bounds__(WARPS * 32) encode_wave_kernel(const EncKernel
       int e[13], s[16];
       if (alive) {
         load_pred4_ctx(S.out2 + off, e);
-        load4x4(S.in + off, s);
+        load_src_block(S.in, b, s);
         // pre-screen: prediction SSE of every eligible mode (encode_parallel.go:955-966)
         for (int m = gl; m < 10; m += G) {
           int v = 0x7fffffff;
@@ -504,7 +521,7 @@ __global__ void __launch_bounds__(WARPS * 32) encode_wave_kernel(const EncKernel
         for (int b = gl; b < 8; b += G) {
           const int off = ((b & 4) ? V_OFF : U_OFF) + ((b >> 1) & 1) * 4 * BPS + (b & 1) * 4;
           int s[16], p[16], c[16], q[16], dq[16], r[16];
-          load4x4(S.in + off, s);
+          load_src_block(S.in, 16 + b, s);
           load4x4(S.out2 + off, p);
           ftransform(s, p, c);
           S.nz[16 + b] = quantize_block(c, q, seg.uv, 0);
@@ -552,7 +569,7 @@ __global__ void __launch_bounds__(WARPS * 32) encode_wave_kernel(const EncKernel
     for (int b = gl; b < 16; b += G) {
       const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
       int s[16], p[16], c[16];
-      load4x4(S.in + off, s);
+      load_src_block(S.in, b, s);
       load4x4(S.out + off, p);
       ftransform(s, p, c);
       S.dc[b] = c[0];
@@ -641,7 +658,7 @@ __global__ void __launch_bounds__(WARPS * 32) encode_wave_kernel(const EncKernel
     for (int b = gl; b < 8; b += G) {
       const int off = ((b & 4) ? V_OFF : U_OFF) + ((b >> 1) & 1) * 4 * BPS + (b & 1) * 4;
       int s[16], p[16], c[16], q[16], dq[16], r[16];
-      load4x4(S.in + off, s);
+      load_src_block(S.in, 16 + b, s);
       load4x4(S.out + off, p);
       ftransform(s, p, c);
       const int nz = quantize_block(c, q, seg.uv, 0);

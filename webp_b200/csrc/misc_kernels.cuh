@@ -166,11 +166,11 @@ __global__ void dsp_pred4_kernel(int n, const uint8_t* ctx13, uint8_t* out) {  /
 __global__ void dsp_quantize_kernel(int n, const int16_t* in, SegQuant sq, int first, int16_t* out, int32_t* nz) {
   WG_TID; int c[16], q[16]; load16s16(in + 16 * (size_t)i, c); nz[i] = quantize_block(c, q, sq, first); store16s16(out + 16 * (size_t)i, q);
 }
-struct TabPtrs { const uint16_t* ecost; const uint16_t* lfc; const uint16_t* lcodes; const uint8_t* proba; };
+struct TabPtrs { const uint16_t* lc; const uint16_t* eob; const uint16_t* lfc; };
 __global__ void dsp_trellis_kernel(int n, const int16_t* in, SegQuant sq, int first, int ctx_type, const int32_t* ctx0, int lambda,
                                    TabPtrs tp, int16_t* out, int32_t* nz) {
   WG_TID;
-  CostTabs T; T.ecost = tp.ecost; T.lfc = tp.lfc; T.lcodes = tp.lcodes; T.proba = tp.proba;
+  CostTabs T; T.lc = tp.lc; T.eob = tp.eob; T.lfc = tp.lfc;
   int c[16], q[16]; load16s16(in + 16 * (size_t)i, c);
   nz[i] = trellis_block(c, q, sq, first, ctx_type, ctx0[i], lambda, T);
   store16s16(out + 16 * (size_t)i, q);
@@ -178,7 +178,7 @@ __global__ void dsp_trellis_kernel(int n, const int16_t* in, SegQuant sq, int fi
 __global__ void dsp_token_cost_kernel(int n, const int16_t* levels, const int32_t* nzc, int ctx_type, const int32_t* ctx0, int first,
                                       TabPtrs tp, int32_t* out) {
   WG_TID;
-  CostTabs T; T.ecost = tp.ecost; T.lfc = tp.lfc; T.lcodes = tp.lcodes; T.proba = tp.proba;
+  CostTabs T; T.lc = tp.lc; T.eob = tp.eob; T.lfc = tp.lfc;
   int q[16]; load16s16(levels + 16 * (size_t)i, q);
   out[i] = token_cost(q, nzc[i], ctx_type, ctx0[i], first, T);
 }

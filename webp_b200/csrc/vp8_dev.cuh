@@ -17,12 +17,18 @@ __device__ __constant__ uint8_t c_rev_zigzag[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 
 __device__ __constant__ uint8_t c_weight_y[16] = {38, 32, 20, 9, 32, 28, 17, 7, 20, 17, 10, 4, 9, 7, 4, 2};
 __device__ __constant__ uint8_t c_weight_trellis[16] = {30, 27, 19, 11, 27, 24, 17, 10, 19, 17, 12, 8, 11, 10, 8, 6};
 
-// Pointers to the cost tables a kernel uses (global or shared memory).
+// Cost tables a kernel uses (global or shared memory).  On the reference's row-parallel path the coefficient
+// probabilities are the constant defaults (encode_parallel.go:1558-1567), so everything TokenCostForCoeffs and
+// TrellisQuantizeBlock look up per coefficient is folded on the host into one table per (type, band, ctx, level):
+//   lc[((type*8+band)*3+ctx)*68 + min(v,67)] = cost(not EOB) + (v == 0 ? cost(zero) : cost(non-zero) + variableLevelCost(v))
+//   eob[(type*8+band)*3+ctx]                 = cost(EOB)
+// built from VP8EntropyCost (internal/dsp/cost.go:6), vp8LevelCodes (internal/lossy/encode_quant.go:226) and
+// CoeffsProba0 (internal/lossy/proba.go:45); lfc = VP8LevelFixedCosts[2048] (internal/dsp/cost.go:33) stays separate.
+enum { LC_LEVELS = 68, LC_SIZE = 4 * 8 * 3 * LC_LEVELS, EOB_SIZE = 4 * 8 * 3 };
 struct CostTabs {
-  const uint16_t* ecost;   // VP8EntropyCost[256]               internal/dsp/cost.go:6
-  const uint16_t* lfc;     // VP8LevelFixedCosts[2048]          internal/dsp/cost.go:33
-  const uint16_t* lcodes;  // vp8LevelCodes[67][2]              internal/lossy/encode_quant.go:226
-  const uint8_t* proba;    // [4][8][3][11] coefficient probas  internal/lossy/proba.go:45
+  const uint16_t* lc;
+  const uint16_t* eob;
+  const uint16_t* lfc;
 };
 
 // SegmentQuant (internal/lossy/encode.go:311)
@@ -292,179 +298,129 @@ __device__ __forceinline__ void dequant_block(const int* in, int* out, const Seg
   for (int n = 1; n < 16; ++n) out[n] = (int)(int16_t)(in[n] * sq.quant);
 }
 
-// variableLevelCost (encode_quant.go:248)
-__device__ __forceinline__ int variable_level_cost(int level, const uint8_t* p, const CostTabs& T) {
-  int idx = min(level - 1, 66);
-  int pattern = T.lcodes[2 * idx], bits = T.lcodes[2 * idx + 1];
-  int cost = 0;
-  for (int i = 2; pattern; ++i) {
-    if (pattern & 1) cost += T.ecost[(bits & 1) ? 255 - p[i] : p[i]];
-    bits >>= 1;
-    pattern >>= 1;
-  }
-  return cost;
-}
-// fastVariableLevelCost (encode_trellis.go:328) -- same values, short paths for 1..4
-__device__ __forceinline__ int fast_variable_level_cost(int level, const uint8_t* p, const CostTabs& T) {
-  const uint16_t* e = T.ecost;
-  switch (level) {
-    case 1: return e[p[2]];
-    case 2: return e[255 - p[2]] + e[p[3]] + e[p[4]];
-    case 3: return e[255 - p[2]] + e[p[3]] + e[255 - p[4]] + e[p[5]];
-    case 4: return e[255 - p[2]] + e[p[3]] + e[255 - p[4]] + e[255 - p[5]];
-    default: return variable_level_cost(level, p, T);
-  }
-}
-// TokenCostForCoeffs (encode_quant.go:170); levels in raster order
+// TokenCostForCoeffs (encode_quant.go:170); levels in raster order.  Per coefficient: one folded-table lookup
+// (+ the fixed level cost); note the reference charges the not-EOB bit at every position up to the last non-zero.
 __device__ __forceinline__ int token_cost(const int* lev, int nz_count, int type, int ctx0, int first, const CostTabs& T) {
-  const uint8_t* pt = T.proba + type * (8 * 3 * 11);
-  if (nz_count <= first) return T.ecost[pt[(c_bands[first] * 3 + ctx0) * 11]];
+  const uint16_t* lc = T.lc + type * (8 * 3 * LC_LEVELS);
+  const uint16_t* eob = T.eob + type * (8 * 3);
+  if (nz_count <= first) return eob[c_bands[first] * 3 + ctx0];
   const int last = nz_count - 1;
   int cost = 0, ctx = ctx0;
+  constexpr int kZig[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+  constexpr int kBnd[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
 #pragma unroll
   for (int n = 0; n < 16; ++n) {
-    if (n < first) continue;
-    const uint8_t* pp = pt + (c_bands[n] * 3 + ctx) * 11;
-    if (n > last) { cost += T.ecost[pp[0]]; break; }
-    const int v = abs(lev[c_zigzag[n]]);
-    cost += T.ecost[255 - pp[0]];
-    if (v == 0) {
-      cost += T.ecost[pp[1]];
-      ctx = 0;
-    } else {
-      cost += T.ecost[255 - pp[1]] + T.lfc[v] + fast_variable_level_cost(v, pp, T);
-      ctx = (v == 1) ? 1 : 2;
+    if (n >= first && n <= last) {
+      const int v = abs(lev[kZig[n]]);
+      cost += lc[(kBnd[n] * 3 + ctx) * LC_LEVELS + min(v, LC_LEVELS - 1)] + T.lfc[v];
+      ctx = min(v, 2);
     }
   }
+  if (last < 15) cost += eob[c_bands[last + 1] * 3 + ctx];
   return cost;
 }
 
-// TrellisQuantizeBlock (internal/lossy/encode_trellis.go:23-324).  in/out raster order.
-// Path storage is packed: per position 3 x (level int16, prev_ctx/valid byte).
-__device__ __noinline__ int trellis_block(const int* in, int* out, const SegQuant& sq, int first, int type,
-                                          int initial_ctx, int lambda, const CostTabs& T) {
-  {  // all-zero pre-scan with neutral bias (encode_trellis.go:39-98)
-    bool non_zero = false;
+// TrellisQuantizeBlock (internal/lossy/encode_trellis.go:23-324).  in/out raster order, register resident: the
+// position loop is fully unrolled so the zigzag walk and the backtracking path use static indices.  Scores are
+// int64 as in the reference (rate*lambda reaches 2^33).  Path entry per (position, ctx): 13-bit signed level,
+// 2-bit previous ctx, valid bit.
+__device__ __forceinline__ uint32_t trellis_pack(int level, int prev) { return ((uint32_t)level & 0x1fffu) | ((uint32_t)prev << 13) | 0x8000u; }
+__device__ __forceinline__ int trellis_block(const int* in, int* out, const SegQuant& sq, int first, int type,
+                                             int initial_ctx, int lambda, const CostTabs& T) {
+  constexpr int kZig[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+  constexpr int kBnd[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
+  constexpr int kWt[16] = {30, 27, 19, 11, 27, 24, 17, 10, 19, 17, 12, 8, 11, 10, 8, 6};  // kWeightTrellis, raster
+  int c0[16];  // |coeff| + sharpen, clamped at 0, raster order
+  bool non_zero = false;
 #pragma unroll
-    for (int n = 0; n < 16; ++n) {
-      if (n < first) continue;
-      const int zig = c_zigzag[n];
-      int c = abs(in[zig]) + sq.sharpen[zig];
-      if (c < 0) c = 0;
-      const int iq = (n == 0) ? sq.dc_iquant : sq.iquant;
-      non_zero |= (((unsigned)c * (unsigned)iq) >> 17) > 0;  // c*iq < 2^31 (c<=~4200, iq<=32768)
-    }
-    if (!non_zero) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) out[i] = 0;
-      return 0;
-    }
+  for (int i = 0; i < 16; ++i) {
+    c0[i] = max(abs(in[i]) + sq.sharpen[i], 0);
+    out[i] = 0;
   }
-  if (initial_ctx > 2) initial_ctx = 2;
-  const uint8_t* pt = T.proba + type * (8 * 3 * 11);
-  const long long kMaxScore = 1ll << 60;
-  long long ps[3];  // prev scores; invalid = kInvalid
+  {  // all-zero pre-scan with neutral bias (encode_trellis.go:39-98); zigzag position >= first <=> raster != 0 or first == 0
+    if (first == 0) non_zero |= (((unsigned)c0[0] * (unsigned)sq.dc_iquant) >> 17) > 0;
+#pragma unroll
+    for (int i = 1; i < 16; ++i) non_zero |= (((unsigned)c0[i] * (unsigned)sq.iquant) >> 17) > 0;
+    if (!non_zero) return 0;
+  }
+  initial_ctx = min(initial_ctx, 2);
+  const uint16_t* lc = T.lc + type * (8 * 3 * LC_LEVELS);
+  const uint16_t* eob = T.eob + type * (8 * 3);
   const long long kInvalid = 0x7fffffffffffffffll;
-  ps[0] = ps[1] = ps[2] = kInvalid;
-  ps[initial_ctx] = 0;
-  short path_level[16][3];
-  signed char path_prev[16][3];  // -1 = invalid
-  const int skip_rate = T.ecost[pt[(c_bands[first] * 3 + initial_ctx) * 11]];
-  long long best_terminal = (long long)skip_rate * lambda;
-  int best_last_n = -1, best_last_ctx = -1;
+  long long ps0 = initial_ctx == 0 ? 0 : kInvalid, ps1 = initial_ctx == 1 ? 0 : kInvalid, ps2 = initial_ctx == 2 ? 0 : kInvalid;
   const long long lam = lambda;
-  for (int n = first; n < 16; ++n) {
-    const int zig = c_zigzag[n];
-    const int band = c_bands[n + 1];  // sic (encode_trellis.go:151)
-    int raw = in[zig];
-    const bool neg = raw < 0;
-    raw = abs(raw);
-    int coeff0 = raw + sq.sharpen[zig];
-    if (coeff0 < 0) coeff0 = 0;
+  long long best_terminal = (long long)eob[c_bands[first] * 3 + initial_ctx] * lam;
+  int best_last_n = -1, best_last_ctx = -1;
+  uint32_t path01[16], path2[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    path01[n] = 0; path2[n] = 0;
+    if (n < first) continue;
+    const int zig = kZig[n];
+    const int band = kBnd[n + 1];  // sic: the next position's band (encode_trellis.go:151)
+    const bool neg = in[zig] < 0;
+    const int coeff0 = c0[zig];
     const int quant = (n == 0) ? sq.dc_quant : sq.quant;
-    const int iquant = (n == 0) ? sq.dc_iquant : sq.iquant;
-    int L0 = (int)(((unsigned)coeff0 * (unsigned)iquant) >> 17);
-    L0 = min(L0, 2047);
-    int thresh_level = (int)(((unsigned)coeff0 * (unsigned)iquant + 65536u) >> 17);
-    thresh_level = min(thresh_level, 2047);
-    const long long weight = c_weight_trellis[zig];
-    const long long coeff0sq = (long long)coeff0 * coeff0;
-    const uint8_t* band_probas = pt + band * 33;
-    long long cs[3] = {kMaxScore, kMaxScore, kMaxScore};
-    bool cv[3] = {false, false, false};
-    short cl[3] = {0, 0, 0};
-    signed char cp[3] = {-1, -1, -1};
-    const bool has_l0 = L0 > 0 && L0 <= thresh_level;
-    const bool has_l1 = L0 + 1 <= 2047 && L0 + 1 <= thresh_level;
-    long long disto_l0 = 0, disto_l1 = 0;
-    int next_ctx0 = 0, next_ctx1 = 0, fixed_l0 = 0, fixed_l1 = 0;
-    if (has_l0) {
-      const long long e = coeff0 - L0 * quant;
-      disto_l0 = 256 * (weight * (e * e - coeff0sq));
-      next_ctx0 = min(L0, 2);
-      fixed_l0 = T.lfc[L0];
-    }
-    if (has_l1) {
-      const long long e = coeff0 - (L0 + 1) * quant;
-      disto_l1 = 256 * (weight * (e * e - coeff0sq));
-      next_ctx1 = min(L0 + 1, 2);
-      fixed_l1 = T.lfc[L0 + 1];
-    }
-    const short sl0 = (short)(neg ? -L0 : L0), sl1 = (short)(neg ? -(L0 + 1) : (L0 + 1));
+    const unsigned iquant = (n == 0) ? (unsigned)sq.dc_iquant : (unsigned)sq.iquant;
+    const int L0 = min((int)(((unsigned)coeff0 * iquant) >> 17), 2047);
+    const int thresh = min((int)(((unsigned)coeff0 * iquant + 65536u) >> 17), 2047);
+    const bool has_l0 = L0 > 0 && L0 <= thresh;
+    const bool has_l1 = L0 + 1 <= 2047 && L0 + 1 <= thresh;
+    const int c0sq = coeff0 * coeff0;
+    const int e0 = coeff0 - L0 * quant, e1 = coeff0 - (L0 + 1) * quant;
+    const long long disto_l0 = (long long)(e0 * e0 - c0sq) * (kWt[zig] * 256);
+    const long long disto_l1 = (long long)(e1 * e1 - c0sq) * (kWt[zig] * 256);
+    const int lfc0 = T.lfc[L0], lfc1 = T.lfc[min(L0 + 1, 2047)];
+    const int li0 = min(L0, LC_LEVELS - 1), li1 = min(L0 + 1, LC_LEVELS - 1);
+    const int sl0 = neg ? -L0 : L0, sl1 = neg ? -(L0 + 1) : (L0 + 1);
+    const bool l0_to_1 = (L0 == 1), l1_to_1 = (L0 == 0);  // next ctx of level L0 / L0+1 is 1, else 2
+    long long cs0 = kInvalid, cs1 = kInvalid, cs2 = kInvalid;  // kInvalid doubles as "not valid yet" (scores stay far below it)
+    uint32_t e_0 = 0, e_1 = 0, e_2 = 0;
+    const uint16_t* row = lc + band * 3 * LC_LEVELS;
 #pragma unroll
     for (int pc = 0; pc < 3; ++pc) {
-      if (ps[pc] == kInvalid) continue;
-      const long long prev_score = ps[pc];
-      const uint8_t* p = band_probas + pc * 11;
-      const int not_eob = T.ecost[255 - p[0]];
-      const int rate0 = not_eob + T.ecost[p[1]];
-      const long long total = prev_score + (long long)rate0 * lam;
-      if (!cv[0] || total < cs[0]) { cs[0] = total; cl[0] = 0; cp[0] = (signed char)pc; cv[0] = true; }
-      if (has_l0 || has_l1) {
-        const int non_zero = not_eob + T.ecost[255 - p[1]];
-        if (has_l0) {
-          const int rate = non_zero + fixed_l0 + fast_variable_level_cost(L0, p, T);
-          const long long ts = prev_score + (long long)rate * lam + disto_l0;
-          // next_ctx0 in {1,2}
-          if (next_ctx0 == 1) { if (!cv[1] || ts < cs[1]) { cs[1] = ts; cl[1] = sl0; cp[1] = (signed char)pc; cv[1] = true; } }
-          else               { if (!cv[2] || ts < cs[2]) { cs[2] = ts; cl[2] = sl0; cp[2] = (signed char)pc; cv[2] = true; } }
-        }
-        if (has_l1) {
-          const int rate = non_zero + fixed_l1 + fast_variable_level_cost(L0 + 1, p, T);
-          const long long ts = prev_score + (long long)rate * lam + disto_l1;
-          if (next_ctx1 == 1) { if (!cv[1] || ts < cs[1]) { cs[1] = ts; cl[1] = sl1; cp[1] = (signed char)pc; cv[1] = true; } }
-          else               { if (!cv[2] || ts < cs[2]) { cs[2] = ts; cl[2] = sl1; cp[2] = (signed char)pc; cv[2] = true; } }
-        }
+      const long long prev = pc == 0 ? ps0 : (pc == 1 ? ps1 : ps2);
+      if (prev == kInvalid) continue;
+      const uint16_t* r = row + pc * LC_LEVELS;
+      const long long t0 = prev + (long long)r[0] * lam;
+      if (t0 < cs0) { cs0 = t0; e_0 = trellis_pack(0, pc); }
+      if (has_l0) {
+        const long long ts = prev + (long long)((int)r[li0] + lfc0) * lam + disto_l0;
+        if (l0_to_1) { if (ts < cs1) { cs1 = ts; e_1 = trellis_pack(sl0, pc); } }
+        else         { if (ts < cs2) { cs2 = ts; e_2 = trellis_pack(sl0, pc); } }
+      }
+      if (has_l1) {
+        const long long ts = prev + (long long)((int)r[li1] + lfc1) * lam + disto_l1;
+        if (l1_to_1) { if (ts < cs1) { cs1 = ts; e_1 = trellis_pack(sl1, pc); } }
+        else         { if (ts < cs2) { cs2 = ts; e_2 = trellis_pack(sl1, pc); } }
       }
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      path_level[n][c] = cl[c];
-      path_prev[n][c] = cv[c] ? cp[c] : (signed char)-1;
+    path01[n] = e_0 | (e_1 << 16);
+    path2[n] = e_2;
+    {
+      const uint16_t* eb = eob + band * 3;
+      if (cs1 != kInvalid) {
+        const long long s = cs1 + (n < 15 ? (long long)eb[1] * lam : 0ll);
+        if (s < best_terminal) { best_terminal = s; best_last_n = n; best_last_ctx = 1; }
+      }
+      if (cs2 != kInvalid) {
+        const long long s = cs2 + (n < 15 ? (long long)eb[2] * lam : 0ll);
+        if (s < best_terminal) { best_terminal = s; best_last_n = n; best_last_ctx = 2; }
+      }
     }
-#pragma unroll
-    for (int c = 1; c < 3; ++c) {
-      if (!cv[c]) continue;
-      long long eob_score = cs[c];
-      if (n < 15) eob_score += (long long)T.ecost[band_probas[c * 11]] * lam;
-      if (eob_score < best_terminal) { best_terminal = eob_score; best_last_n = n; best_last_ctx = c; }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) ps[c] = cv[c] ? cs[c] : kInvalid;
+    ps0 = cs0; ps1 = cs1; ps2 = cs2;
   }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) out[i] = 0;
   if (best_last_n < 0) return 0;
   int ctx = best_last_ctx, last = 0;
-  for (int n = best_last_n; n >= first; --n) {
-    if (path_prev[n][ctx] >= 0) {
-      const int zig = c_zigzag[n];
-      const int lv = path_level[n][ctx];
-      // out[] is register-resident: select by unrolled compare instead of a dynamic index
 #pragma unroll
-      for (int i = 0; i < 16; ++i) if (i == zig) out[i] = lv;
+  for (int n = 15; n >= 0; --n) {
+    if (n > best_last_n || n < first) continue;
+    const uint32_t e = ctx == 0 ? (path01[n] & 0xffffu) : (ctx == 1 ? (path01[n] >> 16) : path2[n]);
+    if (e & 0x8000u) {
+      const int lv = ((int)(e << 19)) >> 19;  // sign-extend 13 bits
+      out[kZig[n]] = lv;
       if (lv != 0 && last == 0) last = n + 1;
-      ctx = path_prev[n][ctx];
+      ctx = (e >> 13) & 3;
     }
   }
   return last;

@@ -70,7 +70,7 @@ struct wgpu_ctx {
   int host_threads = 0;
   std::mutex mu;
   // constant tables
-  DevBuf t_ecost, t_lfc, t_lcodes, t_proba, t_i4cost, t_g2l, t_l2g;
+  DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g;
   // encoder state (device)
   DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, hdr, coeffs;
   PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs;
@@ -154,10 +154,23 @@ int wgpu_ctx_create(int device_ordinal, wgpu_ctx** out) {
   }
   l2g[33] = 255;
   int rc = 0;
-  rc |= upload_table(ctx, ctx->t_ecost, wgh::kEntropyCost, sizeof(wgh::kEntropyCost));
+  // folded per-(type, band, ctx, level) token costs under the default probabilities (vp8_dev.cuh CostTabs)
+  static uint16_t lc[wg::LC_SIZE], eobc[wg::EOB_SIZE];
+  for (int tbc = 0; tbc < 4 * 8 * 3; ++tbc) {
+    const uint8_t* p = &wgh::kCoeffsProba0[tbc * 11];
+    eobc[tbc] = wgh::kEntropyCost[p[0]];
+    const int not_eob = wgh::kEntropyCost[255 - p[0]];
+    lc[tbc * wg::LC_LEVELS] = (uint16_t)(not_eob + wgh::kEntropyCost[p[1]]);
+    for (int v = 1; v < wg::LC_LEVELS; ++v) {  // variableLevelCost (encode_quant.go:248)
+      int pattern = wgh::kLevelCodes[2 * (v - 1)], bits = wgh::kLevelCodes[2 * (v - 1) + 1], cost = 0;
+      for (int i = 2; pattern; ++i, bits >>= 1, pattern >>= 1)
+        if (pattern & 1) cost += wgh::bit_cost(bits & 1, p[i]);
+      lc[tbc * wg::LC_LEVELS + v] = (uint16_t)(not_eob + wgh::kEntropyCost[255 - p[1]] + cost);
+    }
+  }
+  rc |= upload_table(ctx, ctx->t_lc, lc, sizeof(lc));
+  rc |= upload_table(ctx, ctx->t_eob, eobc, sizeof(eobc));
   rc |= upload_table(ctx, ctx->t_lfc, wgh::kLevelFixedCosts, sizeof(wgh::kLevelFixedCosts));
-  rc |= upload_table(ctx, ctx->t_lcodes, wgh::kLevelCodes, sizeof(wgh::kLevelCodes));
-  rc |= upload_table(ctx, ctx->t_proba, wgh::kCoeffsProba0, sizeof(wgh::kCoeffsProba0));
   rc |= upload_table(ctx, ctx->t_i4cost, i4costs, sizeof(i4costs));
   rc |= upload_table(ctx, ctx->t_g2l, g2l, sizeof(g2l));
   rc |= upload_table(ctx, ctx->t_l2g, l2g, sizeof(l2g));
@@ -170,7 +183,7 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->t_ecost, &ctx->t_lfc, &ctx->t_lcodes, &ctx->t_proba, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
+  DevBuf* db[] = {&ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
                   &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
@@ -252,16 +265,40 @@ int wgpu_enc_upload(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int he
   return WGPU_OK;
 }
 
+extern "C++" {
 namespace {
-constexpr int kEncG = 8, kEncWarps = 4;  // lanes per macroblock / warps per CTA of the mode-search kernel
-constexpr int kEncMBPerCTA = kEncWarps * (32 / kEncG);
-constexpr size_t kEncSmem = sizeof(wg::MBShared) * kEncMBPerCTA;
-
 int wave_rows(int wave, int mb_w, int mb_h) {
   const int y_lo = std::max(0, (wave - (mb_w - 1) + 1) >> 1), y_hi = std::min(mb_h - 1, wave >> 1);
   return y_hi - y_lo + 1;
 }
+// Launch configurations of the mode-search kernel: lanes per macroblock (G), warps per CTA, min CTAs per SM (register cap).
+// WGPU_ENC_VARIANT picks one at run time for tuning; the default is the measured best.
+template <int G, int WARPS, int MINB>
+int launch_enc_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
+  constexpr int per_cta = WARPS * (32 / G);
+  constexpr size_t smem = sizeof(wg::MBShared) * per_cta;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wg::encode_wave_kernel<G, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int waves = P.mb_w + 2 * (P.mb_h - 1);
+  for (int w = 0; w < waves; ++w) {
+    const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
+    const unsigned grid = (unsigned)((tasks + per_cta - 1) / per_cta);
+    wg::encode_wave_kernel<G, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(P, w);
+    ctx->launches++;
+  }
+  return WGPU_OK;
+}
+int enc_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("WGPU_ENC_VARIANT"); v = e ? atoi(e) : 0; }
+  return v;
+}
 }  // namespace
+}  // extern "C++"
 
 static int enc_launch_import(wgpu_ctx* ctx) {
   const int n = ctx->e_n, pad_w = ctx->e_mbw * 16, pad_h = ctx->e_mbh * 16;
@@ -292,30 +329,26 @@ static int enc_launch_analysis(wgpu_ctx* ctx) {
   return WGPU_OK;
 }
 static int enc_launch_waves(wgpu_ctx* ctx) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(wg::encode_wave_kernel<kEncG, kEncWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncSmem));
-    attr_set = true;
-  }
   const int n = ctx->e_n, mbw = ctx->e_mbw, mbh = ctx->e_mbh, nmb = mbw * mbh;
   wg::EncKernelParams P;
   P.src_y = ctx->sy.as<uint8_t>(); P.src_u = ctx->su.as<uint8_t>(); P.src_v = ctx->sv.as<uint8_t>();
   P.rec_y = ctx->ry.as<uint8_t>(); P.rec_u = ctx->ru.as<uint8_t>(); P.rec_v = ctx->rv.as<uint8_t>();
   P.segment = ctx->segment.as<uint8_t>(); P.img = ctx->img_params.as<wg::ImageParams>();
   P.ctx = ctx->ctxw.as<uint32_t>(); P.out_hdr = ctx->hdr.as<uint8_t>(); P.out_coeffs = ctx->coeffs.as<int16_t>();
-  P.i4_costs = ctx->t_i4cost.as<uint16_t>(); P.ecost = ctx->t_ecost.as<uint16_t>(); P.lfc = ctx->t_lfc.as<uint16_t>();
-  P.lcodes = ctx->t_lcodes.as<uint16_t>(); P.proba = ctx->t_proba.as<uint8_t>();
+  P.i4_costs = ctx->t_i4cost.as<uint16_t>(); P.lc = ctx->t_lc.as<uint16_t>(); P.eob = ctx->t_eob.as<uint16_t>(); P.lfc = ctx->t_lfc.as<uint16_t>();
   P.n_images = n; P.width = ctx->e_w; P.height = ctx->e_h; P.mb_w = mbw; P.mb_h = mbh;
   P.method = ctx->e_opt.method;
   P.max_i4_modes = ctx->e_opt.quality < 50 ? 2 : 3;  // getMaxI4RDModes (encode_parallel.go:931)
   P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
-  const int waves = mbw + 2 * (mbh - 1);
-  for (int w = 0; w < waves; ++w) {
-    const long long tasks = (long long)wave_rows(w, mbw, mbh) * n;
-    const unsigned grid = (unsigned)((tasks + kEncMBPerCTA - 1) / kEncMBPerCTA);
-    wg::encode_wave_kernel<kEncG, kEncWarps><<<grid, kEncWarps * 32, kEncSmem, ctx->stream>>>(P, w);
-    ctx->launches++;
+  int rc;
+  switch (enc_variant()) {
+    case 1: rc = launch_enc_waves<8, 4, 3>(ctx, P); break;
+    case 2: rc = launch_enc_waves<4, 4, 3>(ctx, P); break;
+    case 3: rc = launch_enc_waves<4, 4, 4>(ctx, P); break;
+    case 4: rc = launch_enc_waves<16, 4, 2>(ctx, P); break;
+    default: rc = launch_enc_waves<8, 4, 2>(ctx, P); break;
   }
+  if (rc) return rc;
   CK(cudaGetLastError());
   return WGPU_OK;
 }
@@ -776,8 +809,7 @@ static wg::SegQuant make_seg_quant(int dc_q, int ac_q, int type, int sharpen) {
 }
 static wg::TabPtrs tab_ptrs(const wgpu_ctx* ctx) {
   wg::TabPtrs t;
-  t.ecost = ctx->t_ecost.as<uint16_t>(); t.lfc = ctx->t_lfc.as<uint16_t>(); t.lcodes = ctx->t_lcodes.as<uint16_t>();
-  t.proba = ctx->t_proba.as<uint8_t>();
+  t.lc = ctx->t_lc.as<uint16_t>(); t.eob = ctx->t_eob.as<uint16_t>(); t.lfc = ctx->t_lfc.as<uint16_t>();
   return t;
 }
 int wgpu_dsp_quantize_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, int ac_q, int type, int sharpen, int first, int16_t* out,
