@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <atomic>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -46,6 +47,9 @@ struct PinBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+bool trace_on() { static int v = -1; if (v < 0) v = getenv("WGPU_TRACE") ? 1 : 0; return v == 1; }
 
 template <class F>
 void parallel_for(int n, int threads, F f) {
@@ -342,11 +346,8 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
   int rc;
   switch (enc_variant()) {
-    case 1: rc = launch_enc_waves<8, 4, 3>(ctx, P); break;
-    case 2: rc = launch_enc_waves<4, 4, 3>(ctx, P); break;
-    case 3: rc = launch_enc_waves<4, 4, 4>(ctx, P); break;
-    case 4: rc = launch_enc_waves<16, 4, 2>(ctx, P); break;
-    default: rc = launch_enc_waves<8, 4, 2>(ctx, P); break;
+    case 1: rc = launch_enc_waves<8, 4, 2>(ctx, P); break;   // no register cap (243 regs, 8 warps/SM)
+    default: rc = launch_enc_waves<8, 4, 3>(ctx, P); break;  // 168 regs, 3 CTAs/SM = 48 macroblocks/SM (measured best)
   }
   if (rc) return rc;
   CK(cudaGetLastError());
@@ -376,11 +377,15 @@ int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
   ctx->e_done = false;
   if ((rc = enc_reserve(ctx))) return rc;
   const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
+  const double t_start = now_ms();
+  if (trace_on()) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "[wgpu] enc_device: upload drained after %.2f ms\n", now_ms() - t_start); }
+  const double t0 = now_ms();
   if ((rc = enc_launch_import(ctx))) return rc;
   if ((rc = enc_launch_analysis(ctx))) return rc;
   CK(cudaMemcpyAsync(ctx->h_alpha.p, ctx->alpha.p, (size_t)n * nmb, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_uv_alpha.p, ctx->uv_alpha.p, (size_t)n * nmb, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  const double t1 = now_ms();
   // host: segment clustering + quantiser / lambda setup (microseconds per image; float64 pow as in the reference)
   ctx->plans.resize(n);
   static_assert(sizeof(wgh::SegParams) == sizeof(wg::SegParams), "SegParams layout");
@@ -396,7 +401,14 @@ int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
   });
   CK(cudaMemcpyAsync(ctx->segment.p, ctx->h_segment.p, (size_t)n * nmb, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->img_params.p, ctx->h_params.p, (size_t)n * sizeof(wg::ImageParams), cudaMemcpyHostToDevice, ctx->stream));
+  const double t2 = now_ms();
   if ((rc = enc_launch_waves(ctx))) return rc;
+  if (trace_on()) {
+    const double t3 = now_ms();
+    cudaStreamSynchronize(ctx->stream);
+    fprintf(stderr, "[wgpu] enc_device: import+analysis+D2H %.2f ms, host plan %.2f ms, wave launch %.2f ms, waves done after %.2f ms\n", t1 - t0,
+            t2 - t1, t3 - t2, now_ms() - t2);
+  }
   ctx->e_done = true;
   return WGPU_OK;
 }
@@ -410,9 +422,13 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
   const size_t n = ctx->e_n, nmb = (size_t)ctx->e_mbw * ctx->e_mbh;
   RESERVE(ctx->h_hdr, n * nmb * 48);
   RESERVE(ctx->h_coeffs, n * nmb * 800);
+  const double t0 = now_ms();
+  if (trace_on()) cudaStreamSynchronize(ctx->stream);
+  const double t0b = now_ms();
   CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_coeffs.p, ctx->coeffs.p, n * nmb * 800, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  const double t1 = now_ms();
   std::atomic<int> too_small(0);
   parallel_for((int)n, threads_of(ctx), [&](int i) {
     std::vector<uint8_t> riff;
@@ -423,6 +439,9 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     if (riff.size() > out_stride) { too_small.store(1); return; }
     memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
   });
+  if (trace_on())
+    fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, D2H %.2f ms (%.1f MB), host serialise %.2f ms (%d threads)\n", t0b - t0, t1 - t0b,
+            (double)(n * nmb * 848) / 1e6, now_ms() - t1, threads_of(ctx));
   if (too_small.load()) FAIL(WGPU_ERR_TOO_SMALL, "output buffer too small (out_sizes holds the required sizes)");
   return WGPU_OK;
 }
