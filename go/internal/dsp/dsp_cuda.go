@@ -1,0 +1,50 @@
+//go:build cuda && cgo
+
+// Batched twins of the per-block operator surface (dsp.go:12-37, *Direct functions).  A per-4x4 cgo call is
+// meaningless on a GPU, so production code never calls these per block; they exist so the reference's own
+// conformance pattern (simd_test.go: backend == scalar Go on random inputs) can be run against the CUDA backend.
+package dsp
+
+/*
+#cgo LDFLAGS: -lwebpgpu
+#include "webpgpu.h"
+*/
+import "C"
+
+import "unsafe"
+
+// FTransformBatchCUDA: n dense 4x4 tiles of src and ref -> n x 16 coefficients (FTransformDirect, transforms.go:371).
+func FTransformBatchCUDA(ctx unsafe.Pointer, src, ref []byte, out []int16) int {
+	n := len(out) / 16
+	return int(C.wgpu_dsp_ftransform_batch((*C.wgpu_ctx)(ctx), C.int(n), (*C.uint8_t)(&src[0]), (*C.uint8_t)(&ref[0]), (*C.int16_t)(&out[0])))
+}
+
+// ITransformBatchCUDA: ITransformDirect (transforms.go:265).
+func ITransformBatchCUDA(ctx unsafe.Pointer, ref []byte, in []int16, dst []byte) int {
+	n := len(dst) / 16
+	return int(C.wgpu_dsp_itransform_batch((*C.wgpu_ctx)(ctx), C.int(n), (*C.uint8_t)(&ref[0]), (*C.int16_t)(&in[0]), (*C.uint8_t)(&dst[0])))
+}
+
+// SSE4x4BatchCUDA / TDisto4x4BatchCUDA: SSE4x4Direct, TDisto4x4 (ssim.go:188,315).
+func SSE4x4BatchCUDA(ctx unsafe.Pointer, a, b []byte, out []int32) int {
+	return int(C.wgpu_dsp_sse4x4_batch((*C.wgpu_ctx)(ctx), C.int(len(out)), (*C.uint8_t)(&a[0]), (*C.uint8_t)(&b[0]), (*C.int32_t)(&out[0])))
+}
+func TDisto4x4BatchCUDA(ctx unsafe.Pointer, a, b []byte, out []int32) int {
+	return int(C.wgpu_dsp_tdisto4x4_batch((*C.wgpu_ctx)(ctx), C.int(len(out)), (*C.uint8_t)(&a[0]), (*C.uint8_t)(&b[0]), (*C.int32_t)(&out[0])))
+}
+
+// UpsampleNRGBACUDA: buildNRGBA / UpsampleLinePairNRGBA over whole planes (webp.go:379, upsample.go:130).
+func UpsampleNRGBACUDA(ctx unsafe.Pointer, n, w, h int, y []byte, yStride int, u, v []byte, uvStride, yPlane, uvPlane int, alpha, out []byte) int {
+	var pa *C.uint8_t
+	if alpha != nil {
+		pa = (*C.uint8_t)(&alpha[0])
+	}
+	return int(C.wgpu_upsample_nrgba((*C.wgpu_ctx)(ctx), C.int(n), C.int(w), C.int(h), (*C.uint8_t)(&y[0]), C.int(yStride), (*C.uint8_t)(&u[0]),
+		(*C.uint8_t)(&v[0]), C.int(uvStride), C.size_t(yPlane), C.size_t(uvPlane), pa, (*C.uint8_t)(&out[0])))
+}
+
+// PlaneMetricsCUDA: SSE + sum of SSIMGet/SSIMGetClipped per plane pair (ssim.go:116-181).
+func PlaneMetricsCUDA(ctx unsafe.Pointer, n int, a, b []byte, w, h, stride, planeStride int, sse []uint64, ssim []float64) int {
+	return int(C.wgpu_plane_metrics((*C.wgpu_ctx)(ctx), C.int(n), (*C.uint8_t)(&a[0]), (*C.uint8_t)(&b[0]), C.int(w), C.int(h), C.int(stride),
+		C.size_t(planeStride), (*C.uint64_t)(&sse[0]), (*C.double)(&ssim[0])))
+}

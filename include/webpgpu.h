@@ -85,6 +85,27 @@ int wgpu_enc_upload(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int he
 int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt);
 int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_sizes);
 
+/* Finer-grained form for a host that keeps the reference's own segmentation and serialiser (the Go shim):
+ *   analyze : import + per-macroblock analysis; alphas [n][nmb] (mixed alpha, encode_analysis.go:245) and
+ *             uv_alpha_sum [n] (sum of per-MB chroma alphas) are copied back
+ *   search  : the host supplies what assignSegments / setSegmentParams / setupSegment produced -- per image four
+ *             wgpu_segment (SegmentInfo subset, internal/lossy/encode.go:278-323) and the per-MB segment map --
+ *             and the wavefront mode search runs; fetch per-MB results with wgpu_enc_fetch.
+ * wgpu_enc_device == analyze + the library's own restatement of that host step + search. */
+typedef struct {
+  int quant, iquant, bias, dc_quant, dc_iquant, dc_bias; /* SegmentQuant: Quant, IQuant, Bias, DCQuant, DCIQuant, DCBias */
+  int16_t sharpen[16];
+} wgpu_seg_quant;
+typedef struct {
+  wgpu_seg_quant y1, y2, uv;
+  int lambda_i4, lambda_i16, lambda_uv, lambda_mode, tlambda_i4, tlambda_i16, tlambda_sd, reserved;
+} wgpu_segment;
+/* setupSegment (internal/lossy/encode.go:1084): quantiser matrices, biases, sharpening and lambdas of one segment from
+ * its quantiser index; provided so hosts and tests can build wgpu_segment without restating the tables. */
+int wgpu_setup_segment(int quant_index, int dq_uv_dc, int dq_uv_ac, int method, int sns_strength, wgpu_segment* out);
+int wgpu_enc_analyze(wgpu_ctx* ctx, const wgpu_enc_options* opt, uint8_t* alphas, int64_t* uv_alpha_sum);
+int wgpu_enc_search(wgpu_ctx* ctx, const wgpu_segment* segments /* [n][4] */, const uint8_t* segment_map /* [n][nmb] */);
+
 /* Debug/parity taps of the last wgpu_enc_device call (any pointer may be NULL).  Layouts as the
  * oracle's taps: mb_hdr [nmb][8] = {mb_type,i16_mode,uv_mode,segment,skip,nz_dc,0,0}, mb_modes [nmb][16],
  * mb_nz [nmb][24], mb_coeffs [nmb][400] int16, planes padded to 16*mb_w x 16*mb_h (chroma half). */

@@ -96,6 +96,37 @@ def test_encode_bytes_and_decisions(oracle, gpu_ctx, w, h, idxs, kw):
         assert files[k] == exp, "image %d: bitstream differs (%d vs %d bytes)" % (i, len(files[k]), len(exp))
 
 
+def test_analyze_search_route_matches_enc_device(oracle, gpu_ctx):
+    """The Go-shim route: GPU analysis -> host segmentation (here: taken from the oracle) -> GPU mode
+    search with host-supplied SegmentInfo -> per-MB results identical to the oracle's mbInfo."""
+    L = native.lib()
+    w, h = 160, 128
+    img = oracle.synth_image(w, h, 1)
+    _, t = oracle.encode(img, taps=True)
+    nmb = ((w + 15) >> 4) * ((h + 15) >> 4)
+    opt = webp_b200.webp.lossy_config(webp_b200.DefaultOptions())
+    gpu_ctx.check(L.wgpu_enc_upload(gpu_ctx.handle, img.ctypes.data, 1, w, h, w * 4, w * h * 4))
+    alphas = np.zeros(nmb, np.uint8); uv_sum = np.zeros(1, np.int64)
+    gpu_ctx.check(L.wgpu_enc_analyze(gpu_ctx.handle, C.byref(opt), alphas.ctypes.data, uv_sum.ctypes.data))
+    assert np.array_equal(alphas, t["alphas"])
+    # setSegmentParams (encode_analysis.go:122): UV quantiser deltas from the global chroma alpha (Go integer division)
+    guv = int(uv_sum[0]) // nmb
+    num = (guv - 64) * 10
+    dq = abs(num) // 70 * (1 if num >= 0 else -1)
+    dq = abs(dq * 50) // 100 * (1 if dq >= 0 else -1)
+    dq_uv_ac, dq_uv_dc = max(-4, min(6, dq)), -2
+    segs = (native.Segment * 4)()
+    for i in range(4):
+        assert L.wgpu_setup_segment(int(t["seg"][i][0]), dq_uv_dc, dq_uv_ac, 4, 50, C.byref(segs[i])) == 0
+        assert (segs[i].lambda_i4, segs[i].lambda_i16, segs[i].lambda_uv, segs[i].lambda_mode) == tuple(int(x) for x in t["seg"][i][4:8])
+    seg_map = np.ascontiguousarray(t["mb_hdr"][:, 3])
+    gpu_ctx.check(L.wgpu_enc_search(gpu_ctx.handle, segs, seg_map.ctypes.data))
+    g = _fetch(gpu_ctx, 0, w, h)
+    for k in ("mb_modes", "mb_nz", "mb_coeffs"):
+        assert np.array_equal(g[k], t[k]), k
+    assert np.array_equal(g["mb_hdr"][:, :6], t["mb_hdr"][:, :6])
+
+
 def test_encode_test_png(oracle, gpu_ctx):
     # BASELINE.json configs[0]: testdata/test.png q75 m4 (768x576 RGBA, all opaque)
     from PIL import Image

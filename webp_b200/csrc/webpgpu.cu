@@ -79,7 +79,7 @@ struct wgpu_ctx {
   DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, hdr, coeffs;
   PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
-  bool e_uploaded = false, e_done = false;
+  bool e_uploaded = false, e_analyzed = false, e_done = false;
   wgpu_enc_options e_opt;
   std::vector<wgh::FramePlan> plans;
   // decoder state
@@ -265,6 +265,7 @@ int wgpu_enc_upload(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int he
   ctx->e_n = n; ctx->e_w = width; ctx->e_h = height; ctx->e_mbw = (width + 15) >> 4; ctx->e_mbh = (height + 15) >> 4;
   ctx->e_rgba_stride = dstride;
   ctx->e_uploaded = true;
+  ctx->e_analyzed = false;
   ctx->e_done = false;
   return WGPU_OK;
 }
@@ -366,10 +367,9 @@ static int enc_reserve(wgpu_ctx* ctx) {
   return WGPU_OK;
 }
 
-int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
-  if (!ctx) return WGPU_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  if (!ctx->e_uploaded) FAIL(WGPU_ERR_INVALID, "wgpu_enc_device called before wgpu_enc_upload");
+// import + analysis, alphas back on the host (ctx->mu held by the caller)
+static int enc_analyze_locked(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
+  if (!ctx->e_uploaded) FAIL(WGPU_ERR_INVALID, "encoder stage called before wgpu_enc_upload");
   int rc = validate_enc_options(ctx, opt, ctx->e_w, ctx->e_h);
   if (rc) return rc;
   CK(cudaSetDevice(ctx->dev));
@@ -377,15 +377,84 @@ int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
   ctx->e_done = false;
   if ((rc = enc_reserve(ctx))) return rc;
   const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
-  const double t_start = now_ms();
-  if (trace_on()) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "[wgpu] enc_device: upload drained after %.2f ms\n", now_ms() - t_start); }
-  const double t0 = now_ms();
   if ((rc = enc_launch_import(ctx))) return rc;
   if ((rc = enc_launch_analysis(ctx))) return rc;
   CK(cudaMemcpyAsync(ctx->h_alpha.p, ctx->alpha.p, (size_t)n * nmb, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_uv_alpha.p, ctx->uv_alpha.p, (size_t)n * nmb, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->e_analyzed = true;
+  return WGPU_OK;
+}
+// segment map + per-image parameters (already in the pinned staging buffers) -> device, then all waves
+static int enc_search_locked(wgpu_ctx* ctx) {
+  const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
+  CK(cudaMemcpyAsync(ctx->segment.p, ctx->h_segment.p, (size_t)n * nmb, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->img_params.p, ctx->h_params.p, (size_t)n * sizeof(wg::ImageParams), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = enc_launch_waves(ctx);
+  if (rc) return rc;
+  ctx->e_done = true;
+  return WGPU_OK;
+}
+
+int wgpu_setup_segment(int quant_index, int dq_uv_dc, int dq_uv_ac, int method, int sns_strength, wgpu_segment* out) {
+  if (!out || quant_index < 0 || quant_index > 127) return WGPU_ERR_INVALID;
+  wgh::FramePlan fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.seg[0].quant = quant_index;
+  fp.dq_uv_dc = dq_uv_dc; fp.dq_uv_ac = dq_uv_ac;
+  wgpu_enc_options o;
+  wgpu_enc_options_default(&o, 75);
+  o.method = method; o.sns_strength = sns_strength;
+  wgh::setup_segment(&fp, o, 0);
+  memcpy(out, &fp.dev[0], sizeof(*out));
+  return WGPU_OK;
+}
+
+int wgpu_enc_analyze(wgpu_ctx* ctx, const wgpu_enc_options* opt, uint8_t* alphas, int64_t* uv_alpha_sum) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int rc = enc_analyze_locked(ctx, opt);
+  if (rc) return rc;
+  const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
+  if (alphas) memcpy(alphas, ctx->h_alpha.p, (size_t)n * nmb);
+  if (uv_alpha_sum)
+    for (int i = 0; i < n; ++i) {
+      int64_t s = 0;
+      const uint8_t* ua = ctx->h_uv_alpha.as<uint8_t>() + (size_t)i * nmb;
+      for (int k = 0; k < nmb; ++k) s += ua[k];
+      uv_alpha_sum[i] = s;
+    }
+  return WGPU_OK;
+}
+
+int wgpu_enc_search(wgpu_ctx* ctx, const wgpu_segment* segments, const uint8_t* segment_map) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->e_analyzed) FAIL(WGPU_ERR_INVALID, "wgpu_enc_search called before wgpu_enc_analyze");
+  if (!segments || !segment_map) FAIL(WGPU_ERR_INVALID, "wgpu_enc_search: nil segment parameters");
+  static_assert(sizeof(wgpu_segment) == sizeof(wg::SegParams), "wgpu_segment layout");
+  const size_t n = ctx->e_n, nmb = (size_t)ctx->e_mbw * ctx->e_mbh;
+  for (size_t i = 0; i < n * nmb; ++i)
+    if (segment_map[i] > 3) FAIL(WGPU_ERR_INVALID, "wgpu_enc_search: segment id out of range");
+  for (size_t i = 0; i < n * 4; ++i)
+    if (segments[i].y1.quant <= 0 || segments[i].y1.dc_quant <= 0 || segments[i].y2.quant <= 0 || segments[i].y2.dc_quant <= 0 ||
+        segments[i].uv.quant <= 0 || segments[i].uv.dc_quant <= 0)
+      FAIL(WGPU_ERR_INVALID, "wgpu_enc_search: non-positive quantiser");
+  CK(cudaSetDevice(ctx->dev));
+  memcpy(ctx->h_segment.p, segment_map, n * nmb);
+  memcpy(ctx->h_params.p, segments, n * sizeof(wg::ImageParams));
+  ctx->plans.clear();  // the host owns segmentation on this route: wgpu_enc_finish is not available, use wgpu_enc_fetch
+  return enc_search_locked(ctx);
+}
+
+int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  const double t0 = now_ms();
+  int rc = enc_analyze_locked(ctx, opt);
+  if (rc) return rc;
   const double t1 = now_ms();
+  const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
   // host: segment clustering + quantiser / lambda setup (microseconds per image; float64 pow as in the reference)
   ctx->plans.resize(n);
   static_assert(sizeof(wgh::SegParams) == sizeof(wg::SegParams), "SegParams layout");
@@ -399,24 +468,21 @@ int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
     fp.num_parts = 1 << ctx->e_opt.partitions;
     memcpy(ctx->h_params.as<uint8_t>() + (size_t)i * sizeof(wg::ImageParams), fp.dev, sizeof(wg::ImageParams));
   });
-  CK(cudaMemcpyAsync(ctx->segment.p, ctx->h_segment.p, (size_t)n * nmb, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->img_params.p, ctx->h_params.p, (size_t)n * sizeof(wg::ImageParams), cudaMemcpyHostToDevice, ctx->stream));
   const double t2 = now_ms();
-  if ((rc = enc_launch_waves(ctx))) return rc;
+  if ((rc = enc_search_locked(ctx))) return rc;
   if (trace_on()) {
     const double t3 = now_ms();
     cudaStreamSynchronize(ctx->stream);
     fprintf(stderr, "[wgpu] enc_device: import+analysis+D2H %.2f ms, host plan %.2f ms, wave launch %.2f ms, waves done after %.2f ms\n", t1 - t0,
             t2 - t1, t3 - t2, now_ms() - t2);
   }
-  ctx->e_done = true;
   return WGPU_OK;
 }
 
 int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_sizes) {
   if (!ctx) return WGPU_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  if (!ctx->e_done) FAIL(WGPU_ERR_INVALID, "wgpu_enc_finish called before wgpu_enc_device");
+  if (!ctx->e_done || ctx->plans.size() != (size_t)ctx->e_n) FAIL(WGPU_ERR_INVALID, "wgpu_enc_finish called before wgpu_enc_device");
   if (!out || !out_sizes) FAIL(WGPU_ERR_INVALID, "webp: nil writer");
   CK(cudaSetDevice(ctx->dev));
   const size_t n = ctx->e_n, nmb = (size_t)ctx->e_mbw * ctx->e_mbh;

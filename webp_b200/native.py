@@ -21,6 +21,16 @@ class EncOptions(C.Structure):
         "partitions", "segments", "preprocessing", "has_alpha")]
 
 
+class SegQuant(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("quant", "iquant", "bias", "dc_quant", "dc_iquant", "dc_bias")] + [("sharpen", C.c_int16 * 16)]
+
+
+class Segment(C.Structure):
+    """wgpu_segment == the SegmentInfo subset the mode search reads (internal/lossy/encode.go:278-323)."""
+    _fields_ = [("y1", SegQuant), ("y2", SegQuant), ("uv", SegQuant)] + [(n, C.c_int) for n in (
+        "lambda_i4", "lambda_i16", "lambda_uv", "lambda_mode", "tlambda_i4", "tlambda_i16", "tlambda_sd", "reserved")]
+
+
 class WebPGPUError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("%s (wgpu status %d)" % (msg, code))
@@ -57,6 +67,9 @@ def lib():
         L.wgpu_encode_batch.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, sz, C.POINTER(EncOptions), u8p, sz, vp]
         L.wgpu_enc_upload.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, sz]
         L.wgpu_enc_device.argtypes = [vp, C.POINTER(EncOptions)]
+        L.wgpu_setup_segment.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Segment)]
+        L.wgpu_enc_analyze.argtypes = [vp, C.POINTER(EncOptions), u8p, vp]
+        L.wgpu_enc_search.argtypes = [vp, vp, u8p]
         L.wgpu_enc_finish.argtypes = [vp, u8p, sz, vp]
         L.wgpu_enc_fetch.argtypes = [vp, C.c_int] + [vp] * 11
         L.wgpu_decode_info.argtypes = [u8p, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]
