@@ -1,0 +1,59 @@
+// TEST INFRASTRUCTURE ONLY.  Drives the PRODUCT's host-side code (webp_b200/csrc/host_enc.h: segment planning and
+// the token / bool-coding serialiser that consumes the GPU's per-macroblock output) from oracle-produced per-MB data,
+// so that host logic is parity-checked and timed on CPU without a GPU.  Nothing in webp_b200/ links this.
+#include "encoder.h"
+#include "../webp_b200/csrc/host_enc.h"
+#include <chrono>
+
+extern "C" {
+struct OrcEncCfg2 {
+  int quality, method, sns_strength, filter_strength, filter_sharpness, filter_type, partitions, segments, preprocessing, has_alpha;
+};
+// Returns the RIFF size produced by the product serialiser (out receives it) or <0; *same = 1 when it equals the
+// oracle's bytes; *ms_per_rep = serialiser time per repetition.
+long hostcheck_serialize(const uint8_t* rgba, int stride, int w, int h, const OrcEncCfg2* c, uint8_t* out, long cap, int reps,
+                         int* same, double* ms_per_rep) {
+  orc::EncodeConfig e;
+  e.quality = c->quality; e.method = c->method; e.sns_strength = c->sns_strength; e.filter_strength = c->filter_strength;
+  e.filter_sharpness = c->filter_sharpness; e.filter_type = c->filter_type; e.partitions = c->partitions; e.segments = c->segments;
+  e.preprocessing = c->preprocessing;
+  orc::Encoder* enc = new orc::Encoder();
+  enc->init(rgba, stride, w, h, e, c->has_alpha);
+  std::vector<uint8_t> ref = orc::riff_wrap(enc->encode_frame());
+  const int nmb = enc->mb_w * enc->mb_h;
+  static thread_local orc::ProbaStats st;
+  enc->record_all_tokens(st);
+  std::vector<uint32_t> stats(4 * 8 * 3 * 11 * 2);
+  memcpy(stats.data(), st, stats.size() * 4);
+  std::vector<uint8_t> hdr((size_t)nmb * 48), segmap(nmb);
+  std::vector<int16_t> coeffs((size_t)nmb * 400);
+  for (int i = 0; i < nmb; ++i) {
+    const orc::MBInfo& m = enc->mb_info[i];
+    uint8_t* hd = &hdr[(size_t)i * 48];
+    hd[0] = (uint8_t)m.mb_type; hd[1] = m.i16_mode; hd[2] = m.uv_mode; hd[3] = m.segment; hd[4] = m.skip; hd[5] = m.nz_dc;
+    memcpy(hd + 8, m.modes, 16); memcpy(hd + 24, m.nz_y, 16); memcpy(hd + 40, m.nz_uv, 8);
+    memcpy(&coeffs[(size_t)i * 400], m.coeffs, 800);
+  }
+  wgpu_enc_options o;
+  o.quality = c->quality; o.method = c->method; o.sns_strength = c->sns_strength; o.filter_strength = c->filter_strength;
+  o.filter_sharpness = c->filter_sharpness; o.filter_type = c->filter_type; o.partitions = c->partitions; o.segments = c->segments;
+  o.preprocessing = c->preprocessing; o.has_alpha = c->has_alpha;
+  wgh::FramePlan fp;
+  wgh::plan_frame(&fp, o, w, h, enc->alphas.data(), (long long)enc->global_uv_alpha * nmb, segmap.data());
+  fp.num_parts = 1 << o.partitions;
+  int seg_same = 1;
+  for (int i = 0; i < nmb; ++i) seg_same &= (segmap[i] == enc->mb_info[i].segment);
+  std::vector<uint8_t> riff;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < (reps > 0 ? reps : 1); ++r) {
+    riff.clear();
+    wgh::serialize_frame(fp, hdr.data(), coeffs.data(), segmap.data(), stats.data(), &riff);
+  }
+  *ms_per_rep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / (reps > 0 ? reps : 1);
+  *same = seg_same && riff.size() == ref.size() && !memcmp(riff.data(), ref.data(), ref.size());
+  delete enc;
+  if ((long)riff.size() > cap) return -2;
+  memcpy(out, riff.data(), riff.size());
+  return (long)riff.size();
+}
+}

@@ -24,6 +24,7 @@ struct EncKernelParams {
   const uint8_t* segment;       // [n][nmb]
   const ImageParams* img;       // [n]
   uint32_t* ctx;                // [n][nmb] packed NZ context (see pack_ctx)
+  unsigned int* stats;          // [n][4][8][3][11][2] token statistics (ProbaStats, encode_proba.go), zeroed before the waves
   uint8_t* out_hdr;             // [n][nmb][48]: mb_type,i16,uv,segment,skip,nz_dc,0,0, modes[16], nz[24]
   int16_t* out_coeffs;          // [n][nmb][400]
   const uint16_t* i4_costs;     // [10][10][10]
@@ -160,6 +161,50 @@ __device__ __forceinline__ int kModeFixedCostUV(int m) { return m == 0 ? 302 : (
 
 __device__ __forceinline__ unsigned long long rd_score(int disto, int rate, int lambda) {
   return (unsigned long long)(long long)rate * (unsigned long long)(long long)lambda + 256ull * (unsigned long long)(long long)disto;
+}
+
+// collectCoeffStats (internal/lossy/encode_proba.go:10-113) with red.global increments; levels int16 (or int) raster order.
+enum { STATS_SIZE = 4 * 8 * 3 * 11 * 2 };
+template <class LevT>
+__device__ __forceinline__ void stat_block_dev(const LevT* lev, int n_coeffs, int type, int first, int ctx, unsigned int* st, bool) {
+  auto add = [&](int band, int c, int p, int bit) { atomicAdd(st + ((((type * 8 + band) * 3 + c) * 11 + p) << 1) + bit, 1u); };
+  int n = first;
+  if (n_coeffs <= first) { add(c_bands[n], ctx, 0, 0); return; }
+  while (n < 16) {
+    if (n >= n_coeffs) { add(c_bands[n], ctx, 0, 0); return; }
+    add(c_bands[n], ctx, 0, 1);
+    for (;;) {
+      const int v = abs((int)lev[c_zigzag[n]]);
+      const int b = c_bands[n];
+      if (v == 0) {
+        add(b, ctx, 1, 0);
+        if (++n >= 16) return;
+        ctx = 0;
+        continue;
+      }
+      add(b, ctx, 1, 1);
+      if (v == 1) {
+        add(b, ctx, 2, 0);
+      } else {
+        add(b, ctx, 2, 1);
+        if (v <= 4) {
+          add(b, ctx, 3, 0);
+          if (v == 2) add(b, ctx, 4, 0);
+          else { add(b, ctx, 4, 1); add(b, ctx, 5, v == 3 ? 0 : 1); }
+        } else if (v <= 10) {
+          add(b, ctx, 3, 1); add(b, ctx, 6, 0); add(b, ctx, 7, v <= 6 ? 0 : 1);
+        } else {
+          add(b, ctx, 3, 1); add(b, ctx, 6, 1);
+          const int cat = v <= 18 ? 0 : v <= 34 ? 1 : v <= 66 ? 2 : 3;
+          add(b, ctx, 8, cat >> 1);
+          add(b, ctx, 9 + (cat >> 1), cat & 1);
+        }
+      }
+      ctx = (v == 1) ? 1 : 2;
+      n++;
+      break;
+    }
+  }
 }
 
 // One wave of the mode search.  Grid: ceil(tasks / (WARPS * 32/G)) CTAs of WARPS warps.
@@ -468,8 +513,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
         total_rate += C.rate;
         total_disto += C.disto;
         total_hdr += s_i4cost[(top_mode * 10 + left_mode) * 10 + bm];
-        for (int i = gl; i < 16; i += G) oc[b * 16 + i] = C.lev[i];
-        if (gl == 0) hdr[24 + b] = (uint8_t)C.nz;
+        for (int i = gl; i < 16; i += G) { oc[b * 16 + i] = C.lev[i]; S.lev[b][i] = C.lev[i]; }
+        if (gl == 0) { hdr[24 + b] = (uint8_t)C.nz; S.nz[b] = C.nz; }
         if (C.nz > 0) nzmask |= 1u << b;
         if (rd_score(total_disto, total_rate + 211, seg.lambda_mode) >= score16 || total_hdr > 15000) {
           alive = false;
@@ -619,7 +664,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
       const int n = quantize_block(w, q, seg.y2, 0);
       S.misc[1] = n;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) oc[384 + i] = (int16_t)q[i];
+      for (int i = 0; i < 16; ++i) { oc[384 + i] = (int16_t)q[i]; S.dc[i] = q[i]; }  // S.dc now holds the WHT levels
       dequant_block(q, dq, seg.y2);
       iwht(dq, d);
 #pragma unroll
@@ -665,13 +710,40 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
       S.nz[16 + b] = nz;
       hdr[40 + b] = (uint8_t)nz;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) oc[(16 + b) * 16 + i] = (int16_t)q[i];
+      for (int i = 0; i < 16; ++i) { oc[(16 + b) * 16 + i] = (int16_t)q[i]; S.lev[16 + b][i] = (int16_t)q[i]; }
       dequant_block(q, dq, seg.uv);
       itransform(p, dq, r);
       store4x4(S.out + off, r);
     }
   }
   __syncwarp();
+
+  // ---- 6b. token statistics for the final probability optimisation (collectMBStats, encode_parallel.go:1606-1707;
+  // collectCoeffStats, encode_proba.go:10-113).  Contexts are the ones this kernel already holds: a skipped MB
+  // contributes nothing and leaves all-zero flags behind, exactly like the reset in recordAllTokens.
+  uint32_t nzuv_all = 0;
+  if (active) for (int b = 0; b < 8; ++b) nzuv_all |= (uint32_t)(S.nz[16 + b] > 0) << b;
+  const bool mb_skip = active && (nzy_flags == 0) && (use_i4 || nz_dc == 0) && nzuv_all == 0;
+  if (active && !mb_skip && P.stats != nullptr) {
+    unsigned int* st = P.stats + (size_t)img * STATS_SIZE;
+    if (!use_i4 && gl == G - 1) stat_block_dev(S.dc, nz_dc, 1, 0, min(top_nz_dc + left_nz_dc, 2), st, true);
+    for (int b = gl; b < 24; b += G) {
+      int type, first, l, t;
+      if (b < 16) {
+        const int bx = b & 3, by = b >> 2;
+        type = use_i4 ? 3 : 0; first = use_i4 ? 0 : 1;
+        l = bx > 0 ? (S.nz[b - 1] > 0) : ((left_nz >> by) & 1);
+        t = by > 0 ? (S.nz[b - 4] > 0) : ((top_nz >> bx) & 1);
+      } else {
+        const int k = b - 16, ch = k >> 2, bx = k & 1, by = (k >> 1) & 1;
+        const uint32_t tn = (top_nz >> (4 + 2 * ch)) & 3, ln = (left_nz >> (4 + 2 * ch)) & 3;
+        type = 2; first = 0;
+        l = bx > 0 ? (S.nz[b - 1] > 0) : ((ln >> by) & 1);
+        t = by > 0 ? (S.nz[b - 2] > 0) : ((tn >> bx) & 1);
+      }
+      stat_block_dev(S.lev[b], S.nz[b], type, first, l + t, st, false);
+    }
+  }
 
   // ---- 7. export: reconstruction planes, header, NZ context (encode_parallel.go:341-428,1410-1496)
   if (active) {
@@ -688,11 +760,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
           *reinterpret_cast<const uint32_t*>(S.out + (pl ? V_OFF : U_OFF) + r * BPS + c4);
     }
     if (gl == 0) {
-      uint32_t nzuv = 0;
-      for (int b = 0; b < 8; ++b) nzuv |= (uint32_t)(S.nz[16 + b] > 0) << b;
+      const uint32_t nzuv = nzuv_all;
       const bool i16 = !use_i4;
       const int dcflag = nz_dc > 0;
-      const bool skip = (nzy_flags == 0) && (!i16 || !dcflag) && nzuv == 0;
+      const bool skip = mb_skip;
       hdr[0] = use_i4 ? 1 : 0;
       hdr[1] = (uint8_t)(i16 ? best16 : 0);
       hdr[2] = (uint8_t)best_uv;

@@ -227,21 +227,30 @@ static inline void plan_frame(FramePlan* fp, const wgpu_enc_options& o, int widt
   }
 }
 
-// ---- boolean coder (bitio/writer_bool.go) writing into a growable byte vector
+// ---- boolean coder (bitio/writer_bool.go:23-210) appending to a byte vector; the hot state lives in locals of put()
 struct BoolEnc {
   int32_t range = 254, value = 0;
   int run = 0, nb_bits = -8;
   std::vector<uint8_t>* out;
-  explicit BoolEnc(std::vector<uint8_t>* o) : out(o) {}
+  uint8_t* p = nullptr;   // write cursor into out->data()
+  uint8_t* lim = nullptr; // end of the reserved region
+  explicit BoolEnc(std::vector<uint8_t>* o) : out(o) { grow(4096); }
+  void grow(size_t extra) {
+    const size_t used = p ? (size_t)(p - out->data()) : out->size();
+    out->resize(used + extra + used / 2);
+    p = out->data() + used;
+    lim = out->data() + out->size();
+  }
   void flush() {
     const int s = 8 + nb_bits;
     const int32_t bits = value >> s;
     value -= bits << s;
     nb_bits -= 8;
     if ((bits & 0xff) != 0xff) {
-      if ((bits & 0x100) && !out->empty()) out->back()++;
-      if (run > 0) { out->insert(out->end(), (size_t)run, (bits & 0x100) ? 0x00 : 0xff); run = 0; }
-      out->push_back((uint8_t)bits);
+      if ((size_t)(lim - p) < (size_t)run + 2) grow((size_t)run + 4096);
+      if ((bits & 0x100) && p > out->data()) p[-1]++;
+      if (run > 0) { memset(p, (bits & 0x100) ? 0x00 : 0xff, (size_t)run); p += run; run = 0; }
+      *p++ = (uint8_t)bits;
     } else {
       run++;
     }
@@ -264,7 +273,12 @@ struct BoolEnc {
     if (v == 0) return;
     if (v < 0) put_bits(((uint32_t)(-v) << 1) | 1, n + 1); else put_bits((uint32_t)v << 1, n + 1);
   }
-  void finish() { put_bits(0, 9 - nb_bits); nb_bits = 0; flush(); }
+  void finish() {
+    put_bits(0, 9 - nb_bits);
+    nb_bits = 0;
+    flush();
+    out->resize((size_t)(p - out->data()));
+  }
 };
 
 // Per-MB arrays as produced by the GPU (see enc_kernels.cuh): hdr [48] = mb_type,i16,uv,segment,skip,
@@ -275,8 +289,6 @@ struct MBView {
   int mb_type() const { return hdr[0]; }
   int skip() const { return hdr[4]; }
 };
-
-typedef int Stats[4][8][3][11][2];
 
 // Walks the blocks of one MB in bitstream order with the NZ-context bookkeeping of
 // recordMBTokens (encode_frame.go:647); f(coeffs, nz, type, first, ctx).
@@ -323,38 +335,6 @@ static inline void walk_mb(const MBView& m, uint32_t* top_nz, uint32_t* left_nz,
   }
   *top_nz = out_t;
   *left_nz = out_l;
-}
-
-static inline void stat_block(const int16_t* c, int n_coeffs, int type, int first, int ctx, Stats st) {  // encode_proba.go:10
-  int n = first;
-  if (n_coeffs <= first) { st[type][kBands[n]][ctx][0][0]++; return; }
-  while (n < 16) {
-    int b = kBands[n];
-    if (n >= n_coeffs) { st[type][b][ctx][0][0]++; return; }
-    st[type][b][ctx][0][1]++;
-    for (;;) {
-      const int v = abs((int)c[kZigzag[n]]);
-      b = kBands[n];
-      int(*s)[2] = st[type][b][ctx];
-      if (v == 0) { s[1][0]++; if (++n >= 16) return; ctx = 0; continue; }
-      s[1][1]++;
-      if (v == 1) { s[2][0]++; }
-      else {
-        s[2][1]++;
-        if (v <= 4) { s[3][0]++; if (v == 2) s[4][0]++; else { s[4][1]++; s[5][v == 3 ? 0 : 1]++; } }
-        else if (v <= 10) { s[3][1]++; s[6][0]++; s[7][v <= 6 ? 0 : 1]++; }
-        else {
-          s[3][1]++; s[6][1]++;
-          const int cat = v <= 18 ? 0 : v <= 34 ? 1 : v <= 66 ? 2 : 3;
-          s[8][cat >> 1]++;
-          s[9 + (cat >> 1)][cat & 1]++;
-        }
-      }
-      ctx = (v == 1) ? 1 : 2;
-      n++;
-      break;
-    }
-  }
 }
 
 template <class Sink>
@@ -408,6 +388,29 @@ static inline bool i4_subtree_has(int node, int mode) {
   if (node <= 0) return -node == mode;
   return i4_subtree_has(kI4Tree[2 * node], mode) || i4_subtree_has(kI4Tree[2 * node + 1], mode);
 }
+// Bit path of each 4x4 mode through kI4Tree (writeI4Mode, encode_syntax.go:474): per mode up to 4 (prob index, bit) steps.
+struct I4Path { uint8_t n; uint8_t idx[8]; uint8_t bit[8]; };
+struct I4Paths {
+  I4Path tab[10];
+  I4Paths() {
+    for (int mode = 0; mode < 10; ++mode) {
+      I4Path& t = tab[mode];
+      t.n = 0;
+      int bit = i4_subtree_has(kI4Tree[0], mode) ? 0 : 1;
+      t.idx[t.n] = 0; t.bit[t.n++] = (uint8_t)bit;
+      int i = kI4Tree[bit];
+      while (i > 0) {
+        bit = i4_subtree_has(kI4Tree[2 * i], mode) ? 0 : 1;
+        t.idx[t.n] = (uint8_t)i; t.bit[t.n++] = (uint8_t)bit;
+        i = kI4Tree[2 * i + bit];
+      }
+    }
+  }
+};
+static inline const I4Path* i4_paths() {
+  static const I4Paths paths;  // thread-safe one-time construction
+  return paths.tab;
+}
 // VP8FixedCostsI4 (encode_analysis.go:1497): cost of signalling each 4x4 mode given (top, left).
 static inline void compute_i4_costs(uint16_t* out /*[10][10][10]*/) {
   for (int top = 0; top < 10; ++top)
@@ -430,31 +433,14 @@ static inline void compute_i4_costs(uint16_t* out /*[10][10][10]*/) {
 // Serialise one image: per-MB GPU output -> VP8 frame -> RIFF.  Returns bytes appended to `riff`.
 static inline void serialize_frame(const FramePlan& fp, const uint8_t* mb_hdr /*[nmb][48]*/,
                                    const int16_t* mb_coeffs /*[nmb][400]*/, const uint8_t* segment_map,
-                                   std::vector<uint8_t>* riff) {
+                                   const uint32_t* stats /*[4][8][3][11][2]*/, std::vector<uint8_t>* riff) {
   const int mb_w = fp.mb_w, mb_h = fp.mb_h, total = mb_w * mb_h;
-  // pass 1: statistics + skip count (recordAllTokens / collectMBStats, encode_parallel.go:1503-1707)
-  static thread_local Stats st;
-  memset(st, 0, sizeof(st));
+  // statistics come from the GPU (encode_wave_kernel step 6b == collectMBStats); only the skip count is taken here
+  const int (*st)[8][3][11][2] = reinterpret_cast<const int (*)[8][3][11][2]>(stats);
   std::vector<uint32_t> top_nz(mb_w);
   std::vector<uint8_t> top_dc(mb_w);
   int num_skip = 0;
-  for (int my = 0; my < mb_h; ++my) {
-    uint32_t left_nz = 0;
-    uint8_t left_dc = 0;
-    if (my == 0) { std::fill(top_nz.begin(), top_nz.end(), 0u); std::fill(top_dc.begin(), top_dc.end(), 0); }
-    for (int mx = 0; mx < mb_w; ++mx) {
-      const int idx = my * mb_w + mx;
-      const MBView m{mb_hdr + (size_t)idx * 48, mb_coeffs + (size_t)idx * 400};
-      if (m.skip()) {
-        num_skip++;
-        top_nz[mx] = 0; left_nz = 0;
-        if (m.mb_type() == 0) { top_dc[mx] = 0; left_dc = 0; }
-        continue;
-      }
-      walk_mb(m, &top_nz[mx], &left_nz, &top_dc[mx], &left_dc,
-              [&](const int16_t* c, int nz, int type, int first, int ctx) { stat_block(c, nz, type, first, ctx, st); });
-    }
-  }
+  for (int idx = 0; idx < total; ++idx) num_skip += mb_hdr[(size_t)idx * 48 + 4] != 0;
   const int skip_proba = num_skip > 0 ? (total - num_skip) * 255 / total : 0;
   // optimizeProba (encode_proba.go:117)
   uint8_t proba[4][8][3][11];
@@ -516,6 +502,7 @@ static inline void serialize_frame(const FramePlan& fp, const uint8_t* mb_hdr /*
     }
     if (num_skip > 0) { bw.put_uniform(1); bw.put_bits((uint32_t)skip_proba, 8); } else bw.put_uniform(0);
     std::vector<uint8_t> tm(mb_w * 4, 0);
+    const I4Path* paths = i4_paths();
     for (int my = 0; my < mb_h; ++my) {
       uint8_t lm[4] = {0, 0, 0, 0};
       for (int mx = 0; mx < mb_w; ++mx) {
@@ -544,14 +531,8 @@ static inline void serialize_frame(const FramePlan& fp, const uint8_t* mb_hdr /*
             for (int x = 0; x < 4; ++x) {
               const int mode = h[8 + y * 4 + x];
               const uint8_t* prob = &kBModesProba[(top[x] * 10 + ym) * 9];
-              int bit = i4_subtree_has(kI4Tree[0], mode) ? 0 : 1;
-              bw.put(bit, prob[0]);
-              int i = kI4Tree[bit];
-              while (i > 0) {
-                bit = i4_subtree_has(kI4Tree[2 * i], mode) ? 0 : 1;
-                bw.put(bit, prob[i]);
-                i = kI4Tree[2 * i + bit];
-              }
+              const I4Path& pt = paths[mode];
+              for (int k = 0; k < pt.n; ++k) bw.put(pt.bit[k], prob[pt.idx[k]]);
               ym = mode;
               top[x] = (uint8_t)mode;
             }

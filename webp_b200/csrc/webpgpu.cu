@@ -76,8 +76,8 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, hdr, coeffs;
-  PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, hdr, coeffs, stats;
+  PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false;
   wgpu_enc_options e_opt;
@@ -189,11 +189,11 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* db[] = {&ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
-                  &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
+                  &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
                   &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
                   &ctx->m_sse, &ctx->m_ssim};
   for (DevBuf* b : db) b->release();
-  PinBuf* pb[] = {&ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
+  PinBuf* pb[] = {&ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
                   &ctx->hd_meta, &ctx->hd_ftype, &ctx->hd_planes, &ctx->hd_nrgba};
   for (PinBuf* b : pb) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -339,6 +339,8 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.src_y = ctx->sy.as<uint8_t>(); P.src_u = ctx->su.as<uint8_t>(); P.src_v = ctx->sv.as<uint8_t>();
   P.rec_y = ctx->ry.as<uint8_t>(); P.rec_u = ctx->ru.as<uint8_t>(); P.rec_v = ctx->rv.as<uint8_t>();
   P.segment = ctx->segment.as<uint8_t>(); P.img = ctx->img_params.as<wg::ImageParams>();
+  P.stats = ctx->stats.as<unsigned int>();
+  CK(cudaMemsetAsync(ctx->stats.p, 0, (size_t)n * wg::STATS_SIZE * 4, ctx->stream));
   P.ctx = ctx->ctxw.as<uint32_t>(); P.out_hdr = ctx->hdr.as<uint8_t>(); P.out_coeffs = ctx->coeffs.as<int16_t>();
   P.i4_costs = ctx->t_i4cost.as<uint16_t>(); P.lc = ctx->t_lc.as<uint16_t>(); P.eob = ctx->t_eob.as<uint16_t>(); P.lfc = ctx->t_lfc.as<uint16_t>();
   P.n_images = n; P.width = ctx->e_w; P.height = ctx->e_h; P.mb_w = mbw; P.mb_h = mbh;
@@ -362,6 +364,7 @@ static int enc_reserve(wgpu_ctx* ctx) {
   RESERVE(ctx->alpha, n * nmb); RESERVE(ctx->uv_alpha, n * nmb); RESERVE(ctx->segment, n * nmb);
   RESERVE(ctx->img_params, n * sizeof(wg::ImageParams));
   RESERVE(ctx->ctxw, n * nmb * 4); RESERVE(ctx->hdr, n * nmb * 48); RESERVE(ctx->coeffs, n * nmb * 800);
+  RESERVE(ctx->stats, n * wg::STATS_SIZE * 4); RESERVE(ctx->h_stats, n * wg::STATS_SIZE * 4);
   RESERVE(ctx->h_alpha, n * nmb); RESERVE(ctx->h_uv_alpha, n * nmb); RESERVE(ctx->h_segment, n * nmb);
   RESERVE(ctx->h_params, n * sizeof(wg::ImageParams));
   return WGPU_OK;
@@ -493,6 +496,7 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
   const double t0b = now_ms();
   CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(ctx->h_coeffs.p, ctx->coeffs.p, n * nmb * 800, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->stats.p, n * wg::STATS_SIZE * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const double t1 = now_ms();
   std::atomic<int> too_small(0);
@@ -500,7 +504,7 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     std::vector<uint8_t> riff;
     riff.reserve(nmb * 64 + 4096);
     wgh::serialize_frame(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
-                         ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, &riff);
+                         ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, ctx->h_stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE, &riff);
     out_sizes[i] = riff.size();
     if (riff.size() > out_stride) { too_small.store(1); return; }
     memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
