@@ -54,6 +54,7 @@ struct MBShared {
   int dcrec[16];
   int nz[24];
   int sse[10];
+  uint8_t smode[12];
   I4Cand cand[3];
   int misc[8];
 };
@@ -261,15 +262,24 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
   if (active) {
     const int x0 = mx * 16, y0 = my * 16;
     const int ww = min(16, P.width - x0), hh = min(16, P.height - y0);
-    for (int i = gl; i < 256; i += G) {
-      const int r = i >> 4, c = i & 15;
-      S.in[r * 16 + c] = src_y[(size_t)(y0 + min(r, hh - 1)) * y_stride + x0 + min(c, ww - 1)];
-    }
-    const int uvw = (ww + 1) >> 1, uvh = (hh + 1) >> 1;
-    for (int i = gl; i < 128; i += G) {
-      const int pl = i >> 6, r = (i >> 3) & 7, c = i & 7;
-      const uint8_t* sp = pl ? src_v : src_u;
-      S.in[256 + pl * 64 + r * 8 + c] = sp[(size_t)(my * 8 + min(r, uvh - 1)) * uv_stride + mx * 8 + min(c, uvw - 1)];
+    if (ww == 16 && hh == 16) {  // interior macroblock: 32-bit loads
+      for (int i = gl; i < 64; i += G)
+        reinterpret_cast<uint32_t*>(S.in)[i] = *reinterpret_cast<const uint32_t*>(src_y + (size_t)(y0 + (i >> 2)) * y_stride + x0 + (i & 3) * 4);
+      for (int i = gl; i < 32; i += G) {
+        const uint8_t* sp = (i >> 4) ? src_v : src_u;
+        reinterpret_cast<uint32_t*>(S.in + 256)[i] = *reinterpret_cast<const uint32_t*>(sp + (size_t)(my * 8 + ((i >> 1) & 7)) * uv_stride + mx * 8 + (i & 1) * 4);
+      }
+    } else {  // partial macroblock: replicate the last valid sample / row inside the block (importBlock)
+      for (int i = gl; i < 256; i += G) {
+        const int r = i >> 4, c = i & 15;
+        S.in[r * 16 + c] = src_y[(size_t)(y0 + min(r, hh - 1)) * y_stride + x0 + min(c, ww - 1)];
+      }
+      const int uvw = (ww + 1) >> 1, uvh = (hh + 1) >> 1;
+      for (int i = gl; i < 128; i += G) {
+        const int pl = i >> 6, r = (i >> 3) & 7, c = i & 7;
+        const uint8_t* sp = pl ? src_v : src_u;
+        S.in[256 + pl * 64 + r * 8 + c] = sp[(size_t)(my * 8 + min(r, uvh - 1)) * uv_stride + mx * 8 + min(c, uvw - 1)];
+      }
     }
     // context from the reconstruction planes (full padded MBs are stored, so partial MBs are exact)
     uint8_t* o = S.out;
@@ -437,36 +447,57 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
       const int t = by > 0 ? ((nzmask >> (b - 4)) & 1) : ((top_nz >> bx) & 1);
       const int nz_ctx = l + t;
       int e[13], s[16];
+      int n_cand = 0;
       if (alive) {
         load_pred4_ctx(S.out2 + off, e);
         load_src_block(S.in, b, s);
-        // pre-screen: prediction SSE of every eligible mode (encode_parallel.go:955-966)
+        // pre-screen: prediction SSE of every eligible mode (encode_parallel.go:955-966), written as the compact
+        // candidate list the reference builds (position = number of eligible modes before this one)
+        uint32_t elig = 0;
+#pragma unroll
+        for (int m = 0; m < 10; ++m)
+          if (!((!has_top && needs_top4(m)) || (!has_left && needs_left4(m)))) elig |= 1u << m;
+        n_cand = __popc(elig);
         for (int m = gl; m < 10; m += G) {
-          int v = 0x7fffffff;
-          if (!((!has_top && needs_top4(m)) || (!has_left && needs_left4(m)))) {
+          if ((elig >> m) & 1) {
             int p[16];
             pred4(m, e, p);
-            v = sse16(s, p);
+            const int pos = __popc(elig & ((1u << m) - 1));
+            S.sse[pos] = sse16(s, p);
+            S.smode[pos] = (uint8_t)m;
           }
-          S.sse[m] = v;
         }
       }
       __syncwarp();
       int K = 0;
       int cand_mode[3] = {0, 0, 0};
-      if (alive) {  // exact selection-sort emulation (encode_parallel.go:969-983); every lane redundantly
-        int cm[10], cs[10], n_c = 0;
+      if (alive) {  // exact selection-sort emulation (encode_parallel.go:969-983) in registers, every lane redundantly
+        int cm[10], cs[10];
 #pragma unroll
-        for (int m = 0; m < 10; ++m) {
-          const int v = S.sse[m];
-          if (v != 0x7fffffff) { cm[n_c] = m; cs[n_c] = v; n_c++; }
+        for (int j = 0; j < 10; ++j) {
+          const bool ok = j < n_cand;
+          cs[j] = ok ? S.sse[j] : 0x7fffffff;
+          cm[j] = ok ? (int)S.smode[j] : 0;
         }
-        K = min(P.max_i4_modes, n_c);
-        for (int i = 0; i < K; ++i) {
-          int mi = i;
-          for (int j = i + 1; j < n_c; ++j) if (cs[j] < cs[mi]) mi = j;
-          if (mi != i) { const int tm = cm[i], ts = cs[i]; cm[i] = cm[mi]; cs[i] = cs[mi]; cm[mi] = tm; cs[mi] = ts; }
-          cand_mode[i] = cm[i];
+        K = min(P.max_i4_modes, n_cand);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (i < K) {
+            int mi = i, mv = cs[i];
+#pragma unroll
+            for (int j = i + 1; j < 10; ++j) { const bool lt = cs[j] < mv; mv = lt ? cs[j] : mv; mi = lt ? j : mi; }
+            const int tm = cm[i], ts = cs[i];
+            int sm = tm;
+#pragma unroll
+            for (int j = i + 1; j < 10; ++j) {
+              const bool hit = (j == mi);
+              sm = hit ? cm[j] : sm;
+              cm[j] = hit ? tm : cm[j];
+              cs[j] = hit ? ts : cs[j];
+            }
+            cm[i] = sm; cs[i] = mv;
+            cand_mode[i] = sm;
+          }
         }
       }
       // full RD on the K candidates, one lane each
@@ -476,8 +507,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
           int p[16], c[16], q[16], dq[16], r[16];
           pred4(mode, e, p);
           ftransform(s, p, c);
-          const int nz = trellis ? trellis_block(c, q, seg.y1, 0, 3, nz_ctx, seg.tlambda_i4, T)
-                                 : quantize_block(c, q, seg.y1, 0);
+          I4Cand& C = S.cand[k];
+          int nz;
+          if (trellis) {  // in place on the candidate's level slot in shared memory
+#pragma unroll
+            for (int i = 0; i < 16; ++i) C.lev[i] = (int16_t)c[i];
+            nz = trellis_block_smem(C.lev, seg.y1, 0, 3, nz_ctx, seg.tlambda_i4, T);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) q[i] = C.lev[i];
+          } else {
+            nz = quantize_block(c, q, seg.y1, 0);
+          }
           dequant_block(q, dq, seg.y1);
           itransform(p, dq, r);
           int disto = sse16(s, r);
@@ -491,7 +531,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
           }
           rate += token_cost(q, nz, 3, nz_ctx, 0, T);
           rate += s_i4cost[(top_mode * 10 + left_mode) * 10 + mode];
-          I4Cand& C = S.cand[k];
           C.score = rd_score(disto, rate, seg.lambda_i4);
           C.disto = disto; C.rate = rate; C.nz = nz; C.mode = mode;
 #pragma unroll
@@ -644,12 +683,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
           const int by = by_lo + k, bx = d - by, b = by * 4 + bx;
           const int l = bx > 0 ? (S.nz[b - 1] > 0) : ((left_nz >> by) & 1);
           const int t = by > 0 ? (S.nz[b - 4] > 0) : ((top_nz >> bx) & 1);
-          int c[16], q[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) c[i] = S.lev[b][i];
-          S.nz[b] = trellis_block(c, q, seg.y1, 1, 0, l + t, seg.tlambda_i16, T);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) S.lev[b][i] = (int16_t)q[i];
+          S.nz[b] = trellis_block_smem(S.lev[b], seg.y1, 1, 0, l + t, seg.tlambda_i16, T);
         }
       }
       __syncwarp();

@@ -169,11 +169,15 @@ __global__ void dsp_quantize_kernel(int n, const int16_t* in, SegQuant sq, int f
 struct TabPtrs { const uint16_t* lc; const uint16_t* eob; const uint16_t* lfc; };
 __global__ void dsp_trellis_kernel(int n, const int16_t* in, SegQuant sq, int first, int ctx_type, const int32_t* ctx0, int lambda,
                                    TabPtrs tp, int16_t* out, int32_t* nz) {
+  __shared__ int16_t s_io[128][16];  // the trellis works in place in shared memory (zigzag-indexed access)
   WG_TID;
   CostTabs T; T.lc = tp.lc; T.eob = tp.eob; T.lfc = tp.lfc;
-  int c[16], q[16]; load16s16(in + 16 * (size_t)i, c);
-  nz[i] = trellis_block(c, q, sq, first, ctx_type, ctx0[i], lambda, T);
-  store16s16(out + 16 * (size_t)i, q);
+  int16_t* io = s_io[threadIdx.x];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) io[k] = in[16 * (size_t)i + k];
+  nz[i] = trellis_block_smem(io, sq, first, ctx_type, ctx0[i], lambda, T);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) out[16 * (size_t)i + k] = io[k];
 }
 __global__ void dsp_token_cost_kernel(int n, const int16_t* levels, const int32_t* nzc, int ctx_type, const int32_t* ctx0, int first,
                                       TabPtrs tp, int32_t* out) {

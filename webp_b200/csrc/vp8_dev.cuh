@@ -320,108 +320,123 @@ __device__ __forceinline__ int token_cost(const int* lev, int nz_count, int type
   return cost;
 }
 
-// TrellisQuantizeBlock (internal/lossy/encode_trellis.go:23-324).  in/out raster order, register resident: the
-// position loop is fully unrolled so the zigzag walk and the backtracking path use static indices.  Scores are
-// int64 as in the reference (rate*lambda reaches 2^33).  Path entry per (position, ctx): 13-bit signed level,
-// 2-bit previous ctx, valid bit.
-__device__ __forceinline__ uint32_t trellis_pack(int level, int prev) { return ((uint32_t)level & 0x1fffu) | ((uint32_t)prev << 13) | 0x8000u; }
-__device__ __forceinline__ int trellis_block(const int* in, int* out, const SegQuant& sq, int first, int type,
-                                             int initial_ctx, int lambda, const CostTabs& T) {
-  constexpr int kZig[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
-  constexpr int kBnd[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
-  constexpr int kWt[16] = {30, 27, 19, 11, 27, 24, 17, 10, 19, 17, 12, 8, 11, 10, 8, 6};  // kWeightTrellis, raster
-  int c0[16];  // |coeff| + sharpen, clamped at 0, raster order
-  bool non_zero = false;
+// TrellisQuantizeBlock (internal/lossy/encode_trellis.go:23-324), in place on 16 int16 values in SHARED memory
+// (raster order: coefficients in, levels out).  The position loop is ROLLED (a fully unrolled 16 x 3 x 3 Viterbi is
+// ~5.5k instructions and thrashes the instruction cache, profiles/r1_mode_search_c_*.md); shared memory provides the
+// zigzag-indexed access, the survivor path is 10 bits per position in three 64-bit registers:
+//   bits 0-2  ctx0: prev ctx (2) + valid          bits 3-5  ctx1: prev ctx + valid (level is L0 if L0 == 1 else L0+1)
+//   bits 6-9  ctx2: prev ctx + valid + "level is L0+1"
+// Scores are int64 as in the reference.  An unreachable state carries kBig (the reference's kMaxScore = 1<<60); real
+// scores stay below 2^50, so >= kThr means "not valid" and transitions out of an unreachable state can never beat a
+// reachable one -- the reference's `if (!prev[pc].valid) continue` without a branch.
+__device__ __forceinline__ int trellis_block_smem(int16_t* io, const SegQuant& sq, int first, int type, int initial_ctx,
+                                                  int lambda, const CostTabs& T) {
+  const int quant_ac = sq.quant, quant_dc = sq.dc_quant;
+  const unsigned iq_ac = (unsigned)sq.iquant, iq_dc = (unsigned)sq.dc_iquant;
+  uint32_t neg_mask = 0;  // bit i: raster coefficient i is negative
+  {
+    bool non_zero = false;  // all-zero pre-scan with neutral bias (encode_trellis.go:39-98)
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    c0[i] = max(abs(in[i]) + sq.sharpen[i], 0);
-    out[i] = 0;
-  }
-  {  // all-zero pre-scan with neutral bias (encode_trellis.go:39-98); zigzag position >= first <=> raster != 0 or first == 0
-    if (first == 0) non_zero |= (((unsigned)c0[0] * (unsigned)sq.dc_iquant) >> 17) > 0;
+    for (int i = 0; i < 16; ++i) {
+      const int raw = io[i];
+      const int c0 = max(abs(raw) + sq.sharpen[i], 0);
+      neg_mask |= (raw < 0 ? 1u : 0u) << i;
+      io[i] = (int16_t)c0;  // <= 32767 + sharpen is clamped by the int16 store only for inputs the encoder never produces
+      if (i > 0 || first == 0) non_zero |= (((unsigned)c0 * (i == 0 ? iq_dc : iq_ac)) >> 17) > 0;
+    }
+    if (!non_zero) {
 #pragma unroll
-    for (int i = 1; i < 16; ++i) non_zero |= (((unsigned)c0[i] * (unsigned)sq.iquant) >> 17) > 0;
-    if (!non_zero) return 0;
+      for (int i = 0; i < 16; ++i) io[i] = 0;
+      return 0;
+    }
   }
   initial_ctx = min(initial_ctx, 2);
   const uint16_t* lc = T.lc + type * (8 * 3 * LC_LEVELS);
   const uint16_t* eob = T.eob + type * (8 * 3);
-  const long long kInvalid = 0x7fffffffffffffffll;
-  long long ps0 = initial_ctx == 0 ? 0 : kInvalid, ps1 = initial_ctx == 1 ? 0 : kInvalid, ps2 = initial_ctx == 2 ? 0 : kInvalid;
+  const long long kBig = 1ll << 60, kThr = 1ll << 59;
+  long long ps0 = initial_ctx == 0 ? 0 : kBig, ps1 = initial_ctx == 1 ? 0 : kBig, ps2 = initial_ctx == 2 ? 0 : kBig;
   const long long lam = lambda;
   long long best_terminal = (long long)eob[c_bands[first] * 3 + initial_ctx] * lam;
   int best_last_n = -1, best_last_ctx = -1;
-  uint32_t path01[16], path2[16];
-#pragma unroll
-  for (int n = 0; n < 16; ++n) {
-    path01[n] = 0; path2[n] = 0;
-    if (n < first) continue;
-    const int zig = kZig[n];
-    const int band = kBnd[n + 1];  // sic: the next position's band (encode_trellis.go:151)
-    const bool neg = in[zig] < 0;
-    const int coeff0 = c0[zig];
-    const int quant = (n == 0) ? sq.dc_quant : sq.quant;
-    const unsigned iquant = (n == 0) ? (unsigned)sq.dc_iquant : (unsigned)sq.iquant;
+  unsigned long long pw0 = 0, pw1 = 0, pw2 = 0;  // survivor paths: positions 0-5, 6-11, 12-15
+#pragma unroll 1
+  for (int n = first; n < 16; ++n) {
+    const int zig = c_zigzag[n];
+    const int band = c_bands[n + 1];  // sic: the next position's band (encode_trellis.go:151)
+    const int coeff0 = io[zig];
+    const int quant = (n == 0) ? quant_dc : quant_ac;
+    const unsigned iquant = (n == 0) ? iq_dc : iq_ac;
     const int L0 = min((int)(((unsigned)coeff0 * iquant) >> 17), 2047);
     const int thresh = min((int)(((unsigned)coeff0 * iquant + 65536u) >> 17), 2047);
+    io[zig] = (int16_t)L0;  // the backtrack only needs the base level
     const bool has_l0 = L0 > 0 && L0 <= thresh;
     const bool has_l1 = L0 + 1 <= 2047 && L0 + 1 <= thresh;
     const int c0sq = coeff0 * coeff0;
     const int e0 = coeff0 - L0 * quant, e1 = coeff0 - (L0 + 1) * quant;
-    const long long disto_l0 = (long long)(e0 * e0 - c0sq) * (kWt[zig] * 256);
-    const long long disto_l1 = (long long)(e1 * e1 - c0sq) * (kWt[zig] * 256);
+    const int wt256 = c_weight_trellis[zig] * 256;
+    const long long disto_l0 = (long long)(e0 * e0 - c0sq) * wt256;
+    const long long disto_l1 = (long long)(e1 * e1 - c0sq) * wt256;
     const int lfc0 = T.lfc[L0], lfc1 = T.lfc[min(L0 + 1, 2047)];
     const int li0 = min(L0, LC_LEVELS - 1), li1 = min(L0 + 1, LC_LEVELS - 1);
-    const int sl0 = neg ? -L0 : L0, sl1 = neg ? -(L0 + 1) : (L0 + 1);
-    const bool l0_to_1 = (L0 == 1), l1_to_1 = (L0 == 0);  // next ctx of level L0 / L0+1 is 1, else 2
-    long long cs0 = kInvalid, cs1 = kInvalid, cs2 = kInvalid;  // kInvalid doubles as "not valid yet" (scores stay far below it)
-    uint32_t e_0 = 0, e_1 = 0, e_2 = 0;
+    // ctx 1 receives at most one candidate (L0 == 1: level L0; L0 == 0: level L0+1); ctx 2 receives level L0 when
+    // L0 >= 2, then level L0+1 when L0 >= 1, in that order (strict '<' keeps the earlier on ties, as the reference does)
+    const bool c1_from_l0 = (L0 == 1);
+    const bool c1_ok = c1_from_l0 ? has_l0 : (L0 == 0 && has_l1);
+    const int c1_li = c1_from_l0 ? li0 : li1, c1_lfc = c1_from_l0 ? lfc0 : lfc1;
+    const long long c1_d = c1_from_l0 ? disto_l0 : disto_l1;
+    const bool c2a_ok = has_l0 && L0 >= 2, c2b_ok = has_l1 && L0 >= 1;
+    long long cs0 = 2 * kBig, cs1 = 2 * kBig, cs2 = 2 * kBig;
+    uint32_t p_0 = 0, p_1 = 0, p_2 = 0;  // prev ctx of the survivor; p_2 bit 3 = took level L0+1
     const uint16_t* row = lc + band * 3 * LC_LEVELS;
 #pragma unroll
     for (int pc = 0; pc < 3; ++pc) {
       const long long prev = pc == 0 ? ps0 : (pc == 1 ? ps1 : ps2);
-      if (prev == kInvalid) continue;
       const uint16_t* r = row + pc * LC_LEVELS;
       const long long t0 = prev + (long long)r[0] * lam;
-      if (t0 < cs0) { cs0 = t0; e_0 = trellis_pack(0, pc); }
-      if (has_l0) {
-        const long long ts = prev + (long long)((int)r[li0] + lfc0) * lam + disto_l0;
-        if (l0_to_1) { if (ts < cs1) { cs1 = ts; e_1 = trellis_pack(sl0, pc); } }
-        else         { if (ts < cs2) { cs2 = ts; e_2 = trellis_pack(sl0, pc); } }
-      }
-      if (has_l1) {
-        const long long ts = prev + (long long)((int)r[li1] + lfc1) * lam + disto_l1;
-        if (l1_to_1) { if (ts < cs1) { cs1 = ts; e_1 = trellis_pack(sl1, pc); } }
-        else         { if (ts < cs2) { cs2 = ts; e_2 = trellis_pack(sl1, pc); } }
-      }
+      const long long t1 = c1_ok ? prev + (long long)((int)r[c1_li] + c1_lfc) * lam + c1_d : kBig;
+      const long long t2a = c2a_ok ? prev + (long long)((int)r[li0] + lfc0) * lam + disto_l0 : kBig;
+      const long long t2b = c2b_ok ? prev + (long long)((int)r[li1] + lfc1) * lam + disto_l1 : kBig;
+      const bool u0 = t0 < cs0;
+      cs0 = u0 ? t0 : cs0; p_0 = u0 ? pc : p_0;
+      const bool u1 = t1 < cs1;
+      cs1 = u1 ? t1 : cs1; p_1 = u1 ? pc : p_1;
+      const bool u2a = t2a < cs2;
+      cs2 = u2a ? t2a : cs2; p_2 = u2a ? pc : p_2;
+      const bool u2b = t2b < cs2;
+      cs2 = u2b ? t2b : cs2; p_2 = u2b ? (pc | 8u) : p_2;
     }
-    path01[n] = e_0 | (e_1 << 16);
-    path2[n] = e_2;
+    const bool v0 = cs0 < kThr, v1 = cs1 < kThr, v2 = cs2 < kThr;
+    const unsigned long long ent = (unsigned long long)((p_0 | (v0 ? 4u : 0u)) | ((p_1 | (v1 ? 4u : 0u)) << 3) |
+                                                        (((p_2 & 3u) | (v2 ? 4u : 0u) | (p_2 & 8u)) << 6));
+    const int sh = (n % 6) * 10;
+    if (n < 6) pw0 |= ent << sh; else if (n < 12) pw1 |= ent << sh; else pw2 |= ent << sh;
     {
       const uint16_t* eb = eob + band * 3;
-      if (cs1 != kInvalid) {
-        const long long s = cs1 + (n < 15 ? (long long)eb[1] * lam : 0ll);
-        if (s < best_terminal) { best_terminal = s; best_last_n = n; best_last_ctx = 1; }
-      }
-      if (cs2 != kInvalid) {
-        const long long s = cs2 + (n < 15 ? (long long)eb[2] * lam : 0ll);
-        if (s < best_terminal) { best_terminal = s; best_last_n = n; best_last_ctx = 2; }
-      }
+      const long long s1 = cs1 + (n < 15 ? (long long)eb[1] * lam : 0ll);  // unreachable states stay >= kThr and never win
+      const bool b1 = s1 < best_terminal;
+      best_terminal = b1 ? s1 : best_terminal; best_last_n = b1 ? n : best_last_n; best_last_ctx = b1 ? 1 : best_last_ctx;
+      const long long s2 = cs2 + (n < 15 ? (long long)eb[2] * lam : 0ll);
+      const bool b2 = s2 < best_terminal;
+      best_terminal = b2 ? s2 : best_terminal; best_last_n = b2 ? n : best_last_n; best_last_ctx = b2 ? 2 : best_last_ctx;
     }
-    ps0 = cs0; ps1 = cs1; ps2 = cs2;
+    ps0 = v0 ? cs0 : kBig; ps1 = v1 ? cs1 : kBig; ps2 = v2 ? cs2 : kBig;
   }
-  if (best_last_n < 0) return 0;
   int ctx = best_last_ctx, last = 0;
-#pragma unroll
-  for (int n = 15; n >= 0; --n) {
-    if (n > best_last_n || n < first) continue;
-    const uint32_t e = ctx == 0 ? (path01[n] & 0xffffu) : (ctx == 1 ? (path01[n] >> 16) : path2[n]);
-    if (e & 0x8000u) {
-      const int lv = ((int)(e << 19)) >> 19;  // sign-extend 13 bits
-      out[kZig[n]] = lv;
-      if (lv != 0 && last == 0) last = n + 1;
-      ctx = (e >> 13) & 3;
-    }
+  if (first == 1) io[0] = 0;
+#pragma unroll 1
+  for (int n = 15; n >= first; --n) {
+    const int zig = c_zigzag[n];
+    const unsigned long long w = n < 6 ? pw0 : (n < 12 ? pw1 : pw2);
+    const uint32_t ent = (uint32_t)(w >> ((n % 6) * 10)) & 0x3ffu;
+    const uint32_t e = ctx == 0 ? (ent & 7u) : (ctx == 1 ? ((ent >> 3) & 7u) : ((ent >> 6) & 15u));
+    const bool take = n <= best_last_n && (e & 4u);
+    const int L0 = io[zig];
+    // level by landing ctx: ctx0 -> 0; ctx1 -> 1 (L0 if L0 == 1 else L0+1, both equal 1); ctx2 -> L0 or L0+1
+    const int mag = ctx == 0 ? 0 : (ctx == 1 ? 1 : L0 + (int)((e >> 3) & 1u));
+    const int lv = ((neg_mask >> zig) & 1u) ? -mag : mag;
+    io[zig] = (int16_t)(take ? lv : 0);
+    last = (take && lv != 0 && last == 0) ? n + 1 : last;
+    ctx = take ? (int)(e & 3u) : ctx;
   }
   return last;
 }
