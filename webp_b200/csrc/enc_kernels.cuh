@@ -122,7 +122,7 @@ __device__ __forceinline__ int check_mode(int mx, int my, int mode) {
 }
 // Cooperative square predictor into buf at off (predict_lossy.go:27-181); modes 0..6.
 template <int G>
-__device__ __forceinline__ void pred_square_coop(int gl, int mode, uint8_t* buf, int off, int size) {
+__device__ __noinline__ void pred_square_coop(int gl, int mode, uint8_t* buf, int off, int size) {
   uint8_t* d = buf + off;
   const int words_per_row = size >> 2;
   const int nwords = size * words_per_row;
@@ -357,15 +357,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
       if (allowed) {
         for (int b = gl; b < 16; b += G) {
           const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
-          int s[16], p[16], c[16], q[16];
+          int s[16], p[16], c[16];
           load_src_block(S.in, b, s);
           load4x4(S.out2 + off, p);
           ftransform(s, p, c);
           S.dc[b] = c[0];
-          c[0] = 0;
-          S.nz[b] = quantize_block(c, q, seg.y1, 1);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) S.lev[b][i] = (int16_t)q[i];
+          for (int i = 0; i < 16; ++i) S.lev[b][i] = (int16_t)c[i];
+          S.nz[b] = quantize_smem(S.lev[b], seg.y1, 1);
         }
       }
       __syncwarp();
@@ -376,8 +375,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
 #pragma unroll
           for (int i = 0; i < 16; ++i) d[i] = S.dc[i];
           fwht(d, w);
-          const int nz_dc = quantize_block(w, q, seg.y2, 0);
-          rate += kModeFixedCost16(mode) + token_cost(q, nz_dc, 1, dc_ctx, 0, T);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) S.dc[i] = w[i];
+          const int nz_dc = quantize_smem(S.dc, seg.y2, 0);
+          rate += kModeFixedCost16(mode) + token_cost_smem(S.dc, nz_dc, 1, dc_ctx, 0, T);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) q[i] = S.dc[i];
           dequant_block(q, dq, seg.y2);
           iwht(dq, d);
 #pragma unroll
@@ -387,10 +390,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
           const int bx = b & 3, by = b >> 2;
           const int l = bx > 0 ? (S.nz[b - 1] > 0) : ((left_nz >> by) & 1);
           const int t = by > 0 ? (S.nz[b - 4] > 0) : ((top_nz >> bx) & 1);
-          int q[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) q[i] = S.lev[b][i];
-          rate += token_cost(q, S.nz[b], 0, l + t, 1, T);
+          rate += token_cost_smem(S.lev[b], S.nz[b], 0, l + t, 1, T);
         }
       }
       __syncwarp();
@@ -516,7 +516,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
 #pragma unroll
             for (int i = 0; i < 16; ++i) q[i] = C.lev[i];
           } else {
-            nz = quantize_block(c, q, seg.y1, 0);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) C.lev[i] = (int16_t)c[i];
+            nz = quantize_smem(C.lev, seg.y1, 0);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) q[i] = C.lev[i];
           }
           dequant_block(q, dq, seg.y1);
           itransform(p, dq, r);
@@ -529,7 +533,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
             for (int i = 1; i < 16; ++i) cnt += (q[i] != 0);
             if (cnt <= 3) rate = 140;
           }
-          rate += token_cost(q, nz, 3, nz_ctx, 0, T);
+          rate += token_cost_smem(C.lev, nz, 3, nz_ctx, 0, T);
           rate += s_i4cost[(top_mode * 10 + left_mode) * 10 + mode];
           C.score = rd_score(disto, rate, seg.lambda_i4);
           C.disto = disto; C.rate = rate; C.nz = nz; C.mode = mode;
@@ -608,9 +612,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
           load_src_block(S.in, 16 + b, s);
           load4x4(S.out2 + off, p);
           ftransform(s, p, c);
-          S.nz[16 + b] = quantize_block(c, q, seg.uv, 0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) S.lev[16 + b][i] = (int16_t)q[i];
+          for (int i = 0; i < 16; ++i) S.lev[16 + b][i] = (int16_t)c[i];
+          S.nz[16 + b] = quantize_smem(S.lev[16 + b], seg.uv, 0);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) q[i] = S.lev[16 + b][i];
 #pragma unroll
           for (int i = 1; i < 16; ++i) ac_cnt += (q[i] != 0);
           dequant_block(q, dq, seg.uv);
@@ -626,10 +632,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
           const uint32_t tn = (top_nz >> (4 + 2 * ch)) & 3, ln = (left_nz >> (4 + 2 * ch)) & 3;
           const int l = bx > 0 ? (S.nz[16 + b - 1] > 0) : ((ln >> by) & 1);
           const int t = by > 0 ? (S.nz[16 + b - 2] > 0) : ((tn >> bx) & 1);
-          int q[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) q[i] = S.lev[16 + b][i];
-          rate += token_cost(q, S.nz[16 + b], 2, l + t, 0, T);
+          rate += token_cost_smem(S.lev[16 + b], S.nz[16 + b], 2, l + t, 0, T);
         }
       }
       rate = grp_sum<G>(rate);
@@ -666,12 +669,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
   if (!trellis) {
     if (active && !use_i4)
       for (int b = gl; b < 16; b += G) {
-        int c[16], q[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) c[i] = S.lev[b][i];
-        S.nz[b] = quantize_block(c, q, seg.y1, 1);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) S.lev[b][i] = (int16_t)q[i];
+        S.nz[b] = quantize_smem(S.lev[b], seg.y1, 1);
       }
     __syncwarp();
   } else {
@@ -695,10 +693,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
 #pragma unroll
       for (int i = 0; i < 16; ++i) d[i] = S.dc[i];
       fwht(d, w);
-      const int n = quantize_block(w, q, seg.y2, 0);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) S.dc[i] = w[i];
+      const int n = quantize_smem(S.dc, seg.y2, 0);  // S.dc now holds the WHT levels
       S.misc[1] = n;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { oc[384 + i] = (int16_t)q[i]; S.dc[i] = q[i]; }  // S.dc now holds the WHT levels
+      for (int i = 0; i < 16; ++i) { q[i] = S.dc[i]; oc[384 + i] = (int16_t)q[i]; }
       dequant_block(q, dq, seg.y2);
       iwht(dq, d);
 #pragma unroll
@@ -740,11 +740,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
       load_src_block(S.in, 16 + b, s);
       load4x4(S.out + off, p);
       ftransform(s, p, c);
-      const int nz = quantize_block(c, q, seg.uv, 0);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) S.lev[16 + b][i] = (int16_t)c[i];
+      const int nz = quantize_smem(S.lev[16 + b], seg.uv, 0);
       S.nz[16 + b] = nz;
       hdr[40 + b] = (uint8_t)nz;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { oc[(16 + b) * 16 + i] = (int16_t)q[i]; S.lev[16 + b][i] = (int16_t)q[i]; }
+      for (int i = 0; i < 16; ++i) { q[i] = S.lev[16 + b][i]; oc[(16 + b) * 16 + i] = (int16_t)q[i]; }
       dequant_block(q, dq, seg.uv);
       itransform(p, dq, r);
       store4x4(S.out + off, r);
