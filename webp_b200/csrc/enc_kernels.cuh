@@ -51,12 +51,13 @@ struct MBShared {
   uint8_t out2[YUV_SIZE];
   int16_t lev[24][16];
   int dc[16];
-  int dcrec[16];
-  int nz[24];
+  int16_t dcrec[16];
+  uint8_t nz[24];
   int sse[10];
   uint8_t smode[12];
+  uint8_t pred4s[10][16];  // the ten 4x4 predictions of the current sub-block (pre-screen -> RD candidates)
   I4Cand cand[3];
-  int misc[8];
+  int misc[4];
 };
 
 template <int G>
@@ -465,47 +466,36 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
             const int pos = __popc(elig & ((1u << m) - 1));
             S.sse[pos] = sse16(s, p);
             S.smode[pos] = (uint8_t)m;
+            uint32_t* ps = reinterpret_cast<uint32_t*>(S.pred4s[m]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              ps[j] = (uint32_t)p[4 * j] | ((uint32_t)p[4 * j + 1] << 8) | ((uint32_t)p[4 * j + 2] << 16) | ((uint32_t)p[4 * j + 3] << 24);
+          }
+        }
+        if (gl == G - 1 && seg.tlambda_sd > 0) S.misc[2] = ttransform(s);  // source half of TDisto, shared by the candidates
+      }
+      __syncwarp();
+      const int K = alive ? min(P.max_i4_modes, n_cand) : 0;
+      if (alive && gl == 0) {  // the reference's selection sort of the first K entries, literally (encode_parallel.go:969-983)
+#pragma unroll 1
+        for (int i = 0; i < K; ++i) {
+          int mi = i, mv = S.sse[i];
+#pragma unroll 1
+          for (int j = i + 1; j < n_cand; ++j) { const int v = S.sse[j]; if (v < mv) { mv = v; mi = j; } }
+          if (mi != i) {
+            const int ts = S.sse[i]; const uint8_t tm = S.smode[i];
+            S.sse[i] = mv; S.smode[i] = S.smode[mi];
+            S.sse[mi] = ts; S.smode[mi] = tm;
           }
         }
       }
       __syncwarp();
-      int K = 0;
-      int cand_mode[3] = {0, 0, 0};
-      if (alive) {  // exact selection-sort emulation (encode_parallel.go:969-983) in registers, every lane redundantly
-        int cm[10], cs[10];
-#pragma unroll
-        for (int j = 0; j < 10; ++j) {
-          const bool ok = j < n_cand;
-          cs[j] = ok ? S.sse[j] : 0x7fffffff;
-          cm[j] = ok ? (int)S.smode[j] : 0;
-        }
-        K = min(P.max_i4_modes, n_cand);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          if (i < K) {
-            int mi = i, mv = cs[i];
-#pragma unroll
-            for (int j = i + 1; j < 10; ++j) { const bool lt = cs[j] < mv; mv = lt ? cs[j] : mv; mi = lt ? j : mi; }
-            const int tm = cm[i], ts = cs[i];
-            int sm = tm;
-#pragma unroll
-            for (int j = i + 1; j < 10; ++j) {
-              const bool hit = (j == mi);
-              sm = hit ? cm[j] : sm;
-              cm[j] = hit ? tm : cm[j];
-              cs[j] = hit ? ts : cs[j];
-            }
-            cm[i] = sm; cs[i] = mv;
-            cand_mode[i] = sm;
-          }
-        }
-      }
       // full RD on the K candidates, one lane each
       if (alive) {
         for (int k = gl; k < K; k += G) {
-          const int mode = cand_mode[k];
+          const int mode = S.smode[k];
           int p[16], c[16], q[16], dq[16], r[16];
-          pred4(mode, e, p);
+          load4x4s<4>(S.pred4s[mode], p);
           ftransform(s, p, c);
           I4Cand& C = S.cand[k];
           int nz;
@@ -525,7 +515,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
           dequant_block(q, dq, seg.y1);
           itransform(p, dq, r);
           int disto = sse16(s, r);
-          if (seg.tlambda_sd > 0) disto += (seg.tlambda_sd * tdisto4x4(s, r) + 128) >> 8;
+          if (seg.tlambda_sd > 0) disto += (seg.tlambda_sd * (abs(ttransform(r) - S.misc[2]) >> 5) + 128) >> 8;
           int rate = 0;
           if (mode > 0) {  // isFlat(levels, 1, 3)  (encode_analysis.go:374)
             int cnt = 0;

@@ -372,7 +372,7 @@ __device__ __forceinline__ int trellis_block_smem(int16_t* io, const SegQuant& s
   uint32_t neg_mask = 0;  // bit i: raster coefficient i is negative
   {
     bool non_zero = false;  // all-zero pre-scan with neutral bias (encode_trellis.go:39-98)
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 16; ++i) {
       const int raw = io[i];
       const int c0 = max(abs(raw) + sq.sharpen[i], 0);
