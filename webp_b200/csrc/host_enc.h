@@ -256,15 +256,17 @@ struct BoolEnc {
     }
   }
   inline void put(int bit, int prob) {
+    // PutBit (writer_bool.go:58-76), branch-free except for the byte flush: the bit selects between the two sub-ranges
+    // with a mask, and the renormalisation shift is 0 whenever range >= 127 (kNorm[range] == clz(range + 1) - 24).
     const int32_t split = (range * prob) >> 8;
-    if (bit) { value += split + 1; range -= split + 1; } else { range = split; }
-    if (range < 127) {
-      const int shift = __builtin_clz((unsigned)(range + 1)) - 24;  // kNorm
-      range = ((range + 1) << shift) - 1;                              // kNewRange
-      value <<= shift;
-      nb_bits += shift;
-      if (nb_bits > 0) flush();
-    }
+    const int32_t mask = -(int32_t)(bit != 0);
+    value += (split + 1) & mask;
+    const int32_t r = split ^ ((split ^ (range - split - 1)) & mask);
+    const int shift = __builtin_clz((unsigned)(r + 1)) - 24;
+    range = ((r + 1) << shift) - 1;  // kNewRange
+    value <<= shift;
+    nb_bits += shift;
+    if (nb_bits > 0) flush();
   }
   inline void put_uniform(int bit) { put(bit, 128); }  // identical arithmetic to PutBitUniform: (r*128)>>8 == r>>1
   void put_bits(uint32_t v, int n) { for (uint32_t m = 1u << (n - 1); m; m >>= 1) put_uniform((v & m) ? 1 : 0); }
