@@ -1411,9 +1411,9 @@ struct Encoder {
       }
     }
   }
-  static int branch_cost(int cnt0, int cnt1, int p) {
+  static int64_t branch_cost(int cnt0, int cnt1, int p) {  // Go int is 64-bit: counts x costs exceed 2^31 on large frames
     p = clampi(p, 1, 255);
-    return cnt1 * bit_cost(1, (uint8_t)p) + cnt0 * bit_cost(0, (uint8_t)p);
+    return (int64_t)cnt1 * bit_cost(1, (uint8_t)p) + (int64_t)cnt0 * bit_cost(0, (uint8_t)p);
   }
   int optimize_proba(ProbaStats st) {  // encode_proba.go:117
     int num_updates = 0;
@@ -1423,12 +1423,12 @@ struct Encoder {
           for (int p = 0; p < 11; ++p) {
             const int cnt0 = st[t][b][c][p][0], cnt1 = st[t][b][c][p][1], total = cnt0 + cnt1;
             if (total == 0) continue;
-            const int new_p = cnt1 > 0 ? 255 - cnt1 * 255 / total : 255;
+            const int new_p = cnt1 > 0 ? 255 - (int)((int64_t)cnt1 * 255 / total) : 255;
             const int idx = ((t * 8 + b) * 3 + c) * 11 + p;
             const int old_p = kCoeffsProba0[idx];
             const uint8_t up = kCoeffsUpdateProba[idx];
-            const int old_cost = branch_cost(cnt0, cnt1, old_p) + bit_cost(0, up);
-            const int new_cost = branch_cost(cnt0, cnt1, new_p) + bit_cost(1, up) + 8 * 256;
+            const int64_t old_cost = branch_cost(cnt0, cnt1, old_p) + bit_cost(0, up);
+            const int64_t new_cost = branch_cost(cnt0, cnt1, new_p) + bit_cost(1, up) + 8 * 256;
             if (old_cost > new_cost) {
               proba.bands[t][b][c][p] = (uint8_t)new_p;
               num_updates++;

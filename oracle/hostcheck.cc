@@ -51,6 +51,16 @@ long hostcheck_serialize(const uint8_t* rgba, int stride, int w, int h, const Or
   }
   *ms_per_rep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / (reps > 0 ? reps : 1);
   *same = seg_same && riff.size() == ref.size() && !memcmp(riff.data(), ref.data(), ref.size());
+  if (getenv("HOSTCHECK_TOKENS") && o.partitions == 0) {  // token route: flat (bit, prob) stream + final probabilities, as the GPU hands them over
+    std::vector<uint8_t> riff2;
+    const auto t1 = std::chrono::steady_clock::now();
+    for (int r = 0; r < (reps > 0 ? reps : 1); ++r) {
+      riff2.clear();
+      wgh::serialize_frame_tokens(fp, hdr.data(), segmap.data(), &enc->proba.bands[0][0][0][0], enc->tokens.data(), enc->tokens.size(), &riff2);
+    }
+    *ms_per_rep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count() / (reps > 0 ? reps : 1);
+    *same = *same && riff2.size() == ref.size() && !memcmp(riff2.data(), ref.data(), ref.size());
+  }
   delete enc;
   if ((long)riff.size() > cap) return -2;
   memcpy(out, riff.data(), riff.size());

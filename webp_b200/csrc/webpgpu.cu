@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -13,6 +14,7 @@
 
 #include "../../include/webpgpu.h"
 #include "misc_kernels.cuh"
+#include "token_kernels.cuh"
 #include "host_dec.h"
 
 namespace {
@@ -74,10 +76,10 @@ struct wgpu_ctx {
   int host_threads = 0;
   std::mutex mu;
   // constant tables
-  DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g;
+  DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, hdr, coeffs, stats;
-  PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, hdr, coeffs, stats, proba, mb_tokens, mb_offset, img_total, img_base, tokens;
+  PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false;
   wgpu_enc_options e_opt;
@@ -175,6 +177,9 @@ int wgpu_ctx_create(int device_ordinal, wgpu_ctx** out) {
   rc |= upload_table(ctx, ctx->t_lc, lc, sizeof(lc));
   rc |= upload_table(ctx, ctx->t_eob, eobc, sizeof(eobc));
   rc |= upload_table(ctx, ctx->t_lfc, wgh::kLevelFixedCosts, sizeof(wgh::kLevelFixedCosts));
+  rc |= upload_table(ctx, ctx->t_proba0, wgh::kCoeffsProba0, sizeof(wgh::kCoeffsProba0));
+  rc |= upload_table(ctx, ctx->t_upd, wgh::kCoeffsUpdateProba, sizeof(wgh::kCoeffsUpdateProba));
+  rc |= upload_table(ctx, ctx->t_ecost, wgh::kEntropyCost, sizeof(wgh::kEntropyCost));
   rc |= upload_table(ctx, ctx->t_i4cost, i4costs, sizeof(i4costs));
   rc |= upload_table(ctx, ctx->t_g2l, g2l, sizeof(g2l));
   rc |= upload_table(ctx, ctx->t_l2g, l2g, sizeof(l2g));
@@ -187,13 +192,14 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
+  DevBuf* db[] = {&ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens,
+                  &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
                   &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
                   &ctx->m_sse, &ctx->m_ssim};
   for (DevBuf* b : db) b->release();
-  PinBuf* pb[] = {&ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
+  PinBuf* pb[] = {&ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
                   &ctx->hd_meta, &ctx->hd_ftype, &ctx->hd_planes, &ctx->hd_nrgba};
   for (PinBuf* b : pb) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -365,8 +371,38 @@ static int enc_reserve(wgpu_ctx* ctx) {
   RESERVE(ctx->img_params, n * sizeof(wg::ImageParams));
   RESERVE(ctx->ctxw, n * nmb * 4); RESERVE(ctx->hdr, n * nmb * 48); RESERVE(ctx->coeffs, n * nmb * 800);
   RESERVE(ctx->stats, n * wg::STATS_SIZE * 4); RESERVE(ctx->h_stats, n * wg::STATS_SIZE * 4);
+  RESERVE(ctx->proba, n * 1056); RESERVE(ctx->h_proba, n * 1056);
+  RESERVE(ctx->mb_tokens, n * nmb * 4); RESERVE(ctx->mb_offset, n * nmb * 8);
+  RESERVE(ctx->img_total, n * 8); RESERVE(ctx->img_base, n * 8); RESERVE(ctx->h_totals, n * 8); RESERVE(ctx->h_bases, n * 8);
   RESERVE(ctx->h_alpha, n * nmb); RESERVE(ctx->h_uv_alpha, n * nmb); RESERVE(ctx->h_segment, n * nmb);
   RESERVE(ctx->h_params, n * sizeof(wg::ImageParams));
+  return WGPU_OK;
+}
+
+static wg::TokenParams token_params(wgpu_ctx* ctx) {
+  wg::TokenParams T;
+  T.hdr = ctx->hdr.as<uint8_t>(); T.coeffs = ctx->coeffs.as<int16_t>(); T.ctxw = ctx->ctxw.as<uint32_t>();
+  T.proba = ctx->proba.as<uint8_t>(); T.mb_tokens = ctx->mb_tokens.as<uint32_t>();
+  T.mb_offset = ctx->mb_offset.as<unsigned long long>(); T.img_total = ctx->img_total.as<unsigned long long>();
+  T.img_base = ctx->img_base.as<unsigned long long>(); T.tokens = ctx->tokens.as<uint16_t>();
+  T.n_images = ctx->e_n; T.mb_w = ctx->e_mbw; T.mb_h = ctx->e_mbh;
+  return T;
+}
+// Single-partition route, device part 1 (queued right behind the waves): final probabilities from the token statistics,
+// tokens per macroblock, per-image prefix sums and totals.
+static int enc_launch_token_prepass(wgpu_ctx* ctx) {
+  const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
+  wg::ProbaParams pp;
+  pp.stats = ctx->stats.as<unsigned int>(); pp.proba0 = ctx->t_proba0.as<uint8_t>(); pp.update = ctx->t_upd.as<uint8_t>();
+  pp.ecost = ctx->t_ecost.as<uint16_t>(); pp.proba = ctx->proba.as<uint8_t>(); pp.n_images = n;
+  wg::optimize_proba_kernel<<<n, 352, 0, ctx->stream>>>(pp);
+  const wg::TokenParams T = token_params(ctx);
+  const long long total = (long long)nmb * n;
+  wg::token_kernel<false><<<(unsigned)((total + 15) / 16), 128, 0, ctx->stream>>>(T);
+  wg::token_scan_kernel<<<n, 256, 0, ctx->stream>>>(T);
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->h_totals.p, ctx->img_total.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   return WGPU_OK;
 }
 
@@ -395,6 +431,7 @@ static int enc_search_locked(wgpu_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->img_params.p, ctx->h_params.p, (size_t)n * sizeof(wg::ImageParams), cudaMemcpyHostToDevice, ctx->stream));
   int rc = enc_launch_waves(ctx);
   if (rc) return rc;
+  if (ctx->e_opt.partitions == 0 && (rc = enc_launch_token_prepass(ctx))) return rc;
   ctx->e_done = true;
   return WGPU_OK;
 }
@@ -490,28 +527,78 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
   CK(cudaSetDevice(ctx->dev));
   const size_t n = ctx->e_n, nmb = (size_t)ctx->e_mbw * ctx->e_mbh;
   RESERVE(ctx->h_hdr, n * nmb * 48);
-  RESERVE(ctx->h_coeffs, n * nmb * 800);
-  const double t0 = now_ms();
-  if (trace_on()) cudaStreamSynchronize(ctx->stream);
-  const double t0b = now_ms();
-  CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_coeffs.p, ctx->coeffs.p, n * nmb * 800, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->stats.p, n * wg::STATS_SIZE * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  const double t1 = now_ms();
   std::atomic<int> too_small(0);
-  parallel_for((int)n, threads_of(ctx), [&](int i) {
-    std::vector<uint8_t> riff;
-    riff.reserve(nmb * 64 + 4096);
-    wgh::serialize_frame(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
-                         ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, ctx->h_stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE, &riff);
-    out_sizes[i] = riff.size();
-    if (riff.size() > out_stride) { too_small.store(1); return; }
-    memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
-  });
-  if (trace_on())
-    fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, D2H %.2f ms (%.1f MB), host serialise %.2f ms (%d threads)\n", t0b - t0, t1 - t0b,
-            (double)(n * nmb * 848) / 1e6, now_ms() - t1, threads_of(ctx));
+  const double t0 = now_ms();
+  if (ctx->e_opt.partitions == 0) {
+    // ---- single partition: tokens are generated on the GPU, the host only boolean-codes flat arrays
+    CK(cudaStreamSynchronize(ctx->stream));  // waves + token pre-pass done, per-image totals on the host
+    const double t1 = now_ms();
+    const unsigned long long* totals = ctx->h_totals.as<unsigned long long>();
+    unsigned long long* bases = ctx->h_bases.as<unsigned long long>();
+    unsigned long long all = 0;
+    for (size_t i = 0; i < n; ++i) { bases[i] = all; all += totals[i]; }
+    RESERVE(ctx->tokens, (size_t)(all + 8) * 2);
+    RESERVE(ctx->h_tokens, (size_t)(all + 8) * 2);
+    CK(cudaMemcpyAsync(ctx->img_base.p, bases, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const wg::TokenParams T = token_params(ctx);
+    wg::token_kernel<true><<<(unsigned)((n * nmb + 15) / 16), 128, 0, ctx->stream>>>(T);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_proba.p, ctx->proba.p, n * 1056, cudaMemcpyDeviceToHost, ctx->stream));
+    if (all) CK(cudaMemcpyAsync(ctx->h_tokens.p, ctx->tokens.p, (size_t)all * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double t2 = now_ms();
+    // pair images of similar length (longest first) so two coders run interleaved in each task
+    std::vector<int> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return totals[a] > totals[b] || (totals[a] == totals[b] && a < b); });
+    const int pairs = (int)((n + 1) / 2);
+    std::vector<std::vector<uint8_t>> coded(n);
+    parallel_for(pairs, threads_of(ctx), [&](int p) {
+      const int ia = order[2 * p], ib = (size_t)(2 * p + 1) < n ? order[2 * p + 1] : -1;
+      coded[ia].reserve((size_t)totals[ia] / 4 + 4096);
+      if (ib >= 0) coded[ib].reserve((size_t)totals[ib] / 4 + 4096);
+      wgh::code_token_streams(ctx->h_tokens.as<uint16_t>() + bases[ia], (size_t)totals[ia], &coded[ia],
+                              ib >= 0 ? ctx->h_tokens.as<uint16_t>() + bases[ib] : nullptr, ib >= 0 ? (size_t)totals[ib] : 0,
+                              ib >= 0 ? &coded[ib] : nullptr);
+      for (int k = 0; k < 2; ++k) {
+        const int i = k == 0 ? ia : ib;
+        if (i < 0) continue;
+        std::vector<uint8_t> riff;
+        riff.reserve(coded[i].size() + nmb * 4 + 4096);
+        wgh::assemble_frame_tokens(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_segment.as<uint8_t>() + (size_t)i * nmb,
+                                   ctx->h_proba.as<uint8_t>() + (size_t)i * 1056, coded[i], &riff);
+        out_sizes[i] = riff.size();
+        if (riff.size() > out_stride) { too_small.store(1); continue; }
+        memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
+        std::vector<uint8_t>().swap(coded[i]);
+      }
+    });
+    if (trace_on())
+      fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, token emit + D2H %.2f ms (%.1f MB tokens), host code %.2f ms (%d threads)\n", t1 - t0,
+              t2 - t1, (double)all * 2 / 1e6, now_ms() - t2, threads_of(ctx));
+  } else {
+    // ---- multi-partition: levels + statistics come back, the host walks them (reference's partitioned emission)
+    RESERVE(ctx->h_coeffs, n * nmb * 800);
+    CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_coeffs.p, ctx->coeffs.p, n * nmb * 800, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->stats.p, n * wg::STATS_SIZE * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double t1 = now_ms();
+    parallel_for((int)n, threads_of(ctx), [&](int i) {
+      std::vector<uint8_t> riff;
+      riff.reserve(nmb * 64 + 4096);
+      wgh::serialize_frame(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
+                           ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, ctx->h_stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE, &riff);
+      out_sizes[i] = riff.size();
+      if (riff.size() > out_stride) { too_small.store(1); return; }
+      memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
+    });
+    if (trace_on())
+      fprintf(stderr, "[wgpu] enc_finish: D2H %.2f ms (%.1f MB), host serialise %.2f ms (%d threads)\n", t1 - t0, (double)(n * nmb * 848) / 1e6,
+              now_ms() - t1, threads_of(ctx));
+  }
   if (too_small.load()) FAIL(WGPU_ERR_TOO_SMALL, "output buffer too small (out_sizes holds the required sizes)");
   return WGPU_OK;
 }
