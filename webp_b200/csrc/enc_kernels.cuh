@@ -24,6 +24,11 @@ struct EncKernelParams {
   const uint8_t* segment;       // [n][nmb]
   const ImageParams* img;       // [n]
   uint32_t* ctx;                // [n][nmb] packed NZ context (see pack_ctx)
+  int* progress;                // [n][mb_h] finished macroblocks per row (persistent kernel)
+  unsigned long long* work_counter;  // next group to claim (persistent kernel)
+  const long long* wave_start;  // [waves + 1] prefix of groups per wave (persistent kernel)
+  long long total_groups;
+  int* error_flag;              // set when a dependency wait exceeded its iteration cap
   unsigned int* stats;          // [n][4][8][3][11][2] token statistics (ProbaStats, encode_proba.go), zeroed before the waves
   uint8_t* out_hdr;             // [n][nmb][48]: mb_type,i16,uv,segment,skip,nz_dc,0,0, modes[16], nz[24]
   int16_t* out_coeffs;          // [n][nmb][400]
@@ -209,41 +214,30 @@ __device__ __forceinline__ void stat_block_dev(const LevT* lev, int n_coeffs, in
   }
 }
 
-// One wave of the mode search.  Grid: ceil(tasks / (WARPS * 32/G)) CTAs of WARPS warps.
-template <int G, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const EncKernelParams P, int wave) {
-  constexpr int MPW = 32 / G;  // macroblocks per warp
-  __shared__ __align__(16) uint16_t s_lc[LC_SIZE];
-  __shared__ __align__(16) uint16_t s_lfc[2048];
-  __shared__ __align__(16) uint16_t s_i4cost[1000];
-  __shared__ __align__(16) uint16_t s_eob[EOB_SIZE];
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  MBShared* s_mb = reinterpret_cast<MBShared*>(s_dyn);  // [WARPS * MPW]
-  {
-    constexpr int NT = WARPS * 32;
-    for (int i = threadIdx.x; i < LC_SIZE / 8; i += NT) reinterpret_cast<uint4*>(s_lc)[i] = reinterpret_cast<const uint4*>(P.lc)[i];
-    for (int i = threadIdx.x; i < 2048 / 8; i += NT) reinterpret_cast<uint4*>(s_lfc)[i] = reinterpret_cast<const uint4*>(P.lfc)[i];
-    for (int i = threadIdx.x; i < 1000 / 8; i += NT) reinterpret_cast<uint4*>(s_i4cost)[i] = reinterpret_cast<const uint4*>(P.i4_costs)[i];
-    for (int i = threadIdx.x; i < EOB_SIZE / 8; i += NT) reinterpret_cast<uint4*>(s_eob)[i] = reinterpret_cast<const uint4*>(P.eob)[i];
-  }
-  __syncthreads();
-  CostTabs T;
-  T.lc = s_lc; T.eob = s_eob; T.lfc = s_lfc;
+// Loads of data another macroblock produced (reconstruction borders, NZ context words, neighbour modes).  In the
+// persistent kernel producers and consumers run concurrently on different SMs, so these must bypass the
+// non-coherent L1 (ld.global.cg); the per-wave kernels see them through a kernel boundary and use plain loads.
+template <bool PERSIST, class Tp>
+__device__ __forceinline__ Tp ldn(const Tp* p) { return PERSIST ? __ldcg(p) : *p; }
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// The mode search of MPW = 32/G macroblocks by one warp: macroblock `task_base + lane/G` of wave `wave`.
+template <int G, bool PERSIST>
+__device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wave, long long task_base, MBShared* s_mb_warp,
+                                                const CostTabs& T, const uint16_t* s_i4cost) {
+  const int lane = threadIdx.x & 31;
   const int g = lane / G, gl = lane % G;
   // rows on this wave: x = wave - 2y in [0, mb_w)
   const int y_lo = max(0, (wave - (P.mb_w - 1) + 1) >> 1), y_hi = min(P.mb_h - 1, wave >> 1);
   const int rows = y_hi - y_lo + 1;
   const long long total = (long long)rows * P.n_images;
-  const long long task = ((long long)blockIdx.x * WARPS + warp) * MPW + g;
+  const long long task = task_base + g;
   const bool active = task < total;
   const int img = active ? (int)(task / rows) : 0;
   const int my = active ? y_lo + (int)(task % rows) : 0;
   const int mx = active ? wave - 2 * my : 0;
   const int nmb = P.mb_w * P.mb_h;
   const int mb_idx = my * P.mb_w + mx;
-  MBShared& S = s_mb[warp * MPW + g];
+  MBShared& S = s_mb_warp[g];
 
   const int y_stride = P.mb_w * 16, uv_stride = P.mb_w * 8;
   const uint8_t* src_y = P.src_y + (size_t)img * P.y_plane;
@@ -258,6 +252,31 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
   const int segment = active ? P.segment[(size_t)img * nmb + mb_idx] : 0;
   const SegParams& seg = P.img[img].seg[segment];
   const bool trellis = P.method >= 4;
+
+  if (PERSIST) {
+    // Dataflow scheduling: wait until the left macroblock and the top-right one (which implies top and top-left) are
+    // done.  progress[img][row] = macroblocks finished in that row (a row finishes strictly left to right).  Work is
+    // claimed in wave order by running warps only, so every dependency is already running or done: no deadlock; the
+    // iteration cap only turns a logic error into a reported failure instead of a hung GPU.
+    volatile int* prog = P.progress + (size_t)img * P.mb_h;
+    const int need_top = (active && my > 0) ? min(mx + 2, P.mb_w) : 0, need_left = active ? mx : 0;
+    int spins = 0;
+    unsigned backoff = 200;
+    for (;;) {
+      bool ok = true;
+      if (gl == 0) {  // one polling lane per macroblock keeps the L2 traffic of waiting warps negligible
+        if (need_top > 0) ok = prog[my - 1] >= need_top;
+        if (ok && need_left > 0) ok = prog[my] >= need_left;
+      }
+      if (__all_sync(0xffffffffu, ok)) break;
+      __nanosleep(backoff);
+      backoff = min(backoff * 2, 4000u);
+      bool bail = ++spins > (1 << 20);
+      if (lane == 0) bail = bail || *reinterpret_cast<volatile int*>(P.error_flag) != 0;
+      if (__any_sync(0xffffffffu, bail)) { if (lane == 0) atomicExch(P.error_flag, 1); break; }
+    }
+    __threadfence();
+  }
 
   // ---- 1. import source MB with edge replication (encode_iterator.go:145) + 2. prediction context
   if (active) {
@@ -288,23 +307,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
       int v = 127;
       if (my > 0) {
         const int xx = (i < 16 || mx < P.mb_w - 1) ? x0 + i : x0 + 15;
-        v = rec_y[(size_t)(y0 - 1) * y_stride + xx];
+        v = ldn<PERSIST>(&rec_y[(size_t)(y0 - 1) * y_stride + xx]);
       }
       o[Y_OFF - BPS + i] = (uint8_t)v;
     }
-    for (int j = gl; j < 16; j += G) o[Y_OFF - 1 + j * BPS] = mx > 0 ? rec_y[(size_t)(y0 + j) * y_stride + x0 - 1] : 129;
+    for (int j = gl; j < 16; j += G) o[Y_OFF - 1 + j * BPS] = mx > 0 ? ldn<PERSIST>(&rec_y[(size_t)(y0 + j) * y_stride + x0 - 1]) : 129;
     for (int i = gl; i < 16; i += G) {
       const int pl = i >> 3, c = i & 7;
       const uint8_t* rp = pl ? rec_v : rec_u;
       const int off = pl ? V_OFF : U_OFF;
-      o[off - BPS + c] = my > 0 ? rp[(size_t)(my * 8 - 1) * uv_stride + mx * 8 + c] : 127;
-      o[off - 1 + c * BPS] = mx > 0 ? rp[(size_t)(my * 8 + c) * uv_stride + mx * 8 - 1] : 129;
+      o[off - BPS + c] = my > 0 ? ldn<PERSIST>(&rp[(size_t)(my * 8 - 1) * uv_stride + mx * 8 + c]) : 127;
+      o[off - 1 + c * BPS] = mx > 0 ? ldn<PERSIST>(&rp[(size_t)(my * 8 + c) * uv_stride + mx * 8 - 1]) : 129;
     }
     if (gl == 0) {
       const bool both = mx > 0 && my > 0;
-      o[Y_OFF - BPS - 1] = both ? rec_y[(size_t)(y0 - 1) * y_stride + x0 - 1] : (my > 0 ? 129 : 127);
-      o[U_OFF - BPS - 1] = both ? rec_u[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1] : (my > 0 ? 129 : 127);
-      o[V_OFF - BPS - 1] = both ? rec_v[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1] : (my > 0 ? 129 : 127);
+      o[Y_OFF - BPS - 1] = both ? ldn<PERSIST>(&rec_y[(size_t)(y0 - 1) * y_stride + x0 - 1]) : (my > 0 ? 129 : 127);
+      o[U_OFF - BPS - 1] = both ? ldn<PERSIST>(&rec_u[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1]) : (my > 0 ? 129 : 127);
+      o[V_OFF - BPS - 1] = both ? ldn<PERSIST>(&rec_v[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1]) : (my > 0 ? 129 : 127);
     }
   }
   __syncwarp();
@@ -320,18 +339,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
   int top_modes[4] = {0, 0, 0, 0}, left_modes[4] = {0, 0, 0, 0};
   if (active) {
     if (my > 0) {
-      const uint32_t cw = ctxw[mb_idx - P.mb_w];
+      const uint32_t cw = ldn<PERSIST>(&ctxw[mb_idx - P.mb_w]);
       top_nz = cw & 0xff;
       top_nz_dc = (cw >> 16) & 1;
       const uint8_t* th = hdr - (size_t)P.mb_w * 48;
-      if (th[0] == 1) { top_modes[0] = th[8 + 12]; top_modes[1] = th[8 + 13]; top_modes[2] = th[8 + 14]; top_modes[3] = th[8 + 15]; }
+      if (ldn<PERSIST>(&th[0]) == 1) { top_modes[0] = ldn<PERSIST>(&th[8 + 12]); top_modes[1] = ldn<PERSIST>(&th[8 + 13]); top_modes[2] = ldn<PERSIST>(&th[8 + 14]); top_modes[3] = ldn<PERSIST>(&th[8 + 15]); }
     }
     if (mx > 0) {
-      const uint32_t cw = ctxw[mb_idx - 1];
+      const uint32_t cw = ldn<PERSIST>(&ctxw[mb_idx - 1]);
       left_nz = (cw >> 8) & 0xff;
       left_nz_dc = (cw >> 17) & 1;
       const uint8_t* lh = hdr - 48;
-      if (lh[0] == 1) { left_modes[0] = lh[8 + 3]; left_modes[1] = lh[8 + 7]; left_modes[2] = lh[8 + 11]; left_modes[3] = lh[8 + 15]; }
+      if (ldn<PERSIST>(&lh[0]) == 1) { left_modes[0] = ldn<PERSIST>(&lh[8 + 3]); left_modes[1] = ldn<PERSIST>(&lh[8 + 7]); left_modes[2] = ldn<PERSIST>(&lh[8 + 11]); left_modes[3] = ldn<PERSIST>(&lh[8 + 15]); }
     }
   }
   __syncwarp();
@@ -806,6 +825,56 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
       const int tdc = i16 ? dcflag : top_nz_dc, ldc = i16 ? dcflag : left_nz_dc;
       ctxw[mb_idx] = pack_ctx(out_t, out_l, tdc, ldc);
     }
+  }
+  if (PERSIST) {  // publish: everything this macroblock wrote must be visible before the row counter moves
+    __threadfence();
+    __syncwarp();
+    if (active && gl == 0) { volatile int* prog = P.progress + (size_t)img * P.mb_h; prog[my] = mx + 1; }
+  }
+}
+
+#define WG_STAGE_TABLES(NT)                                                                                                        \
+  __shared__ __align__(16) uint16_t s_lc[LC_SIZE];                                                                                 \
+  __shared__ __align__(16) uint16_t s_lfc[2048];                                                                                   \
+  __shared__ __align__(16) uint16_t s_i4cost[1000];                                                                                \
+  __shared__ __align__(16) uint16_t s_eob[EOB_SIZE];                                                                               \
+  extern __shared__ __align__(16) unsigned char s_dyn[];                                                                           \
+  MBShared* s_mb = reinterpret_cast<MBShared*>(s_dyn);                                                                             \
+  for (int i = threadIdx.x; i < LC_SIZE / 8; i += (NT)) reinterpret_cast<uint4*>(s_lc)[i] = reinterpret_cast<const uint4*>(P.lc)[i];       \
+  for (int i = threadIdx.x; i < 2048 / 8; i += (NT)) reinterpret_cast<uint4*>(s_lfc)[i] = reinterpret_cast<const uint4*>(P.lfc)[i];        \
+  for (int i = threadIdx.x; i < 1000 / 8; i += (NT)) reinterpret_cast<uint4*>(s_i4cost)[i] = reinterpret_cast<const uint4*>(P.i4_costs)[i]; \
+  for (int i = threadIdx.x; i < EOB_SIZE / 8; i += (NT)) reinterpret_cast<uint4*>(s_eob)[i] = reinterpret_cast<const uint4*>(P.eob)[i];    \
+  __syncthreads();                                                                                                                 \
+  CostTabs T;                                                                                                                      \
+  T.lc = s_lc; T.eob = s_eob; T.lfc = s_lfc
+
+// One wave of the mode search per launch.  Grid: ceil(tasks / (WARPS * 32/G)) CTAs of WARPS warps.
+template <int G, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const EncKernelParams P, int wave) {
+  constexpr int MPW = 32 / G;  // macroblocks per warp
+  WG_STAGE_TABLES(WARPS * 32);
+  const int warp = threadIdx.x >> 5;
+  encode_mb_group<G, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
+}
+
+// The whole mode search in ONE launch: persistent warps claim groups of 32/G macroblocks in wave order from a global
+// counter and synchronise through per-row progress counters (the reference's rowSync, encode_parallel.go:63-113, at
+// macroblock granularity).  No per-wave barrier: light macroblocks do not wait for heavy ones, and the tail of one
+// wave overlaps the head of the next.  wave_start[w] = first group index of wave w (host-computed prefix).
+template <int G, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) encode_persistent_kernel(const EncKernelParams P) {
+  constexpr int MPW = 32 / G;
+  WG_STAGE_TABLES(WARPS * 32);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int wave = 0;
+  for (;;) {
+    long long grp = 0;
+    if (lane == 0) grp = (long long)atomicAdd(P.work_counter, 1ull);
+    grp = __shfl_sync(0xffffffffu, grp, 0);
+    if (grp >= P.total_groups) break;
+    while (grp >= P.wave_start[wave + 1]) ++wave;  // groups are claimed in increasing order by this warp
+    encode_mb_group<G, true>(P, wave, (grp - P.wave_start[wave]) * MPW, s_mb + warp * MPW, T, s_i4cost);
+    __syncwarp();
   }
 }
 

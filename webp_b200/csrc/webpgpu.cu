@@ -78,10 +78,10 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, hdr, coeffs, stats, proba, mb_tokens, mb_offset, img_total, img_base, tokens;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens;
   PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
-  bool e_uploaded = false, e_analyzed = false, e_done = false;
+  bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false;
   wgpu_enc_options e_opt;
   std::vector<wgh::FramePlan> plans;
   // decoder state
@@ -192,7 +192,7 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens,
+  DevBuf* db[] = {&ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
@@ -303,6 +303,50 @@ int launch_enc_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
   }
   return WGPU_OK;
 }
+// Persistent dataflow launch: one kernel for all waves (see encode_persistent_kernel).
+template <int G, int WARPS, int MINB>
+int launch_enc_persistent(wgpu_ctx* ctx, wg::EncKernelParams& P) {
+  constexpr int MPW = 32 / G, per_cta = WARPS * MPW;
+  constexpr size_t smem = sizeof(wg::MBShared) * per_cta;
+  static bool attr_set = false;
+  static int sm_count = 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wg::encode_persistent_kernel<G, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->dev);
+    attr_set = true;
+  }
+  const int waves = P.mb_w + 2 * (P.mb_h - 1);
+  std::vector<long long> ws(waves + 1, 0);
+  for (int w = 0; w < waves; ++w) ws[w + 1] = ws[w] + ((long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images + MPW - 1) / MPW;
+  const size_t ctl_bytes = (size_t)(waves + 1) * 8 + 64 + (size_t)P.n_images * P.mb_h * 4;
+  if (!ctx->enc_ctl.reserve(ctl_bytes)) { ctx->err = "out of memory reserving enc_ctl"; return WGPU_ERR_NOMEM; }
+  // layout: [counter u64][error int + pad][wave_start (waves+1) i64][progress n*mb_h int]
+  uint8_t* base = ctx->enc_ctl.as<uint8_t>();
+  if (cudaMemsetAsync(base, 0, ctl_bytes, ctx->stream) != cudaSuccess) { ctx->err = "cudaMemsetAsync(enc_ctl)"; return WGPU_ERR_CUDA; }
+  if (cudaMemcpyAsync(base + 64, ws.data(), (size_t)(waves + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+    ctx->err = "cudaMemcpyAsync(wave_start)"; return WGPU_ERR_CUDA;
+  }
+  cudaStreamSynchronize(ctx->stream);  // ws is a stack vector: the pageable copy must finish before it goes away
+  P.work_counter = reinterpret_cast<unsigned long long*>(base);
+  P.error_flag = reinterpret_cast<int*>(base + 8);
+  P.wave_start = reinterpret_cast<const long long*>(base + 64);
+  P.progress = reinterpret_cast<int*>(base + 64 + (size_t)(waves + 1) * 8);
+  P.total_groups = ws[waves];
+  static int occ = 0;
+  if (!occ) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wg::encode_persistent_kernel<G, WARPS, MINB>, WARPS * 32, smem);
+    if (trace_on()) fprintf(stderr, "[wgpu] persistent mode search: %d CTAs/SM resident, %d SMs\n", occ, sm_count);
+    if (occ < 1) occ = 1;
+  }
+  const char* gm = getenv("WGPU_PERSIST_CTAS");
+  const int per_sm = gm ? atoi(gm) : occ;
+  const unsigned grid = (unsigned)std::min<long long>((long long)sm_count * per_sm, (P.total_groups + WARPS - 1) / WARPS);
+  wg::encode_persistent_kernel<G, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(P);
+  ctx->launches++;
+  ctx->enc_persistent_used = true;
+  return WGPU_OK;
+}
 int enc_variant() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("WGPU_ENC_VARIANT"); v = e ? atoi(e) : 0; }
@@ -342,6 +386,7 @@ static int enc_launch_analysis(wgpu_ctx* ctx) {
 static int enc_launch_waves(wgpu_ctx* ctx) {
   const int n = ctx->e_n, mbw = ctx->e_mbw, mbh = ctx->e_mbh, nmb = mbw * mbh;
   wg::EncKernelParams P;
+  P.progress = nullptr; P.work_counter = nullptr; P.wave_start = nullptr; P.total_groups = 0; P.error_flag = nullptr;
   P.src_y = ctx->sy.as<uint8_t>(); P.src_u = ctx->su.as<uint8_t>(); P.src_v = ctx->sv.as<uint8_t>();
   P.rec_y = ctx->ry.as<uint8_t>(); P.rec_u = ctx->ru.as<uint8_t>(); P.rec_v = ctx->rv.as<uint8_t>();
   P.segment = ctx->segment.as<uint8_t>(); P.img = ctx->img_params.as<wg::ImageParams>();
@@ -355,7 +400,8 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
   int rc;
   switch (enc_variant()) {
-    case 1: rc = launch_enc_waves<8, 4, 2>(ctx, P); break;   // no register cap (243 regs, 8 warps/SM)
+    case 1: rc = launch_enc_waves<8, 4, 2>(ctx, P); break;   // no register cap, 2 CTAs/SM
+    case 2: rc = launch_enc_persistent<8, 4, 3>(ctx, P); break;  // one persistent launch, dataflow scheduling
     default: rc = launch_enc_waves<8, 4, 3>(ctx, P); break;  // 168 regs, 3 CTAs/SM = 48 macroblocks/SM (measured best)
   }
   if (rc) return rc;
@@ -519,12 +565,24 @@ int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
   return WGPU_OK;
 }
 
+// After a persistent launch: a dependency wait that hit its iteration cap is a hard error, never silent garbage.
+static int enc_check_persistent(wgpu_ctx* ctx) {
+  if (!ctx->enc_persistent_used) return WGPU_OK;
+  int flag = 0;
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(&flag, ctx->enc_ctl.as<uint8_t>() + 8, 4, cudaMemcpyDeviceToHost));
+  ctx->enc_persistent_used = false;
+  if (flag) FAIL(WGPU_ERR_CUDA, "mode-search kernel: macroblock dependency wait timed out");
+  return WGPU_OK;
+}
+
 int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_sizes) {
   if (!ctx) return WGPU_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->e_done || ctx->plans.size() != (size_t)ctx->e_n) FAIL(WGPU_ERR_INVALID, "wgpu_enc_finish called before wgpu_enc_device");
   if (!out || !out_sizes) FAIL(WGPU_ERR_INVALID, "webp: nil writer");
   CK(cudaSetDevice(ctx->dev));
+  { const int prc = enc_check_persistent(ctx); if (prc) return prc; }
   const size_t n = ctx->e_n, nmb = (size_t)ctx->e_mbw * ctx->e_mbh;
   RESERVE(ctx->h_hdr, n * nmb * 48);
   std::atomic<int> too_small(0);
@@ -619,6 +677,7 @@ int wgpu_enc_fetch(wgpu_ctx* ctx, int image, uint8_t* mb_hdr, uint8_t* mb_modes,
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->e_done || image < 0 || image >= ctx->e_n) FAIL(WGPU_ERR_INVALID, "wgpu_enc_fetch: no encoded batch / bad image index");
   CK(cudaSetDevice(ctx->dev));
+  { const int prc = enc_check_persistent(ctx); if (prc) return prc; }
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t nmb = (size_t)ctx->e_mbw * ctx->e_mbh, i = image;
   if (mb_hdr || mb_modes || mb_nz) {
