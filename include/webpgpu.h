@@ -44,7 +44,7 @@ typedef enum {
  * encode.go:478-528; defaults = lossy.DefaultConfig (encode.go:66-86). */
 typedef struct {
   int quality;          /* 0..100 */
-  int method;           /* 0..6; 3..6 supported (parallel path), <3 -> WGPU_ERR_UNSUPPORTED */
+  int method;           /* 0..6; >=3: row-parallel path semantics (needs height > 48); <3: statLoop + serial encodeFrame semantics */
   int sns_strength;     /* 0..100, default 50 */
   int filter_strength;  /* 0..100, default 60 */
   int filter_sharpness; /* 0..7 */
@@ -53,6 +53,7 @@ typedef struct {
   int segments;         /* 1..4 */
   int preprocessing;    /* bit0: segment smoothing */
   int has_alpha;        /* 0: opaque input (alpha bytes ignored) */
+  int passes;           /* EncodeConfig.Pass, 1..10 (statLoop iterations on the Method < 3 path); 0 = 1 */
 } wgpu_enc_options;
 
 void wgpu_enc_options_default(wgpu_enc_options* o, int quality);

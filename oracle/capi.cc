@@ -13,7 +13,7 @@ extern "C" {
 // ---- whole-codec -------------------------------------------------------------------------
 struct OrcEncCfg {
   int quality, method, sns_strength, filter_strength, filter_sharpness, filter_type, partitions, segments,
-      preprocessing, has_alpha;
+      preprocessing, has_alpha, passes;
 };
 static EncodeConfig to_cfg(const OrcEncCfg* c) {
   EncodeConfig e;
@@ -21,6 +21,7 @@ static EncodeConfig to_cfg(const OrcEncCfg* c) {
   e.filter_strength = c->filter_strength; e.filter_sharpness = c->filter_sharpness;
   e.filter_type = c->filter_type; e.partitions = c->partitions; e.segments = c->segments;
   e.preprocessing = c->preprocessing;
+  e.pass = c->passes > 0 ? c->passes : 1;
   return e;
 }
 // Encode one RGBA image (parallel-path semantics).  Returns RIFF size or <0 (-1 unsupported
@@ -34,7 +35,7 @@ long orc_encode(const uint8_t* rgba, int stride, int w, int h, const OrcEncCfg* 
                 uint8_t* mb_hdr, uint8_t* mb_modes, uint8_t* mb_nz, int16_t* mb_coeffs, uint8_t* recon_y,
                 uint8_t* recon_u, uint8_t* recon_v, uint8_t* src_y, uint8_t* src_u, uint8_t* src_v,
                 uint8_t* alphas, int32_t* seg_out) {
-  if (cfg->method < 3 || ((h + 15) >> 4) < 4) return -1;  // serial path (encode.go:1356) not restated yet
+  if (cfg->method >= 3 && ((h + 15) >> 4) < 4) return -1;  // serial RD path (encode.go:1356, Method >= 3 with mbH < 4) not restated yet
   Encoder* enc = new Encoder();
   enc->init(rgba, stride, w, h, to_cfg(cfg), cfg->has_alpha);
   std::vector<uint8_t> vp8 = enc->encode_frame();

@@ -1592,10 +1592,337 @@ struct Encoder {
     return bw.finish();
   }
 
-  // EncodeFrame (encode.go:1324) on the parallel path; returns the raw VP8 frame.
+  // ================================================================================================
+  // Serial path for Method < 3 (encode.go:1334-1336,1356: statLoop + encodeFrame; no RD, no trellis, no
+  // error diffusion).  Mode decisions here do not depend on the coefficient probabilities, but the
+  // probability state does evolve through the mid-stream refreshes of every pass (encode_frame.go:35-57)
+  // and is restated literally, including statistics taken over not-yet-encoded (zero-state) macroblocks.
+  uint8_t yuv_p[33 * BPS] = {0};  // I4 scoring scratch whose borders are never filled
+  bool skip_tokens = false, skip_export = false;
+  std::vector<uint32_t> s_top_nz;
+  std::vector<uint8_t> s_top_nz_dc;
+  uint32_t s_left_nz = 0;
+  uint8_t s_left_nz_dc = 0;
+
+  void mb_import(int mx, int my) {  // MBIterator.Import (encode_iterator.go:115)
+    const int x = mx * 16, y = my * 16;
+    const int ww = width - x > 16 ? 16 : width - x, hh = height - y > 16 ? 16 : height - y;
+    import_block(&y_plane[(size_t)y * y_stride + x], y_stride, yuv_in + Y_OFF, ww, hh, 16);
+    const int uvw = (ww + 1) >> 1, uvh = (hh + 1) >> 1;
+    import_block(&u_plane[(size_t)my * 8 * uv_stride + mx * 8], uv_stride, yuv_in + U_OFF, uvw, uvh, 8);
+    import_block(&v_plane[(size_t)my * 8 * uv_stride + mx * 8], uv_stride, yuv_in + V_OFF, uvw, uvh, 8);
+  }
+  void mb_fill_ctx(int mx, int my, const RowCtx& rc) {  // FillPredContext (encode_iterator.go:262-377)
+    uint8_t* o = yuv_out;
+    for (int i = 0; i < 16; ++i) o[Y_OFF - BPS + i] = my > 0 ? top_y[mx * 16 + i] : 127;
+    for (int i = 0; i < 4; ++i)
+      o[Y_OFF - BPS + 16 + i] = my > 0 ? (mx < mb_w - 1 ? top_y[(mx + 1) * 16 + i] : top_y[mx * 16 + 15]) : 127;
+    for (int r = 1; r <= 3; ++r) memcpy(o + Y_OFF - BPS + 16 + r * 4 * BPS, o + Y_OFF - BPS + 16, 4);
+    o[Y_OFF - BPS - 1] = (mx > 0 && my > 0) ? rc.top_left_y : (my > 0 ? 129 : 127);
+    for (int j = 0; j < 16; ++j) o[Y_OFF - 1 + j * BPS] = mx > 0 ? rc.left_y[j] : 129;
+    for (int i = 0; i < 8; ++i) {
+      o[U_OFF - BPS + i] = my > 0 ? top_u[mx * 8 + i] : 127;
+      o[V_OFF - BPS + i] = my > 0 ? top_v[mx * 8 + i] : 127;
+    }
+    o[U_OFF - BPS - 1] = (mx > 0 && my > 0) ? rc.top_left_u : (my > 0 ? 129 : 127);
+    o[V_OFF - BPS - 1] = (mx > 0 && my > 0) ? rc.top_left_v : (my > 0 ? 129 : 127);
+    for (int j = 0; j < 8; ++j) {
+      o[U_OFF - 1 + j * BPS] = mx > 0 ? rc.left_u[j] : 129;
+      o[V_OFF - 1 + j * BPS] = mx > 0 ? rc.left_v[j] : 129;
+    }
+  }
+  void mb_export(int mx, int my, RowCtx& rc) {  // MBIterator.Export (encode_iterator.go:181-250)
+    if (!skip_export) {
+      const int x = mx * 16, y = my * 16;
+      const int wy = x + 16 > width ? width - x : 16, hy = y + 16 > height ? height - y : 16;
+      for (int j = 0; j < hy; ++j) memcpy(&y_plane[(size_t)(y + j) * y_stride + x], yuv_out + Y_OFF + j * BPS, wy);
+      for (int j = 0; j < 8; ++j) {
+        memcpy(&u_plane[(size_t)(my * 8 + j) * uv_stride + mx * 8], yuv_out + U_OFF + j * BPS, 8);
+        memcpy(&v_plane[(size_t)(my * 8 + j) * uv_stride + mx * 8], yuv_out + V_OFF + j * BPS, 8);
+      }
+    }
+    rc.top_left_y = top_y[mx * 16 + 15];
+    rc.top_left_u = top_u[mx * 8 + 7];
+    rc.top_left_v = top_v[mx * 8 + 7];
+    memcpy(&top_y[mx * 16], yuv_out + Y_OFF + 15 * BPS, 16);
+    memcpy(&top_u[mx * 8], yuv_out + U_OFF + 7 * BPS, 8);
+    memcpy(&top_v[mx * 8], yuv_out + V_OFF + 7 * BPS, 8);
+    for (int j = 0; j < 16; ++j) rc.left_y[j] = yuv_out[Y_OFF + j * BPS + 15];
+    for (int j = 0; j < 8; ++j) {
+      rc.left_u[j] = yuv_out[U_OFF + j * BPS + 7];
+      rc.left_v[j] = yuv_out[V_OFF + j * BPS + 7];
+    }
+  }
+
+  // pickBestMode, Method < 3 branch (encode_frame.go:165-189) with PickBestI16Mode / tryI4Modes / PickBestUVMode
+  // (encode_analysis.go:911-1070, encode_frame.go:193-237).
+  void pick_best_mode_fast(int mx, int my, MBInfo* info, const SegmentInfo* seg, RowCtx& rc) {
+    // I16: SSE of the prediction + fixed mode cost
+    uint64_t best16 = ~(uint64_t)0;
+    int mode16 = DC_PRED;
+    for (int mode = 0; mode < 4; ++mode) {
+      if (mode == V_PRED && my == 0) continue;
+      if (mode == H_PRED && mx == 0) continue;
+      if (mode == TM_PRED && (mx == 0 || my == 0)) continue;
+      pred_luma16(check_mode(mx, my, mode), yuv_out, Y_OFF);
+      const uint64_t sc = rd_score(sse16x16(yuv_in + Y_OFF, yuv_out + Y_OFF), kModeFixedCost16[mode], seg->lambda_i16);
+      if (sc < best16) { best16 = sc; mode16 = mode; }
+    }
+    if ((mx == 0 || my == 0) && is_flat_source16(yuv_in + Y_OFF)) mode16 = (mx == 0) ? DC_PRED : V_PRED;  // score keeps the loop's value
+    // I4 (Method >= 2): every mode is predicted into yuv_p, whose row 0 / column 0 / columns 17.. are never written
+    uint64_t best4 = ~(uint64_t)0;
+    uint8_t modes4[16] = {0};
+    if (cfg.method >= 2) {
+      uint64_t total = 0;
+      uint8_t top_m[4];
+      for (int i = 0; i < 4; ++i) top_m[i] = (my > 0) ? top_modes[mx * 4 + i] : B_DC_PRED;
+      for (int by = 0; by < 4; ++by)
+        for (int bx = 0; bx < 4; ++bx) {
+          const int b = by * 4 + bx;
+          const int top_mode = (by == 0) ? top_m[bx] : modes4[b - 4];
+          const int left_mode = (bx == 0) ? rc.left_modes[by] : modes4[b - 1];
+          const int src_off = Y_OFF + by * 4 * BPS + bx * 4, pred_off = BPS + 1 + by * 4 * BPS + bx * 4;
+          const bool has_top = (my > 0 || by > 0), has_left = (mx > 0 || bx > 0);
+          uint64_t bs = ~(uint64_t)0;
+          int bm = B_DC_PRED;
+          for (int mode = 0; mode < 10; ++mode) {  // PickBestI4Mode (encode_analysis.go:967)
+            if (!has_top && needs_top4(mode)) continue;
+            if (!has_left && needs_left4(mode)) continue;
+            pred_luma4(mode, yuv_p, pred_off);
+            const uint64_t sc = rd_score(sse4x4(yuv_in + src_off, yuv_p + pred_off), fixed_costs_i4[top_mode][left_mode][mode], seg->lambda_i4);
+            if (sc < bs) { bs = sc; bm = mode; }
+          }
+          modes4[b] = (uint8_t)bm;
+          total += bs;
+        }
+      for (int i = 0; i < 4; ++i) {  // saved whether or not I4 wins (encode_frame.go:229-231)
+        top_modes[mx * 4 + i] = modes4[12 + i];
+        rc.left_modes[i] = modes4[3 + 4 * i];
+      }
+      total += (uint64_t)seg->lambda_mode * 211;
+      best4 = total;
+    }
+    if (best4 < best16) {
+      info->mb_type = 1;
+      memcpy(info->modes, modes4, 16);
+    } else {
+      info->mb_type = 0;
+      info->i16_mode = (uint8_t)mode16;
+    }
+    // UV
+    uint64_t bestuv = ~(uint64_t)0;
+    int modeuv = DC_PRED;
+    for (int mode = 0; mode < 4; ++mode) {
+      if (mode == V_PRED && my == 0) continue;
+      if (mode == H_PRED && mx == 0) continue;
+      if (mode == TM_PRED && (mx == 0 || my == 0)) continue;
+      const int am = check_mode(mx, my, mode);
+      pred_chroma8(am, yuv_out, U_OFF);
+      pred_chroma8(am, yuv_out, V_OFF);
+      int disto = 0;
+      for (int by = 0; by < 2; ++by)
+        for (int bx = 0; bx < 2; ++bx) {
+          const int off = by * 4 * BPS + bx * 4;
+          disto += sse4x4(yuv_in + U_OFF + off, yuv_out + U_OFF + off) + sse4x4(yuv_in + V_OFF + off, yuv_out + V_OFF + off);
+        }
+      const uint64_t sc = rd_score(disto, kModeFixedCostUV[mode], seg->lambda_uv);
+      if (sc < bestuv) { bestuv = sc; modeuv = mode; }
+    }
+    info->uv_mode = (uint8_t)modeuv;
+  }
+
+  // One macroblock of encodeFrame (encode_frame.go:44-98) on the Method < 3 path.
+  void encode_mb_serial(int mx, int my, RowCtx& rc) {
+    const size_t idx = (size_t)my * mb_w + mx;
+    MBInfo* info = &mb_info[idx];
+    const SegmentInfo* seg = &dqm[info->segment];
+    mb_import(mx, my);
+    mb_fill_ctx(mx, my, rc);
+    pick_best_mode_fast(mx, my, info, seg, rc);
+    // encodeResiduals (encode_frame.go:350-645): plain quantisation everywhere on this path
+    if (info->mb_type == 0) {
+      pred_luma16(check_mode(mx, my, info->i16_mode), yuv_out, Y_OFF);
+      int16_t dc_coeffs[16];
+      uint32_t nz_y = 0;
+      for (int b = 0; b < 16; ++b) {
+        const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+        int16_t* c = info->coeffs + b * 16;
+        ftransform(yuv_in + off, yuv_out + off, c);
+        dc_coeffs[b] = c[0];
+        c[0] = 0;
+        const int nz = quantize_coeffs(c, c, &seg->y1, 1);
+        info->nz_y[b] = (uint8_t)nz;
+        if (nz > 0) nz_y |= 1u << b;
+      }
+      int16_t wht[16];
+      ftransform_wht(dc_coeffs, wht);
+      const int nz_dc = quantize_coeffs(wht, info->coeffs + 384, &seg->y2, 0);
+      info->nz_dc = (uint8_t)nz_dc;
+      if (nz_dc > 0) nz_y |= 1u << 24;
+      info->non_zero_y = nz_y;
+    } else {
+      uint32_t nz_y = 0;
+      for (int b = 0; b < 16; ++b) {
+        const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+        int16_t* c = info->coeffs + b * 16;
+        int16_t dq[16];
+        pred_luma4(info->modes[b], yuv_out, off);
+        ftransform(yuv_in + off, yuv_out + off, c);
+        const int nz = quantize_coeffs(c, c, &seg->y1, 0);
+        info->nz_y[b] = (uint8_t)nz;
+        if (nz > 0) nz_y |= 1u << b;
+        dequant_coeffs(c, dq, &seg->y1);
+        itransform_one(yuv_out + off, dq, yuv_out + off);
+      }
+      info->non_zero_y = nz_y;
+    }
+    {
+      const int am = check_mode(mx, my, info->uv_mode);
+      pred_chroma8(am, yuv_out, U_OFF);
+      pred_chroma8(am, yuv_out, V_OFF);
+      uint32_t nz_uv = 0;
+      for (int ch = 0; ch < 2; ++ch)
+        for (int b = 0; b < 4; ++b) {
+          const int off = (ch ? V_OFF : U_OFF) + (b >> 1) * 4 * BPS + (b & 1) * 4;
+          int16_t* c = info->coeffs + (16 + ch * 4 + b) * 16;
+          ftransform(yuv_in + off, yuv_out + off, c);
+          const int nz = quantize_coeffs(c, c, &seg->uv, 0);
+          info->nz_uv[ch * 4 + b] = (uint8_t)nz;
+          if (nz > 0) nz_uv |= 1u << (ch * 4 + b);
+        }
+      info->non_zero_uv = nz_uv;
+    }
+    info->skip = (info->non_zero_y == 0 && info->non_zero_uv == 0);
+    if (info->skip) {
+      num_skip++;
+      s_top_nz[mx] = 0; s_left_nz = 0;
+      if (info->mb_type == 0) { s_top_nz_dc[mx] = 0; s_left_nz_dc = 0; }
+    } else if (skip_tokens) {
+      update_nz(info, &s_top_nz[mx], &s_left_nz, &s_top_nz_dc[mx], &s_left_nz_dc);
+    } else {
+      mb_start[idx] = tokens.size();
+      walk_mb(info, &s_top_nz[mx], &s_left_nz, &s_top_nz_dc[mx], &s_left_nz_dc,
+              [&](const int16_t* c, int nz, int type, int first, int ctx) { record_coeffs(c, nz, type, first, ctx); });
+    }
+    // reconstructMB (encode_frame.go:855): I4 is already reconstructed
+    if (info->mb_type == 0) {
+      int16_t wht_dq[16], wht_buf[256], dq[16];
+      dequant_coeffs(info->coeffs + 384, wht_dq, &seg->y2);
+      transform_wht(wht_dq, wht_buf);
+      for (int b = 0; b < 16; ++b) {
+        const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+        dequant_coeffs(info->coeffs + b * 16, dq, &seg->y1);
+        dq[0] = wht_buf[b * 16];
+        itransform_one(yuv_out + off, dq, yuv_out + off);
+      }
+    }
+    for (int b = 0; b < 4; ++b) {
+      int16_t dq[16];
+      const int o = (b >> 1) * 4 * BPS + (b & 1) * 4;
+      dequant_coeffs(info->coeffs + (16 + b) * 16, dq, &seg->uv);
+      itransform_one(yuv_out + U_OFF + o, dq, yuv_out + U_OFF + o);
+      dequant_coeffs(info->coeffs + (20 + b) * 16, dq, &seg->uv);
+      itransform_one(yuv_out + V_OFF + o, dq, yuv_out + V_OFF + o);
+    }
+    mb_export(mx, my, rc);
+  }
+
+  // collectAllStats (encode_proba.go:171-313): the whole mb_info array, whatever it currently holds
+  void collect_all_stats(ProbaStats st) {
+    memset(st, 0, sizeof(ProbaStats));
+    std::vector<uint32_t> tnz(mb_w, 0);
+    std::vector<uint8_t> tdc(mb_w, 0);
+    for (int my = 0; my < mb_h; ++my) {
+      uint32_t lnz = 0;
+      uint8_t ldc = 0;
+      for (int mx = 0; mx < mb_w; ++mx) {
+        const MBInfo* info = &mb_info[(size_t)my * mb_w + mx];
+        if (info->skip) {
+          tnz[mx] = 0; lnz = 0;
+          if (info->mb_type == 0) { tdc[mx] = 0; ldc = 0; }
+          continue;
+        }
+        walk_mb(info, &tnz[mx], &lnz, &tdc[mx], &ldc,
+                [&](const int16_t* c, int nz, int type, int first, int ctx) { collect_coeff_stats(c, nz, type, first, ctx, st); });
+      }
+    }
+  }
+  void refresh_probas() {  // encode_frame.go:113-117
+    static thread_local ProbaStats st;
+    collect_all_stats(st);
+    optimize_proba(st);
+  }
+  // encodeFrame (encode_frame.go:15-108)
+  void encode_frame_serial_pass() {
+    top_y.assign(mb_w * 16, 127); top_u.assign(mb_w * 8, 127); top_v.assign(mb_w * 8, 127);
+    top_modes.assign(mb_w * 4, B_DC_PRED);
+    s_top_nz.assign(mb_w, 0); s_top_nz_dc.assign(mb_w, 0);
+    s_left_nz = 0; s_left_nz_dc = 0;
+    num_skip = 0;
+    const int total_mb = mb_w * mb_h;
+    int max_count = total_mb >> 3;
+    if (max_count < 96) max_count = 96;
+    int refresh_cnt = max_count;
+    for (int my = 0; my < mb_h; ++my) {
+      RowCtx rc;  // resetLeftContext (encode_iterator.go:71)
+      memset(rc.left_y, 129, 16); memset(rc.left_u, 129, 8); memset(rc.left_v, 129, 8);
+      memset(rc.left_modes, B_DC_PRED, 4);
+      rc.top_left_y = rc.top_left_u = rc.top_left_v = 127;
+      rc.left_nz = 0; rc.left_nz_dc = 0;
+      for (int mx = 0; mx < mb_w; ++mx) {
+        if (mx == 0) { s_left_nz = 0; s_left_nz_dc = 0; }
+        if (--refresh_cnt < 0) { refresh_probas(); refresh_cnt = max_count; }
+        encode_mb_serial(mx, my, rc);
+      }
+    }
+    if (num_skip > 0) skip_proba = (uint8_t)((total_mb - num_skip) * 255 / total_mb);
+  }
+  void stat_loop(int passes) {  // encode.go:1405-1437
+    int n = passes < 1 ? 1 : (passes > 10 ? 10 : passes);
+    for (int pass = 0; pass < n; ++pass) {
+      skip_tokens = true; skip_export = true;
+      encode_frame_serial_pass();
+      skip_tokens = false; skip_export = false;
+      static thread_local ProbaStats st;
+      collect_all_stats(st);
+      if (optimize_proba(st) == 0) break;
+    }
+  }
+  void rerecord_all_tokens() { record_all_tokens(nullptr); }  // encode_proba.go:317 (same walk, current probabilities)
+
+  std::vector<uint8_t> assemble_frame() {  // emitFrame / assembleFrame (encode_syntax.go:27-172)
+    std::vector<uint8_t> part0 = emit_partition0();
+    std::vector<std::vector<uint8_t>> parts(num_parts);
+    for (int i = 0; i < num_parts; ++i) parts[i] = emit_token_partition(i);
+    std::vector<uint8_t> out;
+    const uint32_t tag = (0u) | (0u << 1) | (1u << 4) | ((uint32_t)part0.size() << 5);
+    out.push_back((uint8_t)tag); out.push_back((uint8_t)(tag >> 8)); out.push_back((uint8_t)(tag >> 16));
+    out.push_back(0x9d); out.push_back(0x01); out.push_back(0x2a);
+    out.push_back((uint8_t)(width & 0xff)); out.push_back((uint8_t)((width & 0x3fff) >> 8));
+    out.push_back((uint8_t)(height & 0xff)); out.push_back((uint8_t)((height & 0x3fff) >> 8));
+    out.insert(out.end(), part0.begin(), part0.end());
+    for (int i = 0; i + 1 < num_parts; ++i) {
+      const size_t sz = parts[i].size();
+      out.push_back((uint8_t)sz); out.push_back((uint8_t)(sz >> 8)); out.push_back((uint8_t)(sz >> 16));
+    }
+    for (auto& p : parts) out.insert(out.end(), p.begin(), p.end());
+    return out;
+  }
+
+  // EncodeFrame (encode.go:1324); returns the raw VP8 frame.  Method >= 3 -> row-parallel path semantics
+  // (GOMAXPROCS > 1, mbH >= 4); Method < 3 -> statLoop + serial encodeFrame.
   std::vector<uint8_t> encode_frame() {
     analysis();
     set_segment_probas();
+    if (cfg.method < 3) {
+      stat_loop(cfg.pass);
+      tokens.clear();
+      encode_frame_serial_pass();
+      static thread_local ProbaStats st2;
+      collect_all_stats(st2);
+      if (optimize_proba(st2) > 0) rerecord_all_tokens();
+      return assemble_frame();
+    }
     // Phase A
     top_y.assign(mb_w * 16, 127); top_u.assign(mb_w * 8, 127); top_v.assign(mb_w * 8, 127);
     top_modes.assign(mb_w * 4, B_DC_PRED);
@@ -1614,23 +1941,7 @@ struct Encoder {
     const int total_mb = mb_w * mb_h;
     if (num_skip > 0) skip_proba = (uint8_t)((total_mb - num_skip) * 255 / total_mb);
     if (optimize_proba(st) > 0) record_all_tokens(nullptr);
-    // emitFrame / assembleFrame (encode_syntax.go:27-172)
-    std::vector<uint8_t> part0 = emit_partition0();
-    std::vector<std::vector<uint8_t>> parts(num_parts);
-    for (int i = 0; i < num_parts; ++i) parts[i] = emit_token_partition(i);
-    std::vector<uint8_t> out;
-    const uint32_t tag = (0u) | (0u << 1) | (1u << 4) | ((uint32_t)part0.size() << 5);
-    out.push_back((uint8_t)tag); out.push_back((uint8_t)(tag >> 8)); out.push_back((uint8_t)(tag >> 16));
-    out.push_back(0x9d); out.push_back(0x01); out.push_back(0x2a);
-    out.push_back((uint8_t)(width & 0xff)); out.push_back((uint8_t)((width & 0x3fff) >> 8));
-    out.push_back((uint8_t)(height & 0xff)); out.push_back((uint8_t)((height & 0x3fff) >> 8));
-    out.insert(out.end(), part0.begin(), part0.end());
-    for (int i = 0; i + 1 < num_parts; ++i) {
-      const size_t sz = parts[i].size();
-      out.push_back((uint8_t)sz); out.push_back((uint8_t)(sz >> 8)); out.push_back((uint8_t)(sz >> 16));
-    }
-    for (auto& p : parts) out.insert(out.end(), p.begin(), p.end());
-    return out;
+    return assemble_frame();
   }
 };
 

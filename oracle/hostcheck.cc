@@ -7,7 +7,7 @@
 
 extern "C" {
 struct OrcEncCfg2 {
-  int quality, method, sns_strength, filter_strength, filter_sharpness, filter_type, partitions, segments, preprocessing, has_alpha;
+  int quality, method, sns_strength, filter_strength, filter_sharpness, filter_type, partitions, segments, preprocessing, has_alpha, passes;
 };
 // Returns the RIFF size produced by the product serialiser (out receives it) or <0; *same = 1 when it equals the
 // oracle's bytes; *ms_per_rep = serialiser time per repetition.
@@ -17,6 +17,7 @@ long hostcheck_serialize(const uint8_t* rgba, int stride, int w, int h, const Or
   e.quality = c->quality; e.method = c->method; e.sns_strength = c->sns_strength; e.filter_strength = c->filter_strength;
   e.filter_sharpness = c->filter_sharpness; e.filter_type = c->filter_type; e.partitions = c->partitions; e.segments = c->segments;
   e.preprocessing = c->preprocessing;
+  e.pass = c->passes > 0 ? c->passes : 1;
   orc::Encoder* enc = new orc::Encoder();
   enc->init(rgba, stride, w, h, e, c->has_alpha);
   std::vector<uint8_t> ref = orc::riff_wrap(enc->encode_frame());
@@ -37,7 +38,7 @@ long hostcheck_serialize(const uint8_t* rgba, int stride, int w, int h, const Or
   wgpu_enc_options o;
   o.quality = c->quality; o.method = c->method; o.sns_strength = c->sns_strength; o.filter_strength = c->filter_strength;
   o.filter_sharpness = c->filter_sharpness; o.filter_type = c->filter_type; o.partitions = c->partitions; o.segments = c->segments;
-  o.preprocessing = c->preprocessing; o.has_alpha = c->has_alpha;
+  o.preprocessing = c->preprocessing; o.has_alpha = c->has_alpha; o.passes = c->passes;
   wgh::FramePlan fp;
   wgh::plan_frame(&fp, o, w, h, enc->alphas.data(), (long long)enc->global_uv_alpha * nmb, segmap.data());
   fp.num_parts = 1 << o.partitions;
@@ -47,7 +48,8 @@ long hostcheck_serialize(const uint8_t* rgba, int stride, int w, int h, const Or
   const auto t0 = std::chrono::steady_clock::now();
   for (int r = 0; r < (reps > 0 ? reps : 1); ++r) {
     riff.clear();
-    wgh::serialize_frame(fp, hdr.data(), coeffs.data(), segmap.data(), stats.data(), &riff);
+    if (o.method < 3) wgh::serialize_frame_serial(fp, hdr.data(), coeffs.data(), segmap.data(), e.pass, &riff);
+    else wgh::serialize_frame(fp, hdr.data(), coeffs.data(), segmap.data(), stats.data(), &riff);
   }
   *ms_per_rep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / (reps > 0 ? reps : 1);
   *same = seg_same && riff.size() == ref.size() && !memcmp(riff.data(), ref.data(), ref.size());

@@ -72,6 +72,15 @@ ENC_CASES = [
     (128, 128, [2], dict(Partitions=2, Quality=90)),
     (128, 128, [1], dict(Partitions=3)),
     (768, 576, [1], {}),
+    # Method < 3: statLoop + serial encodeFrame semantics (BASELINE configs[4]: 256x256 q80 method 2)
+    (256, 256, [0, 1, 2], dict(Method=2, Quality=80)),
+    (256, 256, [4, 5], dict(Method=2, Quality=80, Segments=1)),
+    (100, 70, [1, 2], dict(Method=0)),
+    (128, 96, [1, 2], dict(Method=1, Quality=50)),
+    (64, 32, [1, 2], dict(Method=2)),
+    (16, 16, [2], dict(Method=2, Quality=90)),
+    (130, 71, [2], dict(Method=2, Partitions=1, Quality=90)),
+    (320, 240, [2], dict(Method=2, Pass=3, Quality=60)),
 ]
 
 
@@ -138,12 +147,11 @@ def test_encode_test_png(oracle, gpu_ctx):
 
 def test_encode_rejections(gpu_ctx):
     img = np.full((64, 64, 4), 255, np.uint8)
-    with pytest.raises(native.WebPGPUError) as e:
-        webp_b200.EncodeBatch(img[None], _opts(Method=2), gpu_ctx)
-    assert e.value.code == native.ERR_UNSUPPORTED
-    with pytest.raises(native.WebPGPUError) as e:
+    with pytest.raises(native.WebPGPUError) as e:  # Method >= 3 on < 4 macroblock rows: the reference's serial RD path
         webp_b200.EncodeBatch(img[None, :40], _opts(), gpu_ctx)
     assert e.value.code == native.ERR_UNSUPPORTED
+    with pytest.raises(webp_b200.WebPError):
+        webp_b200.EncodeBatch(img[None], _opts(TargetPSNR=40.0), gpu_ctx)
     with pytest.raises(webp_b200.WebPError):
         webp_b200.EncodeBatch(img[None], _opts(Lossless=True), gpu_ctx)
 

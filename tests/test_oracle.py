@@ -63,6 +63,8 @@ def test_import_matches_libwebp(oracle, w, h, kind):
     (128, 96, 1, dict(segments=1)), (128, 96, 2, dict(filter_type=0)), (128, 96, 1, dict(method=3)),
     (128, 96, 2, dict(method=6, quality=40)), (128, 96, 1, dict(filter_sharpness=5, filter_strength=80)),
     (128, 128, 2, dict(partitions=2, quality=90)), (128, 96, 2, dict(quality=95)),
+    # serial path (Method < 3)
+    (256, 256, 1, dict(method=2, quality=80)), (100, 70, 2, dict(method=0)), (64, 32, 1, dict(method=1)), (16, 16, 2, dict(method=2)),
 ])
 def test_oracle_stream_decodes_identically_in_libwebp(oracle, w, h, idx, kw):
     """Every oracle-encoded stream must decode in libwebp to exactly what the oracle's decoder produces,
@@ -113,3 +115,21 @@ def test_ssim_identity_and_psnr(oracle):
     assert oracle.lib().orc_psnr_from_sse(0, 100) == 99.0
     b = a.copy(); b[0, 0] ^= 1
     assert oracle.plane_sse(a, b) == 1
+
+
+def test_host_serialisers_reproduce_oracle_bytes(oracle):
+    """Product host code (webp_b200/csrc/host_enc.h: segment plan + token/bool-coding serialisers, incl. the serial-path
+    probability-refresh schedule) driven from oracle per-MB data must reproduce the oracle's bytes (CPU-only check)."""
+    import ctypes as C
+    L = C.CDLL(os.path.join(os.path.dirname(DATA), "..", "oracle", "_build", "libhostcheck.so"))
+    L.hostcheck_serialize.restype = C.c_long
+    os.environ["HOSTCHECK_TOKENS"] = "1"
+    for (w, h, idx, kw) in [(128, 96, 1, {}), (160, 112, 2, dict(partitions=2)), (96, 80, 0, dict(segments=1)), (256, 256, 2, dict(method=2, quality=80)),
+                            (100, 70, 1, dict(method=0)), (320, 240, 2, dict(method=2, passes=3, quality=60)), (130, 71, 2, dict(method=1, partitions=1))]:
+        img = oracle.synth_image(w, h, idx)
+        cfg = oracle.default_cfg(**kw)
+        out = np.zeros(2 << 20, np.uint8)
+        same, ms = C.c_int(), C.c_double()
+        n = L.hostcheck_serialize(img.ctypes.data_as(C.c_void_p), C.c_int(img.strides[0]), w, h, C.byref(cfg), out.ctypes.data_as(C.c_void_p),
+                                  C.c_long(out.size), 1, C.byref(same), C.byref(ms))
+        assert n > 0 and same.value == 1, (w, h, idx, kw)

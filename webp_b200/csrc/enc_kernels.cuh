@@ -24,6 +24,7 @@ struct EncKernelParams {
   const uint8_t* segment;       // [n][nmb]
   const ImageParams* img;       // [n]
   uint32_t* ctx;                // [n][nmb] packed NZ context (see pack_ctx)
+  uint32_t* ctx2;               // [n][nmb] Method < 3: trial 4x4 modes of the bottom row / right column (mode-cost context)
   int* progress;                // [n][mb_h] finished macroblocks per row (persistent kernel)
   unsigned long long* work_counter;  // next group to claim (persistent kernel)
   const long long* wave_start;  // [waves + 1] prefix of groups per wave (persistent kernel)
@@ -221,7 +222,7 @@ template <bool PERSIST, class Tp>
 __device__ __forceinline__ Tp ldn(const Tp* p) { return PERSIST ? __ldcg(p) : *p; }
 
 // The mode search of MPW = 32/G macroblocks by one warp: macroblock `task_base + lane/G` of wave `wave`.
-template <int G, bool PERSIST>
+template <int G, bool PERSIST, bool FAST>
 __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wave, long long task_base, MBShared* s_mb_warp,
                                                 const CostTabs& T, const uint16_t* s_i4cost) {
   const int lane = threadIdx.x & 31;
@@ -343,21 +344,28 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       top_nz = cw & 0xff;
       top_nz_dc = (cw >> 16) & 1;
       const uint8_t* th = hdr - (size_t)P.mb_w * 48;
-      if (ldn<PERSIST>(&th[0]) == 1) { top_modes[0] = ldn<PERSIST>(&th[8 + 12]); top_modes[1] = ldn<PERSIST>(&th[8 + 13]); top_modes[2] = ldn<PERSIST>(&th[8 + 14]); top_modes[3] = ldn<PERSIST>(&th[8 + 15]); }
+      if (FAST) {
+        const uint32_t tm = ldn<PERSIST>(&P.ctx2[(size_t)img * nmb + mb_idx - P.mb_w]);
+        for (int i = 0; i < 4; ++i) top_modes[i] = (tm >> (4 * i)) & 15;
+      } else if (ldn<PERSIST>(&th[0]) == 1) { top_modes[0] = ldn<PERSIST>(&th[8 + 12]); top_modes[1] = ldn<PERSIST>(&th[8 + 13]); top_modes[2] = ldn<PERSIST>(&th[8 + 14]); top_modes[3] = ldn<PERSIST>(&th[8 + 15]); }
     }
     if (mx > 0) {
       const uint32_t cw = ldn<PERSIST>(&ctxw[mb_idx - 1]);
       left_nz = (cw >> 8) & 0xff;
       left_nz_dc = (cw >> 17) & 1;
       const uint8_t* lh = hdr - 48;
-      if (ldn<PERSIST>(&lh[0]) == 1) { left_modes[0] = ldn<PERSIST>(&lh[8 + 3]); left_modes[1] = ldn<PERSIST>(&lh[8 + 7]); left_modes[2] = ldn<PERSIST>(&lh[8 + 11]); left_modes[3] = ldn<PERSIST>(&lh[8 + 15]); }
+      if (FAST) {
+        const uint32_t lm = ldn<PERSIST>(&P.ctx2[(size_t)img * nmb + mb_idx - 1]);
+        for (int i = 0; i < 4; ++i) left_modes[i] = (lm >> (16 + 4 * i)) & 15;
+      } else if (ldn<PERSIST>(&lh[0]) == 1) { left_modes[0] = ldn<PERSIST>(&lh[8 + 3]); left_modes[1] = ldn<PERSIST>(&lh[8 + 7]); left_modes[2] = ldn<PERSIST>(&lh[8 + 11]); left_modes[3] = ldn<PERSIST>(&lh[8 + 15]); }
     }
   }
   __syncwarp();
 
-  // ---- 3a. I16 RD search (encode_parallel.go:624-735)
-  int best16 = 0, rate16 = 0, disto16 = 0;
-  {
+  int best16 = 0;
+  unsigned long long score16 = 0;
+  if constexpr (!FAST) {  // ---- 3a. I16 RD search (encode_parallel.go:624-735)
+    int rate16 = 0, disto16 = 0;
     unsigned long long best_score = ~0ull;
     int src_flat = 0;
     if (active) {  // isFlatSource16 (encode_analysis.go:358)
@@ -443,13 +451,48 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       }
       __syncwarp();
     }
+    score16 = rd_score(disto16, rate16, seg.lambda_mode);
   }
-  const unsigned long long score16 = rd_score(disto16, rate16, seg.lambda_mode);
+  else {  // ---- 3a (Method < 3). PickBestI16Mode (encode_analysis.go:911-961): prediction SSE + fixed mode cost
+    unsigned long long best_score = ~0ull;
+    if (active) for (int i = gl; i < U_OFF / 4; i += G) reinterpret_cast<uint32_t*>(S.out2)[i] = reinterpret_cast<const uint32_t*>(S.out)[i];
+    __syncwarp();
+    for (int mode = 0; mode < 4; ++mode) {
+      const bool allowed = active && !((mode == 2 && my == 0) || (mode == 3 && mx == 0) || (mode == 1 && (mx == 0 || my == 0)));
+      if (allowed) pred_square_coop<G>(gl, check_mode(mx, my, mode), S.out2, Y_OFF, 16);
+      __syncwarp();
+      int disto = 0;
+      if (allowed)
+        for (int b = gl; b < 16; b += G) {
+          int s_[16], p_[16];
+          load_src_block(S.in, b, s_);
+          load4x4(S.out2 + Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4, p_);
+          disto += sse16(s_, p_);
+        }
+      disto = grp_sum<G>(disto);
+      if (allowed) {
+        const unsigned long long score = rd_score(disto, kModeFixedCost16(mode), seg.lambda_i16);
+        if (score < best_score) { best_score = score; best16 = mode; }
+      }
+      __syncwarp();
+    }
+    score16 = best_score;
+    {  // checkerboard avoidance for flat border blocks (encode_analysis.go:950-959); the score keeps the loop's value
+      const bool border = active && (mx == 0 || my == 0);
+      int ok = 1;
+      if (border) {
+        const int v0 = S.in[0];
+        for (int i = gl; i < 256; i += G) ok &= (S.in[i] == v0);
+      }
+      ok = grp_and<G>(ok);
+      if (border && ok) best16 = (mx == 0) ? 0 : 2;
+    }
+  }
 
-  // ---- 3b. I4 RD search (encode_parallel.go:738-1027)
   unsigned long long score4 = ~0ull;
   uint32_t i4_nzmask = 0;
-  {
+  uint32_t trial_modes = 0;  // FAST: bottom-row (bits 0-15) and right-column (16-31) trial modes for the neighbours
+  if constexpr (!FAST) {  // ---- 3b. I4 RD search (encode_parallel.go:738-1027)
     if (active) for (int i = gl; i < YUV_SIZE / 4; i += G) reinterpret_cast<uint32_t*>(S.out2)[i] = reinterpret_cast<const uint32_t*>(S.out)[i];
     __syncwarp();
     int total_rate = 0, total_disto = 0, total_hdr = 0;
@@ -594,12 +637,94 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
     __syncwarp();
     S.misc[0] = use_i4;  // uniform within the group
   }
+  else {  // ---- 3b (Method < 3). tryI4Modes / PickBestI4Mode (encode_frame.go:193-237, encode_analysis.go:967-1010)
+    // Every mode is predicted into a scratch block buffer whose borders are never filled (the reference's yuvP,
+    // SURVEY F7): row 0, column 0 and columns 17.. stay zero, the interior holds the LAST evaluated mode of the
+    // blocks already visited.  S.out2 plays that buffer (block origin BPS + 1, as in the reference).
+    uint32_t modes_lo = 0, modes_hi = 0;
+    unsigned long long total = 0;
+    const bool do_i4 = P.method >= 2;
+    if (active && do_i4) for (int i = gl; i < (17 * BPS) / 4; i += G) reinterpret_cast<uint32_t*>(S.out2)[i] = 0u;
+    __syncwarp();
+    if (do_i4) {
+      for (int b = 0; b < 16; ++b) {
+        const int bx = b & 3, by = b >> 2;
+        auto get_mode = [&](int k) -> int { return (k < 8) ? (modes_lo >> (4 * k)) & 15 : (modes_hi >> (4 * (k - 8))) & 15; };
+        const int top_mode = by == 0 ? top_modes[bx] : get_mode(b - 4);
+        const int left_mode = bx == 0 ? left_modes[by] : get_mode(b - 1);
+        const bool has_top = my > 0 || by > 0, has_left = mx > 0 || bx > 0;
+        uint8_t* pp = S.out2 + BPS + 1 + by * 4 * BPS + bx * 4;
+        uint32_t elig = 0;
+#pragma unroll
+        for (int m = 0; m < 10; ++m)
+          if (!((!has_top && needs_top4(m)) || (!has_left && needs_left4(m)))) elig |= 1u << m;
+        const int last_mode = 31 - __clz(elig);
+        unsigned long long best = ~0ull;  // (score << 4 | mode): lexicographic min == strict '<' in mode order
+        int keep[16];
+        bool have_keep = false;
+        if (active) {
+          int e[13], s_[16];
+          e[0] = pp[-BPS - 1];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[1 + i] = pp[-BPS + i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) e[9 + j] = pp[-1 + j * BPS];
+          load_src_block(S.in, b, s_);
+          for (int m = gl; m < 10; m += G) {
+            if (!((elig >> m) & 1)) continue;
+            int p_[16];
+            pred4(m, e, p_);
+            const unsigned long long sc = rd_score(sse16(s_, p_), s_i4cost[(top_mode * 10 + left_mode) * 10 + m], seg.lambda_i4);
+            const unsigned long long key = (sc << 4) | (unsigned)m;
+            best = key < best ? key : best;
+            if (m == last_mode) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) keep[i] = p_[i];
+              have_keep = true;
+            }
+          }
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o, G);
+          best = other < best ? other : best;
+        }
+        __syncwarp();  // all lanes have read the context before the block area is overwritten
+        if (active && have_keep) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pp[(i >> 2) * BPS + (i & 3)] = (uint8_t)keep[i];
+        }
+        __syncwarp();
+        if (active) {
+          const int bm = (int)(best & 15);
+          if (b < 8) modes_lo |= (uint32_t)bm << (4 * b); else modes_hi |= (uint32_t)bm << (4 * (b - 8));
+          total += best >> 4;
+        }
+      }
+      total += (unsigned long long)seg.lambda_mode * 211ull;
+      score4 = total;
+      // saved for the neighbours whether or not I4 wins (encode_frame.go:229-231)
+      trial_modes = ((modes_hi >> 16) & 0xffffu) | (((modes_lo >> 12) & 15) << 16) | (((modes_lo >> 28) & 15) << 20) |
+                    (((modes_hi >> 12) & 15) << 24) | (((modes_hi >> 28) & 15) << 28);
+    }
+    const bool use_i4 = active && do_i4 && score4 < score16;
+    if (active) {
+      if (use_i4) {
+        for (int i = gl; i < 16; i += G) hdr[8 + i] = (uint8_t)((i < 8) ? (modes_lo >> (4 * i)) & 15 : (modes_hi >> (4 * (i - 8))) & 15);
+      } else {
+        pred_square_coop<G>(gl, check_mode(mx, my, best16), S.out, Y_OFF, 16);
+        for (int i = gl; i < 16; i += G) hdr[8 + i] = 0;
+      }
+    }
+    __syncwarp();
+    S.misc[0] = use_i4;
+    S.misc[3] = (int)modes_lo; S.misc[2] = (int)modes_hi;  // for the residual pass below
+  }
   __syncwarp();
   const bool use_i4 = S.misc[0] != 0;
 
-  // ---- 3c. UV RD search (encode_parallel.go:1030-1116)
   int best_uv = 0;
-  {
+  if constexpr (!FAST) {  // ---- 3c. UV RD search (encode_parallel.go:1030-1116)
     unsigned long long best_score = ~0ull;
     if (active)
       for (int i = gl; i < (YUV_SIZE - U_OFF) / 4; i += G)
@@ -651,6 +776,36 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
         rate += kModeFixedCostUV(mode);
         if (mode > 0 && ac_cnt <= 2) rate += 140 * 8;
         const unsigned long long score = rd_score(disto, rate, seg.lambda_uv);
+        if (score < best_score) { best_score = score; best_uv = mode; }
+      }
+      __syncwarp();
+    }
+  }
+  else {  // ---- 3c (Method < 3). PickBestUVMode (encode_analysis.go:1015-1070): SSE of both planes + fixed mode cost
+    unsigned long long best_score = ~0ull;
+    if (active)
+      for (int i = gl; i < (YUV_SIZE - U_OFF) / 4; i += G)
+        reinterpret_cast<uint32_t*>(S.out2 + U_OFF)[i] = reinterpret_cast<const uint32_t*>(S.out + U_OFF)[i];
+    __syncwarp();
+    for (int mode = 0; mode < 4; ++mode) {
+      const bool allowed = active && !((mode == 2 && my == 0) || (mode == 3 && mx == 0) || (mode == 1 && (mx == 0 || my == 0)));
+      if (allowed) {
+        const int am = check_mode(mx, my, mode);
+        pred_square_coop<G>(gl, am, S.out2, U_OFF, 8);
+        pred_square_coop<G>(gl, am, S.out2, V_OFF, 8);
+      }
+      __syncwarp();
+      int disto = 0;
+      if (allowed)
+        for (int b = gl; b < 8; b += G) {
+          int s_[16], p_[16];
+          load_src_block(S.in, 16 + b, s_);
+          load4x4(S.out2 + ((b & 4) ? V_OFF : U_OFF) + ((b >> 1) & 1) * 4 * BPS + (b & 1) * 4, p_);
+          disto += sse16(s_, p_);
+        }
+      disto = grp_sum<G>(disto);
+      if (allowed) {
+        const unsigned long long score = rd_score(disto, kModeFixedCostUV(mode), seg.lambda_uv);
         if (score < best_score) { best_score = score; best_uv = mode; }
       }
       __syncwarp();
@@ -730,6 +885,37 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       store4x4(S.out + off, r);
     }
     for (int b = 0; b < 16; ++b) nzy_flags |= (uint32_t)(S.nz[b] > 0) << b;
+  }
+  if constexpr (FAST) {
+    // encodeI4Residuals without cached coefficients (encode_frame.go:439-497): predict from the real context, transform,
+    // plain quantisation, immediate reconstruction; the sixteen blocks are a dependency chain, one lane walks them.
+    if (active && use_i4 && gl == 0) {
+      const uint32_t mlo = (uint32_t)S.misc[3], mhi = (uint32_t)S.misc[2];
+      uint32_t nzmask = 0;
+      for (int b = 0; b < 16; ++b) {
+        const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+        const int mode = (b < 8) ? (mlo >> (4 * b)) & 15 : (mhi >> (4 * (b - 8))) & 15;
+        int e[13], s_[16], p_[16], c[16], q[16], dq[16], r[16];
+        load_pred4_ctx(S.out + off, e);
+        load_src_block(S.in, b, s_);
+        pred4(mode, e, p_);
+        ftransform(s_, p_, c);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) S.lev[b][i] = (int16_t)c[i];
+        const int nz = quantize_smem(S.lev[b], seg.y1, 0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { q[i] = S.lev[b][i]; oc[b * 16 + i] = (int16_t)q[i]; }
+        S.nz[b] = (uint8_t)nz;
+        hdr[24 + b] = (uint8_t)nz;
+        if (nz > 0) nzmask |= 1u << b;
+        dequant_block(q, dq, seg.y1);
+        itransform(p_, dq, r);
+        store4x4(S.out + off, r);
+      }
+      S.misc[1] = (int)nzmask;
+    }
+    __syncwarp();
+    if (active && use_i4) i4_nzmask = (uint32_t)S.misc[1];
   }
   if (active && use_i4) {
     nzy_flags = i4_nzmask;
@@ -824,6 +1010,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       const uint32_t out_l = yl | (ul << 4) | (vl << 6);
       const int tdc = i16 ? dcflag : top_nz_dc, ldc = i16 ? dcflag : left_nz_dc;
       ctxw[mb_idx] = pack_ctx(out_t, out_l, tdc, ldc);
+      if (FAST) P.ctx2[(size_t)img * nmb + mb_idx] = trial_modes;
     }
   }
   if (PERSIST) {  // publish: everything this macroblock wrote must be visible before the row counter moves
@@ -854,7 +1041,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
   constexpr int MPW = 32 / G;  // macroblocks per warp
   WG_STAGE_TABLES(WARPS * 32);
   const int warp = threadIdx.x >> 5;
-  encode_mb_group<G, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
+  encode_mb_group<G, false, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
+}
+
+// Method < 3 (the reference's non-RD decisions, serial-path semantics): same wavefront, lighter body.
+template <int G, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) encode_fast_wave_kernel(const EncKernelParams P, int wave) {
+  constexpr int MPW = 32 / G;
+  WG_STAGE_TABLES(WARPS * 32);
+  const int warp = threadIdx.x >> 5;
+  encode_mb_group<G, false, true>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
 }
 
 // The whole mode search in ONE launch: persistent warps claim groups of 32/G macroblocks in wave order from a global
@@ -873,7 +1069,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_persistent_kernel(con
     grp = __shfl_sync(0xffffffffu, grp, 0);
     if (grp >= P.total_groups) break;
     while (grp >= P.wave_start[wave + 1]) ++wave;  // groups are claimed in increasing order by this warp
-    encode_mb_group<G, true>(P, wave, (grp - P.wave_start[wave]) * MPW, s_mb + warp * MPW, T, s_i4cost);
+    encode_mb_group<G, true, false>(P, wave, (grp - P.wave_start[wave]) * MPW, s_mb + warp * MPW, T, s_i4cost);
     __syncwarp();
   }
 }

@@ -339,6 +339,41 @@ static inline void walk_mb(const MBView& m, uint32_t* top_nz, uint32_t* left_nz,
   *left_nz = out_l;
 }
 
+typedef int Stats[4][8][3][11][2];
+// collectCoeffStats (encode_proba.go:10-113) on the host: only the serial-path serialiser needs it (the mid-stream
+// probability refreshes look at partially encoded frames); the parallel path takes its statistics from the GPU.
+static inline void stat_block(const int16_t* c, int n_coeffs, int type, int first, int ctx, Stats st) {
+  int n = first;
+  if (n_coeffs <= first) { st[type][kBands[n]][ctx][0][0]++; return; }
+  while (n < 16) {
+    int b = kBands[n];
+    if (n >= n_coeffs) { st[type][b][ctx][0][0]++; return; }
+    st[type][b][ctx][0][1]++;
+    for (;;) {
+      const int v = abs((int)c[kZigzag[n]]);
+      b = kBands[n];
+      int(*q)[2] = st[type][b][ctx];
+      if (v == 0) { q[1][0]++; if (++n >= 16) return; ctx = 0; continue; }
+      q[1][1]++;
+      if (v == 1) { q[2][0]++; }
+      else {
+        q[2][1]++;
+        if (v <= 4) { q[3][0]++; if (v == 2) q[4][0]++; else { q[4][1]++; q[5][v == 3 ? 0 : 1]++; } }
+        else if (v <= 10) { q[3][1]++; q[6][0]++; q[7][v <= 6 ? 0 : 1]++; }
+        else {
+          q[3][1]++; q[6][1]++;
+          const int cat = v <= 18 ? 0 : v <= 34 ? 1 : v <= 66 ? 2 : 3;
+          q[8][cat >> 1]++;
+          q[9 + (cat >> 1)][cat & 1]++;
+        }
+      }
+      ctx = (v == 1) ? 1 : 2;
+      n++;
+      break;
+    }
+  }
+}
+
 template <class Sink>
 static inline void code_block(Sink& bw, const uint8_t (*pb)[3][11] /*[band][ctx][p]*/, const int16_t* c, int n_coeffs,
                               int first, int ctx) {  // RecordCoeffs + recordLevelVP8 (encode_token.go:115-300)
@@ -702,6 +737,138 @@ static inline void serialize_frame(const FramePlan& fp, const uint8_t* mb_hdr /*
     }
     for (int pi = 0; pi < np; ++pi) riff->insert(riff->end(), parts[pi].begin(), parts[pi].end());
   }
+  finish_riff(fp, hdr_pos, part0.size(), riff);
+}
+
+// optimizeProba (encode_proba.go:117-156): compares against CoeffsProba0, only ever SETS entries of `proba`; returns the
+// number of entries set.  Costs are int64 (Go int).
+static inline int optimize_proba_host(const Stats st, uint8_t proba[4][8][3][11]) {
+  int updates = 0;
+  for (int t = 0; t < 4; ++t)
+    for (int b = 0; b < 8; ++b)
+      for (int c = 0; c < 3; ++c)
+        for (int p = 0; p < 11; ++p) {
+          const int c0 = st[t][b][c][p][0], c1 = st[t][b][c][p][1], tot = c0 + c1;
+          if (!tot) continue;
+          const int new_p = c1 > 0 ? 255 - (int)((long long)c1 * 255 / tot) : 255;
+          const int idx = ((t * 8 + b) * 3 + c) * 11 + p;
+          const int old_p = kCoeffsProba0[idx];
+          const uint8_t up = kCoeffsUpdateProba[idx];
+          auto bc = [&](int pr) -> long long { pr = clampi(pr, 1, 255); return (long long)c1 * bit_cost(1, (uint8_t)pr) + (long long)c0 * bit_cost(0, (uint8_t)pr); };
+          if (bc(old_p) + bit_cost(0, up) > bc(new_p) + bit_cost(1, up) + 8 * 256) { proba[t][b][c][p] = (uint8_t)new_p; ++updates; }
+        }
+  return updates;
+}
+
+// Serial-path serialiser (Method < 3: statLoop + encodeFrame, encode.go:1334-1400, encode_frame.go:15-108).  The GPU's
+// mode decisions on this path do not depend on the coefficient probabilities, so one device pass gives the content
+// of mbInfo for every reference pass; what the host restates is the evolution of enc.proba through the mid-stream
+// refreshes -- in the first statLoop pass the statistics cover the macroblocks encoded so far plus ZERO-STATE entries
+// for the rest (collectAllStats walks the whole array, encode_proba.go:171) -- and the inline token recording.
+static inline void serialize_frame_serial(const FramePlan& fp, const uint8_t* mb_hdr, const int16_t* mb_coeffs, const uint8_t* segment_map,
+                                          int passes, std::vector<uint8_t>* riff) {
+  const int mb_w = fp.mb_w, mb_h = fp.mb_h, total = mb_w * mb_h;
+  uint8_t proba[4][8][3][11];
+  memcpy(proba, kCoeffsProba0, sizeof(proba));
+  static thread_local Stats st;
+  static const uint8_t zero_hdr[48] = {0};
+  static const int16_t zero_coeffs[400] = {0};
+  std::vector<uint32_t> top_nz(mb_w);
+  std::vector<uint8_t> top_dc(mb_w);
+  auto collect = [&](int cut) {  // collectAllStats with macroblocks >= cut still in their zero state
+    memset(st, 0, sizeof(st));
+    std::fill(top_nz.begin(), top_nz.end(), 0u);
+    std::fill(top_dc.begin(), top_dc.end(), 0);
+    for (int my = 0; my < mb_h; ++my) {
+      uint32_t left_nz = 0;
+      uint8_t left_dc = 0;
+      for (int mx = 0; mx < mb_w; ++mx) {
+        const int idx = my * mb_w + mx;
+        const MBView m = idx < cut ? MBView{mb_hdr + (size_t)idx * 48, mb_coeffs + (size_t)idx * 400} : MBView{zero_hdr, zero_coeffs};
+        if (m.skip()) {
+          top_nz[mx] = 0; left_nz = 0;
+          if (m.mb_type() == 0) { top_dc[mx] = 0; left_dc = 0; }
+          continue;
+        }
+        walk_mb(m, &top_nz[mx], &left_nz, &top_dc[mx], &left_dc,
+                [&](const int16_t* c, int nz, int type, int first, int ctx) { stat_block(c, nz, type, first, ctx > 2 ? 2 : ctx, st); });
+      }
+    }
+  };
+  int max_count = total >> 3;
+  if (max_count < 96) max_count = 96;
+  // statLoop (encode.go:1405-1437)
+  const int n_pass = passes < 1 ? 1 : (passes > 10 ? 10 : passes);
+  for (int pass = 0; pass < n_pass; ++pass) {
+    int refresh_cnt = max_count;
+    for (int idx = 0; idx < total; ++idx)
+      if (--refresh_cnt < 0) { collect(pass == 0 ? idx : total); optimize_proba_host(st, proba); refresh_cnt = max_count; }
+    collect(total);
+    if (optimize_proba_host(st, proba) == 0) break;
+  }
+  // main pass: tokens recorded inline with the probabilities of the moment (encode_frame.go:52-92)
+  struct TokSink {
+    std::vector<uint16_t>* v;
+    void put(int bit, int prob) { v->push_back((uint16_t)((bit & 1) | (prob << 8))); }
+  };
+  std::vector<uint16_t> toks;
+  toks.reserve((size_t)total * 64);
+  std::vector<size_t> start((size_t)total + 1, 0);
+  auto record_all = [&](bool with_refresh) {
+    toks.clear();
+    TokSink sink{&toks};
+    std::vector<uint32_t> tnz(mb_w, 0u);
+    std::vector<uint8_t> tdc(mb_w, 0);
+    int refresh_cnt = max_count;
+    for (int my = 0; my < mb_h; ++my) {
+      uint32_t left_nz = 0;
+      uint8_t left_dc = 0;
+      for (int mx = 0; mx < mb_w; ++mx) {
+        const int idx = my * mb_w + mx;
+        if (with_refresh && --refresh_cnt < 0) { collect(total); optimize_proba_host(st, proba); refresh_cnt = max_count; }
+        const MBView m{mb_hdr + (size_t)idx * 48, mb_coeffs + (size_t)idx * 400};
+        if (m.skip()) {
+          tnz[mx] = 0; left_nz = 0;
+          if (m.mb_type() == 0) { tdc[mx] = 0; left_dc = 0; }
+          continue;
+        }
+        start[idx] = toks.size();
+        walk_mb(m, &tnz[mx], &left_nz, &tdc[mx], &left_dc,
+                [&](const int16_t* c, int nz, int type, int first, int ctx) { code_block(sink, proba[type], c, nz, first, ctx > 2 ? 2 : ctx); });
+      }
+    }
+  };
+  record_all(true);
+  const int num_skip = count_skips(mb_hdr, total);
+  const int skip_proba = num_skip > 0 ? (total - num_skip) * 255 / total : 0;
+  collect(total);
+  if (optimize_proba_host(st, proba) > 0) record_all(false);  // rerecordAllTokens (encode_proba.go:317)
+  start[total] = toks.size();
+  std::vector<uint8_t> part0;
+  part0.reserve((size_t)total * 4 + 2048);
+  emit_partition0(fp, mb_hdr, segment_map, &proba[0][0][0][0], num_skip, skip_proba, &part0);
+  const size_t hdr_pos = riff->size();
+  riff->resize(hdr_pos + 20 + 10);
+  riff->insert(riff->end(), part0.begin(), part0.end());
+  const int np = fp.num_parts < 1 ? 1 : fp.num_parts;
+  std::vector<std::vector<uint8_t>> parts(np);
+  for (int pi = 0; pi < np; ++pi) {
+    BoolEnc bw(&parts[pi]);
+    if (np == 1) {
+      for (size_t t = 0; t < toks.size(); ++t) bw.put(toks[t] & 1, toks[t] >> 8);
+    } else {  // EmitTokensPartitioned with the reference's per-MB start table (encode_token.go:322-361)
+      for (int idx = 0; idx < total; ++idx) {
+        if (((idx / mb_w) & (np - 1)) != pi) continue;
+        for (size_t t = start[idx]; t < start[idx + 1]; ++t) bw.put(toks[t] & 1, toks[t] >> 8);
+      }
+    }
+    bw.finish();
+  }
+  for (int pi = 0; pi + 1 < np; ++pi) {
+    const size_t sz = parts[pi].size();
+    riff->push_back((uint8_t)sz); riff->push_back((uint8_t)(sz >> 8)); riff->push_back((uint8_t)(sz >> 16));
+  }
+  for (int pi = 0; pi < np; ++pi) riff->insert(riff->end(), parts[pi].begin(), parts[pi].end());
   finish_riff(fp, hdr_pos, part0.size(), riff);
 }
 

@@ -78,7 +78,7 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens;
   PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false;
@@ -118,7 +118,7 @@ extern "C" {
 void wgpu_enc_options_default(wgpu_enc_options* o, int quality) {
   // DefaultOptions (encode.go:196-214) mapped onto lossy.EncodeConfig (internal/lossy/encode.go:66-86)
   o->quality = quality; o->method = 4; o->sns_strength = 50; o->filter_strength = 60; o->filter_sharpness = 0;
-  o->filter_type = 1; o->partitions = 0; o->segments = 4; o->preprocessing = 0; o->has_alpha = 0;
+  o->filter_type = 1; o->partitions = 0; o->segments = 4; o->preprocessing = 0; o->has_alpha = 0; o->passes = 1;
 }
 
 static int upload_table(wgpu_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
@@ -192,7 +192,7 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens,
+  DevBuf* db[] = {&ctx->ctxw2, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
@@ -248,8 +248,10 @@ static int validate_enc_options(wgpu_ctx* ctx, const wgpu_enc_options* o, int wi
   if (o->segments < 1 || o->segments > 4) FAIL(WGPU_ERR_INVALID, "webp: segments out of range [1, 4]");
   // The GPU path restates the reference's row-parallel encoder (internal/lossy/encode.go:1356):
   // Method >= 3, mbH >= 4, single pass.  The serial-path configurations are a later row of the scope table.
-  if (o->method < 3) FAIL(WGPU_ERR_UNSUPPORTED, "method < 3 takes the reference's serial path (not built yet)");
-  if (((height + 15) >> 4) < 4) FAIL(WGPU_ERR_UNSUPPORTED, "height <= 48 takes the reference's serial path (not built yet)");
+  if (o->passes < 0 || o->passes > 10) FAIL(WGPU_ERR_INVALID, "webp: invalid Pass (must be 1-10 or 0 for default)");
+  // Method < 3: statLoop + serial encodeFrame semantics (non-RD decisions) -- built.  Method >= 3 on frames of fewer than
+  // 4 macroblock rows takes the reference's serial RD path (probability refreshes feed the RD costs) -- not built yet.
+  if (o->method >= 3 && ((height + 15) >> 4) < 4) FAIL(WGPU_ERR_UNSUPPORTED, "Method >= 3 with height <= 48 takes the reference's serial RD path (not built yet)");
   return WGPU_OK;
 }
 
@@ -299,6 +301,25 @@ int launch_enc_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
     const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
     const unsigned grid = (unsigned)((tasks + per_cta - 1) / per_cta);
     wg::encode_wave_kernel<G, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(P, w);
+    ctx->launches++;
+  }
+  return WGPU_OK;
+}
+template <int G, int WARPS, int MINB>
+int launch_enc_fast_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {  // Method < 3: non-RD body, same wave schedule
+  constexpr int per_cta = WARPS * (32 / G);
+  constexpr size_t smem = sizeof(wg::MBShared) * per_cta;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wg::encode_fast_wave_kernel<G, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int waves = P.mb_w + 2 * (P.mb_h - 1);
+  for (int w = 0; w < waves; ++w) {
+    const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
+    const unsigned grid = (unsigned)((tasks + per_cta - 1) / per_cta);
+    wg::encode_fast_wave_kernel<G, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(P, w);
     ctx->launches++;
   }
   return WGPU_OK;
@@ -392,6 +413,7 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.segment = ctx->segment.as<uint8_t>(); P.img = ctx->img_params.as<wg::ImageParams>();
   P.stats = ctx->stats.as<unsigned int>();
   CK(cudaMemsetAsync(ctx->stats.p, 0, (size_t)n * wg::STATS_SIZE * 4, ctx->stream));
+  P.ctx2 = ctx->ctxw2.as<uint32_t>();
   P.ctx = ctx->ctxw.as<uint32_t>(); P.out_hdr = ctx->hdr.as<uint8_t>(); P.out_coeffs = ctx->coeffs.as<int16_t>();
   P.i4_costs = ctx->t_i4cost.as<uint16_t>(); P.lc = ctx->t_lc.as<uint16_t>(); P.eob = ctx->t_eob.as<uint16_t>(); P.lfc = ctx->t_lfc.as<uint16_t>();
   P.n_images = n; P.width = ctx->e_w; P.height = ctx->e_h; P.mb_w = mbw; P.mb_h = mbh;
@@ -399,6 +421,12 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.max_i4_modes = ctx->e_opt.quality < 50 ? 2 : 3;  // getMaxI4RDModes (encode_parallel.go:931)
   P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
   int rc;
+  if (ctx->e_opt.method < 3) {
+    rc = launch_enc_fast_waves<8, 4, 3>(ctx, P);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return WGPU_OK;
+  }
   switch (enc_variant()) {
     case 1: rc = launch_enc_waves<8, 4, 2>(ctx, P); break;   // no register cap, 2 CTAs/SM
     case 2: rc = launch_enc_persistent<8, 4, 3>(ctx, P); break;  // one persistent launch, dataflow scheduling
@@ -415,7 +443,7 @@ static int enc_reserve(wgpu_ctx* ctx) {
   RESERVE(ctx->ry, n * nmb * 256); RESERVE(ctx->ru, n * nmb * 64); RESERVE(ctx->rv, n * nmb * 64);
   RESERVE(ctx->alpha, n * nmb); RESERVE(ctx->uv_alpha, n * nmb); RESERVE(ctx->segment, n * nmb);
   RESERVE(ctx->img_params, n * sizeof(wg::ImageParams));
-  RESERVE(ctx->ctxw, n * nmb * 4); RESERVE(ctx->hdr, n * nmb * 48); RESERVE(ctx->coeffs, n * nmb * 800);
+  RESERVE(ctx->ctxw, n * nmb * 4); RESERVE(ctx->ctxw2, n * nmb * 4); RESERVE(ctx->hdr, n * nmb * 48); RESERVE(ctx->coeffs, n * nmb * 800);
   RESERVE(ctx->stats, n * wg::STATS_SIZE * 4); RESERVE(ctx->h_stats, n * wg::STATS_SIZE * 4);
   RESERVE(ctx->proba, n * 1056); RESERVE(ctx->h_proba, n * 1056);
   RESERVE(ctx->mb_tokens, n * nmb * 4); RESERVE(ctx->mb_offset, n * nmb * 8);
@@ -477,7 +505,7 @@ static int enc_search_locked(wgpu_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->img_params.p, ctx->h_params.p, (size_t)n * sizeof(wg::ImageParams), cudaMemcpyHostToDevice, ctx->stream));
   int rc = enc_launch_waves(ctx);
   if (rc) return rc;
-  if (ctx->e_opt.partitions == 0 && (rc = enc_launch_token_prepass(ctx))) return rc;
+  if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3 && (rc = enc_launch_token_prepass(ctx))) return rc;
   ctx->e_done = true;
   return WGPU_OK;
 }
@@ -587,7 +615,7 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
   RESERVE(ctx->h_hdr, n * nmb * 48);
   std::atomic<int> too_small(0);
   const double t0 = now_ms();
-  if (ctx->e_opt.partitions == 0) {
+  if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3) {
     // ---- single partition: tokens are generated on the GPU, the host only boolean-codes flat arrays
     CK(cudaStreamSynchronize(ctx->stream));  // waves + token pre-pass done, per-image totals on the host
     const double t1 = now_ms();
@@ -637,7 +665,7 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, token emit + D2H %.2f ms (%.1f MB tokens), host code %.2f ms (%d threads)\n", t1 - t0,
               t2 - t1, (double)all * 2 / 1e6, now_ms() - t2, threads_of(ctx));
   } else {
-    // ---- multi-partition: levels + statistics come back, the host walks them (reference's partitioned emission)
+    // ---- multi-partition and Method < 3: levels + statistics come back, the host walks them
     RESERVE(ctx->h_coeffs, n * nmb * 800);
     CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_coeffs.p, ctx->coeffs.p, n * nmb * 800, cudaMemcpyDeviceToHost, ctx->stream));
@@ -647,8 +675,12 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     parallel_for((int)n, threads_of(ctx), [&](int i) {
       std::vector<uint8_t> riff;
       riff.reserve(nmb * 64 + 4096);
-      wgh::serialize_frame(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
-                           ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, ctx->h_stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE, &riff);
+      if (ctx->e_opt.method < 3)  // serial-path semantics: probability refreshes + inline token recording restated on the host
+        wgh::serialize_frame_serial(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
+                                    ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, ctx->e_opt.passes, &riff);
+      else
+        wgh::serialize_frame(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
+                             ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, ctx->h_stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE, &riff);
       out_sizes[i] = riff.size();
       if (riff.size() > out_stride) { too_small.store(1); return; }
       memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());

@@ -130,7 +130,7 @@ def validateConfig(o):
 def lossy_config(o, has_alpha=False):
     """EncoderOptions -> lossy.EncodeConfig (encode.go:478-528 over lossy.DefaultConfig, internal/lossy/encode.go:66-86)."""
     c = native.EncOptions(quality=int(o.Quality), method=o.Method, sns_strength=50, filter_strength=60, filter_sharpness=0,
-                          filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=int(has_alpha))
+                          filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=int(has_alpha), passes=1)
     if o.SNSStrength >= 0:
         c.sns_strength = o.SNSStrength
     if o.FilterStrength >= 0:
@@ -142,6 +142,8 @@ def lossy_config(o, has_alpha=False):
     if o.Segments > 0:
         c.segments = o.Segments
     c.preprocessing = o.Preprocessing
+    if o.Pass > 0:
+        c.passes = o.Pass
     return c
 
 
@@ -158,8 +160,8 @@ def _unsupported(o):
         return "webp: TargetSize/TargetPSNR take the reference's serial multi-pass path (not built yet)"
     if o.Preprocessing & 2:
         return "webp: dithered import (Preprocessing&2) is not built yet"
-    if (o.Pass if o.Pass > 0 else 1) > 1:
-        return "webp: Pass > 1 takes the reference's serial path (not built yet)"
+    if (o.Pass if o.Pass > 0 else 1) > 1 and o.Method >= 3:
+        return "webp: Pass > 1 with Method >= 3 only matters with TargetSize/TargetPSNR (serial RD path, not built yet)"
     if o.ICC or o.EXIF or o.XMP:
         return "webp: metadata chunks (VP8X container) are host-side container work outside this path"
     return None
