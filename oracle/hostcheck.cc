@@ -48,7 +48,7 @@ long hostcheck_serialize(const uint8_t* rgba, int stride, int w, int h, const Or
   const auto t0 = std::chrono::steady_clock::now();
   for (int r = 0; r < (reps > 0 ? reps : 1); ++r) {
     riff.clear();
-    if (o.method < 3) wgh::serialize_frame_serial(fp, hdr.data(), coeffs.data(), segmap.data(), e.pass, &riff);
+    if (o.method < 3) wgh::serialize_frame_serial(fp, hdr.data(), coeffs.data(), segmap.data(), stats.data(), e.pass, &riff);
     else wgh::serialize_frame(fp, hdr.data(), coeffs.data(), segmap.data(), stats.data(), &riff);
   }
   *ms_per_rep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / (reps > 0 ? reps : 1);

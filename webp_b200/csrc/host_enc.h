@@ -762,51 +762,64 @@ static inline int optimize_proba_host(const Stats st, uint8_t proba[4][8][3][11]
 
 // Serial-path serialiser (Method < 3: statLoop + encodeFrame, encode.go:1334-1400, encode_frame.go:15-108).  The GPU's
 // mode decisions on this path do not depend on the coefficient probabilities, so one device pass gives the content
-// of mbInfo for every reference pass; what the host restates is the evolution of enc.proba through the mid-stream
-// refreshes -- in the first statLoop pass the statistics cover the macroblocks encoded so far plus ZERO-STATE entries
-// for the rest (collectAllStats walks the whole array, encode_proba.go:171) -- and the inline token recording.
+// of mbInfo for every reference pass; what the host restates is the evolution of enc.proba:
+//   * statLoop pass 0 refreshes the probabilities before macroblocks M, 2M+1, 3M+2, ... (M = max(total >> 3, 96),
+//     encode_frame.go:35-57) from statistics over the WHOLE mbInfo array (collectAllStats, encode_proba.go:171): the
+//     macroblocks encoded so far plus ZERO-STATE entries (non-skipped I16, all levels zero) for the rest;
+//   * every later refresh / end-of-pass optimisation / the final one sees the complete frame.  optimizeProba compares
+//     against CoeffsProba0 and only sets entries, so with identical statistics it is idempotent: all of those collapse
+//     into one application of the full-frame statistics (which the GPU already accumulated), and the tokens recorded
+//     inline in the main pass equal the ones a re-recording would produce.
+// tests/test_oracle.py::test_host_serialisers_reproduce_oracle_bytes checks this against the literal multi-pass oracle.
 static inline void serialize_frame_serial(const FramePlan& fp, const uint8_t* mb_hdr, const int16_t* mb_coeffs, const uint8_t* segment_map,
-                                          int passes, std::vector<uint8_t>* riff) {
+                                          const uint32_t* full_stats /*[4][8][3][11][2] from the GPU*/, int passes, std::vector<uint8_t>* riff) {
+  (void)passes;  // Pass only repeats idempotent work on this path (see above)
   const int mb_w = fp.mb_w, mb_h = fp.mb_h, total = mb_w * mb_h;
   uint8_t proba[4][8][3][11];
   memcpy(proba, kCoeffsProba0, sizeof(proba));
-  static thread_local Stats st;
+  static thread_local Stats pre, st;
   static const uint8_t zero_hdr[48] = {0};
   static const int16_t zero_coeffs[400] = {0};
-  std::vector<uint32_t> top_nz(mb_w);
-  std::vector<uint8_t> top_dc(mb_w);
-  auto collect = [&](int cut) {  // collectAllStats with macroblocks >= cut still in their zero state
-    memset(st, 0, sizeof(st));
-    std::fill(top_nz.begin(), top_nz.end(), 0u);
-    std::fill(top_dc.begin(), top_dc.end(), 0);
-    for (int my = 0; my < mb_h; ++my) {
-      uint32_t left_nz = 0;
-      uint8_t left_dc = 0;
-      for (int mx = 0; mx < mb_w; ++mx) {
-        const int idx = my * mb_w + mx;
-        const MBView m = idx < cut ? MBView{mb_hdr + (size_t)idx * 48, mb_coeffs + (size_t)idx * 400} : MBView{zero_hdr, zero_coeffs};
-        if (m.skip()) {
-          top_nz[mx] = 0; left_nz = 0;
-          if (m.mb_type() == 0) { top_dc[mx] = 0; left_dc = 0; }
-          continue;
-        }
-        walk_mb(m, &top_nz[mx], &left_nz, &top_dc[mx], &left_dc,
-                [&](const int16_t* c, int nz, int type, int first, int ctx) { stat_block(c, nz, type, first, ctx > 2 ? 2 : ctx, st); });
-      }
-    }
-  };
   int max_count = total >> 3;
   if (max_count < 96) max_count = 96;
-  // statLoop (encode.go:1405-1437)
-  const int n_pass = passes < 1 ? 1 : (passes > 10 ? 10 : passes);
-  for (int pass = 0; pass < n_pass; ++pass) {
+  {  // statLoop pass 0: prefix statistics over the real macroblocks, zero-state tail added at every refresh point
+    memset(pre, 0, sizeof(pre));
+    std::vector<uint32_t> tnz(mb_w, 0u), tnz2(mb_w);
+    std::vector<uint8_t> tdc(mb_w, 0), tdc2(mb_w);
+    uint32_t left_nz = 0;
+    uint8_t left_dc = 0;
     int refresh_cnt = max_count;
-    for (int idx = 0; idx < total; ++idx)
-      if (--refresh_cnt < 0) { collect(pass == 0 ? idx : total); optimize_proba_host(st, proba); refresh_cnt = max_count; }
-    collect(total);
-    if (optimize_proba_host(st, proba) == 0) break;
+    for (int idx = 0; idx < total; ++idx) {
+      const int my = idx / mb_w, mx = idx - my * mb_w;
+      if (mx == 0) { left_nz = 0; left_dc = 0; }
+      if (--refresh_cnt < 0) {
+        memcpy(st, pre, sizeof(st));
+        tnz2 = tnz; tdc2 = tdc;
+        uint32_t l2 = left_nz;
+        uint8_t ld2 = left_dc;
+        const MBView z{zero_hdr, zero_coeffs};
+        for (int j = idx; j < total; ++j) {
+          const int jx = j % mb_w;
+          if (jx == 0) { l2 = 0; ld2 = 0; }
+          walk_mb(z, &tnz2[jx], &l2, &tdc2[jx], &ld2,
+                  [&](const int16_t* c, int nz, int type, int first, int ctx) { stat_block(c, nz, type, first, ctx > 2 ? 2 : ctx, st); });
+        }
+        optimize_proba_host(st, proba);
+        refresh_cnt = max_count;
+      }
+      const MBView m{mb_hdr + (size_t)idx * 48, mb_coeffs + (size_t)idx * 400};
+      if (m.skip()) {
+        tnz[mx] = 0; left_nz = 0;
+        if (m.mb_type() == 0) { tdc[mx] = 0; left_dc = 0; }
+        continue;
+      }
+      walk_mb(m, &tnz[mx], &left_nz, &tdc[mx], &left_dc,
+              [&](const int16_t* c, int nz, int type, int first, int ctx) { stat_block(c, nz, type, first, ctx > 2 ? 2 : ctx, pre); });
+    }
   }
-  // main pass: tokens recorded inline with the probabilities of the moment (encode_frame.go:52-92)
+  // end of statLoop pass 0 == every later optimisation: the full-frame statistics
+  optimize_proba_host(*reinterpret_cast<const Stats*>(full_stats), proba);
+  // main pass: tokens with the (now stable) probabilities
   struct TokSink {
     std::vector<uint16_t>* v;
     void put(int bit, int prob) { v->push_back((uint16_t)((bit & 1) | (prob << 8))); }
@@ -814,18 +827,15 @@ static inline void serialize_frame_serial(const FramePlan& fp, const uint8_t* mb
   std::vector<uint16_t> toks;
   toks.reserve((size_t)total * 64);
   std::vector<size_t> start((size_t)total + 1, 0);
-  auto record_all = [&](bool with_refresh) {
-    toks.clear();
+  {
     TokSink sink{&toks};
     std::vector<uint32_t> tnz(mb_w, 0u);
     std::vector<uint8_t> tdc(mb_w, 0);
-    int refresh_cnt = max_count;
     for (int my = 0; my < mb_h; ++my) {
       uint32_t left_nz = 0;
       uint8_t left_dc = 0;
       for (int mx = 0; mx < mb_w; ++mx) {
         const int idx = my * mb_w + mx;
-        if (with_refresh && --refresh_cnt < 0) { collect(total); optimize_proba_host(st, proba); refresh_cnt = max_count; }
         const MBView m{mb_hdr + (size_t)idx * 48, mb_coeffs + (size_t)idx * 400};
         if (m.skip()) {
           tnz[mx] = 0; left_nz = 0;
@@ -837,12 +847,9 @@ static inline void serialize_frame_serial(const FramePlan& fp, const uint8_t* mb
                 [&](const int16_t* c, int nz, int type, int first, int ctx) { code_block(sink, proba[type], c, nz, first, ctx > 2 ? 2 : ctx); });
       }
     }
-  };
-  record_all(true);
+  }
   const int num_skip = count_skips(mb_hdr, total);
   const int skip_proba = num_skip > 0 ? (total - num_skip) * 255 / total : 0;
-  collect(total);
-  if (optimize_proba_host(st, proba) > 0) record_all(false);  // rerecordAllTokens (encode_proba.go:317)
   start[total] = toks.size();
   std::vector<uint8_t> part0;
   part0.reserve((size_t)total * 4 + 2048);

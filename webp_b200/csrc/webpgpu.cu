@@ -677,7 +677,8 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       riff.reserve(nmb * 64 + 4096);
       if (ctx->e_opt.method < 3)  // serial-path semantics: probability refreshes + inline token recording restated on the host
         wgh::serialize_frame_serial(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
-                                    ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, ctx->e_opt.passes, &riff);
+                                    ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, ctx->h_stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE,
+                                    ctx->e_opt.passes, &riff);
       else
         wgh::serialize_frame(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
                              ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, ctx->h_stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE, &riff);
