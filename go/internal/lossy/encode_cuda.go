@@ -24,7 +24,19 @@ func cudaOptions(cfg *EncodeConfig) C.wgpu_enc_options {
 		filter_strength: C.int(cfg.FilterStrength), filter_sharpness: C.int(cfg.FilterSharpness),
 		filter_type: C.int(cfg.FilterType), partitions: C.int(cfg.Partitions), segments: C.int(cfg.Segments),
 		preprocessing: C.int(cfg.Preprocessing), has_alpha: C.int(cfg.HasAlpha),
+		passes: C.int(cfg.Pass), dither_amp: C.int(ditherAmp(cfg.Dithering)),
 	}
+}
+
+// ditherAmp mirrors dsp.InitRandom (internal/dsp/random.go:39-50): amp = int(256 * dithering), clamped to [0, 256].
+func ditherAmp(d float32) int {
+	if d <= 0 {
+		return 0
+	}
+	if d > 1 {
+		return 256
+	}
+	return int(float32(256) * d)
 }
 
 func cudaSegQuant(q *SegmentQuant) C.wgpu_seg_quant {

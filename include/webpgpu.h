@@ -54,6 +54,7 @@ typedef struct {
   int preprocessing;    /* bit0: segment smoothing */
   int has_alpha;        /* 0: opaque input (alpha bytes ignored) */
   int passes;           /* EncodeConfig.Pass, 1..10 (statLoop iterations on the Method < 3 path); 0 = 1 */
+  int dither_amp;       /* VP8Random.amp = int(256 * EncodeConfig.Dithering), 0..256 (encode.go:563-567, dsp/random.go:39); 0 = off */
 } wgpu_enc_options;
 
 void wgpu_enc_options_default(wgpu_enc_options* o, int quality);
@@ -135,6 +136,7 @@ int wgpu_dec_device(wgpu_ctx* ctx, int want_nrgba);
 int wgpu_dec_fetch(wgpu_ctx* ctx, uint8_t* y, uint8_t* u, uint8_t* v, size_t y_plane_stride, size_t uv_plane_stride,
                    uint8_t* nrgba, size_t nrgba_image_stride);
 
+/* wgpu_import_rgba: has_alpha bit 0 = alpha-weighted chroma, bits 8..16 = dithering amplitude (0 = fixed rounding). */
 /* ---- stage-level entry points (host buffers in/out) ------------------------------------ */
 int wgpu_import_rgba(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int height, int stride,
                      size_t image_stride, int has_alpha, uint8_t* y, uint8_t* u, uint8_t* v);

@@ -13,7 +13,7 @@ extern "C" {
 // ---- whole-codec -------------------------------------------------------------------------
 struct OrcEncCfg {
   int quality, method, sns_strength, filter_strength, filter_sharpness, filter_type, partitions, segments,
-      preprocessing, has_alpha, passes;
+      preprocessing, has_alpha, passes, dither_amp;
 };
 static EncodeConfig to_cfg(const OrcEncCfg* c) {
   EncodeConfig e;
@@ -22,6 +22,7 @@ static EncodeConfig to_cfg(const OrcEncCfg* c) {
   e.filter_type = c->filter_type; e.partitions = c->partitions; e.segments = c->segments;
   e.preprocessing = c->preprocessing;
   e.pass = c->passes > 0 ? c->passes : 1;
+  e.dither_amp = c->dither_amp;
   return e;
 }
 // Encode one RGBA image (parallel-path semantics).  Returns RIFF size or <0 (-1 unsupported
@@ -159,6 +160,8 @@ int orc_decode(const uint8_t* data, long len, int filter, uint8_t* y, uint8_t* u
 void orc_import_rgba(const uint8_t* rgba, int stride, int w, int h, int has_alpha, uint8_t* y, uint8_t* u, uint8_t* v) {
   Encoder* enc = new Encoder();
   EncodeConfig c;
+  c.dither_amp = has_alpha >> 8;  // bits 8.. carry the dithering amplitude for tests
+  has_alpha &= 0xff;
   enc->cfg = c; enc->width = w; enc->height = h; enc->mb_w = (w + 15) >> 4; enc->mb_h = (h + 15) >> 4;
   enc->y_stride = enc->mb_w * 16; enc->uv_stride = enc->mb_w * 8;
   enc->y_plane.assign((size_t)enc->y_stride * enc->mb_h * 16, 0);

@@ -79,6 +79,7 @@ struct BoolWriter {
 struct EncodeConfig {  // internal/lossy/encode.go:46-86 (DefaultConfig)
   int quality = 75, method = 4, sns_strength = 50, filter_strength = 60, filter_sharpness = 0;
   int filter_type = 1, partitions = 0, segments = 4, pass = 1, preprocessing = 0;
+  int dither_amp = 0;  // VP8Random.amp = int(256 * Dithering) (dsp/random.go:39-50); 0 == no dithering
 };
 struct SegmentQuant {  // encode.go:311-323
   int quant, iquant, bias, dc_quant, dc_iquant, dc_bias;
@@ -388,12 +389,37 @@ struct Encoder {
     mb_start.assign((size_t)mb_w * mb_h + 1, 0);
   }
 
+  // VP8Random (internal/dsp/random.go:17-79): subtractive generator over a 55-entry table, lags 55 / 24
+  struct Random {
+    uint32_t tab[55];
+    int i1 = 0, i2 = 31, amp = 0;
+    explicit Random(int a) : amp(a) { memcpy(tab, kRandomTable, sizeof(tab)); }
+    int bits(int num_bits) {
+      int64_t diff = (int64_t)tab[i1] - (int64_t)tab[i2];
+      if (diff < 0) diff += (int64_t)1 << 31;
+      tab[i1] = (uint32_t)diff;
+      if (++i1 == 55) i1 = 0;
+      if (++i2 == 55) i2 = 0;
+      int d = (int)((int32_t)((uint32_t)diff << 1) >> (32 - num_bits));
+      d = (d * amp) >> 8;
+      return d + (1 << (num_bits - 1));
+    }
+  };
   void import_image(const uint8_t* pix, int stride, int has_alpha) {
     const int w = width, h = height, pad_w = mb_w * 16, pad_h = mb_h * 16;
+    Random rg(cfg.dither_amp);
+    const bool dither = cfg.dither_amp > 0;  // amp 0 gives the fixed rounding back, so "Dithering > 0 but amp == 0" is the same
     for (int y = 0; y < pad_h; ++y) {  // encode.go:757-792
       const int sy = y >= h ? h - 1 : y;
       const uint8_t* row = pix + (size_t)sy * stride;
       uint8_t* dst = &y_plane[(size_t)y * y_stride];
+      if (dither) {  // serial dithered branch (encode.go:793-809): every padded pixel draws its own random rounding
+        for (int x = 0; x < pad_w; ++x) {
+          const int sx = x >= w ? w - 1 : x;
+          dst[x] = (uint8_t)((16839 * row[4 * sx] + 33059 * row[4 * sx + 1] + 6420 * row[4 * sx + 2] + rg.bits(16) + (16 << 16)) >> 16);
+        }
+        continue;
+      }
       for (int x = 0; x < w; ++x) dst[x] = rgb_to_y(row[4 * x], row[4 * x + 1], row[4 * x + 2]);
       for (int x = w; x < pad_w; ++x) dst[x] = dst[w - 1];
     }
@@ -436,8 +462,11 @@ struct Encoder {
         }
         // AccumulateRGBA stores uint16 (yuv.go:516)
         rv = (uint16_t)rv; gv = (uint16_t)gv; bv = (uint16_t)bv;
-        u_plane[(size_t)y * uv_stride + i] = rgb_to_u(rv, gv, bv, 1 << 17);
-        v_plane[(size_t)y * uv_stride + i] = rgb_to_v(rv, gv, bv, 1 << 17);
+        // ConvertRGBA32ToUV / ...Dithered (yuv.go:553-576): U draws before V
+        const int ru = dither ? rg.bits(18) : (1 << 17);
+        u_plane[(size_t)y * uv_stride + i] = rgb_to_u(rv, gv, bv, ru);
+        const int rvv = dither ? rg.bits(18) : (1 << 17);
+        v_plane[(size_t)y * uv_stride + i] = rgb_to_v(rv, gv, bv, rvv);
       }
     }
     src_y = y_plane; src_u = u_plane; src_v = v_plane;

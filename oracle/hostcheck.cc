@@ -7,7 +7,7 @@
 
 extern "C" {
 struct OrcEncCfg2 {
-  int quality, method, sns_strength, filter_strength, filter_sharpness, filter_type, partitions, segments, preprocessing, has_alpha, passes;
+  int quality, method, sns_strength, filter_strength, filter_sharpness, filter_type, partitions, segments, preprocessing, has_alpha, passes, dither_amp;
 };
 // Returns the RIFF size produced by the product serialiser (out receives it) or <0; *same = 1 when it equals the
 // oracle's bytes; *ms_per_rep = serialiser time per repetition.
@@ -18,6 +18,7 @@ long hostcheck_serialize(const uint8_t* rgba, int stride, int w, int h, const Or
   e.filter_sharpness = c->filter_sharpness; e.filter_type = c->filter_type; e.partitions = c->partitions; e.segments = c->segments;
   e.preprocessing = c->preprocessing;
   e.pass = c->passes > 0 ? c->passes : 1;
+  e.dither_amp = c->dither_amp;
   orc::Encoder* enc = new orc::Encoder();
   enc->init(rgba, stride, w, h, e, c->has_alpha);
   std::vector<uint8_t> ref = orc::riff_wrap(enc->encode_frame());

@@ -15,13 +15,13 @@ _LIB = None
 class OrcEncCfg(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "quality", "method", "sns_strength", "filter_strength", "filter_sharpness", "filter_type",
-        "partitions", "segments", "preprocessing", "has_alpha", "passes")]
+        "partitions", "segments", "preprocessing", "has_alpha", "passes", "dither_amp")]
 
 
 def default_cfg(quality=75, method=4, **kw):
     """lossy.DefaultConfig (internal/lossy/encode.go:66) + EncoderOptions mapping (encode.go:478-528)."""
     c = OrcEncCfg(quality=quality, method=method, sns_strength=50, filter_strength=60, filter_sharpness=0,
-                  filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=0, passes=1)
+                  filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=0, passes=1, dither_amp=0)
     for k, v in kw.items():
         setattr(c, k, v)
     return c
@@ -118,14 +118,14 @@ def decode(data, filter=True, taps=False, libwebp_inner_rule=False):
     return (w, h, y, u, v, t) if taps else (w, h, y, u, v)
 
 
-def import_rgba(rgba, has_alpha=False):
+def import_rgba(rgba, has_alpha=False, dither_amp=0):
     rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
     h, w = rgba.shape[:2]
     mbw, mbh = (w + 15) >> 4, (h + 15) >> 4
     y = np.zeros((mbh * 16, mbw * 16), np.uint8)
     u = np.zeros((mbh * 8, mbw * 8), np.uint8)
     v = np.zeros((mbh * 8, mbw * 8), np.uint8)
-    lib().orc_import_rgba(_p(rgba), C.c_int(rgba.strides[0]), w, h, int(has_alpha), _p(y), _p(u), _p(v))
+    lib().orc_import_rgba(_p(rgba), C.c_int(rgba.strides[0]), w, h, int(has_alpha) | (int(dither_amp) << 8), _p(y), _p(u), _p(v))
     return y, u, v
 
 

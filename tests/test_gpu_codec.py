@@ -60,6 +60,16 @@ def test_import_rgba(oracle, gpu_ctx, w, h, has_alpha):
         assert np.array_equal(y[i], ey) and np.array_equal(u[i], eu) and np.array_equal(v[i], ev)
 
 
+def test_import_rgba_dithered(oracle, gpu_ctx):
+    # Preprocessing&2: VP8Random rounding terms in the reference's draw order (encode.go:793-809,925-936; dsp/random.go)
+    for (w, h, amp) in [(100, 70, 200), (64, 64, 256), (130, 71, 37)]:
+        imgs = np.stack([oracle.synth_image(w, h, i) for i in range(2)])
+        y, u, v = dsp.ImportRGBA(imgs, False, gpu_ctx, dither_amp=amp)
+        for i in range(2):
+            ey, eu, ev = oracle.import_rgba(imgs[i], False, dither_amp=amp)
+            assert np.array_equal(y[i], ey) and np.array_equal(u[i], eu) and np.array_equal(v[i], ev)
+
+
 ENC_CASES = [
     (128, 96, [0, 1, 2], {}),
     (100, 70, [1, 2], {}),
@@ -81,6 +91,8 @@ ENC_CASES = [
     (16, 16, [2], dict(Method=2, Quality=90)),
     (130, 71, [2], dict(Method=2, Partitions=1, Quality=90)),
     (320, 240, [2], dict(Method=2, Pass=3, Quality=60)),
+    (128, 96, [1, 2], dict(Preprocessing=2, Quality=60)),  # dithered import (PresetPhoto sets this bit)
+    (128, 96, [1], dict(Preprocessing=3, Quality=90, Method=2)),
 ]
 
 

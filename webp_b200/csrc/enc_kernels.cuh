@@ -1086,10 +1086,15 @@ struct ImportParams {
   uint8_t* y; uint8_t* u; uint8_t* v; size_t y_plane, uv_plane;
   const uint16_t* gamma_to_linear;  // [256]  (yuv.go:193)
   const uint16_t* linear_to_gamma;  // [34]   (yuv.go:205)
+  // dithering (Preprocessing&2): the reference seeds VP8Random identically for every image and draws in a fixed order
+  // (all padded luma samples in raster order, then U,V per chroma sample), so the rounding terms depend only on the
+  // padded size and the amplitude: one host-built table per batch, shared by all images.  null = fixed rounding.
+  const uint16_t* dither_y;   // [pad_h][pad_w]      RandomBits(rg, 16)
+  const uint32_t* dither_uv;  // [pad_h/2][pad_w/2][2] RandomBits(rg, 18) for U then V
 };
 __device__ __forceinline__ int rgb_to_y(int r, int g, int b) { return (16839 * r + 33059 * g + 6420 * b + (1 << 15) + (16 << 16)) >> 16; }
-__device__ __forceinline__ int clip_uv(int uv) {  // VP8ClipUV with rounding = 1<<17 (yuv.go:138)
-  uv = (uv + (1 << 17) + (128 << 18)) >> 18;
+__device__ __forceinline__ int clip_uv(int uv, int rounding) {  // VP8ClipUV (yuv.go:138); rounding = 1<<17 unless dithering
+  uv = (uv + rounding + (128 << 18)) >> 18;
   return min(max(uv, 0), 255);
 }
 __device__ __forceinline__ int lin2gamma(uint32_t v, const uint16_t* l2g) {  // yuv.go:237, shift 0
@@ -1132,7 +1137,14 @@ __global__ void __launch_bounds__(256) import_rgba_kernel(const ImportParams P) 
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t p = px[r][i];
-        w |= (uint32_t)rgb_to_y(p & 0xff, (p >> 8) & 0xff, (p >> 16) & 0xff) << (8 * i);
+        int yv;
+        if (P.dither_y) {  // RGBToYRounding (yuv.go:159)
+          const int rnd = P.dither_y[(size_t)(y0 + r) * P.pad_w + x0 + i];
+          yv = (16839 * (int)(p & 0xff) + 33059 * (int)((p >> 8) & 0xff) + 6420 * (int)((p >> 16) & 0xff) + rnd + (16 << 16)) >> 16;
+        } else {
+          yv = rgb_to_y(p & 0xff, (p >> 8) & 0xff, (p >> 16) & 0xff);
+        }
+        w |= (uint32_t)yv << (8 * i);
       }
       *reinterpret_cast<uint32_t*>(yp + (size_t)(y0 + r) * P.pad_w + x0) = w;
     }
@@ -1157,8 +1169,13 @@ __global__ void __launch_bounds__(256) import_rgba_kernel(const ImportParams P) 
         }
         c[ch] &= 0xffff;
       }
-      uu |= (uint32_t)clip_uv(-9719 * c[0] - 19081 * c[1] + 28800 * c[2]) << (8 * k);
-      vv |= (uint32_t)clip_uv(28800 * c[0] - 24116 * c[1] - 4684 * c[2]) << (8 * k);
+      int ru = 1 << 17, rv = 1 << 17;
+      if (P.dither_uv) {
+        const size_t di = ((size_t)cy * (P.pad_w >> 1) + (x0 >> 1) + k) * 2;
+        ru = (int)P.dither_uv[di]; rv = (int)P.dither_uv[di + 1];
+      }
+      uu |= (uint32_t)clip_uv(-9719 * c[0] - 19081 * c[1] + 28800 * c[2], ru) << (8 * k);
+      vv |= (uint32_t)clip_uv(28800 * c[0] - 24116 * c[1] - 4684 * c[2], rv) << (8 * k);
     }
     const size_t uvo = (size_t)img * P.uv_plane + (size_t)cy * (P.pad_w >> 1) + (x0 >> 1);
     *reinterpret_cast<uint16_t*>(P.u + uvo) = (uint16_t)uu;

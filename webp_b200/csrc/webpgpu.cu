@@ -78,10 +78,11 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens;
   PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false;
+  int dither_w = 0, dither_h = 0, dither_amp_cached = 0;  // what the device dither tables currently hold
   wgpu_enc_options e_opt;
   std::vector<wgh::FramePlan> plans;
   // decoder state
@@ -118,7 +119,7 @@ extern "C" {
 void wgpu_enc_options_default(wgpu_enc_options* o, int quality) {
   // DefaultOptions (encode.go:196-214) mapped onto lossy.EncodeConfig (internal/lossy/encode.go:66-86)
   o->quality = quality; o->method = 4; o->sns_strength = 50; o->filter_strength = 60; o->filter_sharpness = 0;
-  o->filter_type = 1; o->partitions = 0; o->segments = 4; o->preprocessing = 0; o->has_alpha = 0; o->passes = 1;
+  o->filter_type = 1; o->partitions = 0; o->segments = 4; o->preprocessing = 0; o->has_alpha = 0; o->passes = 1; o->dither_amp = 0;
 }
 
 static int upload_table(wgpu_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
@@ -192,7 +193,7 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->ctxw2, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens,
+  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
@@ -249,6 +250,7 @@ static int validate_enc_options(wgpu_ctx* ctx, const wgpu_enc_options* o, int wi
   // The GPU path restates the reference's row-parallel encoder (internal/lossy/encode.go:1356):
   // Method >= 3, mbH >= 4, single pass.  The serial-path configurations are a later row of the scope table.
   if (o->passes < 0 || o->passes > 10) FAIL(WGPU_ERR_INVALID, "webp: invalid Pass (must be 1-10 or 0 for default)");
+  if (o->dither_amp < 0 || o->dither_amp > 256) FAIL(WGPU_ERR_INVALID, "webp: dithering amplitude out of range [0, 256]");
   // Method < 3: statLoop + serial encodeFrame semantics (non-RD decisions) -- built.  Method >= 3 on frames of fewer than
   // 4 macroblock rows takes the reference's serial RD path (probability refreshes feed the RD costs) -- not built yet.
   if (o->method >= 3 && ((height + 15) >> 4) < 4) FAIL(WGPU_ERR_UNSUPPORTED, "Method >= 3 with height <= 48 takes the reference's serial RD path (not built yet)");
@@ -384,6 +386,37 @@ static int enc_launch_import(wgpu_ctx* ctx) {
   ip.y = ctx->sy.as<uint8_t>(); ip.u = ctx->su.as<uint8_t>(); ip.v = ctx->sv.as<uint8_t>();
   ip.y_plane = (size_t)pad_w * pad_h; ip.uv_plane = ip.y_plane / 4;
   ip.gamma_to_linear = ctx->t_g2l.as<uint16_t>(); ip.linear_to_gamma = ctx->t_l2g.as<uint16_t>();
+  ip.dither_y = nullptr; ip.dither_uv = nullptr;
+  if (ctx->e_opt.dither_amp > 0) {
+    if (ctx->dither_w != pad_w || ctx->dither_h != pad_h || ctx->dither_amp_cached != ctx->e_opt.dither_amp) {
+      // VP8Random (internal/dsp/random.go:17-79) run once on the host in the reference's draw order (encode.go:793-809, 925-936)
+      std::vector<uint16_t> dy((size_t)pad_w * pad_h);
+      std::vector<uint32_t> duv((size_t)(pad_w / 2) * (pad_h / 2) * 2);
+      uint32_t tab[55];
+      memcpy(tab, wgh::kRandomTable, sizeof(tab));
+      int i1 = 0, i2 = 31;
+      const int amp = ctx->e_opt.dither_amp;
+      auto bits = [&](int num_bits) {
+        long long diff = (long long)tab[i1] - (long long)tab[i2];
+        if (diff < 0) diff += 1ll << 31;
+        tab[i1] = (uint32_t)diff;
+        if (++i1 == 55) i1 = 0;
+        if (++i2 == 55) i2 = 0;
+        int d = (int)((int32_t)((uint32_t)diff << 1) >> (32 - num_bits));
+        d = (d * amp) >> 8;
+        return d + (1 << (num_bits - 1));
+      };
+      for (size_t i = 0; i < dy.size(); ++i) dy[i] = (uint16_t)bits(16);
+      for (size_t i = 0; i < duv.size(); ++i) duv[i] = (uint32_t)bits(18);
+      RESERVE(ctx->dither_y, dy.size() * 2);
+      RESERVE(ctx->dither_uv, duv.size() * 4);
+      CK(cudaMemcpyAsync(ctx->dither_y.p, dy.data(), dy.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->dither_uv.p, duv.data(), duv.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+      ctx->dither_w = pad_w; ctx->dither_h = pad_h; ctx->dither_amp_cached = amp;
+    }
+    ip.dither_y = ctx->dither_y.as<uint16_t>(); ip.dither_uv = ctx->dither_uv.as<uint32_t>();
+  }
   const long long total = (long long)(pad_w / 4) * (pad_h / 2) * n;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
   wg::import_rgba_kernel<<<blocks, 256, 0, ctx->stream>>>(ip);
@@ -909,7 +942,8 @@ int wgpu_import_rgba(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int h
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(ctx->mu);
   wgpu_enc_options_default(&ctx->e_opt, 75);
-  ctx->e_opt.has_alpha = has_alpha;
+  ctx->e_opt.has_alpha = has_alpha & 0xff;
+  ctx->e_opt.dither_amp = (has_alpha >> 8) & 0x1ff;  // bits 8.. of has_alpha carry the dithering amplitude (stage-level entry)
   if ((rc = enc_reserve(ctx))) return rc;
   if ((rc = enc_launch_import(ctx))) return rc;
   const size_t nmb = (size_t)ctx->e_mbw * ctx->e_mbh;

@@ -18,7 +18,7 @@ class EncOptions(C.Structure):
     """wgpu_enc_options == lossy.EncodeConfig (internal/lossy/encode.go:46-63)."""
     _fields_ = [(n, C.c_int) for n in (
         "quality", "method", "sns_strength", "filter_strength", "filter_sharpness", "filter_type",
-        "partitions", "segments", "preprocessing", "has_alpha", "passes")]
+        "partitions", "segments", "preprocessing", "has_alpha", "passes", "dither_amp")]
 
 
 class SegQuant(C.Structure):

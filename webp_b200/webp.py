@@ -130,7 +130,7 @@ def validateConfig(o):
 def lossy_config(o, has_alpha=False):
     """EncoderOptions -> lossy.EncodeConfig (encode.go:478-528 over lossy.DefaultConfig, internal/lossy/encode.go:66-86)."""
     c = native.EncOptions(quality=int(o.Quality), method=o.Method, sns_strength=50, filter_strength=60, filter_sharpness=0,
-                          filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=int(has_alpha), passes=1)
+                          filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=int(has_alpha), passes=1, dither_amp=0)
     if o.SNSStrength >= 0:
         c.sns_strength = o.SNSStrength
     if o.FilterStrength >= 0:
@@ -144,6 +144,12 @@ def lossy_config(o, has_alpha=False):
     c.preprocessing = o.Preprocessing
     if o.Pass > 0:
         c.passes = o.Pass
+    if o.Preprocessing & 2:
+        # encode.go:563-567 in float32: x = Quality/100; dithering = 1.0 + (0.5 - 1.0) * x^4; dsp.InitRandom: amp = int(256 * dithering)
+        x = np.float32(o.Quality) / np.float32(100.0)
+        x2 = np.float32(x * x)
+        d = np.float32(1.0) + np.float32(np.float32(np.float32(-0.5) * x2) * x2)
+        c.dither_amp = 0 if d < 0 else (256 if d > 1 else int(np.float32(256.0) * d))
     return c
 
 
@@ -158,8 +164,6 @@ def _unsupported(o):
         return "webp: UseSharpYUV is outside the GPU lossy path"
     if o.TargetSize > 0 or o.TargetPSNR > 0:
         return "webp: TargetSize/TargetPSNR take the reference's serial multi-pass path (not built yet)"
-    if o.Preprocessing & 2:
-        return "webp: dithered import (Preprocessing&2) is not built yet"
     if (o.Pass if o.Pass > 0 else 1) > 1 and o.Method >= 3:
         return "webp: Pass > 1 with Method >= 3 only matters with TargetSize/TargetPSNR (serial RD path, not built yet)"
     if o.ICC or o.EXIF or o.XMP:
