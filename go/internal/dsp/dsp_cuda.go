@@ -33,6 +33,11 @@ func TDisto4x4BatchCUDA(ctx unsafe.Pointer, a, b []byte, out []int32) int {
 	return int(C.wgpu_dsp_tdisto4x4_batch((*C.wgpu_ctx)(ctx), C.int(len(out)), (*C.uint8_t)(&a[0]), (*C.uint8_t)(&b[0]), (*C.int32_t)(&out[0])))
 }
 
+// PredSquareBatchCUDA: PredLuma16Direct / PredChroma8Direct for the seven modes (predict_lossy.go:27-181).
+func PredSquareBatchCUDA(ctx unsafe.Pointer, n, size int, ctxPx, out []byte) int {
+	return int(C.wgpu_dsp_pred_square_batch((*C.wgpu_ctx)(ctx), C.int(n), C.int(size), (*C.uint8_t)(&ctxPx[0]), (*C.uint8_t)(&out[0])))
+}
+
 // UpsampleNRGBACUDA: buildNRGBA / UpsampleLinePairNRGBA over whole planes (webp.go:379, upsample.go:130).
 func UpsampleNRGBACUDA(ctx unsafe.Pointer, n, w, h int, y []byte, yStride int, u, v []byte, uvStride, yPlane, uvPlane int, alpha, out []byte) int {
 	var pa *C.uint8_t

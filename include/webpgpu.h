@@ -157,6 +157,9 @@ int wgpu_dsp_sse4x4_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t*
 int wgpu_dsp_tdisto4x4_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int32_t* out);
 /* ctx13[i] = {tl, t0..t7, l0..l3}; out[(i*10+mode)*16..] for the ten B_* modes */
 int wgpu_dsp_pred4_batch(wgpu_ctx* ctx, int n, const uint8_t* ctx13, uint8_t* out);
+/* PredLuma16Direct / PredChroma8Direct (predict_lossy.go:27-181): size 16 or 8; ctx[i] = {tl, top[size], left[size]};
+ * out[((i*7+mode)*size + row)*size + col] for modes DC, TM, VE, HE, DC-noTop, DC-noLeft, DC-noTopLeft */
+int wgpu_dsp_pred_square_batch(wgpu_ctx* ctx, int n, int size, const uint8_t* ctx_px, uint8_t* out);
 /* quantizer derived as initSegmentQuant(dc_q, ac_q, type) (+ Y1 sharpening when sharpen!=0) */
 int wgpu_dsp_quantize_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, int ac_q, int type, int sharpen,
                             int first, int16_t* out, int32_t* nz);

@@ -22,7 +22,8 @@ static EncodeConfig to_cfg(const OrcEncCfg* c) {
   e.filter_type = c->filter_type; e.partitions = c->partitions; e.segments = c->segments;
   e.preprocessing = c->preprocessing;
   e.pass = c->passes > 0 ? c->passes : 1;
-  e.dither_amp = c->dither_amp;
+  e.dither_amp = c->dither_amp & 0xffff;
+  e.force_serial = (c->dither_amp >> 16) & 1;  // test hook: GOMAXPROCS == 1 semantics
   return e;
 }
 // Encode one RGBA image (parallel-path semantics).  Returns RIFF size or <0 (-1 unsupported
@@ -36,7 +37,7 @@ long orc_encode(const uint8_t* rgba, int stride, int w, int h, const OrcEncCfg* 
                 uint8_t* mb_hdr, uint8_t* mb_modes, uint8_t* mb_nz, int16_t* mb_coeffs, uint8_t* recon_y,
                 uint8_t* recon_u, uint8_t* recon_v, uint8_t* src_y, uint8_t* src_u, uint8_t* src_v,
                 uint8_t* alphas, int32_t* seg_out) {
-  if (cfg->method >= 3 && ((h + 15) >> 4) < 4) return -1;  // serial RD path (encode.go:1356, Method >= 3 with mbH < 4) not restated yet
+  if (((w + 15) >> 4) > 1024) return -1;
   Encoder* enc = new Encoder();
   enc->init(rgba, stride, w, h, to_cfg(cfg), cfg->has_alpha);
   std::vector<uint8_t> vp8 = enc->encode_frame();

@@ -79,6 +79,7 @@ struct BoolWriter {
 struct EncodeConfig {  // internal/lossy/encode.go:46-86 (DefaultConfig)
   int quality = 75, method = 4, sns_strength = 50, filter_strength = 60, filter_sharpness = 0;
   int filter_type = 1, partitions = 0, segments = 4, pass = 1, preprocessing = 0;
+  bool force_serial = false;  // GOMAXPROCS == 1 semantics: serial encodeFrame even where the reference would go row-parallel
   int dither_amp = 0;  // VP8Random.amp = int(256 * Dithering) (dsp/random.go:39-50); 0 == no dithering
 };
 struct SegmentQuant {  // encode.go:311-323
@@ -381,6 +382,8 @@ struct Encoder {
     v_plane.assign((size_t)uv_stride * mb_h * 8, 0);
     mb_info.assign((size_t)mb_w * mb_h, MBInfo());
     memset(dqm, 0, sizeof(dqm));
+    memset(top_derr, 0, sizeof(top_derr));
+    memset(left_derr, 0, sizeof(left_derr));
     compute_fixed_costs_i4();
     import_image(rgba, stride, has_alpha);
     init_segments();
@@ -1856,6 +1859,265 @@ struct Encoder {
     mb_export(mx, my, rc);
   }
 
+  // ---- serial RD path (Method >= 3 when the reference does not go row-parallel: mbH < 4 or GOMAXPROCS == 1, encode.go:1356)
+  int8_t top_derr[1024][2][2];  // enc.topDerr[x][ch] (encode.go:150); sized for mb_w <= 1024
+  int8_t left_derr[2][2];       // enc.leftDerr[ch]: NOT reset at row starts
+  static int quantize_single(int16_t* v, const SegmentQuant* sq) {  // encode_frame.go:510
+    int V = *v, sign = 1;
+    if (V < 0) { sign = -1; V = -V; }
+    const int zthresh = ((1 << 17) - 1 - sq->dc_bias) / sq->dc_iquant;  // DCZthresh (encode.go:1175)
+    if (V > zthresh) {
+      const int qV = (int)(((uint32_t)V * (uint32_t)sq->dc_iquant + (uint32_t)sq->dc_bias) >> 17) * sq->dc_quant;
+      const int err = V - qV;
+      *v = (int16_t)(sign * qV);
+      return (sign * err) >> 1;
+    }
+    *v = 0;
+    return (sign * V) >> 1;
+  }
+  // PickBestI4ModeRD (encode_analysis.go:1216): every eligible mode, plain quantisation, in mode order
+  void pick_best_i4_all(int off, const SegmentInfo* seg, int top_mode, int left_mode, bool has_top, bool has_left, int nz_ctx,
+                        int* best_mode, int* best_rate, int* best_disto) {
+    uint64_t best_score = ~(uint64_t)0;
+    *best_mode = B_DC_PRED; *best_rate = 0; *best_disto = 0;
+    const uint8_t* src = yuv_in + off;
+    uint8_t* pred_buf = yuv_out2;
+    for (int mode = 0; mode < 10; ++mode) {
+      if (!has_top && needs_top4(mode)) continue;
+      if (!has_left && needs_left4(mode)) continue;
+      int16_t c[16], q[16], dq[16];
+      uint8_t recon[4 * BPS];
+      pred_luma4(mode, pred_buf, off);
+      ftransform(src, pred_buf + off, c);
+      const int nz = quantize_coeffs(c, q, &seg->y1, 0);
+      dequant_coeffs(q, dq, &seg->y1);
+      itransform_one(pred_buf + off, dq, recon);
+      int disto = sse4x4(src, recon);
+      if (seg->tlambda_sd > 0) disto += (seg->tlambda_sd * tdisto4x4(src, recon) + 128) >> 8;
+      if (256 * (uint64_t)disto >= best_score) continue;
+      int rate = 0;
+      if (mode > 0 && is_flat(q, 1, 3)) rate = 140;
+      rate += token_cost(q, nz, 3, &proba, nz_ctx, 0);
+      rate += fixed_costs_i4[top_mode][left_mode][mode];
+      const uint64_t score = rd_score(disto, rate, seg->lambda_i4);
+      if (score < best_score) {
+        best_score = score;
+        *best_mode = mode; *best_rate = rate; *best_disto = disto;
+        memcpy(tmp_best_dq, dq, sizeof(dq));
+        memcpy(tmp_best_q, q, sizeof(q));
+        tmp_best_nz = nz;
+      }
+    }
+  }
+  // tryI4ModesRD (encode_frame.go:242-347): like the parallel twin, but Method 3 scores all modes, and the mode-cost
+  // context is saved here -- only when the search ran to completion, whatever the I4-vs-I16 outcome.
+  uint64_t try_i4_modes_serial(int mx, int my, MBInfo* info, const SegmentInfo* seg, uint8_t* modes, RowCtx& rc, uint64_t i16_score,
+                               uint32_t top_nz_v, uint32_t left_nz_v) {
+    int total_rate = 0, total_disto = 0, total_header_bits = 0;
+    uint8_t top_m[4];
+    for (int i = 0; i < 4; ++i) top_m[i] = (my > 0) ? top_modes[mx * 4 + i] : B_DC_PRED;
+    memcpy(yuv_out2, yuv_out, YUV_SIZE);
+    uint32_t tnz = top_nz_v & 0x0f, lnz = left_nz_v & 0x0f, l = 0;
+    bool early_exit = false;
+    const int max_modes = cfg.quality < 50 ? 2 : 3;
+    for (int by = 0; by < 4 && !early_exit; ++by) {
+      l = lnz & 1;
+      for (int bx = 0; bx < 4; ++bx) {
+        const int b = by * 4 + bx;
+        const int top_mode = (by == 0) ? top_m[bx] : modes[b - 4];
+        const int left_mode = (bx == 0) ? rc.left_modes[by] : modes[b - 1];
+        const int off = Y_OFF + by * 4 * BPS + bx * 4;
+        const bool has_top = (my > 0 || by > 0), has_left = (mx > 0 || bx > 0);
+        int nz_ctx = (int)l + (int)(tnz & 1);
+        if (nz_ctx > 2) nz_ctx = 2;
+        int best_mode, rate, disto;
+        if (cfg.method >= 4) pick_best_i4(off, seg, top_mode, left_mode, has_top, has_left, nz_ctx, max_modes, true, &best_mode, &rate, &disto);
+        else pick_best_i4_all(off, seg, top_mode, left_mode, has_top, has_left, nz_ctx, &best_mode, &rate, &disto);
+        modes[b] = (uint8_t)best_mode;
+        total_rate += rate;
+        total_disto += disto;
+        total_header_bits += fixed_costs_i4[top_mode][left_mode][best_mode];
+        memcpy(info->coeffs + b * 16, tmp_best_q, 32);
+        const int nz = tmp_best_nz;
+        info->nz_y[b] = (uint8_t)nz;
+        if (rd_score(total_disto, total_rate + 211, seg->lambda_mode) >= i16_score) { early_exit = true; break; }
+        if (total_header_bits > 15000) { early_exit = true; break; }
+        pred_luma4(best_mode, yuv_out2, off);
+        itransform_one(yuv_out2 + off, tmp_best_dq, yuv_out2 + off);
+        l = nz > 0;
+        tnz = (tnz >> 1) | (l << 7);
+      }
+      tnz >>= 4;
+      lnz = (lnz >> 1) | (l << 7);
+    }
+    if (early_exit) return ~(uint64_t)0;
+    for (int i = 0; i < 4; ++i) {
+      top_modes[mx * 4 + i] = modes[12 + i];
+      rc.left_modes[i] = modes[3 + 4 * i];
+    }
+    return rd_score(total_disto, total_rate + 211, seg->lambda_mode);
+  }
+  void encode_mb_serial_rd(int mx, int my, RowCtx& rc) {
+    const size_t idx = (size_t)my * mb_w + mx;
+    MBInfo* info = &mb_info[idx];
+    const SegmentInfo* seg = &dqm[info->segment];
+    mb_import(mx, my);
+    mb_fill_ctx(mx, my, rc);
+    const uint32_t tnz_val = s_top_nz[mx], lnz_val = s_left_nz;
+    bool i4_cached = false;
+    {  // pickBestMode, Method >= 3 branch (encode_frame.go:122-164)
+      int best16, rate16, disto16;
+      pick_best_i16(mx, my, seg, tnz_val, lnz_val, s_top_nz_dc[mx], s_left_nz_dc, &best16, &rate16, &disto16);
+      const uint64_t score16 = rd_score(disto16, rate16, seg->lambda_mode);
+      uint8_t modes4[16] = {0};
+      const uint64_t score4 = try_i4_modes_serial(mx, my, info, seg, modes4, rc, score16, tnz_val, lnz_val);
+      if (score4 < score16) {
+        info->mb_type = 1;
+        memcpy(info->modes, modes4, 16);
+        if (cfg.method >= 4) {
+          i4_cached = true;
+          for (int j = 0; j < 16; ++j) memcpy(yuv_out + Y_OFF + j * BPS, yuv_out2 + Y_OFF + j * BPS, 16);
+        }
+      } else {
+        info->mb_type = 0;
+        info->i16_mode = (uint8_t)best16;
+        pred_luma16(check_mode(mx, my, best16), yuv_out, Y_OFF);
+      }
+      const int best_uv = pick_best_uv(mx, my, seg, tnz_val, lnz_val);
+      info->uv_mode = (uint8_t)best_uv;
+      pred_chroma8(check_mode(mx, my, best_uv), yuv_out, U_OFF);
+      pred_chroma8(check_mode(mx, my, best_uv), yuv_out, V_OFF);
+    }
+    // encodeResiduals (encode_frame.go:350-645)
+    if (info->mb_type == 0) {
+      int16_t dc_coeffs[16];
+      uint32_t nz_y = 0, tnz = tnz_val & 0x0f, lnz = lnz_val & 0x0f;
+      for (int by = 0; by < 4; ++by) {
+        uint32_t l = lnz & 1;
+        for (int bx = 0; bx < 4; ++bx) {
+          const int b = by * 4 + bx, off = Y_OFF + by * 4 * BPS + bx * 4;
+          int16_t* c = info->coeffs + b * 16;
+          ftransform(yuv_in + off, yuv_out + off, c);
+          dc_coeffs[b] = c[0];
+          c[0] = 0;
+          int nz;
+          if (cfg.method >= 4) {
+            int ctx = (int)l + (int)(tnz & 1);
+            if (ctx > 2) ctx = 2;
+            nz = trellis_quantize_block(c, c, &seg->y1, 1, 0, ctx, &proba, seg->tlambda_i16);
+          } else {
+            nz = quantize_coeffs(c, c, &seg->y1, 1);
+          }
+          info->nz_y[b] = (uint8_t)nz;
+          if (nz > 0) nz_y |= 1u << b;
+          l = nz > 0;
+          tnz = (tnz >> 1) | (l << 7);
+        }
+        tnz >>= 4;
+        lnz = (lnz >> 1) | (l << 7);
+      }
+      int16_t wht[16];
+      ftransform_wht(dc_coeffs, wht);
+      const int nz_dc = quantize_coeffs(wht, info->coeffs + 384, &seg->y2, 0);
+      info->nz_dc = (uint8_t)nz_dc;
+      if (nz_dc > 0) nz_y |= 1u << 24;
+      info->non_zero_y = nz_y;
+    } else if (i4_cached) {
+      uint32_t nz_y = 0;
+      for (int b = 0; b < 16; ++b) if (info->nz_y[b] > 0) nz_y |= 1u << b;
+      info->non_zero_y = nz_y;
+    } else {
+      uint32_t nz_y = 0;
+      for (int b = 0; b < 16; ++b) {
+        const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+        int16_t* c = info->coeffs + b * 16;
+        int16_t dq[16];
+        pred_luma4(info->modes[b], yuv_out, off);
+        ftransform(yuv_in + off, yuv_out + off, c);
+        const int nz = quantize_coeffs(c, c, &seg->y1, 0);
+        info->nz_y[b] = (uint8_t)nz;
+        if (nz > 0) nz_y |= 1u << b;
+        dequant_coeffs(c, dq, &seg->y1);
+        itransform_one(yuv_out + off, dq, yuv_out + off);
+      }
+      info->non_zero_y = nz_y;
+    }
+    {  // encodeUVResiduals with DC error diffusion (useDerr = Method >= 3, encode_frame.go:569-645)
+      for (int ch = 0; ch < 2; ++ch)
+        for (int b = 0; b < 4; ++b) {
+          const int off = (ch ? V_OFF : U_OFF) + (b >> 1) * 4 * BPS + (b & 1) * 4;
+          ftransform(yuv_in + off, yuv_out + off, info->coeffs + (16 + ch * 4 + b) * 16);
+        }
+      int8_t derr[2][3];
+      for (int ch = 0; ch < 2; ++ch) {  // correctDCValues (encode_frame.go:529)
+        const int8_t* top = top_derr[mx][ch];
+        const int8_t* left = left_derr[ch];
+        int16_t* c0 = info->coeffs + (16 + ch * 4 + 0) * 16;
+        int16_t* c1 = info->coeffs + (16 + ch * 4 + 1) * 16;
+        int16_t* c2 = info->coeffs + (16 + ch * 4 + 2) * 16;
+        int16_t* c3 = info->coeffs + (16 + ch * 4 + 3) * 16;
+        *c0 += (int16_t)((7 * (int)top[0] + 8 * (int)left[0]) >> 3);
+        const int err0 = quantize_single(c0, &seg->uv);
+        *c1 += (int16_t)((7 * (int)top[1] + 8 * err0) >> 3);
+        const int err1 = quantize_single(c1, &seg->uv);
+        *c2 += (int16_t)((7 * err0 + 8 * (int)left[1]) >> 3);
+        const int err2 = quantize_single(c2, &seg->uv);
+        *c3 += (int16_t)((7 * err1 + 8 * err2) >> 3);
+        const int err3 = quantize_single(c3, &seg->uv);
+        derr[ch][0] = (int8_t)err1; derr[ch][1] = (int8_t)err2; derr[ch][2] = (int8_t)err3;
+      }
+      uint32_t nz_uv = 0;
+      for (int ch = 0; ch < 2; ++ch)
+        for (int b = 0; b < 4; ++b) {
+          int16_t* c = info->coeffs + (16 + ch * 4 + b) * 16;
+          const int nz = quantize_coeffs(c, c, &seg->uv, 0);
+          info->nz_uv[ch * 4 + b] = (uint8_t)nz;
+          if (nz > 0) nz_uv |= 1u << (ch * 4 + b);
+        }
+      for (int ch = 0; ch < 2; ++ch) {  // storeDiffusionErrors (encode_frame.go:557)
+        int8_t* top = top_derr[mx][ch];
+        int8_t* left = left_derr[ch];
+        left[0] = derr[ch][0];
+        left[1] = (int8_t)((3 * (int)derr[ch][2]) >> 2);
+        top[0] = derr[ch][1];
+        top[1] = (int8_t)(derr[ch][2] - left[1]);
+      }
+      info->non_zero_uv = nz_uv;
+    }
+    info->skip = (info->non_zero_y == 0 && info->non_zero_uv == 0);
+    if (info->skip) {
+      num_skip++;
+      s_top_nz[mx] = 0; s_left_nz = 0;
+      if (info->mb_type == 0) { s_top_nz_dc[mx] = 0; s_left_nz_dc = 0; }
+    } else if (skip_tokens) {
+      update_nz(info, &s_top_nz[mx], &s_left_nz, &s_top_nz_dc[mx], &s_left_nz_dc);
+    } else {
+      mb_start[idx] = tokens.size();
+      walk_mb(info, &s_top_nz[mx], &s_left_nz, &s_top_nz_dc[mx], &s_left_nz_dc,
+              [&](const int16_t* c, int nz, int type, int first, int ctx) { record_coeffs(c, nz, type, first, ctx); });
+    }
+    if (info->mb_type == 0) {  // reconstructMB
+      int16_t wht_dq[16], wht_buf[256], dq[16];
+      dequant_coeffs(info->coeffs + 384, wht_dq, &seg->y2);
+      transform_wht(wht_dq, wht_buf);
+      for (int b = 0; b < 16; ++b) {
+        const int off = Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+        dequant_coeffs(info->coeffs + b * 16, dq, &seg->y1);
+        dq[0] = wht_buf[b * 16];
+        itransform_one(yuv_out + off, dq, yuv_out + off);
+      }
+    }
+    for (int b = 0; b < 4; ++b) {
+      int16_t dq[16];
+      const int o = (b >> 1) * 4 * BPS + (b & 1) * 4;
+      dequant_coeffs(info->coeffs + (16 + b) * 16, dq, &seg->uv);
+      itransform_one(yuv_out + U_OFF + o, dq, yuv_out + U_OFF + o);
+      dequant_coeffs(info->coeffs + (20 + b) * 16, dq, &seg->uv);
+      itransform_one(yuv_out + V_OFF + o, dq, yuv_out + V_OFF + o);
+    }
+    mb_export(mx, my, rc);
+  }
+
   // collectAllStats (encode_proba.go:171-313): the whole mb_info array, whatever it currently holds
   void collect_all_stats(ProbaStats st) {
     memset(st, 0, sizeof(ProbaStats));
@@ -1888,6 +2150,7 @@ struct Encoder {
     s_top_nz.assign(mb_w, 0); s_top_nz_dc.assign(mb_w, 0);
     s_left_nz = 0; s_left_nz_dc = 0;
     num_skip = 0;
+    // topDerr / leftDerr are zeroed when the encoder is created or recycled (resetForReuse), not per pass or per row
     const int total_mb = mb_w * mb_h;
     int max_count = total_mb >> 3;
     if (max_count < 96) max_count = 96;
@@ -1901,7 +2164,7 @@ struct Encoder {
       for (int mx = 0; mx < mb_w; ++mx) {
         if (mx == 0) { s_left_nz = 0; s_left_nz_dc = 0; }
         if (--refresh_cnt < 0) { refresh_probas(); refresh_cnt = max_count; }
-        encode_mb_serial(mx, my, rc);
+        if (cfg.method >= 3) encode_mb_serial_rd(mx, my, rc); else encode_mb_serial(mx, my, rc);
       }
     }
     if (num_skip > 0) skip_proba = (uint8_t)((total_mb - num_skip) * 255 / total_mb);
@@ -1950,6 +2213,14 @@ struct Encoder {
       static thread_local ProbaStats st2;
       collect_all_stats(st2);
       if (optimize_proba(st2) > 0) rerecord_all_tokens();
+      return assemble_frame();
+    }
+    if (mb_h < 4 || cfg.force_serial) {  // useParallel == false (encode.go:1356): one serial pass, then the common tail
+      tokens.clear();
+      encode_frame_serial_pass();
+      static thread_local ProbaStats st3;
+      collect_all_stats(st3);
+      if (optimize_proba(st3) > 0) rerecord_all_tokens();
       return assemble_frame();
     }
     // Phase A

@@ -93,6 +93,15 @@ ENC_CASES = [
     (320, 240, [2], dict(Method=2, Pass=3, Quality=60)),
     (128, 96, [1, 2], dict(Preprocessing=2, Quality=60)),  # dithered import (PresetPhoto sets this bit)
     (128, 96, [1], dict(Preprocessing=3, Quality=90, Method=2)),
+    # Method >= 3 on fewer than 4 macroblock rows: the reference's serial RD path (all-mode I4 search at Method 3,
+    # trial mode context kept only when the search completes, chroma DC error diffusion) -- built up to 96 macroblocks
+    (64, 48, [0, 1, 2], {}),
+    (100, 40, [1, 2], dict(Method=3)),
+    (33, 17, [1, 2], dict(Method=6, Quality=90)),
+    (512, 48, [1, 2], dict(Method=3, Quality=30)),
+    (512, 48, [0, 2], dict(Method=5, Quality=85, Segments=2)),
+    (16, 16, [1, 2], {}),
+    (160, 33, [2], dict(Quality=98, SNSStrength=100, Partitions=1)),
 ]
 
 
@@ -159,8 +168,9 @@ def test_encode_test_png(oracle, gpu_ctx):
 
 def test_encode_rejections(gpu_ctx):
     img = np.full((64, 64, 4), 255, np.uint8)
-    with pytest.raises(native.WebPGPUError) as e:  # Method >= 3 on < 4 macroblock rows: the reference's serial RD path
-        webp_b200.EncodeBatch(img[None, :40], _opts(), gpu_ctx)
+    wide = np.full((40, 16 * 97, 4), 255, np.uint8)
+    with pytest.raises(native.WebPGPUError) as e:  # serial RD path with mid-stream probability refreshes (> 96 macroblocks)
+        webp_b200.EncodeBatch(wide[None], _opts(), gpu_ctx)
     assert e.value.code == native.ERR_UNSUPPORTED
     with pytest.raises(webp_b200.WebPError):
         webp_b200.EncodeBatch(img[None], _opts(TargetPSNR=40.0), gpu_ctx)

@@ -66,6 +66,17 @@ def test_pred4_all_modes(oracle, gpu_ctx):
     assert np.array_equal(dsp.PredLuma4Batch(c, gpu_ctx), exp)
 
 
+@pytest.mark.parametrize("size", [16, 8])
+def test_pred_square_all_modes(oracle, gpu_ctx, size):
+    rng = np.random.RandomState(8)
+    n = 3000
+    c = rng.randint(0, 256, (n, 1 + 2 * size)).astype(np.uint8)
+    c[:20] = 0; c[20:40] = 255
+    exp = np.zeros((n, 7, size, size), np.uint8)
+    oracle.lib().orc_pred_square_batch(n, size, _p(c), _p(exp))
+    assert np.array_equal(dsp.PredSquareBatch(c, size, gpu_ctx), exp)
+
+
 @pytest.mark.parametrize("dc_q,ac_q,qtype,sharpen,first", [(24, 30, 0, 1, 0), (24, 30, 0, 1, 1), (48, 46, 1, 0, 0), (21, 27, 2, 0, 0),
                                                              (4, 4, 0, 1, 0), (157, 284, 0, 1, 1)])
 def test_quantize(oracle, gpu_ctx, dc_q, ac_q, qtype, sharpen, first):

@@ -65,6 +65,9 @@ def test_import_matches_libwebp(oracle, w, h, kind):
     (128, 128, 2, dict(partitions=2, quality=90)), (128, 96, 2, dict(quality=95)),
     # serial path (Method < 3)
     (256, 256, 1, dict(method=2, quality=80)), (100, 70, 2, dict(method=0)), (64, 32, 1, dict(method=1)), (16, 16, 2, dict(method=2)),
+    # serial RD path (Method >= 3, fewer than 4 macroblock rows; bit 16 of dither_amp = GOMAXPROCS==1 semantics on any frame)
+    (64, 48, 1, {}), (100, 40, 2, dict(method=3)), (512, 48, 1, dict(method=6, quality=85)), (33, 17, 2, dict(quality=30)),
+    (128, 96, 1, dict(dither_amp=1 << 16)), (256, 192, 2, dict(method=3, dither_amp=1 << 16)),
 ])
 def test_oracle_stream_decodes_identically_in_libwebp(oracle, w, h, idx, kw):
     """Every oracle-encoded stream must decode in libwebp to exactly what the oracle's decoder produces,

@@ -24,7 +24,9 @@ struct EncKernelParams {
   const uint8_t* segment;       // [n][nmb]
   const ImageParams* img;       // [n]
   uint32_t* ctx;                // [n][nmb] packed NZ context (see pack_ctx)
-  uint32_t* ctx2;               // [n][nmb] Method < 3: trial 4x4 modes of the bottom row / right column (mode-cost context)
+  int8_t* top_derr;             // [n][mb_w][2][2] serial RD path: DC error diffusion state (enc.topDerr)
+  int8_t* left_derr;            // [n][2][2] (enc.leftDerr)
+  uint32_t* ctx2;               // [n][nmb] Method < 3 / serial RD: trial 4x4 modes of the bottom row / right column (mode-cost context)
   int* progress;                // [n][mb_h] finished macroblocks per row (persistent kernel)
   unsigned long long* work_counter;  // next group to claim (persistent kernel)
   const long long* wave_start;  // [waves + 1] prefix of groups per wave (persistent kernel)
@@ -222,7 +224,7 @@ template <bool PERSIST, class Tp>
 __device__ __forceinline__ Tp ldn(const Tp* p) { return PERSIST ? __ldcg(p) : *p; }
 
 // The mode search of MPW = 32/G macroblocks by one warp: macroblock `task_base + lane/G` of wave `wave`.
-template <int G, bool PERSIST, bool FAST>
+template <int G, bool PERSIST, bool FAST, bool SERIAL = false>
 __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wave, long long task_base, MBShared* s_mb_warp,
                                                 const CostTabs& T, const uint16_t* s_i4cost) {
   const int lane = threadIdx.x & 31;
@@ -230,12 +232,13 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   // rows on this wave: x = wave - 2y in [0, mb_w)
   const int y_lo = max(0, (wave - (P.mb_w - 1) + 1) >> 1), y_hi = min(P.mb_h - 1, wave >> 1);
   const int rows = y_hi - y_lo + 1;
-  const long long total = (long long)rows * P.n_images;
+  const long long total = SERIAL ? (long long)P.n_images : (long long)rows * P.n_images;
   const long long task = task_base + g;
   const bool active = task < total;
-  const int img = active ? (int)(task / rows) : 0;
-  const int my = active ? y_lo + (int)(task % rows) : 0;
-  const int mx = active ? wave - 2 * my : 0;
+  // SERIAL (the reference's serial encodeFrame order): `wave` is the raster macroblock index, one macroblock per image per launch
+  const int img = active ? (SERIAL ? (int)task : (int)(task / rows)) : 0;
+  const int my = active ? (SERIAL ? wave / P.mb_w : y_lo + (int)(task % rows)) : 0;
+  const int mx = active ? (SERIAL ? wave - my * P.mb_w : wave - 2 * my) : 0;
   const int nmb = P.mb_w * P.mb_h;
   const int mb_idx = my * P.mb_w + mx;
   MBShared& S = s_mb_warp[g];
@@ -344,7 +347,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       top_nz = cw & 0xff;
       top_nz_dc = (cw >> 16) & 1;
       const uint8_t* th = hdr - (size_t)P.mb_w * 48;
-      if (FAST) {
+      if (FAST || SERIAL) {
         const uint32_t tm = ldn<PERSIST>(&P.ctx2[(size_t)img * nmb + mb_idx - P.mb_w]);
         for (int i = 0; i < 4; ++i) top_modes[i] = (tm >> (4 * i)) & 15;
       } else if (ldn<PERSIST>(&th[0]) == 1) { top_modes[0] = ldn<PERSIST>(&th[8 + 12]); top_modes[1] = ldn<PERSIST>(&th[8 + 13]); top_modes[2] = ldn<PERSIST>(&th[8 + 14]); top_modes[3] = ldn<PERSIST>(&th[8 + 15]); }
@@ -354,7 +357,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       left_nz = (cw >> 8) & 0xff;
       left_nz_dc = (cw >> 17) & 1;
       const uint8_t* lh = hdr - 48;
-      if (FAST) {
+      if (FAST || SERIAL) {
         const uint32_t lm = ldn<PERSIST>(&P.ctx2[(size_t)img * nmb + mb_idx - 1]);
         for (int i = 0; i < 4; ++i) left_modes[i] = (lm >> (16 + 4 * i)) & 15;
       } else if (ldn<PERSIST>(&lh[0]) == 1) { left_modes[0] = ldn<PERSIST>(&lh[8 + 3]); left_modes[1] = ldn<PERSIST>(&lh[8 + 7]); left_modes[2] = ldn<PERSIST>(&lh[8 + 11]); left_modes[3] = ldn<PERSIST>(&lh[8 + 15]); }
@@ -537,8 +540,10 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
         if (gl == G - 1 && seg.tlambda_sd > 0) S.misc[2] = ttransform(s);  // source half of TDisto, shared by the candidates
       }
       __syncwarp();
-      const int K = alive ? min(P.max_i4_modes, n_cand) : 0;
-      if (alive && gl == 0) {  // the reference's selection sort of the first K entries, literally (encode_parallel.go:969-983)
+      // serial path, Method 3: PickBestI4ModeRD scores every eligible mode in mode order, no pre-screen (encode_analysis.go:1216)
+      const bool all_modes = SERIAL && P.method == 3;
+      const int K = alive ? (all_modes ? n_cand : min(P.max_i4_modes, n_cand)) : 0;
+      if (alive && gl == 0 && !all_modes) {  // the reference's selection sort of the first K entries, literally (encode_parallel.go:969-983)
 #pragma unroll 1
         for (int i = 0; i < K; ++i) {
           int mi = i, mv = S.sse[i];
@@ -552,10 +557,15 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
         }
       }
       __syncwarp();
-      // full RD on the K candidates, one lane each
+      // full RD on the K candidates, one lane each, three candidates per round (one round on the row-parallel path)
+      I4Cand& BEST = *reinterpret_cast<I4Cand*>(&S.lev[16][0]);  // chroma level slots are idle during the luma search
+      unsigned long long bs = ~0ull;
+      bool have_best = false;
+      for (int r0 = 0; r0 < (SERIAL ? 12 : 3); r0 += 3) {
       if (alive) {
-        for (int k = gl; k < K; k += G) {
-          const int mode = S.smode[k];
+        for (int kk = gl; kk < 3 && r0 + kk < K; kk += G) {
+          const int k = kk;
+          const int mode = S.smode[r0 + kk];
           int p[16], c[16], q[16], dq[16], r[16];
           load4x4s<4>(S.pred4s[mode], p);
           ftransform(s, p, c);
@@ -595,14 +605,21 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       }
       __syncwarp();
       if (alive) {
-        unsigned long long bs = ~0ull;
-        int bk = 0;
-        for (int k = 0; k < K; ++k) {
-          const I4Cand& C = S.cand[k];
-          if (256ull * (unsigned long long)C.disto >= bs) continue;
-          if (C.score < bs) { bs = C.score; bk = k; }
+        for (int k = 0; k < 3 && r0 + k < K; ++k) {
+          const I4Cand& Ck = S.cand[k];
+          if (256ull * (unsigned long long)Ck.disto >= bs) continue;
+          if (Ck.score < bs) {
+            bs = Ck.score;
+            have_best = true;
+            for (int i = gl; i < (int)(sizeof(I4Cand) / 4); i += G) reinterpret_cast<uint32_t*>(&BEST)[i] = reinterpret_cast<const uint32_t*>(&Ck)[i];
+          }
         }
-        const I4Cand& C = S.cand[bk];
+      }
+      __syncwarp();
+      }
+      if (alive) {
+        (void)have_best;
+        const I4Cand& C = BEST;
         const int bm = C.mode;
         if (b < 8) modes_lo |= (uint32_t)bm << (4 * b); else modes_hi |= (uint32_t)bm << (4 * (b - 8));
         total_rate += C.rate;
@@ -621,6 +638,16 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
     }
     if (alive) score4 = rd_score(total_disto, total_rate + 211, seg.lambda_mode);
     i4_nzmask = nzmask;
+    if constexpr (SERIAL) {
+      // tryI4ModesRD saves the mode-cost context only when the search ran to completion -- whatever wins afterwards; an
+      // early exit leaves the iterator's topModes / leftModes as they were (encode_frame.go:337-340)
+      if (alive)
+        trial_modes = ((modes_hi >> 16) & 0xffffu) | (((modes_lo >> 12) & 15) << 16) | (((modes_lo >> 28) & 15) << 20) |
+                      (((modes_hi >> 12) & 15) << 24) | (((modes_hi >> 28) & 15) << 28);
+      else
+        trial_modes = (uint32_t)top_modes[0] | ((uint32_t)top_modes[1] << 4) | ((uint32_t)top_modes[2] << 8) | ((uint32_t)top_modes[3] << 12) |
+                      ((uint32_t)left_modes[0] << 16) | ((uint32_t)left_modes[1] << 20) | ((uint32_t)left_modes[2] << 24) | ((uint32_t)left_modes[3] << 28);
+    }
     // ---- decision (encode_parallel.go:572-592)
     const bool use_i4 = active && score4 < score16;
     if (active) {
@@ -931,12 +958,61 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   if (active) {
     for (int b = gl; b < 8; b += G) {
       const int off = ((b & 4) ? V_OFF : U_OFF) + ((b >> 1) & 1) * 4 * BPS + (b & 1) * 4;
-      int s[16], p[16], c[16], q[16], dq[16], r[16];
+      int s[16], p[16], c[16];
       load_src_block(S.in, 16 + b, s);
       load4x4(S.out + off, p);
       ftransform(s, p, c);
 #pragma unroll
       for (int i = 0; i < 16; ++i) S.lev[16 + b][i] = (int16_t)c[i];
+    }
+  }
+  __syncwarp();
+  if constexpr (SERIAL) {
+    // DC error diffusion (useDerr = Method >= 3 on the serial path): correctDCValues before the quantisation,
+    // storeDiffusionErrors after it (encode_frame.go:500-566).  topDerr is per column, leftDerr is NOT reset per row.
+    if (active && gl == 0) {
+      int8_t* td = P.top_derr + ((size_t)img * P.mb_w + mx) * 4;
+      int8_t* ld = P.left_derr + (size_t)img * 4;
+      const SegQuant& sq = seg.uv;
+      const int zthresh = ((1 << 17) - 1 - sq.dc_bias) / sq.dc_iquant;  // DCZthresh (encode.go:1175)
+      auto quantize_single = [&](int16_t* v) -> int {  // quantizeSingle (encode_frame.go:510)
+        int V = *v, sign = 1;
+        if (V < 0) { sign = -1; V = -V; }
+        if (V > zthresh) {
+          const int qV = (int)(((uint32_t)V * (uint32_t)sq.dc_iquant + (uint32_t)sq.dc_bias) >> 17) * sq.dc_quant;
+          *v = (int16_t)(sign * qV);
+          return (sign * (V - qV)) >> 1;
+        }
+        *v = 0;
+        return (sign * V) >> 1;
+      };
+      for (int ch = 0; ch < 2; ++ch) {
+        const int t0 = td[ch * 2], t1 = td[ch * 2 + 1], l0 = ld[ch * 2], l1 = ld[ch * 2 + 1];
+        int16_t* c0 = &S.lev[16 + ch * 4 + 0][0];
+        int16_t* c1 = &S.lev[16 + ch * 4 + 1][0];
+        int16_t* c2 = &S.lev[16 + ch * 4 + 2][0];
+        int16_t* c3 = &S.lev[16 + ch * 4 + 3][0];
+        *c0 = (int16_t)(*c0 + (int16_t)((7 * t0 + 8 * l0) >> 3));
+        const int e0 = quantize_single(c0);
+        *c1 = (int16_t)(*c1 + (int16_t)((7 * t1 + 8 * e0) >> 3));
+        const int e1 = quantize_single(c1);
+        *c2 = (int16_t)(*c2 + (int16_t)((7 * e0 + 8 * l1) >> 3));
+        const int e2 = quantize_single(c2);
+        *c3 = (int16_t)(*c3 + (int16_t)((7 * e1 + 8 * e2) >> 3));
+        const int e3 = quantize_single(c3);
+        const int8_t d0 = (int8_t)e1, d1 = (int8_t)e2, d2 = (int8_t)e3;  // info.Derr[ch] (int8 truncation as in the reference)
+        const int8_t nl1 = (int8_t)((3 * (int)d2) >> 2);
+        ld[ch * 2] = d0; ld[ch * 2 + 1] = nl1;
+        td[ch * 2] = d1; td[ch * 2 + 1] = (int8_t)(d2 - nl1);
+      }
+    }
+    __syncwarp();
+  }
+  if (active) {
+    for (int b = gl; b < 8; b += G) {
+      const int off = ((b & 4) ? V_OFF : U_OFF) + ((b >> 1) & 1) * 4 * BPS + (b & 1) * 4;
+      int p[16], q[16], dq[16], r[16];
+      load4x4(S.out + off, p);
       const int nz = quantize_smem(S.lev[16 + b], seg.uv, 0);
       S.nz[16 + b] = nz;
       hdr[40 + b] = (uint8_t)nz;
@@ -1010,7 +1086,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       const uint32_t out_l = yl | (ul << 4) | (vl << 6);
       const int tdc = i16 ? dcflag : top_nz_dc, ldc = i16 ? dcflag : left_nz_dc;
       ctxw[mb_idx] = pack_ctx(out_t, out_l, tdc, ldc);
-      if (FAST) P.ctx2[(size_t)img * nmb + mb_idx] = trial_modes;
+      if (FAST || SERIAL) P.ctx2[(size_t)img * nmb + mb_idx] = trial_modes;
     }
   }
   if (PERSIST) {  // publish: everything this macroblock wrote must be visible before the row counter moves
@@ -1051,6 +1127,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_fast_wave_kernel(cons
   WG_STAGE_TABLES(WARPS * 32);
   const int warp = threadIdx.x >> 5;
   encode_mb_group<G, false, true>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
+}
+
+// Serial RD path (Method >= 3 where the reference does not go row-parallel): macroblocks in raster order, one launch per
+// macroblock index over the whole batch -- the reference's leftDerr carries from the end of one row into the next, so
+// rows cannot overlap.  Only offered where no mid-stream probability refresh can occur (<= 96 macroblocks).
+template <int G, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) encode_serial_kernel(const EncKernelParams P, int mb_index) {
+  constexpr int MPW = 32 / G;
+  WG_STAGE_TABLES(WARPS * 32);
+  const int warp = threadIdx.x >> 5;
+  encode_mb_group<G, false, false, true>(P, mb_index, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
 }
 
 // The whole mode search in ONE launch: persistent warps claim groups of 32/G macroblocks in wave order from a global

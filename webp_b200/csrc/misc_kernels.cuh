@@ -163,6 +163,26 @@ __global__ void dsp_pred4_kernel(int n, const uint8_t* ctx13, uint8_t* out) {  /
   pred4(mode, e, d);
   store16u8(out + 16 * (size_t)i, d);
 }
+// one 8-lane group per (block, mode): stages the context into a BPS-strided work buffer and runs the cooperative predictor
+__global__ void __launch_bounds__(128) dsp_pred_square_kernel(int n_tasks, int size, const uint8_t* ctx_px, uint8_t* out) {
+  __shared__ __align__(16) uint8_t s_buf[16][18 * BPS];
+  const int grp = threadIdx.x >> 3, gl = threadIdx.x & 7;
+  const int task = blockIdx.x * 16 + grp;
+  const bool active = task < n_tasks;
+  const int blk = active ? task / 7 : 0, mode = active ? task - blk * 7 : 0;
+  uint8_t* buf = s_buf[grp];
+  const int off = BPS + 8, cs = 1 + 2 * size;
+  const uint8_t* c = ctx_px + (size_t)blk * cs;
+  if (active) {
+    if (gl == 0) buf[off - BPS - 1] = c[0];
+    for (int i = gl; i < size; i += 8) { buf[off - BPS + i] = c[1 + i]; buf[off - 1 + i * BPS] = c[1 + size + i]; }
+  }
+  __syncwarp();
+  if (active) pred_square_coop<8>(gl, mode, buf, off, size);
+  __syncwarp();
+  if (active)
+    for (int i = gl; i < size * size; i += 8) out[(size_t)task * size * size + i] = buf[off + (i / size) * BPS + (i % size)];
+}
 __global__ void dsp_quantize_kernel(int n, const int16_t* in, SegQuant sq, int first, int16_t* out, int32_t* nz) {
   WG_TID; int c[16], q[16]; load16s16(in + 16 * (size_t)i, c); nz[i] = quantize_block(c, q, sq, first); store16s16(out + 16 * (size_t)i, q);
 }

@@ -78,7 +78,7 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens;
   PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false;
@@ -193,7 +193,7 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens,
+  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
@@ -253,7 +253,9 @@ static int validate_enc_options(wgpu_ctx* ctx, const wgpu_enc_options* o, int wi
   if (o->dither_amp < 0 || o->dither_amp > 256) FAIL(WGPU_ERR_INVALID, "webp: dithering amplitude out of range [0, 256]");
   // Method < 3: statLoop + serial encodeFrame semantics (non-RD decisions) -- built.  Method >= 3 on frames of fewer than
   // 4 macroblock rows takes the reference's serial RD path (probability refreshes feed the RD costs) -- not built yet.
-  if (o->method >= 3 && ((height + 15) >> 4) < 4) FAIL(WGPU_ERR_UNSUPPORTED, "Method >= 3 with height <= 48 takes the reference's serial RD path (not built yet)");
+  // Built only where no mid-stream probability refresh can occur (<= 96 macroblocks: encode_frame.go:24-40).
+  if (o->method >= 3 && ((height + 15) >> 4) < 4 && ((height + 15) >> 4) * ((width + 15) >> 4) > 96)
+    FAIL(WGPU_ERR_UNSUPPORTED, "Method >= 3 with height <= 48 and more than 96 macroblocks takes the reference's serial RD path with probability refreshes (not built yet)");
   return WGPU_OK;
 }
 
@@ -322,6 +324,24 @@ int launch_enc_fast_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {  // Met
     const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
     const unsigned grid = (unsigned)((tasks + per_cta - 1) / per_cta);
     wg::encode_fast_wave_kernel<G, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(P, w);
+    ctx->launches++;
+  }
+  return WGPU_OK;
+}
+// Serial RD path (Method >= 3, fewer than 4 macroblock rows): raster order, one launch per macroblock index over the batch.
+template <int G, int WARPS, int MINB>
+int launch_enc_serial(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
+  constexpr int per_cta = WARPS * (32 / G);
+  constexpr size_t smem = sizeof(wg::MBShared) * per_cta;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wg::encode_serial_kernel<G, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)((P.n_images + per_cta - 1) / per_cta);
+  for (int i = 0; i < P.mb_w * P.mb_h; ++i) {
+    wg::encode_serial_kernel<G, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(P, i);
     ctx->launches++;
   }
   return WGPU_OK;
@@ -453,7 +473,18 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.method = ctx->e_opt.method;
   P.max_i4_modes = ctx->e_opt.quality < 50 ? 2 : 3;  // getMaxI4RDModes (encode_parallel.go:931)
   P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
+  P.top_derr = nullptr; P.left_derr = nullptr;
   int rc;
+  if (ctx->e_opt.method >= 3 && mbh < 4) {  // useParallel == false (encode.go:1356)
+    RESERVE(ctx->derr, (size_t)n * (mbw + 1) * 4);
+    CK(cudaMemsetAsync(ctx->derr.p, 0, (size_t)n * (mbw + 1) * 4, ctx->stream));
+    P.top_derr = ctx->derr.as<int8_t>();
+    P.left_derr = ctx->derr.as<int8_t>() + (size_t)n * mbw * 4;
+    rc = launch_enc_serial<8, 4, 3>(ctx, P);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return WGPU_OK;
+  }
   if (ctx->e_opt.method < 3) {
     rc = launch_enc_fast_waves<8, 4, 3>(ctx, P);
     if (rc) return rc;
@@ -1097,6 +1128,16 @@ int wgpu_dsp_pred4_batch(wgpu_ctx* ctx, int n, const uint8_t* ctx13, uint8_t* ou
   DSP_IN(d_c, ctx13, (size_t)n * 13); DSP_OUT(d_out, uint8_t, (size_t)n * 160);
   wg::dsp_pred4_kernel<<<(unsigned)((n * 10 + 127) / 128), 128, 0, ctx->stream>>>(n * 10, d_c, d_out);
   DSP_END(d_out, out, (size_t)n * 160);
+  DSP_SYNC;
+}
+int wgpu_dsp_pred_square_batch(wgpu_ctx* ctx, int n, int size, const uint8_t* ctx_px, uint8_t* out) {
+  DSP_BEGIN;
+  (void)grid;
+  if (size != 16 && size != 8) FAIL(WGPU_ERR_INVALID, "dsp pred_square: size must be 16 or 8");
+  const size_t cs = 1 + 2 * (size_t)size;
+  DSP_IN(d_c, ctx_px, (size_t)n * cs); DSP_OUT(d_out, uint8_t, (size_t)n * 7 * size * size);
+  wg::dsp_pred_square_kernel<<<(unsigned)((n * 7 + 15) / 16), 128, 0, ctx->stream>>>(n * 7, size, d_c, d_out);
+  DSP_END(d_out, out, (size_t)n * 7 * size * size);
   DSP_SYNC;
 }
 static wg::SegQuant make_seg_quant(int dc_q, int ac_q, int type, int sharpen) {

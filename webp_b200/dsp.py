@@ -68,6 +68,14 @@ def PredLuma4Batch(ctx13, ctx=None):
     return out
 
 
+def PredSquareBatch(ctx_px, size, ctx=None):
+    """dsp.PredLuma16Direct (size 16) / PredChroma8Direct (size 8) (predict_lossy.go:27-181) for the seven modes:
+    ctx_px uint8 [n][1 + 2*size] = {tl, top[size], left[size]} -> uint8 [n][7][size][size]."""
+    ctx = _ctx(ctx); c = _c(ctx_px, np.uint8); n = c.shape[0]; out = np.empty((n, 7, size, size), np.uint8)
+    ctx.check(native.lib().wgpu_dsp_pred_square_batch(ctx.handle, n, size, c.ctypes.data, out.ctypes.data))
+    return out
+
+
 def QuantizeCoeffsBatch(coeffs, dc_q, ac_q, qtype, sharpen, first, ctx=None):
     """lossy.QuantizeCoeffs (internal/lossy/encode_quant.go:16) -> (levels int16 [n][16], nz int32 [n])."""
     ctx = _ctx(ctx); c = _c(coeffs, np.int16); n = c.shape[0]

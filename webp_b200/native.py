@@ -89,6 +89,7 @@ def lib():
         L.wgpu_dsp_sse4x4_batch.argtypes = [vp, C.c_int, u8p, u8p, i32p]
         L.wgpu_dsp_tdisto4x4_batch.argtypes = [vp, C.c_int, u8p, u8p, i32p]
         L.wgpu_dsp_pred4_batch.argtypes = [vp, C.c_int, u8p, u8p]
+        L.wgpu_dsp_pred_square_batch.argtypes = [vp, C.c_int, C.c_int, u8p, u8p]
         L.wgpu_dsp_quantize_batch.argtypes = [vp, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i16p, i32p]
         L.wgpu_dsp_trellis_batch.argtypes = [vp, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i16p, i32p]
         L.wgpu_dsp_token_cost_batch.argtypes = [vp, C.c_int, i16p, i32p, C.c_int, i32p, C.c_int, i32p]
