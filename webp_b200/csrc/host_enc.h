@@ -582,6 +582,36 @@ static inline int count_skips(const uint8_t* mb_hdr, int total) {
   return n;
 }
 
+// Device-coded route: the token partition arrives already boolean-coded (boolcode_kernel); the host emits partition 0
+// and writes RIFF(20) + frame header(10) around [partition 0][token partition] laid out in place at `dst`.
+static inline void emit_partition0_of(const FramePlan& fp, const uint8_t* mb_hdr, const uint8_t* segment_map, const uint8_t* proba /*[1056]*/,
+                                      std::vector<uint8_t>* part0) {
+  const int total = fp.mb_w * fp.mb_h;
+  const int num_skip = count_skips(mb_hdr, total);
+  const int skip_proba = num_skip > 0 ? (total - num_skip) * 255 / total : 0;
+  part0->reserve((size_t)total * 4 + 2048);
+  emit_partition0(fp, mb_hdr, segment_map, proba, num_skip, skip_proba, part0);
+}
+static inline size_t frame_file_size(size_t part0_size, size_t coded_size) {
+  const size_t payload = 10 + part0_size + coded_size;
+  return 20 + payload + (payload & 1);
+}
+static inline void write_frame_headers(const FramePlan& fp, uint8_t* dst, size_t part0_size, size_t coded_size) {
+  uint8_t* f = dst + 20;
+  const uint32_t tag = (1u << 4) | ((uint32_t)part0_size << 5);
+  f[0] = (uint8_t)tag; f[1] = (uint8_t)(tag >> 8); f[2] = (uint8_t)(tag >> 16);
+  f[3] = 0x9d; f[4] = 0x01; f[5] = 0x2a;
+  f[6] = (uint8_t)fp.width; f[7] = (uint8_t)((fp.width & 0x3fff) >> 8);
+  f[8] = (uint8_t)fp.height; f[9] = (uint8_t)((fp.height & 0x3fff) >> 8);
+  const uint32_t payload = (uint32_t)(10 + part0_size + coded_size);
+  if (payload & 1) dst[20 + payload] = 0;
+  const uint32_t riff_size = 4 + 8 + payload + (payload & 1);
+  memcpy(dst, "RIFF", 4);
+  dst[4] = (uint8_t)riff_size; dst[5] = (uint8_t)(riff_size >> 8); dst[6] = (uint8_t)(riff_size >> 16); dst[7] = (uint8_t)(riff_size >> 24);
+  memcpy(dst + 8, "WEBPVP8 ", 8);
+  dst[16] = (uint8_t)payload; dst[17] = (uint8_t)(payload >> 8); dst[18] = (uint8_t)(payload >> 16); dst[19] = (uint8_t)(payload >> 24);
+}
+
 // Boolean-code two independent token streams in lock step: the coder is a serial dependency chain of ~20 cycles per
 // token, so interleaving two images in one thread nearly doubles throughput (measured 7.4 -> 3.9 ns/token).
 static inline void code_token_streams(const uint16_t* ta, size_t na, std::vector<uint8_t>* oa, const uint16_t* tb, size_t nb,

@@ -211,4 +211,142 @@ __global__ void __launch_bounds__(352) optimize_proba_kernel(const ProbaParams P
   }
 }
 
+// Boolean coder on the device: the token partition of one image per warp.  Restates VP8BitWriter PutBit / Flush / Finish
+// (internal/bitio/writer_bool.go:58-104,140-150) over the flat (bit | prob << 8) token array emitted above.  The coder is
+// a serial dependency chain per partition (range -> split -> renormalise), so one lane codes while the warp streams the
+// tokens through shared memory with 128-bit loads; parallelism comes from the batch (one warp per image partition), and
+// the kernel is small enough (<= 32 registers, 2 KB shared) to run beside the next batch's mode-search waves.  The carry
+// of Flush (buf[pos-1]++) is applied to a byte held back in a register instead of a read-modify-write in HBM.
+struct BoolCodeParams {
+  const uint16_t* tokens;              // compact token buffer
+  const unsigned long long* img_base;  // [n] token offset of each image (multiple of 8 tokens)
+  const unsigned long long* img_total; // [n] token count
+  uint8_t* out;                        // coded partitions
+  const unsigned long long* out_base;  // [n] byte offset of each image's partition in `out` (capacity >= total + 16)
+  unsigned int* out_size;              // [n] coded size in bytes
+  int n_images;
+};
+__global__ void __launch_bounds__(64) boolcode_kernel(const BoolCodeParams P) {
+  // Two warps per partition, pipelined over 512-token chunks through shared memory:
+  //   warp 0 (range warp): streams the tokens in (128-bit loads, all lanes), then lane 0 runs the range recurrence
+  //                        R -> split -> sub-range -> renormalise and leaves (value increment, shift) per token;
+  //   warp 1 (byte warp):  lane 0 folds those into the pending value, four tokens per step, and writes the bytes
+  //                        (Flush with its carry / 0xff run), several per step when due.
+  // The range recurrence is the irreducible serial chain (IMAD -> SHF -> IADD -> FLO -> SHF per token); everything else is
+  // kept off it.  Deferring Flush by up to four tokens is exact: value is a big-number accumulator whose carries ripple
+  // inside the 64-bit register exactly as Flush would have applied them to the held-back byte.
+  constexpr int CHUNK = 512;
+  __shared__ uint4 s_tok[CHUNK / 8];
+  __shared__ uint16_t s_fin[20];
+  __shared__ __align__(16) uint16_t s_ev[2][CHUNK];  // per token: bits 0-8 value increment (0 or split + 1), bits 12-14 shift
+  const int img = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long total = P.img_total[img];
+  const uint4* tk = reinterpret_cast<const uint4*>(P.tokens + P.img_base[img]);
+  uint8_t* out = P.out + P.out_base[img];
+  const long long n_chunks = (long long)((total + CHUNK - 1) / CHUNK);
+  // range warp state: R = range + 1 in [128, 255]
+  int R = 255;
+  uint4 r0 = make_uint4(0, 0, 0, 0), r1v = r0;
+  if (warp == 0 && n_chunks > 0) { r0 = __ldg(tk + lane); r1v = __ldg(tk + 32 + lane); }
+  auto step = [&](uint32_t tok) -> uint32_t {  // one PutBit on the range side; returns the event for the byte side
+    const int prob = (int)(tok >> 8);
+    const bool bit = tok & 1u;
+    // split = ((R - 1) * prob) >> 8; sub-range r + 1 = bit ? R - 1 - split : split + 1.  With sx = bit ? ~split : split
+    // (one IMAD + arithmetic shift, since ~(t >> 8) == (~t) >> 8): r + 1 = (bit ? R : 1) + sx.
+    const int ma = bit ? -prob : prob, mc = bit ? prob - 1 : -prob;
+    const int sx = (R * ma + mc) >> 8;
+    const int r1 = (bit ? R : 1) + sx;
+    const int k = 31 - __clz(r1);  // kNorm[r] = 7 - k, kNewRange[r] + 1 = r1 << (7 - k)
+    R = (r1 << 7) >> k;
+    return (uint32_t)((bit ? -sx : 0) | ((7 - k) << 12));
+  };
+  // byte warp state
+  unsigned long long value = 0;
+  int run = 0, nb_bits = -8, last = -1;
+  unsigned int pos = 0;
+  auto flush = [&]() {
+    const int s = 8 + nb_bits;
+    const int bits = (int)(value >> s);
+    value -= (unsigned long long)bits << s;
+    nb_bits -= 8;
+    if ((bits & 0xff) != 0xff) {
+      const int carry = (bits >> 8) & 1;
+      if (last >= 0) out[pos++] = (uint8_t)(last + carry);
+      if (run > 0) {
+        const uint8_t fill = carry ? 0x00 : 0xff;
+#pragma unroll 1
+        for (; run > 0; --run) out[pos++] = fill;
+      }
+      last = bits & 0xff;
+    } else {
+      ++run;
+    }
+  };
+  auto emit = [&](uint32_t ev) {  // PutBit's value side: value += increment; value <<= shift; nbBits += shift; Flush when > 0
+    const int shift = (int)(ev >> 12);
+    value = (value + (ev & 0x1ffu)) << shift;
+    nb_bits += shift;
+    if (nb_bits > 0) flush();
+  };
+  for (long long c = 0; c <= n_chunks; ++c) {
+    if (warp == 0) {
+      if (c < n_chunks) {
+        s_tok[lane] = r0; s_tok[32 + lane] = r1v;
+        if (c + 1 < n_chunks) { r0 = __ldg(tk + (c + 1) * (CHUNK / 8) + lane); r1v = __ldg(tk + (c + 1) * (CHUNK / 8) + 32 + lane); }
+        __syncwarp();
+        if (lane == 0) {
+          const unsigned long long left = total - (unsigned long long)c * CHUNK;
+          const int cnt = left < (unsigned long long)CHUNK ? (int)left : CHUNK;
+          const uint2* t2 = reinterpret_cast<const uint2*>(s_tok);
+          uint2* ev2 = reinterpret_cast<uint2*>(s_ev[c & 1]);
+          const int groups = cnt >> 2;
+          uint2 nxt = t2[0];
+#pragma unroll 1
+          for (int g = 0; g < groups; ++g) {
+            const uint2 cur = nxt;
+            nxt = t2[(g + 1) & (CHUNK / 4 - 1)];  // one group ahead: the shared-memory latency stays off the chain
+            const uint32_t e0 = step(cur.x & 0xffffu), e1 = step(cur.x >> 16), e2 = step(cur.y & 0xffffu), e3 = step(cur.y >> 16);
+            ev2[g] = make_uint2(e0 | (e1 << 16), e2 | (e3 << 16));
+          }
+          const uint16_t* t = reinterpret_cast<const uint16_t*>(s_tok);
+          for (int i = groups * 4; i < cnt; ++i) s_ev[c & 1][i] = (uint16_t)step(t[i]);
+        }
+        __syncwarp();
+      } else if (lane == 0) {
+        // Finish = PutBits(0, 9 - nbBits): up to 17 zero bits at probability 128, whose shifts still depend on the range
+        for (int i = 0; i < 17; ++i) s_fin[i] = (uint16_t)step(128u << 8);
+      }
+    } else if (c > 0 && lane == 0) {
+      const unsigned long long left = total - (unsigned long long)(c - 1) * CHUNK;
+      const int cnt = left < (unsigned long long)CHUNK ? (int)left : CHUNK;
+      const uint2* ev2 = reinterpret_cast<const uint2*>(s_ev[(c - 1) & 1]);
+      const int groups = cnt >> 2;
+      uint2 nxt = ev2[0];
+#pragma unroll 1
+      for (int g = 0; g < groups; ++g) {
+        const uint2 cur = nxt;
+        nxt = ev2[(g + 1) & (CHUNK / 4 - 1)];
+        // ((((v + a0) << s0) + a1) << s1 ...) == (v << S0) + (a0 << S0) + (a1 << S1) + (a2 << S2) + (a3 << S3), Sj = sj + ... + s3
+        const int s3 = (int)(cur.y >> 28), s2 = s3 + (int)((cur.y >> 12) & 7u), s1 = s2 + (int)(cur.x >> 28), s0 = s1 + (int)((cur.x >> 12) & 7u);
+        const unsigned long long add = ((unsigned long long)(cur.x & 0x1ffu) << s0) + ((unsigned long long)((cur.x >> 16) & 0x1ffu) << s1) +
+                                       ((unsigned long long)(cur.y & 0x1ffu) << s2) + ((unsigned long long)((cur.y >> 16) & 0x1ffu) << s3);
+        value = (value << s0) + add;
+        nb_bits += s0;
+        while (nb_bits > 0) flush();
+      }
+      const uint16_t* ev = s_ev[(c - 1) & 1];
+      for (int i = groups * 4; i < cnt; ++i) emit(ev[i]);
+    }
+    __syncthreads();
+  }
+  if (warp == 1 && lane == 0) {
+    const int n_fin = 9 - nb_bits;  // the closing bits were prepared by the range warp in the last pipeline step
+    for (int i = 0; i < n_fin; ++i) emit(s_fin[i]);
+    nb_bits = 0;
+    flush();
+    if (last >= 0) out[pos++] = (uint8_t)last;
+    P.out_size[img] = pos;
+  }
+}
+
 }  // namespace wg

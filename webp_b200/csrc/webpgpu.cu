@@ -70,7 +70,7 @@ void parallel_for(int n, int threads, F f) {
 struct wgpu_ctx {
   int dev = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_hdr = nullptr;
   std::string err;
   uint64_t launches = 0;
   int host_threads = 0;
@@ -78,8 +78,8 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens;
-  PinBuf h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size;
+  PinBuf h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false;
   int dither_w = 0, dither_h = 0, dither_amp_cached = 0;  // what the device dither tables currently hold
@@ -147,6 +147,7 @@ int wgpu_ctx_create(int device_ordinal, wgpu_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_hdr, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   // tables
   static uint16_t i4costs[1000];
   wgh::compute_i4_costs(i4costs);
@@ -193,18 +194,19 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens,
+  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
                   &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
                   &ctx->m_sse, &ctx->m_ssim};
   for (DevBuf* b : db) b->release();
-  PinBuf* pb[] = {&ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
+  PinBuf* pb[] = {&ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
                   &ctx->hd_meta, &ctx->hd_ftype, &ctx->hd_planes, &ctx->hd_nrgba};
   for (PinBuf* b : pb) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_hdr) cudaEventDestroy(ctx->ev_hdr);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -511,7 +513,8 @@ static int enc_reserve(wgpu_ctx* ctx) {
   RESERVE(ctx->stats, n * wg::STATS_SIZE * 4); RESERVE(ctx->h_stats, n * wg::STATS_SIZE * 4);
   RESERVE(ctx->proba, n * 1056); RESERVE(ctx->h_proba, n * 1056);
   RESERVE(ctx->mb_tokens, n * nmb * 4); RESERVE(ctx->mb_offset, n * nmb * 8);
-  RESERVE(ctx->img_total, n * 8); RESERVE(ctx->img_base, n * 8); RESERVE(ctx->h_totals, n * 8); RESERVE(ctx->h_bases, n * 8);
+  RESERVE(ctx->img_total, n * 8); RESERVE(ctx->img_base, 2 * n * 8); RESERVE(ctx->h_totals, n * 8); RESERVE(ctx->h_bases, 2 * n * 8);
+  RESERVE(ctx->coded_size, n * 4); RESERVE(ctx->h_coded_size, n * 4);
   RESERVE(ctx->h_alpha, n * nmb); RESERVE(ctx->h_uv_alpha, n * nmb); RESERVE(ctx->h_segment, n * nmb);
   RESERVE(ctx->h_params, n * sizeof(wg::ImageParams));
   return WGPU_OK;
@@ -680,54 +683,62 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
   std::atomic<int> too_small(0);
   const double t0 = now_ms();
   if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3) {
-    // ---- single partition: tokens are generated on the GPU, the host only boolean-codes flat arrays
+    // ---- single partition: tokens are generated AND boolean-coded on the GPU (token_kernel, boolcode_kernel); the host
+    // emits partition 0 (modes, a few bits per macroblock) while the coder runs, then lays the frames out
     CK(cudaStreamSynchronize(ctx->stream));  // waves + token pre-pass done, per-image totals on the host
     const double t1 = now_ms();
     const unsigned long long* totals = ctx->h_totals.as<unsigned long long>();
-    unsigned long long* bases = ctx->h_bases.as<unsigned long long>();
-    unsigned long long all = 0;
-    for (size_t i = 0; i < n; ++i) { bases[i] = all; all += totals[i]; }
-    RESERVE(ctx->tokens, (size_t)(all + 8) * 2);
-    RESERVE(ctx->h_tokens, (size_t)(all + 8) * 2);
-    CK(cudaMemcpyAsync(ctx->img_base.p, bases, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long* bases = ctx->h_bases.as<unsigned long long>();  // [0, n): token offsets, [n, 2n): coded byte offsets
+    unsigned long long all = 0, oall = 0;
+    for (size_t i = 0; i < n; ++i) {
+      bases[i] = all; all += (totals[i] + 7) & ~7ull;                    // 128-bit aligned token runs
+      bases[n + i] = oall; oall += (totals[i] + 16 + 15) & ~15ull;        // <= 7 bits out per token + the closing flush
+    }
+    RESERVE(ctx->tokens, (size_t)(all + 512) * 2);  // the coder stages whole 512-token chunks
+    RESERVE(ctx->coded, (size_t)oall);
+    CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_proba.p, ctx->proba.p, n * 1056, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_hdr, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->img_base.p, bases, 2 * n * 8, cudaMemcpyHostToDevice, ctx->stream));
     const wg::TokenParams T = token_params(ctx);
     wg::token_kernel<true><<<(unsigned)((n * nmb + 15) / 16), 128, 0, ctx->stream>>>(T);
     ctx->launches++;
+    wg::BoolCodeParams B;
+    B.tokens = ctx->tokens.as<uint16_t>(); B.img_base = ctx->img_base.as<unsigned long long>(); B.img_total = ctx->img_total.as<unsigned long long>();
+    B.out = ctx->coded.as<uint8_t>(); B.out_base = ctx->img_base.as<unsigned long long>() + n; B.out_size = ctx->coded_size.as<unsigned int>();
+    B.n_images = (int)n;
+    wg::boolcode_kernel<<<(unsigned)n, 64, 0, ctx->stream>>>(B);
+    ctx->launches++;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_proba.p, ctx->proba.p, n * 1056, cudaMemcpyDeviceToHost, ctx->stream));
-    if (all) CK(cudaMemcpyAsync(ctx->h_tokens.p, ctx->tokens.p, (size_t)all * 2, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev_hdr));
     const double t2 = now_ms();
-    // pair images of similar length (longest first) so two coders run interleaved in each task
-    std::vector<int> order(n);
-    for (size_t i = 0; i < n; ++i) order[i] = (int)i;
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return totals[a] > totals[b] || (totals[a] == totals[b] && a < b); });
-    const int pairs = (int)((n + 1) / 2);
-    std::vector<std::vector<uint8_t>> coded(n);
-    parallel_for(pairs, threads_of(ctx), [&](int p) {
-      const int ia = order[2 * p], ib = (size_t)(2 * p + 1) < n ? order[2 * p + 1] : -1;
-      coded[ia].reserve((size_t)totals[ia] / 4 + 4096);
-      if (ib >= 0) coded[ib].reserve((size_t)totals[ib] / 4 + 4096);
-      wgh::code_token_streams(ctx->h_tokens.as<uint16_t>() + bases[ia], (size_t)totals[ia], &coded[ia],
-                              ib >= 0 ? ctx->h_tokens.as<uint16_t>() + bases[ib] : nullptr, ib >= 0 ? (size_t)totals[ib] : 0,
-                              ib >= 0 ? &coded[ib] : nullptr);
-      for (int k = 0; k < 2; ++k) {
-        const int i = k == 0 ? ia : ib;
-        if (i < 0) continue;
-        std::vector<uint8_t> riff;
-        riff.reserve(coded[i].size() + nmb * 4 + 4096);
-        wgh::assemble_frame_tokens(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_segment.as<uint8_t>() + (size_t)i * nmb,
-                                   ctx->h_proba.as<uint8_t>() + (size_t)i * 1056, coded[i], &riff);
-        out_sizes[i] = riff.size();
-        if (riff.size() > out_stride) { too_small.store(1); continue; }
-        memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
-        std::vector<uint8_t>().swap(coded[i]);
-      }
+    std::vector<std::vector<uint8_t>> part0(n);
+    parallel_for((int)n, threads_of(ctx), [&](int i) {
+      wgh::emit_partition0_of(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_segment.as<uint8_t>() + (size_t)i * nmb,
+                              ctx->h_proba.as<uint8_t>() + (size_t)i * 1056, &part0[i]);
     });
+    const double t3 = now_ms();
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double t4 = now_ms();
+    const unsigned int* csz = ctx->h_coded_size.as<unsigned int>();
+    for (size_t i = 0; i < n; ++i) {  // token partitions go straight to their place in the caller's buffer
+      out_sizes[i] = wgh::frame_file_size(part0[i].size(), csz[i]);
+      if (out_sizes[i] > out_stride) { too_small.store(1); continue; }
+      if (csz[i])
+        CK(cudaMemcpyAsync(out + i * out_stride + 30 + part0[i].size(), ctx->coded.as<uint8_t>() + bases[n + i], csz[i], cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    parallel_for((int)n, threads_of(ctx), [&](int i) {
+      if (out_sizes[i] > out_stride) return;
+      uint8_t* dst = out + (size_t)i * out_stride;
+      memcpy(dst + 30, part0[i].data(), part0[i].size());
+      wgh::write_frame_headers(ctx->plans[i], dst, part0[i].size(), csz[i]);
+    });
+    CK(cudaStreamSynchronize(ctx->stream));
     if (trace_on())
-      fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, token emit + D2H %.2f ms (%.1f MB tokens), host code %.2f ms (%d threads)\n", t1 - t0,
-              t2 - t1, (double)all * 2 / 1e6, now_ms() - t2, threads_of(ctx));
+      fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, hdr D2H %.2f ms, partition 0 on host %.2f ms (%d threads), wait coder %.2f ms (%.1f M tokens, longest partition %.2f M), "
+              "frames D2H %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, threads_of(ctx), t4 - t3, (double)all / 1e6,
+              (double)*std::max_element(totals, totals + n) / 1e6, now_ms() - t4);
   } else {
     // ---- multi-partition and Method < 3: levels + statistics come back, the host walks them
     RESERVE(ctx->h_coeffs, n * nmb * 800);
