@@ -117,6 +117,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (BASELINE configs[1]: 256)")
     ap.add_argument("--e2e-workers", type=int, default=2, help="contexts per GPU used by the e2e leg (host coding of one batch overlaps the GPU work of the next)")
+    ap.add_argument("--finish-slots", type=int, default=1, help="how many contexts may be in their finish stage at once")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads per context (default: cores / ranks on this node)")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -149,7 +151,7 @@ def main():
 
     L = native.lib()
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    host_threads = max(1, (os.cpu_count() or 1) // max(1, local_world))
+    host_threads = args.host_threads or max(1, (os.cpu_count() or 1) // max(1, local_world))
     ctx = native.Context(local, host_threads=host_threads)
     n, K = args.batch, args.steps
     px_step = n * W * H
@@ -159,7 +161,7 @@ def main():
     opt = native.EncOptions()
     L.wgpu_enc_options_default(opt, 75)
 
-    gpu_stage, host_stage = threading.Lock(), threading.Lock()
+    upload_stage, gpu_stage, host_stage = threading.Lock(), threading.Lock(), threading.BoundedSemaphore(max(1, args.finish_slots))
 
     class Worker:
         """One wgpu_ctx + its own pinned input/output staging.  Two workers per GPU let the host-side entropy coding of
@@ -180,8 +182,10 @@ def main():
             """wgpu_encode_batch spelled as its three public stages so that two workers pipeline: one batch is in its GPU
             stage (H2D + kernels) while the previous one is in its host stage (D2H + token/bool coding)."""
             h = self.ctx.handle
-            with gpu_stage:
+            with upload_stage:  # H2D of this batch rides under the kernels of the batch before it
                 self.ctx.check(L.wgpu_enc_upload(h, self.h_in, n, W, H, W * 4, W * H * 4))
+                self.ctx.check(L.wgpu_sync(h))
+            with gpu_stage:
                 self.ctx.check(L.wgpu_enc_device(h, C.byref(opt)))
                 self.ctx.check(L.wgpu_sync(h))
             with host_stage:

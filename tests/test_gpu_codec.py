@@ -126,6 +126,34 @@ def test_encode_bytes_and_decisions(oracle, gpu_ctx, w, h, idxs, kw):
         assert files[k] == exp, "image %d: bitstream differs (%d vs %d bytes)" % (i, len(files[k]), len(exp))
 
 
+@pytest.mark.parametrize("device_coder", ["0", "1"])
+@pytest.mark.parametrize("w,h,idxs,kw", [(128, 96, [0, 1, 2], {}), (768, 576, [1, 2], {}), (100, 70, [2], dict(Quality=98, Method=6)),
+                                          (64, 48, [0, 1], {}), (320, 240, [0, 1, 2, 4, 5, 7, 8], dict(Quality=20))])
+def test_token_partition_coder_routes(oracle, gpu_ctx, monkeypatch, device_coder, w, h, idxs, kw):
+    """The token partition is boolean-coded either on the host (code_token_streams) or on the GPU (boolcode_kernel:
+    VP8BitWriter PutBit / Flush / Finish, internal/bitio/writer_bool.go:58-150); both must give the oracle's bytes."""
+    monkeypatch.setenv("WGPU_DEVICE_CODER", device_coder)
+    o = _opts(**kw)
+    imgs = np.stack([oracle.synth_image(w, h, i) for i in idxs])
+    files = webp_b200.EncodeBatch(imgs, o, gpu_ctx)
+    for k in range(len(idxs)):
+        assert files[k] == oracle.encode(imgs[k], _ocfg(oracle, o))
+
+
+def test_device_coder_flat_and_noise_images(oracle, gpu_ctx, monkeypatch):
+    # all-skip frames (zero tokens: only the closing flush) and dense noise (long 0xff runs / carries are likelier)
+    monkeypatch.setenv("WGPU_DEVICE_CODER", "1")
+    rng = np.random.RandomState(5)
+    flat = np.full((64, 64, 4), 255, np.uint8)
+    noise = rng.randint(0, 256, (64, 64, 4)).astype(np.uint8); noise[..., 3] = 255
+    imgs = np.stack([flat, noise])
+    for q in (75, 100):
+        o = _opts(Quality=q)
+        files = webp_b200.EncodeBatch(imgs, o, gpu_ctx)
+        for k in range(2):
+            assert files[k] == oracle.encode(imgs[k], _ocfg(oracle, o))
+
+
 def test_analyze_search_route_matches_enc_device(oracle, gpu_ctx):
     """The Go-shim route: GPU analysis -> host segmentation (here: taken from the oracle) -> GPU mode
     search with host-supplied SegmentInfo -> per-MB results identical to the oracle's mbInfo."""

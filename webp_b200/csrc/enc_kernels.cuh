@@ -1120,6 +1120,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const Enc
   encode_mb_group<G, false, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
 }
 
+// Same kernel under an explicit register cap instead of a minimum-CTAs bound: leaves register-file room for the boolean
+// coder blocks of the previous batch to sit beside three mode-search CTAs on every SM.
+template <int G, int WARPS, int NREG>
+__global__ void __maxnreg__(NREG) encode_wave_kernel_nr(const EncKernelParams P, int wave) {
+  constexpr int MPW = 32 / G;
+  WG_STAGE_TABLES(WARPS * 32);
+  const int warp = threadIdx.x >> 5;
+  encode_mb_group<G, false, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
+}
+
 // Method < 3 (the reference's non-RD decisions, serial-path semantics): same wavefront, lighter body.
 template <int G, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) encode_fast_wave_kernel(const EncKernelParams P, int wave) {

@@ -108,6 +108,17 @@ struct wgpu_ctx {
   } while (0)
 #define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
 
+static int threads_of(const wgpu_ctx* ctx);
+// Where the token partition is boolean-coded.  The coder is one serial chain per partition.  On the GPU the batch's
+// partitions run one per lane on a few dedicated SMs and the batch waits for its longest partition (~40 ns per token); on
+// the host a thread codes ~4 ns per token.  With plenty of host threads per context and few partitions the host wins; when
+// the ranks of one box share its cores (8 GPUs, 2 threads each) the GPU coder keeps the throughput from collapsing
+// (measured at 2 threads per context: 2365 vs 443 Mpix/s).  WGPU_DEVICE_CODER=0/1 forces either.
+static bool device_coder_wanted(const wgpu_ctx* ctx, size_t n_images) {
+  const char* e = getenv("WGPU_DEVICE_CODER");  // read per call: tests flip it
+  if (e && *e) return atoi(e) != 0;
+  return n_images >= 32 && threads_of(ctx) <= 8;
+}
 static int threads_of(const wgpu_ctx* ctx) {
   int t = ctx->host_threads;
   if (t <= 0) t = (int)std::thread::hardware_concurrency();
@@ -292,24 +303,24 @@ int wave_rows(int wave, int mb_w, int mb_h) {
 }
 // Launch configurations of the mode-search kernel: lanes per macroblock (G), warps per CTA, min CTAs per SM (register cap).
 // WGPU_ENC_VARIANT picks one at run time for tuning; the default is the measured best.
-template <int G, int WARPS, int MINB>
-int launch_enc_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
+template <int G, int WARPS>
+int launch_enc_waves_fn(wgpu_ctx* ctx, const wg::EncKernelParams& P, void (*kernel)(const wg::EncKernelParams, int)) {
   constexpr int per_cta = WARPS * (32 / G);
   constexpr size_t smem = sizeof(wg::MBShared) * per_cta;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wg::encode_wave_kernel<G, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
-    attr_set = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
   const int waves = P.mb_w + 2 * (P.mb_h - 1);
   for (int w = 0; w < waves; ++w) {
     const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
     const unsigned grid = (unsigned)((tasks + per_cta - 1) / per_cta);
-    wg::encode_wave_kernel<G, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(P, w);
+    kernel<<<grid, WARPS * 32, smem, ctx->stream>>>(P, w);
     ctx->launches++;
   }
   return WGPU_OK;
+}
+template <int G, int WARPS, int MINB>
+int launch_enc_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
+  return launch_enc_waves_fn<G, WARPS>(ctx, P, wg::encode_wave_kernel<G, WARPS, MINB>);
 }
 template <int G, int WARPS, int MINB>
 int launch_enc_fast_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {  // Method < 3: non-RD body, same wave schedule
@@ -496,6 +507,8 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   switch (enc_variant()) {
     case 1: rc = launch_enc_waves<8, 4, 2>(ctx, P); break;   // no register cap, 2 CTAs/SM
     case 2: rc = launch_enc_persistent<8, 4, 3>(ctx, P); break;  // one persistent launch, dataflow scheduling
+    case 3: rc = launch_enc_waves_fn<8, 4>(ctx, P, wg::encode_wave_kernel_nr<8, 4, 152>); break;  // explicit register caps:
+    case 4: rc = launch_enc_waves_fn<8, 4>(ctx, P, wg::encode_wave_kernel_nr<8, 4, 144>); break;  // same speed, no spills (measured)
     default: rc = launch_enc_waves<8, 4, 3>(ctx, P); break;  // 168 regs, 3 CTAs/SM = 48 macroblocks/SM (measured best)
   }
   if (rc) return rc;
@@ -513,7 +526,7 @@ static int enc_reserve(wgpu_ctx* ctx) {
   RESERVE(ctx->stats, n * wg::STATS_SIZE * 4); RESERVE(ctx->h_stats, n * wg::STATS_SIZE * 4);
   RESERVE(ctx->proba, n * 1056); RESERVE(ctx->h_proba, n * 1056);
   RESERVE(ctx->mb_tokens, n * nmb * 4); RESERVE(ctx->mb_offset, n * nmb * 8);
-  RESERVE(ctx->img_total, n * 8); RESERVE(ctx->img_base, 2 * n * 8); RESERVE(ctx->h_totals, n * 8); RESERVE(ctx->h_bases, 2 * n * 8);
+  RESERVE(ctx->img_total, n * 8); RESERVE(ctx->img_base, 3 * n * 8); RESERVE(ctx->h_totals, n * 8); RESERVE(ctx->h_bases, 3 * n * 8);
   RESERVE(ctx->coded_size, n * 4); RESERVE(ctx->h_coded_size, n * 4);
   RESERVE(ctx->h_alpha, n * nmb); RESERVE(ctx->h_uv_alpha, n * nmb); RESERVE(ctx->h_segment, n * nmb);
   RESERVE(ctx->h_params, n * sizeof(wg::ImageParams));
@@ -682,19 +695,19 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
   RESERVE(ctx->h_hdr, n * nmb * 48);
   std::atomic<int> too_small(0);
   const double t0 = now_ms();
-  if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3) {
+  if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3 && device_coder_wanted(ctx, n)) {
     // ---- single partition: tokens are generated AND boolean-coded on the GPU (token_kernel, boolcode_kernel); the host
     // emits partition 0 (modes, a few bits per macroblock) while the coder runs, then lays the frames out
     CK(cudaStreamSynchronize(ctx->stream));  // waves + token pre-pass done, per-image totals on the host
     const double t1 = now_ms();
     const unsigned long long* totals = ctx->h_totals.as<unsigned long long>();
-    unsigned long long* bases = ctx->h_bases.as<unsigned long long>();  // [0, n): token offsets, [n, 2n): coded byte offsets
+    unsigned long long* bases = ctx->h_bases.as<unsigned long long>();  // [0, n): token offsets, [n, 2n): coded byte offsets, [2n, ..): order
     unsigned long long all = 0, oall = 0;
     for (size_t i = 0; i < n; ++i) {
       bases[i] = all; all += (totals[i] + 7) & ~7ull;                    // 128-bit aligned token runs
       bases[n + i] = oall; oall += (totals[i] + 16 + 15) & ~15ull;        // <= 7 bits out per token + the closing flush
     }
-    RESERVE(ctx->tokens, (size_t)(all + 512) * 2);  // the coder stages whole 512-token chunks
+    RESERVE(ctx->tokens, (size_t)(all + 512) * 2);
     RESERVE(ctx->coded, (size_t)oall);
     CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_proba.p, ctx->proba.p, n * 1056, cudaMemcpyDeviceToHost, ctx->stream));
@@ -707,7 +720,27 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     B.tokens = ctx->tokens.as<uint16_t>(); B.img_base = ctx->img_base.as<unsigned long long>(); B.img_total = ctx->img_total.as<unsigned long long>();
     B.out = ctx->coded.as<uint8_t>(); B.out_base = ctx->img_base.as<unsigned long long>() + n; B.out_size = ctx->coded_size.as<unsigned int>();
     B.n_images = (int)n;
-    wg::boolcode_kernel<<<(unsigned)n, 64, 0, ctx->stream>>>(B);
+    {
+      // The coder runs for 100-200 ms (the serial chain of the longest partition) beside the NEXT batch's mode-search waves
+      // (another context's stream).  Its blocks (32 partitions each, one per lane) ask for 200 KB of shared memory: that
+      // forces the same L1/shared split as the mode-search CTAs (a kernel with a small footprint gets a different split from
+      // the driver and cannot share an SM with them at all -- it then piles onto the few free SMs and stalls both: 540 ms vs
+      // 140 ms), and it gives each block an SM of its own, where the tight coder loops keep the instruction cache (216 ms
+      // vs 280 ms beside mode-search warps).  Cost to the waves: 8 of 148 SMs while the coder runs.
+      static size_t coder_smem = 0;
+      if (!coder_smem) {
+        coder_smem = 200 * 1024;
+        if (getenv("WGPU_CODER_DYNSMEM")) coder_smem = (size_t)atoi(getenv("WGPU_CODER_DYNSMEM"));  // experiment knob
+        coder_smem = std::max(coder_smem, (size_t)wg::BOOLCODE_SMEM);
+        CK(cudaFuncSetAttribute(wg::boolcode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coder_smem));
+      }
+      int* order = reinterpret_cast<int*>(bases + 2 * n);  // longest first, so that the lanes of a warp finish together
+      for (size_t i = 0; i < n; ++i) order[i] = (int)i;
+      std::sort(order, order + n, [&](int a, int b) { return totals[a] > totals[b] || (totals[a] == totals[b] && a < b); });
+      CK(cudaMemcpyAsync(ctx->img_base.as<unsigned long long>() + 2 * n, order, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+      B.order = reinterpret_cast<const int*>(ctx->img_base.as<unsigned long long>() + 2 * n);
+      wg::boolcode_kernel<<<(unsigned)((n + 31) / 32), 64, coder_smem, ctx->stream>>>(B);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -739,6 +772,55 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, hdr D2H %.2f ms, partition 0 on host %.2f ms (%d threads), wait coder %.2f ms (%.1f M tokens, longest partition %.2f M), "
               "frames D2H %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, threads_of(ctx), t4 - t3, (double)all / 1e6,
               (double)*std::max_element(totals, totals + n) / 1e6, now_ms() - t4);
+  } else if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3) {
+    // ---- single partition: tokens are generated on the GPU, the host only boolean-codes flat arrays
+    CK(cudaStreamSynchronize(ctx->stream));  // waves + token pre-pass done, per-image totals on the host
+    const double t1 = now_ms();
+    const unsigned long long* totals = ctx->h_totals.as<unsigned long long>();
+    unsigned long long* bases = ctx->h_bases.as<unsigned long long>();
+    unsigned long long all = 0;
+    for (size_t i = 0; i < n; ++i) { bases[i] = all; all += totals[i]; }
+    RESERVE(ctx->tokens, (size_t)(all + 8) * 2);
+    RESERVE(ctx->h_tokens, (size_t)(all + 8) * 2);
+    CK(cudaMemcpyAsync(ctx->img_base.p, bases, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const wg::TokenParams T = token_params(ctx);
+    wg::token_kernel<true><<<(unsigned)((n * nmb + 15) / 16), 128, 0, ctx->stream>>>(T);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_proba.p, ctx->proba.p, n * 1056, cudaMemcpyDeviceToHost, ctx->stream));
+    if (all) CK(cudaMemcpyAsync(ctx->h_tokens.p, ctx->tokens.p, (size_t)all * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double t2 = now_ms();
+    // pair images of similar length (longest first) so two coders run interleaved in each task
+    std::vector<int> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return totals[a] > totals[b] || (totals[a] == totals[b] && a < b); });
+    const int pairs = (int)((n + 1) / 2);
+    std::vector<std::vector<uint8_t>> coded(n);
+    parallel_for(pairs, threads_of(ctx), [&](int p) {
+      const int ia = order[2 * p], ib = (size_t)(2 * p + 1) < n ? order[2 * p + 1] : -1;
+      coded[ia].reserve((size_t)totals[ia] / 4 + 4096);
+      if (ib >= 0) coded[ib].reserve((size_t)totals[ib] / 4 + 4096);
+      wgh::code_token_streams(ctx->h_tokens.as<uint16_t>() + bases[ia], (size_t)totals[ia], &coded[ia],
+                              ib >= 0 ? ctx->h_tokens.as<uint16_t>() + bases[ib] : nullptr, ib >= 0 ? (size_t)totals[ib] : 0,
+                              ib >= 0 ? &coded[ib] : nullptr);
+      for (int k = 0; k < 2; ++k) {
+        const int i = k == 0 ? ia : ib;
+        if (i < 0) continue;
+        std::vector<uint8_t> riff;
+        riff.reserve(coded[i].size() + nmb * 4 + 4096);
+        wgh::assemble_frame_tokens(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_segment.as<uint8_t>() + (size_t)i * nmb,
+                                   ctx->h_proba.as<uint8_t>() + (size_t)i * 1056, coded[i], &riff);
+        out_sizes[i] = riff.size();
+        if (riff.size() > out_stride) { too_small.store(1); continue; }
+        memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
+        std::vector<uint8_t>().swap(coded[i]);
+      }
+    });
+    if (trace_on())
+      fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, token emit + D2H %.2f ms (%.1f MB tokens), host code %.2f ms (%d threads)\n", t1 - t0,
+              t2 - t1, (double)all * 2 / 1e6, now_ms() - t2, threads_of(ctx));
   } else {
     // ---- multi-partition and Method < 3: levels + statistics come back, the host walks them
     RESERVE(ctx->h_coeffs, n * nmb * 800);
