@@ -116,8 +116,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (BASELINE configs[1]: 256)")
-    ap.add_argument("--e2e-workers", type=int, default=2, help="contexts per GPU used by the e2e leg (host coding of one batch overlaps the GPU work of the next)")
-    ap.add_argument("--finish-slots", type=int, default=1, help="how many contexts may be in their finish stage at once")
+    ap.add_argument("--e2e-workers", type=int, default=3, help="contexts per GPU used by the e2e leg: upload, device and finish stages of consecutive batches overlap")
+    ap.add_argument("--finish-slots", type=int, default=0, help="how many contexts may be in their finish stage at once (default: 2 when the token partitions are coded on the GPU, else 1)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per context (default: cores / ranks on this node)")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -161,7 +161,11 @@ def main():
     opt = native.EncOptions()
     L.wgpu_enc_options_default(opt, 75)
 
-    upload_stage, gpu_stage, host_stage = threading.Lock(), threading.Lock(), threading.BoundedSemaphore(max(1, args.finish_slots))
+    # the library codes the token partitions on the GPU when a context has few host threads (webpgpu.cu device_coder_wanted)
+    env_coder = os.environ.get("WGPU_DEVICE_CODER", "")
+    device_coder = (env_coder != "0") if env_coder else (n >= 32 and host_threads <= 8)
+    finish_slots = args.finish_slots or (2 if device_coder else 1)
+    upload_stage, gpu_stage, host_stage = threading.Lock(), threading.Lock(), threading.BoundedSemaphore(finish_slots)
 
     class Worker:
         """One wgpu_ctx + its own pinned input/output staging.  Two workers per GPU let the host-side entropy coding of
@@ -220,6 +224,8 @@ def main():
     launches = ctx.launch_count() - launches0
     value = px_step * K * world / (dev_ms * 1e-3) / 1e6
     # ---- e2e: host RGBA -> WebP files through the public batch call; K batches in total, dealt to the workers
+    for wk in workers:
+        wk.ctx.transfer_bytes(reset=True)
     barrier()
     t0 = time.perf_counter()
     if len(workers) == 1:
@@ -244,8 +250,10 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = px_step * K * world / e2e_s / 1e6
     nmb = ((W + 15) // 16) * ((H + 15) // 16)
-    h2d = in_bytes + n * nmb + n * 4 * 160  # RGBA + segment map + per-image segment parameters
-    d2h = 2 * n * nmb + n * nmb * (48 + 800) + n * 8448  # analysis alphas + per-MB header/levels + token statistics
+    # bytes actually copied inside the timed region, counted by the library at every cudaMemcpy*Async it issues
+    xfer = [wk.ctx.transfer_bytes() for wk in workers]
+    h2d = sum(x[0] for x in xfer) // K  # RGBA + segment map + per-image segment parameters (+ token bases)
+    d2h = sum(x[1] for x in xfer) // K  # analysis alphas + per-MB headers + probabilities + coded partitions (or tokens)
     # ---- per-kernel device times for the roofline (CUDA events on the library's stream)
     stage_ms = {}
     for name, sid, reps in (("import", 0, 5), ("analysis", 1, 5), ("mode_search", 2, max(1, min(K, 3)))):
@@ -271,7 +279,8 @@ def main():
                          "parallelism": "images sharded across %d GPU(s), no collective" % world},
               "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / K * 1e3,
                       "compressed_bytes_per_step": int(sizes.sum()), "workers_per_gpu": len(workers), "host_threads_per_worker": host_threads,
-                      "api": "wgpu_enc_upload + wgpu_enc_device + wgpu_enc_finish (== wgpu_encode_batch: pinned host RGBA in, WebP files out), %d batches dealt to %d contexts, GPU stage of one batch overlapping the host stage of the previous" % (K, len(workers))},
+                      "token_partition_coder": "gpu" if device_coder else "host", "finish_slots": finish_slots,
+                      "api": "wgpu_enc_upload + wgpu_enc_device + wgpu_enc_finish (== wgpu_encode_batch: pinned host RGBA in, WebP files out), %d batches dealt to %d contexts whose upload / device / finish stages overlap" % (K, len(workers))},
               "gpu_launches": int(launches), "roofline": roofline}
     # ---- decode of the streams just produced (BASELINE configs[2])
     if not args.no_decode:

@@ -173,6 +173,9 @@ int wgpu_timer_begin(wgpu_ctx* ctx);           /* records a CUDA event on the ct
 int wgpu_timer_end(wgpu_ctx* ctx, float* ms);   /* records + synchronises, returns elapsed ms */
 /* Number of kernels this library launched on ctx since creation (for bench.py gpu_launches). */
 uint64_t wgpu_launch_count(const wgpu_ctx* ctx);
+/* Bytes this context has copied host->device and device->host (every cudaMemcpy*Async it issued) since the last call with
+ * reset != 0.  bench.py reports the per-step figures of the e2e leg from it. */
+int wgpu_transfer_bytes(wgpu_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset);
 /* Timed device-only repetitions of one stage over data already uploaded by wgpu_enc_upload /
  * decoded data; used for roofline numbers.  stage: 0 import, 1 analysis, 2 mode search (all waves). */
 int wgpu_enc_stage_time(wgpu_ctx* ctx, const wgpu_enc_options* opt, int stage, int reps, float* ms_per_rep);

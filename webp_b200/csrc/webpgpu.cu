@@ -73,6 +73,7 @@ struct wgpu_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_hdr = nullptr;
   std::string err;
   uint64_t launches = 0;
+  uint64_t xfer_h2d = 0, xfer_d2h = 0;  // bytes copied by this context since the last wgpu_transfer_bytes(reset)
   int host_threads = 0;
   std::mutex mu;
   // constant tables
@@ -136,6 +137,7 @@ void wgpu_enc_options_default(wgpu_enc_options* o, int quality) {
 static int upload_table(wgpu_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
   RESERVE(b, bytes);
   CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)(bytes);
   return 0;
 }
 
@@ -282,10 +284,12 @@ int wgpu_enc_upload(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int he
   RESERVE(ctx->rgba, (size_t)n * height * dstride);
   if (image_stride == (size_t)stride * height) {
     CK(cudaMemcpy2DAsync(ctx->rgba.p, dstride, rgba, stride, (size_t)4 * width, (size_t)n * height, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)4 * width * height * n;
   } else {
     for (int i = 0; i < n; ++i)
       CK(cudaMemcpy2DAsync(ctx->rgba.as<uint8_t>() + (size_t)i * height * dstride, dstride, rgba + (size_t)i * image_stride, stride,
                            (size_t)4 * width, height, cudaMemcpyHostToDevice, ctx->stream));
+    if (image_stride != (size_t)stride * height) ctx->xfer_h2d += (uint64_t)4 * width * height * n;
   }
   ctx->e_n = n; ctx->e_w = width; ctx->e_h = height; ctx->e_mbw = (width + 15) >> 4; ctx->e_mbh = (height + 15) >> 4;
   ctx->e_rgba_stride = dstride;
@@ -444,7 +448,9 @@ static int enc_launch_import(wgpu_ctx* ctx) {
       RESERVE(ctx->dither_y, dy.size() * 2);
       RESERVE(ctx->dither_uv, duv.size() * 4);
       CK(cudaMemcpyAsync(ctx->dither_y.p, dy.data(), dy.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->xfer_h2d += (uint64_t)(dy.size() * 2);
       CK(cudaMemcpyAsync(ctx->dither_uv.p, duv.data(), duv.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->xfer_h2d += (uint64_t)(duv.size() * 4);
       CK(cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
       ctx->dither_w = pad_w; ctx->dither_h = pad_h; ctx->dither_amp_cached = amp;
     }
@@ -557,6 +563,7 @@ static int enc_launch_token_prepass(wgpu_ctx* ctx) {
   ctx->launches += 3;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->h_totals.p, ctx->img_total.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->xfer_d2h += (uint64_t)((size_t)n * 8);
   return WGPU_OK;
 }
 
@@ -573,7 +580,9 @@ static int enc_analyze_locked(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
   if ((rc = enc_launch_import(ctx))) return rc;
   if ((rc = enc_launch_analysis(ctx))) return rc;
   CK(cudaMemcpyAsync(ctx->h_alpha.p, ctx->alpha.p, (size_t)n * nmb, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->xfer_d2h += (uint64_t)((size_t)n * nmb);
   CK(cudaMemcpyAsync(ctx->h_uv_alpha.p, ctx->uv_alpha.p, (size_t)n * nmb, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->xfer_d2h += (uint64_t)((size_t)n * nmb);
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->e_analyzed = true;
   return WGPU_OK;
@@ -582,7 +591,9 @@ static int enc_analyze_locked(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
 static int enc_search_locked(wgpu_ctx* ctx) {
   const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
   CK(cudaMemcpyAsync(ctx->segment.p, ctx->h_segment.p, (size_t)n * nmb, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)((size_t)n * nmb);
   CK(cudaMemcpyAsync(ctx->img_params.p, ctx->h_params.p, (size_t)n * sizeof(wg::ImageParams), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)((size_t)n * sizeof(wg::ImageParams));
   int rc = enc_launch_waves(ctx);
   if (rc) return rc;
   if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3 && (rc = enc_launch_token_prepass(ctx))) return rc;
@@ -710,9 +721,12 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     RESERVE(ctx->tokens, (size_t)(all + 512) * 2);
     RESERVE(ctx->coded, (size_t)oall);
     CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(n * nmb * 48);
     CK(cudaMemcpyAsync(ctx->h_proba.p, ctx->proba.p, n * 1056, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(n * 1056);
     CK(cudaEventRecord(ctx->ev_hdr, ctx->stream));
     CK(cudaMemcpyAsync(ctx->img_base.p, bases, 2 * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)(2 * n * 8);
     const wg::TokenParams T = token_params(ctx);
     wg::token_kernel<true><<<(unsigned)((n * nmb + 15) / 16), 128, 0, ctx->stream>>>(T);
     ctx->launches++;
@@ -738,12 +752,14 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       for (size_t i = 0; i < n; ++i) order[i] = (int)i;
       std::sort(order, order + n, [&](int a, int b) { return totals[a] > totals[b] || (totals[a] == totals[b] && a < b); });
       CK(cudaMemcpyAsync(ctx->img_base.as<unsigned long long>() + 2 * n, order, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->xfer_h2d += (uint64_t)(n * 4);
       B.order = reinterpret_cast<const int*>(ctx->img_base.as<unsigned long long>() + 2 * n);
       wg::boolcode_kernel<<<(unsigned)((n + 31) / 32), 64, coder_smem, ctx->stream>>>(B);
     }
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(n * 4);
     CK(cudaEventSynchronize(ctx->ev_hdr));
     const double t2 = now_ms();
     std::vector<std::vector<uint8_t>> part0(n);
@@ -760,6 +776,7 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       if (out_sizes[i] > out_stride) { too_small.store(1); continue; }
       if (csz[i])
         CK(cudaMemcpyAsync(out + i * out_stride + 30 + part0[i].size(), ctx->coded.as<uint8_t>() + bases[n + i], csz[i], cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->xfer_d2h += (uint64_t)(csz[i]);
     }
     parallel_for((int)n, threads_of(ctx), [&](int i) {
       if (out_sizes[i] > out_stride) return;
@@ -783,13 +800,16 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     RESERVE(ctx->tokens, (size_t)(all + 8) * 2);
     RESERVE(ctx->h_tokens, (size_t)(all + 8) * 2);
     CK(cudaMemcpyAsync(ctx->img_base.p, bases, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)(n * 8);
     const wg::TokenParams T = token_params(ctx);
     wg::token_kernel<true><<<(unsigned)((n * nmb + 15) / 16), 128, 0, ctx->stream>>>(T);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(n * nmb * 48);
     CK(cudaMemcpyAsync(ctx->h_proba.p, ctx->proba.p, n * 1056, cudaMemcpyDeviceToHost, ctx->stream));
-    if (all) CK(cudaMemcpyAsync(ctx->h_tokens.p, ctx->tokens.p, (size_t)all * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(n * 1056);
+    if (all) { CK(cudaMemcpyAsync(ctx->h_tokens.p, ctx->tokens.p, (size_t)all * 2, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)((size_t)all * 2); }
     CK(cudaStreamSynchronize(ctx->stream));
     const double t2 = now_ms();
     // pair images of similar length (longest first) so two coders run interleaved in each task
@@ -825,8 +845,11 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     // ---- multi-partition and Method < 3: levels + statistics come back, the host walks them
     RESERVE(ctx->h_coeffs, n * nmb * 800);
     CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(n * nmb * 48);
     CK(cudaMemcpyAsync(ctx->h_coeffs.p, ctx->coeffs.p, n * nmb * 800, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(n * nmb * 800);
     CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->stats.p, n * wg::STATS_SIZE * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(n * wg::STATS_SIZE * 4);
     CK(cudaStreamSynchronize(ctx->stream));
     const double t1 = now_ms();
     parallel_for((int)n, threads_of(ctx), [&](int i) {
@@ -859,6 +882,15 @@ int wgpu_encode_batch(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int 
   if ((rc = wgpu_enc_upload(ctx, rgba, n, width, height, stride, image_stride))) return rc;
   if ((rc = wgpu_enc_device(ctx, opt))) return rc;
   return wgpu_enc_finish(ctx, out, out_stride, out_sizes);
+}
+
+int wgpu_transfer_bytes(wgpu_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (h2d) *h2d = ctx->xfer_h2d;
+  if (d2h) *d2h = ctx->xfer_d2h;
+  if (reset) ctx->xfer_h2d = ctx->xfer_d2h = 0;
+  return WGPU_OK;
 }
 
 int wgpu_enc_fetch(wgpu_ctx* ctx, int image, uint8_t* mb_hdr, uint8_t* mb_modes, uint8_t* mb_nz, int16_t* mb_coeffs, uint8_t* recon_y,
@@ -997,8 +1029,11 @@ int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* l
   });
   if (bad.load() >= 0) FAIL(WGPU_ERR_BITSTREAM, std::string("image ") + std::to_string(bad.load()) + ": " + (frames[bad.load()].err ? frames[bad.load()].err : "parse error"));
   CK(cudaMemcpyAsync(ctx->d_coeffs.p, ctx->hd_coeffs.p, (size_t)n * nmb * 768, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)((size_t)n * nmb * 768);
   CK(cudaMemcpyAsync(ctx->d_meta.p, ctx->hd_meta.p, (size_t)n * nmb * sizeof(wg::MBMeta), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)((size_t)n * nmb * sizeof(wg::MBMeta));
   CK(cudaMemcpyAsync(ctx->d_ftype.p, ctx->hd_ftype.p, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)((size_t)n);
   ctx->d_any_filter = false;
   for (int i = 0; i < n; ++i) ctx->d_any_filter |= frames[i].filter_type > 0;
   ctx->d_n = n; ctx->d_w = width; ctx->d_h = height; ctx->d_mbw = mbw; ctx->d_mbh = mbh;
@@ -1042,10 +1077,10 @@ int wgpu_dec_fetch(wgpu_ctx* ctx, uint8_t* y, uint8_t* u, uint8_t* v, size_t y_p
   const size_t nmb = (size_t)ctx->d_mbw * ctx->d_mbh, yp = nmb * 256, uvp = nmb * 64, img = (size_t)ctx->d_w * ctx->d_h * 4;
   if ((y && y_plane_stride < yp) || ((u || v) && uv_plane_stride < uvp)) FAIL(WGPU_ERR_TOO_SMALL, "plane stride smaller than the padded plane");
   if (nrgba && (!ctx->d_has_nrgba || nrgba_image_stride < img)) FAIL(WGPU_ERR_TOO_SMALL, "nrgba not produced or image stride too small");
-  if (y) CK(cudaMemcpy2DAsync(y, y_plane_stride, ctx->dy.p, yp, yp, n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (u) CK(cudaMemcpy2DAsync(u, uv_plane_stride, ctx->du.p, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (v) CK(cudaMemcpy2DAsync(v, uv_plane_stride, ctx->dv.p, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream));
-  if (nrgba) CK(cudaMemcpy2DAsync(nrgba, nrgba_image_stride, ctx->d_nrgba.p, img, img, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (y) { CK(cudaMemcpy2DAsync(y, y_plane_stride, ctx->dy.p, yp, yp, n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)yp * n; }
+  if (u) { CK(cudaMemcpy2DAsync(u, uv_plane_stride, ctx->du.p, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)uvp * n; }
+  if (v) { CK(cudaMemcpy2DAsync(v, uv_plane_stride, ctx->dv.p, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)uvp * n; }
+  if (nrgba) { CK(cudaMemcpy2DAsync(nrgba, nrgba_image_stride, ctx->d_nrgba.p, img, img, n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)img * n; }
   CK(cudaStreamSynchronize(ctx->stream));
   return WGPU_OK;
 }
@@ -1071,9 +1106,9 @@ int wgpu_import_rgba(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int h
   if ((rc = enc_reserve(ctx))) return rc;
   if ((rc = enc_launch_import(ctx))) return rc;
   const size_t nmb = (size_t)ctx->e_mbw * ctx->e_mbh;
-  if (y) CK(cudaMemcpyAsync(y, ctx->sy.p, (size_t)n * nmb * 256, cudaMemcpyDeviceToHost, ctx->stream));
-  if (u) CK(cudaMemcpyAsync(u, ctx->su.p, (size_t)n * nmb * 64, cudaMemcpyDeviceToHost, ctx->stream));
-  if (v) CK(cudaMemcpyAsync(v, ctx->sv.p, (size_t)n * nmb * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  if (y) { CK(cudaMemcpyAsync(y, ctx->sy.p, (size_t)n * nmb * 256, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)((size_t)n * nmb * 256); }
+  if (u) { CK(cudaMemcpyAsync(u, ctx->su.p, (size_t)n * nmb * 64, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)((size_t)n * nmb * 64); }
+  if (v) { CK(cudaMemcpyAsync(v, ctx->sv.p, (size_t)n * nmb * 64, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)((size_t)n * nmb * 64); }
   CK(cudaStreamSynchronize(ctx->stream));
   return WGPU_OK;
 }
@@ -1091,18 +1126,23 @@ int wgpu_upsample_nrgba(wgpu_ctx* ctx, int n, int width, int height, const uint8
   RESERVE(ctx->dy, ysz); RESERVE(ctx->du, csz); RESERVE(ctx->dv, csz);
   RESERVE(ctx->d_nrgba, (size_t)n * width * height * 4);
   CK(cudaMemcpyAsync(ctx->dy.p, y, ysz, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)(ysz);
   CK(cudaMemcpyAsync(ctx->du.p, u, csz, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)(csz);
   CK(cudaMemcpyAsync(ctx->dv.p, v, csz, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)(csz);
   const uint8_t* d_alpha = nullptr;
   if (alpha) {
     RESERVE(ctx->d_alpha, (size_t)n * width * height);
     CK(cudaMemcpyAsync(ctx->d_alpha.p, alpha, (size_t)n * width * height, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)((size_t)n * width * height);
     d_alpha = ctx->d_alpha.as<uint8_t>();
   }
   int rc = launch_upsample(ctx, n, width, height, ctx->dy.as<uint8_t>(), y_stride, ctx->du.as<uint8_t>(), ctx->dv.as<uint8_t>(), uv_stride,
                            y_plane_stride, uv_plane_stride, d_alpha, ctx->d_nrgba.as<uint8_t>());
   if (rc) return rc;
   CK(cudaMemcpyAsync(nrgba, ctx->d_nrgba.p, (size_t)n * width * height * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->xfer_d2h += (uint64_t)((size_t)n * width * height * 4);
   CK(cudaStreamSynchronize(ctx->stream));
   return WGPU_OK;
 }
@@ -1131,11 +1171,13 @@ int wgpu_plane_metrics(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b,
   const size_t sz = (size_t)(n - 1) * plane_stride + (size_t)(height - 1) * stride + width;
   RESERVE(ctx->m_a, sz); RESERVE(ctx->m_b, sz);
   CK(cudaMemcpyAsync(ctx->m_a.p, a, sz, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)(sz);
   CK(cudaMemcpyAsync(ctx->m_b.p, b, sz, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)(sz);
   int rc = launch_metrics(ctx, n, ctx->m_a.as<uint8_t>(), ctx->m_b.as<uint8_t>(), width, height, stride, plane_stride);
   if (rc) return rc;
-  if (sse) CK(cudaMemcpyAsync(sse, ctx->m_sse.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (ssim_sum) CK(cudaMemcpyAsync(ssim_sum, ctx->m_ssim.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (sse) { CK(cudaMemcpyAsync(sse, ctx->m_sse.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)((size_t)n * 8); }
+  if (ssim_sum) { CK(cudaMemcpyAsync(ssim_sum, ctx->m_ssim.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)((size_t)n * 8); }
   CK(cudaStreamSynchronize(ctx->stream));
   return WGPU_OK;
 }
@@ -1256,6 +1298,7 @@ int wgpu_dsp_quantize_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, i
   wg::dsp_quantize_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_in, make_seg_quant(dc_q, ac_q, type, sharpen), first, d_out, d_nz);
   DSP_END(d_out, out, (size_t)n * 32);
   CK(cudaMemcpyAsync(nz, d_nz, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->xfer_d2h += (uint64_t)((size_t)n * 4);
   DSP_SYNC;
 }
 int wgpu_dsp_trellis_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, int ac_q, int qtype, int sharpen, int first, int ctx_type,
@@ -1268,6 +1311,7 @@ int wgpu_dsp_trellis_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, in
                                                         tab_ptrs(ctx), d_out, d_nz);
   DSP_END(d_out, out, (size_t)n * 32);
   CK(cudaMemcpyAsync(nz, d_nz, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->xfer_d2h += (uint64_t)((size_t)n * 4);
   DSP_SYNC;
 }
 int wgpu_dsp_token_cost_batch(wgpu_ctx* ctx, int n, const int16_t* levels, const int32_t* nz, int ctx_type, const int32_t* ctx0, int first,

@@ -97,6 +97,7 @@ def lib():
         L.wgpu_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
         L.wgpu_launch_count.argtypes = [vp]
         L.wgpu_launch_count.restype = C.c_uint64
+        L.wgpu_transfer_bytes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
         L.wgpu_enc_stage_time.argtypes = [vp, C.POINTER(EncOptions), C.c_int, C.c_int, C.POINTER(C.c_float)]
         _LIB = L
     return _LIB
@@ -124,6 +125,12 @@ class Context:
 
     def launch_count(self):
         return int(lib().wgpu_launch_count(self._h))
+
+    def transfer_bytes(self, reset=False):
+        """(host->device, device->host) bytes copied by this context since the last reset."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.check(lib().wgpu_transfer_bytes(self._h, C.byref(a), C.byref(b), 1 if reset else 0))
+        return int(a.value), int(b.value)
 
     def close(self):
         if self._h:
