@@ -25,6 +25,7 @@ func cudaOptions(cfg *EncodeConfig) C.wgpu_enc_options {
 		filter_type: C.int(cfg.FilterType), partitions: C.int(cfg.Partitions), segments: C.int(cfg.Segments),
 		preprocessing: C.int(cfg.Preprocessing), has_alpha: C.int(cfg.HasAlpha),
 		passes: C.int(cfg.Pass), dither_amp: C.int(ditherAmp(cfg.Dithering)),
+		target_size: C.int(cfg.TargetSize), target_psnr: C.float(cfg.TargetPSNR), qmin: C.int(cfg.QMin), qmax: C.int(cfg.QMax),
 	}
 }
 

@@ -44,7 +44,7 @@ typedef enum {
  * encode.go:478-528; defaults = lossy.DefaultConfig (encode.go:66-86). */
 typedef struct {
   int quality;          /* 0..100 */
-  int method;           /* 0..6; >=3: row-parallel path semantics (needs height > 48); <3: statLoop + serial encodeFrame semantics */
+  int method;           /* 0..6; >=3: row-parallel path semantics (serial RD semantics when height <= 48 or a target is set: <= 96 macroblocks); <3: statLoop + serial encodeFrame semantics */
   int sns_strength;     /* 0..100, default 50 */
   int filter_strength;  /* 0..100, default 60 */
   int filter_sharpness; /* 0..7 */
@@ -55,6 +55,9 @@ typedef struct {
   int has_alpha;        /* 0: opaque input (alpha bytes ignored) */
   int passes;           /* EncodeConfig.Pass, 1..10 (statLoop iterations on the Method < 3 path); 0 = 1 */
   int dither_amp;       /* VP8Random.amp = int(256 * EncodeConfig.Dithering), 0..256 (encode.go:563-567, dsp/random.go:39); 0 = off */
+  int target_size;      /* EncodeConfig.TargetSize in bytes; > 0: size search (doSearch, internal/lossy/encode.go:1338) */
+  float target_psnr;    /* EncodeConfig.TargetPSNR in dB; > 0: the reference's "PSNR search" (it measures 99.0 dB every pass) */
+  int qmin, qmax;       /* EncodeConfig.QMin / QMax after resolveQMax (encode.go:305): quality clamp of the search; qmax <= 0 means 100 */
 } wgpu_enc_options;
 
 void wgpu_enc_options_default(wgpu_enc_options* o, int quality);
@@ -100,7 +103,7 @@ typedef struct {
 } wgpu_seg_quant;
 typedef struct {
   wgpu_seg_quant y1, y2, uv;
-  int lambda_i4, lambda_i16, lambda_uv, lambda_mode, tlambda_i4, tlambda_i16, tlambda_sd, reserved;
+  int lambda_i4, lambda_i16, lambda_uv, lambda_mode, tlambda_i4, tlambda_i16, tlambda_sd, reserved; /* reserved: 0 */
 } wgpu_segment;
 /* setupSegment (internal/lossy/encode.go:1084): quantiser matrices, biases, sharpening and lambdas of one segment from
  * its quantiser index; provided so hosts and tests can build wgpu_segment without restating the tables. */

@@ -13,7 +13,9 @@ extern "C" {
 // ---- whole-codec -------------------------------------------------------------------------
 struct OrcEncCfg {
   int quality, method, sns_strength, filter_strength, filter_sharpness, filter_type, partitions, segments,
-      preprocessing, has_alpha, passes, dither_amp;
+      preprocessing, has_alpha, passes, dither_amp, target_size;
+  float target_psnr;
+  int qmin, qmax;
 };
 static EncodeConfig to_cfg(const OrcEncCfg* c) {
   EncodeConfig e;
@@ -24,6 +26,7 @@ static EncodeConfig to_cfg(const OrcEncCfg* c) {
   e.pass = c->passes > 0 ? c->passes : 1;
   e.dither_amp = c->dither_amp & 0xffff;
   e.force_serial = (c->dither_amp >> 16) & 1;  // test hook: GOMAXPROCS == 1 semantics
+  e.target_size = c->target_size; e.target_psnr = c->target_psnr; e.qmin = c->qmin; e.qmax = c->qmax <= 0 ? 100 : c->qmax;
   return e;
 }
 // Encode one RGBA image (parallel-path semantics).  Returns RIFF size or <0 (-1 unsupported

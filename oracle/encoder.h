@@ -81,6 +81,9 @@ struct EncodeConfig {  // internal/lossy/encode.go:46-86 (DefaultConfig)
   int filter_type = 1, partitions = 0, segments = 4, pass = 1, preprocessing = 0;
   bool force_serial = false;  // GOMAXPROCS == 1 semantics: serial encodeFrame even where the reference would go row-parallel
   int dither_amp = 0;  // VP8Random.amp = int(256 * Dithering) (dsp/random.go:39-50); 0 == no dithering
+  int target_size = 0;      // bytes; > 0 -> size search (doSearch, encode.go:1338)
+  float target_psnr = 0.f;  // dB; > 0 -> "PSNR search" (the measured PSNR is always 99.0)
+  int qmin = 0, qmax = 100; // resolveQMax(-1) == 100 (encode.go:305-306)
 };
 struct SegmentQuant {  // encode.go:311-323
   int quant, iquant, bias, dc_quant, dc_iquant, dc_bias;
@@ -2201,23 +2204,71 @@ struct Encoder {
     return out;
   }
 
+  // ---- rate control (encode.go:1440-1590): passStats, computeNextQ, adjustQuantForTarget
+  struct PassStats { bool is_first; double dq, q, last_q, qmin, qmax, value, last_value, target; bool do_size; } rc;
+  bool rc_init = false;
+  double compute_next_q() {  // encode.go:1505
+    double dq;
+    if (rc.is_first) {
+      dq = rc.value > rc.target ? -rc.dq : rc.dq;
+      rc.is_first = false;
+    } else if (rc.value != rc.last_value) {
+      const double slope = (rc.target - rc.value) / (rc.last_value - rc.value);
+      dq = slope * (rc.last_q - rc.q);
+    } else {
+      dq = 0;
+    }
+    if (dq < -30) dq = -30;
+    if (dq > 30) dq = 30;
+    rc.dq = dq; rc.last_q = rc.q; rc.last_value = rc.value;
+    rc.q = rc.q + dq;
+    if (rc.q < rc.qmin) rc.q = rc.qmin;
+    if (rc.q > rc.qmax) rc.q = rc.qmax;
+    return rc.q;
+  }
+  bool adjust_quant_for_target() {  // encode.go:1544
+    if (!rc_init) {  // initPassStats (encode.go:1455)
+      rc.do_size = cfg.target_size > 0;
+      rc.target = rc.do_size ? (double)cfg.target_size : (cfg.target_psnr > 0 ? (double)cfg.target_psnr : 40.0);
+      rc.qmin = cfg.qmin; rc.qmax = cfg.qmax <= 0 ? 100.0 : (double)cfg.qmax;
+      double q = cfg.quality;
+      if (q < rc.qmin) q = rc.qmin;
+      if (q > rc.qmax) q = rc.qmax;
+      rc.is_first = true; rc.dq = 10.0; rc.q = q; rc.last_q = q; rc.value = 0; rc.last_value = 0;
+      rc_init = true;
+    }
+    if (rc.do_size) {
+      rc.value = (double)assemble_frame().size();  // trial frame with the probabilities as they stand (not yet optimised)
+    } else {
+      // MBEncInfo.Disto is read here but never written anywhere in the reference: total distortion 0 -> 99 dB
+      rc.value = 99.0;
+    }
+    if (std::fabs(rc.dq) <= 0.4 && !rc.is_first) return true;
+    const double next_q = compute_next_q();
+    cfg.quality = (int)(next_q + 0.5);
+    set_segment_params(num_segments);
+    build_segment_header(num_segments);
+    y_plane = src_y; u_plane = src_u; v_plane = src_v;  // restoreSourcePixels (encode.go:1606)
+    return false;
+  }
+
   // EncodeFrame (encode.go:1324); returns the raw VP8 frame.  Method >= 3 -> row-parallel path semantics
   // (GOMAXPROCS > 1, mbH >= 4); Method < 3 -> statLoop + serial encodeFrame.
   std::vector<uint8_t> encode_frame() {
     analysis();
     set_segment_probas();
-    if (cfg.method < 3) {
-      stat_loop(cfg.pass);
-      tokens.clear();
-      encode_frame_serial_pass();
-      static thread_local ProbaStats st2;
-      collect_all_stats(st2);
-      if (optimize_proba(st2) > 0) rerecord_all_tokens();
-      return assemble_frame();
-    }
-    if (mb_h < 4 || cfg.force_serial) {  // useParallel == false (encode.go:1356): one serial pass, then the common tail
-      tokens.clear();
-      encode_frame_serial_pass();
+    if (cfg.method < 3) stat_loop(cfg.pass);
+    // doSearch (TargetSize / TargetPSNR) always takes the serial encodeFrame, at least three passes (encode.go:1338-1374)
+    const bool do_search = cfg.target_size > 0 || cfg.target_psnr > 0;
+    if (cfg.method < 3 || mb_h < 4 || cfg.force_serial || do_search) {  // useParallel == false (encode.go:1356)
+      int max_passes = cfg.pass > 1 ? cfg.pass : 1;
+      if (do_search && max_passes < 3) max_passes = 3;
+      for (int pass = 0; pass < max_passes; ++pass) {
+        tokens.clear();
+        encode_frame_serial_pass();
+        if (!do_search) break;
+        if (adjust_quant_for_target()) break;
+      }
       static thread_local ProbaStats st3;
       collect_all_stats(st3);
       if (optimize_proba(st3) > 0) rerecord_all_tokens();

@@ -15,13 +15,15 @@ _LIB = None
 class OrcEncCfg(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "quality", "method", "sns_strength", "filter_strength", "filter_sharpness", "filter_type",
-        "partitions", "segments", "preprocessing", "has_alpha", "passes", "dither_amp")]
+        "partitions", "segments", "preprocessing", "has_alpha", "passes", "dither_amp", "target_size")] + [
+        ("target_psnr", C.c_float), ("qmin", C.c_int), ("qmax", C.c_int)]
 
 
 def default_cfg(quality=75, method=4, **kw):
     """lossy.DefaultConfig (internal/lossy/encode.go:66) + EncoderOptions mapping (encode.go:478-528)."""
     c = OrcEncCfg(quality=quality, method=method, sns_strength=50, filter_strength=60, filter_sharpness=0,
-                  filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=0, passes=1, dither_amp=0)
+                  filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=0, passes=1, dither_amp=0,
+                  target_size=0, target_psnr=0.0, qmin=0, qmax=100)
     for k, v in kw.items():
         setattr(c, k, v)
     return c

@@ -194,14 +194,58 @@ def test_encode_test_png(oracle, gpu_ctx):
     assert buf.getvalue() == oracle.encode(img)
 
 
+RC_CASES = [
+    (128, 96, [0, 1, 2], dict(TargetPSNR=40.0)),                 # 48 macroblocks: passes at Q, Q-10, Q-10
+    (128, 96, [1, 2], dict(TargetSize=2000)),                    # secant search on the trial frame size
+    (160, 128, [0, 2], dict(TargetSize=1500, Method=6)),          # 80 macroblocks
+    (100, 70, [1, 2], dict(TargetPSNR=35.0, Method=3, Quality=45)),   # all-mode I4 search, quality crossing 50 (max I4 modes 3 -> 2)
+    (64, 48, [0, 1, 2], dict(TargetSize=600, QMin=20, QMax=90, Pass=6)),
+    (96, 96, [2], dict(TargetSize=4000, Segments=1, Quality=90)),
+    (128, 96, [1], dict(TargetPSNR=42.0, Partitions=2, Quality=90)),
+]
+
+
+@pytest.mark.parametrize("w,h,idxs,kw", RC_CASES)
+def test_rate_control_passes(oracle, gpu_ctx, w, h, idxs, kw):
+    """TargetSize / TargetPSNR: the reference's doSearch loop (internal/lossy/encode.go:1338-1374, adjustQuantForTarget
+    :1544) over the serial RD encodeFrame, images of one batch converging independently; bytes and per-MB data == oracle."""
+    o = _opts(**kw)
+    imgs = np.stack([oracle.synth_image(w, h, i) for i in idxs])
+    files = webp_b200.EncodeBatch(imgs, o, gpu_ctx)
+    for k, i in enumerate(idxs):
+        exp, t = oracle.encode(imgs[k], _ocfg(oracle, o), taps=True)
+        g = _fetch(gpu_ctx, k, w, h)
+        for d in (g, t):  # fields the macroblock type leaves unused keep whatever an earlier pass wrote (in the reference too)
+            i4 = d["mb_hdr"][:, 0] == 1
+            d["mb_modes"][~i4] = 0
+            d["mb_coeffs"][i4, 384:] = 0
+            d["mb_hdr"][i4, 5] = 0
+            d["mb_hdr"][i4, 1] = 0
+        errs = [first_diff("segment", g["mb_hdr"][:, 3], t["mb_hdr"][:, 3]),
+                first_diff("hdr", g["mb_hdr"][:, :6], t["mb_hdr"][:, :6]),
+                first_diff("modes", g["mb_modes"], t["mb_modes"]),
+                first_diff("coeffs", g["mb_coeffs"], t["mb_coeffs"])]
+        # a search that has not converged after its last pass restores the source planes (restoreSourcePixels), so the
+        # reference's planes hold the source then, not the reconstruction
+        if not np.array_equal(t["recon_y"], t["src_y"]):
+            errs.append(first_diff("recon_y", g["recon_y"][:h, :w], t["recon_y"][:h, :w]))
+        errs = [e for e in errs if e]
+        assert not errs, "image %d: %s" % (i, "; ".join(errs))
+        assert files[k] == exp, "image %d: bitstream differs (%d vs %d bytes)" % (i, len(files[k]), len(exp))
+
+
 def test_encode_rejections(gpu_ctx):
     img = np.full((64, 64, 4), 255, np.uint8)
     wide = np.full((40, 16 * 97, 4), 255, np.uint8)
     with pytest.raises(native.WebPGPUError) as e:  # serial RD path with mid-stream probability refreshes (> 96 macroblocks)
         webp_b200.EncodeBatch(wide[None], _opts(), gpu_ctx)
     assert e.value.code == native.ERR_UNSUPPORTED
+    big = np.full((256, 256, 4), 255, np.uint8)
+    with pytest.raises(native.WebPGPUError) as e:  # rate control over more than 96 macroblocks needs the refresh schedule
+        webp_b200.EncodeBatch(big[None], _opts(TargetPSNR=40.0), gpu_ctx)
+    assert e.value.code == native.ERR_UNSUPPORTED
     with pytest.raises(webp_b200.WebPError):
-        webp_b200.EncodeBatch(img[None], _opts(TargetPSNR=40.0), gpu_ctx)
+        webp_b200.EncodeBatch(img[None], _opts(TargetSize=500, Method=2), gpu_ctx)
     with pytest.raises(webp_b200.WebPError):
         webp_b200.EncodeBatch(img[None], _opts(Lossless=True), gpu_ctx)
 

@@ -68,6 +68,9 @@ def test_import_matches_libwebp(oracle, w, h, kind):
     # serial RD path (Method >= 3, fewer than 4 macroblock rows; bit 16 of dither_amp = GOMAXPROCS==1 semantics on any frame)
     (64, 48, 1, {}), (100, 40, 2, dict(method=3)), (512, 48, 1, dict(method=6, quality=85)), (33, 17, 2, dict(quality=30)),
     (128, 96, 1, dict(dither_amp=1 << 16)), (256, 192, 2, dict(method=3, dither_amp=1 << 16)),
+    # rate control (doSearch): three or more serial passes with the quality moved by adjustQuantForTarget
+    (128, 96, 1, dict(target_psnr=40.0)), (128, 96, 2, dict(target_size=2000)), (256, 192, 1, dict(target_size=6000, method=6)),
+    (64, 64, 2, dict(target_size=800, method=2)),
 ])
 def test_oracle_stream_decodes_identically_in_libwebp(oracle, w, h, idx, kw):
     """Every oracle-encoded stream must decode in libwebp to exactly what the oracle's decoder produces,

@@ -234,8 +234,12 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   const int rows = y_hi - y_lo + 1;
   const long long total = SERIAL ? (long long)P.n_images : (long long)rows * P.n_images;
   const long long task = task_base + g;
-  const bool active = task < total;
-  // SERIAL (the reference's serial encodeFrame order): `wave` is the raster macroblock index, one macroblock per image per launch
+  // SERIAL (the reference's serial encodeFrame order): `wave` is the raster macroblock index, one macroblock per image per
+  // launch.  Rate-control passes (adjustQuantForTarget) re-encode only the images that have not converged: bit 8 of
+  // seg[0].flags parks an image, bits 0-7 carry its own getMaxI4RDModes (its quality moves with the search).
+  const int img_flags = (SERIAL && task < total) ? P.img[(int)task].seg[0].flags : 0;
+  const bool active = task < total && !(img_flags & 0x100);
+  const int max_i4_modes = (img_flags & 0xff) ? (img_flags & 0xff) : P.max_i4_modes;
   const int img = active ? (SERIAL ? (int)task : (int)(task / rows)) : 0;
   const int my = active ? (SERIAL ? wave / P.mb_w : y_lo + (int)(task % rows)) : 0;
   const int mx = active ? (SERIAL ? wave - my * P.mb_w : wave - 2 * my) : 0;
@@ -542,7 +546,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       __syncwarp();
       // serial path, Method 3: PickBestI4ModeRD scores every eligible mode in mode order, no pre-screen (encode_analysis.go:1216)
       const bool all_modes = SERIAL && P.method == 3;
-      const int K = alive ? (all_modes ? n_cand : min(P.max_i4_modes, n_cand)) : 0;
+      const int K = alive ? (all_modes ? n_cand : min(max_i4_modes, n_cand)) : 0;
       if (alive && gl == 0 && !all_modes) {  // the reference's selection sort of the first K entries, literally (encode_parallel.go:969-983)
 #pragma unroll 1
         for (int i = 0; i < K; ++i) {

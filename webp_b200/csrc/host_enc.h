@@ -49,6 +49,7 @@ struct FramePlan {
   int f_level, f_sharpness;
   int dq_uv_dc, dq_uv_ac;
   int num_parts;  // 1, 2, 4 or 8 token partitions (encode.go:475)
+  int global_uv_alpha;
 };
 
 static inline double quality_to_compression(int q) {  // encode.go:1039
@@ -87,6 +88,68 @@ static inline void setup_segment(FramePlan* fp, const wgpu_enc_options& o, int i
   d->tlambda_sd = (o.method >= 4 && o.sns_strength > 0) ? (o.sns_strength * qi4) >> 5 : 0;
   d->pad = 0;
   for (int k = 0; k < 16; ++k) d->y1.sharpen[k] = (int16_t)((kSharp[k] * (k == 0 ? y1dc : y1ac)) >> 11);
+}
+
+// setSegmentParams (encode_analysis.go:122) with setupFilterStrength, simplifySegments and setupSegment: everything that
+// depends on the quality.  Called once by plan_frame and again by the rate-control loop (adjustQuantForTarget,
+// lossy/encode.go:1580) with the segment count left by the previous call; the per-segment alpha / beta stay.
+static inline void set_segment_params(FramePlan* fp, const wgpu_enc_options& o, int num_segs, uint8_t* segment_out) {
+  const int total = fp->mb_w * fp->mb_h;
+  const int global_uv_alpha = fp->global_uv_alpha;
+  const int sns = o.sns_strength < 0 ? 0 : o.sns_strength;
+  const double amp = 0.9 * (double)sns / 100.0 / 128.0;
+  const double c_base = quality_to_compression(o.quality);
+  for (int i = 0; i < num_segs; ++i) {
+    const double c = pow(c_base, 1.0 - amp * (double)fp->seg[i].alpha);
+    fp->seg[i].quant = clampi((int)(127.0 * (1.0 - c)), 0, 127);
+  }
+  for (int i = num_segs; i < 4; ++i) fp->seg[i].quant = fp->seg[0].quant;
+  int dq = (global_uv_alpha - 64) * 10 / 70;
+  dq = dq * sns / 100;
+  fp->dq_uv_ac = clampi(dq, -4, 6);
+  fp->dq_uv_dc = clampi(-4 * sns / 100, -15, 15);
+  // setupFilterStrength (encode.go:1276)
+  fp->f_simple = (o.filter_type == 0);
+  fp->f_sharpness = clampi(o.filter_sharpness, 0, 7);
+  if (o.filter_strength <= 0) {
+    fp->f_level = 0;
+  } else {
+    const int level0 = 5 * o.filter_strength, cfg_segs = clampi(o.segments, 1, 4);
+    for (int i = 0; i < cfg_segs; ++i) {
+      const int qstep = kAcTable[clampi(fp->seg[i].quant, 0, 127)] >> 2;
+      int f = kLevelsFromDelta[fp->f_sharpness * 64 + clampi(qstep, 0, 63)] * level0 / (256 + fp->seg[i].beta);
+      if (f < 2) f = 0;
+      if (f > 63) f = 63;
+      fp->seg[i].fstrength = f;
+    }
+    fp->f_level = fp->seg[0].fstrength;
+  }
+  if (num_segs > 1) {  // simplifySegments (encode_analysis.go:197)
+    int smap[4] = {0, 1, 2, 3}, nf = 1;
+    for (int s1 = 1; s1 < num_segs; ++s1) {
+      bool found = false;
+      for (int s2 = 0; s2 < nf; ++s2)
+        if (fp->seg[s1].quant == fp->seg[s2].quant && fp->seg[s1].fstrength == fp->seg[s2].fstrength) { smap[s1] = s2; found = true; break; }
+      if (!found) { smap[s1] = nf; if (nf != s1) fp->seg[nf] = fp->seg[s1]; nf++; }
+    }
+    if (nf < num_segs) {
+      for (int i = 0; i < total; ++i) segment_out[i] = (uint8_t)smap[segment_out[i]];
+      for (int i = nf; i < num_segs; ++i) fp->seg[i] = fp->seg[nf - 1];
+    }
+    num_segs = nf;
+  }
+  fp->num_segments = num_segs;
+  for (int i = 0; i < 4; ++i) setup_segment(fp, o, i);
+}
+static inline void build_segment_header(FramePlan* fp, const wgpu_enc_options& o, int num_segs) {  // encode_analysis.go:852
+  fp->seg_use = num_segs > 1;
+  fp->seg_update_map = fp->seg_use;
+  if (fp->seg_use)  // entries past num_segs keep what an earlier call left, as the reference's do
+    for (int i = 0; i < num_segs; ++i) {
+      fp->seg_quantizer[i] = (int8_t)clampi(fp->seg[i].quant, -127, 127);
+      const int q0 = kAcTable[clampi(fp->seg[0].quant, 0, 127)] >> 2, qi = kAcTable[clampi(fp->seg[i].quant, 0, 127)] >> 2;
+      fp->seg_fstrength[i] = (int8_t)clampi((qi - q0) * o.filter_strength / 100, -63, 63);
+    }
 }
 
 // Between the analysis and mode-search kernels: cluster alphas, derive every per-segment parameter.
@@ -158,62 +221,12 @@ static inline void plan_frame(FramePlan* fp, const wgpu_enc_options& o, int widt
       fp->seg[s].beta = clampi(255 * (centers[s] - min_c) / range_c, 0, 255);
     }
   }
-  // setSegmentParams (encode_analysis.go:122)
-  const int sns = o.sns_strength < 0 ? 0 : o.sns_strength;
-  const double amp = 0.9 * (double)sns / 100.0 / 128.0;
-  const double c_base = quality_to_compression(o.quality);
-  for (int i = 0; i < num_segs; ++i) {
-    const double c = pow(c_base, 1.0 - amp * (double)fp->seg[i].alpha);
-    fp->seg[i].quant = clampi((int)(127.0 * (1.0 - c)), 0, 127);
-  }
-  for (int i = num_segs; i < 4; ++i) fp->seg[i].quant = fp->seg[0].quant;
-  int dq = (global_uv_alpha - 64) * 10 / 70;
-  dq = dq * sns / 100;
-  fp->dq_uv_ac = clampi(dq, -4, 6);
-  fp->dq_uv_dc = clampi(-4 * sns / 100, -15, 15);
-  // setupFilterStrength (encode.go:1276)
-  fp->f_simple = (o.filter_type == 0);
-  fp->f_sharpness = clampi(o.filter_sharpness, 0, 7);
-  if (o.filter_strength <= 0) {
-    fp->f_level = 0;
-  } else {
-    const int level0 = 5 * o.filter_strength, cfg_segs = clampi(o.segments, 1, 4);
-    for (int i = 0; i < cfg_segs; ++i) {
-      const int qstep = kAcTable[clampi(fp->seg[i].quant, 0, 127)] >> 2;
-      int f = kLevelsFromDelta[fp->f_sharpness * 64 + clampi(qstep, 0, 63)] * level0 / (256 + fp->seg[i].beta);
-      if (f < 2) f = 0;
-      if (f > 63) f = 63;
-      fp->seg[i].fstrength = f;
-    }
-    fp->f_level = fp->seg[0].fstrength;
-  }
-  if (num_segs > 1) {  // simplifySegments (encode_analysis.go:197)
-    int smap[4] = {0, 1, 2, 3}, nf = 1;
-    for (int s1 = 1; s1 < num_segs; ++s1) {
-      bool found = false;
-      for (int s2 = 0; s2 < nf; ++s2)
-        if (fp->seg[s1].quant == fp->seg[s2].quant && fp->seg[s1].fstrength == fp->seg[s2].fstrength) { smap[s1] = s2; found = true; break; }
-      if (!found) { smap[s1] = nf; if (nf != s1) fp->seg[nf] = fp->seg[s1]; nf++; }
-    }
-    if (nf < num_segs) {
-      for (int i = 0; i < total; ++i) segment_out[i] = (uint8_t)smap[segment_out[i]];
-      for (int i = nf; i < num_segs; ++i) fp->seg[i] = fp->seg[nf - 1];
-    }
-    num_segs = nf;
-  }
-  fp->num_segments = num_segs;
-  for (int i = 0; i < 4; ++i) setup_segment(fp, o, i);
-  // buildSegmentHeader (encode_analysis.go:852)
-  fp->seg_use = num_segs > 1;
-  fp->seg_update_map = fp->seg_use;
+  fp->global_uv_alpha = global_uv_alpha;
   memset(fp->seg_quantizer, 0, 4);
   memset(fp->seg_fstrength, 0, 4);
-  if (fp->seg_use)
-    for (int i = 0; i < num_segs; ++i) {
-      fp->seg_quantizer[i] = (int8_t)clampi(fp->seg[i].quant, -127, 127);
-      const int q0 = kAcTable[clampi(fp->seg[0].quant, 0, 127)] >> 2, qi = kAcTable[clampi(fp->seg[i].quant, 0, 127)] >> 2;
-      fp->seg_fstrength[i] = (int8_t)clampi((qi - q0) * o.filter_strength / 100, -63, 63);
-    }
+  set_segment_params(fp, o, num_segs, segment_out);
+  num_segs = fp->num_segments;
+  build_segment_header(fp, o, num_segs);
   // setSegmentProbas (encode_analysis.go:874)
   int counts[4] = {0, 0, 0, 0};
   for (int i = 0; i < total; ++i) counts[segment_out[i]]++;

@@ -39,7 +39,8 @@ struct SegQuant {
 // SegmentInfo subset used on the device (internal/lossy/encode.go:278)
 struct SegParams {
   SegQuant y1, y2, uv;
-  int lambda_i4, lambda_i16, lambda_uv, lambda_mode, tlambda_i4, tlambda_i16, tlambda_sd, pad;
+  int lambda_i4, lambda_i16, lambda_uv, lambda_mode, tlambda_i4, tlambda_i16, tlambda_sd;
+  int flags;  // seg[0] only, serial rate-control passes: bits 0-7 per-image max I4 RD modes (0 = launch default), bit 8 = image parked
 };
 
 __device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }

@@ -82,7 +82,7 @@ struct wgpu_ctx {
   DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size;
   PinBuf h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
-  bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false;
+  bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false, e_keep_derr = false, e_keep_stats = false;
   int dither_w = 0, dither_h = 0, dither_amp_cached = 0;  // what the device dither tables currently hold
   wgpu_enc_options e_opt;
   std::vector<wgh::FramePlan> plans;
@@ -132,6 +132,7 @@ void wgpu_enc_options_default(wgpu_enc_options* o, int quality) {
   // DefaultOptions (encode.go:196-214) mapped onto lossy.EncodeConfig (internal/lossy/encode.go:66-86)
   o->quality = quality; o->method = 4; o->sns_strength = 50; o->filter_strength = 60; o->filter_sharpness = 0;
   o->filter_type = 1; o->partitions = 0; o->segments = 4; o->preprocessing = 0; o->has_alpha = 0; o->passes = 1; o->dither_amp = 0;
+  o->target_size = 0; o->target_psnr = 0.f; o->qmin = 0; o->qmax = 100;
 }
 
 static int upload_table(wgpu_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
@@ -268,9 +269,15 @@ static int validate_enc_options(wgpu_ctx* ctx, const wgpu_enc_options* o, int wi
   if (o->dither_amp < 0 || o->dither_amp > 256) FAIL(WGPU_ERR_INVALID, "webp: dithering amplitude out of range [0, 256]");
   // Method < 3: statLoop + serial encodeFrame semantics (non-RD decisions) -- built.  Method >= 3 on frames of fewer than
   // 4 macroblock rows takes the reference's serial RD path (probability refreshes feed the RD costs) -- not built yet.
-  // Built only where no mid-stream probability refresh can occur (<= 96 macroblocks: encode_frame.go:24-40).
-  if (o->method >= 3 && ((height + 15) >> 4) < 4 && ((height + 15) >> 4) * ((width + 15) >> 4) > 96)
-    FAIL(WGPU_ERR_UNSUPPORTED, "Method >= 3 with height <= 48 and more than 96 macroblocks takes the reference's serial RD path with probability refreshes (not built yet)");
+  if (o->target_size < 0) FAIL(WGPU_ERR_INVALID, "webp: invalid TargetSize (must be >= 0)");
+  if (!(o->target_psnr >= 0.f) || o->target_psnr > 1e30f) FAIL(WGPU_ERR_INVALID, "webp: invalid TargetPSNR (must be >= 0, finite)");
+  if (o->qmin < 0 || o->qmax > 100 || (o->qmax > 0 && o->qmin > o->qmax)) FAIL(WGPU_ERR_INVALID, "webp: invalid QMin/QMax (must be 0-100, QMin <= QMax)");
+  // The serial RD path (Method >= 3 on fewer than 4 macroblock rows, or any size under TargetSize / TargetPSNR) is built only
+  // where no mid-stream probability refresh can occur (<= 96 macroblocks: encode_frame.go:24-40).
+  const bool do_search = o->target_size > 0 || o->target_psnr > 0.f;
+  if (do_search && o->method < 3) FAIL(WGPU_ERR_UNSUPPORTED, "TargetSize/TargetPSNR with Method < 3 (rate control over the non-RD serial path) is not built yet");
+  if (o->method >= 3 && (((height + 15) >> 4) < 4 || do_search) && ((height + 15) >> 4) * ((width + 15) >> 4) > 96)
+    FAIL(WGPU_ERR_UNSUPPORTED, "this configuration takes the reference's serial RD path with mid-stream probability refreshes (more than 96 macroblocks): not built yet");
   return WGPU_OK;
 }
 
@@ -484,7 +491,7 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.rec_y = ctx->ry.as<uint8_t>(); P.rec_u = ctx->ru.as<uint8_t>(); P.rec_v = ctx->rv.as<uint8_t>();
   P.segment = ctx->segment.as<uint8_t>(); P.img = ctx->img_params.as<wg::ImageParams>();
   P.stats = ctx->stats.as<unsigned int>();
-  CK(cudaMemsetAsync(ctx->stats.p, 0, (size_t)n * wg::STATS_SIZE * 4, ctx->stream));
+  if (!ctx->e_keep_stats) CK(cudaMemsetAsync(ctx->stats.p, 0, (size_t)n * wg::STATS_SIZE * 4, ctx->stream));  // rate-control passes zero per image
   P.ctx2 = ctx->ctxw2.as<uint32_t>();
   P.ctx = ctx->ctxw.as<uint32_t>(); P.out_hdr = ctx->hdr.as<uint8_t>(); P.out_coeffs = ctx->coeffs.as<int16_t>();
   P.i4_costs = ctx->t_i4cost.as<uint16_t>(); P.lc = ctx->t_lc.as<uint16_t>(); P.eob = ctx->t_eob.as<uint16_t>(); P.lfc = ctx->t_lfc.as<uint16_t>();
@@ -494,9 +501,11 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
   P.top_derr = nullptr; P.left_derr = nullptr;
   int rc;
-  if (ctx->e_opt.method >= 3 && mbh < 4) {  // useParallel == false (encode.go:1356)
+  const bool do_search = ctx->e_opt.target_size > 0 || ctx->e_opt.target_psnr > 0.f;
+  if (ctx->e_opt.method >= 3 && (mbh < 4 || do_search)) {  // useParallel == false (encode.go:1356)
     RESERVE(ctx->derr, (size_t)n * (mbw + 1) * 4);
-    CK(cudaMemsetAsync(ctx->derr.p, 0, (size_t)n * (mbw + 1) * 4, ctx->stream));
+    // topDerr / leftDerr are zeroed when the encoder is created, not between the passes of the rate-control loop
+    if (!ctx->e_keep_derr) CK(cudaMemsetAsync(ctx->derr.p, 0, (size_t)n * (mbw + 1) * 4, ctx->stream));
     P.top_derr = ctx->derr.as<int8_t>();
     P.left_derr = ctx->derr.as<int8_t>() + (size_t)n * mbw * 4;
     rc = launch_enc_serial<8, 4, 3>(ctx, P);
@@ -588,14 +597,100 @@ static int enc_analyze_locked(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
   return WGPU_OK;
 }
 // segment map + per-image parameters (already in the pinned staging buffers) -> device, then all waves
+// Rate control (doSearch: TargetSize / TargetPSNR), internal/lossy/encode.go:1338-1374 + adjustQuantForTarget / computeNextQ
+// (:1505-1590): at least three serial encodeFrame passes; after each one the quality moves by the secant rule on the size of
+// a trial frame (TargetSize) or on the reference's PSNR reading, which is 99.0 dB every time because MBEncInfo.Disto is
+// never written (passes at Q, Q-10, Q-10).  Per image: the images of a batch converge independently, a
+// converged image is parked (seg[0].flags bit 8) while the others go on.  setSegmentParams / buildSegmentHeader are re-run
+// with the new quality -- also after the last pass, whose plan then no longer matches its levels, exactly as in the
+// reference.  Error-diffusion state carries from pass to pass.  Requires the segment map and per-image parameters of the
+// plan (wgpu_enc_device route).
+static int enc_search_rate_control(wgpu_ctx* ctx) {
+  const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
+  if (ctx->plans.size() != (size_t)n) FAIL(WGPU_ERR_UNSUPPORTED, "TargetSize/TargetPSNR need the library's own segment plan (wgpu_enc_device), not wgpu_enc_search");
+  struct RC { bool is_first, active; double dq, q, last_q, qmin, qmax, value, last_value, target; int quality; };
+  const wgpu_enc_options base = ctx->e_opt;
+  const bool do_size = base.target_size > 0;
+  std::vector<RC> rcs(n);
+  for (auto& r : rcs) {  // initPassStats (encode.go:1455)
+    r.is_first = true; r.active = true; r.dq = 10.0;
+    r.qmin = base.qmin; r.qmax = base.qmax <= 0 ? 100.0 : (double)base.qmax;
+    r.q = std::min(std::max((double)base.quality, r.qmin), r.qmax);
+    r.last_q = r.q; r.value = r.last_value = 0;
+    r.target = do_size ? (double)base.target_size : (double)base.target_psnr;
+    r.quality = base.quality;
+  }
+  int max_passes = std::max(base.passes, 1);
+  if (max_passes < 3) max_passes = 3;
+  if (do_size) { RESERVE(ctx->h_hdr, (size_t)n * nmb * 48); RESERVE(ctx->h_coeffs, (size_t)n * nmb * 800); }
+  std::vector<uint32_t> zero_stats(wg::STATS_SIZE, 0);
+  int rc = 0;
+  for (int pass = 0; pass < max_passes; ++pass) {
+    wg::ImageParams* hp = ctx->h_params.as<wg::ImageParams>();
+    for (int i = 0; i < n; ++i) {
+      memcpy(&hp[i], ctx->plans[i].dev, sizeof(wg::ImageParams));
+      hp[i].seg[0].flags = (rcs[i].quality < 50 ? 2 : 3) | (rcs[i].active ? 0 : 0x100);  // getMaxI4RDModes follows the quality
+      if (rcs[i].active) CK(cudaMemsetAsync(ctx->stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE, 0, wg::STATS_SIZE * 4, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(ctx->segment.p, ctx->h_segment.p, (size_t)n * nmb, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)((size_t)n * nmb);
+    CK(cudaMemcpyAsync(ctx->img_params.p, ctx->h_params.p, (size_t)n * sizeof(wg::ImageParams), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)((size_t)n * sizeof(wg::ImageParams));
+    ctx->e_keep_derr = pass > 0; ctx->e_keep_stats = true;
+    rc = enc_launch_waves(ctx);
+    ctx->e_keep_derr = ctx->e_keep_stats = false;
+    if (rc) return rc;
+    if (do_size) {  // trial frame of every image still searching: emitFrame with the probabilities as they stand (defaults)
+      CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, (size_t)n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->xfer_d2h += (uint64_t)((size_t)n * nmb * 48);
+      CK(cudaMemcpyAsync(ctx->h_coeffs.p, ctx->coeffs.p, (size_t)n * nmb * 800, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->xfer_d2h += (uint64_t)((size_t)n * nmb * 800);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));  // the plan below is read by the kernels of this pass until here
+    parallel_for(n, threads_of(ctx), [&](int i) {
+      RC& r = rcs[i];
+      if (!r.active) return;
+      wgh::FramePlan& fp = ctx->plans[i];
+      if (do_size) {
+        std::vector<uint8_t> riff;
+        wgh::serialize_frame(fp, ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
+                             ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, zero_stats.data(), &riff);
+        r.value = (double)((uint32_t)riff[16] | ((uint32_t)riff[17] << 8) | ((uint32_t)riff[18] << 16) | ((uint32_t)riff[19] << 24));  // VP8 payload
+      } else {
+        r.value = 99.0;
+      }
+      if (std::fabs(r.dq) <= 0.4 && !r.is_first) { r.active = false; return; }  // converged (DQ_LIMIT)
+      double dq;  // computeNextQ (encode.go:1505)
+      if (r.is_first) { dq = r.value > r.target ? -r.dq : r.dq; r.is_first = false; }
+      else if (r.value != r.last_value) dq = (r.target - r.value) / (r.last_value - r.value) * (r.last_q - r.q);
+      else dq = 0;
+      dq = std::min(30.0, std::max(-30.0, dq));
+      r.dq = dq; r.last_q = r.q; r.last_value = r.value;
+      r.q = std::min(r.qmax, std::max(r.qmin, r.q + dq));
+      r.quality = (int)(r.q + 0.5);
+      wgpu_enc_options o = base;
+      o.quality = r.quality;
+      wgh::set_segment_params(&fp, o, fp.num_segments, ctx->h_segment.as<uint8_t>() + (size_t)i * nmb);
+      wgh::build_segment_header(&fp, o, fp.num_segments);
+    });
+    bool any = false;
+    for (const auto& r : rcs) any |= r.active;
+    if (!any) break;
+  }
+  return WGPU_OK;
+}
 static int enc_search_locked(wgpu_ctx* ctx) {
   const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
   CK(cudaMemcpyAsync(ctx->segment.p, ctx->h_segment.p, (size_t)n * nmb, cudaMemcpyHostToDevice, ctx->stream));
   ctx->xfer_h2d += (uint64_t)((size_t)n * nmb);
   CK(cudaMemcpyAsync(ctx->img_params.p, ctx->h_params.p, (size_t)n * sizeof(wg::ImageParams), cudaMemcpyHostToDevice, ctx->stream));
   ctx->xfer_h2d += (uint64_t)((size_t)n * sizeof(wg::ImageParams));
-  int rc = enc_launch_waves(ctx);
-  if (rc) return rc;
+  int rc;
+  if (ctx->e_opt.target_size > 0 || ctx->e_opt.target_psnr > 0.f) {
+    if ((rc = enc_search_rate_control(ctx))) return rc;
+  } else if ((rc = enc_launch_waves(ctx))) {
+    return rc;
+  }
   if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3 && (rc = enc_launch_token_prepass(ctx))) return rc;
   ctx->e_done = true;
   return WGPU_OK;

@@ -18,7 +18,8 @@ class EncOptions(C.Structure):
     """wgpu_enc_options == lossy.EncodeConfig (internal/lossy/encode.go:46-63)."""
     _fields_ = [(n, C.c_int) for n in (
         "quality", "method", "sns_strength", "filter_strength", "filter_sharpness", "filter_type",
-        "partitions", "segments", "preprocessing", "has_alpha", "passes", "dither_amp")]
+        "partitions", "segments", "preprocessing", "has_alpha", "passes", "dither_amp", "target_size")] + [
+        ("target_psnr", C.c_float), ("qmin", C.c_int), ("qmax", C.c_int)]
 
 
 class SegQuant(C.Structure):

@@ -130,7 +130,8 @@ def validateConfig(o):
 def lossy_config(o, has_alpha=False):
     """EncoderOptions -> lossy.EncodeConfig (encode.go:478-528 over lossy.DefaultConfig, internal/lossy/encode.go:66-86)."""
     c = native.EncOptions(quality=int(o.Quality), method=o.Method, sns_strength=50, filter_strength=60, filter_sharpness=0,
-                          filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=int(has_alpha), passes=1, dither_amp=0)
+                          filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=int(has_alpha), passes=1, dither_amp=0,
+                          target_size=0, target_psnr=0.0, qmin=0, qmax=100)
     if o.SNSStrength >= 0:
         c.sns_strength = o.SNSStrength
     if o.FilterStrength >= 0:
@@ -144,6 +145,12 @@ def lossy_config(o, has_alpha=False):
     c.preprocessing = o.Preprocessing
     if o.Pass > 0:
         c.passes = o.Pass
+    if o.TargetSize > 0:
+        c.target_size = int(o.TargetSize)
+    if o.TargetPSNR > 0:
+        c.target_psnr = float(np.float32(o.TargetPSNR))
+    c.qmin = int(o.QMin)
+    c.qmax = 100 if o.QMax < 0 else int(o.QMax)  # resolveQMax (encode.go:305-306; -1 is the "unset" sentinel)
     if o.Preprocessing & 2:
         # encode.go:563-567 in float32: x = Quality/100; dithering = 1.0 + (0.5 - 1.0) * x^4; dsp.InitRandom: amp = int(256 * dithering)
         x = np.float32(o.Quality) / np.float32(100.0)
@@ -162,10 +169,8 @@ def _unsupported(o):
         return "webp: Lossless (VP8L) is outside the GPU lossy path"
     if o.UseSharpYUV:
         return "webp: UseSharpYUV is outside the GPU lossy path"
-    if o.TargetSize > 0 or o.TargetPSNR > 0:
-        return "webp: TargetSize/TargetPSNR take the reference's serial multi-pass path (not built yet)"
-    if (o.Pass if o.Pass > 0 else 1) > 1 and o.Method >= 3:
-        return "webp: Pass > 1 with Method >= 3 only matters with TargetSize/TargetPSNR (serial RD path, not built yet)"
+    if (o.TargetSize > 0 or o.TargetPSNR > 0) and o.Method < 3:
+        return "webp: TargetSize/TargetPSNR with Method < 3 (rate control over the non-RD serial path) is not built yet"
     if o.ICC or o.EXIF or o.XMP:
         return "webp: metadata chunks (VP8X container) are host-side container work outside this path"
     return None
