@@ -202,6 +202,12 @@ RC_CASES = [
     (64, 48, [0, 1, 2], dict(TargetSize=600, QMin=20, QMax=90, Pass=6)),
     (96, 96, [2], dict(TargetSize=4000, Segments=1, Quality=90)),
     (128, 96, [1], dict(TargetPSNR=42.0, Partitions=2, Quality=90)),
+    # more than 96 macroblocks: mid-stream probability refreshes feed the RD costs (encode_frame.go:35-57)
+    (256, 256, [0, 1, 2], dict(TargetPSNR=40.0)),                  # 256 MBs: refreshes before macroblocks 96 and 193, three passes
+    (320, 240, [1, 2], dict(TargetSize=9000, Method=6)),           # trial frames carry tokens recorded under mixed tables
+    (640, 48, [0, 2], dict(Method=4)),                             # 120 MBs on 3 rows: serial path without rate control
+    (1600, 40, [1], dict(Method=3, Quality=60)),                   # 300 MBs, all-mode I4 search
+    (200, 150, [0, 1, 2, 4], dict(TargetSize=3000, Quality=50, QMin=10, QMax=80)),
 ]
 
 
@@ -234,15 +240,25 @@ def test_rate_control_passes(oracle, gpu_ctx, w, h, idxs, kw):
         assert files[k] == exp, "image %d: bitstream differs (%d vs %d bytes)" % (i, len(files[k]), len(exp))
 
 
+def test_config4_4k_target_psnr_method6(oracle, gpu_ctx):
+    """BASELINE configs[3]: 3840x2160, Method 6, TargetPSNR multi-pass -- three serial RD passes (Q, Q-10, Q-10: the
+    reference's PSNR reading is always 99 dB) of 32 400 macroblocks with seven probability refreshes each."""
+    w, h = 3840, 2160
+    img = oracle.synth_image(w, h, 1)
+    o = _opts(Method=6, TargetPSNR=42.0)
+    files = webp_b200.EncodeBatch(img[None], o, gpu_ctx)
+    assert files[0] == oracle.encode(img, _ocfg(oracle, o))
+
+
 def test_encode_rejections(gpu_ctx):
     img = np.full((64, 64, 4), 255, np.uint8)
     wide = np.full((40, 16 * 97, 4), 255, np.uint8)
-    with pytest.raises(native.WebPGPUError) as e:  # serial RD path with mid-stream probability refreshes (> 96 macroblocks)
-        webp_b200.EncodeBatch(wide[None], _opts(), gpu_ctx)
+    with pytest.raises(native.WebPGPUError) as e:  # serial RD path with refreshes: one token partition only
+        webp_b200.EncodeBatch(wide[None], _opts(Partitions=2), gpu_ctx)
     assert e.value.code == native.ERR_UNSUPPORTED
     big = np.full((256, 256, 4), 255, np.uint8)
-    with pytest.raises(native.WebPGPUError) as e:  # rate control over more than 96 macroblocks needs the refresh schedule
-        webp_b200.EncodeBatch(big[None], _opts(TargetPSNR=40.0), gpu_ctx)
+    with pytest.raises(native.WebPGPUError) as e:  # the refresh schedule is built for one token partition only
+        webp_b200.EncodeBatch(big[None], _opts(TargetPSNR=40.0, Partitions=1), gpu_ctx)
     assert e.value.code == native.ERR_UNSUPPORTED
     with pytest.raises(webp_b200.WebPError):
         webp_b200.EncodeBatch(img[None], _opts(TargetSize=500, Method=2), gpu_ctx)

@@ -26,6 +26,8 @@ struct EncKernelParams {
   uint32_t* ctx;                // [n][nmb] packed NZ context (see pack_ctx)
   int8_t* top_derr;             // [n][mb_w][2][2] serial RD path: DC error diffusion state (enc.topDerr)
   int8_t* left_derr;            // [n][2][2] (enc.leftDerr)
+  const uint16_t* lc_img;       // [n][LC_SIZE] per-image folded level costs (serial path with probability refreshes), or null
+  const uint16_t* eob_img;      // [n][EOB_SIZE]
   uint32_t* ctx2;               // [n][nmb] Method < 3 / serial RD: trial 4x4 modes of the bottom row / right column (mode-cost context)
   int* progress;                // [n][mb_h] finished macroblocks per row (persistent kernel)
   unsigned long long* work_counter;  // next group to claim (persistent kernel)
@@ -226,7 +228,7 @@ __device__ __forceinline__ Tp ldn(const Tp* p) { return PERSIST ? __ldcg(p) : *p
 // The mode search of MPW = 32/G macroblocks by one warp: macroblock `task_base + lane/G` of wave `wave`.
 template <int G, bool PERSIST, bool FAST, bool SERIAL = false>
 __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wave, long long task_base, MBShared* s_mb_warp,
-                                                const CostTabs& T, const uint16_t* s_i4cost) {
+                                                const CostTabs& T_launch, const uint16_t* s_i4cost) {
   const int lane = threadIdx.x & 31;
   const int g = lane / G, gl = lane % G;
   // rows on this wave: x = wave - 2y in [0, mb_w)
@@ -241,6 +243,10 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   const bool active = task < total && !(img_flags & 0x100);
   const int max_i4_modes = (img_flags & 0xff) ? (img_flags & 0xff) : P.max_i4_modes;
   const int img = active ? (SERIAL ? (int)task : (int)(task / rows)) : 0;
+  // Cost tables: the launch-wide ones in shared memory (constant default probabilities), or -- serial path with mid-stream
+  // probability refreshes (encode_frame.go:35-57) -- this image's own tables in HBM, rebuilt by the host at every refresh.
+  CostTabs T = T_launch;
+  if (SERIAL && P.lc_img != nullptr) { T.lc = P.lc_img + (size_t)img * LC_SIZE; T.eob = P.eob_img + (size_t)img * EOB_SIZE; }
   const int my = active ? (SERIAL ? wave / P.mb_w : y_lo + (int)(task % rows)) : 0;
   const int mx = active ? (SERIAL ? wave - my * P.mb_w : wave - 2 * my) : 0;
   const int nmb = P.mb_w * P.mb_h;
@@ -1141,6 +1147,83 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_fast_wave_kernel(cons
   WG_STAGE_TABLES(WARPS * 32);
   const int warp = threadIdx.x >> 5;
   encode_mb_group<G, false, true>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
+}
+
+// collectAllStats (encode_proba.go:171-313) for the serial path's probability refreshes (encode_frame.go:113-117): token
+// statistics over the WHOLE per-macroblock array as it stands -- macroblocks of this pass above the refresh point, data of
+// the previous pass (or the zero state) below it.  One thread per macroblock; its NZ contexts are rebuilt from the
+// neighbours' headers exactly as the reference's raster walk would carry them: a skipped neighbour leaves zero flags, and the
+// WHT-DC context comes from the nearest I16 macroblock above / to the left (I4 macroblocks do not touch it).
+// hdr [48] = mb_type, i16, uv, segment, skip, nz_dc, 0, 0, modes[16], nz_y[16], nz_uv[8]; stats must be zeroed before.
+struct AllStatsParams {
+  const uint8_t* hdr;      // [n][nmb][48]
+  const int16_t* coeffs;   // [n][nmb][400]
+  unsigned int* stats;     // [n][STATS_SIZE]
+  int n_images, mb_w, mb_h;
+};
+__global__ void __launch_bounds__(128) collect_all_stats_kernel(const AllStatsParams P) {
+  const int nmb = P.mb_w * P.mb_h;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)nmb * P.n_images) return;
+  const int img = (int)(gid / nmb), idx = (int)(gid % nmb), mx = idx % P.mb_w, my = idx / P.mb_w;
+  const uint8_t* H = P.hdr + (size_t)img * nmb * 48;
+  const uint8_t* h = H + (size_t)idx * 48;
+  if (h[4]) return;  // skipped: contributes nothing
+  const int16_t* c = P.coeffs + ((size_t)img * nmb + idx) * 400;
+  unsigned int* st = P.stats + (size_t)img * STATS_SIZE;
+  auto y_flag = [](const uint8_t* n, int b) -> uint32_t { return n[24 + b] > (n[0] == 0 ? 1 : 0); };  // l = nz > first
+  uint32_t top = 0, left = 0;
+  if (my > 0) {
+    const uint8_t* n = h - (size_t)P.mb_w * 48;
+    if (!n[4]) top = y_flag(n, 12) | (y_flag(n, 13) << 1) | (y_flag(n, 14) << 2) | (y_flag(n, 15) << 3) | ((uint32_t)(n[42] > 0) << 4) |
+                     ((uint32_t)(n[43] > 0) << 5) | ((uint32_t)(n[46] > 0) << 6) | ((uint32_t)(n[47] > 0) << 7);
+  }
+  if (mx > 0) {
+    const uint8_t* n = h - 48;
+    if (!n[4]) left = y_flag(n, 3) | (y_flag(n, 7) << 1) | (y_flag(n, 11) << 2) | (y_flag(n, 15) << 3) | ((uint32_t)(n[41] > 0) << 4) |
+                      ((uint32_t)(n[43] > 0) << 5) | ((uint32_t)(n[45] > 0) << 6) | ((uint32_t)(n[47] > 0) << 7);
+  }
+  int first = 0, type = 3;
+  if (h[0] == 0) {
+    int top_dc = 0, left_dc = 0;
+    for (int y = my - 1; y >= 0; --y) {
+      const uint8_t* n = H + (size_t)(y * P.mb_w + mx) * 48;
+      if (n[0] == 0) { top_dc = n[4] ? 0 : (n[5] > 0); break; }
+    }
+    for (int x = mx - 1; x >= 0; --x) {
+      const uint8_t* n = H + (size_t)(my * P.mb_w + x) * 48;
+      if (n[0] == 0) { left_dc = n[4] ? 0 : (n[5] > 0); break; }
+    }
+    stat_block_dev(c + 384, (int)h[5], 1, 0, top_dc + left_dc, st, true);
+    first = 1; type = 0;
+  }
+  uint32_t tnz = top & 0x0f, lnz = left & 0x0f;
+  for (int y = 0; y < 4; ++y) {
+    uint32_t l = lnz & 1;
+    for (int x = 0; x < 4; ++x) {
+      const int b = y * 4 + x, nz = h[24 + b];
+      stat_block_dev(c + b * 16, nz, type, first, (int)(l + (tnz & 1)), st, false);
+      l = nz > first;
+      tnz = (tnz >> 1) | (l << 7);
+    }
+    tnz >>= 4;
+    lnz = (lnz >> 1) | (l << 7);
+  }
+  for (int ch = 0; ch < 4; ch += 2) {
+    tnz = (top >> (4 + ch)) & 0x0f;
+    lnz = (left >> (4 + ch)) & 0x0f;
+    for (int y = 0; y < 2; ++y) {
+      uint32_t l = lnz & 1;
+      for (int x = 0; x < 2; ++x) {
+        const int k = (ch / 2) * 4 + y * 2 + x, nz = h[40 + k];
+        stat_block_dev(c + (16 + k) * 16, nz, 2, 0, (int)(l + (tnz & 1)), st, false);
+        l = nz > 0;
+        tnz = (tnz >> 1) | (l << 3);
+      }
+      tnz >>= 2;
+      lnz = (lnz >> 1) | (l << 5);
+    }
+  }
 }
 
 // Serial RD path (Method >= 3 where the reference does not go row-parallel): macroblocks in raster order, one launch per

@@ -803,6 +803,69 @@ static inline int optimize_proba_host(const Stats st, uint8_t proba[4][8][3][11]
   return updates;
 }
 
+// Serial RD path with mid-stream probability refreshes (encode_frame.go:35-57), single token partition: tokens are recorded
+// while the frame is encoded, each macroblock under the probabilities in force when it was encoded (tabs[k] from macroblock
+// index tab_start[k] on); after a successful final optimizeProba they are all re-recorded under the final table (then
+// n_tabs == 1).  Partition 0 carries part0_proba (what the decoder will use).
+static inline void serialize_frame_tables(const FramePlan& fp, const uint8_t* mb_hdr, const int16_t* mb_coeffs, const uint8_t* segment_map,
+                                          const uint8_t* part0_proba /*[1056]*/, int n_tabs, const int* tab_start, const uint8_t* const* tabs,
+                                          std::vector<uint8_t>* riff) {
+  const int mb_w = fp.mb_w, mb_h = fp.mb_h, total = mb_w * mb_h;
+  const int num_skip = count_skips(mb_hdr, total);
+  const int skip_proba = num_skip > 0 ? (total - num_skip) * 255 / total : 0;
+  std::vector<uint8_t> part0;
+  part0.reserve((size_t)total * 4 + 2048);
+  emit_partition0(fp, mb_hdr, segment_map, part0_proba, num_skip, skip_proba, &part0);
+  const size_t hdr_pos = riff->size();
+  riff->resize(hdr_pos + 20 + 10);
+  riff->insert(riff->end(), part0.begin(), part0.end());
+  std::vector<uint8_t> part;
+  part.reserve((size_t)total * 32 + 4096);
+  {
+    BoolEnc bw(&part);
+    std::vector<uint32_t> top_nz(mb_w, 0u);
+    std::vector<uint8_t> top_dc(mb_w, 0);
+    int k = 0;
+    for (int my = 0; my < mb_h; ++my) {
+      uint32_t left_nz = 0;
+      uint8_t left_dc = 0;
+      for (int mx = 0; mx < mb_w; ++mx) {
+        const int idx = my * mb_w + mx;
+        while (k + 1 < n_tabs && idx >= tab_start[k + 1]) ++k;
+        const uint8_t (*pp)[8][3][11] = reinterpret_cast<const uint8_t (*)[8][3][11]>(tabs[k]);
+        const MBView m{mb_hdr + (size_t)idx * 48, mb_coeffs + (size_t)idx * 400};
+        if (m.skip()) {
+          top_nz[mx] = 0; left_nz = 0;
+          if (m.mb_type() == 0) { top_dc[mx] = 0; left_dc = 0; }
+          continue;
+        }
+        walk_mb(m, &top_nz[mx], &left_nz, &top_dc[mx], &left_dc,
+                [&](const int16_t* c, int nz, int type, int first, int ctx) { code_block(bw, pp[type], c, nz, first, ctx > 2 ? 2 : ctx); });
+      }
+    }
+    bw.finish();
+  }
+  riff->insert(riff->end(), part.begin(), part.end());
+  finish_riff(fp, hdr_pos, part0.size(), riff);
+}
+
+// Folded per-(type, band, ctx, level) token costs of a probability table (vp8_dev.cuh CostTabs; TokenCostForCoeffs,
+// encode_quant.go:170, with variableLevelCost :248 folded in up to level 67).
+static inline void build_cost_tables(const uint8_t* proba /*[1056]*/, uint16_t* lc /*[4*8*3*68]*/, uint16_t* eobc /*[96]*/) {
+  for (int tbc = 0; tbc < 4 * 8 * 3; ++tbc) {
+    const uint8_t* p = proba + tbc * 11;
+    eobc[tbc] = kEntropyCost[p[0]];
+    const int not_eob = kEntropyCost[255 - p[0]];
+    lc[tbc * 68] = (uint16_t)(not_eob + kEntropyCost[p[1]]);
+    for (int v = 1; v < 68; ++v) {
+      int pattern = kLevelCodes[2 * (v - 1)], bits = kLevelCodes[2 * (v - 1) + 1], cost = 0;
+      for (int i = 2; pattern; ++i, bits >>= 1, pattern >>= 1)
+        if (pattern & 1) cost += bit_cost(bits & 1, p[i]);
+      lc[tbc * 68 + v] = (uint16_t)(not_eob + kEntropyCost[255 - p[1]] + cost);
+    }
+  }
+}
+
 // Serial-path serialiser (Method < 3: statLoop + encodeFrame, encode.go:1334-1400, encode_frame.go:15-108).  The GPU's
 // mode decisions on this path do not depend on the coefficient probabilities, so one device pass gives the content
 // of mbInfo for every reference pass; what the host restates is the evolution of enc.proba:

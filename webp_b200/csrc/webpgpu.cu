@@ -79,13 +79,19 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size;
-  PinBuf h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, lc_img, eob_img;
+  PinBuf h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false, e_keep_derr = false, e_keep_stats = false;
   int dither_w = 0, dither_h = 0, dither_amp_cached = 0;  // what the device dither tables currently hold
   wgpu_enc_options e_opt;
   std::vector<wgh::FramePlan> plans;
+  // serial RD path with mid-stream probability refreshes: per-image probability state (carried across refreshes and
+  // rate-control passes, like enc.proba), its history over the last pass (what each macroblock's tokens were recorded under)
+  std::vector<uint8_t> sp_proba;
+  std::vector<std::vector<uint8_t>> sp_hist;  // [image] -> tables [k][1056] in force from macroblock sp_starts[k] on
+  std::vector<int> sp_starts;
+  bool e_refresh_route = false;
   // decoder state
   DevBuf d_coeffs, d_meta, d_ftype, dy, du, dv, d_nrgba, d_alpha;
   PinBuf hd_coeffs, hd_meta, hd_ftype, hd_planes, hd_nrgba;
@@ -177,19 +183,9 @@ int wgpu_ctx_create(int device_ordinal, wgpu_ctx** out) {
   l2g[33] = 255;
   int rc = 0;
   // folded per-(type, band, ctx, level) token costs under the default probabilities (vp8_dev.cuh CostTabs)
+  static_assert(wg::LC_LEVELS == 68, "host_enc.h build_cost_tables folds 68 levels");
   static uint16_t lc[wg::LC_SIZE], eobc[wg::EOB_SIZE];
-  for (int tbc = 0; tbc < 4 * 8 * 3; ++tbc) {
-    const uint8_t* p = &wgh::kCoeffsProba0[tbc * 11];
-    eobc[tbc] = wgh::kEntropyCost[p[0]];
-    const int not_eob = wgh::kEntropyCost[255 - p[0]];
-    lc[tbc * wg::LC_LEVELS] = (uint16_t)(not_eob + wgh::kEntropyCost[p[1]]);
-    for (int v = 1; v < wg::LC_LEVELS; ++v) {  // variableLevelCost (encode_quant.go:248)
-      int pattern = wgh::kLevelCodes[2 * (v - 1)], bits = wgh::kLevelCodes[2 * (v - 1) + 1], cost = 0;
-      for (int i = 2; pattern; ++i, bits >>= 1, pattern >>= 1)
-        if (pattern & 1) cost += wgh::bit_cost(bits & 1, p[i]);
-      lc[tbc * wg::LC_LEVELS + v] = (uint16_t)(not_eob + wgh::kEntropyCost[255 - p[1]] + cost);
-    }
-  }
+  wgh::build_cost_tables(wgh::kCoeffsProba0, lc, eobc);
   rc |= upload_table(ctx, ctx->t_lc, lc, sizeof(lc));
   rc |= upload_table(ctx, ctx->t_eob, eobc, sizeof(eobc));
   rc |= upload_table(ctx, ctx->t_lfc, wgh::kLevelFixedCosts, sizeof(wgh::kLevelFixedCosts));
@@ -208,14 +204,14 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size,
+  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
                   &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
                   &ctx->m_sse, &ctx->m_ssim};
   for (DevBuf* b : db) b->release();
-  PinBuf* pb[] = {&ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
+  PinBuf* pb[] = {&ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
                   &ctx->hd_meta, &ctx->hd_ftype, &ctx->hd_planes, &ctx->hd_nrgba};
   for (PinBuf* b : pb) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -276,8 +272,8 @@ static int validate_enc_options(wgpu_ctx* ctx, const wgpu_enc_options* o, int wi
   // where no mid-stream probability refresh can occur (<= 96 macroblocks: encode_frame.go:24-40).
   const bool do_search = o->target_size > 0 || o->target_psnr > 0.f;
   if (do_search && o->method < 3) FAIL(WGPU_ERR_UNSUPPORTED, "TargetSize/TargetPSNR with Method < 3 (rate control over the non-RD serial path) is not built yet");
-  if (o->method >= 3 && (((height + 15) >> 4) < 4 || do_search) && ((height + 15) >> 4) * ((width + 15) >> 4) > 96)
-    FAIL(WGPU_ERR_UNSUPPORTED, "this configuration takes the reference's serial RD path with mid-stream probability refreshes (more than 96 macroblocks): not built yet");
+  if (o->method >= 3 && (((height + 15) >> 4) < 4 || do_search) && ((height + 15) >> 4) * ((width + 15) >> 4) > 96 && o->partitions > 0)
+    FAIL(WGPU_ERR_UNSUPPORTED, "the serial RD path with mid-stream probability refreshes (more than 96 macroblocks) is built for one token partition only");
   return WGPU_OK;
 }
 
@@ -354,7 +350,7 @@ int launch_enc_fast_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {  // Met
 }
 // Serial RD path (Method >= 3, fewer than 4 macroblock rows): raster order, one launch per macroblock index over the batch.
 template <int G, int WARPS, int MINB>
-int launch_enc_serial(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
+int launch_enc_serial(wgpu_ctx* ctx, const wg::EncKernelParams& P, int mb_begin, int mb_end) {
   constexpr int per_cta = WARPS * (32 / G);
   constexpr size_t smem = sizeof(wg::MBShared) * per_cta;
   static bool attr_set = false;
@@ -364,7 +360,7 @@ int launch_enc_serial(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
     attr_set = true;
   }
   const unsigned grid = (unsigned)((P.n_images + per_cta - 1) / per_cta);
-  for (int i = 0; i < P.mb_w * P.mb_h; ++i) {
+  for (int i = mb_begin; i < mb_end; ++i) {
     wg::encode_serial_kernel<G, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(P, i);
     ctx->launches++;
   }
@@ -484,6 +480,7 @@ static int enc_launch_analysis(wgpu_ctx* ctx) {
   return WGPU_OK;
 }
 static int enc_launch_waves(wgpu_ctx* ctx) {
+  ctx->e_refresh_route = false;
   const int n = ctx->e_n, mbw = ctx->e_mbw, mbh = ctx->e_mbh, nmb = mbw * mbh;
   wg::EncKernelParams P;
   P.progress = nullptr; P.work_counter = nullptr; P.wave_start = nullptr; P.total_groups = 0; P.error_flag = nullptr;
@@ -499,7 +496,7 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.method = ctx->e_opt.method;
   P.max_i4_modes = ctx->e_opt.quality < 50 ? 2 : 3;  // getMaxI4RDModes (encode_parallel.go:931)
   P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
-  P.top_derr = nullptr; P.left_derr = nullptr;
+  P.top_derr = nullptr; P.left_derr = nullptr; P.lc_img = nullptr; P.eob_img = nullptr;
   int rc;
   const bool do_search = ctx->e_opt.target_size > 0 || ctx->e_opt.target_psnr > 0.f;
   if (ctx->e_opt.method >= 3 && (mbh < 4 || do_search)) {  // useParallel == false (encode.go:1356)
@@ -508,8 +505,74 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
     if (!ctx->e_keep_derr) CK(cudaMemsetAsync(ctx->derr.p, 0, (size_t)n * (mbw + 1) * 4, ctx->stream));
     P.top_derr = ctx->derr.as<int8_t>();
     P.left_derr = ctx->derr.as<int8_t>() + (size_t)n * mbw * 4;
-    rc = launch_enc_serial<8, 4, 3>(ctx, P);
-    if (rc) return rc;
+    // refreshProbas every max(total >> 3, 96) macroblocks (encode_frame.go:24-47): before macroblock k*M + (k-1), k = 1, 2, ..
+    const int max_count = std::max(nmb >> 3, 96);
+    ctx->e_refresh_route = nmb > max_count;
+    if (!ctx->e_refresh_route) {
+      rc = launch_enc_serial<8, 4, 3>(ctx, P, 0, nmb);
+      if (rc) return rc;
+      CK(cudaGetLastError());
+      return WGPU_OK;
+    }
+    // ---- with refreshes: the RD costs follow the per-image probability state, rebuilt on the host at every refresh from
+    // statistics over the whole per-macroblock array (this pass above the refresh point, the previous pass or the zero
+    // state below it)
+    if (!ctx->e_keep_derr) {  // first pass of this encode: default probabilities, zero-state macroblock array
+      ctx->sp_proba.resize((size_t)n * 1056);
+      for (int i = 0; i < n; ++i) memcpy(&ctx->sp_proba[(size_t)i * 1056], wgh::kCoeffsProba0, 1056);
+      CK(cudaMemsetAsync(ctx->hdr.p, 0, (size_t)n * nmb * 48, ctx->stream));
+    }
+    P.stats = nullptr;  // statistics are taken by collect_all_stats_kernel, over the whole array
+    RESERVE(ctx->lc_img, (size_t)n * wg::LC_SIZE * 2); RESERVE(ctx->eob_img, (size_t)n * wg::EOB_SIZE * 2);
+    RESERVE(ctx->h_lc_img, (size_t)n * (wg::LC_SIZE + wg::EOB_SIZE) * 2);
+    RESERVE(ctx->h_stats, (size_t)n * wg::STATS_SIZE * 4);
+    P.lc_img = ctx->lc_img.as<uint16_t>(); P.eob_img = ctx->eob_img.as<uint16_t>();
+    const wg::ImageParams* hp = ctx->h_params.as<wg::ImageParams>();  // seg[0].flags bit 8: parked by the rate-control loop
+    ctx->sp_hist.resize(n); ctx->sp_starts.clear();
+    for (int i = 0; i < n; ++i) if (!(hp[i].seg[0].flags & 0x100)) ctx->sp_hist[i].clear();
+    auto upload_tables = [&](int first_mb) -> int {
+      uint16_t* hl = ctx->h_lc_img.as<uint16_t>();
+      uint16_t* he = hl + (size_t)n * wg::LC_SIZE;
+      parallel_for(n, threads_of(ctx), [&](int i) { wgh::build_cost_tables(&ctx->sp_proba[(size_t)i * 1056], hl + (size_t)i * wg::LC_SIZE, he + (size_t)i * wg::EOB_SIZE); });
+      CK(cudaMemcpyAsync(ctx->lc_img.p, hl, (size_t)n * wg::LC_SIZE * 2, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->xfer_h2d += (uint64_t)((size_t)n * wg::LC_SIZE * 2);
+      CK(cudaMemcpyAsync(ctx->eob_img.p, he, (size_t)n * wg::EOB_SIZE * 2, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->xfer_h2d += (uint64_t)((size_t)n * wg::EOB_SIZE * 2);
+      for (int i = 0; i < n; ++i)
+        if (!(hp[i].seg[0].flags & 0x100)) ctx->sp_hist[i].insert(ctx->sp_hist[i].end(), &ctx->sp_proba[(size_t)i * 1056], &ctx->sp_proba[(size_t)i * 1056] + 1056);
+      ctx->sp_starts.push_back(first_mb);
+      return WGPU_OK;
+    };
+    auto all_stats = [&]() -> int {
+      wg::AllStatsParams A;
+      A.hdr = ctx->hdr.as<uint8_t>(); A.coeffs = ctx->coeffs.as<int16_t>(); A.stats = ctx->stats.as<unsigned int>();
+      A.n_images = n; A.mb_w = mbw; A.mb_h = mbh;
+      CK(cudaMemsetAsync(ctx->stats.p, 0, (size_t)n * wg::STATS_SIZE * 4, ctx->stream));
+      wg::collect_all_stats_kernel<<<(unsigned)(((long long)n * nmb + 127) / 128), 128, 0, ctx->stream>>>(A);
+      ctx->launches++;
+      CK(cudaGetLastError());
+      return WGPU_OK;
+    };
+    if ((rc = upload_tables(0))) return rc;
+    int start = 0;
+    for (int k = 1;; ++k) {
+      const int end = std::min(k * max_count + (k - 1), nmb);
+      if ((rc = launch_enc_serial<8, 4, 3>(ctx, P, start, end))) return rc;
+      if (end >= nmb) break;
+      if ((rc = all_stats())) return rc;
+      CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->stats.p, (size_t)n * wg::STATS_SIZE * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->xfer_d2h += (uint64_t)((size_t)n * wg::STATS_SIZE * 4);
+      CK(cudaStreamSynchronize(ctx->stream));  // also: the table upload of the previous refresh has been consumed
+      // images parked by the rate-control loop keep their state (their macroblocks are not re-encoded either)
+      parallel_for(n, threads_of(ctx), [&](int i) {
+        if (hp[i].seg[0].flags & 0x100) return;
+        wgh::optimize_proba_host(*reinterpret_cast<const wgh::Stats*>(ctx->h_stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE),
+                                 *reinterpret_cast<uint8_t (*)[4][8][3][11]>(&ctx->sp_proba[(size_t)i * 1056]));
+      });
+      if ((rc = upload_tables(end))) return rc;
+      start = end;
+    }
+    if ((rc = all_stats())) return rc;  // collectAllStats for the final optimizeProba (encode.go:1378)
     CK(cudaGetLastError());
     return WGPU_OK;
   }
@@ -653,8 +716,17 @@ static int enc_search_rate_control(wgpu_ctx* ctx) {
       wgh::FramePlan& fp = ctx->plans[i];
       if (do_size) {
         std::vector<uint8_t> riff;
-        wgh::serialize_frame(fp, ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
-                             ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, zero_stats.data(), &riff);
+        if (ctx->e_refresh_route) {  // tokens as recorded during the pass: each stretch under the table then in force
+          const int nt = (int)ctx->sp_starts.size();
+          std::vector<const uint8_t*> tabs(nt);
+          for (int k = 0; k < nt; ++k) tabs[k] = &ctx->sp_hist[i][(size_t)k * 1056];
+          wgh::serialize_frame_tables(fp, ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
+                                      ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, &ctx->sp_proba[(size_t)i * 1056], nt, ctx->sp_starts.data(),
+                                      tabs.data(), &riff);
+        } else {
+          wgh::serialize_frame(fp, ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
+                               ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, zero_stats.data(), &riff);
+        }
         r.value = (double)((uint32_t)riff[16] | ((uint32_t)riff[17] << 8) | ((uint32_t)riff[18] << 16) | ((uint32_t)riff[19] << 24));  // VP8 payload
       } else {
         r.value = 99.0;
@@ -691,7 +763,7 @@ static int enc_search_locked(wgpu_ctx* ctx) {
   } else if ((rc = enc_launch_waves(ctx))) {
     return rc;
   }
-  if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3 && (rc = enc_launch_token_prepass(ctx))) return rc;
+  if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3 && !ctx->e_refresh_route && (rc = enc_launch_token_prepass(ctx))) return rc;
   ctx->e_done = true;
   return WGPU_OK;
 }
@@ -801,7 +873,38 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
   RESERVE(ctx->h_hdr, n * nmb * 48);
   std::atomic<int> too_small(0);
   const double t0 = now_ms();
-  if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3 && device_coder_wanted(ctx, n)) {
+  if (ctx->e_refresh_route) {
+    // ---- serial RD path with probability refreshes: final optimizeProba on top of the state the refreshes left (a slot that
+    // does not beat the default keeps what an earlier refresh wrote), then all tokens under the final table -- or, if
+    // nothing changed, as recorded during the pass (encode.go:1376-1383); levels come back, the host serialises
+    RESERVE(ctx->h_coeffs, n * nmb * 800);
+    CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(n * nmb * 48);
+    CK(cudaMemcpyAsync(ctx->h_coeffs.p, ctx->coeffs.p, n * nmb * 800, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(n * nmb * 800);
+    CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->stats.p, n * wg::STATS_SIZE * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(n * wg::STATS_SIZE * 4);
+    CK(cudaStreamSynchronize(ctx->stream));
+    parallel_for((int)n, threads_of(ctx), [&](int i) {
+      uint8_t final_proba[1056];
+      memcpy(final_proba, &ctx->sp_proba[(size_t)i * 1056], 1056);
+      const int updates = wgh::optimize_proba_host(*reinterpret_cast<const wgh::Stats*>(ctx->h_stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE),
+                                                   *reinterpret_cast<uint8_t (*)[4][8][3][11]>(final_proba));
+      const int nt = updates > 0 ? 1 : (int)ctx->sp_starts.size();
+      std::vector<const uint8_t*> tabs(nt);
+      const int zero = 0;
+      if (updates > 0) tabs[0] = final_proba;
+      else for (int k = 0; k < nt; ++k) tabs[k] = &ctx->sp_hist[i][(size_t)k * 1056];
+      std::vector<uint8_t> riff;
+      riff.reserve(nmb * 64 + 4096);
+      wgh::serialize_frame_tables(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_coeffs.as<int16_t>() + (size_t)i * nmb * 400,
+                                  ctx->h_segment.as<uint8_t>() + (size_t)i * nmb, final_proba, nt, updates > 0 ? &zero : ctx->sp_starts.data(),
+                                  tabs.data(), &riff);
+      out_sizes[i] = riff.size();
+      if (riff.size() > out_stride) { too_small.store(1); return; }
+      memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
+    });
+  } else if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3 && device_coder_wanted(ctx, n)) {
     // ---- single partition: tokens are generated AND boolean-coded on the GPU (token_kernel, boolcode_kernel); the host
     // emits partition 0 (modes, a few bits per macroblock) while the coder runs, then lays the frames out
     CK(cudaStreamSynchronize(ctx->stream));  // waves + token pre-pass done, per-image totals on the host
