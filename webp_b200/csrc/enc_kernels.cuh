@@ -28,6 +28,7 @@ struct EncKernelParams {
   int8_t* left_derr;            // [n][2][2] (enc.leftDerr)
   const uint16_t* lc_img;       // [n][LC_SIZE] per-image folded level costs (serial path with probability refreshes), or null
   const uint16_t* eob_img;      // [n][EOB_SIZE]
+  int serial_gpw;               // encode_serial_tab_kernel: macroblock groups (images) per warp actually used, 1..32/G (0 = all)
   uint32_t* ctx2;               // [n][nmb] Method < 3 / serial RD: trial 4x4 modes of the bottom row / right column (mode-cost context)
   int* progress;                // [n][mb_h] finished macroblocks per row (persistent kernel)
   unsigned long long* work_counter;  // next group to claim (persistent kernel)
@@ -239,14 +240,11 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   // SERIAL (the reference's serial encodeFrame order): `wave` is the raster macroblock index, one macroblock per image per
   // launch.  Rate-control passes (adjustQuantForTarget) re-encode only the images that have not converged: bit 8 of
   // seg[0].flags parks an image, bits 0-7 carry its own getMaxI4RDModes (its quality moves with the search).
-  const int img_flags = (SERIAL && task < total) ? P.img[(int)task].seg[0].flags : 0;
-  const bool active = task < total && !(img_flags & 0x100);
+  const int img_flags = (SERIAL && task < total && (P.serial_gpw == 0 || g < P.serial_gpw)) ? P.img[(int)task].seg[0].flags : 0;
+  const bool active = task < total && !(img_flags & 0x100) && (!SERIAL || P.serial_gpw == 0 || g < P.serial_gpw);
   const int max_i4_modes = (img_flags & 0xff) ? (img_flags & 0xff) : P.max_i4_modes;
   const int img = active ? (SERIAL ? (int)task : (int)(task / rows)) : 0;
-  // Cost tables: the launch-wide ones in shared memory (constant default probabilities), or -- serial path with mid-stream
-  // probability refreshes (encode_frame.go:35-57) -- this image's own tables in HBM, rebuilt by the host at every refresh.
-  CostTabs T = T_launch;
-  if (SERIAL && P.lc_img != nullptr) { T.lc = P.lc_img + (size_t)img * LC_SIZE; T.eob = P.eob_img + (size_t)img * EOB_SIZE; }
+  const CostTabs& T = T_launch;  // launch-wide tables, or this macroblock's image's own (encode_serial_tab_kernel)
   const int my = active ? (SERIAL ? wave / P.mb_w : y_lo + (int)(task % rows)) : 0;
   const int mx = active ? (SERIAL ? wave - my * P.mb_w : wave - 2 * my) : 0;
   const int nmb = P.mb_w * P.mb_h;
@@ -1235,6 +1233,37 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_serial_kernel(const E
   WG_STAGE_TABLES(WARPS * 32);
   const int warp = threadIdx.x >> 5;
   encode_mb_group<G, false, false, true>(P, mb_index, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
+}
+
+// Serial RD path with mid-stream probability refreshes (encode_frame.go:35-57): the RD costs follow each image's own
+// probability state, so every macroblock group works from ITS image's folded cost tables (rebuilt by the host at each
+// refresh, P.lc_img / P.eob_img), staged into shared memory next to the group's work buffers -- the Viterbi reads them a
+// dozen times per coefficient position, and from HBM/L2 that latency dominated the pass (380 us per macroblock step).
+// One warp per CTA: 4 macroblocks = 4 images = 4 x 13.4 KB of tables.
+template <int G>
+__global__ void __launch_bounds__(32, 2) encode_serial_tab_kernel(const EncKernelParams P, int mb_index) {
+  // Macroblocks that share a warp run their data-dependent control flow one after the other (a step takes ~130 us for one
+  // group per warp, ~310 us for four), and this path is a chain of 3 x mbW x mbH such steps with the GPU nearly empty: the
+  // host picks P.serial_gpw = 1 group per warp while the batch leaves SMs to spare.
+  const int gpw = P.serial_gpw;
+  WG_STAGE_TABLES(32);
+  uint16_t* s_tabs = reinterpret_cast<uint16_t*>(s_mb + 32 / G);  // [gpw][LC_SIZE + EOB_SIZE], after a work buffer for every group slot
+  const long long task_base = (long long)blockIdx.x * gpw;
+  for (int g = 0; g < gpw; ++g) {
+    const long long img = task_base + g;
+    if (img >= P.n_images) break;
+    uint4* dst = reinterpret_cast<uint4*>(s_tabs + (size_t)g * (LC_SIZE + EOB_SIZE));
+    const uint4* a = reinterpret_cast<const uint4*>(P.lc_img + (size_t)img * LC_SIZE);
+    const uint4* b = reinterpret_cast<const uint4*>(P.eob_img + (size_t)img * EOB_SIZE);
+    for (int i = threadIdx.x; i < LC_SIZE / 8; i += 32) dst[i] = a[i];
+    for (int i = threadIdx.x; i < EOB_SIZE / 8; i += 32) dst[LC_SIZE / 8 + i] = b[i];
+  }
+  __syncwarp();
+  CostTabs Tg = T;
+  const int g = min((int)(threadIdx.x & 31) / G, gpw - 1);
+  Tg.lc = s_tabs + (size_t)g * (LC_SIZE + EOB_SIZE);
+  Tg.eob = Tg.lc + LC_SIZE;
+  encode_mb_group<G, false, false, true>(P, mb_index, task_base, s_mb, Tg, s_i4cost);
 }
 
 // The whole mode search in ONE launch: persistent warps claim groups of 32/G macroblocks in wave order from a global

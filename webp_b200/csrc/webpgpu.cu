@@ -366,6 +366,29 @@ int launch_enc_serial(wgpu_ctx* ctx, const wg::EncKernelParams& P, int mb_begin,
   }
   return WGPU_OK;
 }
+// Serial RD path with probability refreshes: as launch_enc_serial, each macroblock group with its image's own cost tables.
+int launch_enc_serial_tab(wgpu_ctx* ctx, wg::EncKernelParams& P, int mb_begin, int mb_end) {
+  constexpr int G = 8;
+  static int sm_count = 0;
+  if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->dev);
+  // one macroblock group (image) per warp while the batch leaves SMs to spare, then 2, then 4 (see the kernel)
+  const int gpw = P.n_images <= 8 * sm_count ? 1 : (P.n_images <= 24 * sm_count ? 2 : 4);
+  P.serial_gpw = gpw;
+  const size_t smem = sizeof(wg::MBShared) * (32 / G) + (size_t)gpw * (wg::LC_SIZE + wg::EOB_SIZE) * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    const size_t max_smem = sizeof(wg::MBShared) * 4 + (size_t)4 * (wg::LC_SIZE + wg::EOB_SIZE) * 2;
+    cudaError_t e = cudaFuncSetAttribute(wg::encode_serial_tab_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+    if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)((P.n_images + gpw - 1) / gpw);
+  for (int i = mb_begin; i < mb_end; ++i) {
+    wg::encode_serial_tab_kernel<G><<<grid, 32, smem, ctx->stream>>>(P, i);
+    ctx->launches++;
+  }
+  return WGPU_OK;
+}
 // Persistent dataflow launch: one kernel for all waves (see encode_persistent_kernel).
 template <int G, int WARPS, int MINB>
 int launch_enc_persistent(wgpu_ctx* ctx, wg::EncKernelParams& P) {
@@ -496,7 +519,7 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.method = ctx->e_opt.method;
   P.max_i4_modes = ctx->e_opt.quality < 50 ? 2 : 3;  // getMaxI4RDModes (encode_parallel.go:931)
   P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
-  P.top_derr = nullptr; P.left_derr = nullptr; P.lc_img = nullptr; P.eob_img = nullptr;
+  P.top_derr = nullptr; P.left_derr = nullptr; P.lc_img = nullptr; P.eob_img = nullptr; P.serial_gpw = 0;
   int rc;
   const bool do_search = ctx->e_opt.target_size > 0 || ctx->e_opt.target_psnr > 0.f;
   if (ctx->e_opt.method >= 3 && (mbh < 4 || do_search)) {  // useParallel == false (encode.go:1356)
@@ -557,7 +580,7 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
     int start = 0;
     for (int k = 1;; ++k) {
       const int end = std::min(k * max_count + (k - 1), nmb);
-      if ((rc = launch_enc_serial<8, 4, 3>(ctx, P, start, end))) return rc;
+      if ((rc = launch_enc_serial_tab(ctx, P, start, end))) return rc;
       if (end >= nmb) break;
       if ((rc = all_stats())) return rc;
       CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->stats.p, (size_t)n * wg::STATS_SIZE * 4, cudaMemcpyDeviceToHost, ctx->stream));
