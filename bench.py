@@ -266,9 +266,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": "encode_wave_kernel (%d wave launches per step, timed together)" % waves, "achieved": ach,
                 "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (wave 110 of 222: 12288 macroblocks = 3.15 Mpix, 20.3 MB
-                # algorithmic) from the ncu --set full capture in profiles/r1_mode_search_f_full_size_wave110.md
-                "traffic": 116.7e6, "traffic_launch": "wave 110 of 222 (12288 macroblocks, 20.3 MB algorithmic)",
-                "note": "bound by dependent-instruction latency x the 222-step wavefront chain (issue slots 38 % busy), not by HBM; see DESIGN.md 5",
+                # algorithmic) from the ncu --set full capture in profiles/r1_mode_search_h_end_of_round.md
+                "traffic": 115.5e6, "traffic_launch": "wave 110 of 222 (12288 macroblocks, 20.3 MB algorithmic)",
+                "note": "bound by dependent-instruction latency x the 222-step wavefront chain (issue slots 45 % busy), not by HBM; see DESIGN.md 5",
                 "stages_ms": stage_ms,
                 "stages_gbs": {k: ALG_BYTES_PER_PX[k] * px_step / (v * 1e-3) / 1e9 for k, v in stage_ms.items()}}
     result = {"metric": "lossy encode & decode Mpix/s (1536x1024 q75 m4), bit-exact", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": K,
