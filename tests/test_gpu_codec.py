@@ -275,8 +275,16 @@ DEC_CASES = [(128, 96, (2, 1, 0), {}), (100, 70, (2, 1, 0), {}), (130, 71, (2, 1
              (768, 576, (2, 1, 0), dict(segments=1)), (64, 64, (2, 1, 0), dict(quality=10))]
 
 
+@pytest.fixture(params=["0", "1"], ids=["host_parser", "gpu_parser"])
+def parser_route(request, monkeypatch):
+    """Macroblock parsing (intra modes + coefficient tokens) on the host (host_dec.h::parse_frame) or on the GPU
+    (dec_parse_kernel: decode_tree.go:35, decode_mb.go:111-313); the library picks by batch size, the tests force both."""
+    monkeypatch.setenv("WGPU_DEVICE_PARSER", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("w,h,idxs,kw", DEC_CASES)
-def test_decode_planes_and_nrgba(oracle, gpu_ctx, w, h, idxs, kw):
+def test_decode_planes_and_nrgba(oracle, gpu_ctx, parser_route, w, h, idxs, kw):
     streams = [oracle.encode(oracle.synth_image(w, h, i), oracle.default_cfg(**kw)) for i in idxs]
     gw, gh, y, u, v, rgba = webp_b200.webp.decode_padded(streams, nrgba=True, ctx=gpu_ctx)
     assert (gw, gh) == (w, h)
@@ -288,7 +296,7 @@ def test_decode_planes_and_nrgba(oracle, gpu_ctx, w, h, idxs, kw):
         assert not errs, "stream %d: %s" % (i, "; ".join(errs))
 
 
-def test_decode_reference_fixtures_and_foreign_stream(oracle, gpu_ctx):
+def test_decode_reference_fixtures_and_foreign_stream(oracle, gpu_ctx, parser_route):
     for name in ("blue_16x16_lossy.webp", "red_4x4_lossy.webp"):
         data = open(os.path.join(DATA, name), "rb").read()
         w, h, y, u, v, rgba = webp_b200.webp.decode_padded([data], nrgba=True, ctx=gpu_ctx)
@@ -306,7 +314,7 @@ def test_decode_reference_fixtures_and_foreign_stream(oracle, gpu_ctx):
     assert np.array_equal(y[0], ey) and np.array_equal(u[0], eu) and np.array_equal(v[0], ev)
 
 
-def test_decode_errors(gpu_ctx, oracle):
+def test_decode_errors(gpu_ctx, oracle, parser_route):
     data = oracle.encode(oracle.synth_image(64, 64, 1))
     with pytest.raises(webp_b200.WebPError):  # RIFF chunk longer than the file
         webp_b200.webp.decode_padded([data[:len(data) // 2]], ctx=gpu_ctx)
@@ -350,7 +358,7 @@ def test_plane_metrics(oracle, gpu_ctx, w, h):
         assert dsp.PSNRFromSSE(sse[i], w * h) == oracle.lib().orc_psnr_from_sse(int(sse[i]), w * h)
 
 
-def test_round_trip_at_full_size(oracle, gpu_ctx):
+def test_round_trip_at_full_size(oracle, gpu_ctx, parser_route):
     """BASELINE configs[1]/[2] shape: 1536x1024 q75 m4 -> own decoder -> libwebp-identical planes; size-independent
     properties: GPU decode of GPU bytes == encoder's own reconstruction (filter off), PSNR >= 30 dB."""
     imgs = np.stack([oracle.synth_image(1536, 1024, i) for i in (0, 1)])

@@ -1,0 +1,295 @@
+// Decoder macroblock parser on the device (sm_100a): intra modes from partition 0 and coefficient tokens from the token
+// partitions, i.e. parseIntraModeRow (internal/lossy/decode_tree.go:35) and parseResiduals / getCoeffs
+// (decode_mb.go:111-313) over the boolean decoder of internal/bitio/reader_bool.go -- SURVEY 8(f) rank 2, the mirror of
+// boolcode_kernel.  The frame HEADERS stay on the host (host_dec.h::parse_frame: a few hundred bits per image); the host
+// hands over the partition-0 decoder state right after them plus the tables they define (DecHeader).
+//
+// Boolean decoding is a serial chain per partition with data-dependent control flow at every bit, so there is nothing for
+// SIMT to share inside an image: one warp per image, lane 0 walks the macroblocks in raster order, and the batch supplies
+// the parallelism (256 images = 256 warps = 3 % of the warp slots; several batches' parsers overlap on the GPU).  What it
+// buys is the host: 768 B of dequantised coefficients per macroblock no longer cross PCIe (1.26 GB per 256-image batch ->
+// 46 MB of compressed bytes), and 32 host cores no longer parse for 8 GPUs.
+//
+// Output layout is exactly what host_dec.h::parse_frame writes (coefficients dequantised, WHT applied, [nmb][384]; MBMeta).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dec_kernels.cuh"
+
+namespace wg {
+
+// Filled by host_dec.h::parse_frame (same layout as wgh::DecHeaderH).
+struct DecHeader {
+  unsigned long long br_value;  // partition-0 decoder state after the frame headers
+  uint32_t br_range;
+  int32_t br_bits;
+  uint32_t br_pos, br_end;      // next byte / end of partition 0, offsets into this image's VP8 frame
+  uint32_t part_off[8], part_len[8];
+  unsigned long long stream_off;  // offset of the VP8 frame in the packed stream buffer
+  int32_t dq[4][6];             // per segment: y1 dc/ac, y2 dc/ac, uv dc/ac
+  uint8_t fs[4][2][4];          // per (segment, is_i4): limit, ilevel, inner, hev_thresh
+  uint8_t proba[1056];
+  uint8_t seg_proba[3];
+  uint8_t br_eof, update_map, use_skip, skip_p, last_part, filter_type;
+  uint8_t pad[3];
+};
+
+__device__ __constant__ int8_t c_i4tree[18] = {0, 1, -1, 2, -2, 3, 4, 6, -3, 5, -4, -5, -6, 7, -7, 8, -8, -9};
+__device__ __constant__ uint8_t c_dcat3[4] = {173, 148, 140, 0};
+__device__ __constant__ uint8_t c_dcat4[5] = {176, 155, 140, 135, 0};
+__device__ __constant__ uint8_t c_dcat5[6] = {180, 157, 141, 134, 130, 0};
+__device__ __constant__ uint8_t c_dcat6[12] = {254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129, 0};
+
+// VP8 boolean decoder (bitio/reader_bool.go), the device twin of wgh::BoolDec: 32-bit refills, byte-wise tail, one
+// virtual zero byte past the end and then EOF -- the same bits and the same EOF point as the host's 56-bit refills.
+struct DBoolDec {
+  const uint8_t* p; const uint8_t* end;
+  unsigned long long value;
+  uint32_t range;
+  int bits;
+  bool eof;
+  __device__ __forceinline__ void init(const uint8_t* d, uint32_t n) { p = d; end = d + n; value = 0; range = 254; bits = -8; eof = false; refill(); }
+  __device__ __forceinline__ void refill() {
+    if (end - p >= 4) {
+      const uint32_t w = ((uint32_t)__ldg(p) << 24) | ((uint32_t)__ldg(p + 1) << 16) | ((uint32_t)__ldg(p + 2) << 8) | (uint32_t)__ldg(p + 3);
+      p += 4;
+      value = (value << 32) | w;
+      bits += 32;
+    } else if (p < end) {
+      value = (value << 8) | __ldg(p++);
+      bits += 8;
+    } else if (!eof) {
+      value <<= 8;
+      bits += 8;
+      eof = true;
+    } else {
+      bits = 0;
+    }
+  }
+  __device__ __forceinline__ int get(int prob) {
+    uint32_t r = range;
+    if (bits < 0) refill();
+    const int pos = bits;
+    const uint32_t split = (r * (uint32_t)prob) >> 8;
+    const uint32_t v = (uint32_t)(value >> pos);
+    int bit;
+    if (v > split) { r -= split; value -= (unsigned long long)(split + 1) << pos; bit = 1; }
+    else { r = split + 1; bit = 0; }
+    const int shift = 7 ^ (31 - __clz(r));
+    r <<= shift;
+    bits -= shift;
+    range = r - 1;
+    return bit;
+  }
+};
+
+// getCoeffs (decode_mb.go:111): one block's tokens, dequantised into out[zigzag]; returns the position after the last
+// coefficient read.  P = probabilities of this block's type, [band][ctx][11] in shared memory.
+__device__ __forceinline__ int dread_block(DBoolDec& br, const uint8_t* P, int ctx, int dq_dc, int dq_ac, int n, int16_t* out) {
+  const uint8_t* p = P + (c_bands[n] * 3 + ctx) * 11;
+  for (; n < 16; ++n) {
+    if (!br.get(p[0])) return n;
+    while (!br.get(p[1])) {
+      p = P + (c_bands[++n] * 3 + 0) * 11;
+      if (n == 16) return 16;
+    }
+    const uint8_t* next = P + c_bands[n + 1] * 33;
+    int v;
+    if (!br.get(p[2])) { v = 1; p = next + 11; }
+    else {
+      if (!br.get(p[3])) { v = !br.get(p[4]) ? 2 : 3 + br.get(p[5]); }
+      else if (!br.get(p[6])) {
+        if (!br.get(p[7])) v = 5 + br.get(159);
+        else { v = 7 + 2 * br.get(165); v += br.get(145); }
+      } else {
+        const int b1 = br.get(p[8]), b0 = br.get(p[9 + b1]), cat = 2 * b1 + b0;
+        const uint8_t* t = cat == 0 ? c_dcat3 : cat == 1 ? c_dcat4 : cat == 2 ? c_dcat5 : c_dcat6;
+        v = 0;
+        for (; *t; ++t) v += v + br.get(*t);
+        v += 3 + (8 << cat);
+      }
+      p = next + 22;
+    }
+    if (br.get(0x80)) v = -v;
+    out[c_zigzag[n]] = (int16_t)(v * (n > 0 ? dq_ac : dq_dc));
+  }
+  return 16;
+}
+
+__device__ __forceinline__ void dinverse_wht(const int16_t* in, int16_t* out) {  // transformWHT (dsp/transforms.go:223)
+  int t[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a0 = in[i] + in[12 + i], a1 = in[4 + i] + in[8 + i], a2 = in[4 + i] - in[8 + i], a3 = in[i] - in[12 + i];
+    t[i] = a0 + a1; t[8 + i] = a0 - a1; t[4 + i] = a3 + a2; t[12 + i] = a3 - a2;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int dc = t[4 * i] + 3;
+    const int a0 = dc + t[4 * i + 3], a1 = t[4 * i + 1] + t[4 * i + 2], a2 = t[4 * i + 1] - t[4 * i + 2], a3 = dc - t[4 * i + 3];
+    int16_t* o = out + 64 * i;
+    o[0] = (int16_t)((a0 + a1) >> 3); o[16] = (int16_t)((a3 + a2) >> 3); o[32] = (int16_t)((a0 - a1) >> 3); o[48] = (int16_t)((a3 - a2) >> 3);
+  }
+}
+
+struct DecParseParams {
+  const uint8_t* streams;    // packed VP8 frames
+  const DecHeader* hdr;      // [n]
+  const uint8_t* bmodes;     // kBModesProba [10][10][9]
+  int16_t* coeffs;           // [n][nmb][384], zeroed before the launch
+  MBMeta* meta;              // [n][nmb]
+  int* err;                  // [n] 0 ok, 1 premature end of data
+  int n_images, mb_w, mb_h;
+};
+
+// Dynamic shared memory: the image's header (probabilities, quantisers, filter strengths), the intra-mode probabilities,
+// the per-column contexts (4 top modes + NZ flags + DC flag per macroblock column) and the token-partition decoder states.
+__global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  DecHeader* H = reinterpret_cast<DecHeader*>(s_dyn);
+  uint8_t* s_bmodes = s_dyn + ((sizeof(DecHeader) + 15) & ~(size_t)15);
+  uint8_t* top_modes = s_bmodes + 912;
+  uint8_t* top_nz = top_modes + 4 * P.mb_w;
+  uint8_t* top_dc = top_nz + P.mb_w;
+  DBoolDec* parts = reinterpret_cast<DBoolDec*>(s_dyn + ((((top_dc + P.mb_w) - s_dyn) + 15) & ~(size_t)15));
+  const int img = blockIdx.x, lane = threadIdx.x;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.hdr + img);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(H);
+    for (int i = lane; i < (int)(sizeof(DecHeader) / 4); i += 32) dst[i] = src[i];
+    for (int i = lane; i < 900; i += 32) s_bmodes[i] = P.bmodes[i];
+    for (int i = lane; i < 6 * P.mb_w; i += 32) top_modes[i] = 0;
+  }
+  __syncwarp();
+  if (lane != 0) return;
+  const uint8_t* frame = P.streams + H->stream_off;
+  DBoolDec br;
+  br.p = frame + H->br_pos; br.end = frame + H->br_end; br.value = H->br_value; br.range = H->br_range; br.bits = H->br_bits; br.eof = H->br_eof != 0;
+  const int last = H->last_part;
+  for (int p = 0; p <= last; ++p) parts[p].init(frame + H->part_off[p], H->part_len[p]);
+  const int mb_w = P.mb_w, mb_h = P.mb_h;
+  const size_t nmb = (size_t)mb_w * mb_h;
+  const bool update_map = H->update_map, use_skip = H->use_skip;
+  const int skip_p = H->skip_p;
+  const uint8_t* proba = H->proba;
+  for (int my = 0; my < mb_h; ++my) {
+    uint8_t left_modes[4] = {0, 0, 0, 0};
+    MBMeta* row = P.meta + (size_t)img * nmb + (size_t)my * mb_w;
+    for (int mx = 0; mx < mb_w; ++mx) {  // parseIntraModeRow (decode_tree.go:35)
+      MBMeta m;
+      uint8_t* top = top_modes + 4 * mx;
+      m.segment = update_map ? (uint8_t)(!br.get(H->seg_proba[0]) ? br.get(H->seg_proba[1]) : br.get(H->seg_proba[2]) + 2) : 0;
+      m.skip = use_skip ? (uint8_t)br.get(skip_p) : 0;
+      m.is_i4 = !br.get(145);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) m.imodes[i] = 0;
+      if (!m.is_i4) {
+        const int ym = br.get(156) ? (br.get(128) ? 1 : 3) : (br.get(163) ? 2 : 0);
+        m.imodes[0] = (uint8_t)ym;
+        for (int i = 0; i < 4; ++i) { top[i] = (uint8_t)ym; left_modes[i] = (uint8_t)ym; }
+      } else {
+        for (int y = 0; y < 4; ++y) {
+          int ym = left_modes[y];
+          for (int x = 0; x < 4; ++x) {
+            const uint8_t* prob = s_bmodes + (top[x] * 10 + ym) * 9;
+            int i = c_i4tree[br.get(prob[0])];
+            while (i > 0) i = c_i4tree[2 * i + br.get(prob[i])];
+            ym = -i;
+            top[x] = (uint8_t)ym;
+            m.imodes[4 * y + x] = (uint8_t)ym;
+          }
+          left_modes[y] = (uint8_t)ym;
+        }
+      }
+      m.uvmode = !br.get(142) ? 0 : !br.get(114) ? 2 : br.get(183) ? 1 : 3;
+      m.non_zero_y = m.non_zero_uv = 0;
+      m.f_limit = m.f_ilevel = m.f_inner = m.hev_thresh = 0;
+      row[mx] = m;
+    }
+    if (br.eof) { P.err[img] = 1; return; }
+    DBoolDec tb = parts[my & last];
+    uint8_t left_nz = 0, left_dc = 0;
+    for (int mx = 0; mx < mb_w; ++mx) {
+      MBMeta& m = row[mx];
+      const int is_i4 = m.is_i4, segment = m.segment & 3;
+      int16_t* dst = P.coeffs + ((size_t)img * nmb + (size_t)my * mb_w + mx) * 384;
+      const bool skip = use_skip && m.skip;
+      uint32_t nzy = 0, nzuv = 0;
+      if (skip) {
+        left_nz = top_nz[mx] = 0;
+        if (!is_i4) left_dc = top_dc[mx] = 0;
+      } else {  // parseResiduals (decode_mb.go:313)
+        const int* q = H->dq[segment];
+        const uint8_t tnz_in = top_nz[mx], lnz_in = left_nz;
+        int first = 0, type = 3;
+        if (!is_i4) {
+          int16_t dc[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dc[i] = 0;
+          const int nz = dread_block(tb, proba + 1 * 264, top_dc[mx] + left_dc, q[2], q[3], 0, dc);
+          top_dc[mx] = left_dc = (nz > 0);
+          if (nz > 1) dinverse_wht(dc, dst);
+          else { const int16_t d0 = (int16_t)((dc[0] + 3) >> 3); for (int i = 0; i < 256; i += 16) dst[i] = d0; }
+          first = 1;
+          type = 0;
+        }
+        uint8_t tnz = tnz_in & 0x0f, lnz = lnz_in & 0x0f;
+        int16_t* d = dst;
+        for (int y = 0; y < 4; ++y) {
+          uint8_t l = lnz & 1;
+          uint32_t acc = 0;
+          for (int x = 0; x < 4; ++x) {
+            const int nz = dread_block(tb, proba + type * 264, l + (tnz & 1), q[0], q[1], first, d);
+            l = nz > first;
+            tnz = (uint8_t)((tnz >> 1) | (l << 7));
+            acc = (acc << 2) | (uint32_t)(nz > 3 ? 3 : nz > 1 ? 2 : (d[0] != 0));
+            d += 16;
+          }
+          tnz >>= 4;
+          lnz = (uint8_t)((lnz >> 1) | (l << 7));
+          nzy = (nzy << 8) | acc;
+        }
+        uint8_t out_t = tnz, out_l = lnz >> 4;
+        for (int ch = 0; ch < 4; ch += 2) {
+          uint32_t acc = 0;
+          tnz = tnz_in >> (4 + ch);
+          lnz = lnz_in >> (4 + ch);
+          for (int y = 0; y < 2; ++y) {
+            uint8_t l = lnz & 1;
+            for (int x = 0; x < 2; ++x) {
+              const int nz = dread_block(tb, proba + 2 * 264, l + (tnz & 1), q[4], q[5], 0, d);
+              l = nz > 0;
+              tnz = (uint8_t)((tnz >> 1) | (l << 3));
+              acc = (acc << 2) | (uint32_t)(nz > 3 ? 3 : nz > 1 ? 2 : (d[0] != 0));
+              d += 16;
+            }
+            tnz >>= 2;
+            lnz = (uint8_t)((lnz >> 1) | (l << 5));
+          }
+          nzuv |= acc << (4 * ch);
+          out_t |= (uint8_t)((tnz << 4) << ch);
+          out_l |= (uint8_t)((lnz & 0xf0) << ch);
+        }
+        top_nz[mx] = out_t;
+        left_nz = out_l;
+      }
+      m.non_zero_y = nzy;
+      m.non_zero_uv = nzuv;
+      const uint8_t* f = H->fs[segment][is_i4];
+      m.f_limit = f[0]; m.f_ilevel = f[1]; m.hev_thresh = f[3];
+      m.f_inner = (uint8_t)(f[2] || !skip);  // FInner |= !skip (decode_mb.go:291)
+      if (tb.eof) { P.err[img] = 1; return; }
+    }
+    parts[my & last] = tb;
+  }
+}
+
+inline size_t dec_parse_smem(int mb_w) {
+  size_t s = (sizeof(DecHeader) + 15) & ~(size_t)15;
+  s += 912 + 6 * (size_t)mb_w;
+  s = (s + 15) & ~(size_t)15;
+  return s + 8 * sizeof(DBoolDec);
+}
+
+}  // namespace wg

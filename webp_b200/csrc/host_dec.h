@@ -26,12 +26,12 @@ static_assert(sizeof(MBMetaH) == 32, "MBMetaH layout");
 
 // VP8 boolean decoder: 56-bit refills, byte-wise tail, zero-extension past the end (one virtual byte, then EOF).
 struct BoolDec {
-  const uint8_t* p = nullptr; const uint8_t* end = nullptr;
+  const uint8_t* p = nullptr; const uint8_t* end = nullptr; const uint8_t* start = nullptr; size_t len = 0;
   uint64_t value = 0;
   uint32_t range = 254;
   int bits = -8;
   bool eof = false;
-  void init(const uint8_t* d, size_t n) { p = d; end = d + n; value = 0; range = 254; bits = -8; eof = false; refill(); }
+  void init(const uint8_t* d, size_t n) { p = d; end = d + n; start = d; len = n; value = 0; range = 254; bits = -8; eof = false; refill(); }
   inline void refill() {
     if (end - p >= 8) {
       uint64_t w;
@@ -68,6 +68,22 @@ struct BoolDec {
   }
   inline uint32_t value_bits(int n) { uint32_t v = 0; while (n-- > 0) v |= (uint32_t)get(0x80) << n; return v; }
   inline int signed_bits(int n) { const int v = (int)value_bits(n); return get(0x80) ? -v : v; }
+};
+
+// What the device macroblock parser (dec_parse.cuh, wg::DecHeader -- same layout) needs from the frame headers.
+struct DecHeaderH {
+  unsigned long long br_value;
+  uint32_t br_range;
+  int32_t br_bits;
+  uint32_t br_pos, br_end;
+  uint32_t part_off[8], part_len[8];
+  unsigned long long stream_off;
+  int32_t dq[4][6];
+  uint8_t fs[4][2][4];
+  uint8_t proba[1056];
+  uint8_t seg_proba[3];
+  uint8_t br_eof, update_map, use_skip, skip_p, last_part, filter_type;
+  uint8_t pad[3];
 };
 
 struct DecFrame {
@@ -157,8 +173,11 @@ static inline void inverse_wht(const int16_t* in, int16_t* out) {
 
 // Parse one VP8 key frame completely.  coeffs [nmb][384], meta [nmb] (caller-provided, e.g. pinned staging).
 // When coeffs == nullptr only the headers are parsed (dimensions / filter type).
+// With dev_hdr != nullptr only the headers are parsed here and the per-macroblock part is left to the device parser, which
+// continues from the partition-0 decoder state stored in *dev_hdr (BoolDec refills 7 bytes at a time, so the state is
+// rewound to byte granularity: value keeps `bits` + 8 significant bits, the rest is re-read on the device).
 static inline bool parse_frame(const uint8_t* data, size_t len, DecFrame* F, int16_t* coeffs, MBMetaH* meta, int expect_mb_w,
-                               int expect_mb_h) {
+                               int expect_mb_h, DecHeaderH* dev_hdr = nullptr) {
   if (!peek_dims(data, len, &F->width, &F->height, &F->err)) return false;
   const uint32_t part0_len = (data[0] | (data[1] << 8) | (data[2] << 16)) >> 5;
   const uint8_t* buf = data + 10;
@@ -241,7 +260,7 @@ static inline bool parse_frame(const uint8_t* data, size_t len, DecFrame* F, int
     (&proba[0][0][0][0])[i] = br.get(kCoeffsUpdateProba[i]) ? (uint8_t)br.value_bits(8) : kCoeffsProba0[i];
   const bool use_skip = br.get(0x80);
   const int skip_p = use_skip ? (int)br.value_bits(8) : 0;
-  if (!coeffs) return true;
+  if (!coeffs && !dev_hdr) return true;
   if (F->mb_w != expect_mb_w || F->mb_h != expect_mb_h) { F->err = "batch decode needs identical dimensions"; return false; }
   // per-(segment, i4) filter strengths (decode_frame.go:220)
   uint8_t fs[4][2][4];  // limit, ilevel, inner, hev
@@ -264,6 +283,26 @@ static inline bool parse_frame(const uint8_t* data, size_t len, DecFrame* F, int
         fs[s][i4][2] = (uint8_t)i4;
       }
     }
+  if (dev_hdr) {
+    DecHeaderH& D = *dev_hdr;
+    memset(&D, 0, sizeof(D));
+    // hand the decoder over at a byte boundary: drop the whole bytes still unread in `value`
+    int bits = br.bits;
+    uint64_t value = br.value;
+    const uint8_t* p = br.p;
+    if (!br.eof) {
+      while (bits >= 8) { value >>= 8; bits -= 8; --p; }
+    }
+    D.br_value = value; D.br_range = br.range; D.br_bits = bits; D.br_eof = br.eof;
+    D.br_pos = (uint32_t)(p - data); D.br_end = (uint32_t)(br.end - data);
+    for (int p2 = 0; p2 <= last; ++p2) { D.part_off[p2] = (uint32_t)(parts[p2].start - data); D.part_len[p2] = (uint32_t)parts[p2].len; }
+    memcpy(D.dq, dq, sizeof(dq));
+    memcpy(D.fs, fs, sizeof(fs));
+    memcpy(D.proba, proba, sizeof(proba));
+    memcpy(D.seg_proba, seg_proba, 3);
+    D.update_map = update_map; D.use_skip = use_skip; D.skip_p = (uint8_t)skip_p; D.last_part = (uint8_t)last; D.filter_type = (uint8_t)F->filter_type;
+    return true;
+  }
   // macroblocks: intra modes from partition 0, residuals from partition (row & last)
   const int mb_w = F->mb_w, mb_h = F->mb_h;
   std::vector<uint8_t> top_modes((size_t)4 * mb_w, 0), top_nz(mb_w, 0), top_dc(mb_w, 0);

@@ -15,6 +15,7 @@
 #include "../../include/webpgpu.h"
 #include "misc_kernels.cuh"
 #include "token_kernels.cuh"
+#include "dec_parse.cuh"
 #include "host_dec.h"
 
 namespace {
@@ -93,7 +94,9 @@ struct wgpu_ctx {
   std::vector<int> sp_starts;
   bool e_refresh_route = false;
   // decoder state
-  DevBuf d_coeffs, d_meta, d_ftype, dy, du, dv, d_nrgba, d_alpha;
+  DevBuf d_coeffs, d_meta, d_ftype, dy, du, dv, d_nrgba, d_alpha, d_streams, d_hdrs, d_perr, t_bmodes;
+  PinBuf hd_streams, hd_hdrs, hd_perr;
+  bool d_dev_parsed = false;
   PinBuf hd_coeffs, hd_meta, hd_ftype, hd_planes, hd_nrgba;
   int d_n = 0, d_w = 0, d_h = 0, d_mbw = 0, d_mbh = 0;
   bool d_ready = false, d_any_filter = false, d_has_nrgba = false;
@@ -125,6 +128,15 @@ static bool device_coder_wanted(const wgpu_ctx* ctx, size_t n_images) {
   const char* e = getenv("WGPU_DEVICE_CODER");  // read per call: tests flip it
   if (e && *e) return atoi(e) != 0;
   return n_images >= 32 && threads_of(ctx) <= 8;
+}
+// Where the macroblock data of the decoder is parsed (intra modes + coefficient tokens; the frame headers always on the
+// host).  On the GPU: one warp per image (dec_parse_kernel), 46 MB of compressed bytes up instead of 1.26 GB of
+// coefficients per 256-image batch, no host cores.  WGPU_DEVICE_PARSER=0/1 forces either.
+static bool device_parser_wanted(const wgpu_ctx* ctx, size_t n_images) {
+  (void)ctx;
+  const char* e = getenv("WGPU_DEVICE_PARSER");  // read per call: tests flip it
+  if (e && *e) return atoi(e) != 0;
+  return n_images >= 32;
 }
 static int threads_of(const wgpu_ctx* ctx) {
   int t = ctx->host_threads;
@@ -190,6 +202,7 @@ int wgpu_ctx_create(int device_ordinal, wgpu_ctx** out) {
   rc |= upload_table(ctx, ctx->t_eob, eobc, sizeof(eobc));
   rc |= upload_table(ctx, ctx->t_lfc, wgh::kLevelFixedCosts, sizeof(wgh::kLevelFixedCosts));
   rc |= upload_table(ctx, ctx->t_proba0, wgh::kCoeffsProba0, sizeof(wgh::kCoeffsProba0));
+  rc |= upload_table(ctx, ctx->t_bmodes, wgh::kBModesProba, sizeof(wgh::kBModesProba));
   rc |= upload_table(ctx, ctx->t_upd, wgh::kCoeffsUpdateProba, sizeof(wgh::kCoeffsUpdateProba));
   rc |= upload_table(ctx, ctx->t_ecost, wgh::kEntropyCost, sizeof(wgh::kEntropyCost));
   rc |= upload_table(ctx, ctx->t_i4cost, i4costs, sizeof(i4costs));
@@ -207,11 +220,11 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
-                  &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
+                  &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_streams, &ctx->d_hdrs, &ctx->d_perr, &ctx->t_bmodes, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
                   &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
                   &ctx->m_sse, &ctx->m_ssim};
   for (DevBuf* b : db) b->release();
-  PinBuf* pb[] = {&ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
+  PinBuf* pb[] = {&ctx->hd_streams, &ctx->hd_hdrs, &ctx->hd_perr, &ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
                   &ctx->hd_meta, &ctx->hd_ftype, &ctx->hd_planes, &ctx->hd_nrgba};
   for (PinBuf* b : pb) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1236,9 +1249,61 @@ int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* l
   RESERVE(ctx->d_meta, (size_t)n * nmb * sizeof(wg::MBMeta));
   RESERVE(ctx->d_ftype, (size_t)n);
   RESERVE(ctx->dy, (size_t)n * nmb * 256); RESERVE(ctx->du, (size_t)n * nmb * 64); RESERVE(ctx->dv, (size_t)n * nmb * 64);
-  // host: boolean decoding of headers, modes and coefficient tokens (serial per image, parallel across images)
   std::vector<wgh::DecFrame> frames(n);
   std::atomic<int> bad(-1);
+  ctx->d_dev_parsed = device_parser_wanted(ctx, (size_t)n);
+  if (ctx->d_dev_parsed) {
+    // ---- headers on the host, macroblocks on the GPU
+    static_assert(sizeof(wgh::DecHeaderH) == sizeof(wg::DecHeader), "DecHeader layout");
+    std::vector<size_t> off(n + 1, 0);
+    std::vector<const uint8_t*> vp(n, nullptr);
+    std::vector<size_t> vl(n, 0);
+    for (int i = 0; i < n; ++i) {
+      if (!wgh::find_vp8(streams[i], lens[i], &vp[i], &vl[i])) FAIL(WGPU_ERR_BITSTREAM, std::string("image ") + std::to_string(i) + ": webp: no VP8 chunk");
+      off[i + 1] = off[i] + ((vl[i] + 15) & ~(size_t)15);
+    }
+    RESERVE(ctx->hd_streams, off[n] + 16); RESERVE(ctx->d_streams, off[n] + 16);
+    RESERVE(ctx->hd_hdrs, (size_t)n * sizeof(wgh::DecHeaderH)); RESERVE(ctx->d_hdrs, (size_t)n * sizeof(wgh::DecHeaderH));
+    RESERVE(ctx->hd_perr, (size_t)n * 4); RESERVE(ctx->d_perr, (size_t)n * 4);
+    parallel_for(n, threads_of(ctx), [&](int i) {
+      wgh::DecFrame& F = frames[i];
+      wgh::DecHeaderH* D = ctx->hd_hdrs.as<wgh::DecHeaderH>() + i;
+      if (!wgh::parse_frame(vp[i], vl[i], &F, nullptr, nullptr, mbw, mbh, D)) { bad.store(i); return; }
+      if (F.width != width || F.height != height) { F.err = "batch decode needs identical dimensions"; bad.store(i); return; }
+      D->stream_off = off[i];
+      memcpy(ctx->hd_streams.as<uint8_t>() + off[i], vp[i], vl[i]);
+      ctx->hd_ftype.as<uint8_t>()[i] = (uint8_t)F.filter_type;
+    });
+    if (bad.load() >= 0) FAIL(WGPU_ERR_BITSTREAM, std::string("image ") + std::to_string(bad.load()) + ": " + (frames[bad.load()].err ? frames[bad.load()].err : "parse error"));
+    CK(cudaMemcpyAsync(ctx->d_streams.p, ctx->hd_streams.p, off[n], cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)off[n];
+    CK(cudaMemcpyAsync(ctx->d_hdrs.p, ctx->hd_hdrs.p, (size_t)n * sizeof(wgh::DecHeaderH), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)((size_t)n * sizeof(wgh::DecHeaderH));
+    CK(cudaMemcpyAsync(ctx->d_ftype.p, ctx->hd_ftype.p, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)((size_t)n);
+    CK(cudaMemsetAsync(ctx->d_coeffs.p, 0, (size_t)n * nmb * 768, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_perr.p, 0, (size_t)n * 4, ctx->stream));
+    wg::DecParseParams DP;
+    DP.streams = ctx->d_streams.as<uint8_t>(); DP.hdr = ctx->d_hdrs.as<wg::DecHeader>(); DP.bmodes = ctx->t_bmodes.as<uint8_t>();
+    DP.coeffs = ctx->d_coeffs.as<int16_t>(); DP.meta = ctx->d_meta.as<wg::MBMeta>(); DP.err = ctx->d_perr.as<int>();
+    DP.n_images = n; DP.mb_w = mbw; DP.mb_h = mbh;
+    // one warp per image; 24 KB of shared memory per block keeps the block scheduler from stacking dozens of these
+    // single-lane latency chains on one SM
+    const size_t smem = std::max(wg::dec_parse_smem(mbw), (size_t)24 * 1024);
+    wg::dec_parse_kernel<<<n, 32, smem, ctx->stream>>>(DP);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ctx->hd_perr.p, ctx->d_perr.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)((size_t)n * 4);
+    ctx->d_any_filter = false;
+    for (int i = 0; i < n; ++i) ctx->d_any_filter |= frames[i].filter_type > 0;
+    ctx->d_n = n; ctx->d_w = width; ctx->d_h = height; ctx->d_mbw = mbw; ctx->d_mbh = mbh;
+    ctx->d_ready = true;
+    if (width_out) *width_out = width;
+    if (height_out) *height_out = height;
+    return WGPU_OK;
+  }
+  // host: boolean decoding of headers, modes and coefficient tokens (serial per image, parallel across images)
   parallel_for(n, threads_of(ctx), [&](int i) {
     const uint8_t* p; size_t pl;
     wgh::DecFrame& F = frames[i];
@@ -1303,6 +1368,11 @@ int wgpu_dec_fetch(wgpu_ctx* ctx, uint8_t* y, uint8_t* u, uint8_t* v, size_t y_p
   if (v) { CK(cudaMemcpy2DAsync(v, uv_plane_stride, ctx->dv.p, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)uvp * n; }
   if (nrgba) { CK(cudaMemcpy2DAsync(nrgba, nrgba_image_stride, ctx->d_nrgba.p, img, img, n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)img * n; }
   CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_dev_parsed) {  // the device parser reports truncated partitions here, the first point where the host waits
+    const int* pe = ctx->hd_perr.as<int>();
+    for (int i = 0; i < n; ++i)
+      if (pe[i]) FAIL(WGPU_ERR_BITSTREAM, std::string("image ") + std::to_string(i) + ": vp8: premature end of data");
+  }
   return WGPU_OK;
 }
 
