@@ -307,13 +307,27 @@ def main():
         for wk, buf in zip(workers[1:], dec_bufs[1:]):
             wk.ctx.check(L.wgpu_decode_batch(wk.ctx.handle, ptrs, lens, n, None, None, None, 0, 0, buf, W * H * 4))
 
+        env_parser = os.environ.get("WGPU_DEVICE_PARSER", "")
+        device_parser = (env_parser != "0") if env_parser else n >= 32  # webpgpu.cu device_parser_wanted
+
         def decode_e2e(wk, buf):
             h = wk.ctx.handle
+            if device_parser:
+                # macroblocks are parsed on the GPU, one warp per image: a ~200 ms latency chain that occupies 3 % of the
+                # warp slots, so the contexts only take turns for the D2H of the finished batch
+                wk.ctx.check(L.wgpu_dec_parse(h, ptrs, lens, n, None, None))
+                wk.ctx.check(L.wgpu_dec_device(h, 1))
+                wk.ctx.check(L.wgpu_sync(h))
+                with gpu_stage:
+                    wk.ctx.check(L.wgpu_dec_fetch(h, None, None, None, 0, 0, buf, W * H * 4))
+                return
             with host_stage:
                 wk.ctx.check(L.wgpu_dec_parse(h, ptrs, lens, n, None, None))
             with gpu_stage:
                 wk.ctx.check(L.wgpu_dec_device(h, 1))
                 wk.ctx.check(L.wgpu_dec_fetch(h, None, None, None, 0, 0, buf, W * H * 4))
+        for wk in workers:
+            wk.ctx.transfer_bytes(reset=True)
         barrier()
         t0 = time.perf_counter()
         if len(workers) == 1:
@@ -336,11 +350,13 @@ def main():
                 t.join()
         barrier()
         ds = max_over_ranks(time.perf_counter() - t0)
+        dxfer = [wk.ctx.transfer_bytes() for wk in workers]
         for wk, buf in zip(workers[1:], dec_bufs[1:]):
             L.wgpu_host_free(wk.ctx.handle, buf)
         result["decode"] = {"value": px_step * K * world / (dms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": dms / K, "gpu_launches": int(dl),
                             "e2e": {"value": px_step * K * world / ds / 1e6, "unit": "Mpix/s", "ms_per_step": ds / K * 1e3,
-                                    "h2d_bytes_per_step": n * nmb * (768 + 32), "d2h_bytes_per_step": in_bytes},
+                                    "h2d_bytes_per_step": sum(x[0] for x in dxfer) // K, "d2h_bytes_per_step": sum(x[1] for x in dxfer) // K,
+                                    "macroblock_parser": "gpu" if device_parser else "host"},
                             "config": {"workload": "decode of the %d streams above -> recon + loop filter + fancy upsampling to NRGBA (BASELINE configs[2])" % n},
                             "roofline": {"bound": "hbm", "kernel": "recon_wave + filter_wave + upsample_nrgba (whole device step)",
                                          "achieved": (ALG_BYTES_PER_PX["recon"] + ALG_BYTES_PER_PX["filter"] + ALG_BYTES_PER_PX["upsample"]) * px_step / (dms / K * 1e-3) / 1e9,

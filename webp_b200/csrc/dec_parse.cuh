@@ -41,21 +41,28 @@ __device__ __constant__ uint8_t c_dcat4[5] = {176, 155, 140, 135, 0};
 __device__ __constant__ uint8_t c_dcat5[6] = {180, 157, 141, 134, 130, 0};
 __device__ __constant__ uint8_t c_dcat6[12] = {254, 254, 243, 230, 196, 177, 153, 140, 133, 130, 129, 0};
 
-// VP8 boolean decoder (bitio/reader_bool.go), the device twin of wgh::BoolDec: 32-bit refills, byte-wise tail, one
-// virtual zero byte past the end and then EOF -- the same bits and the same EOF point as the host's 56-bit refills.
+// VP8 boolean decoder (bitio/reader_bool.go), the device twin of wgh::BoolDec: a 32-bit window refilled 16 bits at a time
+// (the 64-bit window of the host costs multi-instruction shifts at every bit here), byte-wise tail, one virtual zero byte
+// past the end and then EOF -- the same bits and the same EOF point as the host's 56-bit refills.
 struct DBoolDec {
   const uint8_t* p; const uint8_t* end;
-  unsigned long long value;
+  uint32_t value;
   uint32_t range;
   int bits;
   bool eof;
   __device__ __forceinline__ void init(const uint8_t* d, uint32_t n) { p = d; end = d + n; value = 0; range = 254; bits = -8; eof = false; refill(); }
+  // adopt a state handed over by the host at byte granularity (bits < 8, value < 2^17)
+  __device__ __forceinline__ void adopt(const uint8_t* cur, const uint8_t* e, unsigned long long v, uint32_t r, int b, bool f) {
+    p = cur; end = e; range = r; eof = f;
+    // the host may hand over with EOF already hit and up to 55 unread (zero) bits: keep the low window only
+    while (b > 15) { v >>= 8; b -= 8; }
+    value = (uint32_t)v; bits = b;
+  }
   __device__ __forceinline__ void refill() {
-    if (end - p >= 4) {
-      const uint32_t w = ((uint32_t)__ldg(p) << 24) | ((uint32_t)__ldg(p + 1) << 16) | ((uint32_t)__ldg(p + 2) << 8) | (uint32_t)__ldg(p + 3);
-      p += 4;
-      value = (value << 32) | w;
-      bits += 32;
+    if (end - p >= 2) {
+      value = (value << 16) | ((uint32_t)__ldg(p) << 8) | (uint32_t)__ldg(p + 1);
+      p += 2;
+      bits += 16;
     } else if (p < end) {
       value = (value << 8) | __ldg(p++);
       bits += 8;
@@ -72,9 +79,9 @@ struct DBoolDec {
     if (bits < 0) refill();
     const int pos = bits;
     const uint32_t split = (r * (uint32_t)prob) >> 8;
-    const uint32_t v = (uint32_t)(value >> pos);
+    const uint32_t v = value >> pos;
     int bit;
-    if (v > split) { r -= split; value -= (unsigned long long)(split + 1) << pos; bit = 1; }
+    if (v > split) { r -= split; value -= (split + 1) << pos; bit = 1; }
     else { r = split + 1; bit = 0; }
     const int shift = 7 ^ (31 - __clz(r));
     r <<= shift;
@@ -85,52 +92,63 @@ struct DBoolDec {
 };
 
 // getCoeffs (decode_mb.go:111): one block's tokens, dequantised into out[zigzag]; returns the position after the last
-// coefficient read.  P = probabilities of this block's type, [band][ctx][11] in shared memory.
-__device__ __forceinline__ int dread_block(DBoolDec& br, const uint8_t* P, int ctx, int dq_dc, int dq_ac, int n, int16_t* out) {
-  const uint8_t* p = P + (c_bands[n] * 3 + ctx) * 11;
+// coefficient read.  P = probabilities of this block's type in shared memory, rows [band][ctx] padded to 16 bytes so that
+// a row is ONE 128-bit load into registers per coefficient instead of a dependent byte load per bit; *dc_nz = whether
+// out[0] was written non-zero (as the int16 it is stored as).
+#define WG_PB(row, i) (((i) < 4 ? (row).x >> (8 * (i)) : (i) < 8 ? (row).y >> (8 * ((i) - 4)) : (row).z >> (8 * ((i) - 8))) & 0xffu)
+__device__ __forceinline__ int dread_block(DBoolDec& br, const uint4* P, int ctx, int dq_dc, int dq_ac, int n, int16_t* out, bool* dc_nz) {
+  uint4 p = P[c_bands[n] * 3 + ctx];
   for (; n < 16; ++n) {
-    if (!br.get(p[0])) return n;
-    while (!br.get(p[1])) {
-      p = P + (c_bands[++n] * 3 + 0) * 11;
+    if (!br.get(WG_PB(p, 0))) return n;
+    while (!br.get(WG_PB(p, 1))) {
+      p = P[c_bands[++n] * 3 + 0];
       if (n == 16) return 16;
     }
-    const uint8_t* next = P + c_bands[n + 1] * 33;
+    const uint4* next = P + c_bands[n + 1] * 3;
+    const uint4 n1 = next[1], n2 = next[2];  // both candidates for the next row, issued before the level is known
     int v;
-    if (!br.get(p[2])) { v = 1; p = next + 11; }
+    if (!br.get(WG_PB(p, 2))) { v = 1; p = n1; }
     else {
-      if (!br.get(p[3])) { v = !br.get(p[4]) ? 2 : 3 + br.get(p[5]); }
-      else if (!br.get(p[6])) {
-        if (!br.get(p[7])) v = 5 + br.get(159);
+      if (!br.get(WG_PB(p, 3))) { v = !br.get(WG_PB(p, 4)) ? 2 : 3 + br.get(WG_PB(p, 5)); }
+      else if (!br.get(WG_PB(p, 6))) {
+        if (!br.get(WG_PB(p, 7))) v = 5 + br.get(159);
         else { v = 7 + 2 * br.get(165); v += br.get(145); }
       } else {
-        const int b1 = br.get(p[8]), b0 = br.get(p[9 + b1]), cat = 2 * b1 + b0;
+        const int b1 = br.get(WG_PB(p, 8)), b0 = br.get(b1 ? WG_PB(p, 10) : WG_PB(p, 9)), cat = 2 * b1 + b0;
         const uint8_t* t = cat == 0 ? c_dcat3 : cat == 1 ? c_dcat4 : cat == 2 ? c_dcat5 : c_dcat6;
         v = 0;
         for (; *t; ++t) v += v + br.get(*t);
         v += 3 + (8 << cat);
       }
-      p = next + 22;
+      p = n2;
     }
     if (br.get(0x80)) v = -v;
-    out[c_zigzag[n]] = (int16_t)(v * (n > 0 ? dq_ac : dq_dc));
+    const int16_t q = (int16_t)(v * (n > 0 ? dq_ac : dq_dc));
+    if (n == 0) *dc_nz = q != 0;
+    out[c_zigzag[n]] = q;
   }
   return 16;
 }
 
-__device__ __forceinline__ void dinverse_wht(const int16_t* in, int16_t* out) {  // transformWHT (dsp/transforms.go:223)
+// transformWHT (dsp/transforms.go:223): the sixteen block DCs at stride 16; returns which of them are non-zero
+__device__ __forceinline__ uint32_t dinverse_wht(const int16_t* in, int16_t* out) {
   int t[16];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int a0 = in[i] + in[12 + i], a1 = in[4 + i] + in[8 + i], a2 = in[4 + i] - in[8 + i], a3 = in[i] - in[12 + i];
     t[i] = a0 + a1; t[8 + i] = a0 - a1; t[4 + i] = a3 + a2; t[12 + i] = a3 - a2;
   }
+  uint32_t mask = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int dc = t[4 * i] + 3;
     const int a0 = dc + t[4 * i + 3], a1 = t[4 * i + 1] + t[4 * i + 2], a2 = t[4 * i + 1] - t[4 * i + 2], a3 = dc - t[4 * i + 3];
     int16_t* o = out + 64 * i;
-    o[0] = (int16_t)((a0 + a1) >> 3); o[16] = (int16_t)((a3 + a2) >> 3); o[32] = (int16_t)((a0 - a1) >> 3); o[48] = (int16_t)((a3 - a2) >> 3);
+    const int16_t v0 = (int16_t)((a0 + a1) >> 3), v1 = (int16_t)((a3 + a2) >> 3), v2 = (int16_t)((a0 - a1) >> 3), v3 = (int16_t)((a3 - a2) >> 3);
+    o[0] = v0; o[16] = v1; o[32] = v2; o[48] = v3;
+    mask |= ((uint32_t)(v0 != 0) | ((uint32_t)(v1 != 0) << 1) | ((uint32_t)(v2 != 0) << 2) | ((uint32_t)(v3 != 0) << 3)) << (4 * i);
   }
+  return mask;
 }
 
 struct DecParseParams {
@@ -148,7 +166,8 @@ struct DecParseParams {
 __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   DecHeader* H = reinterpret_cast<DecHeader*>(s_dyn);
-  uint8_t* s_bmodes = s_dyn + ((sizeof(DecHeader) + 15) & ~(size_t)15);
+  uint4* s_prob = reinterpret_cast<uint4*>(s_dyn + ((sizeof(DecHeader) + 15) & ~(size_t)15));  // [4][8][3] rows of 11 (+5) bytes
+  uint8_t* s_bmodes = reinterpret_cast<uint8_t*>(s_prob + 96);
   uint8_t* top_modes = s_bmodes + 912;
   uint8_t* top_nz = top_modes + 4 * P.mb_w;
   uint8_t* top_dc = top_nz + P.mb_w;
@@ -159,20 +178,24 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
     uint32_t* dst = reinterpret_cast<uint32_t*>(H);
     for (int i = lane; i < (int)(sizeof(DecHeader) / 4); i += 32) dst[i] = src[i];
     for (int i = lane; i < 900; i += 32) s_bmodes[i] = P.bmodes[i];
+    __syncwarp();
+    for (int r = lane; r < 96; r += 32) {
+      uint8_t* d = reinterpret_cast<uint8_t*>(s_prob + r);
+      for (int k = 0; k < 16; ++k) d[k] = k < 11 ? H->proba[r * 11 + k] : 0;
+    }
     for (int i = lane; i < 6 * P.mb_w; i += 32) top_modes[i] = 0;
   }
   __syncwarp();
   if (lane != 0) return;
   const uint8_t* frame = P.streams + H->stream_off;
   DBoolDec br;
-  br.p = frame + H->br_pos; br.end = frame + H->br_end; br.value = H->br_value; br.range = H->br_range; br.bits = H->br_bits; br.eof = H->br_eof != 0;
+  br.adopt(frame + H->br_pos, frame + H->br_end, H->br_value, H->br_range, H->br_bits, H->br_eof != 0);
   const int last = H->last_part;
   for (int p = 0; p <= last; ++p) parts[p].init(frame + H->part_off[p], H->part_len[p]);
   const int mb_w = P.mb_w, mb_h = P.mb_h;
   const size_t nmb = (size_t)mb_w * mb_h;
   const bool update_map = H->update_map, use_skip = H->use_skip;
   const int skip_p = H->skip_p;
-  const uint8_t* proba = H->proba;
   for (int my = 0; my < mb_h; ++my) {
     uint8_t left_modes[4] = {0, 0, 0, 0};
     MBMeta* row = P.meta + (size_t)img * nmb + (size_t)my * mb_w;
@@ -223,14 +246,21 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
         const int* q = H->dq[segment];
         const uint8_t tnz_in = top_nz[mx], lnz_in = left_nz;
         int first = 0, type = 3;
+        uint32_t wht_nz = 0;  // I16: which blocks got a non-zero DC from the WHT
         if (!is_i4) {
           int16_t dc[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) dc[i] = 0;
-          const int nz = dread_block(tb, proba + 1 * 264, top_dc[mx] + left_dc, q[2], q[3], 0, dc);
+          bool unused;
+          const int nz = dread_block(tb, s_prob + 1 * 24, top_dc[mx] + left_dc, q[2], q[3], 0, dc, &unused);
           top_dc[mx] = left_dc = (nz > 0);
-          if (nz > 1) dinverse_wht(dc, dst);
-          else { const int16_t d0 = (int16_t)((dc[0] + 3) >> 3); for (int i = 0; i < 256; i += 16) dst[i] = d0; }
+          if (nz > 1) {
+            wht_nz = dinverse_wht(dc, dst);
+          } else {
+            const int16_t d0 = (int16_t)((dc[0] + 3) >> 3);
+            for (int i = 0; i < 256; i += 16) dst[i] = d0;
+            wht_nz = d0 != 0 ? 0xffffu : 0u;
+          }
           first = 1;
           type = 0;
         }
@@ -240,10 +270,11 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
           uint8_t l = lnz & 1;
           uint32_t acc = 0;
           for (int x = 0; x < 4; ++x) {
-            const int nz = dread_block(tb, proba + type * 264, l + (tnz & 1), q[0], q[1], first, d);
+            bool dc_nz = (wht_nz >> (4 * y + x)) & 1u;
+            const int nz = dread_block(tb, s_prob + type * 24, l + (tnz & 1), q[0], q[1], first, d, &dc_nz);
             l = nz > first;
             tnz = (uint8_t)((tnz >> 1) | (l << 7));
-            acc = (acc << 2) | (uint32_t)(nz > 3 ? 3 : nz > 1 ? 2 : (d[0] != 0));
+            acc = (acc << 2) | (uint32_t)(nz > 3 ? 3 : nz > 1 ? 2 : dc_nz);
             d += 16;
           }
           tnz >>= 4;
@@ -258,10 +289,11 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
           for (int y = 0; y < 2; ++y) {
             uint8_t l = lnz & 1;
             for (int x = 0; x < 2; ++x) {
-              const int nz = dread_block(tb, proba + 2 * 264, l + (tnz & 1), q[4], q[5], 0, d);
+              bool dc_nz = false;
+              const int nz = dread_block(tb, s_prob + 2 * 24, l + (tnz & 1), q[4], q[5], 0, d, &dc_nz);
               l = nz > 0;
               tnz = (uint8_t)((tnz >> 1) | (l << 3));
-              acc = (acc << 2) | (uint32_t)(nz > 3 ? 3 : nz > 1 ? 2 : (d[0] != 0));
+              acc = (acc << 2) | (uint32_t)(nz > 3 ? 3 : nz > 1 ? 2 : dc_nz);
               d += 16;
             }
             tnz >>= 2;
@@ -287,7 +319,7 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
 
 inline size_t dec_parse_smem(int mb_w) {
   size_t s = (sizeof(DecHeader) + 15) & ~(size_t)15;
-  s += 912 + 6 * (size_t)mb_w;
+  s += 96 * 16 + 912 + 6 * (size_t)mb_w;
   s = (s + 15) & ~(size_t)15;
   return s + 8 * sizeof(DBoolDec);
 }
