@@ -118,6 +118,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (BASELINE configs[1]: 256)")
     ap.add_argument("--e2e-workers", type=int, default=3, help="contexts per GPU used by the e2e leg: upload, device and finish stages of consecutive batches overlap")
     ap.add_argument("--finish-slots", type=int, default=0, help="how many contexts may be in their finish stage at once (default: 2 when the token partitions are coded on the GPU, else 1)")
+    ap.add_argument("--decode-workers", type=int, default=0, help="contexts per GPU for the decode e2e leg (default: 4 with the GPU macroblock parser, whose ~0.3 s latency per batch they hide; else the encode workers)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per context (default: cores / ranks on this node)")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -161,9 +162,9 @@ def main():
     opt = native.EncOptions()
     L.wgpu_enc_options_default(opt, 75)
 
-    # the library codes the token partitions on the GPU when a context has few host threads (webpgpu.cu device_coder_wanted)
+    # the library codes the token partitions on the GPU for batches of at least 32 images (webpgpu.cu device_coder_wanted)
     env_coder = os.environ.get("WGPU_DEVICE_CODER", "")
-    device_coder = (env_coder != "0") if env_coder else (n >= 32 and host_threads <= 8)
+    device_coder = (env_coder != "0") if env_coder else n >= 32
     finish_slots = args.finish_slots or (2 if device_coder else 1)
     upload_stage, gpu_stage, host_stage = threading.Lock(), threading.Lock(), threading.BoundedSemaphore(finish_slots)
 
@@ -196,8 +197,10 @@ def main():
                 self.ctx.check(L.wgpu_enc_finish(h, self.h_out, cap, self.sizes.ctypes.data))
 
         def free(self):
-            L.wgpu_host_free(self.ctx.handle, self.h_in)
-            L.wgpu_host_free(self.ctx.handle, self.h_out)
+            if self.h_in:
+                L.wgpu_host_free(self.ctx.handle, self.h_in)
+                L.wgpu_host_free(self.ctx.handle, self.h_out)
+                self.h_in = self.h_out = None
 
     w0 = Worker(ctx, rank * 24)
     imgs, out, sizes, h_in = w0.imgs, w0.out, w0.sizes, w0.h_in
@@ -303,12 +306,24 @@ def main():
         dl = ctx.launch_count() - l0
         # e2e: the staged public calls (wgpu_dec_parse -> wgpu_dec_device -> wgpu_dec_fetch == wgpu_decode_batch), K batches dealt to
         # the same contexts as the encode leg so the host parse of one batch overlaps the GPU + D2H stage of the previous one
-        dec_bufs = [h_rgba] + [L.wgpu_host_alloc(wk.ctx.handle, in_bytes) for wk in workers[1:]]
-        for wk, buf in zip(workers[1:], dec_bufs[1:]):
-            wk.ctx.check(L.wgpu_decode_batch(wk.ctx.handle, ptrs, lens, n, None, None, None, 0, 0, buf, W * H * 4))
-
         env_parser = os.environ.get("WGPU_DEVICE_PARSER", "")
         device_parser = (env_parser != "0") if env_parser else n >= 32  # webpgpu.cu device_parser_wanted
+        # the encode staging of the extra contexts is no longer needed: give the pinned memory back before the decode buffers
+        for wk in workers[1:]:
+            wk.free()
+        n_dec = args.decode_workers or (4 if device_parser else len(workers))
+        dctxs = [wk.ctx for wk in workers] + [native.Context(local, host_threads=host_threads) for _ in range(max(0, n_dec - len(workers)))]
+        dctxs = dctxs[:max(1, n_dec)]
+        dec_bufs = [h_rgba] + [L.wgpu_host_alloc(c.handle, in_bytes) for c in dctxs[1:]]
+        if not all(dec_bufs):
+            raise SystemExit("pinned allocation failed")
+
+        class DW:
+            def __init__(self, c):
+                self.ctx = c
+        dworkers = [DW(c) for c in dctxs]
+        for wk, buf in zip(dworkers[1:], dec_bufs[1:]):
+            wk.ctx.check(L.wgpu_decode_batch(wk.ctx.handle, ptrs, lens, n, None, None, None, 0, 0, buf, W * H * 4))
 
         def decode_e2e(wk, buf):
             h = wk.ctx.handle
@@ -326,11 +341,11 @@ def main():
             with gpu_stage:
                 wk.ctx.check(L.wgpu_dec_device(h, 1))
                 wk.ctx.check(L.wgpu_dec_fetch(h, None, None, None, 0, 0, buf, W * H * 4))
-        for wk in workers:
+        for wk in dworkers:
             wk.ctx.transfer_bytes(reset=True)
         barrier()
         t0 = time.perf_counter()
-        if len(workers) == 1:
+        if len(dworkers) == 1:
             for _ in range(K):
                 decode_e2e(w0, h_rgba)
         else:
@@ -343,20 +358,20 @@ def main():
                         if next(dcounter, None) is None:
                             return
                     decode_e2e(wk, buf)
-            ths = [threading.Thread(target=drun, args=(wk, buf)) for wk, buf in zip(workers, dec_bufs)]
+            ths = [threading.Thread(target=drun, args=(wk, buf)) for wk, buf in zip(dworkers, dec_bufs)]
             for t in ths:
                 t.start()
             for t in ths:
                 t.join()
         barrier()
         ds = max_over_ranks(time.perf_counter() - t0)
-        dxfer = [wk.ctx.transfer_bytes() for wk in workers]
-        for wk, buf in zip(workers[1:], dec_bufs[1:]):
+        dxfer = [wk.ctx.transfer_bytes() for wk in dworkers]
+        for wk, buf in zip(dworkers[1:], dec_bufs[1:]):
             L.wgpu_host_free(wk.ctx.handle, buf)
         result["decode"] = {"value": px_step * K * world / (dms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": dms / K, "gpu_launches": int(dl),
                             "e2e": {"value": px_step * K * world / ds / 1e6, "unit": "Mpix/s", "ms_per_step": ds / K * 1e3,
                                     "h2d_bytes_per_step": sum(x[0] for x in dxfer) // K, "d2h_bytes_per_step": sum(x[1] for x in dxfer) // K,
-                                    "macroblock_parser": "gpu" if device_parser else "host"},
+                                    "macroblock_parser": "gpu" if device_parser else "host", "workers_per_gpu": len(dworkers)},
                             "config": {"workload": "decode of the %d streams above -> recon + loop filter + fancy upsampling to NRGBA (BASELINE configs[2])" % n},
                             "roofline": {"bound": "hbm", "kernel": "recon_wave + filter_wave + upsample_nrgba (whole device step)",
                                          "achieved": (ALG_BYTES_PER_PX["recon"] + ALG_BYTES_PER_PX["filter"] + ALG_BYTES_PER_PX["upsample"]) * px_step / (dms / K * 1e-3) / 1e9,

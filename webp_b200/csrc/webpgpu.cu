@@ -121,13 +121,14 @@ struct wgpu_ctx {
 static int threads_of(const wgpu_ctx* ctx);
 // Where the token partition is boolean-coded.  The coder is one serial chain per partition.  On the GPU the batch's
 // partitions run one per lane on a few dedicated SMs and the batch waits for its longest partition (~40 ns per token); on
-// the host a thread codes ~4 ns per token.  With plenty of host threads per context and few partitions the host wins; when
-// the ranks of one box share its cores (8 GPUs, 2 threads each) the GPU coder keeps the throughput from collapsing
-// (measured at 2 threads per context: 2365 vs 443 Mpix/s).  WGPU_DEVICE_CODER=0/1 forces either.
+// the host a thread codes ~4 ns per token.  For a batch of at least a warp of partitions the GPU route matches 16 host
+// threads (2336 vs 2339 Mpix/s end to end) and does not depend on the host at all (2365 Mpix/s with 2 threads per context,
+// where host coding gives 443); small batches keep the host's lower latency.  WGPU_DEVICE_CODER=0/1 forces either.
 static bool device_coder_wanted(const wgpu_ctx* ctx, size_t n_images) {
   const char* e = getenv("WGPU_DEVICE_CODER");  // read per call: tests flip it
   if (e && *e) return atoi(e) != 0;
-  return n_images >= 32 && threads_of(ctx) <= 8;
+  (void)ctx;
+  return n_images >= 32;  // a full warp of partitions: the GPU coder then matches 16 host threads and leaves the host free
 }
 // Where the macroblock data of the decoder is parsed (intra modes + coefficient tokens; the frame headers always on the
 // host).  On the GPU: one warp per image (dec_parse_kernel), 46 MB of compressed bytes up instead of 1.26 GB of
