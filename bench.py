@@ -116,10 +116,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (BASELINE configs[1]: 256)")
-    ap.add_argument("--e2e-workers", type=int, default=4, help="contexts per GPU used by the e2e leg: upload, device and finish stages of consecutive batches overlap")
+    ap.add_argument("--e2e-workers", type=int, default=5, help="contexts per GPU used by the e2e leg: upload, device and finish stages of consecutive batches overlap")
     ap.add_argument("--value-contexts", type=int, default=2, help="contexts whose device-resident steps run side by side in the `value` leg")
     ap.add_argument("--gpu-slots", type=int, default=2, help="how many contexts may have their mode-search waves on the GPU at once")
-    ap.add_argument("--finish-slots", type=int, default=0, help="how many contexts may be in their finish stage at once (default: 2 when the token partitions are coded on the GPU, else 1)")
+    ap.add_argument("--finish-slots", type=int, default=0, help="how many contexts may be in their finish stage at once (default: 3 when the token partitions are coded on the GPU, else 1)")
     ap.add_argument("--decode-workers", type=int, default=0, help="contexts per GPU for the decode e2e leg (default: 4 with the GPU macroblock parser, whose ~0.3 s latency per batch they hide; else the encode workers)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per context (default: cores / ranks on this node)")
     ap.add_argument("--no-decode", action="store_true")
@@ -167,7 +167,7 @@ def main():
     # the library codes the token partitions on the GPU for batches of at least 32 images (webpgpu.cu device_coder_wanted)
     env_coder = os.environ.get("WGPU_DEVICE_CODER", "")
     device_coder = (env_coder != "0") if env_coder else n >= 32
-    finish_slots = args.finish_slots or (2 if device_coder else 1)
+    finish_slots = args.finish_slots or (3 if device_coder else 1)
     upload_stage, gpu_stage, host_stage = threading.Lock(), threading.BoundedSemaphore(max(1, args.gpu_slots)), threading.BoundedSemaphore(finish_slots)
 
     class Worker:
