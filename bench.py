@@ -82,6 +82,10 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+METRIC = "lossy encode & decode Mpix/s (1536x1024 q75 m4), bit-exact"
+WORKLOAD = "synthetic 1536x1024 RGBA lossy encode q75 method 4, batch of %d images per GPU (BASELINE configs[1])"
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of the reference encoder, one image per thread on all host cores, bounded sample."""
     if rank != 0:
@@ -99,10 +103,11 @@ def run_reference(args, rank, world):
         oracle_lib.encode_batch(imgs, threads=cores)
     dt = time.perf_counter() - t0
     v = sample * W * H * args.steps / dt / 1e6
-    line = {"impl": "reference", "metric": "lossy encode Mpix/s (1536x1024 q75 m4, bit-exact)", "value": v, "unit": "Mpix/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-            "config": {"workload": "1536x1024 RGBA lossy encode q75 method 4 (reference parallel-path semantics)", "sample_images_per_step": sample},
+            "config": {"workload": WORKLOAD % args.batch, "sample_images_per_step": sample,
+                       "note": "the reference's row-parallel encoder (Method >= 3) restated in C++ (oracle/), all host cores"},
             "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
                              "sample": "%d images of the 1536x1024 q75 m4 workload per step, one image per thread (C++ oracle, -O2)" % sample},
             "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -294,10 +299,10 @@ def main():
                 "note": "bound by dependent-instruction latency x the 222-step wavefront chain (issue slots 45 % busy), not by HBM; see DESIGN.md 5",
                 "stages_ms": stage_ms,
                 "stages_gbs": {k: ALG_BYTES_PER_PX[k] * px_step / (v * 1e-3) / 1e9 for k, v in stage_ms.items()}}
-    result = {"metric": "lossy encode & decode Mpix/s (1536x1024 q75 m4), bit-exact", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": K,
+    result = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": K,
               "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
               "dtype": "u8/int32", "data": "synthetic",
-              "config": {"workload": "synthetic 1536x1024 RGBA lossy encode q75 method 4, batch of %d images per GPU (BASELINE configs[1])" % n,
+              "config": {"workload": WORKLOAD % n,
                          "batch_per_gpu": n, "l2": "inputs (%.0f MB RGBA per step) exceed the 126 MB L2" % (in_bytes / 1e6),
                          "parallelism": "images sharded across %d GPU(s), no collective" % world,
                          "batches_in_flight": len(vws)},
