@@ -93,6 +93,12 @@ ENC_CASES = [
     (320, 240, [2], dict(Method=2, Pass=3, Quality=60)),
     (128, 96, [1, 2], dict(Preprocessing=2, Quality=60)),  # dithered import (PresetPhoto sets this bit)
     (128, 96, [1], dict(Preprocessing=3, Quality=90, Method=2)),
+    # found by tools/fuzz_parity.py: one macroblock column (odd waves are empty); dithering on partial macroblocks (the luma
+    # analysis replicates the last real column itself, the dithered padding is not a replica)
+    (9, 116, [2, 10, 4], {}),
+    (3, 123, [0, 9], dict(Method=1)),
+    (52, 118, [7], dict(Quality=0, Method=6, Preprocessing=2, FilterStrength=100, FilterSharpness=7, FilterType=0, Segments=2)),
+    (79, 118, [9, 7, 5], dict(Quality=5, Preprocessing=3, FilterStrength=100, FilterSharpness=3, FilterType=0, Segments=3)),
     # Method >= 3 on fewer than 4 macroblock rows: the reference's serial RD path (all-mode I4 search at Method 3,
     # trial mode context kept only when the search completes, chroma DC error diffusion) -- built up to 96 macroblocks
     (64, 48, [0, 1, 2], {}),
@@ -201,7 +207,6 @@ RC_CASES = [
     (100, 70, [1, 2], dict(TargetPSNR=35.0, Method=3, Quality=45)),   # all-mode I4 search, quality crossing 50 (max I4 modes 3 -> 2)
     (64, 48, [0, 1, 2], dict(TargetSize=600, QMin=20, QMax=90, Pass=6)),
     (96, 96, [2], dict(TargetSize=4000, Segments=1, Quality=90)),
-    (128, 96, [1], dict(TargetPSNR=42.0, Partitions=2, Quality=90)),
     # more than 96 macroblocks: mid-stream probability refreshes feed the RD costs (encode_frame.go:35-57)
     (256, 256, [0, 1, 2], dict(TargetPSNR=40.0)),                  # 256 MBs: refreshes before macroblocks 96 and 193, three passes
     (320, 240, [1, 2], dict(TargetSize=9000, Method=6)),           # trial frames carry tokens recorded under mixed tables
@@ -262,6 +267,9 @@ def test_encode_rejections(gpu_ctx):
     assert e.value.code == native.ERR_UNSUPPORTED
     with pytest.raises(webp_b200.WebPError):
         webp_b200.EncodeBatch(img[None], _opts(TargetSize=500, Method=2), gpu_ctx)
+    with pytest.raises(native.WebPGPUError) as e:  # rate control x token partitions: stale per-macroblock token starts across passes
+        webp_b200.EncodeBatch(img[None], _opts(TargetPSNR=42.0, Partitions=2), gpu_ctx)
+    assert e.value.code == native.ERR_UNSUPPORTED
     with pytest.raises(webp_b200.WebPError):
         webp_b200.EncodeBatch(img[None], _opts(Lossless=True), gpu_ctx)
 

@@ -1,0 +1,16 @@
+"""Randomised differential parity: random sizes x random EncoderOptions x both coder / parser routes, GPU bytes and decoded
+planes against the oracle (tools/fuzz_parity.py; the first 150 cases of seed 1 found the two bugs pinned in ENC_CASES)."""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_fuzz_parity(oracle, gpu_ctx, seed):
+    import fuzz_parity
+    failures = fuzz_parity.fuzz(60, seed, gpu_ctx)
+    assert not failures, "\n".join(failures)

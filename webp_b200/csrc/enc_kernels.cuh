@@ -1403,6 +1403,8 @@ __global__ void __launch_bounds__(256) import_rgba_kernel(const ImportParams P) 
 struct AnalysisParams {
   const uint8_t* y; const uint8_t* u; const uint8_t* v; size_t y_plane, uv_plane;
   int n, mb_w, mb_h;
+  int width, height;  // the luma analysis replicates the last real column / row itself (encode_analysis.go:412-424): with dithering
+                      // the padded samples of the plane are NOT replicas (each drew its own rounding term)
   uint8_t* alpha;     // [n][nmb] mixed alpha
   uint8_t* uv_alpha;  // [n][nmb] chroma alpha (host sums it for dq_uv_ac)
 };
@@ -1439,16 +1441,21 @@ __global__ void __launch_bounds__(128) analysis_kernel(const AnalysisParams P) {
   const uint8_t* yp = P.y + (size_t)img * P.y_plane + (size_t)my * 16 * ys + mx * 16;
   int* hist = s_hist[grp];
   const int bx = gl & 3, by = gl >> 2;
+  // source coordinates clamped to the picture (relative to this macroblock's origin)
+  const int xmax = P.width - 1 - mx * 16, ymax = P.height - 1 - my * 16;
+  auto cx = [&](int i) { return min(i, xmax); };
+  auto cy = [&](int j) { return min(j, ymax); };
   int src[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const uint32_t w = *reinterpret_cast<const uint32_t*>(yp + (size_t)(by * 4 + j) * ys + bx * 4);
-    src[4 * j] = w & 0xff; src[4 * j + 1] = (w >> 8) & 0xff; src[4 * j + 2] = (w >> 16) & 0xff; src[4 * j + 3] = w >> 24;
+    const uint8_t* rowp = yp + (size_t)cy(by * 4 + j) * ys;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) src[4 * j + i] = rowp[cx(bx * 4 + i)];
   }
   // DC value from source neighbours (encode_analysis.go:455-500)
   int s = 0;
-  if (my > 0) s += yp[-(ptrdiff_t)ys + gl];
-  if (mx > 0) s += yp[(size_t)gl * ys - 1];
+  if (my > 0) s += yp[-(ptrdiff_t)ys + cx(gl)];
+  if (mx > 0) s += yp[(size_t)cy(gl) * ys - 1];
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
   const int count = (my > 0 ? 16 : 0) + (mx > 0 ? 16 : 0);
@@ -1468,12 +1475,12 @@ __global__ void __launch_bounds__(128) analysis_kernel(const AnalysisParams P) {
   }
   if (mx > 0 && my > 0) {  // uniform per 16-lane group; groups of a warp may diverge here, shuffles use width 16
     hist[gl] = 0; hist[gl + 16] = 0;
-    const uint32_t tw = *reinterpret_cast<const uint32_t*>(yp - (ptrdiff_t)ys + bx * 4);
-    const int tl = yp[-(ptrdiff_t)ys - 1];
-    const int t[4] = {(int)(tw & 0xff), (int)((tw >> 8) & 0xff), (int)((tw >> 16) & 0xff), (int)(tw >> 24)};
+    const uint8_t* topp = yp - (ptrdiff_t)ys;
+    const int tl = topp[-1];
+    const int t[4] = {(int)topp[cx(bx * 4)], (int)topp[cx(bx * 4 + 1)], (int)topp[cx(bx * 4 + 2)], (int)topp[cx(bx * 4 + 3)]};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int l = yp[(size_t)(by * 4 + j) * ys - 1];
+      const int l = yp[(size_t)cy(by * 4 + j) * ys - 1];
 #pragma unroll
       for (int i = 0; i < 4; ++i) pred[4 * j + i] = clip8(t[i] + l - tl);
     }

@@ -286,6 +286,9 @@ static int validate_enc_options(wgpu_ctx* ctx, const wgpu_enc_options* o, int wi
   // where no mid-stream probability refresh can occur (<= 96 macroblocks: encode_frame.go:24-40).
   const bool do_search = o->target_size > 0 || o->target_psnr > 0.f;
   if (do_search && o->method < 3) FAIL(WGPU_ERR_UNSUPPORTED, "TargetSize/TargetPSNR with Method < 3 (rate control over the non-RD serial path) is not built yet");
+  // With several token partitions the reference emits [mbStart[i], mbStart[i+1]) per macroblock, and mbStart keeps entries of
+  // EARLIER passes for macroblocks skipped in the last one: rate control x partitions would need every pass's token counts.
+  if (do_search && o->partitions > 0) FAIL(WGPU_ERR_UNSUPPORTED, "TargetSize/TargetPSNR with Partitions > 0 is not built (the reference's per-macroblock token start table carries stale entries across passes)");
   if (o->method >= 3 && (((height + 15) >> 4) < 4 || do_search) && ((height + 15) >> 4) * ((width + 15) >> 4) > 96 && o->partitions > 0)
     FAIL(WGPU_ERR_UNSUPPORTED, "the serial RD path with mid-stream probability refreshes (more than 96 macroblocks) is built for one token partition only");
   return WGPU_OK;
@@ -333,6 +336,7 @@ int launch_enc_waves_fn(wgpu_ctx* ctx, const wg::EncKernelParams& P, void (*kern
   const int waves = P.mb_w + 2 * (P.mb_h - 1);
   for (int w = 0; w < waves; ++w) {
     const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
+    if (tasks <= 0) continue;  // one macroblock column: odd waves hold no macroblock (x = w - 2y)
     const unsigned grid = (unsigned)((tasks + per_cta - 1) / per_cta);
     kernel<<<grid, WARPS * 32, smem, ctx->stream>>>(P, w);
     ctx->launches++;
@@ -356,6 +360,7 @@ int launch_enc_fast_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {  // Met
   const int waves = P.mb_w + 2 * (P.mb_h - 1);
   for (int w = 0; w < waves; ++w) {
     const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
+    if (tasks <= 0) continue;  // one macroblock column: odd waves hold no macroblock (x = w - 2y)
     const unsigned grid = (unsigned)((tasks + per_cta - 1) / per_cta);
     wg::encode_fast_wave_kernel<G, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(P, w);
     ctx->launches++;
@@ -508,7 +513,7 @@ static int enc_launch_analysis(wgpu_ctx* ctx) {
   wg::AnalysisParams ap;
   ap.y = ctx->sy.as<uint8_t>(); ap.u = ctx->su.as<uint8_t>(); ap.v = ctx->sv.as<uint8_t>();
   ap.y_plane = (size_t)nmb * 256; ap.uv_plane = (size_t)nmb * 64;
-  ap.n = n; ap.mb_w = ctx->e_mbw; ap.mb_h = ctx->e_mbh;
+  ap.n = n; ap.mb_w = ctx->e_mbw; ap.mb_h = ctx->e_mbh; ap.width = ctx->e_w; ap.height = ctx->e_h;
   ap.alpha = ctx->alpha.as<uint8_t>(); ap.uv_alpha = ctx->uv_alpha.as<uint8_t>();
   const long long total = (long long)nmb * n;
   wg::analysis_kernel<<<(unsigned)((total + 7) / 8), 128, 0, ctx->stream>>>(ap);
@@ -1199,6 +1204,7 @@ static int dec_launch_recon(wgpu_ctx* ctx, const wg::DecKernelParams& P) {
   const int per_cta = kDecWarps * (32 / kDecG);
   for (int w = 0; w < waves; ++w) {
     const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
+    if (tasks <= 0) continue;  // one macroblock column: odd waves hold no macroblock (x = w - 2y)
     wg::recon_wave_kernel<kDecG, kDecWarps><<<(unsigned)((tasks + per_cta - 1) / per_cta), kDecWarps * 32, 0, ctx->stream>>>(P, w);
     ctx->launches++;
   }
@@ -1210,6 +1216,7 @@ static int dec_launch_filter(wgpu_ctx* ctx, const wg::DecKernelParams& P) {
   const int per_cta = kFiltWarps * 2;
   for (int w = 0; w < waves; ++w) {
     const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
+    if (tasks <= 0) continue;  // one macroblock column: odd waves hold no macroblock (x = w - 2y)
     wg::filter_wave_kernel<kFiltWarps><<<(unsigned)((tasks + per_cta - 1) / per_cta), kFiltWarps * 32, 0, ctx->stream>>>(P, w);
     ctx->launches++;
   }
