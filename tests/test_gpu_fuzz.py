@@ -14,3 +14,9 @@ def test_fuzz_parity(oracle, gpu_ctx, seed):
     import fuzz_parity
     failures = fuzz_parity.fuzz(60, seed, gpu_ctx)
     assert not failures, "\n".join(failures)
+
+
+def test_fuzz_foreign_streams(oracle, gpu_ctx):
+    import fuzz_parity
+    failures = fuzz_parity.fuzz_foreign(40, 5, gpu_ctx)
+    assert not failures, "\n".join(failures)

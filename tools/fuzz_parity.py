@@ -89,9 +89,49 @@ def fuzz(cases, seed, ctx=None):
     return failures
 
 
+def fuzz_foreign(cases, seed, ctx=None):
+    """Streams of a foreign encoder (libwebp through Pillow: loop-filter deltas, quantiser deltas, modes and segment maps our
+    encoder never emits) through both macroblock-parser routes, planes against the oracle decoder."""
+    import io
+    from PIL import Image
+    rnd = random.Random(seed)
+    ctx = ctx or native.Context(0)
+    failures = []
+    saved = os.environ.get("WGPU_DEVICE_PARSER")
+    for c in range(cases):
+        w, h = rnd.randint(1, 300), rnd.randint(1, 220)
+        q, m = rnd.choice([1, 10, 30, 50, 75, 90, 100]), rnd.randint(0, 6)
+        n = rnd.choice([1, 2, 3])
+        streams = []
+        for k in range(n):
+            buf = io.BytesIO()
+            Image.fromarray(O.synth_image(w, h, rnd.randint(0, 11))[..., :3]).save(buf, "WEBP", quality=q, method=m)
+            streams.append(buf.getvalue())
+        os.environ["WGPU_DEVICE_PARSER"] = rnd.choice(["0", "1"])
+        desc = "foreign case %d: %dx%d q%d m%d n=%d parser=%s" % (c, w, h, q, m, n, os.environ["WGPU_DEVICE_PARSER"])
+        try:
+            gw, gh, y, u, v, rgba = webp_b200.webp.decode_padded(streams, nrgba=True, ctx=ctx)
+            for k in range(n):
+                _, _, ey, eu, ev = O.decode(streams[k])
+                if not (np.array_equal(y[k], ey) and np.array_equal(u[k], eu) and np.array_equal(v[k], ev) and
+                        np.array_equal(rgba[k], O.build_nrgba(w, h, ey, eu, ev))):
+                    failures.append("MISMATCH " + desc)
+                    print("MISMATCH", desc)
+                    break
+        except Exception as e:  # noqa
+            failures.append("ERROR " + desc + " " + repr(e)[:200])
+            print("ERROR", desc, repr(e)[:300])
+    if saved is None:
+        os.environ.pop("WGPU_DEVICE_PARSER", None)
+    else:
+        os.environ["WGPU_DEVICE_PARSER"] = saved
+    return failures
+
+
 if __name__ == "__main__":
     n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
     the_seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     fails = fuzz(n_cases, the_seed)
+    fails += fuzz_foreign(max(10, n_cases // 3), the_seed)
     print("fuzz: %d cases, %d bad (seed %d)" % (n_cases, len(fails), the_seed))
     sys.exit(1 if fails else 0)
