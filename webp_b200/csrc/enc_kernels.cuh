@@ -1158,26 +1158,32 @@ struct AllStatsParams {
   const int16_t* coeffs;   // [n][nmb][400]
   unsigned int* stats;     // [n][STATS_SIZE]
   int n_images, mb_w, mb_h;
+  int cut;                 // macroblocks with raster index >= cut count in their zero state (not yet encoded in the first pass:
+                           // I16, not skipped, no coefficients -- encode_frame.go:35-57 over a fresh mbInfo); nmb = none
 };
 __global__ void __launch_bounds__(128) collect_all_stats_kernel(const AllStatsParams P) {
   const int nmb = P.mb_w * P.mb_h;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint8_t s_zero[48];  // the zero-state header
+  if (threadIdx.x < 48) s_zero[threadIdx.x] = 0;
+  __syncthreads();
   if (gid >= (long long)nmb * P.n_images) return;
   const int img = (int)(gid / nmb), idx = (int)(gid % nmb), mx = idx % P.mb_w, my = idx / P.mb_w;
   const uint8_t* H = P.hdr + (size_t)img * nmb * 48;
-  const uint8_t* h = H + (size_t)idx * 48;
+  auto hdr_of = [&](int i) -> const uint8_t* { return i >= P.cut ? s_zero : H + (size_t)i * 48; };
+  const uint8_t* h = hdr_of(idx);
   if (h[4]) return;  // skipped: contributes nothing
   const int16_t* c = P.coeffs + ((size_t)img * nmb + idx) * 400;
   unsigned int* st = P.stats + (size_t)img * STATS_SIZE;
   auto y_flag = [](const uint8_t* n, int b) -> uint32_t { return n[24 + b] > (n[0] == 0 ? 1 : 0); };  // l = nz > first
   uint32_t top = 0, left = 0;
   if (my > 0) {
-    const uint8_t* n = h - (size_t)P.mb_w * 48;
+    const uint8_t* n = hdr_of(idx - P.mb_w);
     if (!n[4]) top = y_flag(n, 12) | (y_flag(n, 13) << 1) | (y_flag(n, 14) << 2) | (y_flag(n, 15) << 3) | ((uint32_t)(n[42] > 0) << 4) |
                      ((uint32_t)(n[43] > 0) << 5) | ((uint32_t)(n[46] > 0) << 6) | ((uint32_t)(n[47] > 0) << 7);
   }
   if (mx > 0) {
-    const uint8_t* n = h - 48;
+    const uint8_t* n = hdr_of(idx - 1);
     if (!n[4]) left = y_flag(n, 3) | (y_flag(n, 7) << 1) | (y_flag(n, 11) << 2) | (y_flag(n, 15) << 3) | ((uint32_t)(n[41] > 0) << 4) |
                       ((uint32_t)(n[43] > 0) << 5) | ((uint32_t)(n[45] > 0) << 6) | ((uint32_t)(n[47] > 0) << 7);
   }
@@ -1185,11 +1191,11 @@ __global__ void __launch_bounds__(128) collect_all_stats_kernel(const AllStatsPa
   if (h[0] == 0) {
     int top_dc = 0, left_dc = 0;
     for (int y = my - 1; y >= 0; --y) {
-      const uint8_t* n = H + (size_t)(y * P.mb_w + mx) * 48;
+      const uint8_t* n = hdr_of(y * P.mb_w + mx);
       if (n[0] == 0) { top_dc = n[4] ? 0 : (n[5] > 0); break; }
     }
     for (int x = mx - 1; x >= 0; --x) {
-      const uint8_t* n = H + (size_t)(my * P.mb_w + x) * 48;
+      const uint8_t* n = hdr_of(my * P.mb_w + x);
       if (n[0] == 0) { left_dc = n[4] ? 0 : (n[5] > 0); break; }
     }
     stat_block_dev(c + 384, (int)h[5], 1, 0, top_dc + left_dc, st, true);

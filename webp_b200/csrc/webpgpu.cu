@@ -80,8 +80,8 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, lc_img, eob_img;
-  PinBuf h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, lc_img, eob_img, stats_cuts;
+  PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false, e_keep_derr = false, e_keep_stats = false;
   int dither_w = 0, dither_h = 0, dither_amp_cached = 0;  // what the device dither tables currently hold
@@ -92,7 +92,7 @@ struct wgpu_ctx {
   std::vector<uint8_t> sp_proba;
   std::vector<std::vector<uint8_t>> sp_hist;  // [image] -> tables [k][1056] in force from macroblock sp_starts[k] on
   std::vector<int> sp_starts;
-  bool e_refresh_route = false;
+  bool e_refresh_route = false, e_token_route = false;
   // decoder state
   DevBuf d_coeffs, d_meta, d_ftype, dy, du, dv, d_nrgba, d_alpha, d_streams, d_hdrs, d_perr, t_bmodes;
   PinBuf hd_streams, hd_hdrs, hd_perr;
@@ -119,6 +119,7 @@ struct wgpu_ctx {
 #define FAIL(code, msg) do { ctx->err = (msg); return (code); } while (0)
 
 static int threads_of(const wgpu_ctx* ctx);
+static int getenv_int(const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
 // Where the token partition is boolean-coded.  The coder is one serial chain per partition.  On the GPU the batch's
 // partitions run one per lane on a few dedicated SMs and the batch waits for its longest partition (~40 ns per token); on
 // the host a thread codes ~4 ns per token.  For a batch of at least a warp of partitions the GPU route matches 16 host
@@ -218,14 +219,14 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img,
+  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_streams, &ctx->d_hdrs, &ctx->d_perr, &ctx->t_bmodes, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
                   &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
                   &ctx->m_sse, &ctx->m_ssim};
   for (DevBuf* b : db) b->release();
-  PinBuf* pb[] = {&ctx->hd_streams, &ctx->hd_hdrs, &ctx->hd_perr, &ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
+  PinBuf* pb[] = {&ctx->h_stats_cuts, &ctx->hd_streams, &ctx->hd_hdrs, &ctx->hd_perr, &ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
                   &ctx->hd_meta, &ctx->hd_ftype, &ctx->hd_planes, &ctx->hd_nrgba};
   for (PinBuf* b : pb) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -588,7 +589,7 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
     auto all_stats = [&]() -> int {
       wg::AllStatsParams A;
       A.hdr = ctx->hdr.as<uint8_t>(); A.coeffs = ctx->coeffs.as<int16_t>(); A.stats = ctx->stats.as<unsigned int>();
-      A.n_images = n; A.mb_w = mbw; A.mb_h = mbh;
+      A.n_images = n; A.mb_w = mbw; A.mb_h = mbh; A.cut = nmb;
       CK(cudaMemsetAsync(ctx->stats.p, 0, (size_t)n * wg::STATS_SIZE * 4, ctx->stream));
       wg::collect_all_stats_kernel<<<(unsigned)(((long long)n * nmb + 127) / 128), 128, 0, ctx->stream>>>(A);
       ctx->launches++;
@@ -664,17 +665,20 @@ static wg::TokenParams token_params(wgpu_ctx* ctx) {
 }
 // Single-partition route, device part 1 (queued right behind the waves): final probabilities from the token statistics,
 // tokens per macroblock, per-image prefix sums and totals.
-static int enc_launch_token_prepass(wgpu_ctx* ctx) {
+static int enc_launch_token_prepass(wgpu_ctx* ctx, bool run_optimize = true) {
   const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
-  wg::ProbaParams pp;
-  pp.stats = ctx->stats.as<unsigned int>(); pp.proba0 = ctx->t_proba0.as<uint8_t>(); pp.update = ctx->t_upd.as<uint8_t>();
-  pp.ecost = ctx->t_ecost.as<uint16_t>(); pp.proba = ctx->proba.as<uint8_t>(); pp.n_images = n;
-  wg::optimize_proba_kernel<<<n, 352, 0, ctx->stream>>>(pp);
+  if (run_optimize) {
+    wg::ProbaParams pp;
+    pp.stats = ctx->stats.as<unsigned int>(); pp.proba0 = ctx->t_proba0.as<uint8_t>(); pp.update = ctx->t_upd.as<uint8_t>();
+    pp.ecost = ctx->t_ecost.as<uint16_t>(); pp.proba = ctx->proba.as<uint8_t>(); pp.n_images = n;
+    wg::optimize_proba_kernel<<<n, 352, 0, ctx->stream>>>(pp);
+    ctx->launches++;
+  }
   const wg::TokenParams T = token_params(ctx);
   const long long total = (long long)nmb * n;
   wg::token_kernel<false><<<(unsigned)((total + 15) / 16), 128, 0, ctx->stream>>>(T);
   wg::token_scan_kernel<<<n, 256, 0, ctx->stream>>>(T);
-  ctx->launches += 3;
+  ctx->launches += 2;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->h_totals.p, ctx->img_total.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   ctx->xfer_d2h += (uint64_t)((size_t)n * 8);
@@ -702,6 +706,48 @@ static int enc_analyze_locked(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
   return WGPU_OK;
 }
 // segment map + per-image parameters (already in the pinned staging buffers) -> device, then all waves
+// Method < 3, one token partition: the final probabilities of the serial path without bringing the levels back.  The mode
+// decisions of this path do not read the probabilities, so every pass of statLoop and the main pass encode the same
+// macroblocks; what evolves is the probability state: refreshProbas at macroblocks k*M + (k-1) of the FIRST pass sees this
+// pass's macroblocks above the refresh point and a fresh (zero-state) array below it, every later optimisation sees the whole
+// frame and is idempotent (host_enc.h::serialize_frame_serial).  The statistics of each refresh point are taken on the GPU
+// (collect_all_stats_kernel with a cut), the stateful optimizeProba chain is folded on the host (8 KB per image and point),
+// and the result goes back up for token generation.
+static int enc_fold_serial_probas(wgpu_ctx* ctx) {
+  const int n = ctx->e_n, mbw = ctx->e_mbw, mbh = ctx->e_mbh, nmb = mbw * mbh;
+  const int max_count = std::max(nmb >> 3, 96);
+  std::vector<int> cuts;
+  for (int k = 1; k * max_count + (k - 1) < nmb; ++k) cuts.push_back(k * max_count + (k - 1));
+  const size_t K = cuts.size(), one = (size_t)n * wg::STATS_SIZE * 4;
+  RESERVE(ctx->stats_cuts, std::max<size_t>(K, 1) * one);
+  RESERVE(ctx->h_stats_cuts, std::max<size_t>(K, 1) * one);
+  RESERVE(ctx->h_stats, one);
+  for (size_t k = 0; k < K; ++k) {
+    wg::AllStatsParams A;
+    A.hdr = ctx->hdr.as<uint8_t>(); A.coeffs = ctx->coeffs.as<int16_t>();
+    A.stats = ctx->stats_cuts.as<unsigned int>() + k * (size_t)n * wg::STATS_SIZE;
+    A.n_images = n; A.mb_w = mbw; A.mb_h = mbh; A.cut = cuts[k];
+    CK(cudaMemsetAsync(A.stats, 0, one, ctx->stream));
+    wg::collect_all_stats_kernel<<<(unsigned)(((long long)n * nmb + 127) / 128), 128, 0, ctx->stream>>>(A);
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  if (K) { CK(cudaMemcpyAsync(ctx->h_stats_cuts.p, ctx->stats_cuts.p, K * one, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)(K * one); }
+  CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->stats.p, one, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->xfer_d2h += (uint64_t)one;
+  CK(cudaStreamSynchronize(ctx->stream));
+  parallel_for(n, threads_of(ctx), [&](int i) {
+    uint8_t (*pr)[8][3][11] = reinterpret_cast<uint8_t (*)[8][3][11]>(ctx->h_proba.as<uint8_t>() + (size_t)i * 1056);
+    memcpy(pr, wgh::kCoeffsProba0, 1056);
+    for (size_t k = 0; k < K; ++k)
+      wgh::optimize_proba_host(*reinterpret_cast<const wgh::Stats*>(ctx->h_stats_cuts.as<uint32_t>() + (k * n + i) * wg::STATS_SIZE), pr);
+    wgh::optimize_proba_host(*reinterpret_cast<const wgh::Stats*>(ctx->h_stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE), pr);
+  });
+  CK(cudaMemcpyAsync(ctx->proba.p, ctx->h_proba.p, (size_t)n * 1056, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)((size_t)n * 1056);
+  return WGPU_OK;
+}
+
 // Rate control (doSearch: TargetSize / TargetPSNR), internal/lossy/encode.go:1338-1374 + adjustQuantForTarget / computeNextQ
 // (:1505-1590): at least three serial encodeFrame passes; after each one the quality moves by the secant rule on the size of
 // a trial frame (TargetSize) or on the reference's PSNR reading, which is 99.0 dB every time because MBEncInfo.Disto is
@@ -805,7 +851,17 @@ static int enc_search_locked(wgpu_ctx* ctx) {
   } else if ((rc = enc_launch_waves(ctx))) {
     return rc;
   }
-  if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3 && !ctx->e_refresh_route && (rc = enc_launch_token_prepass(ctx))) return rc;
+  ctx->e_token_route = false;
+  if (ctx->e_opt.partitions == 0 && !ctx->e_refresh_route) {
+    if (ctx->e_opt.method >= 3) {
+      if ((rc = enc_launch_token_prepass(ctx))) return rc;
+      ctx->e_token_route = true;
+    } else if (ctx->plans.size() == (size_t)ctx->e_n && getenv_int("WGPU_FAST_TOKEN_ROUTE", 1)) {
+      if ((rc = enc_fold_serial_probas(ctx))) return rc;
+      if ((rc = enc_launch_token_prepass(ctx, false))) return rc;
+      ctx->e_token_route = true;
+    }
+  }
   ctx->e_done = true;
   return WGPU_OK;
 }
@@ -946,7 +1002,7 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       if (riff.size() > out_stride) { too_small.store(1); return; }
       memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
     });
-  } else if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3 && device_coder_wanted(ctx, n)) {
+  } else if (ctx->e_token_route && device_coder_wanted(ctx, n)) {
     // ---- single partition: tokens are generated AND boolean-coded on the GPU (token_kernel, boolcode_kernel); the host
     // emits partition 0 (modes, a few bits per macroblock) while the coder runs, then lays the frames out
     CK(cudaStreamSynchronize(ctx->stream));  // waves + token pre-pass done, per-image totals on the host
@@ -1029,7 +1085,7 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, hdr D2H %.2f ms, partition 0 on host %.2f ms (%d threads), wait coder %.2f ms (%.1f M tokens, longest partition %.2f M), "
               "frames D2H %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, threads_of(ctx), t4 - t3, (double)all / 1e6,
               (double)*std::max_element(totals, totals + n) / 1e6, now_ms() - t4);
-  } else if (ctx->e_opt.partitions == 0 && ctx->e_opt.method >= 3) {
+  } else if (ctx->e_token_route) {
     // ---- single partition: tokens are generated on the GPU, the host only boolean-codes flat arrays
     CK(cudaStreamSynchronize(ctx->stream));  // waves + token pre-pass done, per-image totals on the host
     const double t1 = now_ms();
