@@ -22,6 +22,8 @@ def fuzz(cases, seed, ctx=None):
         w, h = rnd.choice([(16, 16), (33, 17), (64, 48), (100, 70), (128, 96), (130, 71), (200, 150), (256, 64), (320, 240), (48, 200), (640, 40)])
         if rnd.random() < 0.3:
             w, h = rnd.randint(1, 260), rnd.randint(1, 200)
+        if os.environ.get("FUZZ_BIG") and rnd.random() < 0.5:  # several probability refreshes on the serial paths
+            w, h = rnd.choice([(400, 300), (640, 360), (512, 512), (1000, 48), (333, 777)])
         o = webp_b200.DefaultOptions()
         o.Quality = rnd.choice([0, 5, 20, 40, 49, 50, 60, 75, 90, 98, 100])
         o.Method = rnd.randint(0, 6)
