@@ -213,6 +213,11 @@ RC_CASES = [
     (640, 48, [0, 2], dict(Method=4)),                             # 120 MBs on 3 rows: serial path without rate control
     (1600, 40, [1], dict(Method=3, Quality=60)),                   # 300 MBs, all-mode I4 search
     (200, 150, [0, 1, 2, 4], dict(TargetSize=3000, Quality=50, QMin=10, QMax=80)),
+    # Method < 3: statLoop, then the search passes over the non-RD serial path; refresh points see the previous pass below them
+    (128, 96, [0, 1, 2], dict(Method=2, TargetSize=1500)),
+    (256, 256, [1, 2, 5], dict(Method=2, TargetSize=5000, Quality=80)),
+    (320, 240, [0, 2], dict(Method=0, TargetPSNR=40.0, Pass=2)),
+    (400, 300, [1, 4], dict(Method=1, TargetSize=12000, Quality=60, Segments=2)),
 ]
 
 
@@ -265,8 +270,6 @@ def test_encode_rejections(gpu_ctx):
     with pytest.raises(native.WebPGPUError) as e:  # the refresh schedule is built for one token partition only
         webp_b200.EncodeBatch(big[None], _opts(TargetPSNR=40.0, Partitions=1), gpu_ctx)
     assert e.value.code == native.ERR_UNSUPPORTED
-    with pytest.raises(webp_b200.WebPError):
-        webp_b200.EncodeBatch(img[None], _opts(TargetSize=500, Method=2), gpu_ctx)
     with pytest.raises(native.WebPGPUError) as e:  # rate control x token partitions: stale per-macroblock token starts across passes
         webp_b200.EncodeBatch(img[None], _opts(TargetPSNR=42.0, Partitions=2), gpu_ctx)
     assert e.value.code == native.ERR_UNSUPPORTED

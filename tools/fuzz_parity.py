@@ -37,9 +37,9 @@ def fuzz(cases, seed, ctx=None):
         mode = rnd.random()
         nmb = ((w + 15) // 16) * ((h + 15) // 16)
         serial = o.Method >= 3 and (((h + 15) // 16) < 4)
-        if mode < 0.25 and o.Method >= 3:
+        if mode < 0.25:
             o.TargetSize = rnd.choice([300, 1000, 3000, 8000]); serial = True
-        elif mode < 0.45 and o.Method >= 3:
+        elif mode < 0.45:
             o.TargetPSNR = rnd.choice([30.0, 38.5, 45.0]); serial = True
             o.QMin, o.QMax = rnd.choice([(0, -1), (10, 80), (0, 100), (30, 60)])
         o.Partitions = rnd.choice([0, 0, 0, 1, 2, 3])

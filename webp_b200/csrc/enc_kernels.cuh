@@ -240,7 +240,8 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   // SERIAL (the reference's serial encodeFrame order): `wave` is the raster macroblock index, one macroblock per image per
   // launch.  Rate-control passes (adjustQuantForTarget) re-encode only the images that have not converged: bit 8 of
   // seg[0].flags parks an image, bits 0-7 carry its own getMaxI4RDModes (its quality moves with the search).
-  const int img_flags = (SERIAL && task < total && (P.serial_gpw == 0 || g < P.serial_gpw)) ? P.img[(int)task].seg[0].flags : 0;
+  const bool in_range = task < total && (!SERIAL || P.serial_gpw == 0 || g < P.serial_gpw);
+  const int img_flags = ((SERIAL || FAST) && in_range) ? P.img[SERIAL ? (int)task : (int)(task / rows)].seg[0].flags : 0;
   const bool active = task < total && !(img_flags & 0x100) && (!SERIAL || P.serial_gpw == 0 || g < P.serial_gpw);
   const int max_i4_modes = (img_flags & 0xff) ? (img_flags & 0xff) : P.max_i4_modes;
   const int img = active ? (SERIAL ? (int)task : (int)(task / rows)) : 0;
@@ -1158,8 +1159,11 @@ struct AllStatsParams {
   const int16_t* coeffs;   // [n][nmb][400]
   unsigned int* stats;     // [n][STATS_SIZE]
   int n_images, mb_w, mb_h;
-  int cut;                 // macroblocks with raster index >= cut count in their zero state (not yet encoded in the first pass:
-                           // I16, not skipped, no coefficients -- encode_frame.go:35-57 over a fresh mbInfo); nmb = none
+  int cut;                 // macroblocks with raster index >= cut come from the PREVIOUS pass (hdr_prev / coeffs_prev) or, when
+                           // those are null, count in their zero state (not yet encoded in the first pass: I16, not skipped, no
+                           // coefficients -- encode_frame.go:35-57 over a fresh mbInfo); nmb = none
+  const uint8_t* hdr_prev;
+  const int16_t* coeffs_prev;
 };
 __global__ void __launch_bounds__(128) collect_all_stats_kernel(const AllStatsParams P) {
   const int nmb = P.mb_w * P.mb_h;
@@ -1170,10 +1174,11 @@ __global__ void __launch_bounds__(128) collect_all_stats_kernel(const AllStatsPa
   if (gid >= (long long)nmb * P.n_images) return;
   const int img = (int)(gid / nmb), idx = (int)(gid % nmb), mx = idx % P.mb_w, my = idx / P.mb_w;
   const uint8_t* H = P.hdr + (size_t)img * nmb * 48;
-  auto hdr_of = [&](int i) -> const uint8_t* { return i >= P.cut ? s_zero : H + (size_t)i * 48; };
+  const uint8_t* HP = P.hdr_prev ? P.hdr_prev + (size_t)img * nmb * 48 : nullptr;
+  auto hdr_of = [&](int i) -> const uint8_t* { return i >= P.cut ? (HP ? HP + (size_t)i * 48 : s_zero) : H + (size_t)i * 48; };
   const uint8_t* h = hdr_of(idx);
   if (h[4]) return;  // skipped: contributes nothing
-  const int16_t* c = P.coeffs + ((size_t)img * nmb + idx) * 400;
+  const int16_t* c = ((idx >= P.cut && P.coeffs_prev) ? P.coeffs_prev : P.coeffs) + ((size_t)img * nmb + idx) * 400;
   unsigned int* st = P.stats + (size_t)img * STATS_SIZE;
   auto y_flag = [](const uint8_t* n, int b) -> uint32_t { return n[24 + b] > (n[0] == 0 ? 1 : 0); };  // l = nz > first
   uint32_t top = 0, left = 0;

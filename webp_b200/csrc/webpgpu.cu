@@ -80,7 +80,7 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, lc_img, eob_img, stats_cuts;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
   PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false, e_keep_derr = false, e_keep_stats = false;
@@ -219,7 +219,7 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts,
+  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_streams, &ctx->d_hdrs, &ctx->d_perr, &ctx->t_bmodes, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
@@ -286,7 +286,6 @@ static int validate_enc_options(wgpu_ctx* ctx, const wgpu_enc_options* o, int wi
   // The serial RD path (Method >= 3 on fewer than 4 macroblock rows, or any size under TargetSize / TargetPSNR) is built only
   // where no mid-stream probability refresh can occur (<= 96 macroblocks: encode_frame.go:24-40).
   const bool do_search = o->target_size > 0 || o->target_psnr > 0.f;
-  if (do_search && o->method < 3) FAIL(WGPU_ERR_UNSUPPORTED, "TargetSize/TargetPSNR with Method < 3 (rate control over the non-RD serial path) is not built yet");
   // With several token partitions the reference emits [mbStart[i], mbStart[i+1]) per macroblock, and mbStart keeps entries of
   // EARLIER passes for macroblocks skipped in the last one: rate control x partitions would need every pass's token counts.
   if (do_search && o->partitions > 0) FAIL(WGPU_ERR_UNSUPPORTED, "TargetSize/TargetPSNR with Partitions > 0 is not built (the reference's per-macroblock token start table carries stale entries across passes)");
@@ -589,7 +588,7 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
     auto all_stats = [&]() -> int {
       wg::AllStatsParams A;
       A.hdr = ctx->hdr.as<uint8_t>(); A.coeffs = ctx->coeffs.as<int16_t>(); A.stats = ctx->stats.as<unsigned int>();
-      A.n_images = n; A.mb_w = mbw; A.mb_h = mbh; A.cut = nmb;
+      A.n_images = n; A.mb_w = mbw; A.mb_h = mbh; A.cut = nmb; A.hdr_prev = nullptr; A.coeffs_prev = nullptr;
       CK(cudaMemsetAsync(ctx->stats.p, 0, (size_t)n * wg::STATS_SIZE * 4, ctx->stream));
       wg::collect_all_stats_kernel<<<(unsigned)(((long long)n * nmb + 127) / 128), 128, 0, ctx->stream>>>(A);
       ctx->launches++;
@@ -726,7 +725,7 @@ static int enc_fold_serial_probas(wgpu_ctx* ctx) {
     wg::AllStatsParams A;
     A.hdr = ctx->hdr.as<uint8_t>(); A.coeffs = ctx->coeffs.as<int16_t>();
     A.stats = ctx->stats_cuts.as<unsigned int>() + k * (size_t)n * wg::STATS_SIZE;
-    A.n_images = n; A.mb_w = mbw; A.mb_h = mbh; A.cut = cuts[k];
+    A.n_images = n; A.mb_w = mbw; A.mb_h = mbh; A.cut = cuts[k]; A.hdr_prev = nullptr; A.coeffs_prev = nullptr;
     CK(cudaMemsetAsync(A.stats, 0, one, ctx->stream));
     wg::collect_all_stats_kernel<<<(unsigned)(((long long)n * nmb + 127) / 128), 128, 0, ctx->stream>>>(A);
     ctx->launches++;
@@ -776,7 +775,31 @@ static int enc_search_rate_control(wgpu_ctx* ctx) {
   if (do_size) { RESERVE(ctx->h_hdr, (size_t)n * nmb * 48); RESERVE(ctx->h_coeffs, (size_t)n * nmb * 800); }
   std::vector<uint32_t> zero_stats(wg::STATS_SIZE, 0);
   int rc = 0;
-  for (int pass = 0; pass < max_passes; ++pass) {
+  // Method < 3: the decisions do not read the probabilities, so a pass is one run of the wavefront kernel and the refresh
+  // schedule is replayed afterwards: the statistics of refresh point k are those of this pass above the point and of the
+  // PREVIOUS pass below it (collect_all_stats_kernel with a cut and the previous arrays), folded statefully on the host.
+  // statLoop (encode.go:1405) runs first at the starting quality; its first pass sees a zero-state array below the points.
+  const bool fast = base.method < 3;
+  const int mbw = ctx->e_mbw, mbh = ctx->e_mbh;
+  std::vector<int> cuts;
+  const size_t one = (size_t)n * wg::STATS_SIZE * 4;
+  auto cut_stats = [&](bool with_prev) -> int {  // statistics of every refresh point -> h_stats_cuts (synchronises)
+    for (size_t k = 0; k < cuts.size(); ++k) {
+      wg::AllStatsParams A;
+      A.hdr = ctx->hdr.as<uint8_t>(); A.coeffs = ctx->coeffs.as<int16_t>();
+      A.stats = ctx->stats_cuts.as<unsigned int>() + k * (size_t)n * wg::STATS_SIZE;
+      A.n_images = n; A.mb_w = mbw; A.mb_h = mbh; A.cut = cuts[k]; A.hdr_prev = nullptr; A.coeffs_prev = nullptr;
+      A.hdr_prev = with_prev ? ctx->hdr_prev.as<uint8_t>() : nullptr; A.coeffs_prev = with_prev ? ctx->coeffs_prev.as<int16_t>() : nullptr;
+      CK(cudaMemsetAsync(A.stats, 0, one, ctx->stream));
+      wg::collect_all_stats_kernel<<<(unsigned)(((long long)n * nmb + 127) / 128), 128, 0, ctx->stream>>>(A);
+      ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    if (!cuts.empty()) { CK(cudaMemcpyAsync(ctx->h_stats_cuts.p, ctx->stats_cuts.p, cuts.size() * one, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)(cuts.size() * one); }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return WGPU_OK;
+  };
+  auto upload_plans = [&]() -> int {
     wg::ImageParams* hp = ctx->h_params.as<wg::ImageParams>();
     for (int i = 0; i < n; ++i) {
       memcpy(&hp[i], ctx->plans[i].dev, sizeof(wg::ImageParams));
@@ -787,10 +810,68 @@ static int enc_search_rate_control(wgpu_ctx* ctx) {
     ctx->xfer_h2d += (uint64_t)((size_t)n * nmb);
     CK(cudaMemcpyAsync(ctx->img_params.p, ctx->h_params.p, (size_t)n * sizeof(wg::ImageParams), cudaMemcpyHostToDevice, ctx->stream));
     ctx->xfer_h2d += (uint64_t)((size_t)n * sizeof(wg::ImageParams));
-    ctx->e_keep_derr = pass > 0; ctx->e_keep_stats = true;
+    return WGPU_OK;
+  };
+  if (fast) {
+    const int max_count = std::max(nmb >> 3, 96);
+    for (int k = 1; k * max_count + (k - 1) < nmb; ++k) cuts.push_back(k * max_count + (k - 1));
+    RESERVE(ctx->stats_cuts, std::max<size_t>(cuts.size(), 1) * one); RESERVE(ctx->h_stats_cuts, std::max<size_t>(cuts.size(), 1) * one);
+    RESERVE(ctx->h_stats, one);
+    RESERVE(ctx->hdr_prev, (size_t)n * nmb * 48); RESERVE(ctx->coeffs_prev, (size_t)n * nmb * 800);
+    RESERVE(ctx->h_hdr, (size_t)n * nmb * 48); RESERVE(ctx->h_coeffs, (size_t)n * nmb * 800);
+    ctx->sp_proba.resize((size_t)n * 1056);
+    ctx->sp_hist.assign(n, std::vector<uint8_t>());
+    ctx->sp_starts.assign(1, 0);
+    for (int c : cuts) ctx->sp_starts.push_back(c);
+    // statLoop at the starting quality
+    if ((rc = upload_plans())) return rc;
+    ctx->e_keep_stats = true;
     rc = enc_launch_waves(ctx);
-    ctx->e_keep_derr = ctx->e_keep_stats = false;
+    ctx->e_keep_stats = false;
     if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->stats.p, one, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)one;
+    if ((rc = cut_stats(false))) return rc;
+    parallel_for(n, threads_of(ctx), [&](int i) {
+      uint8_t (*pr)[8][3][11] = reinterpret_cast<uint8_t (*)[8][3][11]>(&ctx->sp_proba[(size_t)i * 1056]);
+      memcpy(pr, wgh::kCoeffsProba0, 1056);
+      for (size_t k = 0; k < cuts.size(); ++k)
+        wgh::optimize_proba_host(*reinterpret_cast<const wgh::Stats*>(ctx->h_stats_cuts.as<uint32_t>() + (k * n + i) * wg::STATS_SIZE), pr);
+      wgh::optimize_proba_host(*reinterpret_cast<const wgh::Stats*>(ctx->h_stats.as<uint32_t>() + (size_t)i * wg::STATS_SIZE), pr);
+    });
+  }
+  for (int pass = 0; pass < max_passes; ++pass) {
+    if (fast) {
+      if (pass > 0) {  // pass 0 repeats statLoop's arrays (same quality, same decisions): nothing to run, its refreshes are idempotent
+        CK(cudaMemcpyAsync(ctx->hdr_prev.p, ctx->hdr.p, (size_t)n * nmb * 48, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->coeffs_prev.p, ctx->coeffs.p, (size_t)n * nmb * 800, cudaMemcpyDeviceToDevice, ctx->stream));
+        if ((rc = upload_plans())) return rc;
+        ctx->e_keep_stats = true;
+        rc = enc_launch_waves(ctx);
+        ctx->e_keep_stats = false;
+        if (rc) return rc;
+        if ((rc = cut_stats(true))) return rc;
+      }
+      // probability state through this pass's refreshes, and the table each stretch of macroblocks was recorded under
+      parallel_for(n, threads_of(ctx), [&](int i) {
+        if (!rcs[i].active) return;
+        uint8_t (*pr)[8][3][11] = reinterpret_cast<uint8_t (*)[8][3][11]>(&ctx->sp_proba[(size_t)i * 1056]);
+        std::vector<uint8_t>& hist = ctx->sp_hist[i];
+        hist.assign(&ctx->sp_proba[(size_t)i * 1056], &ctx->sp_proba[(size_t)i * 1056] + 1056);
+        for (size_t k = 0; k < cuts.size(); ++k) {
+          if (pass > 0)
+            wgh::optimize_proba_host(*reinterpret_cast<const wgh::Stats*>(ctx->h_stats_cuts.as<uint32_t>() + (k * n + i) * wg::STATS_SIZE), pr);
+          hist.insert(hist.end(), &ctx->sp_proba[(size_t)i * 1056], &ctx->sp_proba[(size_t)i * 1056] + 1056);
+        }
+      });
+    } else {
+      if ((rc = upload_plans())) return rc;
+      ctx->e_keep_derr = pass > 0; ctx->e_keep_stats = true;
+      rc = enc_launch_waves(ctx);
+      ctx->e_keep_derr = ctx->e_keep_stats = false;
+      if (rc) return rc;
+    }
+    const bool tables_route = fast || ctx->e_refresh_route;
     if (do_size) {  // trial frame of every image still searching: emitFrame with the probabilities as they stand (defaults)
       CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, (size_t)n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
       ctx->xfer_d2h += (uint64_t)((size_t)n * nmb * 48);
@@ -804,7 +885,7 @@ static int enc_search_rate_control(wgpu_ctx* ctx) {
       wgh::FramePlan& fp = ctx->plans[i];
       if (do_size) {
         std::vector<uint8_t> riff;
-        if (ctx->e_refresh_route) {  // tokens as recorded during the pass: each stretch under the table then in force
+        if (tables_route) {  // tokens as recorded during the pass: each stretch under the table then in force
           const int nt = (int)ctx->sp_starts.size();
           std::vector<const uint8_t*> tabs(nt);
           for (int k = 0; k < nt; ++k) tabs[k] = &ctx->sp_hist[i][(size_t)k * 1056];
@@ -837,6 +918,7 @@ static int enc_search_rate_control(wgpu_ctx* ctx) {
     for (const auto& r : rcs) any |= r.active;
     if (!any) break;
   }
+  if (fast) ctx->e_refresh_route = true;  // wgpu_enc_finish: final optimizeProba on this state, tokens per table or re-recorded
   return WGPU_OK;
 }
 static int enc_search_locked(wgpu_ctx* ctx) {

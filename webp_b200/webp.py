@@ -169,8 +169,6 @@ def _unsupported(o):
         return "webp: Lossless (VP8L) is outside the GPU lossy path"
     if o.UseSharpYUV:
         return "webp: UseSharpYUV is outside the GPU lossy path"
-    if (o.TargetSize > 0 or o.TargetPSNR > 0) and o.Method < 3:
-        return "webp: TargetSize/TargetPSNR with Method < 3 (rate control over the non-RD serial path) is not built yet"
     if o.ICC or o.EXIF or o.XMP:
         return "webp: metadata chunks (VP8X container) are host-side container work outside this path"
     return None
