@@ -231,9 +231,10 @@ struct BoolCodeParams {
 // which keeps both the 16-byte cp.async destinations aligned and the per-lane 128-bit reads conflict-free.
 constexpr int BOOLCODE_T = 64;            // tokens per lane per chunk
 constexpr int BOOLCODE_STRIDE = 144;      // bytes per lane region
-constexpr int BOOLCODE_SMEM = 4 * 32 * BOOLCODE_STRIDE + 32 * 40 + 32 * 8 * 2;  // 2 token + 2 event buffers, closing events, bases/totals
+constexpr int BOOLCODE_SMEM = 4 * 32 * BOOLCODE_STRIDE + 32 * 40 + 32 * 8 * 2;  // per warp pair: 2 token + 2 event buffers, closing events, bases/totals
+constexpr int BOOLCODE_MAX_PAIRS = 4;     // warp pairs (x 32 partitions) a block may carry; 1 measured best (packing slows the chains)
 
-__global__ void __launch_bounds__(64) boolcode_kernel(const BoolCodeParams P) {
+__global__ void __launch_bounds__(256) boolcode_kernel(const BoolCodeParams P) {
   // SIMT across partitions: a block codes 32 partitions (slots 32b .. 32b+31 of the longest-first order), one per lane, with
   // two warps pipelined over 64-token chunks through shared memory:
   //   warp 0 (range warp): cp.async streams each lane's tokens in; every lane runs the range recurrence of ITS partition
@@ -246,14 +247,19 @@ __global__ void __launch_bounds__(64) boolcode_kernel(const BoolCodeParams P) {
   // Deferring Flush by up to four tokens is exact: value is a big-number accumulator whose carries ripple inside the
   // 64-bit register exactly as Flush would have applied them to the held-back byte.
   constexpr int T = BOOLCODE_T, STRIDE = BOOLCODE_STRIDE;
-  extern __shared__ __align__(16) unsigned char s_dyn[];
+  // A block carries blockDim / 64 such warp pairs (32 partitions each), every pair on its own named barrier: the pairs of a
+  // block land on different SM sub-partitions, so packing four of them halves the SMs the coder takes from the waves twice.
+  extern __shared__ __align__(16) unsigned char s_dyn_all[];
+  const int pair = threadIdx.x >> 6;
+  unsigned char* s_dyn = s_dyn_all + (size_t)pair * BOOLCODE_SMEM;
+  auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); };
   unsigned char* s_tok = s_dyn;                                   // [2][32][STRIDE]
   unsigned char* s_ev = s_dyn + 2 * 32 * STRIDE;                  // [2][32][STRIDE]
   uint16_t* s_fin = reinterpret_cast<uint16_t*>(s_dyn + 4 * 32 * STRIDE);  // [32][20]
   unsigned long long* s_base = reinterpret_cast<unsigned long long*>(s_dyn + 4 * 32 * STRIDE + 32 * 40);  // [32] token offset
   unsigned long long* s_total = s_base + 32;                                                                // [32] token count
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int slot = blockIdx.x * 32 + lane;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 1;
+  const int slot = (blockIdx.x * (blockDim.x >> 6) + pair) * 32 + lane;
   const int img = slot < P.n_images ? (P.order ? P.order[slot] : slot) : -1;
   const unsigned long long total = img >= 0 ? P.img_total[img] : 0ull;
   if (warp == 0) { s_base[lane] = img >= 0 ? P.img_base[img] : 0ull; s_total[lane] = total; }
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(64) boolcode_kernel(const BoolCodeParams P) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, max_total, o); max_total = v > max_total ? v : max_total; }
   const long long n_chunks = (long long)((max_total + T - 1) / T);
-  __syncthreads();
+  pair_sync();
   // ---- range warp state: R = range + 1 in [128, 255]
   int R = 255;
   auto step = [&](uint32_t tok, bool valid) -> uint32_t {  // one PutBit on the range side; returns the event for the byte side
@@ -387,7 +393,7 @@ __global__ void __launch_bounds__(64) boolcode_kernel(const BoolCodeParams P) {
         fold4(cur.z, cur.w);
       }
     }
-    __syncthreads();
+    pair_sync();
   }
   if (warp == 1 && img >= 0) {
     const int n_fin = 9 - nb_bits;  // the closing bits were prepared by the range warp in the last pipeline step

@@ -1118,12 +1118,14 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       // forces the same L1/shared split as the mode-search CTAs (a kernel with a small footprint gets a different split from
       // the driver and cannot share an SM with them at all -- it then piles onto the few free SMs and stalls both: 540 ms vs
       // 140 ms), and it gives each block an SM of its own, where the tight coder loops keep the instruction cache (216 ms
-      // vs 280 ms beside mode-search warps).  Cost to the waves: 8 of 148 SMs while the coder runs.
+      // vs 280 ms beside mode-search warps).  Cost to the waves: 8 of 148 SMs while the coder runs (packing more warp pairs
+      // per block, WGPU_CODER_PAIRS, frees SMs but slows the chains: 2639 vs 2790 Mpix/s end to end at 4 pairs).
       static size_t coder_smem = 0;
+      static const int coder_pairs = std::min((int)wg::BOOLCODE_MAX_PAIRS, std::max(1, getenv_int("WGPU_CODER_PAIRS", 1)));
       if (!coder_smem) {
         coder_smem = 200 * 1024;
         if (getenv("WGPU_CODER_DYNSMEM")) coder_smem = (size_t)atoi(getenv("WGPU_CODER_DYNSMEM"));  // experiment knob
-        coder_smem = std::max(coder_smem, (size_t)wg::BOOLCODE_SMEM);
+        coder_smem = std::max(coder_smem, (size_t)wg::BOOLCODE_SMEM * wg::BOOLCODE_MAX_PAIRS);
         CK(cudaFuncSetAttribute(wg::boolcode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coder_smem));
       }
       int* order = reinterpret_cast<int*>(bases + 2 * n);  // longest first, so that the lanes of a warp finish together
@@ -1132,7 +1134,8 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       CK(cudaMemcpyAsync(ctx->img_base.as<unsigned long long>() + 2 * n, order, n * 4, cudaMemcpyHostToDevice, ctx->stream));
       ctx->xfer_h2d += (uint64_t)(n * 4);
       B.order = reinterpret_cast<const int*>(ctx->img_base.as<unsigned long long>() + 2 * n);
-      wg::boolcode_kernel<<<(unsigned)((n + 31) / 32), 64, coder_smem, ctx->stream>>>(B);
+      const int per_block = 32 * coder_pairs;
+      wg::boolcode_kernel<<<(unsigned)((n + per_block - 1) / per_block), 64 * coder_pairs, coder_smem, ctx->stream>>>(B);
     }
     ctx->launches++;
     CK(cudaGetLastError());
