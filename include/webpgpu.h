@@ -12,6 +12,7 @@
  *                            (called from encodeLossyWithAlpha, encode.go:472-546) + writeRIFFSimple encode.go:968
  *   wgpu_decode_batch        lossy.DecodeFrame (+ buildYCbCr / buildNRGBA)    internal/lossy/decode.go:209, webp.go:351,379
  *   wgpu_import_rgba         (*VP8Encoder).importImage                       internal/lossy/encode.go:671
+ *   wgpu_cleanup_transparent cleanupTransparentAreaLossy                      encode.go:788
  *   wgpu_upsample_nrgba      buildNRGBA / dsp.UpsampleLinePairNRGBA           webp.go:379, internal/dsp/upsample.go:130
  *   wgpu_plane_metrics       dsp.SSE / SSIMGet / SSIMGetClipped / PSNRFromSSE internal/dsp/ssim.go:116-181
  *   wgpu_dsp_*_batch         the per-block operator surface                  internal/dsp/dsp.go:12-37,
@@ -139,6 +140,10 @@ int wgpu_dec_device(wgpu_ctx* ctx, int want_nrgba);
 int wgpu_dec_fetch(wgpu_ctx* ctx, uint8_t* y, uint8_t* u, uint8_t* v, size_t y_plane_stride, size_t uv_plane_stride,
                    uint8_t* nrgba, size_t nrgba_image_stride);
 
+/* cleanupTransparentAreaLossy (encode.go:788-890) on n NRGBA images (non-premultiplied, 4 bytes per pixel): colours under
+ * fully transparent pixels are smoothed / flattened per 8x8 block before the lossy encode of an image with alpha. */
+int wgpu_cleanup_transparent(wgpu_ctx* ctx, const uint8_t* nrgba, int n, int width, int height, int stride, size_t image_stride,
+                             uint8_t* out /* [n][height][4 * width] */);
 /* wgpu_import_rgba: has_alpha bit 0 = alpha-weighted chroma, bits 8..16 = dithering amplitude (0 = fixed rounding). */
 /* ---- stage-level entry points (host buffers in/out) ------------------------------------ */
 int wgpu_import_rgba(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int height, int stride,

@@ -159,6 +159,60 @@ int orc_decode(const uint8_t* data, long len, int filter, uint8_t* y, uint8_t* u
   return rc;
 }
 
+// cleanupTransparentAreaLossy on an NRGBA image, in place (encode.go:788-890): 8x8 blocks; transparent pixels of a partly
+// transparent block take the average colour of its opaque pixels (integer division), fully transparent blocks of a block
+// row are flattened to the colour of the first pixel of their run; right / bottom remainders are smoothened only.
+static bool orc_smoothen_block(uint8_t* px, int stride, int bx, int by, int w, int h) {
+  int cnt = 0, sr = 0, sg = 0, sb = 0;
+  for (int y = by; y < by + h; ++y)
+    for (int x = bx; x < bx + w; ++x) {
+      const uint8_t* c = px + (size_t)y * stride + 4 * x;
+      if (c[3] != 0) { cnt++; sr += c[0]; sg += c[1]; sb += c[2]; }
+    }
+  if (cnt == 0) return true;
+  if (cnt < w * h) {
+    const uint8_t ar = (uint8_t)(sr / cnt), ag = (uint8_t)(sg / cnt), ab = (uint8_t)(sb / cnt);
+    for (int y = by; y < by + h; ++y)
+      for (int x = bx; x < bx + w; ++x) {
+        uint8_t* c = px + (size_t)y * stride + 4 * x;
+        if (c[3] == 0) { c[0] = ar; c[1] = ag; c[2] = ab; }
+      }
+  }
+  return false;
+}
+void orc_cleanup_transparent(uint8_t* px, int stride, int width, int height) {
+  const int B = 8;
+  for (int by = 0; by + B <= height; by += B) {
+    uint8_t cr = 0, cg = 0, cb = 0;
+    bool need_reset = true;
+    for (int bx = 0; bx + B <= width; bx += B) {
+      if (orc_smoothen_block(px, stride, bx, by, B, B)) {
+        if (need_reset) {
+          const uint8_t* c = px + (size_t)by * stride + 4 * bx;
+          cr = c[0]; cg = c[1]; cb = c[2];
+          need_reset = false;
+        }
+        for (int y = by; y < by + B; ++y)
+          for (int x = bx; x < bx + B; ++x) {
+            uint8_t* c = px + (size_t)y * stride + 4 * x;
+            c[0] = cr; c[1] = cg; c[2] = cb; c[3] = 0;
+          }
+      } else {
+        need_reset = true;
+      }
+    }
+    const int rem = width % B;
+    if (rem > 0) orc_smoothen_block(px, stride, width - rem, by, rem, B);
+  }
+  const int rem_h = height % B;
+  if (rem_h > 0) {
+    const int by = height - rem_h;
+    for (int bx = 0; bx + B <= width; bx += B) orc_smoothen_block(px, stride, bx, by, B, rem_h);
+    const int rem = width % B;
+    if (rem > 0) orc_smoothen_block(px, stride, width - rem, by, rem, rem_h);
+  }
+}
+
 // ---- stage-level ---------------------------------------------------------------------------
 // RGBA -> padded YUV420 planes (encode.go:671 importImage).
 void orc_import_rgba(const uint8_t* rgba, int stride, int w, int h, int has_alpha, uint8_t* y, uint8_t* u, uint8_t* v) {

@@ -131,6 +131,14 @@ def import_rgba(rgba, has_alpha=False, dither_amp=0):
     return y, u, v
 
 
+def cleanup_transparent(nrgba):
+    """cleanupTransparentAreaLossy (encode.go:788) on a copy of an NRGBA image [h][w][4]."""
+    out = np.ascontiguousarray(nrgba, dtype=np.uint8).copy()
+    h, w = out.shape[:2]
+    lib().orc_cleanup_transparent(_p(out), C.c_int(out.strides[0]), w, h)
+    return out
+
+
 def build_nrgba(w, h, y, u, v, alpha=None):
     out = np.zeros((h, w, 4), np.uint8)
     lib().orc_build_nrgba(w, h, _p(y), C.c_int(y.strides[0]), _p(u), _p(v), C.c_int(u.strides[0]),

@@ -106,3 +106,16 @@ def test_trellis_and_token_cost(oracle, gpu_ctx, dc_q, ac_q, first, ctx_type, la
     ecost = np.zeros(n, np.int32)
     oracle.lib().orc_token_cost_batch(n, _p(exp), _p(enz), ctx_type, _p(c0), first, _p(ecost))
     assert np.array_equal(dsp.TokenCostForCoeffsBatch(exp, enz, ctx_type, c0, first, gpu_ctx), ecost)
+
+
+@pytest.mark.parametrize("w,h", [(64, 48), (100, 70), (37, 21), (7, 5), (130, 71), (8, 8), (1536, 1024)])
+def test_cleanup_transparent_area(oracle, gpu_ctx, w, h):
+    """cleanupTransparentAreaLossy (encode.go:788-890): smoothing of partly transparent 8x8 blocks, flattening of runs of fully
+    transparent ones, remainders smoothened only -- a batch of images against the oracle, bit-exact."""
+    from test_oracle import alpha_test_image
+    imgs = np.stack([alpha_test_image(oracle, w, h, s) for s in (1, 2, 3)])
+    imgs[2, ..., 3] = 255  # one fully opaque image: untouched
+    out = dsp.CleanupTransparentArea(imgs, gpu_ctx)
+    for k in range(3):
+        assert np.array_equal(out[k], oracle.cleanup_transparent(imgs[k]))
+    assert np.array_equal(out[2], imgs[2])

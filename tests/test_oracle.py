@@ -142,3 +142,59 @@ def test_host_serialisers_reproduce_oracle_bytes(oracle):
         n = L.hostcheck_serialize(img.ctypes.data_as(C.c_void_p), C.c_int(img.strides[0]), w, h, C.byref(cfg), out.ctypes.data_as(C.c_void_p),
                                   C.c_long(out.size), 1, C.byref(same), C.byref(ms))
         assert n > 0 and same.value == 1, (w, h, idx, kw)
+
+
+def _cleanup_numpy(img):
+    """cleanupTransparentAreaLossy (encode.go:788-890) restated once more in plain numpy, to cross-check the C++ oracle."""
+    px = img.copy()
+    h, w = px.shape[:2]
+
+    def smoothen(bx, by, bw, bh):
+        blk = px[by:by + bh, bx:bx + bw]
+        opaque = blk[..., 3] != 0
+        cnt = int(opaque.sum())
+        if cnt == 0:
+            return True
+        if cnt < bw * bh:
+            avg = [int(blk[..., c][opaque].astype(np.int64).sum()) // cnt for c in range(3)]
+            for c in range(3):
+                blk[..., c][~opaque] = avg[c]
+        return False
+    for by in range(0, h - 7, 8):
+        carry, need_reset = None, True
+        for bx in range(0, w - 7, 8):
+            if smoothen(bx, by, 8, 8):
+                if need_reset:
+                    carry = px[by, bx, :3].copy()
+                    need_reset = False
+                px[by:by + 8, bx:bx + 8, :3] = carry
+                px[by:by + 8, bx:bx + 8, 3] = 0
+            else:
+                need_reset = True
+        if w % 8:
+            smoothen(w - w % 8, by, w % 8, 8)
+    if h % 8:
+        by = h - h % 8
+        for bx in range(0, w - 7, 8):
+            smoothen(bx, by, 8, h % 8)
+        if w % 8:
+            smoothen(w - w % 8, by, w % 8, h % 8)
+    return px
+
+
+def alpha_test_image(oracle, w, h, seed):
+    rng = np.random.RandomState(seed)
+    img = oracle.synth_image(w, h, seed % 9)
+    a = rng.randint(0, 256, (h, w)).astype(np.uint8)
+    a[rng.rand(h, w) < 0.4] = 0
+    for _ in range(6):  # fully transparent rectangles so that runs of transparent 8x8 blocks occur
+        x0, y0 = rng.randint(0, max(1, w - 8)), rng.randint(0, max(1, h - 8))
+        a[y0:y0 + rng.randint(8, 40), x0:x0 + rng.randint(8, 60)] = 0
+    img[..., 3] = a
+    return img
+
+
+@pytest.mark.parametrize("w,h,seed", [(64, 48, 1), (100, 70, 2), (37, 21, 3), (7, 5, 4), (130, 71, 5), (8, 8, 6)])
+def test_cleanup_transparent_oracle(oracle, w, h, seed):
+    img = alpha_test_image(oracle, w, h, seed)
+    assert np.array_equal(oracle.cleanup_transparent(img), _cleanup_numpy(img))

@@ -114,6 +114,68 @@ __global__ void __launch_bounds__(256) metrics_reduce_kernel(const unsigned long
   if (threadIdx.x == 0) { sse[img] = s_s[0]; ssim[img] = s_q[0]; }
 }
 
+// ---- cleanupTransparentAreaLossy (encode.go:788-890) on NRGBA images, in place.  One CTA per (image, row of 8x8 blocks), a
+// warp per block (two pixels per lane): transparent pixels of a partly transparent block take the average colour of its
+// opaque pixels; fully transparent blocks are flattened to the colour of the first pixel of their run in the block row
+// (the reference carries it from block to block: a run starts after any block that is not fully transparent).  The right
+// remainder and the bottom remainder rows are smoothened only.
+struct CleanupParams {
+  uint8_t* px;           // [n][height][stride] NRGBA
+  size_t image_stride;
+  int stride, n, width, height;
+};
+__global__ void __launch_bounds__(128) cleanup_transparent_kernel(const CleanupParams P) {
+  extern __shared__ uint8_t s_transp[];  // [full blocks of the row] 1 = fully transparent
+  const int rows_full = P.height / 8, rem_h = P.height % 8;
+  const int block_rows = rows_full + (rem_h ? 1 : 0);
+  const int img = blockIdx.x / block_rows, brow = blockIdx.x % block_rows;
+  const int by = brow * 8, bh = brow < rows_full ? 8 : rem_h;
+  const int nfull = P.width / 8, rem_w = P.width % 8, nblk = nfull + (rem_w ? 1 : 0);
+  uint8_t* base = P.px + (size_t)img * P.image_stride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = warp; b < nblk; b += 4) {
+    const int bx = b * 8, bw = b < nfull ? 8 : rem_w;
+    int cnt = 0, sr = 0, sg = 0, sb = 0;
+    uint32_t pix[2];
+    bool in[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = lane + 32 * k, x = i & 7, y = i >> 3;
+      in[k] = x < bw && y < bh;
+      pix[k] = in[k] ? *reinterpret_cast<const uint32_t*>(base + (size_t)(by + y) * P.stride + 4 * (bx + x)) : 0u;
+      if (in[k] && (pix[k] >> 24) != 0) { cnt++; sr += pix[k] & 0xff; sg += (pix[k] >> 8) & 0xff; sb += (pix[k] >> 16) & 0xff; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o); sr += __shfl_xor_sync(0xffffffffu, sr, o);
+      sg += __shfl_xor_sync(0xffffffffu, sg, o); sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    if (cnt > 0 && cnt < bw * bh) {
+      const uint32_t avg = (uint32_t)(sr / cnt) | ((uint32_t)(sg / cnt) << 8) | ((uint32_t)(sb / cnt) << 16);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = lane + 32 * k, x = i & 7, y = i >> 3;
+        if (in[k] && (pix[k] >> 24) == 0) *reinterpret_cast<uint32_t*>(base + (size_t)(by + y) * P.stride + 4 * (bx + x)) = avg;
+      }
+    }
+    if (lane == 0 && b < nfull) s_transp[b] = (cnt == 0);
+  }
+  __syncthreads();
+  if (bh < 8) return;  // bottom remainder: smoothing only
+  for (int b = warp; b < nfull; b += 4) {
+    if (!s_transp[b]) continue;
+    int start = b;
+    while (start > 0 && s_transp[start - 1]) --start;
+    const uint32_t c = *reinterpret_cast<const uint32_t*>(base + (size_t)by * P.stride + 4 * (start * 8)) & 0x00ffffffu;  // untouched so far
+    // (that pixel is transparent already, so the warp flattening the run's first block rewrites it with the same value)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = lane + 32 * k, x = i & 7, y = i >> 3;
+      *reinterpret_cast<uint32_t*>(base + (size_t)(by + y) * P.stride + 4 * (b * 8 + x)) = c;
+    }
+  }
+}
+
 // ---- batched dsp surface: one thread per 4x4 block, dense 16-byte tiles ----------------------------------
 __device__ __forceinline__ void load16u8(const uint8_t* p, int* d) {
   const uint4 q = *reinterpret_cast<const uint4*>(p);

@@ -1553,6 +1553,26 @@ int wgpu_import_rgba(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int h
   return WGPU_OK;
 }
 
+int wgpu_cleanup_transparent(wgpu_ctx* ctx, const uint8_t* nrgba, int n, int width, int height, int stride, size_t image_stride, uint8_t* out) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  if (!out) { std::lock_guard<std::mutex> lk(ctx->mu); FAIL(WGPU_ERR_INVALID, "wgpu_cleanup_transparent: nil output"); }
+  int rc = wgpu_enc_upload(ctx, nrgba, n, width, height, stride, image_stride);  // rows land 16-byte aligned in ctx->rgba
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->e_uploaded = false;  // the staged pixels are about to change: not an encoder input any more
+  wg::CleanupParams P;
+  P.px = ctx->rgba.as<uint8_t>(); P.stride = ctx->e_rgba_stride; P.image_stride = (size_t)height * ctx->e_rgba_stride;
+  P.n = n; P.width = width; P.height = height;
+  const int block_rows = height / 8 + (height % 8 ? 1 : 0);
+  wg::cleanup_transparent_kernel<<<(unsigned)(n * block_rows), 128, (size_t)(width / 8 + 1), ctx->stream>>>(P);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpy2DAsync(out, (size_t)4 * width, ctx->rgba.p, ctx->e_rgba_stride, (size_t)4 * width, (size_t)n * height, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->xfer_d2h += (uint64_t)4 * width * height * n;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WGPU_OK;
+}
+
 int wgpu_upsample_nrgba(wgpu_ctx* ctx, int n, int width, int height, const uint8_t* y, int y_stride, const uint8_t* u, const uint8_t* v,
                         int uv_stride, size_t y_plane_stride, size_t uv_plane_stride, const uint8_t* alpha, uint8_t* nrgba) {
   if (!ctx) return WGPU_ERR_INVALID;

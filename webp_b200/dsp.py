@@ -113,6 +113,14 @@ def ImportRGBA(rgba, has_alpha=False, ctx=None, dither_amp=0):
     return y, u, v
 
 
+def CleanupTransparentArea(nrgba, ctx=None):
+    """cleanupTransparentAreaLossy (encode.go:788): uint8 NRGBA [n][h][w][4] -> same shape, colours under alpha == 0 smoothed per 8x8 block."""
+    ctx = _ctx(ctx); a = _c(nrgba, np.uint8); n, h, w = a.shape[:3]
+    out = np.empty_like(a)
+    ctx.check(native.lib().wgpu_cleanup_transparent(ctx.handle, a.ctypes.data, n, w, h, w * 4, w * h * 4, out.ctypes.data))
+    return out
+
+
 def UpsampleNRGBA(y, u, v, width, height, alpha=None, ctx=None):
     """buildNRGBA (webp.go:379) / dsp.UpsampleLinePairNRGBA (internal/dsp/upsample.go:130): planes [n][H][S] -> NRGBA."""
     ctx = _ctx(ctx); y = _c(y, np.uint8); u = _c(u, np.uint8); v = _c(v, np.uint8)

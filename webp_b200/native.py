@@ -94,6 +94,7 @@ def lib():
         L.wgpu_dsp_quantize_batch.argtypes = [vp, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i16p, i32p]
         L.wgpu_dsp_trellis_batch.argtypes = [vp, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i16p, i32p]
         L.wgpu_dsp_token_cost_batch.argtypes = [vp, C.c_int, i16p, i32p, C.c_int, i32p, C.c_int, i32p]
+        L.wgpu_cleanup_transparent.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, sz, u8p]
         L.wgpu_timer_begin.argtypes = [vp]
         L.wgpu_timer_end.argtypes = [vp, C.POINTER(C.c_float)]
         L.wgpu_launch_count.argtypes = [vp]
