@@ -125,7 +125,7 @@ def main():
     ap.add_argument("--value-contexts", type=int, default=2, help="contexts whose device-resident steps run side by side in the `value` leg")
     ap.add_argument("--gpu-slots", type=int, default=2, help="how many contexts may have their mode-search waves on the GPU at once")
     ap.add_argument("--finish-slots", type=int, default=0, help="how many contexts may be in their finish stage at once (default: 3 when the token partitions are coded on the GPU, else 1)")
-    ap.add_argument("--decode-workers", type=int, default=0, help="contexts per GPU for the decode e2e leg (default: 4 with the GPU macroblock parser, whose ~0.3 s latency per batch they hide; else the encode workers)")
+    ap.add_argument("--decode-workers", type=int, default=0, help="contexts per GPU for the decode e2e leg (default: 8 with the GPU macroblock parser, whose ~0.35 s latency per batch they hide; else the encode workers)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads per context (default: cores / ranks on this node)")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -337,7 +337,7 @@ def main():
         # the encode staging of the extra contexts is no longer needed: give the pinned memory back before the decode buffers
         for wk in workers[1:]:
             wk.free()
-        n_dec = args.decode_workers or (4 if device_parser else len(workers))
+        n_dec = args.decode_workers or (8 if device_parser else len(workers))
         dctxs = [wk.ctx for wk in workers] + [native.Context(local, host_threads=host_threads) for _ in range(max(0, n_dec - len(workers)))]
         dctxs = dctxs[:max(1, n_dec)]
         dec_bufs = [h_rgba] + [L.wgpu_host_alloc(c.handle, in_bytes) for c in dctxs[1:]]
