@@ -194,14 +194,23 @@ def main():
             """wgpu_encode_batch spelled as its three public stages so that two workers pipeline: one batch is in its GPU
             stage (H2D + kernels) while the previous one is in its host stage (D2H + token/bool coding)."""
             h = self.ctx.handle
+            t = [time.perf_counter()]
             with upload_stage:  # H2D of this batch rides under the kernels of the batch before it
+                t.append(time.perf_counter())
                 self.ctx.check(L.wgpu_enc_upload(h, self.h_in, n, W, H, W * 4, W * H * 4))
                 self.ctx.check(L.wgpu_sync(h))
+            t.append(time.perf_counter())
             with gpu_stage:
+                t.append(time.perf_counter())
                 self.ctx.check(L.wgpu_enc_device(h, C.byref(opt)))
                 self.ctx.check(L.wgpu_sync(h))
+            t.append(time.perf_counter())
             with host_stage:
+                t.append(time.perf_counter())
                 self.ctx.check(L.wgpu_enc_finish(h, self.h_out, cap, self.sizes.ctypes.data))
+            t.append(time.perf_counter())
+            if os.environ.get("BENCH_TRACE"):  # wait-upload, upload, wait-gpu, device, wait-finish, finish (ms)
+                sys.stderr.write("[bench] stages ms: " + " ".join("%.0f" % ((b - a) * 1e3) for a, b in zip(t, t[1:])) + "\n")
 
         def free(self):
             if self.h_in:
