@@ -369,6 +369,30 @@ def test_plane_metrics(oracle, gpu_ctx, w, h):
         assert dsp.PSNRFromSSE(sse[i], w * h) == oracle.lib().orc_psnr_from_sse(int(sse[i]), w * h)
 
 
+def test_large_batch_takes_gpu_coder_and_parser(oracle, gpu_ctx, monkeypatch):
+    """40 images in one call: the library's own choice of routes (>= 32 images: token partitions coded and macroblocks parsed
+    on the GPU; 40 = one full warp of partitions + a partial one), bytes and decoded planes against the oracle."""
+    monkeypatch.delenv("WGPU_DEVICE_CODER", raising=False)
+    monkeypatch.delenv("WGPU_DEVICE_PARSER", raising=False)
+    w, h = 96, 80
+    imgs = np.stack([oracle.synth_image(w, h, i % 12) for i in range(40)])
+    imgs[5] = 255  # a flat image: all macroblocks skipped, an empty token partition
+    for kw in ({}, dict(Method=2, Quality=60)):
+        o = _opts(**kw)
+        files = webp_b200.EncodeBatch(imgs, o, gpu_ctx)
+        exp = {}
+        for k in range(40):
+            key = imgs[k].tobytes()
+            if key not in exp:
+                exp[key] = oracle.encode(imgs[k], _ocfg(oracle, o))
+            assert files[k] == exp[key], "image %d" % k
+        _, _, y, u, v, rgba = webp_b200.webp.decode_padded(files, nrgba=True, ctx=gpu_ctx)
+        for k in (0, 5, 31, 32, 39):
+            _, _, ey, eu, ev = oracle.decode(files[k])
+            assert np.array_equal(y[k], ey) and np.array_equal(u[k], eu) and np.array_equal(v[k], ev)
+            assert np.array_equal(rgba[k], oracle.build_nrgba(w, h, ey, eu, ev))
+
+
 def test_round_trip_at_full_size(oracle, gpu_ctx, parser_route):
     """BASELINE configs[1]/[2] shape: 1536x1024 q75 m4 -> own decoder -> libwebp-identical planes; size-independent
     properties: GPU decode of GPU bytes == encoder's own reconstruction (filter off), PSNR >= 30 dB."""
