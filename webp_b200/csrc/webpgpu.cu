@@ -97,6 +97,10 @@ struct wgpu_ctx {
   DevBuf d_coeffs, d_meta, d_ftype, dy, du, dv, d_nrgba, d_alpha, d_streams, d_hdrs, d_perr, t_bmodes;
   PinBuf hd_streams, hd_hdrs, hd_perr;
   bool d_dev_parsed = false;
+  // CUDA graph of the decoder's device step (444 wave launches of a few microseconds each are launch-bound otherwise)
+  cudaGraphExec_t d_graph = nullptr;
+  uint64_t d_graph_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t d_graph_launches = 0;
   PinBuf hd_coeffs, hd_meta, hd_ftype, hd_planes, hd_nrgba;
   int d_n = 0, d_w = 0, d_h = 0, d_mbw = 0, d_mbh = 0;
   bool d_ready = false, d_any_filter = false, d_has_nrgba = false;
@@ -232,6 +236,7 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_hdr) cudaEventDestroy(ctx->ev_hdr);
+  if (ctx->d_graph) cudaGraphExecDestroy(ctx->d_graph);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1491,12 +1496,48 @@ int wgpu_dec_device(wgpu_ctx* ctx, int want_nrgba) {
   P.y_plane = nmb * 256; P.uv_plane = nmb * 64; P.filter_type = ctx->d_ftype.as<uint8_t>();
   P.n_images = n; P.mb_w = ctx->d_mbw; P.mb_h = ctx->d_mbh;
   int rc;
-  if ((rc = dec_launch_recon(ctx, P))) return rc;
-  if (ctx->d_any_filter && (rc = dec_launch_filter(ctx, P))) return rc;
-  if (want_nrgba) {
-    RESERVE(ctx->d_nrgba, (size_t)n * ctx->d_w * ctx->d_h * 4);
-    if ((rc = launch_upsample(ctx, n, ctx->d_w, ctx->d_h, P.y, ctx->d_mbw * 16, P.u, P.v, ctx->d_mbw * 8, P.y_plane, P.uv_plane, nullptr,
-                              ctx->d_nrgba.as<uint8_t>()))) return rc;
+  if (want_nrgba) RESERVE(ctx->d_nrgba, (size_t)n * ctx->d_w * ctx->d_h * 4);
+  // The device step is 2 x (mbW + 2 mbH - 2) wave launches of 3-25 us each plus the upsampler: launch-bound.  It is captured
+  // once per (shape, buffers, options) into a CUDA graph and replayed; any change of the key re-captures.
+  const uint64_t key[8] = {(uint64_t)n | ((uint64_t)ctx->d_mbw << 32), (uint64_t)ctx->d_mbh | ((uint64_t)ctx->d_w << 20) | ((uint64_t)ctx->d_h << 40),
+                           (uint64_t)(ctx->d_any_filter ? 1 : 0) | (want_nrgba ? 2 : 0), (uint64_t)(uintptr_t)ctx->d_coeffs.p,
+                           (uint64_t)(uintptr_t)ctx->d_meta.p, (uint64_t)(uintptr_t)ctx->dy.p ^ ((uint64_t)(uintptr_t)ctx->du.p << 1) ^ ((uint64_t)(uintptr_t)ctx->dv.p << 2),
+                           (uint64_t)(uintptr_t)ctx->d_nrgba.p, (uint64_t)(uintptr_t)ctx->d_ftype.p};
+  auto launch_all = [&]() -> int {
+    int r;
+    if ((r = dec_launch_recon(ctx, P))) return r;
+    if (ctx->d_any_filter && (r = dec_launch_filter(ctx, P))) return r;
+    if (want_nrgba && (r = launch_upsample(ctx, n, ctx->d_w, ctx->d_h, P.y, ctx->d_mbw * 16, P.u, P.v, ctx->d_mbw * 8, P.y_plane, P.uv_plane, nullptr,
+                                           ctx->d_nrgba.as<uint8_t>()))) return r;
+    return WGPU_OK;
+  };
+  static const bool use_graph = getenv_int("WGPU_DEC_GRAPH", 1) != 0;
+  if (!use_graph) {
+    if ((rc = launch_all())) return rc;
+  } else {
+    if (!ctx->d_graph || memcmp(key, ctx->d_graph_key, sizeof(key)) != 0) {
+      if (ctx->d_graph) { cudaGraphExecDestroy(ctx->d_graph); ctx->d_graph = nullptr; }
+      const uint64_t launches_before = ctx->launches;
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      rc = launch_all();
+      cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+      if (rc || ce != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        if (rc) return rc;
+        ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce);
+        return WGPU_ERR_CUDA;
+      }
+      ce = cudaGraphInstantiate(&ctx->d_graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) { ctx->d_graph = nullptr; ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return WGPU_ERR_CUDA; }
+      memcpy(ctx->d_graph_key, key, sizeof(key));
+      ctx->d_graph_launches = ctx->launches - launches_before;
+      ctx->launches = launches_before;  // captured, not launched
+    }
+    CK(cudaGraphLaunch(ctx->d_graph, ctx->stream));
+    ctx->launches += ctx->d_graph_launches;  // kernels the replay runs
   }
   ctx->d_has_nrgba = want_nrgba != 0;
   return WGPU_OK;
