@@ -53,3 +53,10 @@ func PlaneMetricsCUDA(ctx unsafe.Pointer, n int, a, b []byte, w, h, stride, plan
 	return int(C.wgpu_plane_metrics((*C.wgpu_ctx)(ctx), C.int(n), (*C.uint8_t)(&a[0]), (*C.uint8_t)(&b[0]), C.int(w), C.int(h), C.int(stride),
 		C.size_t(planeStride), (*C.uint64_t)(&sse[0]), (*C.double)(&ssim[0])))
 }
+
+// CleanupTransparentAreaCUDA: cleanupTransparentAreaLossy (encode.go:788) over n NRGBA images of one size; webp.Encode calls
+// it (when !opts.Exact and the image has alpha) before handing the pixels to lossy.NewEncoder.
+func CleanupTransparentAreaCUDA(ctx unsafe.Pointer, nrgba []byte, n, w, h, stride, imageStride int, out []byte) int {
+	return int(C.wgpu_cleanup_transparent((*C.wgpu_ctx)(ctx), (*C.uint8_t)(&nrgba[0]), C.int(n), C.int(w), C.int(h), C.int(stride),
+		C.size_t(imageStride), (*C.uint8_t)(&out[0])))
+}
