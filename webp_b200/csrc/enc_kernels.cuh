@@ -1139,6 +1139,19 @@ __global__ void __maxnreg__(NREG) encode_wave_kernel_nr(const EncKernelParams P,
   encode_mb_group<G, false, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
 }
 
+// Experiment (WGPU_ENC_VARIANT=5/6): cost tables read through L1 from HBM instead of being staged into every CTA's shared
+// memory -- 19 KB less per CTA, which makes room for a fourth CTA (64 instead of 48 macroblocks per SM) under a 128-register cap.
+template <int G, int WARPS, int NREG>
+__global__ void __maxnreg__(NREG) encode_wave_kernel_gt(const EncKernelParams P, int wave) {
+  constexpr int MPW = 32 / G;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  MBShared* s_mb = reinterpret_cast<MBShared*>(s_dyn);
+  CostTabs T;
+  T.lc = P.lc; T.eob = P.eob; T.lfc = P.lfc;
+  const int warp = threadIdx.x >> 5;
+  encode_mb_group<G, false, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, P.i4_costs);
+}
+
 // Method < 3 (the reference's non-RD decisions, serial-path semantics): same wavefront, lighter body.
 template <int G, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) encode_fast_wave_kernel(const EncKernelParams P, int wave) {
