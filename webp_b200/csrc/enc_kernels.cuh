@@ -227,7 +227,7 @@ template <bool PERSIST, class Tp>
 __device__ __forceinline__ Tp ldn(const Tp* p) { return PERSIST ? __ldcg(p) : *p; }
 
 // The mode search of MPW = 32/G macroblocks by one warp: macroblock `task_base + lane/G` of wave `wave`.
-template <int G, bool PERSIST, bool FAST, bool SERIAL = false>
+template <int G, bool PERSIST, bool FAST, bool SERIAL = false, bool SYNC = false>
 __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wave, long long task_base, MBShared* s_mb_warp,
                                                 const CostTabs& T_launch, const uint16_t* s_i4cost) {
   const int lane = threadIdx.x & 31;
@@ -391,6 +391,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
     __syncwarp();
     const int dc_ctx = min(top_nz_dc + left_nz_dc, 2);
     for (int mode = 0; mode < 4; ++mode) {
+      if constexpr (SYNC) __syncthreads();  // experiment: the warps of an SM walk the code together (shared instruction fetch)
       const bool allowed = active && !((mode == 2 && my == 0) || (mode == 3 && mx == 0) || (mode == 1 && (mx == 0 || my == 0)));
       if (allowed) pred_square_coop<G>(gl, check_mode(mx, my, mode), S.out2, Y_OFF, 16);
       __syncwarp();
@@ -512,6 +513,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
     uint32_t nzmask = 0;   // bit b: block b has nz > 0
     uint32_t modes_lo = 0, modes_hi = 0;  // 16 x 4-bit modes
     for (int b = 0; b < 16; ++b) {
+      if constexpr (SYNC) __syncthreads();
       const int bx = b & 3, by = b >> 2;
       const int off = Y_OFF + by * 4 * BPS + bx * 4;
       auto get_mode = [&](int k) -> int { return (k < 8) ? (modes_lo >> (4 * k)) & 15 : (modes_hi >> (4 * (k - 8))) & 15; };
@@ -767,6 +769,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
         reinterpret_cast<uint32_t*>(S.out2 + U_OFF)[i] = reinterpret_cast<const uint32_t*>(S.out + U_OFF)[i];
     __syncwarp();
     for (int mode = 0; mode < 4; ++mode) {
+      if constexpr (SYNC) __syncthreads();
       const bool allowed = active && !((mode == 2 && my == 0) || (mode == 3 && mx == 0) || (mode == 1 && (mx == 0 || my == 0)));
       if (allowed) {
         const int am = check_mode(mx, my, mode);
@@ -1150,6 +1153,16 @@ __global__ void __maxnreg__(NREG) encode_wave_kernel_gt(const EncKernelParams P,
   T.lc = P.lc; T.eob = P.eob; T.lfc = P.lfc;
   const int warp = threadIdx.x >> 5;
   encode_mb_group<G, false, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, P.i4_costs);
+}
+
+// Experiment (WGPU_ENC_VARIANT=7/8): one CTA of 12 warps per SM (tables staged once), optionally with CTA-wide barriers at
+// every mode / block step so that the 12 warps fetch the same instructions at the same time.
+template <int G, int WARPS, bool SYNC>
+__global__ void __launch_bounds__(WARPS * 32, 1) encode_wave_kernel_big(const EncKernelParams P, int wave) {
+  constexpr int MPW = 32 / G;
+  WG_STAGE_TABLES(WARPS * 32);
+  const int warp = threadIdx.x >> 5;
+  encode_mb_group<G, false, false, false, SYNC>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
 }
 
 // Method < 3 (the reference's non-RD decisions, serial-path semantics): same wavefront, lighter body.

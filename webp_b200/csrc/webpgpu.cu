@@ -636,6 +636,8 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
     case 4: rc = launch_enc_waves_fn<8, 4>(ctx, P, wg::encode_wave_kernel_nr<8, 4, 144>); break;  // same speed, no spills (measured)
     case 5: rc = launch_enc_waves_fn<8, 4>(ctx, P, wg::encode_wave_kernel_gt<8, 4, 128>); break;  // tables through L1, 4 CTAs/SM
     case 6: rc = launch_enc_waves_fn<8, 4>(ctx, P, wg::encode_wave_kernel_gt<8, 4, 160>); break;  // tables through L1, 3 CTAs/SM
+    case 7: rc = launch_enc_waves_fn<8, 12>(ctx, P, wg::encode_wave_kernel_big<8, 12, false>); break;  // one 12-warp CTA per SM
+    case 8: rc = launch_enc_waves_fn<8, 12>(ctx, P, wg::encode_wave_kernel_big<8, 12, true>); break;   // + CTA-wide step barriers
     default: rc = launch_enc_waves<8, 4, 3>(ctx, P); break;  // 168 regs, 3 CTAs/SM = 48 macroblocks/SM (measured best)
   }
   if (rc) return rc;
