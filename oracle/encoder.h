@@ -325,6 +325,9 @@ struct Encoder {
   std::vector<MBInfo> mb_info;
   SegmentInfo dqm[4];
   Proba proba;
+  std::vector<Proba> proba_hist;   // test taps: probability tables in force over the last serial pass, from macroblock hist_starts[k] on
+  std::vector<int> hist_starts;
+  Proba proba_pre_final;           // state before the final optimizeProba
   // segment / filter headers
   bool seg_use = false, seg_update_map = false;
   int8_t seg_quantizer[4] = {0, 0, 0, 0}, seg_fstrength[4] = {0, 0, 0, 0};
@@ -2148,6 +2151,7 @@ struct Encoder {
   }
   // encodeFrame (encode_frame.go:15-108)
   void encode_frame_serial_pass() {
+    proba_hist.assign(1, proba); hist_starts.assign(1, 0);  // test taps (hostcheck.cc)
     top_y.assign(mb_w * 16, 127); top_u.assign(mb_w * 8, 127); top_v.assign(mb_w * 8, 127);
     top_modes.assign(mb_w * 4, B_DC_PRED);
     s_top_nz.assign(mb_w, 0); s_top_nz_dc.assign(mb_w, 0);
@@ -2166,7 +2170,10 @@ struct Encoder {
       rc.left_nz = 0; rc.left_nz_dc = 0;
       for (int mx = 0; mx < mb_w; ++mx) {
         if (mx == 0) { s_left_nz = 0; s_left_nz_dc = 0; }
-        if (--refresh_cnt < 0) { refresh_probas(); refresh_cnt = max_count; }
+        if (--refresh_cnt < 0) {
+          refresh_probas(); refresh_cnt = max_count;
+          proba_hist.push_back(proba); hist_starts.push_back(my * mb_w + mx);  // test tap: what the following macroblocks are recorded under
+        }
         if (cfg.method >= 3) encode_mb_serial_rd(mx, my, rc); else encode_mb_serial(mx, my, rc);
       }
     }
@@ -2271,6 +2278,7 @@ struct Encoder {
       }
       static thread_local ProbaStats st3;
       collect_all_stats(st3);
+      proba_pre_final = proba;  // test tap
       if (optimize_proba(st3) > 0) rerecord_all_tokens();
       return assemble_frame();
     }

@@ -18,7 +18,8 @@ long hostcheck_serialize(const uint8_t* rgba, int stride, int w, int h, const Or
   e.filter_sharpness = c->filter_sharpness; e.filter_type = c->filter_type; e.partitions = c->partitions; e.segments = c->segments;
   e.preprocessing = c->preprocessing;
   e.pass = c->passes > 0 ? c->passes : 1;
-  e.dither_amp = c->dither_amp;
+  e.dither_amp = c->dither_amp & 0xffff;
+  e.force_serial = (c->dither_amp >> 16) & 1;  // test hook: GOMAXPROCS == 1 semantics
   orc::Encoder* enc = new orc::Encoder();
   enc->init(rgba, stride, w, h, e, c->has_alpha);
   std::vector<uint8_t> ref = orc::riff_wrap(enc->encode_frame());
@@ -63,6 +64,28 @@ long hostcheck_serialize(const uint8_t* rgba, int stride, int w, int h, const Or
     }
     *ms_per_rep = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count() / (reps > 0 ? reps : 1);
     *same = *same && riff2.size() == ref.size() && !memcmp(riff2.data(), ref.data(), ref.size());
+  }
+  if (o.method >= 3 && (enc->mb_h < 4 || e.force_serial) && o.partitions == 0) {
+    // serial RD path (with or without mid-stream refreshes): final optimizeProba on the state the refreshes left + tokens per
+    // table or re-recorded -- the product's serialize_frame_tables / optimize_proba_host / build_cost_tables from oracle data
+    enc->collect_all_stats(st);
+    memcpy(stats.data(), st, stats.size() * 4);
+    uint8_t final_proba[1056];
+    memcpy(final_proba, &enc->proba_pre_final.bands[0][0][0][0], 1056);
+    const int updates = wgh::optimize_proba_host(*reinterpret_cast<const wgh::Stats*>(stats.data()), *reinterpret_cast<uint8_t (*)[4][8][3][11]>(final_proba));
+    const int nt = updates > 0 ? 1 : (int)enc->hist_starts.size();
+    std::vector<const uint8_t*> tabs(nt);
+    const int zero = 0;
+    if (updates > 0) tabs[0] = final_proba;
+    else for (int k = 0; k < nt; ++k) tabs[k] = &enc->proba_hist[k].bands[0][0][0][0];
+    std::vector<uint8_t> riff3;
+    wgh::serialize_frame_tables(fp, hdr.data(), coeffs.data(), segmap.data(), final_proba, nt, updates > 0 ? &zero : enc->hist_starts.data(), tabs.data(), &riff3);
+    // cost tables of the default probabilities == what the library uploads at start-up (sanity of build_cost_tables' layout)
+    static uint16_t lc[4 * 8 * 3 * 68], eobc[96];
+    wgh::build_cost_tables(wgh::kCoeffsProba0, lc, eobc);
+    const bool tab_ok = eobc[0] == wgh::kEntropyCost[wgh::kCoeffsProba0[0]] && lc[0] == wgh::kEntropyCost[255 - wgh::kCoeffsProba0[0]] + wgh::kEntropyCost[wgh::kCoeffsProba0[1]];
+    riff = riff3;
+    *same = seg_same && tab_ok && riff.size() == ref.size() && !memcmp(riff.data(), ref.data(), ref.size());
   }
   delete enc;
   if ((long)riff.size() > cap) return -2;

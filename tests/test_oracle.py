@@ -134,7 +134,10 @@ def test_host_serialisers_reproduce_oracle_bytes(oracle):
     L.hostcheck_serialize.restype = C.c_long
     os.environ["HOSTCHECK_TOKENS"] = "1"
     for (w, h, idx, kw) in [(128, 96, 1, {}), (160, 112, 2, dict(partitions=2)), (96, 80, 0, dict(segments=1)), (256, 256, 2, dict(method=2, quality=80)),
-                            (100, 70, 1, dict(method=0)), (320, 240, 2, dict(method=2, passes=3, quality=60)), (130, 71, 2, dict(method=1, partitions=1))]:
+                            (100, 70, 1, dict(method=0)), (320, 240, 2, dict(method=2, passes=3, quality=60)), (130, 71, 2, dict(method=1, partitions=1)),
+                            # serial RD path: final optimizeProba on top of the refreshed state, tokens per table (serialize_frame_tables)
+                            (640, 48, 1, {}), (1600, 40, 2, dict(method=3, quality=60)), (100, 40, 1, dict(method=3)),
+                            (256, 192, 2, dict(dither_amp=1 << 16)), (400, 300, 1, dict(method=6, quality=40, dither_amp=1 << 16))]:
         img = oracle.synth_image(w, h, idx)
         cfg = oracle.default_cfg(**kw)
         out = np.zeros(2 << 20, np.uint8)
