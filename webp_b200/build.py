@@ -10,8 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libwebpgpu.so")
 SOURCES = ["webpgpu.cu"]
-HEADERS = ["vp8_dev.cuh", "enc_kernels.cuh", "dec_kernels.cuh", "misc_kernels.cuh", "host_enc.h", "host_dec.h",
-           "vp8_tables.inc", os.path.join("..", "..", "include", "webpgpu.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))) + [os.path.join("..", "..", "include", "webpgpu.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
