@@ -53,6 +53,18 @@ def test_default_options_and_mapping():
     assert [getattr(d, f) for f, _ in d._fields_] == [getattr(c, f) for f, _ in c._fields_]
 
 
+def test_rate_control_option_mapping():
+    # EncoderOptions -> lossy.EncodeConfig for the doSearch fields (encode.go:480-488): QMax -1 is the "unset" sentinel (resolveQMax)
+    o = webp_b200.DefaultOptions()
+    o.TargetSize, o.TargetPSNR, o.QMin, o.QMax = 12000, 41.5, 10, -1
+    c = webp_b200.webp.lossy_config(o)
+    assert (c.target_size, c.qmin, c.qmax) == (12000, 10, 100) and abs(c.target_psnr - 41.5) < 1e-6
+    o.QMax = 80
+    assert webp_b200.webp.lossy_config(o).qmax == 80
+    o.QMin = 90
+    assert "QMin/QMax" in webp_b200.validateConfig(o)
+
+
 @pytest.mark.parametrize("field,value,frag", [
     ("Quality", 101, "invalid Quality"), ("Method", 7, "invalid Method"), ("FilterSharpness", 8, "invalid FilterSharpness"),
     ("Partitions", 4, "invalid Partitions"), ("Segments", 5, "invalid Segments"), ("SNSStrength", 101, "invalid SNSStrength"),
