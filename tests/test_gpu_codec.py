@@ -369,6 +369,27 @@ def test_plane_metrics(oracle, gpu_ctx, w, h):
         assert dsp.PSNRFromSSE(sse[i], w * h) == oracle.lib().orc_psnr_from_sse(int(sse[i]), w * h)
 
 
+def test_partition_starting_with_0xff_goes_to_the_host_decoder(oracle, gpu_ctx, monkeypatch):
+    """A (corrupt) partition whose first byte is 0xff breaks value >> bits <= range, which the GPU parser's narrow window relies
+    on (tests/test_decoder_model.py): the library parses such a batch on the host whatever route is asked for, so both routes
+    must make the same thing of it (the same planes, or the same refusal)."""
+    good = oracle.encode(oracle.synth_image(96, 80, 1))
+    part0_len = (good[20] | (good[21] << 8) | (good[22] << 16)) >> 5
+    for pos in (20 + 10 + part0_len, 20 + 10):  # first byte of the token partition / of partition 0
+        bad = bytearray(good)
+        bad[pos] = 0xff
+        bad = bytes(bad)
+        outcome = []
+        for route in ("0", "1"):
+            monkeypatch.setenv("WGPU_DEVICE_PARSER", route)
+            try:
+                _, _, y, u, v, _ = webp_b200.webp.decode_padded([good, bad], ctx=gpu_ctx)
+                outcome.append((y[1].tobytes(), u[1].tobytes(), v[1].tobytes()))
+            except (native.WebPGPUError, webp_b200.WebPError) as e:
+                outcome.append(("error", type(e).__name__))
+        assert outcome[0] == outcome[1]
+
+
 def test_large_batch_takes_gpu_coder_and_parser(oracle, gpu_ctx, monkeypatch):
     """40 images in one call: the library's own choice of routes (>= 32 images: token partitions coded and macroblocks parsed
     on the GPU; 40 = one full warp of partitions + a partial one), bytes and decoded planes against the oracle."""

@@ -1410,6 +1410,8 @@ int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* l
   std::vector<wgh::DecFrame> frames(n);
   std::atomic<int> bad(-1);
   ctx->d_dev_parsed = device_parser_wanted(ctx, (size_t)n);
+  std::atomic<int> irregular(0);
+  size_t stream_bytes = 0;
   if (ctx->d_dev_parsed) {
     // ---- headers on the host, macroblocks on the GPU
     static_assert(sizeof(wgh::DecHeaderH) == sizeof(wg::DecHeader), "DecHeader layout");
@@ -1431,10 +1433,20 @@ int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* l
       D->stream_off = off[i];
       memcpy(ctx->hd_streams.as<uint8_t>() + off[i], vp[i], vl[i]);
       ctx->hd_ftype.as<uint8_t>()[i] = (uint8_t)F.filter_type;
+      // The device decoder's 32-bit window relies on value >> bits <= range, which every boolean-coded partition satisfies
+      // unless its FIRST byte is 0xff (no encoder emits that: value < range + 1 = 255 at the start); such a (corrupt) stream
+      // is parsed by the host decoder, whose wide window defines what comes out of it (tests/test_decoder_model.py).
+      if (vl[i] > 10 && vp[i][10] == 0xff) irregular.store(1);
+      for (int p = 0; p <= D->last_part; ++p)
+        if (D->part_len[p] > 0 && vp[i][D->part_off[p]] == 0xff) irregular.store(1);
     });
     if (bad.load() >= 0) FAIL(WGPU_ERR_BITSTREAM, std::string("image ") + std::to_string(bad.load()) + ": " + (frames[bad.load()].err ? frames[bad.load()].err : "parse error"));
-    CK(cudaMemcpyAsync(ctx->d_streams.p, ctx->hd_streams.p, off[n], cudaMemcpyHostToDevice, ctx->stream));
-    ctx->xfer_h2d += (uint64_t)off[n];
+    if (irregular.load()) ctx->d_dev_parsed = false;
+    stream_bytes = off[n];
+  }
+  if (ctx->d_dev_parsed) {
+    CK(cudaMemcpyAsync(ctx->d_streams.p, ctx->hd_streams.p, stream_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)stream_bytes;
     CK(cudaMemcpyAsync(ctx->d_hdrs.p, ctx->hd_hdrs.p, (size_t)n * sizeof(wgh::DecHeaderH), cudaMemcpyHostToDevice, ctx->stream));
     ctx->xfer_h2d += (uint64_t)((size_t)n * sizeof(wgh::DecHeaderH));
     CK(cudaMemcpyAsync(ctx->d_ftype.p, ctx->hd_ftype.p, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
