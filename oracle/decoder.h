@@ -21,18 +21,24 @@ struct BoolReader {
     buf = d; size = n; pos = 0; value = 0; range = 254; bits = -8; eof = false;
     load();
   }
-  void load() {
-    while (bits < 0) {
-      if (pos < size) {
-        value = (value << 8) | buf[pos++];
-        bits += 8;
-      } else if (!eof) {
-        value <<= 8;
-        bits += 8;
-        eof = true;
-      } else {
-        bits = 0;
-      }
+  void load() {  // loadNewBytes / loadFinalBytes (bitio/reader_bool.go:40-75): 56 bits at a time while 8 bytes remain, then byte-wise,
+                 // one virtual zero byte past the end, then EOF.  For a well-formed partition the width of the load does not
+                 // matter; it does for a corrupt one that starts with 0xff (value >> bits > range from the first bit on).
+    if (pos + 8 <= size) {
+      uint64_t in = 0;
+      for (int i = 0; i < 7; ++i) in = (in << 8) | buf[pos + i];
+      value = in | (value << 56);
+      pos += 7;
+      bits += 56;
+    } else if (pos < size) {
+      bits += 8;
+      value = (uint64_t)buf[pos++] | (value << 8);
+    } else if (!eof) {
+      value <<= 8;
+      bits += 8;
+      eof = true;
+    } else {
+      bits = 0;
     }
   }
   int get_bit(int prob) {
