@@ -3,6 +3,7 @@
 // so that host logic is parity-checked and timed on CPU without a GPU.  Nothing in webp_b200/ links this.
 #include "encoder.h"
 #include "../webp_b200/csrc/host_enc.h"
+#include "../webp_b200/csrc/host_dec.h"
 #include <chrono>
 
 extern "C" {
@@ -91,5 +92,21 @@ long hostcheck_serialize(const uint8_t* rgba, int stride, int w, int h, const Or
   if ((long)riff.size() > cap) return -2;
   memcpy(out, riff.data(), riff.size());
   return (long)riff.size();
+}
+
+// The PRODUCT's host macroblock parser (webp_b200/csrc/host_dec.h parse_frame, the route small batches and irregular
+// partitions take) on one file: 0 and the per-macroblock arrays it hands to the reconstruction kernels, or <0 when it
+// rejects the stream (-1 no VP8 chunk, -2 headers / macroblock data).  dims receives width, height, mb_w, mb_h, filter_type.
+int hostcheck_parse(const uint8_t* data, long len, int16_t* coeffs, uint8_t* meta, long nmb_cap, int* dims) {
+  const uint8_t* vp8; size_t n;
+  if (!wgh::find_vp8(data, (size_t)len, &vp8, &n)) return -1;
+  wgh::DecFrame F;
+  int w = 0, h = 0; const char* err = nullptr;
+  if (!wgh::peek_dims(vp8, n, &w, &h, &err)) return -2;
+  const int mb_w = (w + 15) >> 4, mb_h = (h + 15) >> 4;
+  if ((long)mb_w * mb_h > nmb_cap) return -4;
+  if (!wgh::parse_frame(vp8, n, &F, coeffs, reinterpret_cast<wgh::MBMetaH*>(meta), mb_w, mb_h)) return -2;
+  dims[0] = F.width; dims[1] = F.height; dims[2] = F.mb_w; dims[3] = F.mb_h; dims[4] = F.filter_type;
+  return 0;
 }
 }

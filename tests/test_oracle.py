@@ -147,6 +147,68 @@ def test_host_serialisers_reproduce_oracle_bytes(oracle):
         assert n > 0 and same.value == 1, (w, h, idx, kw)
 
 
+def test_host_macroblock_parser_matches_oracle_on_valid_and_corrupt_streams(oracle):
+    """Product host parser (webp_b200/csrc/host_dec.h parse_frame) vs the oracle decoder's per-macroblock taps, CPU only: own
+    and libwebp-made streams, then byte flips, truncations and 0xff runs (incl. a token partition starting with 0xff, the case
+    where 56-bit and byte-wise refills diverge): same accept / reject decision, same coefficients, modes, nz masks, filter info."""
+    import ctypes as C, io, random
+    L = C.CDLL(os.path.join(os.path.dirname(DATA), "..", "oracle", "_build", "libhostcheck.so"))
+    cap = 1024
+    co = np.zeros((cap, 384), np.int16)
+    me = np.zeros((cap, 32), np.uint8)
+    dims = (C.c_int * 5)()
+
+    def same(data):
+        rc = L.hostcheck_parse(data, C.c_long(len(data)), co.ctypes.data_as(C.c_void_p), me.ctypes.data_as(C.c_void_p), C.c_long(cap), dims)
+        try:
+            w, h, _, _, _, t = oracle.decode(data, taps=True)
+        except RuntimeError:
+            return rc != 0, False
+        if rc != 0 or [dims[0], dims[1]] != [w, h]:
+            return False, True
+        m = me[:dims[2] * dims[3]]
+        return bool(np.array_equal(co[:len(m)], t["coeffs"]) and np.array_equal(m[:, :8].copy().view(np.uint32), t["nz"]) and
+                    np.array_equal(m[:, 8:24], t["meta"][:, 8:24]) and np.array_equal(m[:, 24:28], t["meta"][:, 0:4]) and
+                    np.array_equal(m[:, 28:32], t["meta"][:, 4:8])), True
+
+    try:
+        from PIL import Image
+    except ImportError:
+        Image = None
+    rnd = random.Random(5)
+    accepted = rejected = 0
+    for c in range(60):
+        w, h = rnd.randint(1, 200), rnd.randint(1, 150)
+        img = oracle.synth_image(w, h, rnd.randint(0, 11))
+        if Image is None or rnd.random() < 0.5:
+            data = oracle.encode(img, oracle.default_cfg(quality=rnd.choice([20, 50, 75, 95]), method=rnd.randint(0, 6), segments=rnd.choice([1, 4])))
+        else:
+            b = io.BytesIO()
+            Image.fromarray(img[..., :3]).save(b, "WEBP", quality=rnd.choice([5, 50, 90]), method=rnd.randint(0, 6))
+            data = b.getvalue()
+        assert same(data) == (True, True), c
+        for k in range(6):
+            m = bytearray(data)
+            kind = rnd.random()
+            if kind < 0.4:
+                for _ in range(rnd.randint(1, 4)):
+                    m[rnd.randint(20, len(m) - 1)] = rnd.randint(0, 255)
+            elif kind < 0.6:
+                m = m[:rnd.randint(21, len(m) - 1)]
+            elif kind < 0.8:
+                off = 30 + ((m[20] | m[21] << 8 | m[22] << 16) >> 5)  # first byte of the first token partition
+                if off < len(m):
+                    m[off] = 0xff
+            else:
+                i = rnd.randint(30, len(m) - 1)
+                m[i:i + rnd.randint(1, 8)] = b"\xff" * 8
+            ok, acc = same(bytes(m))
+            assert ok, (c, k)
+            accepted += acc
+            rejected += not acc
+    assert accepted > 50 and rejected > 50
+
+
 def _cleanup_numpy(img):
     """cleanupTransparentAreaLossy (encode.go:788-890) restated once more in plain numpy, to cross-check the C++ oracle."""
     px = img.copy()
