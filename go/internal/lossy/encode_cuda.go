@@ -26,6 +26,7 @@ func cudaOptions(cfg *EncodeConfig) C.wgpu_enc_options {
 		preprocessing: C.int(cfg.Preprocessing), has_alpha: C.int(cfg.HasAlpha),
 		passes: C.int(cfg.Pass), dither_amp: C.int(ditherAmp(cfg.Dithering)),
 		target_size: C.int(cfg.TargetSize), target_psnr: C.float(cfg.TargetPSNR), qmin: C.int(cfg.QMin), qmax: C.int(cfg.QMax),
+		// use_sharp_yuv: set by the caller of NewEncoderFromYUV's replacement (encode.go:531) -- the RGBA goes to the GPU instead of sharpyuv.Convert
 	}
 }
 

@@ -59,6 +59,7 @@ typedef struct {
   int target_size;      /* EncodeConfig.TargetSize in bytes; > 0: size search (doSearch, internal/lossy/encode.go:1338) */
   float target_psnr;    /* EncodeConfig.TargetPSNR in dB; > 0: the reference's "PSNR search" (it measures 99.0 dB every pass) */
   int qmin, qmax;       /* EncodeConfig.QMin / QMax after resolveQMax (encode.go:305): quality clamp of the search; qmax <= 0 means 100 */
+  int use_sharp_yuv;    /* EncoderOptions.UseSharpYUV (encode.go:62, 531-535): source planes from sharpyuv.Convert (WebP matrix, sRGB transfer) instead of importImage; has_alpha / dither_amp then have no effect on the planes */
 } wgpu_enc_options;
 
 void wgpu_enc_options_default(wgpu_enc_options* o, int quality);
@@ -144,7 +145,8 @@ int wgpu_dec_fetch(wgpu_ctx* ctx, uint8_t* y, uint8_t* u, uint8_t* v, size_t y_p
  * fully transparent pixels are smoothed / flattened per 8x8 block before the lossy encode of an image with alpha. */
 int wgpu_cleanup_transparent(wgpu_ctx* ctx, const uint8_t* nrgba, int n, int width, int height, int stride, size_t image_stride,
                              uint8_t* out /* [n][height][4 * width] */);
-/* wgpu_import_rgba: has_alpha bit 0 = alpha-weighted chroma, bits 8..16 = dithering amplitude (0 = fixed rounding). */
+/* wgpu_import_rgba: has_alpha bit 0 = alpha-weighted chroma, bit 1 = SharpYUV planes (sharpyuv/sharpyuv.go:40 Convert +
+ * importYCbCr internal/lossy/encode.go:544), bits 8..16 = dithering amplitude (0 = fixed rounding). */
 /* ---- stage-level entry points (host buffers in/out) ------------------------------------ */
 int wgpu_import_rgba(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int height, int stride,
                      size_t image_stride, int has_alpha, uint8_t* y, uint8_t* u, uint8_t* v);

@@ -16,6 +16,7 @@ struct OrcEncCfg {
       preprocessing, has_alpha, passes, dither_amp, target_size;
   float target_psnr;
   int qmin, qmax;
+  int use_sharp_yuv;
 };
 static EncodeConfig to_cfg(const OrcEncCfg* c) {
   EncodeConfig e;
@@ -27,6 +28,7 @@ static EncodeConfig to_cfg(const OrcEncCfg* c) {
   e.dither_amp = c->dither_amp & 0xffff;
   e.force_serial = (c->dither_amp >> 16) & 1;  // test hook: GOMAXPROCS == 1 semantics
   e.target_size = c->target_size; e.target_psnr = c->target_psnr; e.qmin = c->qmin; e.qmax = c->qmax <= 0 ? 100 : c->qmax;
+  e.use_sharp_yuv = c->use_sharp_yuv != 0;
   return e;
 }
 // Encode one RGBA image (parallel-path semantics).  Returns RIFF size or <0 (-1 unsupported
@@ -219,7 +221,8 @@ void orc_import_rgba(const uint8_t* rgba, int stride, int w, int h, int has_alph
   Encoder* enc = new Encoder();
   EncodeConfig c;
   c.dither_amp = has_alpha >> 8;  // bits 8.. carry the dithering amplitude for tests
-  has_alpha &= 0xff;
+  c.use_sharp_yuv = (has_alpha & 2) != 0;  // bit 1: SharpYUV planes
+  has_alpha &= 1;
   enc->cfg = c; enc->width = w; enc->height = h; enc->mb_w = (w + 15) >> 4; enc->mb_h = (h + 15) >> 4;
   enc->y_stride = enc->mb_w * 16; enc->uv_stride = enc->mb_w * 8;
   enc->y_plane.assign((size_t)enc->y_stride * enc->mb_h * 16, 0);
@@ -230,6 +233,12 @@ void orc_import_rgba(const uint8_t* rgba, int stride, int w, int h, int has_alph
   memcpy(u, enc->u_plane.data(), enc->u_plane.size());
   memcpy(v, enc->v_plane.data(), enc->v_plane.size());
   delete enc;
+}
+// sharpyuv.Convert with the WebP matrix and sRGB transfer on RGBA input: tight planes; returns the refinement passes run.
+int orc_sharp_yuv(const uint8_t* rgba, int stride, int w, int h, uint8_t* y, uint8_t* u, uint8_t* v) {
+  int iters = 0;
+  sharp::convert(rgba, stride, w, h, y, w, u, v, (w + 1) >> 1, &iters);
+  return iters;
 }
 // buildNRGBA (webp.go:379)
 void orc_build_nrgba(int w, int h, const uint8_t* y, int ys, const uint8_t* u, const uint8_t* v, int uvs,

@@ -11,6 +11,7 @@
 // dependencies as the reference's row-pipelined workers (results are order-independent).
 #pragma once
 #include "dsp.h"
+#include "sharpyuv.h"
 #include <vector>
 
 namespace orc {
@@ -84,6 +85,7 @@ struct EncodeConfig {  // internal/lossy/encode.go:46-86 (DefaultConfig)
   int target_size = 0;      // bytes; > 0 -> size search (doSearch, encode.go:1338)
   float target_psnr = 0.f;  // dB; > 0 -> "PSNR search" (the measured PSNR is always 99.0)
   int qmin = 0, qmax = 100; // resolveQMax(-1) == 100 (encode.go:305-306)
+  bool use_sharp_yuv = false;  // EncoderOptions.UseSharpYUV: planes from sharpyuv.Convert + importYCbCr (encode.go:531-535)
 };
 struct SegmentQuant {  // encode.go:311-323
   int quant, iquant, bias, dc_quant, dc_iquant, dc_bias;
@@ -414,7 +416,22 @@ struct Encoder {
       return d + (1 << (num_bits - 1));
     }
   };
+  // NewEncoderFromYUV's importYCbCr (internal/lossy/encode.go:544-585): sharp planes, edges replicated up to the macroblock grid
+  void import_sharp(const uint8_t* pix, int stride) {
+    const int w = width, h = height, pad_w = mb_w * 16, pad_h = mb_h * 16, uv_w = (w + 1) >> 1, uv_h = (h + 1) >> 1;
+    std::vector<uint8_t> ty((size_t)w * h), tu((size_t)uv_w * uv_h), tv((size_t)uv_w * uv_h);
+    sharp::convert(pix, stride, w, h, ty.data(), w, tu.data(), tv.data(), uv_w);
+    for (int y = 0; y < pad_h; ++y)
+      for (int x = 0; x < pad_w; ++x) y_plane[(size_t)y * y_stride + x] = ty[(size_t)(y >= h ? h - 1 : y) * w + (x >= w ? w - 1 : x)];
+    for (int y = 0; y < pad_h / 2; ++y)
+      for (int x = 0; x < pad_w / 2; ++x) {
+        const size_t s = (size_t)(y >= uv_h ? uv_h - 1 : y) * uv_w + (x >= uv_w ? uv_w - 1 : x);
+        u_plane[(size_t)y * uv_stride + x] = tu[s];
+        v_plane[(size_t)y * uv_stride + x] = tv[s];
+      }
+  }
   void import_image(const uint8_t* pix, int stride, int has_alpha) {
+    if (cfg.use_sharp_yuv) return import_sharp(pix, stride);
     const int w = width, h = height, pad_w = mb_w * 16, pad_h = mb_h * 16;
     Random rg(cfg.dither_amp);
     const bool dither = cfg.dither_amp > 0;  // amp 0 gives the fixed rounding back, so "Dithering > 0 but amp == 0" is the same

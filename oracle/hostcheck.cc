@@ -4,6 +4,9 @@
 #include "encoder.h"
 #include "../webp_b200/csrc/host_enc.h"
 #include "../webp_b200/csrc/host_dec.h"
+#include "../webp_b200/csrc/sharp_kernels.cuh"
+#include <algorithm>
+#include <random>
 #include <chrono>
 
 extern "C" {
@@ -107,6 +110,61 @@ int hostcheck_parse(const uint8_t* data, long len, int16_t* coeffs, uint8_t* met
   if ((long)mb_w * mb_h > nmb_cap) return -4;
   if (!wgh::parse_frame(vp8, n, &F, coeffs, reinterpret_cast<wgh::MBMetaH*>(meta), mb_w, mb_h)) return -2;
   dims[0] = F.width; dims[1] = F.height; dims[2] = F.mb_w; dims[3] = F.mb_h; dims[4] = F.filter_type;
+  return 0;
+}
+
+// The PRODUCT's SharpYUV import (webp_b200/csrc/sharp_kernels.cuh) run on the CPU in the kernels' schedule: the same per-sample
+// functions the three kernels call, "threads" of a phase visited in a shuffled order (order_seed) so that any dependence
+// between samples of one phase shows, barriers where the kernels have them.  Outputs padded planes as the encoder gets them.
+int hostcheck_sharp(const uint8_t* rgba, int stride, int n, int width, int height, unsigned order_seed, uint8_t* y, uint8_t* u, uint8_t* v, int* iterations) {
+  std::vector<uint32_t> tab(wg::kSharpG2L + wg::kSharpL2G);
+  wg::sharp_build_tables(tab.data());
+  wg::SharpParams P;
+  P.rgba = rgba; P.image_stride = (size_t)stride * height; P.stride = stride; P.n = n; P.width = width; P.height = height;
+  P.w = (width + 1) & ~1; P.h = (height + 1) & ~1; P.uv_w = P.w >> 1; P.uv_h = P.h >> 1;
+  std::vector<uint16_t> by((size_t)n * P.w * P.h), ty(by.size());
+  std::vector<int16_t> buv((size_t)n * 3 * P.uv_w * P.uv_h), tuv(buv.size());
+  P.best_y = by.data(); P.target_y = ty.data(); P.best_uv = buv.data(); P.target_uv = tuv.data();
+  P.g2l = tab.data(); P.l2g = tab.data() + wg::kSharpG2L;
+  const int pad_w = ((width + 15) >> 4) * 16, pad_h = ((height + 15) >> 4) * 16;
+  P.y = y; P.u = u; P.v = v; P.y_plane = (size_t)pad_w * pad_h; P.uv_plane = P.y_plane / 4; P.pad_w = pad_w; P.pad_h = pad_h;
+  P.iterations = iterations;
+  std::mt19937 rng(order_seed);
+  auto shuffled = [&](long long count) {
+    std::vector<long long> o((size_t)count);
+    for (long long i = 0; i < count; ++i) o[(size_t)i] = i;
+    if (order_seed) std::shuffle(o.begin(), o.end(), rng);
+    return o;
+  };
+  const long long per1 = (long long)P.uv_w * P.uv_h;
+  for (long long t : shuffled(per1 * n)) {  // sharp_init_kernel
+    const int img = (int)(t / per1), rem = (int)(t % per1);
+    wg::sharp_init_item(P, img, rem / P.uv_w, rem % P.uv_w, P.g2l, P.l2g);
+  }
+  std::vector<int> keep((size_t)3 * P.uv_w);
+  for (int img = 0; img < n; ++img) {  // sharp_refine_kernel: one CTA per image
+    const unsigned long long threshold = 3ull * (unsigned long long)P.w * (unsigned long long)P.h;
+    unsigned long long prev_sum = ~0ull;
+    int iters = 0;
+    for (int iter = 0; iter < 4; ++iter) {
+      unsigned long long sum = 0;
+      ++iters;
+      for (int jp = 0; jp < P.uv_h; ++jp) {
+        for (long long i : shuffled(P.uv_w)) sum += wg::sharp_refine_item(P, img, jp, (int)i, P.g2l, P.l2g, &keep[(size_t)3 * i]);
+        // __syncthreads()
+        for (long long i : shuffled(P.uv_w)) wg::sharp_commit_item(P, img, jp, (int)i, &keep[(size_t)3 * i]);
+        // __syncthreads()
+      }
+      if (wg::sharp_stop(iter, sum, prev_sum, threshold)) break;
+      prev_sum = sum;
+    }
+    if (iterations) iterations[img] = iters;
+  }
+  const long long per3 = (long long)(pad_w / 2) * (pad_h / 2);
+  for (long long t : shuffled(per3 * n)) {  // sharp_finish_kernel
+    const int img = (int)(t / per3), rem = (int)(t % per3);
+    wg::sharp_finish_item(P, img, rem / (pad_w / 2), rem % (pad_w / 2));
+  }
   return 0;
 }
 }

@@ -16,14 +16,14 @@ class OrcEncCfg(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "quality", "method", "sns_strength", "filter_strength", "filter_sharpness", "filter_type",
         "partitions", "segments", "preprocessing", "has_alpha", "passes", "dither_amp", "target_size")] + [
-        ("target_psnr", C.c_float), ("qmin", C.c_int), ("qmax", C.c_int)]
+        ("target_psnr", C.c_float), ("qmin", C.c_int), ("qmax", C.c_int), ("use_sharp_yuv", C.c_int)]
 
 
 def default_cfg(quality=75, method=4, **kw):
     """lossy.DefaultConfig (internal/lossy/encode.go:66) + EncoderOptions mapping (encode.go:478-528)."""
     c = OrcEncCfg(quality=quality, method=method, sns_strength=50, filter_strength=60, filter_sharpness=0,
                   filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=0, passes=1, dither_amp=0,
-                  target_size=0, target_psnr=0.0, qmin=0, qmax=100)
+                  target_size=0, target_psnr=0.0, qmin=0, qmax=100, use_sharp_yuv=0)
     for k, v in kw.items():
         setattr(c, k, v)
     return c
@@ -168,3 +168,14 @@ import sys as _sys
 if ROOT not in _sys.path:
     _sys.path.insert(0, ROOT)
 from webp_b200.synth import synth_image  # noqa: E402,F401  (shared generator; pure numpy, no native code)
+
+
+def sharp_yuv(rgba):
+    """sharpyuv.Convert (WebP matrix, sRGB transfer) on RGBA [h][w][4]: tight Y, U, V planes and the refinement passes run."""
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = rgba.shape[:2]
+    y = np.zeros((h, w), np.uint8)
+    u = np.zeros(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    v = np.zeros_like(u)
+    iters = lib().orc_sharp_yuv(_p(rgba), C.c_int(rgba.strides[0]), w, h, _p(y), _p(u), _p(v))
+    return y, u, v, iters

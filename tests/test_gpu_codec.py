@@ -60,6 +60,33 @@ def test_import_rgba(oracle, gpu_ctx, w, h, has_alpha):
         assert np.array_equal(y[i], ey) and np.array_equal(u[i], eu) and np.array_equal(v[i], ev)
 
 
+@pytest.mark.parametrize("w,h", [(64, 64), (130, 71), (33, 49), (1, 1), (2, 1), (1, 2), (5, 7), (1536, 1024), (4200, 18)])
+def test_import_sharp_yuv(oracle, gpu_ctx, w, h):
+    """UseSharpYUV planes (sharpyuv.Convert + importYCbCr): sharp_init / sharp_refine / sharp_finish kernels vs the oracle, incl.
+    noise and hard-edged images (3-4 refinement passes), odd sizes, and a row of more than 2048 chroma samples (1024-thread CTA)."""
+    rng = np.random.RandomState(w * 31 + h)
+    imgs = np.stack([oracle.synth_image(w, h, 1), oracle.synth_image(w, h, 5), rng.randint(0, 256, (h, w, 4)).astype(np.uint8),
+                     (rng.randint(0, 2, (h, w, 4)) * 255).astype(np.uint8)])
+    y, u, v = dsp.ImportRGBA(imgs, False, gpu_ctx, sharp_yuv=True)
+    for i in range(len(imgs)):
+        ey, eu, ev = oracle.import_rgba(imgs[i], has_alpha=2)
+        errs = [e for e in (first_diff("y", y[i], ey), first_diff("u", u[i], eu), first_diff("v", v[i], ev)) if e]
+        assert not errs, "image %d: %s" % (i, "; ".join(errs))
+
+
+@pytest.mark.parametrize("w,h,idxs,kw", [(128, 96, [0, 1, 2], {}), (100, 70, [1, 2], dict(Method=2, Quality=60)), (130, 71, [2, 5], dict(Method=6, Preprocessing=2)),
+                                          (64, 48, [0, 1], dict(TargetSize=800))])
+def test_encode_with_sharp_yuv(oracle, gpu_ctx, w, h, idxs, kw):
+    # EncoderOptions.UseSharpYUV (encode.go:531-535, TestEdge_SharpYUV edge_cases_test.go:482): same bytes as the oracle, and not the standard import's
+    o = _opts(UseSharpYUV=True, **kw)
+    imgs = np.stack([oracle.synth_image(w, h, i) for i in idxs])
+    files = webp_b200.EncodeBatch(imgs, o, gpu_ctx)
+    plain = webp_b200.EncodeBatch(imgs, _opts(**kw), gpu_ctx)
+    for k in range(len(idxs)):
+        assert files[k] == oracle.encode(imgs[k], _ocfg(oracle, o)), "image %d" % idxs[k]
+        assert files[k] != plain[k]
+
+
 def test_import_rgba_dithered(oracle, gpu_ctx):
     # Preprocessing&2: VP8Random rounding terms in the reference's draw order (encode.go:793-809,925-936; dsp/random.go)
     for (w, h, amp) in [(100, 70, 200), (64, 64, 256), (130, 71, 37)]:

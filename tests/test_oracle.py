@@ -209,6 +209,65 @@ def test_host_macroblock_parser_matches_oracle_on_valid_and_corrupt_streams(orac
     assert accepted > 50 and rejected > 50
 
 
+def _sharp_golden():
+    import importlib.util, json
+    g = os.path.join(os.path.dirname(DATA), "golden")
+    spec = importlib.util.spec_from_file_location("make_sharpyuv_golden", os.path.join(g, "make_sharpyuv_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m, json.load(open(os.path.join(g, "sharpyuv_libsharpyuv.json")))
+
+
+def test_sharpyuv_oracle_matches_libsharpyuv_golden(oracle):
+    """oracle/sharpyuv.h (restatement of sharpyuv.Convert as UseSharpYUV reaches it) against planes of libsharpyuv, the C library the
+    reference's own testc/sharpyuv suite compares with (there within +-1; the restatement agrees exactly): committed digests
+    (tests/golden/sharpyuv_libsharpyuv.json, made by make_sharpyuv_golden.py) and, where this image has it, the library itself."""
+    m, gold = _sharp_golden()
+    S = m.libsharpyuv()
+    for c in gold["cases"]:
+        img = m.case_image(c["w"], c["h"], c["image"])
+        y, u, v, iters = oracle.sharp_yuv(img)
+        assert 1 <= iters <= 4
+        assert m.digest(y, u, v) == c["sha256"], c
+        if S is not None:
+            ry, ru, rv = m.convert(S, img)
+            assert np.array_equal(y, ry) and np.array_equal(u, ru) and np.array_equal(v, rv), c
+    # importYCbCr (internal/lossy/encode.go:544): the padded planes replicate the last row / column of the tight ones
+    img = oracle.synth_image(37, 21, 3)
+    y, u, v, _ = oracle.sharp_yuv(img)
+    py, pu, pv = oracle.import_rgba(img, has_alpha=2)
+    assert np.array_equal(py[:21, :37], y) and np.array_equal(pu[:11, :19], u) and np.array_equal(pv[:11, :19], v)
+    assert np.all(py[21:, :37] == y[-1]) and np.all(py[:21, 37:] == y[:, -1:]) and np.all(pu[11:, :19] == u[-1]) and np.all(pv[:11, 19:] == v[:, -1:])
+    # the encoder takes those planes: a decodable stream that differs from the standard import's
+    a = oracle.encode(img, oracle.default_cfg(use_sharp_yuv=1))
+    assert a != oracle.encode(img) and oracle.decode(a)[0] == 37
+
+
+def test_sharpyuv_kernel_code_on_cpu_matches_oracle(oracle):
+    """The product's SharpYUV per-sample functions (webp_b200/csrc/sharp_kernels.cuh, host+device) run on the CPU in the kernels'
+    schedule with the threads of each phase in shuffled order (oracle/hostcheck.cc hostcheck_sharp): planes and pass counts
+    equal the oracle's whatever the order, i.e. the barriers sit where the data dependences are."""
+    import ctypes as C
+    L = C.CDLL(os.path.join(os.path.dirname(DATA), "..", "oracle", "_build", "libhostcheck.so"))
+    m, gold = _sharp_golden()
+    for (w, h, idxs) in [(32, 32, [0]), (33, 17, [1, 2]), (1, 1, [2]), (2, 1, [3]), (1, 2, [3]), (5, 7, [4, 5, 6]), (130, 71, [6, 7]), (256, 192, [7]),
+                         (100, 1, [9]), (1, 100, [10]), (64, 64, [-1, -2]), (97, 33, [-2, -1]), (2, 2, [-3])]:
+        imgs = np.stack([m.case_image(w, h, i) for i in idxs])
+        n = len(idxs)
+        mbw, mbh = (w + 15) >> 4, (h + 15) >> 4
+        for seed in (0, 11):
+            y = np.zeros((n, mbh * 16, mbw * 16), np.uint8)
+            u = np.zeros((n, mbh * 8, mbw * 8), np.uint8)
+            v = np.zeros_like(u)
+            it = np.zeros(n, np.int32)
+            L.hostcheck_sharp(imgs.ctypes.data_as(C.c_void_p), w * 4, n, w, h, C.c_uint(seed), y.ctypes.data_as(C.c_void_p),
+                              u.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), it.ctypes.data_as(C.c_void_p))
+            for k in range(n):
+                ey, eu, ev = oracle.import_rgba(imgs[k], has_alpha=2)
+                assert np.array_equal(y[k], ey) and np.array_equal(u[k], eu) and np.array_equal(v[k], ev), (w, h, idxs[k], seed)
+                assert it[k] == oracle.sharp_yuv(imgs[k])[3]
+
+
 def _cleanup_numpy(img):
     """cleanupTransparentAreaLossy (encode.go:788-890) restated once more in plain numpy, to cross-check the C++ oracle."""
     px = img.copy()

@@ -16,6 +16,7 @@
 #include "misc_kernels.cuh"
 #include "token_kernels.cuh"
 #include "dec_parse.cuh"
+#include "sharp_kernels.cuh"
 #include "host_dec.h"
 
 namespace {
@@ -81,6 +82,7 @@ struct wgpu_ctx {
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
   DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
+  DevBuf sharp_best_y, sharp_target_y, sharp_best_uv, sharp_target_uv, t_sharp;  // SharpYUV import working planes + gamma tables
   PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false, e_keep_derr = false, e_keep_stats = false;
@@ -156,7 +158,7 @@ void wgpu_enc_options_default(wgpu_enc_options* o, int quality) {
   // DefaultOptions (encode.go:196-214) mapped onto lossy.EncodeConfig (internal/lossy/encode.go:66-86)
   o->quality = quality; o->method = 4; o->sns_strength = 50; o->filter_strength = 60; o->filter_sharpness = 0;
   o->filter_type = 1; o->partitions = 0; o->segments = 4; o->preprocessing = 0; o->has_alpha = 0; o->passes = 1; o->dither_amp = 0;
-  o->target_size = 0; o->target_psnr = 0.f; o->qmin = 0; o->qmax = 100;
+  o->target_size = 0; o->target_psnr = 0.f; o->qmin = 0; o->qmax = 100; o->use_sharp_yuv = 0;
 }
 
 static int upload_table(wgpu_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
@@ -223,7 +225,7 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
+  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_streams, &ctx->d_hdrs, &ctx->d_perr, &ctx->t_bmodes, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
@@ -465,7 +467,41 @@ int enc_variant() {
 }  // namespace
 }  // extern "C++"
 
+// EncoderOptions.UseSharpYUV (encode.go:531-535): sharpyuv.Convert with the WebP matrix and the sRGB transfer, then importYCbCr.
+static int enc_launch_import_sharp(wgpu_ctx* ctx) {
+  const int n = ctx->e_n, pad_w = ctx->e_mbw * 16, pad_h = ctx->e_mbh * 16;
+  if (!ctx->t_sharp.p) {  // gamma tables (sharpyuv/gamma.go:47-91): doubles, as the reference builds them
+    std::vector<uint32_t> tab(wg::kSharpG2L + wg::kSharpL2G);
+    wg::sharp_build_tables(tab.data());
+    int rc = upload_table(ctx, ctx->t_sharp, tab.data(), tab.size() * 4);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));  // the host vector goes out of scope
+  }
+  wg::SharpParams P;
+  P.rgba = ctx->rgba.as<uint8_t>(); P.image_stride = (size_t)ctx->e_h * ctx->e_rgba_stride; P.stride = ctx->e_rgba_stride;
+  P.n = n; P.width = ctx->e_w; P.height = ctx->e_h;
+  P.w = (ctx->e_w + 1) & ~1; P.h = (ctx->e_h + 1) & ~1; P.uv_w = P.w >> 1; P.uv_h = P.h >> 1;
+  const size_t luma = (size_t)n * P.w * P.h, chroma = (size_t)n * 3 * P.uv_w * P.uv_h;
+  RESERVE(ctx->sharp_best_y, luma * 2); RESERVE(ctx->sharp_target_y, luma * 2);
+  RESERVE(ctx->sharp_best_uv, chroma * 2); RESERVE(ctx->sharp_target_uv, chroma * 2);
+  P.best_y = ctx->sharp_best_y.as<uint16_t>(); P.target_y = ctx->sharp_target_y.as<uint16_t>();
+  P.best_uv = ctx->sharp_best_uv.as<int16_t>(); P.target_uv = ctx->sharp_target_uv.as<int16_t>();
+  P.g2l = ctx->t_sharp.as<uint32_t>(); P.l2g = P.g2l + wg::kSharpG2L;
+  P.y = ctx->sy.as<uint8_t>(); P.u = ctx->su.as<uint8_t>(); P.v = ctx->sv.as<uint8_t>();
+  P.y_plane = (size_t)pad_w * pad_h; P.uv_plane = P.y_plane / 4; P.pad_w = pad_w; P.pad_h = pad_h;
+  P.iterations = nullptr;
+  const long long blocks2 = (long long)P.uv_w * P.uv_h * n;
+  wg::sharp_init_kernel<<<(unsigned)std::min<long long>((blocks2 + 255) / 256, 148LL * 64), 256, 0, ctx->stream>>>(P);
+  if (P.uv_w <= 256 * wg::SHARP_ITEMS) wg::sharp_refine_kernel<256><<<(unsigned)n, 256, 0, ctx->stream>>>(P);
+  else wg::sharp_refine_kernel<1024><<<(unsigned)n, 1024, 0, ctx->stream>>>(P);  // up to 8192 chroma samples per row: any WebP width
+  const long long blocks3 = (long long)(pad_w / 2) * (pad_h / 2) * n;
+  wg::sharp_finish_kernel<<<(unsigned)std::min<long long>((blocks3 + 255) / 256, 148LL * 64), 256, 0, ctx->stream>>>(P);
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  return WGPU_OK;
+}
 static int enc_launch_import(wgpu_ctx* ctx) {
+  if (ctx->e_opt.use_sharp_yuv) return enc_launch_import_sharp(ctx);
   const int n = ctx->e_n, pad_w = ctx->e_mbw * 16, pad_h = ctx->e_mbh * 16;
   wg::ImportParams ip;
   ip.rgba = ctx->rgba.as<uint8_t>(); ip.image_stride = (size_t)ctx->e_h * ctx->e_rgba_stride; ip.stride = ctx->e_rgba_stride;
@@ -1598,7 +1634,8 @@ int wgpu_import_rgba(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int h
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(ctx->mu);
   wgpu_enc_options_default(&ctx->e_opt, 75);
-  ctx->e_opt.has_alpha = has_alpha & 0xff;
+  ctx->e_opt.has_alpha = has_alpha & 1;
+  ctx->e_opt.use_sharp_yuv = (has_alpha >> 1) & 1;
   ctx->e_opt.dither_amp = (has_alpha >> 8) & 0x1ff;  // bits 8.. of has_alpha carry the dithering amplitude (stage-level entry)
   if ((rc = enc_reserve(ctx))) return rc;
   if ((rc = enc_launch_import(ctx))) return rc;

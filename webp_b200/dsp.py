@@ -103,12 +103,13 @@ def TokenCostForCoeffsBatch(levels, nz, ctx_type, ctx0, first, ctx=None):
     return out
 
 
-def ImportRGBA(rgba, has_alpha=False, ctx=None, dither_amp=0):
-    """(*VP8Encoder).importImage (internal/lossy/encode.go:671): uint8 [n][h][w][4] -> padded Y, U, V planes."""
+def ImportRGBA(rgba, has_alpha=False, ctx=None, dither_amp=0, sharp_yuv=False):
+    """(*VP8Encoder).importImage (internal/lossy/encode.go:671): uint8 [n][h][w][4] -> padded Y, U, V planes.  sharp_yuv: the planes
+    NewEncoderFromYUV gets under UseSharpYUV instead (sharpyuv.Convert, sharpyuv/sharpyuv.go:40, + importYCbCr, encode.go:544)."""
     ctx = _ctx(ctx); a = _c(rgba, np.uint8); n, h, w = a.shape[:3]
     mbw, mbh = (w + 15) >> 4, (h + 15) >> 4
     y = np.empty((n, mbh * 16, mbw * 16), np.uint8); u = np.empty((n, mbh * 8, mbw * 8), np.uint8); v = np.empty_like(u)
-    ctx.check(native.lib().wgpu_import_rgba(ctx.handle, a.ctypes.data, n, w, h, w * 4, w * h * 4, int(has_alpha) | (int(dither_amp) << 8), y.ctypes.data,
+    ctx.check(native.lib().wgpu_import_rgba(ctx.handle, a.ctypes.data, n, w, h, w * 4, w * h * 4, int(bool(has_alpha)) | (2 if sharp_yuv else 0) | (int(dither_amp) << 8), y.ctypes.data,
                                            u.ctypes.data, v.ctypes.data))
     return y, u, v
 

@@ -19,7 +19,7 @@ class EncOptions(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "quality", "method", "sns_strength", "filter_strength", "filter_sharpness", "filter_type",
         "partitions", "segments", "preprocessing", "has_alpha", "passes", "dither_amp", "target_size")] + [
-        ("target_psnr", C.c_float), ("qmin", C.c_int), ("qmax", C.c_int)]
+        ("target_psnr", C.c_float), ("qmin", C.c_int), ("qmax", C.c_int), ("use_sharp_yuv", C.c_int)]
 
 
 class SegQuant(C.Structure):

@@ -131,7 +131,7 @@ def lossy_config(o, has_alpha=False):
     """EncoderOptions -> lossy.EncodeConfig (encode.go:478-528 over lossy.DefaultConfig, internal/lossy/encode.go:66-86)."""
     c = native.EncOptions(quality=int(o.Quality), method=o.Method, sns_strength=50, filter_strength=60, filter_sharpness=0,
                           filter_type=1, partitions=0, segments=4, preprocessing=0, has_alpha=int(has_alpha), passes=1, dither_amp=0,
-                          target_size=0, target_psnr=0.0, qmin=0, qmax=100)
+                          target_size=0, target_psnr=0.0, qmin=0, qmax=100, use_sharp_yuv=int(bool(o.UseSharpYUV)))  # encode.go:531
     if o.SNSStrength >= 0:
         c.sns_strength = o.SNSStrength
     if o.FilterStrength >= 0:
@@ -167,8 +167,6 @@ class WebPError(ValueError):
 def _unsupported(o):
     if o.Lossless:
         return "webp: Lossless (VP8L) is outside the GPU lossy path"
-    if o.UseSharpYUV:
-        return "webp: UseSharpYUV is outside the GPU lossy path"
     if o.ICC or o.EXIF or o.XMP:
         return "webp: metadata chunks (VP8X container) are host-side container work outside this path"
     return None
