@@ -429,6 +429,7 @@ struct Encoder {
         u_plane[(size_t)y * uv_stride + x] = tu[s];
         v_plane[(size_t)y * uv_stride + x] = tv[s];
       }
+    src_y = y_plane; src_u = u_plane; src_v = v_plane;
   }
   void import_image(const uint8_t* pix, int stride, int has_alpha) {
     if (cfg.use_sharp_yuv) return import_sharp(pix, stride);

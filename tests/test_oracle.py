@@ -241,6 +241,11 @@ def test_sharpyuv_oracle_matches_libsharpyuv_golden(oracle):
     # the encoder takes those planes: a decodable stream that differs from the standard import's
     a = oracle.encode(img, oracle.default_cfg(use_sharp_yuv=1))
     assert a != oracle.encode(img) and oracle.decode(a)[0] == 37
+    # rate control restores the source planes after every pass (restoreSourcePixels, encode.go:1606): the sharp planes, not stale ones;
+    # an unreachable target ends at QMax = 100 with the size of a plain quality-100 encode of the same planes
+    img = oracle.synth_image(64, 48, 0)
+    rc = oracle.encode(img, oracle.default_cfg(use_sharp_yuv=1, target_size=800))
+    assert len(rc) == len(oracle.encode(img, oracle.default_cfg(use_sharp_yuv=1, quality=100))) and oracle.decode(rc)[0] == 64
 
 
 def test_sharpyuv_kernel_code_on_cpu_matches_oracle(oracle):

@@ -1,4 +1,5 @@
-"""Small encode (+ optional decode) job for ncu captures: python tools/prof_encode.py [n] [w] [h] [reps] [decode]"""
+"""Small encode (+ optional decode) job for ncu captures: python tools/prof_encode.py [n] [w] [h] [reps] [decode]
+STAGE_TIME=1 prints per-stage device times; SHARP=1 encodes with UseSharpYUV (stage "import" is then the three SharpYUV kernels)."""
 import ctypes as C, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -15,6 +16,7 @@ imgs = synth_batch(n, w, h, distinct=min(n, 12))
 cap = w * h + 65536
 out = np.empty((n, cap), np.uint8); sizes = np.zeros(n, np.uint64)
 opt = native.EncOptions(); L.wgpu_enc_options_default(opt, 75)
+opt.use_sharp_yuv = 1 if os.environ.get("SHARP") else 0
 for _ in range(reps):
     ctx.check(L.wgpu_encode_batch(ctx.handle, imgs.ctypes.data, n, w, h, w * 4, w * h * 4, C.byref(opt), out.ctypes.data, cap, sizes.ctypes.data))
 ms = C.c_float()
