@@ -46,6 +46,7 @@ def fuzz(cases, seed, ctx=None):
         if (serial and nmb > 96) or o.TargetSize > 0 or o.TargetPSNR > 0:
             o.Partitions = 0  # the refresh route and rate control are single-partition
         idxs = [rnd.randint(0, 11) for _ in range(rnd.choice([1, 2, 3]))]
+        o.UseSharpYUV = random.Random(seed * 7919 + c).random() < 0.2  # own generator: the other draws of a (seed, case) stay what they were
         os.environ["WGPU_DEVICE_CODER"] = rnd.choice(["0", "1"])
         os.environ["WGPU_DEVICE_PARSER"] = rnd.choice(["0", "1"])
         desc = "case %d: %dx%d imgs=%s coder=%s parser=%s %s" % (c, w, h, idxs, os.environ["WGPU_DEVICE_CODER"], os.environ["WGPU_DEVICE_PARSER"],
