@@ -18,15 +18,21 @@ import (
 	"github.com/deepteams/webp/internal/pool"
 )
 
-func cudaOptions(cfg *EncodeConfig) C.wgpu_enc_options {
+// UseSharpYUV: under the cuda tag webp.encodeLossyWithAlpha (encode.go:531) keeps the RGBA and sets sharp instead of calling
+// sharpYUVConvert + NewEncoderFromYUV; the library then derives the source planes itself (sharp_kernels.cuh).
+func cudaOptions(cfg *EncodeConfig, sharp ...bool) C.wgpu_enc_options {
+	sharpYUV := 0
+	if len(sharp) > 0 && sharp[0] {
+		sharpYUV = 1
+	}
 	return C.wgpu_enc_options{
+		use_sharp_yuv: C.int(sharpYUV),
 		quality: C.int(cfg.Quality), method: C.int(cfg.Method), sns_strength: C.int(cfg.SNSStrength),
 		filter_strength: C.int(cfg.FilterStrength), filter_sharpness: C.int(cfg.FilterSharpness),
 		filter_type: C.int(cfg.FilterType), partitions: C.int(cfg.Partitions), segments: C.int(cfg.Segments),
 		preprocessing: C.int(cfg.Preprocessing), has_alpha: C.int(cfg.HasAlpha),
 		passes: C.int(cfg.Pass), dither_amp: C.int(ditherAmp(cfg.Dithering)),
 		target_size: C.int(cfg.TargetSize), target_psnr: C.float(cfg.TargetPSNR), qmin: C.int(cfg.QMin), qmax: C.int(cfg.QMax),
-		// use_sharp_yuv: set by the caller of NewEncoderFromYUV's replacement (encode.go:531) -- the RGBA goes to the GPU instead of sharpyuv.Convert
 	}
 }
 
