@@ -116,7 +116,7 @@ int hostcheck_parse(const uint8_t* data, long len, int16_t* coeffs, uint8_t* met
 // The PRODUCT's SharpYUV import (webp_b200/csrc/sharp_kernels.cuh) run on the CPU in the kernels' schedule: the same per-sample
 // functions the three kernels call, "threads" of a phase visited in a shuffled order (order_seed) so that any dependence
 // between samples of one phase shows, barriers where the kernels have them.  Outputs padded planes as the encoder gets them.
-int hostcheck_sharp(const uint8_t* rgba, int stride, int n, int width, int height, unsigned order_seed, uint8_t* y, uint8_t* u, uint8_t* v, int* iterations) {
+int hostcheck_sharp(const uint8_t* rgba, int stride, int n, int width, int height, unsigned order_seed, uint8_t* y, uint8_t* u, uint8_t* v, int* iterations, int variant) {
   std::vector<uint32_t> tab(wg::kSharpG2L + wg::kSharpL2G);
   wg::sharp_build_tables(tab.data());
   wg::SharpParams P;
@@ -149,6 +149,27 @@ int hostcheck_sharp(const uint8_t* rgba, int stride, int n, int width, int heigh
     for (int iter = 0; iter < 4; ++iter) {
       unsigned long long sum = 0;
       ++iters;
+      if (variant == 1) {  // sharp_refine_ring_kernel: ring of 4 residual rows, operands fetched one row pair ahead
+        const int uv_w = P.uv_w, row_len = 3 * uv_w;
+        std::vector<int16_t> ring((size_t)4 * row_len, (int16_t)0x7fff);
+        std::vector<wg::SharpOperands> op(uv_w), nx(uv_w);
+        for (long long e : shuffled(row_len)) wg::sharp_ring_preload(P, img, (int)e, ring.data());
+        for (long long i : shuffled(uv_w)) wg::sharp_fetch_operands(P, img, 0, (int)i, op[(size_t)i]);
+        // __syncthreads()
+        for (int jp = 0; jp < P.uv_h; ++jp) {
+          if (jp + 1 < P.uv_h)
+            for (long long i : shuffled(uv_w)) wg::sharp_fetch_operands(P, img, jp + 1, (int)i, nx[(size_t)i]);
+          const int16_t* cur = ring.data() + (size_t)(jp & 3) * row_len;
+          const int16_t* prev = jp > 0 ? ring.data() + (size_t)((jp - 1) & 3) * row_len : cur;
+          const int16_t* next = jp < P.uv_h - 1 ? ring.data() + (size_t)((jp + 1) & 3) * row_len : cur;
+          for (long long i : shuffled(uv_w))
+            sum += wg::sharp_refine_item_ring(P, img, jp, (int)i, prev, cur, next, op[(size_t)i], P.g2l, P.l2g, &keep[(size_t)3 * i]);
+          // __syncthreads()
+          for (long long i : shuffled(uv_w)) wg::sharp_commit_item_ring(P, img, jp, (int)i, ring.data(), op[(size_t)i], &keep[(size_t)3 * i]);
+          // __syncthreads()
+          op.swap(nx);
+        }
+      } else
       for (int jp = 0; jp < P.uv_h; ++jp) {
         for (long long i : shuffled(P.uv_w)) sum += wg::sharp_refine_item(P, img, jp, (int)i, P.g2l, P.l2g, &keep[(size_t)3 * i]);
         // __syncthreads()

@@ -260,16 +260,16 @@ def test_sharpyuv_kernel_code_on_cpu_matches_oracle(oracle):
         imgs = np.stack([m.case_image(w, h, i) for i in idxs])
         n = len(idxs)
         mbw, mbh = (w + 15) >> 4, (h + 15) >> 4
-        for seed in (0, 11):
+        for seed, variant in ((0, 0), (11, 0), (0, 1), (13, 1)):  # variant 1: the pipelined kernel's schedule (shared-memory ring, operands a step ahead)
             y = np.zeros((n, mbh * 16, mbw * 16), np.uint8)
             u = np.zeros((n, mbh * 8, mbw * 8), np.uint8)
             v = np.zeros_like(u)
             it = np.zeros(n, np.int32)
             L.hostcheck_sharp(imgs.ctypes.data_as(C.c_void_p), w * 4, n, w, h, C.c_uint(seed), y.ctypes.data_as(C.c_void_p),
-                              u.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), it.ctypes.data_as(C.c_void_p))
+                              u.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), it.ctypes.data_as(C.c_void_p), variant)
             for k in range(n):
                 ey, eu, ev = oracle.import_rgba(imgs[k], has_alpha=2)
-                assert np.array_equal(y[k], ey) and np.array_equal(u[k], eu) and np.array_equal(v[k], ev), (w, h, idxs[k], seed)
+                assert np.array_equal(y[k], ey) and np.array_equal(u[k], eu) and np.array_equal(v[k], ev), (w, h, idxs[k], seed, variant)
                 assert it[k] == oracle.sharp_yuv(imgs[k])[3]
 
 

@@ -153,6 +153,85 @@ WG_SHD bool sharp_stop(int iter, unsigned long long sum, unsigned long long prev
   return iter > 0 && (sum < threshold || sum > prev_sum);
 }
 
+// ---- phase 2, pipelined variant (WGPU_SHARP_VARIANT=1): the operands of a row pair that do not depend on the row pair above it
+// (its W and target samples, its target residuals, the residual row two below) are fetched one step ahead, and the residual rows
+// live in a 4-slot ring in shared memory (slot = row & 3), so the dependent path of a step has no global-memory round trip.
+struct SharpOperands {
+  uint32_t by[2], ty[2];  // two 10-bit samples per word: W and target W of the 2x2 block, upper row then lower row
+  int16_t tuv[3];         // target residuals
+  int16_t ahead[3];       // residuals of row pair jp + 2 (still as the previous sweep left them), for the ring
+};
+WG_SHD void sharp_fetch_operands(const SharpParams& P, int img, int jp, int i, SharpOperands& o) {
+  const size_t yo = ((size_t)img * P.h + 2 * jp) * P.w + 2 * i;  // even: 4-byte aligned pairs
+  for (int r = 0; r < 2; ++r) {
+    o.by[r] = *reinterpret_cast<const uint32_t*>(P.best_y + yo + (size_t)r * P.w);
+    o.ty[r] = *reinterpret_cast<const uint32_t*>(P.target_y + yo + (size_t)r * P.w);
+  }
+  const int16_t* tgt = P.target_uv + ((size_t)img * P.uv_h + jp) * 3 * P.uv_w + i;
+  for (int k = 0; k < 3; ++k) o.tuv[k] = tgt[k * P.uv_w];
+  if (jp + 2 < P.uv_h) {
+    const int16_t* a = P.best_uv + ((size_t)img * P.uv_h + jp + 2) * 3 * P.uv_w + i;
+    for (int k = 0; k < 3; ++k) o.ahead[k] = a[k * P.uv_w];
+  }
+}
+// Same arithmetic as sharp_refine_item; prev / cur / next are ring rows ([3][uv_w]), the rest comes from `o`.  Stores the four W
+// samples; the caller stores new_uv (ring + global) after the barrier.
+WG_SHD uint32_t sharp_refine_item_ring(const SharpParams& P, int img, int jp, int i, const int16_t* prev, const int16_t* cur, const int16_t* next,
+                                       const SharpOperands& o, const uint32_t* g2l, const uint32_t* l2g, int new_uv[3]) {
+  const int uv_w = P.uv_w;
+  const int il = i > 0 ? i - 1 : 0, ir = i < uv_w - 1 ? i + 1 : uv_w - 1;
+  int px[2][2][3];
+  int by[2][2], ty[2][2];
+  for (int r = 0; r < 2; ++r) {
+    by[r][0] = (int)(o.by[r] & 0xffff); by[r][1] = (int)(o.by[r] >> 16);
+    ty[r][0] = (int)(o.ty[r] & 0xffff); ty[r][1] = (int)(o.ty[r] >> 16);
+  }
+  for (int k = 0; k < 3; ++k) {
+    const int16_t* cu = cur + k * uv_w;
+    const int a = cu[i];
+    for (int r = 0; r < 2; ++r) {
+      const int16_t* q = (r ? next : prev) + k * uv_w;
+      const int b = q[i];
+      const int vl = i == 0 ? (a * 3 + b + 2) >> 2 : (a * 9 + cu[il] * 3 + b * 3 + q[il] + 8) >> 4;
+      const int vr = i == uv_w - 1 ? (a * 3 + b + 2) >> 2 : (a * 9 + cu[ir] * 3 + b * 3 + q[ir] + 8) >> 4;
+      px[r][0][k] = sharp_clip(by[r][0] + vl);
+      px[r][1][k] = sharp_clip(by[r][1] + vr);
+    }
+  }
+  uint32_t diff = 0;
+  const size_t yo = ((size_t)img * P.h + 2 * jp) * P.w + 2 * i;
+  for (int r = 0; r < 2; ++r) {
+    uint32_t packed = 0;
+    for (int c = 0; c < 2; ++c) {
+      const int d = ty[r][c] - sharp_w_of(px[r][c][0], px[r][c][1], px[r][c][2], g2l, l2g);
+      packed |= (uint32_t)sharp_clip(by[r][c] + d) << (16 * c);
+      diff += (uint32_t)(d < 0 ? -d : d);
+    }
+    *reinterpret_cast<uint32_t*>(P.best_y + yo + (size_t)r * P.w) = packed;
+  }
+  int uv[3];
+  sharp_chroma_of(px, g2l, l2g, uv);
+  for (int k = 0; k < 3; ++k) new_uv[k] = (int16_t)(cur[k * uv_w + i] + (int16_t)(o.tuv[k] - (int16_t)uv[k]));
+  return diff;
+}
+// after the barrier: the new residuals of row pair jp into its ring slot and into global memory, row pair jp + 2 into the ring
+WG_SHD void sharp_commit_item_ring(const SharpParams& P, int img, int jp, int i, int16_t* ring, const SharpOperands& o, const int new_uv[3]) {
+  const int uv_w = P.uv_w;
+  int16_t* slot = ring + (size_t)(jp & 3) * 3 * uv_w;
+  int16_t* g = P.best_uv + ((size_t)img * P.uv_h + jp) * 3 * uv_w;
+  for (int k = 0; k < 3; ++k) { slot[k * uv_w + i] = (int16_t)new_uv[k]; g[k * uv_w + i] = (int16_t)new_uv[k]; }
+  if (jp + 2 < P.uv_h) {
+    int16_t* ahead = ring + (size_t)((jp + 2) & 3) * 3 * uv_w;
+    for (int k = 0; k < 3; ++k) ahead[k * uv_w + i] = o.ahead[k];
+  }
+}
+// start of a sweep: row pairs 0 and 1 into ring slots 0 and 1 (element e of 3 * uv_w)
+WG_SHD void sharp_ring_preload(const SharpParams& P, int img, int e, int16_t* ring) {
+  const int16_t* g = P.best_uv + (size_t)img * P.uv_h * 3 * P.uv_w;
+  ring[e] = g[e];
+  if (P.uv_h > 1) ring[3 * P.uv_w + e] = g[3 * P.uv_w + e];
+}
+
 // ---- phase 3: padded 2x2 block (cx, cy) of the encoder's source planes (convertWRGBToYUV + importYCbCr)
 WG_SHD int sharp_matrix(int r, int g, int b, int c0, int c1, int c2, int offset) {  // offsets << 2, rounder 1 << 17, >> 18
   const long long v = (long long)c0 * r + (long long)c1 * g + (long long)c2 * b + ((long long)offset << 2) + (1ll << 17);
@@ -232,6 +311,72 @@ __global__ void __launch_bounds__(SHARP_THREADS) sharp_refine_kernel(const Sharp
     if (threadIdx.x == 0) {
       unsigned long long s = 0;
       for (int k = 0; k < SHARP_THREADS / 32; ++k) s += s_part[k];
+      s_sum = s;
+    }
+    __syncthreads();
+    const unsigned long long sum = s_sum;
+    if (sharp_stop(iter, sum, prev_sum, threshold)) break;
+    prev_sum = sum;
+  }
+  if (P.iterations && threadIdx.x == 0) P.iterations[img] = iters;
+}
+// Pipelined variant: 256 threads, ITEMS samples per thread (256 * ITEMS >= uv_w), dynamic shared memory = ring of 4 residual rows.
+template <int ITEMS>
+__global__ void __launch_bounds__(256) sharp_refine_ring_kernel(const SharpParams P) {
+  extern __shared__ __align__(16) int16_t s_ring[];  // [4][3][uv_w]
+  __shared__ uint32_t s_g2l[1026], s_l2g[514];
+  __shared__ unsigned long long s_part[8];
+  __shared__ unsigned long long s_sum;
+  sharp_load_tables(P, s_g2l, s_l2g);
+  const int img = blockIdx.x, uv_w = P.uv_w, row_len = 3 * uv_w;
+  const unsigned long long threshold = 3ull * (unsigned long long)P.w * (unsigned long long)P.h;
+  unsigned long long prev_sum = ~0ull;
+  int iters = 0;
+  for (int iter = 0; iter < 4; ++iter) {
+    unsigned long long mine = 0;
+    ++iters;
+    for (int e = threadIdx.x; e < row_len; e += 256) sharp_ring_preload(P, img, e, s_ring);
+    SharpOperands op[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < uv_w) sharp_fetch_operands(P, img, 0, i, op[k]);
+    }
+    __syncthreads();
+    for (int jp = 0; jp < P.uv_h; ++jp) {
+      SharpOperands nx[ITEMS];
+      if (jp + 1 < P.uv_h) {
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+          const int i = threadIdx.x + k * 256;
+          if (i < uv_w) sharp_fetch_operands(P, img, jp + 1, i, nx[k]);  // in flight while this step computes
+        }
+      }
+      const int16_t* cur = s_ring + (jp & 3) * row_len;
+      const int16_t* prev = jp > 0 ? s_ring + ((jp - 1) & 3) * row_len : cur;
+      const int16_t* next = jp < P.uv_h - 1 ? s_ring + ((jp + 1) & 3) * row_len : cur;
+      int keep[ITEMS][3];
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < uv_w) mine += sharp_refine_item_ring(P, img, jp, i, prev, cur, next, op[k], s_g2l, s_l2g, keep[k]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) {
+        const int i = threadIdx.x + k * 256;
+        if (i < uv_w) sharp_commit_item_ring(P, img, jp, i, s_ring, op[k], keep[k]);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < ITEMS; ++k) op[k] = nx[k];
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long s = 0;
+      for (int k = 0; k < 8; ++k) s += s_part[k];
       s_sum = s;
     }
     __syncthreads();

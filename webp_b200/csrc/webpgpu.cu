@@ -467,6 +467,13 @@ int enc_variant() {
 }  // namespace
 }  // extern "C++"
 
+extern "C++" {
+template <int ITEMS>
+static void launch_sharp_ring(const wg::SharpParams& P, int n, cudaStream_t st) {
+  cudaFuncSetAttribute(wg::sharp_refine_ring_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+  wg::sharp_refine_ring_kernel<ITEMS><<<(unsigned)n, 256, (size_t)24 * P.uv_w, st>>>(P);
+}
+}  // extern "C++"
 // EncoderOptions.UseSharpYUV (encode.go:531-535): sharpyuv.Convert with the WebP matrix and the sRGB transfer, then importYCbCr.
 static int enc_launch_import_sharp(wgpu_ctx* ctx) {
   const int n = ctx->e_n, pad_w = ctx->e_mbw * 16, pad_h = ctx->e_mbh * 16;
@@ -492,7 +499,16 @@ static int enc_launch_import_sharp(wgpu_ctx* ctx) {
   P.iterations = nullptr;
   const long long blocks2 = (long long)P.uv_w * P.uv_h * n;
   wg::sharp_init_kernel<<<(unsigned)std::min<long long>((blocks2 + 255) / 256, 148LL * 64), 256, 0, ctx->stream>>>(P);
-  if (P.uv_w <= 256 * wg::SHARP_ITEMS) wg::sharp_refine_kernel<256><<<(unsigned)n, 256, 0, ctx->stream>>>(P);
+  static const int variant = getenv_int("WGPU_SHARP_VARIANT", 0);  // 1: operands fetched a row pair ahead, residual rows in a shared-memory ring (experimental)
+  if (variant == 1 && P.uv_w <= 256 * wg::SHARP_ITEMS) {
+    const int items = (P.uv_w + 255) / 256;
+    if (items <= 1) launch_sharp_ring<1>(P, n, ctx->stream);
+    else if (items == 2) launch_sharp_ring<2>(P, n, ctx->stream);
+    else if (items == 3) launch_sharp_ring<3>(P, n, ctx->stream);
+    else if (items == 4) launch_sharp_ring<4>(P, n, ctx->stream);
+    else if (items <= 6) launch_sharp_ring<6>(P, n, ctx->stream);
+    else launch_sharp_ring<8>(P, n, ctx->stream);
+  } else if (P.uv_w <= 256 * wg::SHARP_ITEMS) wg::sharp_refine_kernel<256><<<(unsigned)n, 256, 0, ctx->stream>>>(P);
   else wg::sharp_refine_kernel<1024><<<(unsigned)n, 1024, 0, ctx->stream>>>(P);  // up to 8192 chroma samples per row: any WebP width
   const long long blocks3 = (long long)(pad_w / 2) * (pad_h / 2) * n;
   wg::sharp_finish_kernel<<<(unsigned)std::min<long long>((blocks3 + 255) / 256, 148LL * 64), 256, 0, ctx->stream>>>(P);
