@@ -53,6 +53,32 @@ def test_default_options_and_mapping():
     assert [getattr(d, f) for f, _ in d._fields_] == [getattr(c, f) for f, _ in c._fields_]
 
 
+def test_enc_options_layout_matches_the_header():
+    """wgpu_enc_options in include/webpgpu.h, its ctypes mirror and the oracle's config struct list the same fields in the same order
+    (a field added on one side only would silently shift every later option)."""
+    import ctypes as C, os, re, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import oracle_lib
+    text = open(os.path.join(os.path.dirname(here), "include", "webpgpu.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} wgpu_enc_options;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            ctype, names = decl.split(None, 1)
+            fields += [(n.strip(), ctype) for n in names.split(",")]
+    mirror = [(n, "float" if t is C.c_float else "int") for n, t in native.EncOptions._fields_]
+    assert fields == mirror
+    assert [n for n, _ in oracle_lib.OrcEncCfg._fields_] == [n for n, _ in fields]
+    assert C.sizeof(native.EncOptions) == 4 * len(fields)
+    o = webp_b200.DefaultOptions()
+    o.UseSharpYUV = True  # EncoderOptions.UseSharpYUV (encode.go:62) -> use_sharp_yuv
+    assert webp_b200.webp.lossy_config(o).use_sharp_yuv == 1 and webp_b200.validateConfig(o) is None
+
+
 def test_rate_control_option_mapping():
     # EncoderOptions -> lossy.EncodeConfig for the doSearch fields (encode.go:480-488): QMax -1 is the "unset" sentinel (resolveQMax)
     o = webp_b200.DefaultOptions()
