@@ -8,6 +8,8 @@
 // Three kernels: sharp_init (one thread per 2x2 block, all images), sharp_refine (one CTA per image: the refinement sweeps a
 // frame top to bottom and every row pair reads the chroma row above AFTER its update, so row pairs are a serial chain; the
 // samples of one row pair are independent and go across the CTA's threads), sharp_finish (one thread per padded 2x2 block).
+// sharp_refine_ring_kernel is the same sweep with the step's independent operands fetched one row pair ahead and the residual
+// rows in a shared-memory ring (WGPU_SHARP_VARIANT=1; bit-exact, not yet timed).
 // The per-sample code is host+device so that a CPU test harness can run the same functions in the kernels' schedule.
 #pragma once
 #include <stdint.h>
