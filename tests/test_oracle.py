@@ -209,6 +209,19 @@ def test_host_macroblock_parser_matches_oracle_on_valid_and_corrupt_streams(orac
     assert accepted > 50 and rejected > 50
 
 
+def test_encoder_sizes_stay_close_to_libwebp(oracle):
+    """Sanity anchor, not a pin: the reference is a (non bit-exact) port of libwebp, so at equal quality / method the oracle encoder's
+    file sizes should stay near libwebp's (Pillow).  Observed -7 % ... +5 %; a restatement slip in quantisation or costs moves this far more."""
+    import io
+    Image = pytest.importorskip("PIL.Image")
+    for (w, h, idx, q, m) in [(64, 48, 1, 75, 4), (128, 96, 1, 75, 4), (128, 96, 2, 50, 2), (64, 48, 1, 75, 0), (256, 192, 5, 75, 4), (320, 240, 7, 90, 6)]:
+        img = oracle.synth_image(w, h, idx)
+        b = io.BytesIO()
+        Image.fromarray(img[..., :3]).save(b, "WEBP", quality=q, method=m)
+        ratio = len(oracle.encode(img, oracle.default_cfg(quality=q, method=m))) / len(b.getvalue())
+        assert 0.85 < ratio < 1.15, (w, h, idx, q, m, ratio)
+
+
 def _sharp_golden():
     import importlib.util, json
     g = os.path.join(os.path.dirname(DATA), "golden")
