@@ -5,6 +5,7 @@
 #include "../webp_b200/csrc/host_enc.h"
 #include "../webp_b200/csrc/host_dec.h"
 #include "../webp_b200/csrc/sharp_kernels.cuh"
+#include "../webp_b200/csrc/enc_phased.cuh"
 #include <algorithm>
 #include <random>
 #include <chrono>
@@ -187,5 +188,116 @@ int hostcheck_sharp(const uint8_t* rgba, int stride, int n, int width, int heigh
     wg::sharp_finish_item(P, img, rem / (pad_w / 2), rem % (pad_w / 2));
   }
   return 0;
+}
+
+// The PRODUCT's phase-synchronous mode search (webp_b200/csrc/enc_phased.cuh, the row-parallel RD path) run on the CPU in the
+// kernel's schedule: waves in order, the CTAs of a wave one after the other, every phase as a loop over the CTA's threads in
+// shuffled order (order_seed != 0), a barrier where the kernel has one.  Inputs are what the GPU path feeds the kernel (source
+// planes, the product's own segment plan and folded cost tables); the per-macroblock output (48-byte header, 400 levels) and
+// the reconstruction planes must equal the oracle encoder's.  Returns the number of differing macroblocks; first_bad receives
+// {macroblock index, what: 1 header, 2 levels, 3 reconstruction, byte offset}.
+extern "C++" {
+template <int M, int NT>
+static void run_phased_waves(const wg::EncKernelParams& P, const wg::CostTabs& T, const uint16_t* i4cost, unsigned order_seed) {
+  std::vector<wg::PhMB> mbs(M);
+  std::vector<int> order(NT);
+  for (int i = 0; i < NT; ++i) order[i] = i;
+  std::mt19937 rng(order_seed);
+  const int waves = P.mb_w + 2 * (P.mb_h - 1);
+  for (int w = 0; w < waves; ++w) {
+    const int y_lo = std::max(0, (w - (P.mb_w - 1) + 1) >> 1), y_hi = std::min(P.mb_h - 1, w >> 1);
+    const long long tasks = (long long)(y_hi - y_lo + 1) * P.n_images;
+    if (tasks <= 0) continue;
+    std::vector<long long> ctas((size_t)((tasks + M - 1) / M));
+    for (size_t i = 0; i < ctas.size(); ++i) ctas[i] = (long long)i;
+    if (order_seed) std::shuffle(ctas.begin(), ctas.end(), rng);
+    for (long long c : ctas) {
+      if (order_seed) std::shuffle(order.begin(), order.end(), rng);
+      memset((void*)mbs.data(), 0xA5, sizeof(wg::PhMB) * M);  // shared memory starts undefined
+      wg::ph_run_cta<M, NT>(P, mbs.data(), T, i4cost, w, c * M, 0, order_seed ? order.data() : nullptr);
+    }
+  }
+}
+}  // extern "C++"
+int hostcheck_modesearch(const uint8_t* rgba, int stride, int w, int h, const OrcEncCfg2* c, unsigned order_seed, int m_per_cta, int* first_bad) {
+  orc::EncodeConfig e;
+  e.quality = c->quality; e.method = c->method; e.sns_strength = c->sns_strength; e.filter_strength = c->filter_strength;
+  e.filter_sharpness = c->filter_sharpness; e.filter_type = c->filter_type; e.partitions = c->partitions; e.segments = c->segments;
+  e.preprocessing = c->preprocessing;
+  e.pass = 1;
+  orc::Encoder* enc = new orc::Encoder();
+  enc->init(rgba, stride, w, h, e, c->has_alpha);
+  enc->encode_frame();
+  const int mbw = enc->mb_w, mbh = enc->mb_h, nmb = mbw * mbh;
+  if (c->method < 3 || mbh < 4) { delete enc; return -1; }  // not the row-parallel RD path
+  wgpu_enc_options o;
+  memset(&o, 0, sizeof(o));
+  o.quality = c->quality; o.method = c->method; o.sns_strength = c->sns_strength; o.filter_strength = c->filter_strength;
+  o.filter_sharpness = c->filter_sharpness; o.filter_type = c->filter_type; o.partitions = c->partitions; o.segments = c->segments;
+  o.preprocessing = c->preprocessing; o.has_alpha = c->has_alpha; o.passes = 1;
+  std::vector<uint8_t> segmap(nmb);
+  wgh::FramePlan fp;
+  wgh::plan_frame(&fp, o, w, h, enc->alphas.data(), (long long)enc->global_uv_alpha * nmb, segmap.data());
+  static_assert(sizeof(wgh::SegParams) == sizeof(wg::SegParams), "SegParams layout");
+  wg::ImageParams ip;
+  memcpy(&ip, fp.dev, sizeof(ip));
+  static uint16_t lc[wg::LC_SIZE], eobc[wg::EOB_SIZE], i4costs[1000];
+  wgh::build_cost_tables(wgh::kCoeffsProba0, lc, eobc);
+  wgh::compute_i4_costs(i4costs);
+  std::vector<uint8_t> ry((size_t)nmb * 256, 0xEE), ru((size_t)nmb * 64, 0xEE), rv((size_t)nmb * 64, 0xEE), hdr((size_t)nmb * 48, 0xEE);
+  std::vector<int16_t> coeffs((size_t)nmb * 400, 0x7777);
+  std::vector<uint32_t> ctxw(nmb, 0xEEEEEEEEu);
+  wg::EncKernelParams P;
+  memset(&P, 0, sizeof(P));
+  P.src_y = enc->src_y.data(); P.src_u = enc->src_u.data(); P.src_v = enc->src_v.data();
+  P.rec_y = ry.data(); P.rec_u = ru.data(); P.rec_v = rv.data();
+  P.segment = segmap.data(); P.img = &ip; P.ctx = ctxw.data();
+  P.out_hdr = hdr.data(); P.out_coeffs = coeffs.data();
+  P.i4_costs = i4costs; P.lc = lc; P.eob = eobc; P.lfc = wgh::kLevelFixedCosts;
+  P.n_images = 1; P.width = w; P.height = h; P.mb_w = mbw; P.mb_h = mbh;
+  P.method = c->method; P.max_i4_modes = c->quality < 50 ? 2 : 3;
+  P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
+  wg::CostTabs T;
+  T.lc = lc; T.eob = eobc; T.lfc = wgh::kLevelFixedCosts;
+  if (m_per_cta == 8) run_phased_waves<8, 128>(P, T, i4costs, order_seed);
+  else if (m_per_cta == 12) run_phased_waves<12, 192>(P, T, i4costs, order_seed);
+  else run_phased_waves<16, 256>(P, T, i4costs, order_seed);
+  int bad = 0;
+  for (int i = 0; i < nmb; ++i) {
+    const orc::MBInfo& m = enc->mb_info[i];
+    uint8_t hd[48];
+    memset(hd, 0, 48);
+    hd[0] = (uint8_t)m.mb_type; hd[1] = m.i16_mode; hd[2] = m.uv_mode; hd[3] = m.segment; hd[4] = m.skip; hd[5] = m.nz_dc;
+    memcpy(hd + 8, m.modes, 16); memcpy(hd + 24, m.nz_y, 16); memcpy(hd + 40, m.nz_uv, 8);
+    if (m.mb_type == 0) { hd[1] = m.i16_mode; memset(hd + 8, 0, 16); }
+    int what = 0, off = 0;
+    if (memcmp(hd, &hdr[(size_t)i * 48], 48)) { what = 1; while (hd[off] == hdr[(size_t)i * 48 + off]) ++off; }
+    else if (memcmp(m.coeffs, &coeffs[(size_t)i * 400], 800)) { what = 2; while (m.coeffs[off] == coeffs[(size_t)i * 400 + off]) ++off; }
+    else {
+      const int mx = i % mbw, my = i / mbw;
+      // the oracle (like the reference's export, encode_parallel.go:1410) writes back only the visible part of the luma block
+      const int wy = std::min(16, w - mx * 16), hy = std::min(16, h - my * 16);
+      for (int r = 0; r < hy && !what; ++r)
+        if (memcmp(&enc->y_plane[(size_t)(my * 16 + r) * enc->y_stride + mx * 16], &ry[(size_t)(my * 16 + r) * mbw * 16 + mx * 16], wy)) { what = 3; off = r; }
+      for (int r = 0; r < 8 && !what; ++r)
+        if (memcmp(&enc->u_plane[(size_t)(my * 8 + r) * enc->uv_stride + mx * 8], &ru[(size_t)(my * 8 + r) * mbw * 8 + mx * 8], 8) ||
+            memcmp(&enc->v_plane[(size_t)(my * 8 + r) * enc->uv_stride + mx * 8], &rv[(size_t)(my * 8 + r) * mbw * 8 + mx * 8], 8)) { what = 3; off = 16 + r; }
+    }
+    if (what && getenv("HOSTCHECK_DEBUG") && bad < 3) {
+      fprintf(stderr, "mb %d (%d,%d) what %d off %d\n ref:", i, i % mbw, i / mbw, what, off);
+      for (int k = 0; k < 48; ++k) fprintf(stderr, " %d", hd[k]);
+      fprintf(stderr, "\n got:");
+      for (int k = 0; k < 48; ++k) fprintf(stderr, " %d", hdr[(size_t)i * 48 + k]);
+      fprintf(stderr, "\n");
+    }
+    if (what) {
+      if (!bad && first_bad) { first_bad[0] = i; first_bad[1] = what; first_bad[2] = off; first_bad[3] = m.mb_type; }
+      ++bad;
+    }
+  }
+  int seg_bad = 0;
+  for (int i = 0; i < nmb; ++i) seg_bad += segmap[i] != enc->mb_info[i].segment;
+  delete enc;
+  return bad + seg_bad;
 }
 }

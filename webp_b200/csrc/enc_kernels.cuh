@@ -8,47 +8,9 @@
 // warp per macroblock, block rows staged in shared memory in the reference's BPS=32 work-buffer
 // layout (internal/lossy/constants.go:66-75).
 #pragma once
-#include "vp8_dev.cuh"
+#include "enc_common.cuh"
 
 namespace wg {
-
-enum { BPS = 32, YUV_SIZE = BPS * 17 + BPS * 9, Y_OFF = BPS + 8, U_OFF = Y_OFF + BPS * 16 + BPS, V_OFF = U_OFF + 16 };
-
-struct ImageParams {  // per image, written by the host after segmentation
-  SegParams seg[4];
-};
-
-struct EncKernelParams {
-  const uint8_t* src_y; const uint8_t* src_u; const uint8_t* src_v;  // padded source planes [n][..]
-  uint8_t* rec_y; uint8_t* rec_u; uint8_t* rec_v;                    // padded reconstruction planes
-  const uint8_t* segment;       // [n][nmb]
-  const ImageParams* img;       // [n]
-  uint32_t* ctx;                // [n][nmb] packed NZ context (see pack_ctx)
-  int8_t* top_derr;             // [n][mb_w][2][2] serial RD path: DC error diffusion state (enc.topDerr)
-  int8_t* left_derr;            // [n][2][2] (enc.leftDerr)
-  const uint16_t* lc_img;       // [n][LC_SIZE] per-image folded level costs (serial path with probability refreshes), or null
-  const uint16_t* eob_img;      // [n][EOB_SIZE]
-  int serial_gpw;               // encode_serial_tab_kernel: macroblock groups (images) per warp actually used, 1..32/G (0 = all)
-  uint32_t* ctx2;               // [n][nmb] Method < 3 / serial RD: trial 4x4 modes of the bottom row / right column (mode-cost context)
-  int* progress;                // [n][mb_h] finished macroblocks per row (persistent kernel)
-  unsigned long long* work_counter;  // next group to claim (persistent kernel)
-  const long long* wave_start;  // [waves + 1] prefix of groups per wave (persistent kernel)
-  long long total_groups;
-  int* error_flag;              // set when a dependency wait exceeded its iteration cap
-  unsigned int* stats;          // [n][4][8][3][11][2] token statistics (ProbaStats, encode_proba.go), zeroed before the waves
-  uint8_t* out_hdr;             // [n][nmb][48]: mb_type,i16,uv,segment,skip,nz_dc,0,0, modes[16], nz[24]
-  int16_t* out_coeffs;          // [n][nmb][400]
-  const uint16_t* i4_costs;     // [10][10][10]
-  const uint16_t* lc; const uint16_t* eob; const uint16_t* lfc;  // folded cost tables (vp8_dev.cuh CostTabs), global
-  int n_images, width, height, mb_w, mb_h;
-  int method, max_i4_modes;
-  size_t y_plane, uv_plane;     // bytes per image plane
-};
-
-// ctx word: bits 0-7 out_t (4 Y, 2 U, 2 V), 8-15 out_l, 16 top-DC carry, 17 left-DC carry
-__device__ __forceinline__ uint32_t pack_ctx(uint32_t out_t, uint32_t out_l, int top_dc, int left_dc) {
-  return (out_t & 0xff) | ((out_l & 0xff) << 8) | ((uint32_t)top_dc << 16) | ((uint32_t)left_dc << 17);
-}
 
 struct I4Cand {
   unsigned long long score;
@@ -124,14 +86,6 @@ __device__ __forceinline__ void load_pred4_ctx(const uint8_t* p, int* e) {  // p
   e[9] = p[-1]; e[10] = p[-1 + BPS]; e[11] = p[-1 + 2 * BPS]; e[12] = p[-1 + 3 * BPS];
 }
 
-// checkMode (internal/lossy/decode_frame.go:6)
-__device__ __forceinline__ int check_mode(int mx, int my, int mode) {
-  if (mode == 0) {
-    if (mx == 0) return my == 0 ? 6 : 5;
-    if (my == 0) return 4;
-  }
-  return mode;
-}
 // Cooperative square predictor into buf at off (predict_lossy.go:27-181); modes 0..6.
 template <int G>
 __device__ __noinline__ void pred_square_coop(int gl, int mode, uint8_t* buf, int off, int size) {
@@ -165,19 +119,7 @@ __device__ __noinline__ void pred_square_coop(int gl, int mode, uint8_t* buf, in
   }
 }
 
-__device__ __forceinline__ bool needs_top4(int m) { return m == 1 || m == 2 || m == 4 || m == 5 || m == 6 || m == 7 || m == 8; }
-__device__ __forceinline__ bool needs_left4(int m) { return m == 1 || m == 3 || m == 4 || m == 8 || m == 9; }
-
-// modeFixedCost16 / modeFixedCostUV (internal/lossy/encode_analysis.go:1481,1485)
-__device__ __forceinline__ int kModeFixedCost16(int m) { return m == 0 ? 663 : (m == 2 ? 872 : 919); }
-__device__ __forceinline__ int kModeFixedCostUV(int m) { return m == 0 ? 302 : (m == 1 ? 984 : (m == 2 ? 439 : 642)); }
-
-__device__ __forceinline__ unsigned long long rd_score(int disto, int rate, int lambda) {
-  return (unsigned long long)(long long)rate * (unsigned long long)(long long)lambda + 256ull * (unsigned long long)(long long)disto;
-}
-
 // collectCoeffStats (internal/lossy/encode_proba.go:10-113) with red.global increments; levels int16 (or int) raster order.
-enum { STATS_SIZE = 4 * 8 * 3 * 11 * 2 };
 template <class LevT>
 __device__ __forceinline__ void stat_block_dev(const LevT* lev, int n_coeffs, int type, int first, int ctx, unsigned int* st, bool) {
   auto add = [&](int band, int c, int p, int bit) { atomicAdd(st + ((((type * 8 + band) * 3 + c) * 11 + p) << 1) + bit, 1u); };
@@ -1259,6 +1201,58 @@ __global__ void __launch_bounds__(128) collect_all_stats_kernel(const AllStatsPa
       lnz = (lnz >> 1) | (l << 5);
     }
   }
+}
+
+// Token statistics of the row-parallel path (collectMBStats, encode_parallel.go:1606-1707; collectCoeffStats,
+// encode_proba.go:10-113) after the waves: one (macroblock, block) pair per thread, contexts exactly as the mode search
+// held them (neighbour flags from the NZ context words it wrote, in-macroblock flags from the header's nz counts; a skipped
+// macroblock contributes nothing).  Counts go to a per-CTA shared-memory histogram first: a CTA covers macroblocks of one
+// image, so the 2112 counters of an image see one global atomic per CTA and counter instead of one per token.
+struct MBStatsParams {
+  const uint8_t* hdr;      // [n][nmb][48]
+  const int16_t* coeffs;   // [n][nmb][400]
+  const uint32_t* ctxw;    // [n][nmb]
+  unsigned int* stats;     // [n][STATS_SIZE], zeroed before
+  int mb_w, mb_h, mbs_per_cta;
+};
+__global__ void __launch_bounds__(256) mb_stats_kernel(const MBStatsParams P) {
+  __shared__ unsigned int s_hist[STATS_SIZE];
+  for (int i = threadIdx.x; i < STATS_SIZE; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const int nmb = P.mb_w * P.mb_h, img = blockIdx.y;
+  const int first_mb = blockIdx.x * P.mbs_per_cta, count = min(P.mbs_per_cta, nmb - first_mb);
+  const uint8_t* H = P.hdr + (size_t)img * nmb * 48;
+  const uint32_t* CW = P.ctxw + (size_t)img * nmb;
+  for (int t = threadIdx.x; t < count * 25; t += blockDim.x) {
+    const int mb = first_mb + t / 25, b = t % 25;
+    const uint8_t* h = H + (size_t)mb * 48;
+    if (h[4]) continue;
+    const bool use_i4 = h[0] == 1;
+    const int my = mb / P.mb_w, mx = mb - my * P.mb_w;
+    uint32_t top_nz = 0, left_nz = 0;
+    int top_dc = 0, left_dc = 0;
+    if (my > 0) { const uint32_t cw = CW[mb - P.mb_w]; top_nz = cw & 0xff; top_dc = (cw >> 16) & 1; }
+    if (mx > 0) { const uint32_t cw = CW[mb - 1]; left_nz = (cw >> 8) & 0xff; left_dc = (cw >> 17) & 1; }
+    const int16_t* c = P.coeffs + ((size_t)img * nmb + mb) * 400;
+    if (b == 24) {
+      if (!use_i4) stat_block_dev(c + 384, (int)h[5], 1, 0, min(top_dc + left_dc, 2), s_hist, true);
+    } else if (b < 16) {
+      const int bx = b & 3, by = b >> 2;
+      const int l = bx > 0 ? (h[24 + b - 1] > 0) : ((left_nz >> by) & 1);
+      const int tt = by > 0 ? (h[24 + b - 4] > 0) : ((top_nz >> bx) & 1);
+      stat_block_dev(c + b * 16, (int)h[24 + b], use_i4 ? 3 : 0, use_i4 ? 0 : 1, l + tt, s_hist, false);
+    } else {
+      const int k = b - 16, ch = k >> 2, bx = k & 1, by = (k >> 1) & 1;
+      const uint32_t tn = (top_nz >> (4 + 2 * ch)) & 3, ln = (left_nz >> (4 + 2 * ch)) & 3;
+      const int l = bx > 0 ? (h[24 + b - 1] > 0) : ((ln >> by) & 1);
+      const int tt = by > 0 ? (h[24 + b - 2] > 0) : ((tn >> bx) & 1);
+      stat_block_dev(c + b * 16, (int)h[24 + b], 2, 0, l + tt, s_hist, false);
+    }
+  }
+  __syncthreads();
+  unsigned int* st = P.stats + (size_t)img * STATS_SIZE;
+  for (int i = threadIdx.x; i < STATS_SIZE; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(st + i, s_hist[i]);
 }
 
 // Serial RD path (Method >= 3 where the reference does not go row-parallel): macroblocks in raster order, one launch per

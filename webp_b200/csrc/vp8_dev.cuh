@@ -4,18 +4,53 @@
 // intermediate ranges fit int32 (|coeff| <= 2048+sharpen, residual <= 255).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#define WG_HD __host__ __device__ __forceinline__
+#else
+#include <algorithm>
+#define WG_HD inline
+#endif
 
 namespace wg {
+#ifndef __CUDACC__
+// by value (std::min / std::max return references to their arguments, temporaries included)
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+#endif
 
 #include "vp8_tables.inc"  // host-visible copies (static const); device copies below
 
 // ---- tables in device global memory (L1/L2 cached); hot kernels stage them into shared memory
-__device__ __constant__ uint8_t c_zigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
-__device__ __constant__ uint8_t c_bands[17] = {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0};
-__device__ __constant__ uint8_t c_rev_zigzag[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15};
-__device__ __constant__ uint8_t c_weight_y[16] = {38, 32, 20, 9, 32, 28, 17, 7, 20, 17, 10, 4, 9, 7, 4, 2};
-__device__ __constant__ uint8_t c_weight_trellis[16] = {30, 27, 19, 11, 27, 24, 17, 10, 19, 17, 12, 8, 11, 10, 8, 6};
+// The per-block routines below are host+device (WG_HD) so that a CPU harness (oracle/hostcheck.cc) can run the kernels' code
+// in the kernels' schedule; on the host the small tables are plain static arrays.
+#define WG_TAB_ZIGZAG {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15}
+#define WG_TAB_BANDS {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0}
+#define WG_TAB_REV_ZIGZAG {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15}
+#define WG_TAB_WEIGHT_Y {38, 32, 20, 9, 32, 28, 17, 7, 20, 17, 10, 4, 9, 7, 4, 2}
+#define WG_TAB_WEIGHT_TRELLIS {30, 27, 19, 11, 27, 24, 17, 10, 19, 17, 12, 8, 11, 10, 8, 6}
+#ifdef __CUDACC__
+__device__ __constant__ uint8_t c_zigzag_d[16] = WG_TAB_ZIGZAG;
+__device__ __constant__ uint8_t c_bands_d[17] = WG_TAB_BANDS;
+__device__ __constant__ uint8_t c_rev_zigzag_d[16] = WG_TAB_REV_ZIGZAG;
+__device__ __constant__ uint8_t c_weight_trellis_d[16] = WG_TAB_WEIGHT_TRELLIS;
+#endif
+static const uint8_t c_zigzag_h[16] = WG_TAB_ZIGZAG;
+static const uint8_t c_bands_h[17] = WG_TAB_BANDS;
+static const uint8_t c_rev_zigzag_h[16] = WG_TAB_REV_ZIGZAG;
+static const uint8_t c_weight_trellis_h[16] = WG_TAB_WEIGHT_TRELLIS;
+#ifdef __CUDA_ARCH__
+#define c_zigzag c_zigzag_d
+#define c_bands c_bands_d
+#define c_rev_zigzag c_rev_zigzag_d
+#define c_weight_trellis c_weight_trellis_d
+#else
+#define c_zigzag c_zigzag_h
+#define c_bands c_bands_h
+#define c_rev_zigzag c_rev_zigzag_h
+#define c_weight_trellis c_weight_trellis_h
+#endif
 
 // Cost tables a kernel uses (global or shared memory).  On the reference's row-parallel path the coefficient
 // probabilities are the constant defaults (encode_parallel.go:1558-1567), so everything TokenCostForCoeffs and
@@ -43,12 +78,12 @@ struct SegParams {
   int flags;  // seg[0] only, serial rate-control passes: bits 0-7 per-image max I4 RD modes (0 = launch default), bit 8 = image parked
 };
 
-__device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
-__device__ __forceinline__ int mul1(int a) { return ((a * 20091) >> 16) + a; }  // transforms.go:20
-__device__ __forceinline__ int mul2(int a) { return (a * 35468) >> 16; }        // transforms.go:25
+WG_HD int clip8(int v) { return min(max(v, 0), 255); }
+WG_HD int mul1(int a) { return ((a * 20091) >> 16) + a; }  // transforms.go:20
+WG_HD int mul2(int a) { return (a * 35468) >> 16; }        // transforms.go:25
 
 // fTransform (internal/dsp/transforms.go:371): src - ref -> 16 coefficients
-__device__ __forceinline__ void ftransform(const int* src, const int* ref, int* out) {
+WG_HD void ftransform(const int* src, const int* ref, int* out) {
   int tmp[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -71,7 +106,7 @@ __device__ __forceinline__ void ftransform(const int* src, const int* ref, int* 
   }
 }
 // iTransformOne (internal/dsp/transforms.go:265): dst = clip(ref + IDCT(in)); dst may alias ref
-__device__ __forceinline__ void itransform(const int* ref, const int* in, int* dst) {
+WG_HD void itransform(const int* ref, const int* in, int* dst) {
   int tmp[16];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -97,7 +132,7 @@ __device__ __forceinline__ void itransform(const int* ref, const int* in, int* d
   }
 }
 // fTransformWHT (transforms.go:500): flat 4x4 DCs -> 16
-__device__ __forceinline__ void fwht(const int* in, int* out) {
+WG_HD void fwht(const int* in, int* out) {
   int tmp[16];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -120,7 +155,7 @@ __device__ __forceinline__ void fwht(const int* in, int* out) {
 }
 // transformWHT (transforms.go:223); out[b] = DC of block b (the reference's stride-16 layout, flattened);
 // values are truncated to int16 as the reference stores them.
-__device__ __forceinline__ void iwht(const int* in, int* out) {
+WG_HD void iwht(const int* in, int* out) {
   int tmp[16];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -142,7 +177,7 @@ __device__ __forceinline__ void iwht(const int* in, int* out) {
     out[i * 4 + 3] = (int)(int16_t)((a3 - a2) >> 3);
   }
 }
-__device__ __forceinline__ int sse16(const int* a, const int* b) {  // ssim.go:188
+WG_HD int sse16(const int* a, const int* b) {  // ssim.go:188
   int s = 0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -151,7 +186,7 @@ __device__ __forceinline__ int sse16(const int* a, const int* b) {  // ssim.go:1
   }
   return s;
 }
-__device__ __forceinline__ int ttransform(const int* in) {  // ssim.go:266 with kWeightY
+WG_HD int ttransform(const int* in) {  // ssim.go:266 with kWeightY
   int tmp[16];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -172,14 +207,14 @@ __device__ __forceinline__ int ttransform(const int* in) {  // ssim.go:266 with 
   }
   return sum;
 }
-__device__ __forceinline__ int tdisto4x4(const int* a, const int* b) {  // ssim.go:315
+WG_HD int tdisto4x4(const int* a, const int* b) {  // ssim.go:315
   return abs(ttransform(b) - ttransform(a)) >> 5;
 }
 
 // PredLuma4Direct (internal/dsp/predict_lossy.go:185-451).  e[0]=top-left, e[1..8]=top[0..7], e[9..12]=left[0..3]
-__device__ __forceinline__ int avg3(int a, int b, int c) { return (a + 2 * b + c + 2) >> 2; }
-__device__ __forceinline__ int avg2(int a, int b) { return (a + b + 1) >> 1; }
-__device__ __forceinline__ void pred4(int mode, const int* e, int* d) {
+WG_HD int avg3(int a, int b, int c) { return (a + 2 * b + c + 2) >> 2; }
+WG_HD int avg2(int a, int b) { return (a + b + 1) >> 1; }
+WG_HD void pred4(int mode, const int* e, int* d) {
   const int tl = e[0], t0 = e[1], t1 = e[2], t2 = e[3], t3 = e[4], t4 = e[5], t5 = e[6], t6 = e[7], t7 = e[8];
   const int l0 = e[9], l1 = e[10], l2 = e[11], l3 = e[12];
 #define D(x, y) d[(x) + 4 * (y)]
@@ -274,7 +309,7 @@ __device__ __forceinline__ void pred4(int mode, const int* e, int* d) {
 }
 
 // quantizeCoeffsGo (internal/lossy/encode_quant.go:16): returns zigzag last-nz + 1
-__device__ __forceinline__ int quantize_block(const int* in, int* out, const SegQuant& sq, int first) {
+WG_HD int quantize_block(const int* in, int* out, const SegQuant& sq, int first) {
   int max_zz = -1;
 #pragma unroll
   for (int n = 0; n < 16; ++n) {
@@ -293,7 +328,7 @@ __device__ __forceinline__ int quantize_block(const int* in, int* out, const Seg
   return max_zz + 1;
 }
 // dequantCoeffsGo (encode_quant.go:81): int16 truncation kept
-__device__ __forceinline__ void dequant_block(const int* in, int* out, const SegQuant& sq) {
+WG_HD void dequant_block(const int* in, int* out, const SegQuant& sq) {
   out[0] = (int)(int16_t)(in[0] * sq.dc_quant);
 #pragma unroll
   for (int n = 1; n < 16; ++n) out[n] = (int)(int16_t)(in[n] * sq.quant);
@@ -303,7 +338,7 @@ __device__ __forceinline__ void dequant_block(const int* in, int* out, const Seg
 // extra LDS here: the mode-search kernel is instruction-fetch bound when primitives are unrolled and inlined at every
 // call site (L0 I-cache ~6 KB, L1.5 32 KB; profiles/README.md).
 template <class LevT>
-__device__ __forceinline__ int quantize_smem(LevT* io, const SegQuant& sq, int first) {  // quantizeCoeffsGo, encode_quant.go:16
+WG_HD int quantize_smem(LevT* io, const SegQuant& sq, int first) {  // quantizeCoeffsGo, encode_quant.go:16
   int max_zz = -1;
   if (first != 0) io[0] = 0;
 #pragma unroll 1
@@ -320,7 +355,7 @@ __device__ __forceinline__ int quantize_smem(LevT* io, const SegQuant& sq, int f
   return max_zz + 1;
 }
 template <class LevT>
-__device__ __forceinline__ int token_cost_smem(const LevT* lev, int nz_count, int type, int ctx0, int first, const CostTabs& T) {
+WG_HD int token_cost_smem(const LevT* lev, int nz_count, int type, int ctx0, int first, const CostTabs& T) {
   const uint16_t* lc = T.lc + type * (8 * 3 * LC_LEVELS);
   const uint16_t* eob = T.eob + type * (8 * 3);
   if (nz_count <= first) return eob[c_bands[first] * 3 + ctx0];
@@ -337,7 +372,7 @@ __device__ __forceinline__ int token_cost_smem(const LevT* lev, int nz_count, in
 
 // TokenCostForCoeffs (encode_quant.go:170); levels in raster order.  Per coefficient: one folded-table lookup
 // (+ the fixed level cost); note the reference charges the not-EOB bit at every position up to the last non-zero.
-__device__ __forceinline__ int token_cost(const int* lev, int nz_count, int type, int ctx0, int first, const CostTabs& T) {
+WG_HD int token_cost(const int* lev, int nz_count, int type, int ctx0, int first, const CostTabs& T) {
   const uint16_t* lc = T.lc + type * (8 * 3 * LC_LEVELS);
   const uint16_t* eob = T.eob + type * (8 * 3);
   if (nz_count <= first) return eob[c_bands[first] * 3 + ctx0];
@@ -366,7 +401,7 @@ __device__ __forceinline__ int token_cost(const int* lev, int nz_count, int type
 // Scores are int64 as in the reference.  An unreachable state carries kBig (the reference's kMaxScore = 1<<60); real
 // scores stay below 2^50, so >= kThr means "not valid" and transitions out of an unreachable state can never beat a
 // reachable one -- the reference's `if (!prev[pc].valid) continue` without a branch.
-__device__ __forceinline__ int trellis_block_smem(int16_t* io, const SegQuant& sq, int first, int type, int initial_ctx,
+WG_HD int trellis_block_smem(int16_t* io, const SegQuant& sq, int first, int type, int initial_ctx,
                                                   int lambda, const CostTabs& T) {
   const int quant_ac = sq.quant, quant_dc = sq.dc_quant;
   const unsigned iq_ac = (unsigned)sq.iquant, iq_dc = (unsigned)sq.dc_iquant;

@@ -15,6 +15,7 @@
 #include "../../include/webpgpu.h"
 #include "misc_kernels.cuh"
 #include "token_kernels.cuh"
+#include "enc_phased.cuh"
 #include "dec_parse.cuh"
 #include "sharp_kernels.cuh"
 #include "host_dec.h"
@@ -459,6 +460,43 @@ int launch_enc_persistent(wgpu_ctx* ctx, wg::EncKernelParams& P) {
   ctx->enc_persistent_used = true;
   return WGPU_OK;
 }
+// Row-parallel RD path: the phase-synchronous kernel (enc_phased.cuh).  M macroblocks per CTA, 16 threads per macroblock;
+// narrow waves take smaller CTAs so that they still spread over the SMs.  Token statistics follow in one pass (mb_stats_kernel).
+template <int M, int MINB>
+int launch_phased_wave(wgpu_ctx* ctx, const wg::EncKernelParams& P, int w, long long tasks) {
+  constexpr int NT = M * 16;
+  constexpr size_t smem = sizeof(wg::PhMB) * M;
+  cudaError_t e = cudaFuncSetAttribute(wg::encode_phased_kernel<M, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
+  wg::encode_phased_kernel<M, NT, MINB><<<(unsigned)((tasks + M - 1) / M), NT, smem, ctx->stream>>>(P, w);
+  ctx->launches++;
+  return WGPU_OK;
+}
+int launch_enc_phased(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->dev);
+  static const int force_m = getenv_int("WGPU_PHASED_M", 0);
+  const int waves = P.mb_w + 2 * (P.mb_h - 1);
+  for (int w = 0; w < waves; ++w) {
+    const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
+    if (tasks <= 0) continue;  // one macroblock column: odd waves hold no macroblock (x = w - 2y)
+    int rc;
+    const int m = force_m ? force_m : (tasks <= (long long)sm_count * 4 * 6 ? 4 : (tasks <= (long long)sm_count * 8 * 4 ? 8 : 16));
+    if (m == 4) rc = launch_phased_wave<4, 6>(ctx, P, w, tasks);
+    else if (m == 8) rc = launch_phased_wave<8, 4>(ctx, P, w, tasks);
+    else rc = launch_phased_wave<16, 3>(ctx, P, w, tasks);
+    if (rc) return rc;
+  }
+  if (P.stats) {
+    wg::MBStatsParams S;
+    S.hdr = P.out_hdr; S.coeffs = P.out_coeffs; S.ctxw = P.ctx; S.stats = P.stats; S.mb_w = P.mb_w; S.mb_h = P.mb_h;
+    S.mbs_per_cta = 128;
+    const int nmb = P.mb_w * P.mb_h;
+    wg::mb_stats_kernel<<<dim3((unsigned)((nmb + S.mbs_per_cta - 1) / S.mbs_per_cta), (unsigned)P.n_images), 256, 0, ctx->stream>>>(S);
+    ctx->launches++;
+  }
+  return WGPU_OK;
+}
 int enc_variant() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("WGPU_ENC_VARIANT"); v = e ? atoi(e) : 0; }
@@ -690,7 +728,8 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
     case 6: rc = launch_enc_waves_fn<8, 4>(ctx, P, wg::encode_wave_kernel_gt<8, 4, 160>); break;  // tables through L1, 3 CTAs/SM
     case 7: rc = launch_enc_waves_fn<8, 12>(ctx, P, wg::encode_wave_kernel_big<8, 12, false>); break;  // one 12-warp CTA per SM
     case 8: rc = launch_enc_waves_fn<8, 12>(ctx, P, wg::encode_wave_kernel_big<8, 12, true>); break;   // + CTA-wide step barriers
-    default: rc = launch_enc_waves<8, 4, 3>(ctx, P); break;  // 168 regs, 3 CTAs/SM = 48 macroblocks/SM (measured best)
+    case 9: rc = launch_enc_waves<8, 4, 3>(ctx, P); break;  // round-1 wavefront kernel: 8 lanes per macroblock, 3 CTAs/SM
+    default: rc = launch_enc_phased(ctx, P); break;
   }
   if (rc) return rc;
   CK(cudaGetLastError());
