@@ -72,6 +72,11 @@ WG_HD void ph_store4x4(uint8_t* p, const int* d) {
   for (int j = 0; j < 4; ++j)
     ph_st32(p + j * STRIDE, (uint32_t)d[4 * j] | ((uint32_t)d[4 * j + 1] << 8) | ((uint32_t)d[4 * j + 2] << 16) | ((uint32_t)d[4 * j + 3] << 24));
 }
+WG_HD void ph_store_lev(int16_t* lev, const int* q) {  // lev 4-byte aligned
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    ph_st32(reinterpret_cast<uint8_t*>(lev) + 4 * i, ((uint32_t)q[2 * i] & 0xffffu) | ((uint32_t)q[2 * i + 1] << 16));
+}
 // source block b of the compact `in` buffer: luma 0..15 (stride 16), chroma 16..23 (U at 256, V at 320, stride 8)
 WG_HD void ph_load_src(const uint8_t* in, int b, int* d) {
   if (b < 16) ph_load4x4<16>(in + (b >> 2) * 64 + (b & 3) * 4, d);
@@ -315,16 +320,15 @@ WG_HD void ph_search_a(const EncKernelParams& P, PhMB* mbs, int pass, int tid) {
     ph_pred_of_block(S, b, mode, p);
     ftransform(s, p, c);
     int16_t* lev = Q.lev[m2][b];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) lev[i] = (int16_t)c[i];
+    int q[16];
     if (b < 16) {
       Q.dc[m2][b] = c[0];
-      Q.nz[m2][b] = (uint8_t)quantize_smem(lev, seg.y1, 1);
+      Q.nz[m2][b] = (uint8_t)quantize_block(c, q, seg.y1, 1);
+      ph_store_lev(lev, q);
     } else {
-      Q.nz[m2][b] = (uint8_t)quantize_smem(lev, seg.uv, 0);
-      int q[16], dq[16], r[16], ac = 0;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) q[i] = lev[i];
+      Q.nz[m2][b] = (uint8_t)quantize_block(c, q, seg.uv, 0);
+      ph_store_lev(lev, q);
+      int dq[16], r[16], ac = 0;
 #pragma unroll
       for (int i = 1; i < 16; ++i) ac += (q[i] != 0);
       dequant_block(q, dq, seg.uv);
@@ -542,7 +546,7 @@ WG_HD void ph_i4_rd(const EncKernelParams& P, PhMB* mbs, const CostTabs& T, cons
     int16_t* lev = W.lev[k];
 #pragma unroll
     for (int i = 0; i < 16; ++i) lev[i] = (int16_t)c[i];
-    const int nz = (P.method >= 4) ? trellis_block_smem(lev, seg.y1, 0, 3, nz_ctx, seg.tlambda_i4, T) : quantize_smem(lev, seg.y1, 0);
+    const int nz = (P.method >= 4) ? trellis_block_v2(lev, seg.y1, 0, 3, nz_ctx, seg.tlambda_i4, T) : quantize_smem(lev, seg.y1, 0);
 #pragma unroll
     for (int i = 0; i < 16; ++i) q[i] = lev[i];
     dequant_block(q, dq, seg.y1);
@@ -637,14 +641,11 @@ WG_HD void ph_final_transform(const EncKernelParams& P, PhMB* mbs, int tid) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) lev[i] = (int16_t)c[i];
     } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) lev[i] = (int16_t)c[i];
-      const int nz = quantize_smem(lev, seg.uv, 0);
+      int q[16], dq[16], r[16];
+      const int nz = quantize_block(c, q, seg.uv, 0);
+      ph_store_lev(lev, q);
       F.nz[b] = (uint8_t)nz;
       S.hdr[24 + b] = (uint8_t)nz;
-      int q[16], dq[16], r[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) q[i] = lev[i];
       dequant_block(q, dq, seg.uv);
       itransform(p, dq, r);
       ph_store4x4<BPS>(S.out + ph_block_off(b), r);
@@ -692,7 +693,7 @@ WG_HD void ph_final_i16_levels(const EncKernelParams& P, PhMB* mbs, const CostTa
       const int bx = b & 3, by = b >> 2;
       const int l = bx > 0 ? (F.nz[b - 1] > 0) : ((S.left_nz >> by) & 1);
       const int tt = by > 0 ? (F.nz[b - 4] > 0) : ((S.top_nz >> bx) & 1);
-      nz = trellis_block_smem(F.lev[b], seg.y1, 1, 0, l + tt, seg.tlambda_i16, T);
+      nz = trellis_block_v2(F.lev[b], seg.y1, 1, 0, l + tt, seg.tlambda_i16, T);
     }
     F.nz[b] = (uint8_t)nz;
     S.hdr[24 + b] = (uint8_t)nz;

@@ -462,9 +462,8 @@ int launch_enc_persistent(wgpu_ctx* ctx, wg::EncKernelParams& P) {
 }
 // Row-parallel RD path: the phase-synchronous kernel (enc_phased.cuh).  M macroblocks per CTA, 16 threads per macroblock;
 // narrow waves take smaller CTAs so that they still spread over the SMs.  Token statistics follow in one pass (mb_stats_kernel).
-template <int M, int MINB>
+template <int M, int NT, int MINB>
 int launch_phased_wave(wgpu_ctx* ctx, const wg::EncKernelParams& P, int w, long long tasks) {
-  constexpr int NT = M * 16;
   constexpr size_t smem = sizeof(wg::PhMB) * M;
   cudaError_t e = cudaFuncSetAttribute(wg::encode_phased_kernel<M, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
@@ -475,16 +474,18 @@ int launch_phased_wave(wgpu_ctx* ctx, const wg::EncKernelParams& P, int w, long 
 int launch_enc_phased(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->dev);
-  static const int force_m = getenv_int("WGPU_PHASED_M", 0);
+  static const int cfg = getenv_int("WGPU_PHASED_CFG", 0);  // tuning knob: CTA shape of the wide waves
   const int waves = P.mb_w + 2 * (P.mb_h - 1);
   for (int w = 0; w < waves; ++w) {
     const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
     if (tasks <= 0) continue;  // one macroblock column: odd waves hold no macroblock (x = w - 2y)
     int rc;
-    const int m = force_m ? force_m : (tasks <= (long long)sm_count * 4 * 6 ? 4 : (tasks <= (long long)sm_count * 8 * 4 ? 8 : 16));
-    if (m == 4) rc = launch_phased_wave<4, 6>(ctx, P, w, tasks);
-    else if (m == 8) rc = launch_phased_wave<8, 4>(ctx, P, w, tasks);
-    else rc = launch_phased_wave<16, 3>(ctx, P, w, tasks);
+    if (cfg == 1) rc = launch_phased_wave<16, 128, 3>(ctx, P, w, tasks);
+    else if (cfg == 2) rc = launch_phased_wave<8, 64, 4>(ctx, P, w, tasks);
+    else if (cfg == 3) rc = launch_phased_wave<8, 128, 4>(ctx, P, w, tasks);
+    else if (cfg == 4) rc = launch_phased_wave<16, 192, 3>(ctx, P, w, tasks);
+    else if (tasks <= (long long)sm_count * 8 * 4) rc = launch_phased_wave<8, 128, 4>(ctx, P, w, tasks);
+    else rc = launch_phased_wave<16, 256, 3>(ctx, P, w, tasks);
     if (rc) return rc;
   }
   if (P.stats) {
