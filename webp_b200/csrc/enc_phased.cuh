@@ -24,9 +24,11 @@ namespace wg {
 
 #ifdef __CUDA_ARCH__
 #define WG_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define WG_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define WG_POPC(x) __popc(x)
 #else
 #define WG_ATOMIC_ADD(p, v) (*(p) += (v))
+#define WG_ATOMIC_OR(p, v) (*(p) |= (v))
 #define WG_POPC(x) __builtin_popcount(x)
 #endif
 
@@ -76,6 +78,13 @@ WG_HD void ph_store_lev(int16_t* lev, const int* q) {  // lev 4-byte aligned
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     ph_st32(reinterpret_cast<uint8_t*>(lev) + 4 * i, ((uint32_t)q[2 * i] & 0xffffu) | ((uint32_t)q[2 * i + 1] << 16));
+}
+WG_HD void ph_load_lev(const int16_t* lev, int* q) {  // lev 4-byte aligned
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t w = ph_ld32(reinterpret_cast<const uint8_t*>(lev) + 4 * i);
+    q[2 * i] = (int)(int16_t)(w & 0xffffu); q[2 * i + 1] = (int)(int16_t)(w >> 16);
+  }
 }
 // source block b of the compact `in` buffer: luma 0..15 (stride 16), chroma 16..23 (U at 256, V at 320, stride 8)
 WG_HD void ph_load_src(const uint8_t* in, int b, int* d) {
@@ -160,7 +169,7 @@ struct alignas(16) PhMB {
   int top_nz, left_nz, top_nz_dc, left_nz_dc;
   uint8_t top_modes[4], left_modes[4];
   int dcv[3];
-  int src_flat, best16, best_uv, use_i4, nz_dc, alive;
+  int src_flat, best16, best_uv, use_i4, nz_dc;
   unsigned long long score16;
   int tot_rate, tot_disto, tot_hdr;
   uint32_t nzmask, modes_lo, modes_hi;
@@ -352,16 +361,11 @@ WG_HD void ph_search_b(const EncKernelParams& P, PhMB* mbs, const CostTabs& T, i
 #pragma unroll
     for (int i = 0; i < 16; ++i) d[i] = Q.dc[m2][i];
     fwht(d, w);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) Q.dc[m2][i] = w[i];
-    const int nz_dc = quantize_smem(Q.dc[m2], seg.y2, 0);
-    Q.acc.rate16[mode] = kModeFixedCost16(mode) + token_cost_smem(Q.dc[m2], nz_dc, 1, min(S.top_nz_dc + S.left_nz_dc, 2), 0, T);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) q[i] = Q.dc[m2][i];
+    const int nz_dc = quantize_block(w, q, seg.y2, 0);
+    Q.acc.rate16[mode] = kModeFixedCost16(mode) + token_cost(q, nz_dc, 1, min(S.top_nz_dc + S.left_nz_dc, 2), 0, T);
     dequant_block(q, dq, seg.y2);
     iwht(dq, d);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) Q.dcrec[m2][i] = (int16_t)d[i];
+    ph_store_lev(Q.dcrec[m2], d);
   }
 }
 // C: token costs with the in-macroblock NZ contexts, luma reconstruction + SSE + TDisto
@@ -379,10 +383,9 @@ WG_HD void ph_search_c(const EncKernelParams& P, PhMB* mbs, const CostTabs& T, i
       const int bx = b & 3, by = b >> 2;
       const int l = bx > 0 ? (Q.nz[m2][b - 1] > 0) : ((S.left_nz >> by) & 1);
       const int tt = by > 0 ? (Q.nz[m2][b - 4] > 0) : ((S.top_nz >> bx) & 1);
-      const int rate = token_cost_smem(Q.lev[m2][b], Q.nz[m2][b], 0, l + tt, 1, T);
       int q[16], dq[16], p[16], r[16], s[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) q[i] = Q.lev[m2][b][i];
+      ph_load_lev(Q.lev[m2][b], q);
+      const int rate = token_cost(q, Q.nz[m2][b], 0, l + tt, 1, T);
       dequant_block(q, dq, seg.y1);
       dq[0] = Q.dcrec[m2][b];
       ph_pred_of_block(S, b, mode, p);
@@ -397,7 +400,9 @@ WG_HD void ph_search_c(const EncKernelParams& P, PhMB* mbs, const CostTabs& T, i
       const int tn = (S.top_nz >> (4 + 2 * ch)) & 3, ln = (S.left_nz >> (4 + 2 * ch)) & 3;
       const int l = bx > 0 ? (Q.nz[m2][b - 1] > 0) : ((ln >> by) & 1);
       const int tt = by > 0 ? (Q.nz[m2][b - 2] > 0) : ((tn >> bx) & 1);
-      WG_ATOMIC_ADD(&Q.acc.rate_uv[mode], token_cost_smem(Q.lev[m2][b], Q.nz[m2][b], 2, l + tt, 0, T));
+      int q[16];
+      ph_load_lev(Q.lev[m2][b], q);
+      WG_ATOMIC_ADD(&Q.acc.rate_uv[mode], token_cost(q, Q.nz[m2][b], 2, l + tt, 0, T));
     }
   }
 }
@@ -442,10 +447,14 @@ WG_HD void ph_i4_init(PhMB* mbs, int tid) {
   for (int t = tid; t < M * 37; t += NT) {
     PhMB& S = mbs[t / 37];
     const int i = t % 37;
-    if (!S.active) { if (i == 36) S.alive = 0; continue; }
+    if (!S.active) continue;
     if (i < 36) ph_cp16(S.u.q.out2 + 16 * i, S.out + 16 * i);
-    else { S.alive = 1; S.tot_rate = 0; S.tot_disto = 0; S.tot_hdr = 0; S.nzmask = 0; S.modes_lo = 0; S.modes_hi = 0; }
+    else { S.tot_rate = 0; S.tot_disto = 0; S.tot_hdr = 0; S.nzmask = 0; S.modes_lo = 0; S.modes_hi = 0; }
   }
+}
+// The exit test of tryI4ModesRDParallel (encode_parallel.go:830) on the totals committed so far (see the file comment)
+WG_HD bool ph_i4_alive(const EncKernelParams& P, const PhMB& S) {
+  return S.active && !(rd_score(S.tot_disto, S.tot_rate + 211, P.img[S.img].seg[S.segment].lambda_mode) >= S.score16 || S.tot_hdr > 15000);
 }
 // sub-block of wavefront step `step` in slot j (bx + 2*by == step), or -1
 WG_HD int ph_i4_block(int step, int j) {
@@ -459,13 +468,13 @@ WG_HD int ph_i4_block(int step, int j) {
 WG_HD int ph_get_mode(const PhMB& S, int k) { return (k < 8) ? (S.modes_lo >> (4 * k)) & 15 : (S.modes_hi >> (4 * (k - 8))) & 15; }
 // P1: prediction SSE of every eligible mode (the pre-screen of pickBestI4ModeRDParallel, encode_parallel.go:955-966)
 template <int M, int NT>
-WG_HD void ph_i4_prescreen(PhMB* mbs, int step, int tid) {
+WG_HD void ph_i4_prescreen(const EncKernelParams& P, PhMB* mbs, int step, int tid) {
   for (int t = tid; t < 10 * 2 * M; t += NT) {
     const int mode = t / (2 * M), r = t % (2 * M), j = r & 1;
     PhMB& S = mbs[r >> 1];
     PhI4Slot& W = S.u.q.slot[j];
     const int b = ph_i4_block(step, j);
-    const bool valid = S.alive && b >= 0;
+    const bool valid = b >= 0 && ph_i4_alive(P, S);
     if (!valid) { if (mode == 0) W.valid = 0; continue; }
     const int bx = b & 3, by = b >> 2;
     const bool has_top = S.my > 0 || by > 0, has_left = S.mx > 0 || bx > 0;
@@ -510,17 +519,24 @@ WG_HD void ph_i4_sort(const EncKernelParams& P, PhMB* mbs, int tid) {
     if (what == 0) {
       const int n_cand = W.ncand, K = min(P.max_i4_modes, n_cand);
       W.K = (uint8_t)K;
-#pragma unroll 1
-      for (int i = 0; i < K; ++i) {
-        int mi = i, mv = W.sse[i];
-#pragma unroll 1
-        for (int jj = i + 1; jj < n_cand; ++jj) { const int v = W.sse[jj]; if (v < mv) { mv = v; mi = jj; } }
-        if (mi != i) {
-          const int ts = W.sse[i]; const uint8_t tm = W.smode[i];
-          W.sse[i] = mv; W.smode[i] = W.smode[mi];
-          W.sse[mi] = ts; W.smode[mi] = tm;
+      int sse[10], md[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) { sse[i] = W.sse[i]; md[i] = W.smode[i]; }  // entries >= n_cand are never looked at
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {  // K <= 3 rounds (getMaxI4RDModes)
+        if (i < K) {
+          int mi = i, mv = sse[i], mm = md[i];
+#pragma unroll
+          for (int jj = i + 1; jj < 10; ++jj)
+            if (jj < n_cand && sse[jj] < mv) { mv = sse[jj]; mm = md[jj]; mi = jj; }
+          const int ts = sse[i], tm = md[i];
+#pragma unroll
+          for (int jj = i + 1; jj < 10; ++jj)
+            if (jj == mi) { sse[jj] = ts; md[jj] = tm; }
+          sse[i] = mv; md[i] = mm;
         }
       }
+      W.smode[0] = (uint8_t)md[0]; W.smode[1] = (uint8_t)md[1]; W.smode[2] = (uint8_t)md[2];
     } else if (P.img[S.img].seg[S.segment].tlambda_sd > 0) {
       int s[16];
       ph_load_src(S.in, W.b, s);
@@ -544,11 +560,15 @@ WG_HD void ph_i4_rd(const EncKernelParams& P, PhMB* mbs, const CostTabs& T, cons
     ph_load4x4<4>(W.pred[mode], p);
     ftransform(s, p, c);
     int16_t* lev = W.lev[k];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) lev[i] = (int16_t)c[i];
-    const int nz = (P.method >= 4) ? trellis_block_v2(lev, seg.y1, 0, 3, nz_ctx, seg.tlambda_i4, T) : quantize_smem(lev, seg.y1, 0);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) q[i] = lev[i];
+    int nz;
+    if (P.method >= 4) {
+      ph_store_lev(lev, c);
+      nz = trellis_block_v3(lev, seg.y1, 0, 3, nz_ctx, seg.tlambda_i4, T);
+      ph_load_lev(lev, q);
+    } else {
+      nz = quantize_block(c, q, seg.y1, 0);
+      ph_store_lev(lev, q);
+    }
     dequant_block(q, dq, seg.y1);
     itransform(p, dq, r);
     int disto = sse16(s, r);
@@ -560,55 +580,55 @@ WG_HD void ph_i4_rd(const EncKernelParams& P, PhMB* mbs, const CostTabs& T, cons
       for (int i = 1; i < 16; ++i) cnt += (q[i] != 0);
       if (cnt <= 3) rate = 140;
     }
-    rate += token_cost_smem(lev, nz, 3, nz_ctx, 0, T);
+    rate += token_cost(q, nz, 3, nz_ctx, 0, T);
     rate += i4cost[(W.top_mode * 10 + W.left_mode) * 10 + mode];
     W.score[k] = rd_score(disto, rate, seg.lambda_i4);
     W.disto[k] = disto; W.rate[k] = rate; W.nz[k] = (uint8_t)nz; W.cmode[k] = (uint8_t)mode;
     ph_store4x4<4>(W.rec[k], r);
   }
 }
-// P4: pick the winner of each sub-block in flight and commit it (modes, NZ bit, totals, levels, reconstruction)
+// P4: pick the winner of each sub-block in flight and commit it (modes, NZ bit, totals, levels, reconstruction).  One lane
+// per sub-block; the two sub-blocks of a macroblock add into the same totals (integer sums: order does not matter).
 template <int M, int NT>
-WG_HD void ph_i4_commit(const EncKernelParams& P, PhMB* mbs, const uint16_t* i4cost, int tid) {
-  for (int t = tid; t < M; t += NT) {
-    PhMB& S = mbs[t];
-    if (!S.active || !S.alive) continue;
-    const SegParams& seg = P.img[S.img].seg[S.segment];
-    for (int j = 0; j < 2; ++j) {
-      PhI4Slot& W = S.u.q.slot[j];
-      if (!W.valid) continue;
-      unsigned long long bs = ~0ull;
-      int best = 0;
-      for (int k = 0; k < W.K; ++k) {
-        if (256ull * (unsigned long long)W.disto[k] >= bs) continue;
-        if (W.score[k] < bs) { bs = W.score[k]; best = k; }
-      }
-      const int b = W.b, bm = W.cmode[best];
-      if (b < 8) S.modes_lo |= (uint32_t)bm << (4 * b); else S.modes_hi |= (uint32_t)bm << (4 * (b - 8));
-      S.tot_rate += W.rate[best];
-      S.tot_disto += W.disto[best];
-      S.tot_hdr += i4cost[(W.top_mode * 10 + W.left_mode) * 10 + bm];
-      if (W.nz[best] > 0) S.nzmask |= 1u << b;
-      S.hdr[24 + b] = W.nz[best];
-      ph_cp16(S.u.q.lev4[b], W.lev[best]);
-      ph_cp16(S.u.q.lev4[b] + 8, W.lev[best] + 8);
-      uint8_t* o = S.u.q.out2 + Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+WG_HD void ph_i4_commit(PhMB* mbs, const uint16_t* i4cost, int tid) {
+  for (int t = tid; t < 2 * M; t += NT) {
+    PhMB& S = mbs[t >> 1];
+    PhI4Slot& W = S.u.q.slot[t & 1];
+    if (!S.active || !W.valid) continue;
+    const int K = W.K;
+    unsigned long long sc[3];
+    int di[3];
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) ph_st32(o + rr * BPS, ph_ld32(W.rec[best] + 4 * rr));
+    for (int k = 0; k < 3; ++k) { sc[k] = W.score[k]; di[k] = W.disto[k]; }
+    unsigned long long bs = ~0ull;
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < K && !(256ull * (unsigned long long)di[k] >= bs) && sc[k] < bs) { bs = sc[k]; best = k; }
     }
-    if (rd_score(S.tot_disto, S.tot_rate + 211, seg.lambda_mode) >= S.score16 || S.tot_hdr > 15000) S.alive = 0;
+    const int b = W.b, bm = W.cmode[best];
+    if (b < 8) WG_ATOMIC_OR(&S.modes_lo, (uint32_t)bm << (4 * b)); else WG_ATOMIC_OR(&S.modes_hi, (uint32_t)bm << (4 * (b - 8)));
+    WG_ATOMIC_ADD(&S.tot_rate, W.rate[best]);
+    WG_ATOMIC_ADD(&S.tot_disto, W.disto[best]);
+    WG_ATOMIC_ADD(&S.tot_hdr, (int)i4cost[(W.top_mode * 10 + W.left_mode) * 10 + bm]);
+    if (W.nz[best] > 0) WG_ATOMIC_OR(&S.nzmask, 1u << b);
+    S.hdr[24 + b] = W.nz[best];
+    ph_cp16(S.u.q.lev4[b], W.lev[best]);
+    ph_cp16(S.u.q.lev4[b] + 8, W.lev[best] + 8);
+    uint8_t* o = S.u.q.out2 + Y_OFF + (b >> 2) * 4 * BPS + (b & 3) * 4;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) ph_st32(o + rr * BPS, ph_ld32(W.rec[best] + 4 * rr));
   }
 }
-
 // ---- final residuals and reconstruction (encode_parallel.go:1164-1407)
 // F0: the decision (encode_parallel.go:572-592); an I4 macroblock takes the trial buffer as its reconstruction
 template <int M, int NT>
-WG_HD void ph_final_decide(PhMB* mbs, int tid) {
+WG_HD void ph_final_decide(const EncKernelParams& P, PhMB* mbs, int tid) {
   for (int t = tid; t < M * 16; t += NT) {
     PhMB& S = mbs[t >> 4];
     const int i = t & 15;
     if (!S.active) continue;
-    const bool use_i4 = S.alive != 0;  // alive after the last commit <=> score4 < score16 and <= 15000 header bits
+    const bool use_i4 = ph_i4_alive(P, S);  // on the complete totals: score4 < score16 and <= 15000 header bits
     if (i == 0) S.use_i4 = use_i4;
     if (use_i4) {
       ph_cp8(S.out + Y_OFF + i * BPS, S.u.q.out2 + Y_OFF + i * BPS);
@@ -669,15 +689,11 @@ WG_HD void ph_final_i16_levels(const EncKernelParams& P, PhMB* mbs, const CostTa
 #pragma unroll
       for (int i = 0; i < 16; ++i) dd[i] = F.dc[i];
       fwht(dd, w);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) F.dc[i] = w[i];
-      S.nz_dc = quantize_smem(F.dc, seg.y2, 0);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { q[i] = F.dc[i]; F.lev[24][i] = (int16_t)q[i]; }
+      S.nz_dc = quantize_block(w, q, seg.y2, 0);
+      ph_store_lev(F.lev[24], q);
       dequant_block(q, dq, seg.y2);
       iwht(dq, dd);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) F.dcrec[i] = (int16_t)dd[i];
+      ph_store_lev(F.dcrec, dd);
       continue;
     }
     int b;
@@ -688,12 +704,17 @@ WG_HD void ph_final_i16_levels(const EncKernelParams& P, PhMB* mbs, const CostTa
       b = by * 4 + (d - by);
     }
     int nz;
-    if (d < 0) nz = quantize_smem(F.lev[b], seg.y1, 1);
+    if (d < 0) {
+      int c[16], q[16];
+      ph_load_lev(F.lev[b], c);
+      nz = quantize_block(c, q, seg.y1, 1);
+      ph_store_lev(F.lev[b], q);
+    }
     else {
       const int bx = b & 3, by = b >> 2;
       const int l = bx > 0 ? (F.nz[b - 1] > 0) : ((S.left_nz >> by) & 1);
       const int tt = by > 0 ? (F.nz[b - 4] > 0) : ((S.top_nz >> bx) & 1);
-      nz = trellis_block_v2(F.lev[b], seg.y1, 1, 0, l + tt, seg.tlambda_i16, T);
+      nz = trellis_block_v3(F.lev[b], seg.y1, 1, 0, l + tt, seg.tlambda_i16, T);
     }
     F.nz[b] = (uint8_t)nz;
     S.hdr[24 + b] = (uint8_t)nz;
@@ -764,7 +785,10 @@ WG_HD void ph_export(const EncKernelParams& P, PhMB* mbs, int tid) {
 }
 
 // The whole per-CTA schedule.  WG_PH(stmt) runs `stmt` for every thread of the CTA and ends with a barrier.
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && defined(WG_PHASE_CLOCK)
+// profiling build only (tools/phase_clock.py): CTA 0 timestamps every phase boundary
+#define WG_PH(stmt) { stmt; } __syncthreads(); if (P.work_counter && blockIdx.x == P.total_groups && threadIdx.x == 0) P.work_counter[ph_i_++] = clock64()
+#elif defined(__CUDA_ARCH__)
 #define WG_PH(stmt) { stmt; } __syncthreads()
 #else
 #define WG_PH(stmt) for (int k_ = 0; k_ < NT; ++k_) { const int tid = order ? order[k_] : k_; stmt; }
@@ -773,6 +797,10 @@ template <int M, int NT>
 WG_HD void ph_run_cta(const EncKernelParams& P, PhMB* mbs, const CostTabs& T, const uint16_t* i4cost, int wave, long long task_base,
                       int tid, const int* order) {
   (void)tid; (void)order;
+#if defined(__CUDA_ARCH__) && defined(WG_PHASE_CLOCK)
+  int ph_i_ = 0;
+  if (P.work_counter && blockIdx.x == P.total_groups && threadIdx.x == 0) P.work_counter[ph_i_++] = clock64();
+#endif
   WG_PH((ph_load<M, NT>(P, mbs, wave, task_base, tid)));
   WG_PH((ph_prep<M, NT>(mbs, tid)));
   for (int pass = 0; pass < 2; ++pass) {
@@ -783,12 +811,12 @@ WG_HD void ph_run_cta(const EncKernelParams& P, PhMB* mbs, const CostTabs& T, co
   WG_PH((ph_decide<M, NT>(P, mbs, tid)));
   WG_PH((ph_i4_init<M, NT>(mbs, tid)));
   for (int step = 0; step < 10; ++step) {
-    WG_PH((ph_i4_prescreen<M, NT>(mbs, step, tid)));
+    WG_PH((ph_i4_prescreen<M, NT>(P, mbs, step, tid)));
     WG_PH((ph_i4_sort<M, NT>(P, mbs, tid)));
     WG_PH((ph_i4_rd<M, NT>(P, mbs, T, i4cost, tid)));
-    WG_PH((ph_i4_commit<M, NT>(P, mbs, i4cost, tid)));
+    WG_PH((ph_i4_commit<M, NT>(mbs, i4cost, tid)));
   }
-  WG_PH((ph_final_decide<M, NT>(mbs, tid)));
+  WG_PH((ph_final_decide<M, NT>(P, mbs, tid)));
   WG_PH((ph_final_transform<M, NT>(P, mbs, tid)));
   if (P.method >= 4) {
     for (int d = 0; d < 7; ++d) { WG_PH((ph_final_i16_levels<M, NT>(P, mbs, T, d, tid))); }

@@ -258,7 +258,7 @@ __global__ void dsp_trellis_kernel(int n, const int16_t* in, SegQuant sq, int fi
 #pragma unroll
   for (int k = 0; k < 16; ++k) io[k] = in[16 * (size_t)i + k];
   // rate * lambda stays a 32-bit product in the latency-oriented trellis (encoder lambdas are <= 21567)
-  nz[i] = lambda <= 50000 ? trellis_block_v2(io, sq, first, ctx_type, ctx0[i], lambda, T) : trellis_block_smem(io, sq, first, ctx_type, ctx0[i], lambda, T);
+  nz[i] = lambda <= 50000 ? trellis_block_v3(io, sq, first, ctx_type, ctx0[i], lambda, T) : trellis_block_smem(io, sq, first, ctx_type, ctx0[i], lambda, T);
 #pragma unroll
   for (int k = 0; k < 16; ++k) out[16 * (size_t)i + k] = io[k];
 }

@@ -652,4 +652,152 @@ WG_HD int trellis_block_v2(int16_t* io, const SegQuant& sq, int first, int type,
   return last;
 }
 
+// Third formulation of TrellisQuantizeBlock (same contract again), cut for instruction count: a trellis position was ~275 SASS
+// instructions in trellis_block_v2, most of them 64-bit compare / select pairs and index bookkeeping.  Here every score is
+// kept multiplied by 64, which frees the low six bits of the 64-bit word for the bookkeeping the comparisons have to carry:
+//   * a transition key is (score * 64 | prev ctx): the minimum over the three previous contexts is then a plain signed
+//     minimum, and equal scores resolve to the lower context exactly as the reference's strict '<' in loop order does;
+//   * bit 3 marks "level L0 + 1" on the way into context 2, and key(L0+1) < key(L0) is the reference's order of visits
+//     (prev ctx major, then level) on equal scores;
+//   * the running best terminal carries 1 + 2n + (ctx - 1): a later terminal only wins when strictly smaller.
+// rate * (lambda * 64) + score is one IMAD.WIDE.U32.  The survivor entries (10 bits per position) go through a 160-bit shift
+// register of five 32-bit words (funnel shifts) instead of variable 64-bit shifts.  Scaled scores stay below 2^47.
+WG_HD uint32_t wg_fshl(uint32_t lo, uint32_t hi, int s) {  // upper word of (hi:lo) << s, 0 < s < 32
+#ifdef __CUDA_ARCH__
+  return __funnelshift_l(lo, hi, s);
+#else
+  return (hi << s) | (lo >> (32 - s));
+#endif
+}
+WG_HD uint32_t wg_fshr(uint32_t lo, uint32_t hi, int s) {  // lower word of (hi:lo) >> s, 0 < s < 32
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, s);
+#else
+  return (lo >> s) | (hi << (32 - s));
+#endif
+}
+struct TrellisPos3 {
+  int L0;
+  uint32_t flags;     // 1: level L0 exists, 2: level L0+1 exists
+  long long k0, k1;   // 64 * (fixed-cost * lambda + weighted distortion delta) of level L0 / L0+1
+  uint32_t r0[3], rA[3], rB[3];  // table cost of level 0 / L0 / L0+1 after previous context pc
+};
+WG_HD void trellis_prep3(const int16_t* io, int n, int quant_dc, int quant_ac, unsigned iq_dc, unsigned iq_ac, const uint16_t* lc,
+                         const uint16_t* lfc, uint32_t lam64, TrellisPos3& P) {
+  const int zig = c_zigzag[n];
+  const int band = c_bands[n + 1];  // sic: the next position's band (encode_trellis.go:151)
+  const int coeff0 = io[zig];
+  const int quant = (n == 0) ? quant_dc : quant_ac;
+  const unsigned iquant = (n == 0) ? iq_dc : iq_ac;
+  const int L0 = min((int)(((unsigned)coeff0 * iquant) >> 17), 2047);
+  const int thresh = min((int)(((unsigned)coeff0 * iquant + 65536u) >> 17), 2047);
+  P.L0 = L0;
+  P.flags = ((L0 > 0 && L0 <= thresh) ? 1u : 0u) | ((L0 + 1 <= 2047 && L0 + 1 <= thresh) ? 2u : 0u);
+  const int c0sq = coeff0 * coeff0;
+  const int e0 = coeff0 - L0 * quant, e1 = coeff0 - (L0 + 1) * quant;
+  const int wt = c_weight_trellis[zig] * (256 * 64);
+  P.k0 = (long long)(e0 * e0 - c0sq) * wt + (long long)((unsigned long long)lfc[L0] * lam64);
+  P.k1 = (long long)(e1 * e1 - c0sq) * wt + (long long)((unsigned long long)lfc[min(L0 + 1, 2047)] * lam64);
+  const int li0 = min(L0, LC_LEVELS - 1), li1 = min(L0 + 1, LC_LEVELS - 1);
+  const uint16_t* row = lc + band * 3 * LC_LEVELS;
+#pragma unroll
+  for (int pc = 0; pc < 3; ++pc) {
+    P.r0[pc] = row[pc * LC_LEVELS];
+    P.rA[pc] = row[pc * LC_LEVELS + li0];
+    P.rB[pc] = row[pc * LC_LEVELS + li1];
+  }
+}
+WG_HD long long trellis_min3(long long a, long long b, long long c) {
+  const long long m = b < a ? b : a;
+  return c < m ? c : m;
+}
+WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type, int initial_ctx, int lambda, const CostTabs& T) {
+  const int quant_ac = sq.quant, quant_dc = sq.dc_quant;
+  const unsigned iq_ac = (unsigned)sq.iquant, iq_dc = (unsigned)sq.dc_iquant;
+  uint32_t neg_mask = 0;  // bit i: raster coefficient i is negative
+  {
+    bool non_zero = false;  // all-zero pre-scan with neutral bias (encode_trellis.go:39-98)
+    int c0[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int raw = io[i];
+      c0[i] = max(abs(raw) + sq.sharpen[i], 0);
+      neg_mask |= (raw < 0 ? 1u : 0u) << i;
+      if (i > 0) non_zero |= (((unsigned)c0[i] * iq_ac) >> 17) > 0;
+      else non_zero |= first == 0 && (((unsigned)c0[0] * iq_dc) >> 17) > 0;
+    }
+    if (!non_zero) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) io[i] = 0;
+      return 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) io[i] = (int16_t)c0[i];
+  }
+  initial_ctx = min(initial_ctx, 2);
+  const uint16_t* lc = T.lc + type * (8 * 3 * LC_LEVELS);
+  const uint16_t* eob = T.eob + type * (8 * 3);
+  const long long kBig = 1ll << 56, kThr = 1ll << 55, kMask = ~63ll;
+  long long ps0 = initial_ctx == 0 ? 0 : kBig, ps1 = initial_ctx == 1 ? 0 : kBig, ps2 = initial_ctx == 2 ? 0 : kBig;
+  const uint32_t lam64 = (uint32_t)lambda << 6;
+  long long best = (long long)((unsigned long long)eob[c_bands[first] * 3 + initial_ctx] * lam64);  // order tag 0: "no coefficient"
+  uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;  // survivor entries, newest in the low 10 bits of w0
+  TrellisPos3 cur;
+  trellis_prep3(io, first, quant_dc, quant_ac, iq_dc, iq_ac, lc, T.lfc, lam64, cur);
+#pragma unroll 1
+  for (int n = first; n < 16; ++n) {
+    TrellisPos3 nxt;
+    trellis_prep3(io, min(n + 1, 15), quant_dc, quant_ac, iq_dc, iq_ac, lc, T.lfc, lam64, nxt);  // independent of the state below
+    const uint32_t eb1 = (n < 15) ? eob[c_bands[n + 1] * 3 + 1] : 0u, eb2 = (n < 15) ? eob[c_bands[n + 1] * 3 + 2] : 0u;
+    const int L0 = cur.L0;
+    io[c_zigzag[n]] = (int16_t)L0;  // the backtrack only needs the base level (position n + 1 was read above)
+    const long long q0 = ps0, q1 = ps1 | 1, q2 = ps2 | 2;
+    const long long key0 = trellis_min3(q0 + (long long)((unsigned long long)cur.r0[0] * lam64), q1 + (long long)((unsigned long long)cur.r0[1] * lam64),
+                                        q2 + (long long)((unsigned long long)cur.r0[2] * lam64));
+    const long long keyA = trellis_min3(q0 + (long long)((unsigned long long)cur.rA[0] * lam64), q1 + (long long)((unsigned long long)cur.rA[1] * lam64),
+                                        q2 + (long long)((unsigned long long)cur.rA[2] * lam64)) + cur.k0;
+    const long long keyB = trellis_min3(q0 + (long long)((unsigned long long)cur.rB[0] * lam64), q1 + (long long)((unsigned long long)cur.rB[1] * lam64),
+                                        q2 + (long long)((unsigned long long)cur.rB[2] * lam64)) + cur.k1;
+    const bool hasA = (cur.flags & 1u) != 0, hasB = (cur.flags & 2u) != 0;
+    // level L0 lands in context min(L0, 2), level L0 + 1 in min(L0 + 1, 2)
+    const bool a1 = hasA && L0 == 1, b1 = hasB && L0 == 0;  // at most one of them
+    const bool a2 = hasA && L0 >= 2, b2 = hasB && L0 >= 1;
+    const long long key1 = a1 ? keyA : (b1 ? keyB : kBig);
+    const bool take_b = b2 && (!a2 || keyB < keyA);
+    const long long key2 = take_b ? (keyB | 8) : (a2 ? keyA : kBig);
+    const bool v0 = key0 < kThr, v1 = key1 < kThr, v2 = key2 < kThr;
+    const uint32_t l0 = (uint32_t)key0, l1 = (uint32_t)key1, l2 = (uint32_t)key2;
+    const uint32_t ent = ((l0 & 3u) | (v0 ? 4u : 0u)) | (((l1 & 3u) | (v1 ? 4u : 0u)) << 3) | (((l2 & 11u) | (v2 ? 4u : 0u)) << 6);
+    w4 = wg_fshl(w3, w4, 10); w3 = wg_fshl(w2, w3, 10); w2 = wg_fshl(w1, w2, 10); w1 = wg_fshl(w0, w1, 10); w0 = (w0 << 10) | ent;
+    const long long s1 = key1 & kMask, s2 = key2 & kMask;
+    {  // terminals: unreachable states stay >= kThr and never win
+      const long long t1 = (s1 + (long long)((unsigned long long)eb1 * lam64)) | (long long)(2 * n + 1);
+      best = t1 < best ? t1 : best;
+      const long long t2 = (s2 + (long long)((unsigned long long)eb2 * lam64)) | (long long)(2 * n + 2);
+      best = t2 < best ? t2 : best;
+    }
+    ps0 = v0 ? (key0 & kMask) : kBig; ps1 = v1 ? s1 : kBig; ps2 = v2 ? s2 : kBig;
+    cur = nxt;
+  }
+  const int tag = (int)((uint32_t)best & 63u);
+  const int best_last_n = tag ? (tag - 1) >> 1 : -1;
+  int ctx = tag ? 1 + ((tag - 1) & 1) : -1, last = 0;
+  if (first == 1) io[0] = 0;
+#pragma unroll 4
+  for (int n = 15; n >= first; --n) {
+    const int zig = c_zigzag[n];
+    const uint32_t ent = w0 & 0x3ffu;
+    w0 = wg_fshr(w0, w1, 10); w1 = wg_fshr(w1, w2, 10); w2 = wg_fshr(w2, w3, 10); w3 = wg_fshr(w3, w4, 10); w4 >>= 10;
+    const uint32_t e = ctx == 0 ? (ent & 7u) : (ctx == 1 ? ((ent >> 3) & 7u) : ((ent >> 6) & 15u));
+    const bool take = n <= best_last_n && (e & 4u);
+    const int L0 = io[zig];
+    const int mag = ctx == 0 ? 0 : (ctx == 1 ? 1 : L0 + (int)((e >> 3) & 1u));
+    const int lv = ((neg_mask >> zig) & 1u) ? -mag : mag;
+    io[zig] = (int16_t)(take ? lv : 0);
+    last = (take && lv != 0 && last == 0) ? n + 1 : last;
+    ctx = take ? (int)(e & 3u) : ctx;
+  }
+  return last;
+}
+
 }  // namespace wg

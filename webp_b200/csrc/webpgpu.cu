@@ -476,10 +476,22 @@ int launch_enc_phased(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->dev);
   static const int cfg = getenv_int("WGPU_PHASED_CFG", 0);  // tuning knob: CTA shape of the wide waves
   const int waves = P.mb_w + 2 * (P.mb_h - 1);
+#ifdef WG_PHASE_CLOCK
+  static unsigned long long* clk = nullptr;
+  if (!clk) cudaMalloc(&clk, 256 * 8);
+  cudaMemsetAsync(clk, 0, 256 * 8, ctx->stream);
+  const int clk_wave = getenv_int("WGPU_CLOCK_WAVE", 110);
+  const wg::EncKernelParams P0 = P;
+#endif
   for (int w = 0; w < waves; ++w) {
     const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
     if (tasks <= 0) continue;  // one macroblock column: odd waves hold no macroblock (x = w - 2y)
     int rc;
+#ifdef WG_PHASE_CLOCK
+    wg::EncKernelParams& Pm = const_cast<wg::EncKernelParams&>(P);
+    Pm = P0;
+    if (w == clk_wave) { Pm.work_counter = clk; Pm.total_groups = getenv_int("WGPU_CLOCK_CTA", 300); }
+#endif
     if (cfg == 1) rc = launch_phased_wave<16, 128, 3>(ctx, P, w, tasks);
     else if (cfg == 2) rc = launch_phased_wave<8, 64, 4>(ctx, P, w, tasks);
     else if (cfg == 3) rc = launch_phased_wave<8, 128, 4>(ctx, P, w, tasks);
@@ -488,6 +500,16 @@ int launch_enc_phased(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
     else rc = launch_phased_wave<16, 256, 3>(ctx, P, w, tasks);
     if (rc) return rc;
   }
+#ifdef WG_PHASE_CLOCK
+  {
+    unsigned long long h[256];
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[phase clock] wave %d:", clk_wave);
+    for (int i = 1; i < 256 && h[i]; ++i) fprintf(stderr, " %llu", h[i] - h[i - 1]);
+    fprintf(stderr, "\n");
+  }
+#endif
   if (P.stats) {
     wg::MBStatsParams S;
     S.hdr = P.out_hdr; S.coeffs = P.out_coeffs; S.ctxw = P.ctx; S.stats = P.stats; S.mb_w = P.mb_w; S.mb_h = P.mb_h;

@@ -49,7 +49,8 @@ def header_symbols():
 def lib():
     global _LIB
     if _LIB is None:
-        path = _build.build_native()
+        # WGPU_LIB: a differently built libwebpgpu.so (profiling builds, tools/phase_clock.py); same ABI, still no fallback
+        path = os.environ.get("WGPU_LIB") or _build.build_native()
         L = C.CDLL(path)
         vp, u8p, i16p, i32p, sz = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t
         L.wgpu_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
