@@ -74,17 +74,17 @@ WG_HD void ph_store4x4(uint8_t* p, const int* d) {
   for (int j = 0; j < 4; ++j)
     ph_st32(p + j * STRIDE, (uint32_t)d[4 * j] | ((uint32_t)d[4 * j + 1] << 8) | ((uint32_t)d[4 * j + 2] << 16) | ((uint32_t)d[4 * j + 3] << 24));
 }
-WG_HD void ph_store_lev(int16_t* lev, const int* q) {  // lev 4-byte aligned
+WG_HD void ph_store_lev(int16_t* lev, const int* q) {  // lev 16-byte aligned
+  uint32_t w[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    ph_st32(reinterpret_cast<uint8_t*>(lev) + 4 * i, ((uint32_t)q[2 * i] & 0xffffu) | ((uint32_t)q[2 * i + 1] << 16));
+  for (int i = 0; i < 8; ++i) w[i] = ((uint32_t)q[2 * i] & 0xffffu) | ((uint32_t)q[2 * i + 1] << 16);
+  ph_cp16(lev, w); ph_cp16(lev + 8, w + 4);
 }
-WG_HD void ph_load_lev(const int16_t* lev, int* q) {  // lev 4-byte aligned
+WG_HD void ph_load_lev(const int16_t* lev, int* q) {  // lev 16-byte aligned
+  uint32_t w[8];
+  ph_cp16(w, lev); ph_cp16(w + 4, lev + 8);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint32_t w = ph_ld32(reinterpret_cast<const uint8_t*>(lev) + 4 * i);
-    q[2 * i] = (int)(int16_t)(w & 0xffffu); q[2 * i + 1] = (int)(int16_t)(w >> 16);
-  }
+  for (int i = 0; i < 8; ++i) { q[2 * i] = (int)(int16_t)(w[i] & 0xffffu); q[2 * i + 1] = (int)(int16_t)(w[i] >> 16); }
 }
 // source block b of the compact `in` buffer: luma 0..15 (stride 16), chroma 16..23 (U at 256, V at 320, stride 8)
 WG_HD void ph_load_src(const uint8_t* in, int b, int* d) {
@@ -147,6 +147,7 @@ struct alignas(16) PhI4Slot {  // one 4x4 sub-block in flight
   uint8_t smode[10];
   uint8_t nz[3], cmode[3];
   uint8_t ncand, K, b, valid, top_mode, left_mode, nz_ctx, pad;
+  uint8_t bank_pad[16];  // slot stride = 112 words = 16 (mod 32 banks), see PhMB::bank_pad
 };
 enum { PH_OUT2 = 576 };
 struct PhI4 {
@@ -173,7 +174,12 @@ struct alignas(16) PhMB {
   unsigned long long score16;
   int tot_rate, tot_disto, tot_hdr;
   uint32_t nzmask, modes_lo, modes_hi;
+  // Lanes of a warp work on the same field of different macroblocks (and slots), so the strides decide the bank conflicts:
+  // a macroblock stride of 4 (mod 8) words and a slot stride of 16 spread 16 macroblocks x 2 slots over 8 bank groups
+  // (4-way worst case; a stride that is a multiple of 32 words -- the natural size was -- puts all 32 lanes on one bank).
+  uint8_t bank_pad[16];
 };
+static_assert((sizeof(PhMB) / 4) % 8 == 4 && (sizeof(PhI4Slot) / 4) % 32 == 16, "bank spreading strides");
 
 static_assert(sizeof(PhI4Slot) % 16 == 0 && offsetof(PhI4, out2) % 16 == 0 && offsetof(PhI4, slot) % 16 == 0, "128-bit copies");
 static_assert(offsetof(PhMB, in) % 16 == 0 && offsetof(PhMB, out) % 16 == 0 && offsetof(PhMB, hdr) % 16 == 0 && sizeof(PhMB) % 16 == 0, "128-bit copies");

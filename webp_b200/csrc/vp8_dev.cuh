@@ -676,16 +676,24 @@ WG_HD uint32_t wg_fshr(uint32_t lo, uint32_t hi, int s) {  // lower word of (hi:
   return (lo >> s) | (hi << (32 - s));
 #endif
 }
-struct TrellisPos3 {
+WG_HD long long wg_mad_wide(uint32_t a, uint32_t b, long long c) {  // a * b + c, one IMAD.WIDE.U32
+#ifdef __CUDA_ARCH__
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"((unsigned long long)c));
+  return (long long)r;
+#else
+  return c + (long long)((unsigned long long)a * b);
+#endif
+}
+struct TrellisPos3 {  // what a position contributes, independent of the Viterbi state
   int L0;
-  uint32_t flags;     // 1: level L0 exists, 2: level L0+1 exists
-  long long k0, k1;   // 64 * (fixed-cost * lambda + weighted distortion delta) of level L0 / L0+1
-  uint32_t r0[3], rA[3], rB[3];  // table cost of level 0 / L0 / L0+1 after previous context pc
+  uint32_t flags;      // 1: level L0 exists, 2: level L0+1 exists
+  long long k0, k1;    // 64 * (fixed-cost * lambda + weighted distortion delta) of level L0 / L0+1
+  int iA, iB;          // offsets of the cost-table entries of level L0 / L0+1 in the row of previous context 0
 };
-WG_HD void trellis_prep3(const int16_t* io, int n, int quant_dc, int quant_ac, unsigned iq_dc, unsigned iq_ac, const uint16_t* lc,
-                         const uint16_t* lfc, uint32_t lam64, TrellisPos3& P) {
+WG_HD void trellis_prep3(const int16_t* io, int n, int quant_dc, int quant_ac, unsigned iq_dc, unsigned iq_ac, const uint16_t* lfc,
+                         uint32_t lam64, TrellisPos3& P) {
   const int zig = c_zigzag[n];
-  const int band = c_bands[n + 1];  // sic: the next position's band (encode_trellis.go:151)
   const int coeff0 = io[zig];
   const int quant = (n == 0) ? quant_dc : quant_ac;
   const unsigned iquant = (n == 0) ? iq_dc : iq_ac;
@@ -696,21 +704,16 @@ WG_HD void trellis_prep3(const int16_t* io, int n, int quant_dc, int quant_ac, u
   const int c0sq = coeff0 * coeff0;
   const int e0 = coeff0 - L0 * quant, e1 = coeff0 - (L0 + 1) * quant;
   const int wt = c_weight_trellis[zig] * (256 * 64);
-  P.k0 = (long long)(e0 * e0 - c0sq) * wt + (long long)((unsigned long long)lfc[L0] * lam64);
-  P.k1 = (long long)(e1 * e1 - c0sq) * wt + (long long)((unsigned long long)lfc[min(L0 + 1, 2047)] * lam64);
-  const int li0 = min(L0, LC_LEVELS - 1), li1 = min(L0 + 1, LC_LEVELS - 1);
-  const uint16_t* row = lc + band * 3 * LC_LEVELS;
-#pragma unroll
-  for (int pc = 0; pc < 3; ++pc) {
-    P.r0[pc] = row[pc * LC_LEVELS];
-    P.rA[pc] = row[pc * LC_LEVELS + li0];
-    P.rB[pc] = row[pc * LC_LEVELS + li1];
-  }
+  P.k0 = wg_mad_wide(lfc[L0], lam64, (long long)(e0 * e0 - c0sq) * wt);
+  P.k1 = wg_mad_wide(lfc[min(L0 + 1, 2047)], lam64, (long long)(e1 * e1 - c0sq) * wt);
+  P.iA = min(L0, LC_LEVELS - 1);
+  P.iB = min(L0 + 1, LC_LEVELS - 1);
 }
 WG_HD long long trellis_min3(long long a, long long b, long long c) {
   const long long m = b < a ? b : a;
   return c < m ? c : m;
 }
+WG_HD int wg_hi32(long long v) { return (int)(v >> 32); }
 WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type, int initial_ctx, int lambda, const CostTabs& T) {
   const int quant_ac = sq.quant, quant_dc = sq.dc_quant;
   const unsigned iq_ac = (unsigned)sq.iquant, iq_dc = (unsigned)sq.dc_iquant;
@@ -742,22 +745,27 @@ WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type,
   const uint32_t lam64 = (uint32_t)lambda << 6;
   long long best = (long long)((unsigned long long)eob[c_bands[first] * 3 + initial_ctx] * lam64);  // order tag 0: "no coefficient"
   uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;  // survivor entries, newest in the low 10 bits of w0
+  const int kThrHi = 1 << 23;  // key < kThr  <=>  its upper word < 2^23 (scores may be negative)
   TrellisPos3 cur;
-  trellis_prep3(io, first, quant_dc, quant_ac, iq_dc, iq_ac, lc, T.lfc, lam64, cur);
-#pragma unroll 1
+  trellis_prep3(io, first, quant_dc, quant_ac, iq_dc, iq_ac, T.lfc, lam64, cur);
+#pragma unroll 2
   for (int n = first; n < 16; ++n) {
+    // this position's table costs: addresses known since the previous iteration, issued first ...
+    const int band = c_bands[n + 1];  // sic: the next position's band (encode_trellis.go:151)
+    const uint16_t* row = lc + band * 3 * LC_LEVELS;
+    const uint32_t r00 = row[0], r01 = row[LC_LEVELS], r02 = row[2 * LC_LEVELS];
+    const uint32_t rA0 = row[cur.iA], rA1 = row[LC_LEVELS + cur.iA], rA2 = row[2 * LC_LEVELS + cur.iA];
+    const uint32_t rB0 = row[cur.iB], rB1 = row[LC_LEVELS + cur.iB], rB2 = row[2 * LC_LEVELS + cur.iB];
+    const uint32_t eb1 = (n < 15) ? eob[band * 3 + 1] : 0u, eb2 = (n < 15) ? eob[band * 3 + 2] : 0u;
+    // ... then the next position's state-independent half while those loads are in flight
     TrellisPos3 nxt;
-    trellis_prep3(io, min(n + 1, 15), quant_dc, quant_ac, iq_dc, iq_ac, lc, T.lfc, lam64, nxt);  // independent of the state below
-    const uint32_t eb1 = (n < 15) ? eob[c_bands[n + 1] * 3 + 1] : 0u, eb2 = (n < 15) ? eob[c_bands[n + 1] * 3 + 2] : 0u;
+    trellis_prep3(io, min(n + 1, 15), quant_dc, quant_ac, iq_dc, iq_ac, T.lfc, lam64, nxt);
     const int L0 = cur.L0;
     io[c_zigzag[n]] = (int16_t)L0;  // the backtrack only needs the base level (position n + 1 was read above)
     const long long q0 = ps0, q1 = ps1 | 1, q2 = ps2 | 2;
-    const long long key0 = trellis_min3(q0 + (long long)((unsigned long long)cur.r0[0] * lam64), q1 + (long long)((unsigned long long)cur.r0[1] * lam64),
-                                        q2 + (long long)((unsigned long long)cur.r0[2] * lam64));
-    const long long keyA = trellis_min3(q0 + (long long)((unsigned long long)cur.rA[0] * lam64), q1 + (long long)((unsigned long long)cur.rA[1] * lam64),
-                                        q2 + (long long)((unsigned long long)cur.rA[2] * lam64)) + cur.k0;
-    const long long keyB = trellis_min3(q0 + (long long)((unsigned long long)cur.rB[0] * lam64), q1 + (long long)((unsigned long long)cur.rB[1] * lam64),
-                                        q2 + (long long)((unsigned long long)cur.rB[2] * lam64)) + cur.k1;
+    const long long key0 = trellis_min3(wg_mad_wide(r00, lam64, q0), wg_mad_wide(r01, lam64, q1), wg_mad_wide(r02, lam64, q2));
+    const long long keyA = trellis_min3(wg_mad_wide(rA0, lam64, q0), wg_mad_wide(rA1, lam64, q1), wg_mad_wide(rA2, lam64, q2)) + cur.k0;
+    const long long keyB = trellis_min3(wg_mad_wide(rB0, lam64, q0), wg_mad_wide(rB1, lam64, q1), wg_mad_wide(rB2, lam64, q2)) + cur.k1;
     const bool hasA = (cur.flags & 1u) != 0, hasB = (cur.flags & 2u) != 0;
     // level L0 lands in context min(L0, 2), level L0 + 1 in min(L0 + 1, 2)
     const bool a1 = hasA && L0 == 1, b1 = hasB && L0 == 0;  // at most one of them
@@ -765,15 +773,15 @@ WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type,
     const long long key1 = a1 ? keyA : (b1 ? keyB : kBig);
     const bool take_b = b2 && (!a2 || keyB < keyA);
     const long long key2 = take_b ? (keyB | 8) : (a2 ? keyA : kBig);
-    const bool v0 = key0 < kThr, v1 = key1 < kThr, v2 = key2 < kThr;
+    const bool v0 = wg_hi32(key0) < kThrHi, v1 = wg_hi32(key1) < kThrHi, v2 = wg_hi32(key2) < kThrHi;
     const uint32_t l0 = (uint32_t)key0, l1 = (uint32_t)key1, l2 = (uint32_t)key2;
     const uint32_t ent = ((l0 & 3u) | (v0 ? 4u : 0u)) | (((l1 & 3u) | (v1 ? 4u : 0u)) << 3) | (((l2 & 11u) | (v2 ? 4u : 0u)) << 6);
     w4 = wg_fshl(w3, w4, 10); w3 = wg_fshl(w2, w3, 10); w2 = wg_fshl(w1, w2, 10); w1 = wg_fshl(w0, w1, 10); w0 = (w0 << 10) | ent;
     const long long s1 = key1 & kMask, s2 = key2 & kMask;
     {  // terminals: unreachable states stay >= kThr and never win
-      const long long t1 = (s1 + (long long)((unsigned long long)eb1 * lam64)) | (long long)(2 * n + 1);
+      const long long t1 = wg_mad_wide(eb1, lam64, s1) | (long long)(2 * n + 1);
       best = t1 < best ? t1 : best;
-      const long long t2 = (s2 + (long long)((unsigned long long)eb2 * lam64)) | (long long)(2 * n + 2);
+      const long long t2 = wg_mad_wide(eb2, lam64, s2) | (long long)(2 * n + 2);
       best = t2 < best ? t2 : best;
     }
     ps0 = v0 ? (key0 & kMask) : kBig; ps1 = v1 ? s1 : kBig; ps2 = v2 ? s2 : kBig;
