@@ -340,3 +340,22 @@ def alpha_test_image(oracle, w, h, seed):
 def test_cleanup_transparent_oracle(oracle, w, h, seed):
     img = alpha_test_image(oracle, w, h, seed)
     assert np.array_equal(oracle.cleanup_transparent(img), _cleanup_numpy(img))
+
+
+def test_phased_mode_search_code_on_cpu_matches_oracle(oracle):
+    """The PRODUCT's row-parallel mode search (webp_b200/csrc/enc_phased.cuh: every phase of the kernel is a host+device
+    function) run on the CPU in the kernel's schedule -- waves, CTAs of M macroblocks, each phase as a loop over the CTA's
+    threads in shuffled order with a barrier where the kernel has one (oracle/hostcheck.cc hostcheck_modesearch) -- must
+    reproduce the oracle encoder's per-macroblock headers, levels and reconstruction.  Covers the I4 sub-block wavefront,
+    the partial-sum early exit, trellis v3 and partial macroblocks without a GPU."""
+    import ctypes as C
+    L = C.CDLL(os.path.join(os.path.dirname(DATA), "..", "oracle", "_build", "libhostcheck.so"))
+    cases = [(128, 96, 1, {}, 7, 16), (160, 112, 2, {}, 0, 8), (96, 80, 0, dict(segments=1), 3, 12), (200, 150, 1, dict(method=3), 5, 16),
+             (256, 192, 2, dict(method=6, quality=40), 9, 16), (130, 71, 1, dict(quality=90), 11, 8), (320, 240, 2, dict(method=5, quality=20), 13, 16),
+             (64, 64, 1, dict(sns_strength=0), 2, 16), (768, 576, 1, {}, 17, 16)]
+    for (w, h, idx, kw, seed, m) in cases:
+        img = oracle.synth_image(w, h, idx)
+        cfg = oracle.default_cfg(**kw)
+        fb = (C.c_int * 4)()
+        bad = L.hostcheck_modesearch(img.ctypes.data_as(C.c_void_p), C.c_int(img.strides[0]), w, h, C.byref(cfg), C.c_uint(seed), m, fb)
+        assert bad == 0, (w, h, idx, kw, seed, m, list(fb))

@@ -1,6 +1,6 @@
 // Definitions shared by the mode-search kernels (enc_kernels.cuh: wavefront kernels with G lanes per macroblock, used for the
 // Method < 3 and serial RD paths; enc_phased.cuh: the phase-synchronous kernel of the row-parallel RD path) and by the CPU
-// harness that runs the phased kernel's code (oracle/hostcheck.cc).  Plain C++ when compiled without nvcc.
+// harness that runs the phased kernel's code (the hostcheck test harness).  Plain C++ when compiled without nvcc.
 #pragma once
 #include <stddef.h>
 #include "vp8_dev.cuh"

@@ -10,7 +10,7 @@
 //   * the warps of a CTA are in the same few KB of code at the same time (the old kernel's 131 KB body with 12 warps at 12
 //     places was instruction-fetch bound);
 //   * no warp shuffles and no per-thread state across phases: the very same functions run on the CPU as
-//     `for (tid...) phase(tid)` (oracle/hostcheck.cc, threads in shuffled order), which checks the schedule and every
+//     `for (tid...) phase(tid)` (the hostcheck test harness, threads in shuffled order), which checks the schedule and every
 //     barrier against the oracle without a GPU.
 // The I4 early exit of tryI4ModesRDParallel (encode_parallel.go:830: running score >= the I16 score, or > 15000 header
 // bits) is evaluated on partial sums in wavefront order: rates, distortions and header costs are non-negative, so any

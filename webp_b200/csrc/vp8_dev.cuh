@@ -23,7 +23,7 @@ inline int max(int a, int b) { return a > b ? a : b; }
 #include "vp8_tables.inc"  // host-visible copies (static const); device copies below
 
 // ---- tables in device global memory (L1/L2 cached); hot kernels stage them into shared memory
-// The per-block routines below are host+device (WG_HD) so that a CPU harness (oracle/hostcheck.cc) can run the kernels' code
+// The per-block routines below are host+device (WG_HD) so that a CPU harness (the hostcheck test harness) can run the kernels' code
 // in the kernels' schedule; on the host the small tables are plain static arrays.
 #define WG_TAB_ZIGZAG {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15}
 #define WG_TAB_BANDS {0, 1, 2, 3, 6, 4, 5, 6, 6, 6, 6, 6, 6, 6, 6, 7, 0}
@@ -748,7 +748,7 @@ WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type,
   const int kThrHi = 1 << 23;  // key < kThr  <=>  its upper word < 2^23 (scores may be negative)
   TrellisPos3 cur;
   trellis_prep3(io, first, quant_dc, quant_ac, iq_dc, iq_ac, T.lfc, lam64, cur);
-#pragma unroll 2
+#pragma unroll 1
   for (int n = first; n < 16; ++n) {
     // this position's table costs: addresses known since the previous iteration, issued first ...
     const int band = c_bands[n + 1];  // sic: the next position's band (encode_trellis.go:151)
@@ -791,7 +791,7 @@ WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type,
   const int best_last_n = tag ? (tag - 1) >> 1 : -1;
   int ctx = tag ? 1 + ((tag - 1) & 1) : -1, last = 0;
   if (first == 1) io[0] = 0;
-#pragma unroll 4
+#pragma unroll 1
   for (int n = 15; n >= first; --n) {
     const int zig = c_zigzag[n];
     const uint32_t ent = w0 & 0x3ffu;

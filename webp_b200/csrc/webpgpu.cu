@@ -496,6 +496,8 @@ int launch_enc_phased(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
     else if (cfg == 2) rc = launch_phased_wave<8, 64, 4>(ctx, P, w, tasks);
     else if (cfg == 3) rc = launch_phased_wave<8, 128, 4>(ctx, P, w, tasks);
     else if (cfg == 4) rc = launch_phased_wave<16, 192, 3>(ctx, P, w, tasks);
+    else if (cfg == 5) rc = launch_phased_wave<24, 384, 2>(ctx, P, w, tasks);
+    else if (cfg == 6) rc = launch_phased_wave<32, 512, 1>(ctx, P, w, tasks);
     else if (tasks <= (long long)sm_count * 8 * 4) rc = launch_phased_wave<8, 128, 4>(ctx, P, w, tasks);
     else rc = launch_phased_wave<16, 256, 3>(ctx, P, w, tasks);
     if (rc) return rc;
