@@ -258,7 +258,9 @@ int hostcheck_modesearch(const uint8_t* rgba, int stride, int w, int h, const Or
   P.method = c->method; P.max_i4_modes = c->quality < 50 ? 2 : 3;
   P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
   wg::CostTabs T;
-  T.lc = lc; T.eob = eobc; T.lfc = wgh::kLevelFixedCosts;
+  static uint16_t lfc_near[wg::LFC_NEAR];  // what the kernel stages in shared memory
+  memcpy(lfc_near, wgh::kLevelFixedCosts, sizeof(lfc_near));
+  T.lc = lc; T.eob = eobc; T.lfc = lfc_near; T.lfc_hi = wgh::kLevelFixedCosts;
   if (m_per_cta == 8) run_phased_waves<8, 128>(P, T, i4costs, order_seed);
   else if (m_per_cta == 12) run_phased_waves<12, 192>(P, T, i4costs, order_seed);
   else run_phased_waves<16, 256>(P, T, i4costs, order_seed);

@@ -1063,7 +1063,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   for (int i = threadIdx.x; i < EOB_SIZE / 8; i += (NT)) reinterpret_cast<uint4*>(s_eob)[i] = reinterpret_cast<const uint4*>(P.eob)[i];    \
   __syncthreads();                                                                                                                 \
   CostTabs T;                                                                                                                      \
-  T.lc = s_lc; T.eob = s_eob; T.lfc = s_lfc
+  T.lc = s_lc; T.eob = s_eob; T.lfc = s_lfc; T.lfc_hi = s_lfc
 
 // One wave of the mode search per launch.  Grid: ceil(tasks / (WARPS * 32/G)) CTAs of WARPS warps.
 template <int G, int WARPS, int MINB>
@@ -1092,7 +1092,7 @@ __global__ void __maxnreg__(NREG) encode_wave_kernel_gt(const EncKernelParams P,
   extern __shared__ __align__(16) unsigned char s_dyn[];
   MBShared* s_mb = reinterpret_cast<MBShared*>(s_dyn);
   CostTabs T;
-  T.lc = P.lc; T.eob = P.eob; T.lfc = P.lfc;
+  T.lc = P.lc; T.eob = P.eob; T.lfc = P.lfc; T.lfc_hi = P.lfc;
   const int warp = threadIdx.x >> 5;
   encode_mb_group<G, false, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, P.i4_costs);
 }

@@ -838,17 +838,17 @@ WG_HD void ph_run_cta(const EncKernelParams& P, PhMB* mbs, const CostTabs& T, co
 template <int M, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) encode_phased_kernel(const EncKernelParams P, int wave) {
   __shared__ __align__(16) uint16_t s_lc[LC_SIZE];
-  __shared__ __align__(16) uint16_t s_lfc[2048];
+  __shared__ __align__(16) uint16_t s_lfc[LFC_NEAR];
   __shared__ __align__(16) uint16_t s_i4cost[1000];
   __shared__ __align__(16) uint16_t s_eob[EOB_SIZE];
   extern __shared__ __align__(16) unsigned char s_dyn[];
   PhMB* mbs = reinterpret_cast<PhMB*>(s_dyn);
   for (int i = threadIdx.x; i < LC_SIZE / 8; i += NT) reinterpret_cast<uint4*>(s_lc)[i] = reinterpret_cast<const uint4*>(P.lc)[i];
-  for (int i = threadIdx.x; i < 2048 / 8; i += NT) reinterpret_cast<uint4*>(s_lfc)[i] = reinterpret_cast<const uint4*>(P.lfc)[i];
+  for (int i = threadIdx.x; i < LFC_NEAR / 8; i += NT) reinterpret_cast<uint4*>(s_lfc)[i] = reinterpret_cast<const uint4*>(P.lfc)[i];
   for (int i = threadIdx.x; i < 1000 / 8; i += NT) reinterpret_cast<uint4*>(s_i4cost)[i] = reinterpret_cast<const uint4*>(P.i4_costs)[i];
   for (int i = threadIdx.x; i < EOB_SIZE / 8; i += NT) reinterpret_cast<uint4*>(s_eob)[i] = reinterpret_cast<const uint4*>(P.eob)[i];
   CostTabs T;
-  T.lc = s_lc; T.eob = s_eob; T.lfc = s_lfc;
+  T.lc = s_lc; T.eob = s_eob; T.lfc = s_lfc; T.lfc_hi = P.lfc;
   ph_run_cta<M, NT>(P, mbs, T, s_i4cost, wave, (long long)blockIdx.x * M, (int)threadIdx.x, nullptr);
 }
 #endif

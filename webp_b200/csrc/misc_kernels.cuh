@@ -253,7 +253,7 @@ __global__ void dsp_trellis_kernel(int n, const int16_t* in, SegQuant sq, int fi
                                    TabPtrs tp, int16_t* out, int32_t* nz) {
   __shared__ int16_t s_io[128][16];  // the trellis works in place in shared memory (zigzag-indexed access)
   WG_TID;
-  CostTabs T; T.lc = tp.lc; T.eob = tp.eob; T.lfc = tp.lfc;
+  CostTabs T; T.lc = tp.lc; T.eob = tp.eob; T.lfc = tp.lfc; T.lfc_hi = tp.lfc;
   int16_t* io = s_io[threadIdx.x];
 #pragma unroll
   for (int k = 0; k < 16; ++k) io[k] = in[16 * (size_t)i + k];
@@ -265,7 +265,7 @@ __global__ void dsp_trellis_kernel(int n, const int16_t* in, SegQuant sq, int fi
 __global__ void dsp_token_cost_kernel(int n, const int16_t* levels, const int32_t* nzc, int ctx_type, const int32_t* ctx0, int first,
                                       TabPtrs tp, int32_t* out) {
   WG_TID;
-  CostTabs T; T.lc = tp.lc; T.eob = tp.eob; T.lfc = tp.lfc;
+  CostTabs T; T.lc = tp.lc; T.eob = tp.eob; T.lfc = tp.lfc; T.lfc_hi = tp.lfc;
   int q[16]; load16s16(levels + 16 * (size_t)i, q);
   out[i] = token_cost(q, nzc[i], ctx_type, ctx0[i], first, T);
 }

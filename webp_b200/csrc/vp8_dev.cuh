@@ -63,8 +63,11 @@ enum { LC_LEVELS = 68, LC_SIZE = 4 * 8 * 3 * LC_LEVELS, EOB_SIZE = 4 * 8 * 3 };
 struct CostTabs {
   const uint16_t* lc;
   const uint16_t* eob;
-  const uint16_t* lfc;
+  const uint16_t* lfc;     // VP8LevelFixedCosts: at least the first LFC_NEAR entries (the phased kernel stages only those)
+  const uint16_t* lfc_hi;  // the whole table (levels >= LFC_NEAR: very low quality, rare)
 };
+enum { LFC_NEAR = 512 };
+WG_HD int lfc_at(const CostTabs& T, int v) { return v < LFC_NEAR ? T.lfc[v] : T.lfc_hi[v]; }
 
 // SegmentQuant (internal/lossy/encode.go:311)
 struct SegQuant {
@@ -384,7 +387,7 @@ WG_HD int token_cost(const int* lev, int nz_count, int type, int ctx0, int first
   for (int n = 0; n < 16; ++n) {
     if (n >= first && n <= last) {
       const int v = abs(lev[kZig[n]]);
-      cost += lc[(kBnd[n] * 3 + ctx) * LC_LEVELS + min(v, LC_LEVELS - 1)] + T.lfc[v];
+      cost += lc[(kBnd[n] * 3 + ctx) * LC_LEVELS + min(v, LC_LEVELS - 1)] + lfc_at(T, v);
       ctx = min(v, 2);
     }
   }
@@ -514,146 +517,12 @@ WG_HD int trellis_block_smem(int16_t* io, const SegQuant& sq, int first, int typ
 }
 
 // TrellisQuantizeBlock again (same contract as trellis_block_smem: 16 int16 in shared memory, raster order, coefficients in,
-// levels out, returns last + 1), organised for latency: a macroblock's chain of dependent trellis calls is what a wave of the
-// mode search waits for.  (1) Everything about a position that does not depend on the Viterbi state -- base level, which
-// of the three candidate levels {0, L0, L0+1} exist, their distortion and fixed-cost terms, the nine table costs
-// r[prev ctx][level] -- is computed one position AHEAD, so its shared-memory round trips overlap the previous position's
-// compare/select chain.  (2) The recurrence runs per candidate LEVEL (argmin over the three previous contexts, ties to the
-// lower context) and then scatters the two non-zero levels to their landing context min(level, 2); the reference visits
-// (prev ctx, level) pairs prev-major with strict '<' (encode_trellis.go:173-262), so when both levels land in context 2 the
-// later level wins a tie only if its best previous context is the smaller one.  Rate terms are <= (65535 + 7000) * 21567
-// < 2^31, so rate * lambda is a 32-bit product; scores stay 64-bit.
-struct TrellisPos {
-  int L0;
-  uint32_t flags;     // 1: level L0 exists, 2: level L0+1 exists
-  long long k0, k1;   // fixed-cost * lambda + weighted distortion delta of level L0 / L0+1
-  uint32_t r0[3], rA[3], rB[3];  // (table cost of level 0 / L0 / L0+1 after previous context pc) * lambda
-};
-WG_HD void trellis_prep(const int16_t* io, int n, int quant_dc, int quant_ac, unsigned iq_dc, unsigned iq_ac, const uint16_t* lc,
-                        const uint16_t* lfc, uint32_t lam, TrellisPos& P) {
-  const int zig = c_zigzag[n];
-  const int band = c_bands[n + 1];  // sic: the next position's band (encode_trellis.go:151)
-  const int coeff0 = io[zig];
-  const int quant = (n == 0) ? quant_dc : quant_ac;
-  const unsigned iquant = (n == 0) ? iq_dc : iq_ac;
-  const int L0 = min((int)(((unsigned)coeff0 * iquant) >> 17), 2047);
-  const int thresh = min((int)(((unsigned)coeff0 * iquant + 65536u) >> 17), 2047);
-  P.L0 = L0;
-  P.flags = ((L0 > 0 && L0 <= thresh) ? 1u : 0u) | ((L0 + 1 <= 2047 && L0 + 1 <= thresh) ? 2u : 0u);
-  const int c0sq = coeff0 * coeff0;
-  const int e0 = coeff0 - L0 * quant, e1 = coeff0 - (L0 + 1) * quant;
-  const int wt256 = c_weight_trellis[zig] * 256;
-  P.k0 = (long long)(e0 * e0 - c0sq) * wt256 + (long long)((uint32_t)lfc[L0] * lam);
-  P.k1 = (long long)(e1 * e1 - c0sq) * wt256 + (long long)((uint32_t)lfc[min(L0 + 1, 2047)] * lam);
-  const int li0 = min(L0, LC_LEVELS - 1), li1 = min(L0 + 1, LC_LEVELS - 1);
-  const uint16_t* row = lc + band * 3 * LC_LEVELS;
-#pragma unroll
-  for (int pc = 0; pc < 3; ++pc) {
-    P.r0[pc] = (uint32_t)row[pc * LC_LEVELS] * lam;
-    P.rA[pc] = (uint32_t)row[pc * LC_LEVELS + li0] * lam;
-    P.rB[pc] = (uint32_t)row[pc * LC_LEVELS + li1] * lam;
-  }
-}
-WG_HD void trellis_argmin3(long long a0, long long a1, long long a2, long long* best, uint32_t* arg) {
-  long long b = a0; uint32_t k = 0;
-  if (a1 < b) { b = a1; k = 1; }
-  if (a2 < b) { b = a2; k = 2; }
-  *best = b; *arg = k;
-}
-WG_HD int trellis_block_v2(int16_t* io, const SegQuant& sq, int first, int type, int initial_ctx, int lambda, const CostTabs& T) {
-  const int quant_ac = sq.quant, quant_dc = sq.dc_quant;
-  const unsigned iq_ac = (unsigned)sq.iquant, iq_dc = (unsigned)sq.dc_iquant;
-  uint32_t neg_mask = 0;  // bit i: raster coefficient i is negative
-  {
-    bool non_zero = false;  // all-zero pre-scan with neutral bias (encode_trellis.go:39-98)
-    int c0[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int raw = io[i];
-      c0[i] = max(abs(raw) + sq.sharpen[i], 0);
-      neg_mask |= (raw < 0 ? 1u : 0u) << i;
-      if (i > 0) non_zero |= (((unsigned)c0[i] * iq_ac) >> 17) > 0;
-      else non_zero |= first == 0 && (((unsigned)c0[0] * iq_dc) >> 17) > 0;
-    }
-    if (!non_zero) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) io[i] = 0;
-      return 0;
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) io[i] = (int16_t)c0[i];
-  }
-  initial_ctx = min(initial_ctx, 2);
-  const uint16_t* lc = T.lc + type * (8 * 3 * LC_LEVELS);
-  const uint16_t* eob = T.eob + type * (8 * 3);
-  const long long kBig = 1ll << 60, kThr = 1ll << 59;
-  long long ps0 = initial_ctx == 0 ? 0 : kBig, ps1 = initial_ctx == 1 ? 0 : kBig, ps2 = initial_ctx == 2 ? 0 : kBig;
-  const uint32_t lam = (uint32_t)lambda;
-  long long best_terminal = (long long)((uint32_t)eob[c_bands[first] * 3 + initial_ctx] * lam);
-  int best_last_n = -1, best_last_ctx = -1;
-  unsigned long long pw0 = 0, pw1 = 0, pw2 = 0;  // survivor paths, 10 bits per position: positions 0-5, 6-11, 12-15
-  TrellisPos cur;
-  trellis_prep(io, first, quant_dc, quant_ac, iq_dc, iq_ac, lc, T.lfc, lam, cur);
-#pragma unroll 1
-  for (int n = first; n < 16; ++n) {
-    TrellisPos nxt;
-    trellis_prep(io, min(n + 1, 15), quant_dc, quant_ac, iq_dc, iq_ac, lc, T.lfc, lam, nxt);  // independent of the state below
-    const uint32_t eb1 = (n < 15) ? (uint32_t)eob[c_bands[n + 1] * 3 + 1] * lam : 0u;
-    const uint32_t eb2 = (n < 15) ? (uint32_t)eob[c_bands[n + 1] * 3 + 2] * lam : 0u;
-    const int L0 = cur.L0;
-    io[c_zigzag[n]] = (int16_t)L0;  // the backtrack only needs the base level (position n + 1 was read above)
-    long long s0, sA, sB;
-    uint32_t p0, pA, pB;
-    trellis_argmin3(ps0 + cur.r0[0], ps1 + cur.r0[1], ps2 + cur.r0[2], &s0, &p0);
-    trellis_argmin3(ps0 + cur.rA[0], ps1 + cur.rA[1], ps2 + cur.rA[2], &sA, &pA);
-    trellis_argmin3(ps0 + cur.rB[0], ps1 + cur.rB[1], ps2 + cur.rB[2], &sB, &pB);
-    sA += cur.k0; sB += cur.k1;
-    const bool hasA = cur.flags & 1u, hasB = (cur.flags & 2u) != 0;
-    // level L0 lands in context min(L0, 2), level L0 + 1 in min(L0 + 1, 2)
-    const bool a1 = hasA && L0 == 1, b1 = hasB && L0 == 0;   // at most one of them
-    const bool a2 = hasA && L0 >= 2, b2 = hasB && L0 >= 1;
-    const long long cs1 = a1 ? sA : (b1 ? sB : kBig);
-    const uint32_t p1 = a1 ? pA : pB;
-    const bool take_b = b2 && (!a2 || sB < sA || (sB == sA && pB < pA));
-    const long long cs2 = take_b ? sB : (a2 ? sA : kBig);
-    const uint32_t p2 = take_b ? (pB | 8u) : pA;
-    const bool v0 = s0 < kThr, v1 = cs1 < kThr, v2 = cs2 < kThr;
-    const unsigned long long ent = (unsigned long long)((p0 | (v0 ? 4u : 0u)) | ((p1 | (v1 ? 4u : 0u)) << 3) |
-                                                        (((p2 & 3u) | (v2 ? 4u : 0u) | (p2 & 8u)) << 6));
-    const int sh = (n % 6) * 10;
-    if (n < 6) pw0 |= ent << sh; else if (n < 12) pw1 |= ent << sh; else pw2 |= ent << sh;
-    {
-      const long long t1 = cs1 + eb1;  // unreachable states stay >= kThr and never win
-      const bool w1 = t1 < best_terminal;
-      best_terminal = w1 ? t1 : best_terminal; best_last_n = w1 ? n : best_last_n; best_last_ctx = w1 ? 1 : best_last_ctx;
-      const long long t2 = cs2 + eb2;
-      const bool w2 = t2 < best_terminal;
-      best_terminal = w2 ? t2 : best_terminal; best_last_n = w2 ? n : best_last_n; best_last_ctx = w2 ? 2 : best_last_ctx;
-    }
-    ps0 = v0 ? s0 : kBig; ps1 = v1 ? cs1 : kBig; ps2 = v2 ? cs2 : kBig;
-    cur = nxt;
-  }
-  int ctx = best_last_ctx, last = 0;
-  if (first == 1) io[0] = 0;
-#pragma unroll 4
-  for (int n = 15; n >= first; --n) {
-    const int zig = c_zigzag[n];
-    const unsigned long long w = n < 6 ? pw0 : (n < 12 ? pw1 : pw2);
-    const uint32_t ent = (uint32_t)(w >> ((n % 6) * 10)) & 0x3ffu;
-    const uint32_t e = ctx == 0 ? (ent & 7u) : (ctx == 1 ? ((ent >> 3) & 7u) : ((ent >> 6) & 15u));
-    const bool take = n <= best_last_n && (e & 4u);
-    const int L0 = io[zig];
-    const int mag = ctx == 0 ? 0 : (ctx == 1 ? 1 : L0 + (int)((e >> 3) & 1u));
-    const int lv = ((neg_mask >> zig) & 1u) ? -mag : mag;
-    io[zig] = (int16_t)(take ? lv : 0);
-    last = (take && lv != 0 && last == 0) ? n + 1 : last;
-    ctx = take ? (int)(e & 3u) : ctx;
-  }
-  return last;
-}
-
-// Third formulation of TrellisQuantizeBlock (same contract again), cut for instruction count: a trellis position was ~275 SASS
-// instructions in trellis_block_v2, most of them 64-bit compare / select pairs and index bookkeeping.  Here every score is
+// levels out, returns last + 1), organised for the latency of one call -- a macroblock's chain of dependent trellis calls is
+// what a wave of the mode search waits for.  Everything about a position that does not depend on the Viterbi state (base
+// level, which of the candidate levels {0, L0, L0+1} exist, their distortion and fixed-cost terms, where their table costs
+// sit) is computed one position AHEAD, and the recurrence runs per candidate LEVEL (minimum over the three previous contexts)
+// before the two non-zero levels scatter to their landing context min(level, 2).  A straightforward 64-bit version of that
+// was ~275 SASS instructions per position, most of them 64-bit compare / select pairs and index bookkeeping.  Here every score is
 // kept multiplied by 64, which frees the low six bits of the 64-bit word for the bookkeeping the comparisons have to carry:
 //   * a transition key is (score * 64 | prev ctx): the minimum over the three previous contexts is then a plain signed
 //     minimum, and equal scores resolve to the lower context exactly as the reference's strict '<' in loop order does;
@@ -691,7 +560,7 @@ struct TrellisPos3 {  // what a position contributes, independent of the Viterbi
   long long k0, k1;    // 64 * (fixed-cost * lambda + weighted distortion delta) of level L0 / L0+1
   int iA, iB;          // offsets of the cost-table entries of level L0 / L0+1 in the row of previous context 0
 };
-WG_HD void trellis_prep3(const int16_t* io, int n, int quant_dc, int quant_ac, unsigned iq_dc, unsigned iq_ac, const uint16_t* lfc,
+WG_HD void trellis_prep3(const int16_t* io, int n, int quant_dc, int quant_ac, unsigned iq_dc, unsigned iq_ac, const CostTabs& T,
                          uint32_t lam64, TrellisPos3& P) {
   const int zig = c_zigzag[n];
   const int coeff0 = io[zig];
@@ -704,8 +573,8 @@ WG_HD void trellis_prep3(const int16_t* io, int n, int quant_dc, int quant_ac, u
   const int c0sq = coeff0 * coeff0;
   const int e0 = coeff0 - L0 * quant, e1 = coeff0 - (L0 + 1) * quant;
   const int wt = c_weight_trellis[zig] * (256 * 64);
-  P.k0 = wg_mad_wide(lfc[L0], lam64, (long long)(e0 * e0 - c0sq) * wt);
-  P.k1 = wg_mad_wide(lfc[min(L0 + 1, 2047)], lam64, (long long)(e1 * e1 - c0sq) * wt);
+  P.k0 = wg_mad_wide((uint32_t)lfc_at(T, L0), lam64, (long long)(e0 * e0 - c0sq) * wt);
+  P.k1 = wg_mad_wide((uint32_t)lfc_at(T, min(L0 + 1, 2047)), lam64, (long long)(e1 * e1 - c0sq) * wt);
   P.iA = min(L0, LC_LEVELS - 1);
   P.iB = min(L0 + 1, LC_LEVELS - 1);
 }
@@ -747,7 +616,7 @@ WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type,
   uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;  // survivor entries, newest in the low 10 bits of w0
   const int kThrHi = 1 << 23;  // key < kThr  <=>  its upper word < 2^23 (scores may be negative)
   TrellisPos3 cur;
-  trellis_prep3(io, first, quant_dc, quant_ac, iq_dc, iq_ac, T.lfc, lam64, cur);
+  trellis_prep3(io, first, quant_dc, quant_ac, iq_dc, iq_ac, T, lam64, cur);
 #pragma unroll 1
   for (int n = first; n < 16; ++n) {
     // this position's table costs: addresses known since the previous iteration, issued first ...
@@ -759,7 +628,7 @@ WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type,
     const uint32_t eb1 = (n < 15) ? eob[band * 3 + 1] : 0u, eb2 = (n < 15) ? eob[band * 3 + 2] : 0u;
     // ... then the next position's state-independent half while those loads are in flight
     TrellisPos3 nxt;
-    trellis_prep3(io, min(n + 1, 15), quant_dc, quant_ac, iq_dc, iq_ac, T.lfc, lam64, nxt);
+    trellis_prep3(io, min(n + 1, 15), quant_dc, quant_ac, iq_dc, iq_ac, T, lam64, nxt);
     const int L0 = cur.L0;
     io[c_zigzag[n]] = (int16_t)L0;  // the backtrack only needs the base level (position n + 1 was read above)
     const long long q0 = ps0, q1 = ps1 | 1, q2 = ps2 | 2;
