@@ -104,6 +104,24 @@ long orc_encode_batch(const uint8_t* rgba, int n, int stride, int w, int h, cons
   return bad ? -1 : total.load();
 }
 
+// Integer-operation counts of ONE encode.  Only the build with -DORC_COUNT_OPS (liboracle_ops.so) counts;
+// the plain library returns -1.  counts[OP_STAGES] receives units per stage, weights[OP_STAGES] the operations per unit
+// (vp8_common.h kOpWeight); returns the number of stages.
+int orc_encode_ops(const uint8_t* rgba, int stride, int w, int h, const OrcEncCfg* cfg, unsigned long long* counts, unsigned* weights) {
+#ifdef ORC_COUNT_OPS
+  for (int i = 0; i < OP_STAGES; ++i) g_op_count[i] = 0;
+  std::vector<uint8_t> out((size_t)w * h * 2 + (1 << 16));
+  const long r = orc_encode(rgba, stride, w, h, cfg, out.data(), (long)out.size(), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+  if (r < 0) return -2;
+  for (int i = 0; i < OP_STAGES; ++i) { counts[i] = g_op_count[i]; weights[i] = kOpWeight[i]; }
+  return OP_STAGES;
+#else
+  (void)rgba; (void)stride; (void)w; (void)h; (void)cfg; (void)counts; (void)weights;
+  return -1;
+#endif
+}
+const char* orc_op_name(int i) { return (i >= 0 && i < OP_STAGES) ? kOpName[i] : ""; }
+
 // Decode header only: 0 ok.
 int orc_decode_info(const uint8_t* data, long len, int* w, int* h, int* mb_w, int* mb_h) {
   const uint8_t* vp8; size_t n;

@@ -13,6 +13,7 @@ static inline int mul2(int a) { return (a * 35468) >> 16; }        // transforms
 
 // iTransformOne (transforms.go:265): dst = clip(ref + IDCT(in)); ref/dst BPS-strided, may alias.
 static inline void itransform_one(const uint8_t* ref, const int16_t* in, uint8_t* dst) {
+  ORC_COUNT(OP_ITRANSFORM, 1);
   int tmp[16];
   for (int i = 0; i < 4; ++i) {  // vertical pass, column i
     const int a = in[i] + in[8 + i];
@@ -59,6 +60,7 @@ static inline void transform_ac3(const int16_t* in, uint8_t* dst) {  // transfor
 }
 // transformWHT (transforms.go:223): out has stride 16 between DCs.
 static inline void transform_wht(const int16_t* in, int16_t* out) {
+  ORC_COUNT(OP_IWHT, 1);
   int tmp[16];
   for (int i = 0; i < 4; ++i) {
     const int a0 = in[0 + i] + in[12 + i];
@@ -85,6 +87,7 @@ static inline void transform_wht(const int16_t* in, int16_t* out) {
 }
 // fTransform (transforms.go:371)
 static inline void ftransform(const uint8_t* src, const uint8_t* ref, int16_t* out) {
+  ORC_COUNT(OP_FTRANSFORM, 1);
   int tmp[16];
   for (int j = 0; j < 4; ++j) {
     const int d0 = src[j * BPS + 0] - ref[j * BPS + 0];
@@ -110,6 +113,7 @@ static inline void ftransform(const uint8_t* src, const uint8_t* ref, int16_t* o
 }
 // fTransformWHT (transforms.go:500): flat 4x4 DC array in, 16 out.
 static inline void ftransform_wht(const int16_t* in, int16_t* out) {
+  ORC_COUNT(OP_FWHT, 1);
   int tmp[16];
   for (int i = 0; i < 4; ++i) {
     const int a0 = in[i * 4 + 0] + in[i * 4 + 2];
@@ -146,11 +150,13 @@ static inline void pred_square(int mode, uint8_t* buf, int off, int size) {
   switch (mode) {
     case 0: {
       int dc = 0;
+      ORC_COUNT(OP_PRED_DC_SUM, 2 * size + 2);
       for (int i = 0; i < size; ++i) dc += d[i - BPS] + d[-1 + i * BPS];
       fill_block(d, size, (dc + size) >> (shift + 1));
     } break;
     case 1: {
       const int tl = d[-1 - BPS];
+      ORC_COUNT(OP_PRED_TM_PIXEL, size * size);
       for (int j = 0; j < size; ++j) {
         const int base = d[-1 + j * BPS] - tl;
         for (int i = 0; i < size; ++i) d[i + j * BPS] = clip8(base + d[i - BPS]);
@@ -164,11 +170,13 @@ static inline void pred_square(int mode, uint8_t* buf, int off, int size) {
       break;
     case 4: {
       int dc = 0;
+      ORC_COUNT(OP_PRED_DC_SUM, size + 2);
       for (int i = 0; i < size; ++i) dc += d[-1 + i * BPS];
       fill_block(d, size, (dc + (size >> 1)) >> shift);
     } break;
     case 5: {
       int dc = 0;
+      ORC_COUNT(OP_PRED_DC_SUM, size + 2);
       for (int i = 0; i < size; ++i) dc += d[i - BPS];
       fill_block(d, size, (dc + (size >> 1)) >> shift);
     } break;
@@ -181,6 +189,7 @@ static inline void pred_chroma8(int mode, uint8_t* buf, int off) { pred_square(m
 
 // PredLuma4Direct (predict_lossy.go:185-451)
 static inline void pred_luma4(int mode, uint8_t* buf, int off) {
+  ORC_COUNT(OP_PRED4, 1);
   uint8_t* d = buf + off;
 #define DST(x, y) d[(x) + (y)*BPS]
   const int tl = d[-1 - BPS];
@@ -275,6 +284,7 @@ static inline void pred_luma4(int mode, uint8_t* buf, int off) {
 
 // ---------------------------------------------------------------- ssim.go:188-335
 static inline int sse4x4(const uint8_t* a, const uint8_t* b) {
+  ORC_COUNT(OP_SSE4X4, 1);
   int s = 0;
   for (int j = 0; j < 4; ++j)
     for (int i = 0; i < 4; ++i) {
@@ -284,6 +294,7 @@ static inline int sse4x4(const uint8_t* a, const uint8_t* b) {
   return s;
 }
 static inline int sse16x16(const uint8_t* a, const uint8_t* b) {
+  ORC_COUNT(OP_SSE4X4, 16);
   int s = 0;
   for (int j = 0; j < 16; ++j)
     for (int i = 0; i < 16; ++i) {
@@ -294,6 +305,7 @@ static inline int sse16x16(const uint8_t* a, const uint8_t* b) {
 }
 static const uint16_t kWeightY[16] = {38, 32, 20, 9, 32, 28, 17, 7, 20, 17, 10, 4, 9, 7, 4, 2};
 static inline int ttransform(const uint8_t* in, const uint16_t* w) {  // ssim.go:266
+  ORC_COUNT(OP_TTRANSFORM, 1);
   int tmp[16];
   for (int i = 0; i < 4; ++i) {
     const uint8_t* p = in + i * BPS;

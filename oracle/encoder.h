@@ -116,6 +116,7 @@ static const int kReverseZigzag[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9,
 
 // ------------------------------------------------------------------ quantization (encode_quant.go)
 static inline int quantize_coeffs(const int16_t* in, int16_t* out, const SegmentQuant* sq, int first) {
+  ORC_COUNT(OP_QUANT_COEFF, 16 - first);
   int max_zz = -1;
   if (first == 0) {
     int v = in[0];
@@ -145,10 +146,12 @@ static inline int quantize_coeffs(const int16_t* in, int16_t* out, const Segment
   return max_zz + 1;
 }
 static inline void dequant_coeffs(const int16_t* in, int16_t* out, const SegmentQuant* sq) {
+  ORC_COUNT(OP_DEQUANT_BLOCK, 1);
   out[0] = (int16_t)(in[0] * sq->dc_quant);
   for (int n = 1; n < 16; ++n) out[n] = (int16_t)(in[n] * sq->quant);
 }
 static inline uint64_t rd_score(int disto, int rate, int lambda) {
+  ORC_COUNT(OP_MODE_SCORE, 1);
   return (uint64_t)(int64_t)rate * (uint64_t)(int64_t)lambda + 256 * (uint64_t)(int64_t)disto;
 }
 static inline int variable_level_cost(int level, const uint8_t* probas) {  // encode_quant.go:248
@@ -168,6 +171,7 @@ static inline int token_cost(const int16_t* coeffs, int nz_count, int type, cons
   if (nz_count <= first) return kEntropyCost[proba->bands[type][kBands[first]][ctx0][0]];
   const int last = nz_count - 1;
   int cost = 0, ctx = ctx0;
+  ORC_COUNT(OP_TOKEN_COEFF, (last < 15 ? last + 2 : 16) - first);
   for (int n = first; n < 16; ++n) {
     const uint8_t* pp = proba->bands[type][kBands[n]][ctx];
     int v = coeffs[kZigzag[n]];
@@ -200,6 +204,7 @@ static inline int trellis_quantize_block(const int16_t* in_, int16_t* out, const
   {  // all-zero pre-scan with neutral bias (encode_trellis.go:39-98)
     bool non_zero = false;
     for (int n = first; n < 16 && !non_zero; ++n) {
+      ORC_COUNT(OP_TRELLIS_PRESCAN_COEFF, 1);
       int raw = in_[kZigzag[n]];
       if (raw < 0) raw = -raw;
       int c = raw + sq->sharpen[kZigzag[n]];
@@ -229,6 +234,7 @@ static inline int trellis_quantize_block(const int16_t* in_, int16_t* out, const
   int best_last_n = -1, best_last_ctx = -1;
   const int64_t lam = lambda;
   for (int n = first; n < 16; ++n) {
+    ORC_COUNT(OP_TRELLIS_POS, 1);
     const int zig = kZigzag[n];
     const int band = kBands[n + 1];  // sic: next position's band (encode_trellis.go:151)
     int raw = in[zig];
@@ -270,6 +276,7 @@ static inline int trellis_quantize_block(const int16_t* in_, int16_t* out, const
     const int64_t disto_l0 = 256 * delta_d0, disto_l1 = 256 * delta_d1;
     for (int pc = 0; pc < 3; ++pc) {
       if (!prev[pc].valid) continue;
+      ORC_COUNT(OP_TRELLIS_TRANS, 1 + (has_l0 ? 1 : 0) + (has_l1 ? 1 : 0));
       const int64_t prev_score = prev[pc].score;
       const uint8_t* p = band_probas[pc];
       const int not_eob = kEntropyCost[255 - p[0]];
@@ -294,6 +301,7 @@ static inline int trellis_quantize_block(const int16_t* in_, int16_t* out, const
       if (curr[c].valid) path[n][c] = Path{curr[c].level, curr[c].prev_ctx, true};
     for (int c = 1; c < 3; ++c) {
       if (!curr[c].valid) continue;
+      ORC_COUNT(OP_TRELLIS_TERMINAL, 1);
       int64_t eob_score = curr[c].score;
       if (n < 15) eob_score += (int64_t)kEntropyCost[proba->bands[type][band][c][0]] * lam;
       if (eob_score < best_terminal) {
@@ -307,6 +315,7 @@ static inline int trellis_quantize_block(const int16_t* in_, int16_t* out, const
   if (best_last_n < 0) return 0;
   int ctx = best_last_ctx, last = 0;
   for (int n = best_last_n; n >= first; --n) {
+    ORC_COUNT(OP_TRELLIS_BACKTRACK, 1);
     if (path[n][ctx].valid) {
       const int zig = kZigzag[n];
       out[zig] = path[n][ctx].level;

@@ -17,6 +17,32 @@
 
 namespace orc {
 
+// Integer-operation accounting ("the oracle must carry exact per-stage op counters, compile-time switch").
+// With -DORC_COUNT_OPS every primitive on the encoder's mode-search path counts its invocations (or, where the work is data
+// dependent, its inner units: trellis positions and transitions actually evaluated, coefficients the cost walk visits,
+// coefficients quantised).  kOpWeight is the number of scalar integer operations (add / sub / mul / shift / compare /
+// select / abs / clip; loads, stores and address arithmetic not counted) of ONE unit in the reference's formulation, counted
+// by hand from the cited Go source once; bench.py reports sum(count * weight) / time against the integer-issue peak.
+enum OpStage { OP_FTRANSFORM, OP_ITRANSFORM, OP_FWHT, OP_IWHT, OP_QUANT_COEFF, OP_DEQUANT_BLOCK, OP_SSE4X4, OP_TTRANSFORM, OP_PRED4,
+               OP_PRED_TM_PIXEL, OP_PRED_DC_SUM, OP_TRELLIS_PRESCAN_COEFF, OP_TRELLIS_POS, OP_TRELLIS_TRANS, OP_TRELLIS_TERMINAL,
+               OP_TRELLIS_BACKTRACK, OP_TOKEN_COEFF, OP_MODE_SCORE, OP_STAGES };
+static const char* const kOpName[OP_STAGES] = {"ftransform", "itransform", "fwht", "iwht", "quantize_coeff", "dequant_block", "sse4x4",
+                                               "ttransform", "pred4", "pred_tm_pixel", "pred_dc_sum", "trellis_prescan_coeff", "trellis_pos",
+                                               "trellis_transition", "trellis_terminal", "trellis_backtrack", "token_cost_coeff", "mode_score"};
+// transforms.go:371 (2 x 4 butterflies of 22 ops), :265 (18 + 35 per row/column), :500 / :223 (WHT), encode_quant.go:16 per
+// coefficient (sign, abs, +sharpen, clamp, mul, +bias, shift, min, sign, nz compare + max), :81 (16 mul), ssim.go:188 (16 x
+// sub/mul/add), :266 (32 + 80), predict_lossy.go:185-424 (~30 averaged over the ten modes), TM: add, sub, clip(2) per pixel, DC:
+// one add per border sample, encode_trellis.go: pre-scan 6 per coefficient, 30 per position (level / threshold / two distortion
+// deltas), 8 per (valid previous context, candidate level) transition (rate sum, mul, two adds, compare, select), 4 per terminal
+// check, 4 per backtrack step, encode_quant.go:170 6 per coefficient walked, RDScore 3.
+static const unsigned kOpWeight[OP_STAGES] = {176, 212, 80, 84, 11, 16, 48, 112, 30, 4, 1, 6, 30, 8, 4, 4, 6, 3};
+#ifdef ORC_COUNT_OPS
+inline thread_local unsigned long long g_op_count[OP_STAGES] = {0};
+#define ORC_COUNT(stage, n) (orc::g_op_count[orc::stage] += (unsigned long long)(n))
+#else
+#define ORC_COUNT(stage, n) ((void)0)
+#endif
+
 #include "vp8_tables.inc"
 
 // internal/lossy/constants.go:66-75

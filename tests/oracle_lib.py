@@ -81,6 +81,30 @@ def encode(rgba, cfg=None, taps=False):
     return (data, t) if taps else data
 
 
+_OPS_LIB = None
+
+
+def encode_ops(rgba, cfg=None):
+    """Integer operations of one encode, counted by the oracle built with its per-stage counters (oracle/vp8_common.h OpStage,
+    liboracle_ops.so): {stage name: units x operations per unit}.  SURVEY.md 8(d): the numerator of the integer-issue roofline."""
+    global _OPS_LIB
+    if _OPS_LIB is None:
+        path = os.path.join(ROOT, "oracle", "_build", "liboracle_ops.so")
+        if not os.path.exists(path):
+            build()
+        _OPS_LIB = C.CDLL(path)
+        _OPS_LIB.orc_op_name.restype = C.c_char_p
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = rgba.shape[:2]
+    cfg = cfg or default_cfg()
+    cnt = (C.c_ulonglong * 64)()
+    wt = (C.c_uint * 64)()
+    n = _OPS_LIB.orc_encode_ops(_p(rgba), C.c_int(rgba.strides[0]), w, h, C.byref(cfg), cnt, wt)
+    if n < 0:
+        raise RuntimeError("orc_encode_ops failed: %d" % n)
+    return {_OPS_LIB.orc_op_name(i).decode(): int(cnt[i]) * int(wt[i]) for i in range(n)}
+
+
 def encode_batch(rgba_batch, cfg=None, threads=1):
     """rgba_batch uint8 [n][h][w][4]; returns total compressed bytes (timing leg)."""
     rgba_batch = np.ascontiguousarray(rgba_batch, dtype=np.uint8)

@@ -25,11 +25,10 @@ struct EncKernelParams {
   const uint16_t* eob_img;      // [n][EOB_SIZE]
   int serial_gpw;               // encode_serial_tab_kernel: macroblock groups (images) per warp actually used, 1..32/G (0 = all)
   uint32_t* ctx2;               // [n][nmb] Method < 3 / serial RD: trial 4x4 modes of the bottom row / right column (mode-cost context)
-  int* progress;                // [n][mb_h] finished macroblocks per row (persistent kernel)
-  unsigned long long* work_counter;  // next group to claim (persistent kernel)
-  const long long* wave_start;  // [waves + 1] prefix of groups per wave (persistent kernel)
-  long long total_groups;
-  int* error_flag;              // set when a dependency wait exceeded its iteration cap
+#ifdef WG_PHASE_CLOCK
+  unsigned long long* phase_clock;  // profiling build: CTA `clock_cta` timestamps its phase boundaries
+  int clock_cta;
+#endif
   unsigned int* stats;          // [n][4][8][3][11][2] token statistics (ProbaStats, encode_proba.go), zeroed before the waves
   uint8_t* out_hdr;             // [n][nmb][48]: mb_type,i16,uv,segment,skip,nz_dc,0,0, modes[16], nz[24]
   int16_t* out_coeffs;          // [n][nmb][400]

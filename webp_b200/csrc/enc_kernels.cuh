@@ -162,14 +162,13 @@ __device__ __forceinline__ void stat_block_dev(const LevT* lev, int n_coeffs, in
   }
 }
 
-// Loads of data another macroblock produced (reconstruction borders, NZ context words, neighbour modes).  In the
-// persistent kernel producers and consumers run concurrently on different SMs, so these must bypass the
-// non-coherent L1 (ld.global.cg); the per-wave kernels see them through a kernel boundary and use plain loads.
-template <bool PERSIST, class Tp>
-__device__ __forceinline__ Tp ldn(const Tp* p) { return PERSIST ? __ldcg(p) : *p; }
+// Loads of data another macroblock produced (reconstruction borders, NZ context words, neighbour modes): they come through a
+// kernel boundary (one launch per wave / macroblock index), so plain loads see them.
+template <class Tp>
+__device__ __forceinline__ Tp ldn(const Tp* p) { return *p; }
 
 // The mode search of MPW = 32/G macroblocks by one warp: macroblock `task_base + lane/G` of wave `wave`.
-template <int G, bool PERSIST, bool FAST, bool SERIAL = false, bool SYNC = false>
+template <int G, bool FAST, bool SERIAL = false>
 __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wave, long long task_base, MBShared* s_mb_warp,
                                                 const CostTabs& T_launch, const uint16_t* s_i4cost) {
   const int lane = threadIdx.x & 31;
@@ -208,31 +207,6 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   const SegParams& seg = P.img[img].seg[segment];
   const bool trellis = P.method >= 4;
 
-  if (PERSIST) {
-    // Dataflow scheduling: wait until the left macroblock and the top-right one (which implies top and top-left) are
-    // done.  progress[img][row] = macroblocks finished in that row (a row finishes strictly left to right).  Work is
-    // claimed in wave order by running warps only, so every dependency is already running or done: no deadlock; the
-    // iteration cap only turns a logic error into a reported failure instead of a hung GPU.
-    volatile int* prog = P.progress + (size_t)img * P.mb_h;
-    const int need_top = (active && my > 0) ? min(mx + 2, P.mb_w) : 0, need_left = active ? mx : 0;
-    int spins = 0;
-    unsigned backoff = 200;
-    for (;;) {
-      bool ok = true;
-      if (gl == 0) {  // one polling lane per macroblock keeps the L2 traffic of waiting warps negligible
-        if (need_top > 0) ok = prog[my - 1] >= need_top;
-        if (ok && need_left > 0) ok = prog[my] >= need_left;
-      }
-      if (__all_sync(0xffffffffu, ok)) break;
-      __nanosleep(backoff);
-      backoff = min(backoff * 2, 4000u);
-      bool bail = ++spins > (1 << 20);
-      if (lane == 0) bail = bail || *reinterpret_cast<volatile int*>(P.error_flag) != 0;
-      if (__any_sync(0xffffffffu, bail)) { if (lane == 0) atomicExch(P.error_flag, 1); break; }
-    }
-    __threadfence();
-  }
-
   // ---- 1. import source MB with edge replication (encode_iterator.go:145) + 2. prediction context
   if (active) {
     const int x0 = mx * 16, y0 = my * 16;
@@ -262,23 +236,23 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       int v = 127;
       if (my > 0) {
         const int xx = (i < 16 || mx < P.mb_w - 1) ? x0 + i : x0 + 15;
-        v = ldn<PERSIST>(&rec_y[(size_t)(y0 - 1) * y_stride + xx]);
+        v = ldn(&rec_y[(size_t)(y0 - 1) * y_stride + xx]);
       }
       o[Y_OFF - BPS + i] = (uint8_t)v;
     }
-    for (int j = gl; j < 16; j += G) o[Y_OFF - 1 + j * BPS] = mx > 0 ? ldn<PERSIST>(&rec_y[(size_t)(y0 + j) * y_stride + x0 - 1]) : 129;
+    for (int j = gl; j < 16; j += G) o[Y_OFF - 1 + j * BPS] = mx > 0 ? ldn(&rec_y[(size_t)(y0 + j) * y_stride + x0 - 1]) : 129;
     for (int i = gl; i < 16; i += G) {
       const int pl = i >> 3, c = i & 7;
       const uint8_t* rp = pl ? rec_v : rec_u;
       const int off = pl ? V_OFF : U_OFF;
-      o[off - BPS + c] = my > 0 ? ldn<PERSIST>(&rp[(size_t)(my * 8 - 1) * uv_stride + mx * 8 + c]) : 127;
-      o[off - 1 + c * BPS] = mx > 0 ? ldn<PERSIST>(&rp[(size_t)(my * 8 + c) * uv_stride + mx * 8 - 1]) : 129;
+      o[off - BPS + c] = my > 0 ? ldn(&rp[(size_t)(my * 8 - 1) * uv_stride + mx * 8 + c]) : 127;
+      o[off - 1 + c * BPS] = mx > 0 ? ldn(&rp[(size_t)(my * 8 + c) * uv_stride + mx * 8 - 1]) : 129;
     }
     if (gl == 0) {
       const bool both = mx > 0 && my > 0;
-      o[Y_OFF - BPS - 1] = both ? ldn<PERSIST>(&rec_y[(size_t)(y0 - 1) * y_stride + x0 - 1]) : (my > 0 ? 129 : 127);
-      o[U_OFF - BPS - 1] = both ? ldn<PERSIST>(&rec_u[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1]) : (my > 0 ? 129 : 127);
-      o[V_OFF - BPS - 1] = both ? ldn<PERSIST>(&rec_v[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1]) : (my > 0 ? 129 : 127);
+      o[Y_OFF - BPS - 1] = both ? ldn(&rec_y[(size_t)(y0 - 1) * y_stride + x0 - 1]) : (my > 0 ? 129 : 127);
+      o[U_OFF - BPS - 1] = both ? ldn(&rec_u[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1]) : (my > 0 ? 129 : 127);
+      o[V_OFF - BPS - 1] = both ? ldn(&rec_v[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1]) : (my > 0 ? 129 : 127);
     }
   }
   __syncwarp();
@@ -294,24 +268,24 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   int top_modes[4] = {0, 0, 0, 0}, left_modes[4] = {0, 0, 0, 0};
   if (active) {
     if (my > 0) {
-      const uint32_t cw = ldn<PERSIST>(&ctxw[mb_idx - P.mb_w]);
+      const uint32_t cw = ldn(&ctxw[mb_idx - P.mb_w]);
       top_nz = cw & 0xff;
       top_nz_dc = (cw >> 16) & 1;
       const uint8_t* th = hdr - (size_t)P.mb_w * 48;
       if (FAST || SERIAL) {
-        const uint32_t tm = ldn<PERSIST>(&P.ctx2[(size_t)img * nmb + mb_idx - P.mb_w]);
+        const uint32_t tm = ldn(&P.ctx2[(size_t)img * nmb + mb_idx - P.mb_w]);
         for (int i = 0; i < 4; ++i) top_modes[i] = (tm >> (4 * i)) & 15;
-      } else if (ldn<PERSIST>(&th[0]) == 1) { top_modes[0] = ldn<PERSIST>(&th[8 + 12]); top_modes[1] = ldn<PERSIST>(&th[8 + 13]); top_modes[2] = ldn<PERSIST>(&th[8 + 14]); top_modes[3] = ldn<PERSIST>(&th[8 + 15]); }
+      } else if (ldn(&th[0]) == 1) { top_modes[0] = ldn(&th[8 + 12]); top_modes[1] = ldn(&th[8 + 13]); top_modes[2] = ldn(&th[8 + 14]); top_modes[3] = ldn(&th[8 + 15]); }
     }
     if (mx > 0) {
-      const uint32_t cw = ldn<PERSIST>(&ctxw[mb_idx - 1]);
+      const uint32_t cw = ldn(&ctxw[mb_idx - 1]);
       left_nz = (cw >> 8) & 0xff;
       left_nz_dc = (cw >> 17) & 1;
       const uint8_t* lh = hdr - 48;
       if (FAST || SERIAL) {
-        const uint32_t lm = ldn<PERSIST>(&P.ctx2[(size_t)img * nmb + mb_idx - 1]);
+        const uint32_t lm = ldn(&P.ctx2[(size_t)img * nmb + mb_idx - 1]);
         for (int i = 0; i < 4; ++i) left_modes[i] = (lm >> (16 + 4 * i)) & 15;
-      } else if (ldn<PERSIST>(&lh[0]) == 1) { left_modes[0] = ldn<PERSIST>(&lh[8 + 3]); left_modes[1] = ldn<PERSIST>(&lh[8 + 7]); left_modes[2] = ldn<PERSIST>(&lh[8 + 11]); left_modes[3] = ldn<PERSIST>(&lh[8 + 15]); }
+      } else if (ldn(&lh[0]) == 1) { left_modes[0] = ldn(&lh[8 + 3]); left_modes[1] = ldn(&lh[8 + 7]); left_modes[2] = ldn(&lh[8 + 11]); left_modes[3] = ldn(&lh[8 + 15]); }
     }
   }
   __syncwarp();
@@ -333,7 +307,6 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
     __syncwarp();
     const int dc_ctx = min(top_nz_dc + left_nz_dc, 2);
     for (int mode = 0; mode < 4; ++mode) {
-      if constexpr (SYNC) __syncthreads();  // experiment: the warps of an SM walk the code together (shared instruction fetch)
       const bool allowed = active && !((mode == 2 && my == 0) || (mode == 3 && mx == 0) || (mode == 1 && (mx == 0 || my == 0)));
       if (allowed) pred_square_coop<G>(gl, check_mode(mx, my, mode), S.out2, Y_OFF, 16);
       __syncwarp();
@@ -455,7 +428,6 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
     uint32_t nzmask = 0;   // bit b: block b has nz > 0
     uint32_t modes_lo = 0, modes_hi = 0;  // 16 x 4-bit modes
     for (int b = 0; b < 16; ++b) {
-      if constexpr (SYNC) __syncthreads();
       const int bx = b & 3, by = b >> 2;
       const int off = Y_OFF + by * 4 * BPS + bx * 4;
       auto get_mode = [&](int k) -> int { return (k < 8) ? (modes_lo >> (4 * k)) & 15 : (modes_hi >> (4 * (k - 8))) & 15; };
@@ -711,7 +683,6 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
         reinterpret_cast<uint32_t*>(S.out2 + U_OFF)[i] = reinterpret_cast<const uint32_t*>(S.out + U_OFF)[i];
     __syncwarp();
     for (int mode = 0; mode < 4; ++mode) {
-      if constexpr (SYNC) __syncthreads();
       const bool allowed = active && !((mode == 2 && my == 0) || (mode == 3 && mx == 0) || (mode == 1 && (mx == 0 || my == 0)));
       if (allowed) {
         const int am = check_mode(mx, my, mode);
@@ -1043,11 +1014,6 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       if (FAST || SERIAL) P.ctx2[(size_t)img * nmb + mb_idx] = trial_modes;
     }
   }
-  if (PERSIST) {  // publish: everything this macroblock wrote must be visible before the row counter moves
-    __threadfence();
-    __syncwarp();
-    if (active && gl == 0) { volatile int* prog = P.progress + (size_t)img * P.mb_h; prog[my] = mx + 1; }
-  }
 }
 
 #define WG_STAGE_TABLES(NT)                                                                                                        \
@@ -1065,55 +1031,13 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   CostTabs T;                                                                                                                      \
   T.lc = s_lc; T.eob = s_eob; T.lfc = s_lfc; T.lfc_hi = s_lfc
 
-// One wave of the mode search per launch.  Grid: ceil(tasks / (WARPS * 32/G)) CTAs of WARPS warps.
-template <int G, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) encode_wave_kernel(const EncKernelParams P, int wave) {
-  constexpr int MPW = 32 / G;  // macroblocks per warp
-  WG_STAGE_TABLES(WARPS * 32);
-  const int warp = threadIdx.x >> 5;
-  encode_mb_group<G, false, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
-}
-
-// Same kernel under an explicit register cap instead of a minimum-CTAs bound: leaves register-file room for the boolean
-// coder blocks of the previous batch to sit beside three mode-search CTAs on every SM.
-template <int G, int WARPS, int NREG>
-__global__ void __maxnreg__(NREG) encode_wave_kernel_nr(const EncKernelParams P, int wave) {
-  constexpr int MPW = 32 / G;
-  WG_STAGE_TABLES(WARPS * 32);
-  const int warp = threadIdx.x >> 5;
-  encode_mb_group<G, false, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
-}
-
-// Experiment (WGPU_ENC_VARIANT=5/6): cost tables read through L1 from HBM instead of being staged into every CTA's shared
-// memory -- 19 KB less per CTA, which makes room for a fourth CTA (64 instead of 48 macroblocks per SM) under a 128-register cap.
-template <int G, int WARPS, int NREG>
-__global__ void __maxnreg__(NREG) encode_wave_kernel_gt(const EncKernelParams P, int wave) {
-  constexpr int MPW = 32 / G;
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  MBShared* s_mb = reinterpret_cast<MBShared*>(s_dyn);
-  CostTabs T;
-  T.lc = P.lc; T.eob = P.eob; T.lfc = P.lfc; T.lfc_hi = P.lfc;
-  const int warp = threadIdx.x >> 5;
-  encode_mb_group<G, false, false>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, P.i4_costs);
-}
-
-// Experiment (WGPU_ENC_VARIANT=7/8): one CTA of 12 warps per SM (tables staged once), optionally with CTA-wide barriers at
-// every mode / block step so that the 12 warps fetch the same instructions at the same time.
-template <int G, int WARPS, bool SYNC>
-__global__ void __launch_bounds__(WARPS * 32, 1) encode_wave_kernel_big(const EncKernelParams P, int wave) {
-  constexpr int MPW = 32 / G;
-  WG_STAGE_TABLES(WARPS * 32);
-  const int warp = threadIdx.x >> 5;
-  encode_mb_group<G, false, false, false, SYNC>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
-}
-
 // Method < 3 (the reference's non-RD decisions, serial-path semantics): same wavefront, lighter body.
 template <int G, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB) encode_fast_wave_kernel(const EncKernelParams P, int wave) {
   constexpr int MPW = 32 / G;
   WG_STAGE_TABLES(WARPS * 32);
   const int warp = threadIdx.x >> 5;
-  encode_mb_group<G, false, true>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
+  encode_mb_group<G, true>(P, wave, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
 }
 
 // collectAllStats (encode_proba.go:171-313) for the serial path's probability refreshes (encode_frame.go:113-117): token
@@ -1263,7 +1187,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_serial_kernel(const E
   constexpr int MPW = 32 / G;
   WG_STAGE_TABLES(WARPS * 32);
   const int warp = threadIdx.x >> 5;
-  encode_mb_group<G, false, false, true>(P, mb_index, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
+  encode_mb_group<G, false, true>(P, mb_index, ((long long)blockIdx.x * WARPS + warp) * MPW, s_mb + warp * MPW, T, s_i4cost);
 }
 
 // Serial RD path with mid-stream probability refreshes (encode_frame.go:35-57): the RD costs follow each image's own
@@ -1294,28 +1218,7 @@ __global__ void __launch_bounds__(32, 2) encode_serial_tab_kernel(const EncKerne
   const int g = min((int)(threadIdx.x & 31) / G, gpw - 1);
   Tg.lc = s_tabs + (size_t)g * (LC_SIZE + EOB_SIZE);
   Tg.eob = Tg.lc + LC_SIZE;
-  encode_mb_group<G, false, false, true>(P, mb_index, task_base, s_mb, Tg, s_i4cost);
-}
-
-// The whole mode search in ONE launch: persistent warps claim groups of 32/G macroblocks in wave order from a global
-// counter and synchronise through per-row progress counters (the reference's rowSync, encode_parallel.go:63-113, at
-// macroblock granularity).  No per-wave barrier: light macroblocks do not wait for heavy ones, and the tail of one
-// wave overlaps the head of the next.  wave_start[w] = first group index of wave w (host-computed prefix).
-template <int G, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) encode_persistent_kernel(const EncKernelParams P) {
-  constexpr int MPW = 32 / G;
-  WG_STAGE_TABLES(WARPS * 32);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int wave = 0;
-  for (;;) {
-    long long grp = 0;
-    if (lane == 0) grp = (long long)atomicAdd(P.work_counter, 1ull);
-    grp = __shfl_sync(0xffffffffu, grp, 0);
-    if (grp >= P.total_groups) break;
-    while (grp >= P.wave_start[wave + 1]) ++wave;  // groups are claimed in increasing order by this warp
-    encode_mb_group<G, true, false>(P, wave, (grp - P.wave_start[wave]) * MPW, s_mb + warp * MPW, T, s_i4cost);
-    __syncwarp();
-  }
+  encode_mb_group<G, false, true>(P, mb_index, task_base, s_mb, Tg, s_i4cost);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -793,7 +793,7 @@ WG_HD void ph_export(const EncKernelParams& P, PhMB* mbs, int tid) {
 // The whole per-CTA schedule.  WG_PH(stmt) runs `stmt` for every thread of the CTA and ends with a barrier.
 #if defined(__CUDA_ARCH__) && defined(WG_PHASE_CLOCK)
 // profiling build only (tools/phase_clock.py): CTA 0 timestamps every phase boundary
-#define WG_PH(stmt) { stmt; } __syncthreads(); if (P.work_counter && blockIdx.x == P.total_groups && threadIdx.x == 0) P.work_counter[ph_i_++] = clock64()
+#define WG_PH(stmt) { stmt; } __syncthreads(); if (P.phase_clock && (int)blockIdx.x == P.clock_cta && threadIdx.x == 0) P.phase_clock[ph_i_++] = clock64()
 #elif defined(__CUDA_ARCH__)
 #define WG_PH(stmt) { stmt; } __syncthreads()
 #else
@@ -805,7 +805,7 @@ WG_HD void ph_run_cta(const EncKernelParams& P, PhMB* mbs, const CostTabs& T, co
   (void)tid; (void)order;
 #if defined(__CUDA_ARCH__) && defined(WG_PHASE_CLOCK)
   int ph_i_ = 0;
-  if (P.work_counter && blockIdx.x == P.total_groups && threadIdx.x == 0) P.work_counter[ph_i_++] = clock64();
+  if (P.phase_clock && (int)blockIdx.x == P.clock_cta && threadIdx.x == 0) P.phase_clock[ph_i_++] = clock64();
 #endif
   WG_PH((ph_load<M, NT>(P, mbs, wave, task_base, tid)));
   WG_PH((ph_prep<M, NT>(mbs, tid)));

@@ -609,7 +609,7 @@ WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type,
   initial_ctx = min(initial_ctx, 2);
   const uint16_t* lc = T.lc + type * (8 * 3 * LC_LEVELS);
   const uint16_t* eob = T.eob + type * (8 * 3);
-  const long long kBig = 1ll << 56, kThr = 1ll << 55, kMask = ~63ll;
+  const long long kBig = 1ll << 56, kMask = ~63ll;  // keys below 2^55 are reachable states
   long long ps0 = initial_ctx == 0 ? 0 : kBig, ps1 = initial_ctx == 1 ? 0 : kBig, ps2 = initial_ctx == 2 ? 0 : kBig;
   const uint32_t lam64 = (uint32_t)lambda << 6;
   long long best = (long long)((unsigned long long)eob[c_bands[first] * 3 + initial_ctx] * lam64);  // order tag 0: "no coefficient"

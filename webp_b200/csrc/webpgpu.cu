@@ -72,6 +72,7 @@ void parallel_for(int n, int threads, F f) {
 
 struct wgpu_ctx {
   int dev = 0;
+  int sm_count = 148;  // of this context's device
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_hdr = nullptr;
   std::string err;
@@ -82,11 +83,11 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, enc_ctl, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
   DevBuf sharp_best_y, sharp_target_y, sharp_best_uv, sharp_target_uv, t_sharp;  // SharpYUV import working planes + gamma tables
   PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
-  bool e_uploaded = false, e_analyzed = false, e_done = false, enc_persistent_used = false, e_keep_derr = false, e_keep_stats = false;
+  bool e_uploaded = false, e_analyzed = false, e_done = false, e_keep_derr = false, e_keep_stats = false;
   int dither_w = 0, dither_h = 0, dither_amp_cached = 0;  // what the device dither tables currently hold
   wgpu_enc_options e_opt;
   std::vector<wgh::FramePlan> plans;
@@ -183,6 +184,7 @@ int wgpu_ctx_create(int device_ordinal, wgpu_ctx** out) {
   if (device_ordinal < 0 || device_ordinal >= count) { g_create_error = "device ordinal out of range"; return WGPU_ERR_INVALID; }
   wgpu_ctx* ctx = new wgpu_ctx();
   ctx->dev = device_ordinal;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_ordinal);
   auto bail = [&](const char* what, cudaError_t ce) { g_create_error = std::string(what) + ": " + cudaGetErrorString(ce); delete ctx; return WGPU_ERR_CUDA; };
   if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
@@ -226,7 +228,7 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->enc_ctl, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
+  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_streams, &ctx->d_hdrs, &ctx->d_perr, &ctx->t_bmodes, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
@@ -333,37 +335,13 @@ int wave_rows(int wave, int mb_w, int mb_h) {
   const int y_lo = std::max(0, (wave - (mb_w - 1) + 1) >> 1), y_hi = std::min(mb_h - 1, wave >> 1);
   return y_hi - y_lo + 1;
 }
-// Launch configurations of the mode-search kernel: lanes per macroblock (G), warps per CTA, min CTAs per SM (register cap).
-// WGPU_ENC_VARIANT picks one at run time for tuning; the default is the measured best.
-template <int G, int WARPS>
-int launch_enc_waves_fn(wgpu_ctx* ctx, const wg::EncKernelParams& P, void (*kernel)(const wg::EncKernelParams, int)) {
-  constexpr int per_cta = WARPS * (32 / G);
-  constexpr size_t smem = sizeof(wg::MBShared) * per_cta;
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
-  const int waves = P.mb_w + 2 * (P.mb_h - 1);
-  for (int w = 0; w < waves; ++w) {
-    const long long tasks = (long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images;
-    if (tasks <= 0) continue;  // one macroblock column: odd waves hold no macroblock (x = w - 2y)
-    const unsigned grid = (unsigned)((tasks + per_cta - 1) / per_cta);
-    kernel<<<grid, WARPS * 32, smem, ctx->stream>>>(P, w);
-    ctx->launches++;
-  }
-  return WGPU_OK;
-}
-template <int G, int WARPS, int MINB>
-int launch_enc_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
-  return launch_enc_waves_fn<G, WARPS>(ctx, P, wg::encode_wave_kernel<G, WARPS, MINB>);
-}
 template <int G, int WARPS, int MINB>
 int launch_enc_fast_waves(wgpu_ctx* ctx, const wg::EncKernelParams& P) {  // Method < 3: non-RD body, same wave schedule
   constexpr int per_cta = WARPS * (32 / G);
   constexpr size_t smem = sizeof(wg::MBShared) * per_cta;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // the attribute is per device (contexts may sit on different GPUs of one process): set it on every call
     cudaError_t e = cudaFuncSetAttribute(wg::encode_fast_wave_kernel<G, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
-    attr_set = true;
   }
   const int waves = P.mb_w + 2 * (P.mb_h - 1);
   for (int w = 0; w < waves; ++w) {
@@ -380,11 +358,9 @@ template <int G, int WARPS, int MINB>
 int launch_enc_serial(wgpu_ctx* ctx, const wg::EncKernelParams& P, int mb_begin, int mb_end) {
   constexpr int per_cta = WARPS * (32 / G);
   constexpr size_t smem = sizeof(wg::MBShared) * per_cta;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {
     cudaError_t e = cudaFuncSetAttribute(wg::encode_serial_kernel<G, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
-    attr_set = true;
   }
   const unsigned grid = (unsigned)((P.n_images + per_cta - 1) / per_cta);
   for (int i = mb_begin; i < mb_end; ++i) {
@@ -396,68 +372,21 @@ int launch_enc_serial(wgpu_ctx* ctx, const wg::EncKernelParams& P, int mb_begin,
 // Serial RD path with probability refreshes: as launch_enc_serial, each macroblock group with its image's own cost tables.
 int launch_enc_serial_tab(wgpu_ctx* ctx, wg::EncKernelParams& P, int mb_begin, int mb_end) {
   constexpr int G = 8;
-  static int sm_count = 0;
-  if (!sm_count) cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->dev);
+  const int sm_count = ctx->sm_count;
   // one macroblock group (image) per warp while the batch leaves SMs to spare, then 2, then 4 (see the kernel)
   const int gpw = P.n_images <= 8 * sm_count ? 1 : (P.n_images <= 24 * sm_count ? 2 : 4);
   P.serial_gpw = gpw;
   const size_t smem = sizeof(wg::MBShared) * (32 / G) + (size_t)gpw * (wg::LC_SIZE + wg::EOB_SIZE) * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {
     const size_t max_smem = sizeof(wg::MBShared) * 4 + (size_t)4 * (wg::LC_SIZE + wg::EOB_SIZE) * 2;
     cudaError_t e = cudaFuncSetAttribute(wg::encode_serial_tab_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
     if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
-    attr_set = true;
   }
   const unsigned grid = (unsigned)((P.n_images + gpw - 1) / gpw);
   for (int i = mb_begin; i < mb_end; ++i) {
     wg::encode_serial_tab_kernel<G><<<grid, 32, smem, ctx->stream>>>(P, i);
     ctx->launches++;
   }
-  return WGPU_OK;
-}
-// Persistent dataflow launch: one kernel for all waves (see encode_persistent_kernel).
-template <int G, int WARPS, int MINB>
-int launch_enc_persistent(wgpu_ctx* ctx, wg::EncKernelParams& P) {
-  constexpr int MPW = 32 / G, per_cta = WARPS * MPW;
-  constexpr size_t smem = sizeof(wg::MBShared) * per_cta;
-  static bool attr_set = false;
-  static int sm_count = 0;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wg::encode_persistent_kernel<G, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->dev);
-    attr_set = true;
-  }
-  const int waves = P.mb_w + 2 * (P.mb_h - 1);
-  std::vector<long long> ws(waves + 1, 0);
-  for (int w = 0; w < waves; ++w) ws[w + 1] = ws[w] + ((long long)wave_rows(w, P.mb_w, P.mb_h) * P.n_images + MPW - 1) / MPW;
-  const size_t ctl_bytes = (size_t)(waves + 1) * 8 + 64 + (size_t)P.n_images * P.mb_h * 4;
-  if (!ctx->enc_ctl.reserve(ctl_bytes)) { ctx->err = "out of memory reserving enc_ctl"; return WGPU_ERR_NOMEM; }
-  // layout: [counter u64][error int + pad][wave_start (waves+1) i64][progress n*mb_h int]
-  uint8_t* base = ctx->enc_ctl.as<uint8_t>();
-  if (cudaMemsetAsync(base, 0, ctl_bytes, ctx->stream) != cudaSuccess) { ctx->err = "cudaMemsetAsync(enc_ctl)"; return WGPU_ERR_CUDA; }
-  if (cudaMemcpyAsync(base + 64, ws.data(), (size_t)(waves + 1) * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
-    ctx->err = "cudaMemcpyAsync(wave_start)"; return WGPU_ERR_CUDA;
-  }
-  cudaStreamSynchronize(ctx->stream);  // ws is a stack vector: the pageable copy must finish before it goes away
-  P.work_counter = reinterpret_cast<unsigned long long*>(base);
-  P.error_flag = reinterpret_cast<int*>(base + 8);
-  P.wave_start = reinterpret_cast<const long long*>(base + 64);
-  P.progress = reinterpret_cast<int*>(base + 64 + (size_t)(waves + 1) * 8);
-  P.total_groups = ws[waves];
-  static int occ = 0;
-  if (!occ) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wg::encode_persistent_kernel<G, WARPS, MINB>, WARPS * 32, smem);
-    if (trace_on()) fprintf(stderr, "[wgpu] persistent mode search: %d CTAs/SM resident, %d SMs\n", occ, sm_count);
-    if (occ < 1) occ = 1;
-  }
-  const char* gm = getenv("WGPU_PERSIST_CTAS");
-  const int per_sm = gm ? atoi(gm) : occ;
-  const unsigned grid = (unsigned)std::min<long long>((long long)sm_count * per_sm, (P.total_groups + WARPS - 1) / WARPS);
-  wg::encode_persistent_kernel<G, WARPS, MINB><<<grid, WARPS * 32, smem, ctx->stream>>>(P);
-  ctx->launches++;
-  ctx->enc_persistent_used = true;
   return WGPU_OK;
 }
 // Row-parallel RD path: the phase-synchronous kernel (enc_phased.cuh).  M macroblocks per CTA, 16 threads per macroblock;
@@ -472,9 +401,7 @@ int launch_phased_wave(wgpu_ctx* ctx, const wg::EncKernelParams& P, int w, long 
   return WGPU_OK;
 }
 int launch_enc_phased(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
-  int sm_count = 148;
-  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->dev);
-  static const int cfg = getenv_int("WGPU_PHASED_CFG", 0);  // tuning knob: CTA shape of the wide waves
+  const int sm_count = ctx->sm_count;
   const int waves = P.mb_w + 2 * (P.mb_h - 1);
 #ifdef WG_PHASE_CLOCK
   static unsigned long long* clk = nullptr;
@@ -490,15 +417,9 @@ int launch_enc_phased(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
 #ifdef WG_PHASE_CLOCK
     wg::EncKernelParams& Pm = const_cast<wg::EncKernelParams&>(P);
     Pm = P0;
-    if (w == clk_wave) { Pm.work_counter = clk; Pm.total_groups = getenv_int("WGPU_CLOCK_CTA", 300); }
+    if (w == clk_wave) { Pm.phase_clock = clk; Pm.clock_cta = getenv_int("WGPU_CLOCK_CTA", 300); }
 #endif
-    if (cfg == 1) rc = launch_phased_wave<16, 128, 3>(ctx, P, w, tasks);
-    else if (cfg == 2) rc = launch_phased_wave<8, 64, 4>(ctx, P, w, tasks);
-    else if (cfg == 3) rc = launch_phased_wave<8, 128, 4>(ctx, P, w, tasks);
-    else if (cfg == 4) rc = launch_phased_wave<16, 192, 3>(ctx, P, w, tasks);
-    else if (cfg == 5) rc = launch_phased_wave<24, 384, 2>(ctx, P, w, tasks);
-    else if (cfg == 6) rc = launch_phased_wave<32, 512, 1>(ctx, P, w, tasks);
-    else if (tasks <= (long long)sm_count * 8 * 4) rc = launch_phased_wave<8, 128, 4>(ctx, P, w, tasks);
+    if (tasks <= (long long)sm_count * 8 * 4) rc = launch_phased_wave<8, 128, 4>(ctx, P, w, tasks);  // narrow wave: smaller CTAs reach more SMs
     else rc = launch_phased_wave<16, 256, 3>(ctx, P, w, tasks);
     if (rc) return rc;
   }
@@ -521,11 +442,6 @@ int launch_enc_phased(wgpu_ctx* ctx, const wg::EncKernelParams& P) {
     ctx->launches++;
   }
   return WGPU_OK;
-}
-int enc_variant() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("WGPU_ENC_VARIANT"); v = e ? atoi(e) : 0; }
-  return v;
 }
 }  // namespace
 }  // extern "C++"
@@ -645,7 +561,9 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   ctx->e_refresh_route = false;
   const int n = ctx->e_n, mbw = ctx->e_mbw, mbh = ctx->e_mbh, nmb = mbw * mbh;
   wg::EncKernelParams P;
-  P.progress = nullptr; P.work_counter = nullptr; P.wave_start = nullptr; P.total_groups = 0; P.error_flag = nullptr;
+#ifdef WG_PHASE_CLOCK
+  P.phase_clock = nullptr; P.clock_cta = 0;
+#endif
   P.src_y = ctx->sy.as<uint8_t>(); P.src_u = ctx->su.as<uint8_t>(); P.src_v = ctx->sv.as<uint8_t>();
   P.rec_y = ctx->ry.as<uint8_t>(); P.rec_u = ctx->ru.as<uint8_t>(); P.rec_v = ctx->rv.as<uint8_t>();
   P.segment = ctx->segment.as<uint8_t>(); P.img = ctx->img_params.as<wg::ImageParams>();
@@ -744,18 +662,7 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
     CK(cudaGetLastError());
     return WGPU_OK;
   }
-  switch (enc_variant()) {
-    case 1: rc = launch_enc_waves<8, 4, 2>(ctx, P); break;   // no register cap, 2 CTAs/SM
-    case 2: rc = launch_enc_persistent<8, 4, 3>(ctx, P); break;  // one persistent launch, dataflow scheduling
-    case 3: rc = launch_enc_waves_fn<8, 4>(ctx, P, wg::encode_wave_kernel_nr<8, 4, 152>); break;  // explicit register caps:
-    case 4: rc = launch_enc_waves_fn<8, 4>(ctx, P, wg::encode_wave_kernel_nr<8, 4, 144>); break;  // same speed, no spills (measured)
-    case 5: rc = launch_enc_waves_fn<8, 4>(ctx, P, wg::encode_wave_kernel_gt<8, 4, 128>); break;  // tables through L1, 4 CTAs/SM
-    case 6: rc = launch_enc_waves_fn<8, 4>(ctx, P, wg::encode_wave_kernel_gt<8, 4, 160>); break;  // tables through L1, 3 CTAs/SM
-    case 7: rc = launch_enc_waves_fn<8, 12>(ctx, P, wg::encode_wave_kernel_big<8, 12, false>); break;  // one 12-warp CTA per SM
-    case 8: rc = launch_enc_waves_fn<8, 12>(ctx, P, wg::encode_wave_kernel_big<8, 12, true>); break;   // + CTA-wide step barriers
-    case 9: rc = launch_enc_waves<8, 4, 3>(ctx, P); break;  // round-1 wavefront kernel: 8 lanes per macroblock, 3 CTAs/SM
-    default: rc = launch_enc_phased(ctx, P); break;
-  }
+  rc = launch_enc_phased(ctx, P);
   if (rc) return rc;
   CK(cudaGetLastError());
   return WGPU_OK;
@@ -1156,24 +1063,12 @@ int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
   return WGPU_OK;
 }
 
-// After a persistent launch: a dependency wait that hit its iteration cap is a hard error, never silent garbage.
-static int enc_check_persistent(wgpu_ctx* ctx) {
-  if (!ctx->enc_persistent_used) return WGPU_OK;
-  int flag = 0;
-  CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaMemcpy(&flag, ctx->enc_ctl.as<uint8_t>() + 8, 4, cudaMemcpyDeviceToHost));
-  ctx->enc_persistent_used = false;
-  if (flag) FAIL(WGPU_ERR_CUDA, "mode-search kernel: macroblock dependency wait timed out");
-  return WGPU_OK;
-}
-
 int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_sizes) {
   if (!ctx) return WGPU_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->e_done || ctx->plans.size() != (size_t)ctx->e_n) FAIL(WGPU_ERR_INVALID, "wgpu_enc_finish called before wgpu_enc_device");
   if (!out || !out_sizes) FAIL(WGPU_ERR_INVALID, "webp: nil writer");
   CK(cudaSetDevice(ctx->dev));
-  { const int prc = enc_check_persistent(ctx); if (prc) return prc; }
   const size_t n = ctx->e_n, nmb = (size_t)ctx->e_mbw * ctx->e_mbh;
   RESERVE(ctx->h_hdr, n * nmb * 48);
   std::atomic<int> too_small(0);
@@ -1245,14 +1140,10 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       // 140 ms), and it gives each block an SM of its own, where the tight coder loops keep the instruction cache (216 ms
       // vs 280 ms beside mode-search warps).  Cost to the waves: 8 of 148 SMs while the coder runs (packing more warp pairs
       // per block, WGPU_CODER_PAIRS, frees SMs but slows the chains: 2639 vs 2790 Mpix/s end to end at 4 pairs).
-      static size_t coder_smem = 0;
       static const int coder_pairs = std::min((int)wg::BOOLCODE_MAX_PAIRS, std::max(1, getenv_int("WGPU_CODER_PAIRS", 1)));
-      if (!coder_smem) {
-        coder_smem = 200 * 1024;
-        if (getenv("WGPU_CODER_DYNSMEM")) coder_smem = (size_t)atoi(getenv("WGPU_CODER_DYNSMEM"));  // experiment knob
-        coder_smem = std::max(coder_smem, (size_t)wg::BOOLCODE_SMEM * wg::BOOLCODE_MAX_PAIRS);
-        CK(cudaFuncSetAttribute(wg::boolcode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coder_smem));
-      }
+      const size_t coder_smem = std::max((size_t)200 * 1024, (size_t)wg::BOOLCODE_SMEM * wg::BOOLCODE_MAX_PAIRS);
+      // per device, so on every call (contexts of one process may sit on different GPUs)
+      CK(cudaFuncSetAttribute(wg::boolcode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coder_smem));
       int* order = reinterpret_cast<int*>(bases + 2 * n);  // longest first, so that the lanes of a warp finish together
       for (size_t i = 0; i < n; ++i) order[i] = (int)i;
       std::sort(order, order + n, [&](int a, int b) { return totals[a] > totals[b] || (totals[a] == totals[b] && a < b); });
@@ -1280,9 +1171,10 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     for (size_t i = 0; i < n; ++i) {  // token partitions go straight to their place in the caller's buffer
       out_sizes[i] = wgh::frame_file_size(part0[i].size(), csz[i]);
       if (out_sizes[i] > out_stride) { too_small.store(1); continue; }
-      if (csz[i])
+      if (csz[i]) {
         CK(cudaMemcpyAsync(out + i * out_stride + 30 + part0[i].size(), ctx->coded.as<uint8_t>() + bases[n + i], csz[i], cudaMemcpyDeviceToHost, ctx->stream));
         ctx->xfer_d2h += (uint64_t)(csz[i]);
+      }
     }
     parallel_for((int)n, threads_of(ctx), [&](int i) {
       if (out_sizes[i] > out_stride) return;
@@ -1405,7 +1297,6 @@ int wgpu_enc_fetch(wgpu_ctx* ctx, int image, uint8_t* mb_hdr, uint8_t* mb_modes,
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->e_done || image < 0 || image >= ctx->e_n) FAIL(WGPU_ERR_INVALID, "wgpu_enc_fetch: no encoded batch / bad image index");
   CK(cudaSetDevice(ctx->dev));
-  { const int prc = enc_check_persistent(ctx); if (prc) return prc; }
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t nmb = (size_t)ctx->e_mbw * ctx->e_mbh, i = image;
   if (mb_hdr || mb_modes || mb_nz) {
