@@ -273,14 +273,21 @@ __global__ void __launch_bounds__(256) boolcode_kernel(const BoolCodeParams P) {
   auto step = [&](uint32_t tok, bool valid) -> uint32_t {  // one PutBit on the range side; returns the event for the byte side
     const int prob = (int)(tok >> 8);
     const bool bit = tok & 1u;
-    // split = ((R - 1) * prob) >> 8; sub-range r + 1 = bit ? R - 1 - split : split + 1.  With sx = bit ? ~split : split
-    // (one IMAD + arithmetic shift, since ~(t >> 8) == (~t) >> 8): r + 1 = (bit ? R : 1) + sx.
-    const int ma = bit ? -prob : prob, mc = bit ? prob - 1 : -prob;
-    const int sx = (R * ma + mc) >> 8;
-    const int r1 = (bit ? R : 1) + sx;
-    const int k = 31 - __clz(r1);  // kNorm[r] = 7 - k, kNewRange[r] + 1 = r1 << (7 - k)
-    R = valid ? (r1 << 7) >> k : R;
-    return valid ? (uint32_t)((bit ? -sx : 0) | ((7 - k) << 12)) : 0u;  // an all-zero event is a no-op on the byte side
+    // split = ((R - 1) * prob) >> 8; sub-range r + 1 = bit ? R - 1 - split : split + 1.  Both cases are one multiply-add on R:
+    //   r + 1 = (R * A + Cc) >> 8  with (A, Cc) = bit ? (256 - prob, prob - 1) : (prob, 256 - prob),
+    // and a lane past the end of its partition takes (256, 0): the identity.  The pair depends on the token only, so the
+    // chain per token is IMAD -> FLO -> SHF: the leading-one index is taken on the 16-bit product itself (it is the index of
+    // r + 1 plus 8), and the renormalised range is ((t & 0xff00) << 7) >> index.
+    //   (measured and rejected: the same recurrence as a 64 KB shared-memory table rtab[token][range]: 2x slower, a byte load
+    //   per token whose address hangs on the previous load)
+    const int A = valid ? (bit ? 256 - prob : prob) : 256, Cc = valid ? (bit ? prob - 1 : 256 - prob) : 0;
+    const int Rold = R;
+    const int t = Rold * A + Cc;
+    const int kk = 31 - __clz(t);  // >= 8
+    R = ((t & 0xff00) << 7) >> kk;
+    // off the chain: the value increment (bit ? split + 1 : 0, as -sx of the former formulation) and the shift 7 - k = 15 - kk
+    const int sx = (Rold * (bit ? -prob : prob) + (bit ? prob - 1 : -prob)) >> 8;
+    return valid ? (uint32_t)((bit ? -sx : 0) | ((15 - kk) << 12)) : 0u;  // an all-zero event is a no-op on the byte side
   };
   auto issue_loads = [&](long long c) {  // chunk c of all 32 partitions -> token buffer c & 1 (8 lanes x 16 bytes per partition)
     unsigned char* dst_buf = s_tok + (size_t)(c & 1) * 32 * STRIDE;
@@ -325,32 +332,28 @@ __global__ void __launch_bounds__(256) boolcode_kernel(const BoolCodeParams P) {
                                    ((unsigned long long)(y & 0x1ffu) << s2) + ((unsigned long long)((y >> 16) & 0x1ffu) << s3);
     value = (value << s0) + add;
     nb_bits += s0;
-    // All complete bytes of this step at once (1-4 of them under a carry bit).  Fast path, the same for every lane: no
-    // 0xff among them and no 0xff run pending -> the held-back byte takes the carry and goes out, the new bytes follow,
-    // the last one is held back.  Anything involving 0xff goes through Flush byte by byte (rare, divergent).
+    // All complete bytes of this step at once (1-4 of them under a carry bit).  Fast path: no 0xff among them and no 0xff
+    // run pending -> the held-back byte takes the carry and goes out, the new bytes follow, the last one is held back, and
+    // the pending value keeps its low bits (an AND: the extraction below stays off the value's dependency chain).
+    // Anything involving 0xff goes through Flush byte by byte (rare, divergent).
     const int nbytes = (nb_bits + 7) >> 3;  // <= 0 when nothing is due
-    if (__any_sync(0xffffffffu, nbytes > 0)) {
-      bool slow = false;
-      if (nbytes > 0) {
-        const int s_low = 16 + nb_bits - 8 * nbytes;  // what Flush leaves pending after the last of these bytes
-        const unsigned long long cb = value >> s_low;  // carry bit + nbytes bytes
-        const uint32_t bytes = (uint32_t)cb;            // the bytes, most significant first from bit 8 * nbytes - 1 down
-        const uint32_t ff = bytes & (bytes >> 1), f2 = ff & (ff >> 2), f4 = f2 & (f2 >> 4);  // bit 8j set iff byte j == 0xff
-        const uint32_t mask = nbytes == 4 ? 0x01010101u : ((1u << (8 * nbytes)) - 1u) & 0x01010101u;
-        slow = run > 0 || (f4 & mask) != 0;
-        if (!slow) {
-          const int carry = (int)(cb >> (8 * nbytes)) & 1;
-          if (last >= 0) out[pos++] = (uint8_t)(last + carry);
-          if (nbytes > 1) out[pos++] = (uint8_t)(bytes >> (8 * nbytes - 8));
-          if (nbytes > 2) out[pos++] = (uint8_t)(bytes >> (8 * nbytes - 16));
-          if (nbytes > 3) out[pos++] = (uint8_t)(bytes >> 8);
-          last = (int)(bytes & 0xffu);
-          value -= cb << s_low;
-          nb_bits -= 8 * nbytes;
-        }
-      }
-      if (__any_sync(0xffffffffu, slow)) {
-        if (slow) while (nb_bits > 0) flush();
+    if (nbytes > 0) {
+      const int s_low = 16 + nb_bits - 8 * nbytes;  // what Flush leaves pending after the last of these bytes
+      const unsigned long long cb = value >> s_low;  // carry bit + nbytes bytes
+      const uint32_t bytes = (uint32_t)cb;            // the bytes, most significant first from bit 8 * nbytes - 1 down
+      const uint32_t ff = bytes & (bytes >> 1), f2 = ff & (ff >> 2), f4 = f2 & (f2 >> 4);  // bit 8j set iff byte j == 0xff
+      const uint32_t mask = nbytes == 4 ? 0x01010101u : ((1u << (8 * nbytes)) - 1u) & 0x01010101u;
+      if (run > 0 || (f4 & mask) != 0) {
+        while (nb_bits > 0) flush();
+      } else {
+        const int carry = (int)(cb >> (8 * nbytes)) & 1;
+        if (last >= 0) out[pos++] = (uint8_t)(last + carry);
+        if (nbytes > 1) out[pos++] = (uint8_t)(bytes >> (8 * nbytes - 8));
+        if (nbytes > 2) out[pos++] = (uint8_t)(bytes >> (8 * nbytes - 16));
+        if (nbytes > 3) out[pos++] = (uint8_t)(bytes >> 8);
+        last = (int)(bytes & 0xffu);
+        value &= (1ull << s_low) - 1ull;
+        nb_bits -= 8 * nbytes;
       }
     }
   };
