@@ -178,6 +178,30 @@ int wgpu_dsp_trellis_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, in
 int wgpu_dsp_token_cost_batch(wgpu_ctx* ctx, int n, const int16_t* levels, const int32_t* nz, int ctx_type,
                               const int32_t* ctx0, int first, int32_t* out);
 
+/* The rest of the dsp function surface (internal/dsp/dsp.go:12-37 and the *Direct / exported functions), batched:
+ *   sse16x16 (ssim.go:220), tDisto16x16Go (:327): a, b [n][256] (16x16, stride 16) -> out [n]
+ *   DequantCoeffs / dequantCoeffsGo (internal/lossy/encode_quant.go:81): in [n][16] -> out [n][16]
+ *   FTransform2 (dsp.go:14): n pairs of adjacent blocks, src / ref [n][2][16] -> out [n][2][16]
+ *   decoder transforms (transforms.go:37-216): kind 0 transformOne, 1 transformDC, 2 transformAC3 on 4x4 blocks
+ *     (in [n][16], ref / dst [n][16]); kind 3 transformUV, 4 transformDCUV on 8x8 tiles (in [n][4][16], ref / dst [n][64], stride 8)
+ *   loop-filter set (filter.go:93-242) on 24x24 tiles holding the block at (4, 4): kind 0 SimpleVFilter16, 1 SimpleHFilter16,
+ *     2 SimpleVFilter16i, 3 SimpleHFilter16i, 4 VFilter16, 5 HFilter16, 6 VFilter16i, 7 HFilter16i, 8 VFilter8, 9 HFilter8,
+ *     10 VFilter8i, 11 HFilter8i (8..11: one chroma plane per tile); tiles_in / tiles_out [n][24][24]
+ *   UpsampleLinePair (upsample.go:45, channels = 3) / UpsampleLinePairNRGBA (:130, channels = 4) on n line pairs:
+ *     top_y / bot_y [n][width] (bot_y NULL = last row of an odd height), *_u / *_v [n][(width + 1) / 2], alpha rows optional,
+ *     top_dst / bot_dst [n][width][channels] */
+int wgpu_dsp_sse16x16_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int32_t* out);
+int wgpu_dsp_tdisto16x16_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int32_t* out);
+int wgpu_dsp_dequant_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, int ac_q, int16_t* out);
+int wgpu_dsp_ftransform2_batch(wgpu_ctx* ctx, int n, const uint8_t* src, const uint8_t* ref, int16_t* out);
+int wgpu_dsp_dec_transform_batch(wgpu_ctx* ctx, int n, int kind, const int16_t* in, const uint8_t* ref, uint8_t* dst);
+int wgpu_dsp_filter_batch(wgpu_ctx* ctx, int n, int kind, const uint8_t* tiles_in, int thresh, int ithresh, int hev_thresh,
+                          uint8_t* tiles_out);
+int wgpu_dsp_upsample_line_pair_batch(wgpu_ctx* ctx, int n, int width, const uint8_t* top_y, const uint8_t* bot_y,
+                                      const uint8_t* top_u, const uint8_t* top_v, const uint8_t* bot_u, const uint8_t* bot_v,
+                                      const uint8_t* alpha_top, const uint8_t* alpha_bot, int channels, uint8_t* top_dst,
+                                      uint8_t* bot_dst);
+
 /* ---- measurement helpers (device timing on the library's own stream) -------------------- */
 int wgpu_timer_begin(wgpu_ctx* ctx);           /* records a CUDA event on the ctx stream */
 int wgpu_timer_end(wgpu_ctx* ctx, float* ms);   /* records + synchronises, returns elapsed ms */
@@ -187,7 +211,9 @@ uint64_t wgpu_launch_count(const wgpu_ctx* ctx);
  * reset != 0.  bench.py reports the per-step figures of the e2e leg from it. */
 int wgpu_transfer_bytes(wgpu_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset);
 /* Timed device-only repetitions of one stage over data already uploaded by wgpu_enc_upload /
- * decoded data; used for roofline numbers.  stage: 0 import, 1 analysis, 2 mode search (all waves). */
+ * decoded data; used for roofline numbers.  stage: 0 import, 1 analysis, 2 mode search (all waves), 3 SSE + SSIM of the
+ * source luma planes against the reconstruction (dsp/ssim.go:12-181; 5 = the SSE alone), 4 fancy upsampling of the batch last decoded on this
+ * context (wgpu_dec_parse + wgpu_dec_device) to NRGBA. */
 int wgpu_enc_stage_time(wgpu_ctx* ctx, const wgpu_enc_options* opt, int stage, int reps, float* ms_per_rep);
 
 #ifdef __cplusplus

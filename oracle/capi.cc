@@ -392,4 +392,85 @@ int orc_quality_to_qindex(int q) { return Encoder::quality_to_qindex(q); }
 const uint16_t* orc_level_fixed_costs() { return kLevelFixedCosts; }
 const uint16_t* orc_entropy_cost() { return kEntropyCost; }
 
+// ---- the rest of the dsp surface, batched like the product's twins (same layouts as include/webpgpu.h)
+void orc_sse16x16_batch(int n, const uint8_t* a, const uint8_t* b, int32_t* out) {
+  uint8_t x[16 * BPS], y[16 * BPS];
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < 16; ++j) { memcpy(x + j * BPS, a + 256 * (size_t)i + 16 * j, 16); memcpy(y + j * BPS, b + 256 * (size_t)i + 16 * j, 16); }
+    out[i] = sse16x16(x, y);
+  }
+}
+void orc_tdisto16x16_batch(int n, const uint8_t* a, const uint8_t* b, int32_t* out) {
+  uint8_t x[16 * BPS], y[16 * BPS];
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < 16; ++j) { memcpy(x + j * BPS, a + 256 * (size_t)i + 16 * j, 16); memcpy(y + j * BPS, b + 256 * (size_t)i + 16 * j, 16); }
+    out[i] = tdisto16x16(x, y);
+  }
+}
+void orc_dequant_batch(int n, const int16_t* in, int dc_q, int ac_q, int16_t* out) {
+  SegmentQuant sq;
+  memset(&sq, 0, sizeof(sq));
+  sq.quant = ac_q; sq.dc_quant = dc_q;
+  for (int i = 0; i < n; ++i) dequant_coeffs(in + 16 * (size_t)i, out + 16 * (size_t)i, &sq);
+}
+void orc_dec_transform_batch(int n, int kind, const int16_t* in, const uint8_t* ref, uint8_t* dst) {
+  uint8_t buf[8 * BPS];
+  for (int i = 0; i < n; ++i) {
+    if (kind < 3) {
+      for (int j = 0; j < 4; ++j) memcpy(buf + j * BPS, ref + 16 * (size_t)i + 4 * j, 4);
+      if (kind == 0) transform_one(in + 16 * (size_t)i, buf); else if (kind == 1) transform_dc(in + 16 * (size_t)i, buf); else transform_ac3(in + 16 * (size_t)i, buf);
+      for (int j = 0; j < 4; ++j) memcpy(dst + 16 * (size_t)i + 4 * j, buf + j * BPS, 4);
+    } else {  // transformUV / transformDCUV (transforms.go:186-216): the four blocks of an 8x8 tile
+      for (int j = 0; j < 8; ++j) memcpy(buf + j * BPS, ref + 64 * (size_t)i + 8 * j, 8);
+      for (int b = 0; b < 4; ++b) {
+        uint8_t* d = buf + (b >> 1) * 4 * BPS + (b & 1) * 4;
+        if (kind == 3) transform_one(in + 64 * (size_t)i + 16 * b, d); else transform_dc(in + 64 * (size_t)i + 16 * b, d);
+      }
+      for (int j = 0; j < 8; ++j) memcpy(dst + 64 * (size_t)i + 8 * j, buf + j * BPS, 8);
+    }
+  }
+}
+void orc_filter_batch(int n, int kind, uint8_t* tiles, int thresh, int ithresh, int hev_t) {
+  for (int i = 0; i < n; ++i) {
+    uint8_t* p = tiles + 576 * (size_t)i + 4 * 24 + 4;
+    const int S = 24;
+    switch (kind) {
+      case 0: simple_filter(p, S, 1, 16, thresh); break;                                        // SimpleVFilter16 (filter.go:93)
+      case 1: simple_filter(p, 1, S, 16, thresh); break;                                        // SimpleHFilter16
+      case 2: for (int k = 1; k <= 3; ++k) simple_filter(p + k * 4 * S, S, 1, 16, thresh); break;  // SimpleVFilter16i
+      case 3: for (int k = 1; k <= 3; ++k) simple_filter(p + k * 4, 1, S, 16, thresh); break;      // SimpleHFilter16i
+      case 4: filter_loop26(p, S, 1, 16, thresh, ithresh, hev_t); break;                        // VFilter16
+      case 5: filter_loop26(p, 1, S, 16, thresh, ithresh, hev_t); break;                        // HFilter16
+      case 6: for (int k = 1; k <= 3; ++k) filter_loop24(p + k * 4 * S, S, 1, 16, thresh, ithresh, hev_t); break;  // VFilter16i
+      case 7: for (int k = 1; k <= 3; ++k) filter_loop24(p + k * 4, 1, S, 16, thresh, ithresh, hev_t); break;      // HFilter16i
+      case 8: filter_loop26(p, S, 1, 8, thresh, ithresh, hev_t); break;                         // VFilter8 (one plane)
+      case 9: filter_loop26(p, 1, S, 8, thresh, ithresh, hev_t); break;                         // HFilter8
+      case 10: filter_loop24(p + 4 * S, S, 1, 8, thresh, ithresh, hev_t); break;                // VFilter8i
+      default: filter_loop24(p + 4, 1, S, 8, thresh, ithresh, hev_t); break;                    // HFilter8i
+    }
+  }
+}
+void orc_upsample_line_pair_batch(int n, int width, const uint8_t* top_y, const uint8_t* bot_y, const uint8_t* top_u, const uint8_t* top_v,
+                                  const uint8_t* bot_u, const uint8_t* bot_v, const uint8_t* alpha_top, const uint8_t* alpha_bot, int channels,
+                                  uint8_t* top_dst, uint8_t* bot_dst) {
+  const int cw = (width + 1) / 2;
+  std::vector<uint8_t> t4((size_t)width * 4), b4((size_t)width * 4);
+  for (int i = 0; i < n; ++i) {
+    const size_t o = (size_t)i * width, c = (size_t)i * cw;
+    upsample_line_pair_nrgba(top_y + o, bot_y ? bot_y + o : nullptr, top_u + c, top_v + c, bot_u + c, bot_v + c, t4.data(), b4.data(),
+                             alpha_top ? alpha_top + o : nullptr, alpha_bot ? alpha_bot + o : nullptr, width);
+    for (int x = 0; x < width; ++x)
+      for (int k = 0; k < channels; ++k) {
+        top_dst[(o + x) * channels + k] = t4[4 * x + k];
+        if (bot_y) bot_dst[(o + x) * channels + k] = b4[4 * x + k];
+      }
+  }
+}
+// VP8Random (internal/dsp/random.go): state after InitRandom(dithering) -- index1, index2, amp (random_test.go:5-50)
+void orc_random_init(float dithering, int* out3) {
+  const int amp = dithering < 0.0f ? 0 : (dithering > 1.0f ? 256 : (int)(256.0f * dithering));  // InitRandom (random.go:39-50)
+  Encoder::Random rg(amp);
+  out3[0] = rg.i1; out3[1] = rg.i2; out3[2] = rg.amp;
+}
+
 }  // extern "C"

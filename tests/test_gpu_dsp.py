@@ -119,3 +119,81 @@ def test_cleanup_transparent_area(oracle, gpu_ctx, w, h):
     for k in range(3):
         assert np.array_equal(out[k], oracle.cleanup_transparent(imgs[k]))
     assert np.array_equal(out[2], imgs[2])
+
+
+def test_sse_tdisto_16x16(oracle, gpu_ctx):
+    rng = np.random.RandomState(21)
+    n = 4000
+    a = rng.randint(0, 256, (n, 16, 16)).astype(np.uint8); b = np.clip(a.astype(np.int32) + rng.randint(-40, 41, a.shape), 0, 255).astype(np.uint8)
+    b[:50] = 255 - a[:50]
+    e1 = np.zeros(n, np.int32); e2 = np.zeros(n, np.int32)
+    oracle.lib().orc_sse16x16_batch(n, _p(a), _p(b), _p(e1)); oracle.lib().orc_tdisto16x16_batch(n, _p(a), _p(b), _p(e2))
+    assert np.array_equal(dsp.SSE16x16Batch(a, b, gpu_ctx), e1)
+    assert np.array_equal(dsp.TDisto16x16Batch(a, b, gpu_ctx), e2)
+
+
+def test_dequant_and_ftransform2(oracle, gpu_ctx):
+    rng = np.random.RandomState(22)
+    lv = rng.randint(-2047, 2048, (N, 16)).astype(np.int16)
+    for dc_q, ac_q in ((8, 8), (37, 43), (157, 157), (132, 284)):  # the last pair overflows int16 for big levels: truncation as the reference
+        exp = np.zeros((N, 16), np.int16)
+        oracle.lib().orc_dequant_batch(N, _p(lv), dc_q, ac_q, _p(exp))
+        assert np.array_equal(dsp.DequantCoeffsBatch(lv, dc_q, ac_q, gpu_ctx), exp)
+    src = rng.randint(0, 256, (N // 2, 2, 16)).astype(np.uint8); ref = rng.randint(0, 256, (N // 2, 2, 16)).astype(np.uint8)
+    exp = np.zeros((N // 2, 2, 16), np.int16)
+    oracle.lib().orc_ftransform_batch(N, _p(src), _p(ref), _p(exp))  # FTransform2 == FTransform on both blocks (dsp.go:14)
+    assert np.array_equal(dsp.FTransform2Batch(src, ref, gpu_ctx), exp)
+
+
+@pytest.mark.parametrize("kind", ["Transform", "TransformDC", "TransformAC3", "TransformUV", "TransformDCUV"])
+def test_decoder_transforms(oracle, gpu_ctx, kind):
+    rng = np.random.RandomState(23)
+    n = 6000
+    uv = kind.endswith("UV")
+    co = rng.randint(-2048, 2049, (n, 4, 16) if uv else (n, 16)).astype(np.int16)
+    if kind == "TransformAC3":
+        m = np.zeros(16, bool); m[[0, 1, 4]] = True
+        co[:, ~m] = 0
+    if kind in ("TransformDC", "TransformDCUV"):
+        co[..., 1:] = 0
+    ref = rng.randint(0, 256, (n, 8, 8) if uv else (n, 16)).astype(np.uint8)
+    exp = np.zeros_like(ref)
+    oracle.lib().orc_dec_transform_batch(n, dsp.DEC_TRANSFORMS[kind], _p(co), _p(ref), _p(exp))
+    assert np.array_equal(dsp.DecTransformBatch(kind, co, ref, gpu_ctx), exp)
+    if kind in ("TransformDC", "TransformAC3"):  # the short cuts equal the full transform on their input shapes (decode_frame.go:22-44)
+        assert np.array_equal(exp, dsp.DecTransformBatch("Transform", co, ref, gpu_ctx))
+
+
+@pytest.mark.parametrize("kind", dsp.FILTERS)
+def test_loop_filter_set(oracle, gpu_ctx, kind):
+    rng = np.random.RandomState(24 + dsp.FILTERS.index(kind))
+    n = 3000
+    base = rng.randint(0, 256, (n, 1, 1)).astype(np.int32)
+    tiles = np.clip(base + rng.randint(-30, 31, (n, 24, 24)), 0, 255).astype(np.uint8)  # smooth-ish tiles so that the filters fire
+    tiles[: n // 3] = rng.randint(0, 256, (n // 3, 24, 24))
+    for thresh, ithresh, hev in ((10, 5, 1), (40, 20, 2), (63, 30, 0), (1, 1, 0)):
+        exp = tiles.copy()
+        oracle.lib().orc_filter_batch(n, dsp.FILTERS.index(kind), _p(exp), thresh, ithresh, hev)
+        got = dsp.FilterBatch(kind, tiles, thresh, ithresh, hev, gpu_ctx)
+        assert np.array_equal(got, exp), (kind, thresh)
+        if thresh >= 40:
+            assert not np.array_equal(got, tiles)  # the case does filter something
+
+
+@pytest.mark.parametrize("width,channels", [(1, 3), (2, 4), (3, 3), (4, 4), (17, 3), (64, 4), (255, 4)])
+def test_upsample_line_pair(oracle, gpu_ctx, width, channels):
+    rng = np.random.RandomState(40 + width)
+    n, cw = 300, (width + 1) // 2
+    ty, by = rng.randint(0, 256, (2, n, width)).astype(np.uint8)
+    tu, tv, bu, bv = rng.randint(0, 256, (4, n, cw)).astype(np.uint8)
+    at, ab = rng.randint(0, 256, (2, n, width)).astype(np.uint8)
+    for with_bot in (True, False):
+        for with_alpha in ((False, True) if channels == 4 else (False,)):
+            et = np.zeros((n, width, channels), np.uint8); eb = np.zeros_like(et)
+            oracle.lib().orc_upsample_line_pair_batch(n, width, _p(ty), _p(by) if with_bot else None, _p(tu), _p(tv), _p(bu), _p(bv),
+                                                      _p(at) if with_alpha else None, _p(ab) if with_alpha else None, channels, _p(et), _p(eb))
+            gt, gb = dsp.UpsampleLinePairBatch(ty, by if with_bot else None, tu, tv, bu, bv, channels, at if with_alpha else None,
+                                               ab if with_alpha else None, gpu_ctx)
+            assert np.array_equal(gt, et)
+            if with_bot:
+                assert np.array_equal(gb, eb)

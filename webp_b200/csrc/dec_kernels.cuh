@@ -311,63 +311,117 @@ __device__ __forceinline__ uint32_t yuv_to_rgba(int y, int u, int v, int a) {  /
   const int b = yuv_clip6(yy + ((u * 33050) >> 8) - 17685);
   return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16) | ((uint32_t)a << 24);
 }
+// Fancy upsampling + YUV -> NRGBA (buildNRGBA webp.go:379-450, upsampleLinePairNRGBAGo upsample.go:130, yuv.go:71-104).
+// One thread = 16 pixels of a LINE PAIR, as the reference walks the picture: luma rows 2p-1 and 2p share chroma rows p-1 and
+// p (row 0 and, for even heights, the last row pair with a mirrored chroma row).  Per thread: one 128-bit luma load per row,
+// one 64-bit load + 2 edge bytes per chroma row (U and V of both rows are used by BOTH luma rows), the 9-3-3-1 diamond in
+// the reference's packed u | v << 16 arithmetic (avg, diag12 and diag03 once per 2x2 output quad), 4 x 128-bit stores per row.
+// One pixel: y24 = luma << 24, uv = u | v << 16 (other bits are don't-care, as in the reference's packed arithmetic).
+// MultHi(v, c) = (v * c) >> 8 is the upper word of (v << 24) * c (one IMAD.HI); VP8YUVToR/G/B's clip (yuv.go:71: < 0 -> 0,
+// > 16383 -> 255, else >> 6) is an arithmetic shift followed by a saturating conversion, and cvt.pack.sat.u8.s32 converts
+// and packs two channels per instruction.
+__device__ __forceinline__ uint32_t ups_px(uint32_t y24, uint32_t uv, uint32_t a) {
+  const uint32_t u24 = __byte_perm(uv, 0, 0x0444), v24 = __byte_perm(uv, 0, 0x2444);
+  const int yy = (int)__umulhi(y24, 19077u);
+  const int r = (yy + (int)__umulhi(v24, 26149u) - 14234) >> 6;
+  const int g = (yy - (int)__umulhi(u24, 6419u) - (int)__umulhi(v24, 13320u) + 8708) >> 6;
+  const int b = (yy + (int)__umulhi(u24, 33050u) - 17685) >> 6;
+  uint32_t ba, px;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(ba) : "r"((int)a), "r"(b), "r"(0));   // b | a << 8
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(px) : "r"(g), "r"(r), "r"(ba));        // r | g << 8 | b << 16 | a << 24
+  return px;
+}
 __global__ void __launch_bounds__(256) upsample_nrgba_kernel(const UpsampleParams P) {
-  const int qw = (P.width + 3) >> 2;
-  const long long per_img = (long long)qw * P.height;
-  const long long total = per_img * P.n;
-  const int half_w = (P.width + 1) >> 1;  // chroma samples per row that carry data
+  const int gw = (P.width + 15) >> 4, npairs = (P.height >> 1) + 1;
+  const int ch = (P.height + 1) >> 1, half_w = (P.width + 1) >> 1;
+  const long long per_img = (long long)gw * npairs, total = per_img * P.n;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int img = (int)(t / per_img);
     const int rem = (int)(t - (long long)img * per_img);
-    const int r = rem / qw, x0 = (rem - r * qw) * 4;
-    // chroma rows: "cur" is the row nearer to this luma row, "oth" the farther one
-    int rc, ro;
-    if (r == 0) { rc = ro = 0; }
-    else {
-      const int j = (r - 1) >> 1;
-      if (r & 1) { rc = j; ro = j + 1; } else { rc = j + 1; ro = j; }
-      if (r == P.height - 1 && !(P.height & 1)) rc = ro = (P.height - 1) >> 1;  // mirrored last row
-    }
-    const uint8_t* yrow = P.y + (size_t)img * P.y_plane + (size_t)r * P.y_stride;
-    const uint8_t* uc = P.u + (size_t)img * P.uv_plane + (size_t)rc * P.uv_stride;
-    const uint8_t* uo = P.u + (size_t)img * P.uv_plane + (size_t)ro * P.uv_stride;
-    const uint8_t* vc = P.v + (size_t)img * P.uv_plane + (size_t)rc * P.uv_stride;
-    const uint8_t* vo = P.v + (size_t)img * P.uv_plane + (size_t)ro * P.uv_stride;
-    const uint8_t* arow = P.alpha ? P.alpha + (size_t)img * P.alpha_plane + (size_t)r * P.width : nullptr;
-    uint32_t px[4];
+    const int p = rem / gw, x0 = (rem - p * gw) * 16;
+    const int rt = 2 * p - 1, rb = 2 * p;
+    const bool has_top = p >= 1, has_bot = rb < P.height;
+    const int ca = max(p - 1, 0), cb = min(p, ch - 1);
+    const uint8_t* ua = P.u + (size_t)img * P.uv_plane + (size_t)ca * P.uv_stride;
+    const uint8_t* ub = P.u + (size_t)img * P.uv_plane + (size_t)cb * P.uv_stride;
+    const uint8_t* va = P.v + (size_t)img * P.uv_plane + (size_t)ca * P.uv_stride;
+    const uint8_t* vb = P.v + (size_t)img * P.uv_plane + (size_t)cb * P.uv_stride;
+    // chroma samples x0/2 - 1 .. x0/2 + 8 of both rows (clamped at the row ends), packed u | v << 16
+    uint32_t A[10], B[10];
+    const int c0 = (x0 >> 1) - 1;
+    const bool wide = c0 >= 0 && c0 + 9 < half_w && (((uintptr_t)(ua + c0 + 1) | (uintptr_t)(ub + c0 + 1) | (uintptr_t)(va + c0 + 1) | (uintptr_t)(vb + c0 + 1)) & 7) == 0;
+    if (wide) {
+      const uint2 wua = *reinterpret_cast<const uint2*>(ua + c0 + 1), wva = *reinterpret_cast<const uint2*>(va + c0 + 1);
+      const uint2 wub = *reinterpret_cast<const uint2*>(ub + c0 + 1), wvb = *reinterpret_cast<const uint2*>(vb + c0 + 1);
+      A[0] = ua[c0] | ((uint32_t)va[c0] << 16); B[0] = ub[c0] | ((uint32_t)vb[c0] << 16);
+      A[9] = ua[c0 + 9] | ((uint32_t)va[c0 + 9] << 16); B[9] = ub[c0 + 9] | ((uint32_t)vb[c0 + 9] << 16);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int x = x0 + i;
-      if (x >= P.width) { px[i] = 0; continue; }
-      int u, v;
-      if (x == 0) {
-        u = (3 * uc[0] + uo[0] + 2) >> 2;
-        v = (3 * vc[0] + vo[0] + 2) >> 2;
-      } else if ((x & 1) && ((x + 1) >> 1) >= half_w) {  // last pixel of an even-width row
-        const int k = (x - 1) >> 1;
-        u = (3 * uc[k] + uo[k] + 2) >> 2;
-        v = (3 * vc[k] + vo[k] + 2) >> 2;
-      } else {
-        const int k = (x + 1) >> 1;  // pair index: samples k-1 and k
-        const int ua = uc[k - 1], ub = uc[k], uc2 = uo[k - 1], ud = uo[k];
-        const int va = vc[k - 1], vb = vc[k], vc2 = vo[k - 1], vd = vo[k];
-        const int avg_u = ua + ub + uc2 + ud + 8, avg_v = va + vb + vc2 + vd + 8;
-        if (x & 1) {  // nearer to sample k-1: diagonal is (cur[k], oth[k-1])
-          u = (((avg_u + 2 * (ub + uc2)) >> 3) + ua) >> 1;
-          v = (((avg_v + 2 * (vb + vc2)) >> 3) + va) >> 1;
-        } else {      // nearer to sample k: diagonal is (cur[k-1], oth[k])
-          u = (((avg_u + 2 * (ua + ud)) >> 3) + ub) >> 1;
-          v = (((avg_v + 2 * (va + vd)) >> 3) + vb) >> 1;
-        }
+      for (int j = 0; j < 4; ++j) {
+        A[1 + j] = ((wua.x >> (8 * j)) & 0xffu) | (((wva.x >> (8 * j)) & 0xffu) << 16);
+        A[5 + j] = ((wua.y >> (8 * j)) & 0xffu) | (((wva.y >> (8 * j)) & 0xffu) << 16);
+        B[1 + j] = ((wub.x >> (8 * j)) & 0xffu) | (((wvb.x >> (8 * j)) & 0xffu) << 16);
+        B[5 + j] = ((wub.y >> (8 * j)) & 0xffu) | (((wvb.y >> (8 * j)) & 0xffu) << 16);
       }
-      px[i] = yuv_to_rgba(yrow[x], u, v, arow ? arow[x] : 255);
-    }
-    uint8_t* dst = P.out + (size_t)img * P.out_image + ((size_t)r * P.width + x0) * 4;
-    if (x0 + 3 < P.width && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(px[0], px[1], px[2], px[3]);
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) if (x0 + i < P.width) reinterpret_cast<uint32_t*>(dst)[i] = px[i];
+      for (int j = 0; j < 10; ++j) {
+        const int c = min(max(c0 + j, 0), half_w - 1);
+        A[j] = ua[c] | ((uint32_t)va[c] << 16);
+        B[j] = ub[c] | ((uint32_t)vb[c] << 16);
+      }
+    }
+    // luma of both rows
+    uint32_t yt[4] = {0, 0, 0, 0}, yb[4] = {0, 0, 0, 0};
+    const uint8_t* ytr = P.y + (size_t)img * P.y_plane + (size_t)max(rt, 0) * P.y_stride + x0;
+    const uint8_t* ybr = P.y + (size_t)img * P.y_plane + (size_t)min(rb, P.height - 1) * P.y_stride + x0;
+    const bool full = x0 + 15 < P.width;
+    if (full && (((uintptr_t)ytr | (uintptr_t)ybr) & 15) == 0) {
+      const uint4 a = *reinterpret_cast<const uint4*>(ytr), b = *reinterpret_cast<const uint4*>(ybr);
+      yt[0] = a.x; yt[1] = a.y; yt[2] = a.z; yt[3] = a.w; yb[0] = b.x; yb[1] = b.y; yb[2] = b.z; yb[3] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int xx = min(i, P.width - 1 - x0);
+        yt[i >> 2] |= (uint32_t)ytr[xx] << (8 * (i & 3));
+        yb[i >> 2] |= (uint32_t)ybr[xx] << (8 * (i & 3));
+      }
+    }
+    const uint8_t* at = P.alpha ? P.alpha + (size_t)img * P.alpha_plane + (size_t)max(rt, 0) * P.width + x0 : nullptr;
+    const uint8_t* ab = P.alpha ? P.alpha + (size_t)img * P.alpha_plane + (size_t)min(rb, P.height - 1) * P.width + x0 : nullptr;
+    uint8_t* dt = P.out + (size_t)img * P.out_image + ((size_t)max(rt, 0) * P.width + x0) * 4;
+    uint8_t* db = P.out + (size_t)img * P.out_image + ((size_t)min(rb, P.height - 1) * P.width + x0) * 4;
+    const bool vec = full && (((uintptr_t)dt | (uintptr_t)db) & 15) == 0;
+    // pixel i (x = x0 + i) sits in the quad between samples j = (i + 1) >> 1 and j + 1 of A / B: odd x takes the quad's first
+    // output, even x its second (upsample.go:74-107); x == 0 and the last pixel of an even width have no horizontal neighbour
+#pragma unroll
+    for (int g4 = 0; g4 < 4; ++g4) {
+      uint32_t pt[4], pb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = 4 * g4 + k, x = x0 + i, j = (i + 1) >> 1;
+        const uint32_t tl = A[j], tt = A[j + 1], l = B[j], cur = B[j + 1];
+        const uint32_t avg = tl + tt + l + cur + 0x00080008u;
+        const uint32_t diag12 = (avg + 2 * (tt + l)) >> 3, diag03 = (avg + 2 * (tl + cur)) >> 3;
+        uint32_t uvt = (i & 1) ? (diag12 + tl) >> 1 : (diag03 + tt) >> 1;
+        uint32_t uvb = (i & 1) ? (diag03 + l) >> 1 : (diag12 + cur) >> 1;
+        if (x == 0) { uvt = (3 * tt + cur + 0x00020002u) >> 2; uvb = (3 * cur + tt + 0x00020002u) >> 2; }      // samples 0 of both rows (j + 1 == 1)
+        else if ((x & 1) && ((x + 1) >> 1) >= half_w) { uvt = (3 * tl + l + 0x00020002u) >> 2; uvb = (3 * l + tl + 0x00020002u) >> 2; }  // sample (x - 1) / 2
+        const uint32_t ytv = __byte_perm(yt[g4], 0, (k << 12) | 0x444), ybv = __byte_perm(yb[g4], 0, (k << 12) | 0x444);  // luma << 24
+        const int xa = min(i, P.width - 1 - x0);
+        pt[k] = ups_px(ytv, uvt, at ? at[xa] : 255u);
+        pb[k] = ups_px(ybv, uvb, ab ? ab[xa] : 255u);
+      }
+      if (vec) {
+        if (has_top) *reinterpret_cast<uint4*>(dt + 16 * g4) = make_uint4(pt[0], pt[1], pt[2], pt[3]);
+        if (has_bot) *reinterpret_cast<uint4*>(db + 16 * g4) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (x0 + 4 * g4 + k < P.width) {
+            if (has_top) reinterpret_cast<uint32_t*>(dt)[4 * g4 + k] = pt[k];
+            if (has_bot) reinterpret_cast<uint32_t*>(db)[4 * g4 + k] = pb[k];
+          }
+      }
     }
   }
 }

@@ -92,24 +92,30 @@ struct DecFrame {
   const char* err = nullptr;
 };
 
-// Locate the VP8 payload inside a RIFF/WebP file (or accept a raw VP8 frame).
-static inline bool find_vp8(const uint8_t* d, size_t n, const uint8_t** out, size_t* out_n) {
+// Locate the VP8 payload inside a RIFF/WebP file (or accept a raw VP8 frame).  1 = found, 0 = no VP8 chunk, -1 = the file
+// uses a feature outside the lossy path: an ALPH chunk or the VP8X alpha flag (webp.Decode would return NRGBA with the real
+// alpha, webp.go:323-350 -- decoding the VP8 chunk alone would silently hand back an opaque picture), or animation.
+static inline int find_vp8_ex(const uint8_t* d, size_t n, const uint8_t** out, size_t* out_n) {
   if (n >= 12 && !memcmp(d, "RIFF", 4) && !memcmp(d + 8, "WEBP", 4)) {
     size_t pos = 12;
     while (pos + 8 <= n) {
       const uint32_t sz = d[pos + 4] | (d[pos + 5] << 8) | (d[pos + 6] << 16) | ((uint32_t)d[pos + 7] << 24);
+      if (!memcmp(d + pos, "VP8X", 4) && pos + 9 <= n && (d[pos + 8] & (0x10 | 0x02))) return -1;  // alpha / animation flags
+      if (!memcmp(d + pos, "ALPH", 4) || !memcmp(d + pos, "ANIM", 4) || !memcmp(d + pos, "ANMF", 4)) return -1;
       if (!memcmp(d + pos, "VP8 ", 4)) {
-        if (pos + 8 + (size_t)sz > n) return false;
+        if (pos + 8 + (size_t)sz > n) return 0;
         *out = d + pos + 8; *out_n = sz;
-        return true;
+        return 1;
       }
       pos += 8 + (size_t)sz + (sz & 1);
     }
-    return false;
+    return 0;
   }
   *out = d; *out_n = n;
-  return true;
+  return 1;
 }
+static inline bool find_vp8(const uint8_t* d, size_t n, const uint8_t** out, size_t* out_n) { return find_vp8_ex(d, n, out, out_n) == 1; }
+static const char* const kErrOutsideLossyPath = "webp: ALPH chunk / alpha or animation flag: outside the GPU lossy path";
 // Frame tag + picture header only (webp.DecodeConfig path).
 static inline bool peek_dims(const uint8_t* d, size_t n, int* w, int* h, const char** err) {
   if (n < 10) { *err = "vp8: truncated header"; return false; }

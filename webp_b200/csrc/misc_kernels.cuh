@@ -33,6 +33,7 @@ __device__ __forceinline__ double ssim_calc(uint32_t xm, uint32_t ym, uint32_t x
   if (fden == 0) return 1.0;
   return (double)fnum / (double)fden;
 }
+enum { MET_TW = 32, MET_TH = 8 };  // windows per tile (one per thread)
 __global__ void __launch_bounds__(256) metrics_kernel(const MetricsParams P) {
   constexpr int TW = 32, TH = 8, AW = TW + 6, AH = TH + 6;
   __shared__ uint8_t sa[AH][AW + 2], sb[AH][AW + 2];
@@ -94,6 +95,40 @@ __global__ void __launch_bounds__(256) metrics_kernel(const MetricsParams P) {
     for (int i = 0; i < 8; ++i) { ts += s_sse[i]; tq += s_ssim[i]; }
     P.sse_part[blockIdx.x] = ts;
     P.ssim_part[blockIdx.x] = tq;
+  }
+}
+// SSE alone (dsp.SSE, ssim.go:172; PSNR for TargetPSNR): a pure stream, 2 B/px.  16 bytes of each plane per thread and step
+// (128-bit loads where the row allows), |a - b| per byte and the dot product of the differences with themselves (dp4a).
+__global__ void __launch_bounds__(256) sse_kernel(const MetricsParams P, unsigned long long* sse) {
+  __shared__ unsigned long long s_part[8];
+  const int chunks = (P.width + 15) >> 4;
+  const long long per_img = (long long)chunks * P.height;
+  const int img = blockIdx.y;
+  const uint8_t* pa = P.a + (size_t)img * P.plane_stride;
+  const uint8_t* pb = P.b + (size_t)img * P.plane_stride;
+  unsigned long long acc = 0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < per_img; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / chunks), c = (int)(t - (long long)r * chunks) * 16;
+    const uint8_t* ra = pa + (size_t)r * P.stride + c;
+    const uint8_t* rb = pb + (size_t)r * P.stride + c;
+    uint32_t s = 0;
+    if (c + 16 <= P.width && (((uintptr_t)ra | (uintptr_t)rb) & 15) == 0) {
+      const uint4 va = *reinterpret_cast<const uint4*>(ra), vb = *reinterpret_cast<const uint4*>(rb);
+      const uint32_t d0 = __vabsdiffu4(va.x, vb.x), d1 = __vabsdiffu4(va.y, vb.y), d2 = __vabsdiffu4(va.z, vb.z), d3 = __vabsdiffu4(va.w, vb.w);
+      s = __dp4a(d0, d0, s); s = __dp4a(d1, d1, s); s = __dp4a(d2, d2, s); s = __dp4a(d3, d3, s);
+    } else {
+      for (int k = 0; k < 16 && c + k < P.width; ++k) { const int d = (int)ra[k] - (int)rb[k]; s += (uint32_t)(d * d); }
+    }
+    acc += s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tsum = 0;
+    for (int i = 0; i < 8; ++i) tsum += s_part[i];
+    if (tsum) atomicAdd(sse + img, tsum);  // integer sum: the order of the CTAs does not matter
   }
 }
 // one CTA per image: fixed-order reduction of the tile partials
@@ -268,6 +303,126 @@ __global__ void dsp_token_cost_kernel(int n, const int16_t* levels, const int32_
   CostTabs T; T.lc = tp.lc; T.eob = tp.eob; T.lfc = tp.lfc; T.lfc_hi = tp.lfc;
   int q[16]; load16s16(levels + 16 * (size_t)i, q);
   out[i] = token_cost(q, nzc[i], ctx_type, ctx0[i], first, T);
+}
+// ---- the rest of the per-block operator surface, batched: 16x16 SSE / TDisto, DequantCoeffs, the decoder's
+// short-cut transforms, the loop-filter set on 24x24 tiles, UpsampleLinePair (RGB and NRGBA)
+__global__ void dsp_sse16x16_kernel(int n, const uint8_t* a, const uint8_t* b, int32_t* out) {  // ssim.go:220
+  WG_TID;
+  const uint8_t* pa = a + 256 * (size_t)i; const uint8_t* pb = b + 256 * (size_t)i;
+  int s = 0;
+  for (int k = 0; k < 256; ++k) { const int d = (int)pa[k] - (int)pb[k]; s += d * d; }
+  out[i] = s;
+}
+__global__ void dsp_tdisto16x16_kernel(int n, const uint8_t* a, const uint8_t* b, int32_t* out) {  // tDisto16x16Go (ssim.go:327)
+  WG_TID;
+  const uint8_t* pa = a + 256 * (size_t)i; const uint8_t* pb = b + 256 * (size_t)i;
+  int d = 0;
+  for (int blk = 0; blk < 16; ++blk) {
+    int x[16], y[16];
+    for (int k = 0; k < 16; ++k) {
+      const int off = ((blk >> 2) * 4 + (k >> 2)) * 16 + (blk & 3) * 4 + (k & 3);
+      x[k] = pa[off]; y[k] = pb[off];
+    }
+    d += tdisto4x4(x, y);
+  }
+  out[i] = d;
+}
+__global__ void dsp_dequant_kernel(int n, const int16_t* in, SegQuant sq, int16_t* out) {  // dequantCoeffsGo (encode_quant.go:81)
+  WG_TID; int q[16], dq[16]; load16s16(in + 16 * (size_t)i, q); dequant_block(q, dq, sq); store16s16(out + 16 * (size_t)i, dq);
+}
+// decoder transforms on one 4x4 block (transforms.go:37-216): kind 0 transformOne, 1 transformDC ((dc + 4) >> 3 everywhere),
+// 2 transformAC3 (only in[0], in[1], in[4]); kinds 3 / 4 = transformUV / transformDCUV: four blocks of an 8x8 tile
+__device__ __forceinline__ void dec_transform_block(int kind, const int* in, const int* ref, int* dst) {
+  if (kind == 1) {
+    const int add = (in[0] + 4) >> 3;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dst[k] = clip8(ref[k] + add);
+  } else if (kind == 2) {
+    const int a = in[0] + 4, c4 = mul2(in[4]), d4 = mul1(in[4]), c1 = mul2(in[1]), d1 = mul1(in[1]);
+    const int rowv[4] = {a + d4, a + c4, a - c4, a - d4};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dst[4 * j + 0] = clip8(ref[4 * j + 0] + ((rowv[j] + d1) >> 3));
+      dst[4 * j + 1] = clip8(ref[4 * j + 1] + ((rowv[j] + c1) >> 3));
+      dst[4 * j + 2] = clip8(ref[4 * j + 2] + ((rowv[j] - c1) >> 3));
+      dst[4 * j + 3] = clip8(ref[4 * j + 3] + ((rowv[j] - d1) >> 3));
+    }
+  } else {
+    itransform(ref, in, dst);
+  }
+}
+__global__ void dsp_dec_transform_kernel(int n, int kind, const int16_t* in, const uint8_t* ref, uint8_t* dst) {
+  WG_TID;
+  if (kind < 3) {
+    int c[16], r[16], d[16];
+    load16s16(in + 16 * (size_t)i, c); load16u8(ref + 16 * (size_t)i, r);
+    dec_transform_block(kind, c, r, d);
+    store16u8(dst + 16 * (size_t)i, d);
+    return;
+  }
+  for (int blk = 0; blk < 4; ++blk) {  // 8x8 tile (stride 8), coefficients [4][16]
+    int c[16], r[16], d[16];
+    load16s16(in + 64 * (size_t)i + 16 * blk, c);
+    const size_t o = 64 * (size_t)i + (blk >> 1) * 32 + (blk & 1) * 4;
+    for (int k = 0; k < 16; ++k) r[k] = ref[o + (k >> 2) * 8 + (k & 3)];
+    dec_transform_block(kind == 3 ? 0 : 1, c, r, d);
+    for (int k = 0; k < 16; ++k) dst[o + (k >> 2) * 8 + (k & 3)] = (uint8_t)d[k];
+  }
+}
+// loop-filter set (filter.go:93-242) on 24x24 tiles: the 16x16 (or 8x8) block sits at (4, 4), so edge 0 has its four
+// samples of context.  kind: 0 SimpleVFilter16, 1 SimpleHFilter16, 2 SimpleVFilter16i, 3 SimpleHFilter16i, 4 VFilter16,
+// 5 HFilter16, 6 VFilter16i, 7 HFilter16i, 8 VFilter8, 9 HFilter8, 10 VFilter8i, 11 HFilter8i (one chroma plane per tile).
+// One thread = one sample position along the edge; the inner edges of a position are walked in order as the reference does.
+__global__ void dsp_filter_kernel(int n_tasks, int kind, uint8_t* tiles, int thresh, int ithresh, int hev_t) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tasks) return;
+  const int size = kind >= 8 ? 8 : 16;
+  const int tile = t / size, i = t - tile * size;
+  uint8_t* base = tiles + (size_t)tile * 576 + 4 * 24 + 4;
+  const bool vertical = (kind & 1) == 0;                 // V filters cross a horizontal edge: step across = one row
+  const int across = vertical ? 24 : 1, along = vertical ? 1 : 24;
+  const bool simple = kind < 4, inner = (kind & 2) != 0;
+  const int k0 = inner ? 1 : 0, k1 = inner ? (size == 16 ? 3 : 1) : 0;
+  for (int k = k0; k <= k1; ++k) {
+    uint8_t* p = base + i * along + k * 4 * across;
+    if (simple) simple_edge(p, across, thresh);
+    else complex_edge(p, across, thresh, ithresh, hev_t, !inner);
+  }
+}
+// UpsampleLinePair / UpsampleLinePairNRGBA (upsample.go:45,130) on n independent line pairs of `width` pixels: one thread per
+// output column, both rows.  channels = 3 (RGB) or 4 (NRGBA, alpha rows optional).  bot_y may be null (last row of an odd height).
+__global__ void dsp_upsample_pair_kernel(int n, int width, const uint8_t* top_y, const uint8_t* bot_y, const uint8_t* top_u, const uint8_t* top_v,
+                                         const uint8_t* bot_u, const uint8_t* bot_v, const uint8_t* alpha_top, const uint8_t* alpha_bot, int channels,
+                                         uint8_t* top_dst, uint8_t* bot_dst) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * width) return;
+  const int pair = (int)(t / width), x = (int)(t - (long long)pair * width);
+  const int cw = (width + 1) >> 1;
+  const uint8_t* tu = top_u + (size_t)pair * cw; const uint8_t* tv = top_v + (size_t)pair * cw;
+  const uint8_t* bu = bot_u + (size_t)pair * cw; const uint8_t* bv = bot_v + (size_t)pair * cw;
+  auto ld = [](const uint8_t* u, const uint8_t* v, int k) { return (uint32_t)u[k] | ((uint32_t)v[k] << 16); };
+  uint32_t uvt, uvb;
+  const int last_pair = (width - 1) >> 1;
+  if (x == 0) {
+    const uint32_t tl = ld(tu, tv, 0), l = ld(bu, bv, 0);
+    uvt = (3 * tl + l + 0x00020002u) >> 2; uvb = (3 * l + tl + 0x00020002u) >> 2;
+  } else if (((x + 1) >> 1) > last_pair) {  // last pixel of an even width
+    const uint32_t tl = ld(tu, tv, last_pair), l = ld(bu, bv, last_pair);
+    uvt = (3 * tl + l + 0x00020002u) >> 2; uvb = (3 * l + tl + 0x00020002u) >> 2;
+  } else {
+    const int k = (x + 1) >> 1;
+    const uint32_t tl = ld(tu, tv, k - 1), tt = ld(tu, tv, k), l = ld(bu, bv, k - 1), cur = ld(bu, bv, k);
+    const uint32_t avg = tl + tt + l + cur + 0x00080008u;
+    const uint32_t diag12 = (avg + 2 * (tt + l)) >> 3, diag03 = (avg + 2 * (tl + cur)) >> 3;
+    if (x & 1) { uvt = (diag12 + tl) >> 1; uvb = (diag03 + l) >> 1; } else { uvt = (diag03 + tt) >> 1; uvb = (diag12 + cur) >> 1; }
+  }
+  const size_t o = ((size_t)pair * width + x);
+  const uint32_t pt = yuv_to_rgba(top_y[o], uvt & 0xff, (uvt >> 16) & 0xff, alpha_top ? alpha_top[o] : 255);
+  for (int c = 0; c < channels; ++c) top_dst[o * channels + c] = (uint8_t)(pt >> (8 * c));
+  if (bot_y) {
+    const uint32_t pb = yuv_to_rgba(bot_y[o], uvb & 0xff, (uvb >> 16) & 0xff, alpha_bot ? alpha_bot[o] : 255);
+    for (int c = 0; c < channels; ++c) bot_dst[o * channels + c] = (uint8_t)(pb >> (8 * c));
+  }
 }
 #undef WG_TID
 

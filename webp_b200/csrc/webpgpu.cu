@@ -1319,10 +1319,14 @@ int wgpu_enc_fetch(wgpu_ctx* ctx, int image, uint8_t* mb_hdr, uint8_t* mb_modes,
   return WGPU_OK;
 }
 
+static int launch_metrics(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int width, int height, int stride, size_t plane_stride, bool want_ssim);
+static int launch_upsample(wgpu_ctx* ctx, int n, int width, int height, const uint8_t* y, int ys, const uint8_t* u, const uint8_t* v,
+                           int uvs, size_t y_plane, size_t uv_plane, const uint8_t* alpha, uint8_t* out);
 int wgpu_enc_stage_time(wgpu_ctx* ctx, const wgpu_enc_options* opt, int stage, int reps, float* ms_per_rep) {
   if (!ctx || !ms_per_rep || reps <= 0) return WGPU_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  if (!ctx->e_done) FAIL(WGPU_ERR_INVALID, "wgpu_enc_stage_time needs a completed wgpu_enc_device");
+  if ((stage <= 3 || stage == 5) && !ctx->e_done) FAIL(WGPU_ERR_INVALID, "wgpu_enc_stage_time needs a completed wgpu_enc_device");
+  if (stage == 4 && !ctx->d_ready) FAIL(WGPU_ERR_INVALID, "stage 4 (upsampling) needs a decoded batch (wgpu_dec_parse + wgpu_dec_device)");
   (void)opt;
   CK(cudaSetDevice(ctx->dev));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1332,7 +1336,15 @@ int wgpu_enc_stage_time(wgpu_ctx* ctx, const wgpu_enc_options* opt, int stage, i
     if (stage == 0) rc = enc_launch_import(ctx);
     else if (stage == 1) rc = enc_launch_analysis(ctx);
     else if (stage == 2) rc = enc_launch_waves(ctx);
-    else FAIL(WGPU_ERR_INVALID, "unknown stage");
+    else if (stage == 3)  // SSE + SSIM of the source luma planes against the reconstruction, both resident from the encode
+      rc = launch_metrics(ctx, ctx->e_n, ctx->sy.as<uint8_t>(), ctx->ry.as<uint8_t>(), ctx->e_mbw * 16, ctx->e_mbh * 16, ctx->e_mbw * 16, (size_t)ctx->e_mbw * ctx->e_mbh * 256, true);
+    else if (stage == 5)  // SSE alone (PSNR): the streaming form
+      rc = launch_metrics(ctx, ctx->e_n, ctx->sy.as<uint8_t>(), ctx->ry.as<uint8_t>(), ctx->e_mbw * 16, ctx->e_mbh * 16, ctx->e_mbw * 16, (size_t)ctx->e_mbw * ctx->e_mbh * 256, false);
+    else if (stage == 4) {
+      RESERVE(ctx->d_nrgba, (size_t)ctx->d_n * ctx->d_w * ctx->d_h * 4);
+      rc = launch_upsample(ctx, ctx->d_n, ctx->d_w, ctx->d_h, ctx->dy.as<uint8_t>(), ctx->d_mbw * 16, ctx->du.as<uint8_t>(), ctx->dv.as<uint8_t>(), ctx->d_mbw * 8,
+                           (size_t)ctx->d_mbw * ctx->d_mbh * 256, (size_t)ctx->d_mbw * ctx->d_mbh * 64, nullptr, ctx->d_nrgba.as<uint8_t>());
+    } else FAIL(WGPU_ERR_INVALID, "unknown stage");
   }
   if (rc) return rc;
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -1347,7 +1359,9 @@ int wgpu_enc_stage_time(wgpu_ctx* ctx, const wgpu_enc_options* opt, int stage, i
 int wgpu_decode_info(const uint8_t* data, size_t len, int* width, int* height) {
   if (!data || !width || !height) return WGPU_ERR_INVALID;
   const uint8_t* vp8; size_t vlen; const char* err = nullptr;
-  if (!wgh::find_vp8(data, len, &vp8, &vlen)) return WGPU_ERR_BITSTREAM;
+  const int fr = wgh::find_vp8_ex(data, len, &vp8, &vlen);
+  if (fr < 0) return WGPU_ERR_UNSUPPORTED;
+  if (!fr) return WGPU_ERR_BITSTREAM;
   if (!wgh::peek_dims(vp8, vlen, width, height, &err)) return WGPU_ERR_BITSTREAM;
   return WGPU_OK;
 }
@@ -1386,8 +1400,8 @@ static int launch_upsample(wgpu_ctx* ctx, int n, int width, int height, const ui
   up.y = y; up.u = u; up.v = v; up.alpha = alpha;
   up.y_plane = y_plane; up.uv_plane = uv_plane; up.alpha_plane = (size_t)width * height; up.out_image = (size_t)width * height * 4;
   up.y_stride = ys; up.uv_stride = uvs; up.width = width; up.height = height; up.n = n; up.out = out;
-  const long long total = (long long)((width + 3) / 4) * height * n;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
+  const long long total = (long long)((width + 15) / 16) * (height / 2 + 1) * n;  // 16 pixels of a line pair per thread
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 64);
   wg::upsample_nrgba_kernel<<<blocks, 256, 0, ctx->stream>>>(up);
   ctx->launches++;
   CK(cudaGetLastError());
@@ -1403,6 +1417,10 @@ int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* l
   // dimensions from the first stream; every stream of the batch must match
   const uint8_t* vp8; size_t vlen; const char* perr = nullptr;
   int width = 0, height = 0;
+  for (int i = 0; i < n; ++i) {  // a VP8X + ALPH (or animated) file is rejected, never decoded as if it were opaque
+    const uint8_t* q; size_t ql;
+    if (wgh::find_vp8_ex(streams[i], lens[i], &q, &ql) < 0) FAIL(WGPU_ERR_UNSUPPORTED, std::string("image ") + std::to_string(i) + ": " + wgh::kErrOutsideLossyPath);
+  }
   if (!wgh::find_vp8(streams[0], lens[0], &vp8, &vlen) || !wgh::peek_dims(vp8, vlen, &width, &height, &perr))
     FAIL(WGPU_ERR_BITSTREAM, perr ? perr : "webp: no VP8 chunk");
   const int mbw = (width + 15) >> 4, mbh = (height + 15) >> 4;
@@ -1460,6 +1478,8 @@ int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* l
     ctx->xfer_h2d += (uint64_t)((size_t)n);
     CK(cudaMemsetAsync(ctx->d_coeffs.p, 0, (size_t)n * nmb * 768, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_perr.p, 0, (size_t)n * 4, ctx->stream));
+    // a truncated partition makes the parser stop early: what it did not reach must not be stale or uninitialised memory
+    CK(cudaMemsetAsync(ctx->d_meta.p, 0, (size_t)n * nmb * sizeof(wg::MBMeta), ctx->stream));
     wg::DecParseParams DP;
     DP.streams = ctx->d_streams.as<uint8_t>(); DP.hdr = ctx->d_hdrs.as<wg::DecHeader>(); DP.bmodes = ctx->t_bmodes.as<uint8_t>();
     DP.coeffs = ctx->d_coeffs.as<int16_t>(); DP.meta = ctx->d_meta.as<wg::MBMeta>(); DP.err = ctx->d_perr.as<int>();
@@ -1576,16 +1596,18 @@ int wgpu_dec_fetch(wgpu_ctx* ctx, uint8_t* y, uint8_t* u, uint8_t* v, size_t y_p
   const size_t nmb = (size_t)ctx->d_mbw * ctx->d_mbh, yp = nmb * 256, uvp = nmb * 64, img = (size_t)ctx->d_w * ctx->d_h * 4;
   if ((y && y_plane_stride < yp) || ((u || v) && uv_plane_stride < uvp)) FAIL(WGPU_ERR_TOO_SMALL, "plane stride smaller than the padded plane");
   if (nrgba && (!ctx->d_has_nrgba || nrgba_image_stride < img)) FAIL(WGPU_ERR_TOO_SMALL, "nrgba not produced or image stride too small");
+  if (ctx->d_dev_parsed) {  // the device parser reports truncated partitions here, the first point where the host waits -- and
+    // BEFORE anything is copied out: planes reconstructed from a partially parsed frame never reach the caller
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int* pe = ctx->hd_perr.as<int>();
+    for (int i = 0; i < n; ++i)
+      if (pe[i]) FAIL(WGPU_ERR_BITSTREAM, std::string("image ") + std::to_string(i) + ": vp8: premature end of data");
+  }
   if (y) { CK(cudaMemcpy2DAsync(y, y_plane_stride, ctx->dy.p, yp, yp, n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)yp * n; }
   if (u) { CK(cudaMemcpy2DAsync(u, uv_plane_stride, ctx->du.p, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)uvp * n; }
   if (v) { CK(cudaMemcpy2DAsync(v, uv_plane_stride, ctx->dv.p, uvp, uvp, n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)uvp * n; }
   if (nrgba) { CK(cudaMemcpy2DAsync(nrgba, nrgba_image_stride, ctx->d_nrgba.p, img, img, n, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)img * n; }
   CK(cudaStreamSynchronize(ctx->stream));
-  if (ctx->d_dev_parsed) {  // the device parser reports truncated partitions here, the first point where the host waits
-    const int* pe = ctx->hd_perr.as<int>();
-    for (int i = 0; i < n; ++i)
-      if (pe[i]) FAIL(WGPU_ERR_BITSTREAM, std::string("image ") + std::to_string(i) + ": vp8: premature end of data");
-  }
   return WGPU_OK;
 }
 
@@ -1650,6 +1672,7 @@ int wgpu_upsample_nrgba(wgpu_ctx* ctx, int n, int width, int height, const uint8
   const size_t csz = (size_t)(n - 1) * uv_plane_stride + (size_t)(ch - 1) * uv_stride + (width + 1) / 2;
   RESERVE(ctx->dy, ysz); RESERVE(ctx->du, csz); RESERVE(ctx->dv, csz);
   RESERVE(ctx->d_nrgba, (size_t)n * width * height * 4);
+  ctx->d_ready = false; ctx->d_has_nrgba = false;  // the decoder's result buffers are reused: a later wgpu_dec_fetch must not return them
   CK(cudaMemcpyAsync(ctx->dy.p, y, ysz, cudaMemcpyHostToDevice, ctx->stream));
   ctx->xfer_h2d += (uint64_t)(ysz);
   CK(cudaMemcpyAsync(ctx->du.p, u, csz, cudaMemcpyHostToDevice, ctx->stream));
@@ -1672,13 +1695,22 @@ int wgpu_upsample_nrgba(wgpu_ctx* ctx, int n, int width, int height, const uint8
   return WGPU_OK;
 }
 
-static int launch_metrics(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int width, int height, int stride, size_t plane_stride) {
+static int launch_metrics(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int width, int height, int stride, size_t plane_stride, bool want_ssim) {
   wg::MetricsParams mp;
   mp.a = a; mp.b = b; mp.plane_stride = plane_stride; mp.stride = stride; mp.width = width; mp.height = height; mp.n = n;
-  mp.tiles_x = (width + 31) / 32; mp.tiles_y = (height + 7) / 8;
+  mp.tiles_x = (width + wg::MET_TW - 1) / wg::MET_TW; mp.tiles_y = (height + wg::MET_TH - 1) / wg::MET_TH;
   const int tiles = mp.tiles_x * mp.tiles_y;
-  RESERVE(ctx->m_sse_part, (size_t)n * tiles * 8); RESERVE(ctx->m_ssim_part, (size_t)n * tiles * 8);
   RESERVE(ctx->m_sse, (size_t)n * 8); RESERVE(ctx->m_ssim, (size_t)n * 8);
+  if (!want_ssim) {  // SSE / PSNR only: the streaming kernel
+    CK(cudaMemsetAsync(ctx->m_sse.p, 0, (size_t)n * 8, ctx->stream));
+    const long long per_img = (long long)((width + 15) / 16) * height;
+    const unsigned bx = (unsigned)std::max<long long>(1, std::min<long long>((per_img + 255) / 256, std::max(1, ctx->sm_count * 16 / std::max(1, n))));
+    wg::sse_kernel<<<dim3(bx, (unsigned)n), 256, 0, ctx->stream>>>(mp, ctx->m_sse.as<unsigned long long>());
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return WGPU_OK;
+  }
+  RESERVE(ctx->m_sse_part, (size_t)n * tiles * 8); RESERVE(ctx->m_ssim_part, (size_t)n * tiles * 8);
   mp.sse_part = ctx->m_sse_part.as<unsigned long long>(); mp.ssim_part = ctx->m_ssim_part.as<double>();
   wg::metrics_kernel<<<(unsigned)(n * tiles), 256, 0, ctx->stream>>>(mp);
   wg::metrics_reduce_kernel<<<n, 256, 0, ctx->stream>>>(mp.sse_part, mp.ssim_part, tiles, ctx->m_sse.as<unsigned long long>(), ctx->m_ssim.as<double>());
@@ -1699,7 +1731,7 @@ int wgpu_plane_metrics(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b,
   ctx->xfer_h2d += (uint64_t)(sz);
   CK(cudaMemcpyAsync(ctx->m_b.p, b, sz, cudaMemcpyHostToDevice, ctx->stream));
   ctx->xfer_h2d += (uint64_t)(sz);
-  int rc = launch_metrics(ctx, n, ctx->m_a.as<uint8_t>(), ctx->m_b.as<uint8_t>(), width, height, stride, plane_stride);
+  int rc = launch_metrics(ctx, n, ctx->m_a.as<uint8_t>(), ctx->m_b.as<uint8_t>(), width, height, stride, plane_stride, ssim_sum != nullptr);
   if (rc) return rc;
   if (sse) { CK(cudaMemcpyAsync(sse, ctx->m_sse.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)((size_t)n * 8); }
   if (ssim_sum) { CK(cudaMemcpyAsync(ssim_sum, ctx->m_ssim.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream)); ctx->xfer_d2h += (uint64_t)((size_t)n * 8); }
@@ -1851,6 +1883,72 @@ int wgpu_dsp_token_cost_batch(wgpu_ctx* ctx, int n, const int16_t* levels, const
 }
 
 // ======================================================================================== measurement
+int wgpu_dsp_sse16x16_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int32_t* out) {
+  DSP_BEGIN;
+  DSP_IN(d_a, a, (size_t)n * 256); DSP_IN(d_b, b, (size_t)n * 256); DSP_OUT(d_out, int32_t, (size_t)n * 4);
+  wg::dsp_sse16x16_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_a, d_b, d_out);
+  DSP_END(d_out, out, (size_t)n * 4);
+  DSP_SYNC;
+}
+int wgpu_dsp_tdisto16x16_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int32_t* out) {
+  DSP_BEGIN;
+  DSP_IN(d_a, a, (size_t)n * 256); DSP_IN(d_b, b, (size_t)n * 256); DSP_OUT(d_out, int32_t, (size_t)n * 4);
+  wg::dsp_tdisto16x16_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_a, d_b, d_out);
+  DSP_END(d_out, out, (size_t)n * 4);
+  DSP_SYNC;
+}
+int wgpu_dsp_dequant_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, int ac_q, int16_t* out) {
+  DSP_BEGIN;
+  DSP_IN(d_in, in, (size_t)n * 32); DSP_OUT(d_out, int16_t, (size_t)n * 32);
+  wg::SegQuant sq;
+  memset(&sq, 0, sizeof(sq));
+  sq.quant = ac_q; sq.dc_quant = dc_q;
+  wg::dsp_dequant_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_in, sq, d_out);
+  DSP_END(d_out, out, (size_t)n * 32);
+  DSP_SYNC;
+}
+int wgpu_dsp_ftransform2_batch(wgpu_ctx* ctx, int n, const uint8_t* src, const uint8_t* ref, int16_t* out) {
+  return wgpu_dsp_ftransform_batch(ctx, 2 * n, src, ref, out);  // FTransform2 = two adjacent blocks (dsp.go:14)
+}
+int wgpu_dsp_dec_transform_batch(wgpu_ctx* ctx, int n, int kind, const int16_t* in, const uint8_t* ref, uint8_t* dst) {
+  DSP_BEGIN;
+  if (kind < 0 || kind > 4) FAIL(WGPU_ERR_INVALID, "wgpu_dsp_dec_transform_batch: kind 0..4");
+  const size_t per = kind < 3 ? 16 : 64;
+  DSP_IN(d_in, in, (size_t)n * per * 2); DSP_IN(d_ref, ref, (size_t)n * per); DSP_OUT(d_out, uint8_t, (size_t)n * per);
+  wg::dsp_dec_transform_kernel<<<grid, 128, 0, ctx->stream>>>(n, kind, d_in, d_ref, d_out);
+  DSP_END(d_out, dst, (size_t)n * per);
+  DSP_SYNC;
+}
+int wgpu_dsp_filter_batch(wgpu_ctx* ctx, int n, int kind, const uint8_t* tiles_in, int thresh, int ithresh, int hev_thresh, uint8_t* tiles_out) {
+  DSP_BEGIN;
+  (void)grid;
+  if (kind < 0 || kind > 11) FAIL(WGPU_ERR_INVALID, "wgpu_dsp_filter_batch: kind 0..11");
+  DSP_IN(d_t, tiles_in, (size_t)n * 576);
+  const int tasks = n * (kind >= 8 ? 8 : 16);
+  wg::dsp_filter_kernel<<<(unsigned)((tasks + 127) / 128), 128, 0, ctx->stream>>>(tasks, kind, const_cast<uint8_t*>(d_t), thresh, ithresh, hev_thresh);
+  DSP_END(d_t, tiles_out, (size_t)n * 576);
+  DSP_SYNC;
+}
+int wgpu_dsp_upsample_line_pair_batch(wgpu_ctx* ctx, int n, int width, const uint8_t* top_y, const uint8_t* bot_y, const uint8_t* top_u, const uint8_t* top_v,
+                                      const uint8_t* bot_u, const uint8_t* bot_v, const uint8_t* alpha_top, const uint8_t* alpha_bot, int channels,
+                                      uint8_t* top_dst, uint8_t* bot_dst) {
+  DSP_BEGIN;
+  (void)grid;
+  if (width <= 0 || (channels != 3 && channels != 4) || !top_y || !top_u || !top_v || !bot_u || !bot_v || !top_dst || (bot_y && !bot_dst))
+    FAIL(WGPU_ERR_INVALID, "wgpu_dsp_upsample_line_pair_batch: bad arguments");
+  const size_t yb = (size_t)n * width, cb = (size_t)n * ((width + 1) / 2);
+  DSP_IN(d_ty, top_y, yb); DSP_IN(d_tu, top_u, cb); DSP_IN(d_tv, top_v, cb); DSP_IN(d_bu, bot_u, cb); DSP_IN(d_bv, bot_v, cb);
+  const uint8_t* d_by = nullptr; const uint8_t* d_at = nullptr; const uint8_t* d_ab = nullptr;
+  if (bot_y) { DSP_IN(t_, bot_y, yb); d_by = t_; }
+  if (alpha_top) { DSP_IN(t_, alpha_top, yb); d_at = t_; }
+  if (alpha_bot) { DSP_IN(t_, alpha_bot, yb); d_ab = t_; }
+  DSP_OUT(d_td, uint8_t, yb * channels); DSP_OUT(d_bd, uint8_t, yb * channels);
+  wg::dsp_upsample_pair_kernel<<<(unsigned)((yb + 127) / 128), 128, 0, ctx->stream>>>(n, width, d_ty, d_by, d_tu, d_tv, d_bu, d_bv, d_at, d_ab, channels, d_td, d_bd);
+  DSP_END(d_td, top_dst, yb * channels);
+  if (bot_y) { DSP_END(d_bd, bot_dst, yb * channels); }
+  DSP_SYNC;
+}
+
 int wgpu_timer_begin(wgpu_ctx* ctx) {
   if (!ctx) return WGPU_ERR_INVALID;
   CK(cudaSetDevice(ctx->dev));

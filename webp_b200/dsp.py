@@ -145,3 +145,65 @@ def PlaneMetrics(a, b, ctx=None):
 def PSNRFromSSE(sse, count):
     """dsp.PSNRFromSSE (ssim.go:163)."""
     return float(native.lib().wgpu_psnr_from_sse(int(sse), int(count)))
+
+
+def SSE16x16Batch(a, b, ctx=None):
+    """dsp.SSE16x16Direct (ssim.go:220): uint8 [n][16][16] x2 -> int32 [n]."""
+    ctx = _ctx(ctx); a = _c(a, np.uint8); b = _c(b, np.uint8); n = a.shape[0]; out = np.empty(n, np.int32)
+    ctx.check(native.lib().wgpu_dsp_sse16x16_batch(ctx.handle, n, a.ctypes.data, b.ctypes.data, out.ctypes.data))
+    return out
+
+
+def TDisto16x16Batch(a, b, ctx=None):
+    """dsp.TDisto16x16 (ssim.go:327)."""
+    ctx = _ctx(ctx); a = _c(a, np.uint8); b = _c(b, np.uint8); n = a.shape[0]; out = np.empty(n, np.int32)
+    ctx.check(native.lib().wgpu_dsp_tdisto16x16_batch(ctx.handle, n, a.ctypes.data, b.ctypes.data, out.ctypes.data))
+    return out
+
+
+def DequantCoeffsBatch(levels, dc_q, ac_q, ctx=None):
+    """lossy.DequantCoeffs (internal/lossy/encode_quant.go:81): int16 [n][16] -> int16 [n][16] (int16 truncation as the reference)."""
+    ctx = _ctx(ctx); levels = _c(levels, np.int16); n = levels.shape[0]; out = np.empty((n, 16), np.int16)
+    ctx.check(native.lib().wgpu_dsp_dequant_batch(ctx.handle, n, levels.ctypes.data, int(dc_q), int(ac_q), out.ctypes.data))
+    return out
+
+
+def FTransform2Batch(src, ref, ctx=None):
+    """dsp.FTransform2 (dsp.go:14): two adjacent blocks per call: uint8 [n][2][16] x2 -> int16 [n][2][16]."""
+    ctx = _ctx(ctx); src = _c(src, np.uint8); ref = _c(ref, np.uint8); n = src.shape[0]; out = np.empty((n, 2, 16), np.int16)
+    ctx.check(native.lib().wgpu_dsp_ftransform2_batch(ctx.handle, n, src.ctypes.data, ref.ctypes.data, out.ctypes.data))
+    return out
+
+
+DEC_TRANSFORMS = {"Transform": 0, "TransformDC": 1, "TransformAC3": 2, "TransformUV": 3, "TransformDCUV": 4}
+
+
+def DecTransformBatch(kind, coeffs, ref, ctx=None):
+    """dsp.Transform / TransformDC / TransformAC3 (4x4 blocks: coeffs int16 [n][16], ref uint8 [n][16]) and TransformUV /
+    TransformDCUV (8x8 tiles: coeffs [n][4][16], ref [n][8][8]) -- transforms.go:37-216.  Returns ref + inverse transform."""
+    ctx = _ctx(ctx); coeffs = _c(coeffs, np.int16); ref = _c(ref, np.uint8); n = ref.shape[0]; out = np.empty_like(ref)
+    ctx.check(native.lib().wgpu_dsp_dec_transform_batch(ctx.handle, n, DEC_TRANSFORMS[kind], coeffs.ctypes.data, ref.ctypes.data, out.ctypes.data))
+    return out
+
+
+FILTERS = ["SimpleVFilter16", "SimpleHFilter16", "SimpleVFilter16i", "SimpleHFilter16i", "VFilter16", "HFilter16", "VFilter16i", "HFilter16i",
+           "VFilter8", "HFilter8", "VFilter8i", "HFilter8i"]
+
+
+def FilterBatch(kind, tiles, thresh, ithresh=0, hev_thresh=0, ctx=None):
+    """The loop-filter set of internal/dsp/filter.go:93-242 on uint8 tiles [n][24][24] holding the block at (4, 4)."""
+    ctx = _ctx(ctx); tiles = _c(tiles, np.uint8); n = tiles.shape[0]; out = np.empty_like(tiles)
+    ctx.check(native.lib().wgpu_dsp_filter_batch(ctx.handle, n, FILTERS.index(kind), tiles.ctypes.data, int(thresh), int(ithresh), int(hev_thresh),
+                                                 out.ctypes.data))
+    return out
+
+
+def UpsampleLinePairBatch(top_y, bot_y, top_u, top_v, bot_u, bot_v, channels=3, alpha_top=None, alpha_bot=None, ctx=None):
+    """dsp.UpsampleLinePair (upsample.go:45, channels=3) / UpsampleLinePairNRGBA (:130, channels=4) on n line pairs [n][width]."""
+    ctx = _ctx(ctx); top_y = _c(top_y, np.uint8); n, width = top_y.shape
+    arrs = [None if a is None else _c(a, np.uint8) for a in (bot_y, top_u, top_v, bot_u, bot_v, alpha_top, alpha_bot)]
+    ptr = [None if a is None else a.ctypes.data for a in arrs]
+    td = np.empty((n, width, channels), np.uint8); bd = np.empty((n, width, channels), np.uint8)
+    ctx.check(native.lib().wgpu_dsp_upsample_line_pair_batch(ctx.handle, n, width, top_y.ctypes.data, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4],
+                                                             ptr[5], ptr[6], channels, td.ctypes.data, bd.ctypes.data))
+    return td, (bd if bot_y is not None else None)

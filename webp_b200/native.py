@@ -95,6 +95,13 @@ def lib():
         L.wgpu_dsp_quantize_batch.argtypes = [vp, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i16p, i32p]
         L.wgpu_dsp_trellis_batch.argtypes = [vp, C.c_int, i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i16p, i32p]
         L.wgpu_dsp_token_cost_batch.argtypes = [vp, C.c_int, i16p, i32p, C.c_int, i32p, C.c_int, i32p]
+        L.wgpu_dsp_sse16x16_batch.argtypes = [vp, C.c_int, u8p, u8p, i32p]
+        L.wgpu_dsp_tdisto16x16_batch.argtypes = [vp, C.c_int, u8p, u8p, i32p]
+        L.wgpu_dsp_dequant_batch.argtypes = [vp, C.c_int, i16p, C.c_int, C.c_int, i16p]
+        L.wgpu_dsp_ftransform2_batch.argtypes = [vp, C.c_int, u8p, u8p, i16p]
+        L.wgpu_dsp_dec_transform_batch.argtypes = [vp, C.c_int, C.c_int, i16p, u8p, u8p]
+        L.wgpu_dsp_filter_batch.argtypes = [vp, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p]
+        L.wgpu_dsp_upsample_line_pair_batch.argtypes = [vp, C.c_int, C.c_int] + [u8p] * 8 + [C.c_int, u8p, u8p]
         L.wgpu_cleanup_transparent.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, sz, u8p]
         L.wgpu_timer_begin.argtypes = [vp]
         L.wgpu_timer_end.argtypes = [vp, C.POINTER(C.c_float)]

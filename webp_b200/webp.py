@@ -251,6 +251,8 @@ def DecodeConfig(r):
     data = bytes(_read_all(r))
     w, h = C.c_int(), C.c_int()
     rc = native.lib().wgpu_decode_info(data, len(data), C.byref(w), C.byref(h))
+    if rc == native.ERR_UNSUPPORTED:
+        raise WebPError("webp: ALPH chunk / alpha or animation flag: outside the GPU lossy path")
     if rc != native.OK:
         raise WebPError("webp: invalid VP8 lossy stream")
     return Config(w.value, h.value)
