@@ -454,3 +454,76 @@ def test_round_trip_at_full_size(oracle, gpu_ctx, parser_route):
         sse, _ = dsp.PlaneMetrics(g[k]["src_y"][None], y[k][None], gpu_ctx)
         assert dsp.PSNRFromSSE(sse[0], 1536 * 1024) >= 30.0
     assert files[1] == oracle.encode(imgs[1], _ocfg(oracle, o))
+
+
+def test_two_contexts_concurrently_at_bench_size(oracle, monkeypatch):
+    """What bench.py times, checked: 64 images 1536x1024 with DEFAULT options (FilterStrength 60, 4 segments, Method 4) through
+    TWO contexts running at the same time on one GPU, token partitions coded on the GPU (boolcode_kernel of one context beside
+    the other context's mode-search waves); then the streams decoded concurrently on both contexts, one per macroblock-parser
+    route, with the complex loop filter on.  Files, planes and NRGBA against the oracle."""
+    import concurrent.futures as cf
+    import threading
+    monkeypatch.setenv("WGPU_DEVICE_CODER", "1")
+    w, h, n = 1536, 1024, 64
+    distinct = [np.stack([oracle.synth_image(w, h, 3 * k + j) for j in range(3)]) for k in (0, 1)]  # six different pictures, all classes
+    batches = [np.concatenate([d] * ((n + 2) // 3))[:n] for d in distinct]
+    ctxs = [native.Context(0), native.Context(0)]
+    try:
+        o = webp_b200.DefaultOptions()
+        files = [None, None]
+        go = threading.Barrier(2)
+
+        def enc(i):
+            go.wait()
+            for _ in range(2):  # twice: the second batch of a context overlaps the other context's coder
+                files[i] = webp_b200.EncodeBatch(batches[i], o, ctxs[i])
+        ths = [threading.Thread(target=enc, args=(i,)) for i in range(2)]
+        [t.start() for t in ths]; [t.join() for t in ths]
+        with cf.ThreadPoolExecutor(max_workers=6) as ex:
+            exp = list(ex.map(lambda im: oracle.encode(im, _ocfg(oracle, o)), [distinct[i][j] for i in range(2) for j in range(3)]))
+        for i in range(2):
+            for k in range(n):
+                assert files[i][k] == exp[3 * i + k % 3], "context %d image %d" % (i, k)
+        # decode: context 0 parses on the host, context 1 on the GPU
+        out = [None, None]
+
+        # the parser route is an environment knob read at call time: run the two routes one after the other with the OTHER context
+        # busy encoding, so that each decode still shares the GPU with foreign kernels
+        for i in range(2):
+            os.environ["WGPU_DEVICE_PARSER"] = str(i)
+            t = threading.Thread(target=lambda j=1 - i: webp_b200.EncodeBatch(batches[j][:16], o, ctxs[j]))
+            t.start()
+            out[i] = webp_b200.webp.decode_padded(files[i], nrgba=True, ctx=ctxs[i])
+            t.join()
+        os.environ.pop("WGPU_DEVICE_PARSER", None)
+        for i in range(2):
+            _, _, y, u, v, rgba = out[i]
+            for k in (0, 1, 2, n - 1):
+                _, _, ey, eu, ev = oracle.decode(files[i][k])
+                assert np.array_equal(y[k], ey) and np.array_equal(u[k], eu) and np.array_equal(v[k], ev), "planes ctx %d image %d" % (i, k)
+                assert np.array_equal(rgba[k], oracle.build_nrgba(w, h, ey, eu, ev)), "nrgba ctx %d image %d" % (i, k)
+    finally:
+        os.environ.pop("WGPU_DEVICE_PARSER", None)
+        for c in ctxs:
+            c.close()
+
+
+def test_alph_and_vp8x_alpha_files_are_rejected(oracle, gpu_ctx):
+    """A lossy-with-alpha file (VP8X alpha flag + ALPH chunk) must not decode as if it were opaque (webp.go:323-350 returns NRGBA
+    with the real alpha there): the GPU path rejects it with its own message instead of silently dropping the alpha plane."""
+    import struct
+    vp8 = oracle.encode(oracle.synth_image(32, 32, 1))[20:]  # the VP8 payload of a simple RIFF file
+    def chunk(tag, payload):
+        return tag + struct.pack("<I", len(payload)) + payload + (b"\0" if len(payload) & 1 else b"")
+    vp8x = chunk(b"VP8X", bytes([0x10, 0, 0, 0, 31, 0, 0, 31, 0, 0]))
+    body = b"WEBP" + vp8x + chunk(b"ALPH", b"\0" + bytes(32 * 32)) + chunk(b"VP8 ", vp8)
+    data = b"RIFF" + struct.pack("<I", len(body)) + body
+    with pytest.raises(webp_b200.WebPError) as e:
+        webp_b200.DecodeBatch([data], ctx=gpu_ctx)
+    assert "ALPH" in str(e.value) or "alpha" in str(e.value)
+    with pytest.raises(webp_b200.WebPError):
+        webp_b200.DecodeConfig(data)
+    # without the alpha flag and chunk the same payload in an extended container still decodes
+    body = b"WEBP" + chunk(b"VP8X", bytes([0, 0, 0, 0, 31, 0, 0, 31, 0, 0])) + chunk(b"VP8 ", vp8)
+    ok = b"RIFF" + struct.pack("<I", len(body)) + body
+    assert webp_b200.DecodeConfig(ok).Width == 32
