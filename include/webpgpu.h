@@ -141,6 +141,22 @@ int wgpu_dec_device(wgpu_ctx* ctx, int want_nrgba);
 int wgpu_dec_fetch(wgpu_ctx* ctx, uint8_t* y, uint8_t* u, uint8_t* v, size_t y_plane_stride, size_t uv_plane_stride,
                    uint8_t* nrgba, size_t nrgba_image_stride);
 
+/* Pre-parsed entry: the Go decoder keeps parseHeaders / parseIntraModeRow / decodeMB (internal/lossy/decode.go:245-438,
+ * decode_tree.go:35, decode_mb.go:111-313) and hands over what reconstructRow + doFilter + buildNRGBA consume, for whole frames instead
+ * of one macroblock row.  wgpu_mb_data is MBData (decode.go:122-131: Coeffs dequantised with the WHT applied, the two 2-bit-per-block
+ * transform codes NonZeroY / NonZeroUV, IsI4x4, IModes, UVMode, Skip, Segment) followed by that macroblock's FInfo (decode.go:107-112) as
+ * precomputeFilterStrengths left it.  filter_type[i] = dec.filterType of image i (0 none, 1 simple, 2 complex, decode.go:399).
+ * Runs the reconstruction, loop-filter and (want_nrgba) upsampling kernels; wgpu_dec_fetch then returns planes / NRGBA. */
+typedef struct wgpu_mb_data {
+  int16_t coeffs[384];
+  uint32_t non_zero_y, non_zero_uv;
+  uint8_t imodes[16];
+  uint8_t is_i4x4, uv_mode, skip, segment;
+  uint8_t f_limit, f_ilevel, f_inner, hev_thresh;
+} wgpu_mb_data;
+int wgpu_dec_reconstruct(wgpu_ctx* ctx, int n, int width, int height, const wgpu_mb_data* mbs /* [n][mb_h][mb_w] */,
+                         const uint8_t* filter_type /* [n] */, int want_nrgba);
+
 /* cleanupTransparentAreaLossy (encode.go:788-890) on n NRGBA images (non-premultiplied, 4 bytes per pixel): colours under
  * fully transparent pixels are smoothed / flattened per 8x8 block before the lossy encode of an image with alpha. */
 int wgpu_cleanup_transparent(wgpu_ctx* ctx, const uint8_t* nrgba, int n, int width, int height, int stride, size_t image_stride,
@@ -201,6 +217,12 @@ int wgpu_dsp_upsample_line_pair_batch(wgpu_ctx* ctx, int n, int width, const uin
                                       const uint8_t* top_u, const uint8_t* top_v, const uint8_t* bot_u, const uint8_t* bot_v,
                                       const uint8_t* alpha_top, const uint8_t* alpha_bot, int channels, uint8_t* top_dst,
                                       uint8_t* bot_dst);
+
+/* Token statistics for a host that keeps the serial path's probability refresh to itself (refreshProbas -> collectAllStats,
+ * encode_frame.go:113, encode_proba.go:171): after wgpu_enc_device / wgpu_enc_search, the counts over the per-macroblock array of
+ * every image as it stands with macroblocks of raster index >= upto_mb still in their zero state (not yet encoded: I16, not skipped,
+ * no coefficients) -- upto_mb = mb_w * mb_h is collectAllStats over the finished frame.  stats [n][4][8][3][11][2] uint32. */
+int wgpu_enc_stats(wgpu_ctx* ctx, int upto_mb, uint32_t* stats);
 
 /* ---- measurement helpers (device timing on the library's own stream) -------------------- */
 int wgpu_timer_begin(wgpu_ctx* ctx);           /* records a CUDA event on the ctx stream */

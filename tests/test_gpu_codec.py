@@ -527,3 +527,60 @@ def test_alph_and_vp8x_alpha_files_are_rejected(oracle, gpu_ctx):
     body = b"WEBP" + chunk(b"VP8X", bytes([0, 0, 0, 0, 31, 0, 0, 31, 0, 0])) + chunk(b"VP8 ", vp8)
     ok = b"RIFF" + struct.pack("<I", len(body)) + body
     assert webp_b200.DecodeConfig(ok).Width == 32
+
+
+def test_dec_reconstruct_from_preparsed_macroblocks(oracle, gpu_ctx):
+    """the Go decoder keeps its own parser and hands frame-sized MBData + FInfo arrays to wgpu_dec_reconstruct.
+    The records come from the product's host parser run on the CPU (hostcheck_parse: coefficients + the 32-byte side record per
+    macroblock, checked against the oracle decoder's taps in tests/test_oracle.py); planes and NRGBA must equal the oracle's."""
+    H = C.CDLL(os.path.join(os.path.dirname(DATA), "..", "oracle", "_build", "libhostcheck.so"))
+    L = native.lib()
+    for (w, h, idxs, kw) in [(128, 96, (0, 1, 2), {}), (130, 71, (1, 2), dict(filter_type=0, filter_strength=40)), (320, 240, (2,), dict(filter_strength=0)),
+                             (768, 576, (1, 2), dict(quality=40, filter_sharpness=5))]:
+        files = [oracle.encode(oracle.synth_image(w, h, i), oracle.default_cfg(**kw)) for i in idxs]
+        n, mbw, mbh = len(files), (w + 15) >> 4, (h + 15) >> 4
+        nmb = mbw * mbh
+        rec = np.zeros((n, nmb, 800), np.uint8)
+        ftype = np.zeros(n, np.uint8)
+        for i, f in enumerate(files):
+            co = np.zeros((nmb, 384), np.int16); me = np.zeros((nmb, 32), np.uint8); dims = (C.c_int * 5)()
+            assert H.hostcheck_parse(f, C.c_long(len(f)), co.ctypes.data_as(C.c_void_p), me.ctypes.data_as(C.c_void_p), C.c_long(nmb), dims) == 0
+            assert (dims[0], dims[1]) == (w, h)
+            rec[i, :, :768] = co.view(np.uint8).reshape(nmb, 768)
+            rec[i, :, 768:] = me
+            ftype[i] = dims[4]
+        gpu_ctx.check(L.wgpu_dec_reconstruct(gpu_ctx.handle, n, w, h, rec.ctypes.data, ftype.ctypes.data, 1))
+        y = np.empty((n, mbh * 16, mbw * 16), np.uint8); u = np.empty((n, mbh * 8, mbw * 8), np.uint8); v = np.empty_like(u)
+        rgba = np.empty((n, h, w, 4), np.uint8)
+        gpu_ctx.check(L.wgpu_dec_fetch(gpu_ctx.handle, y.ctypes.data, u.ctypes.data, v.ctypes.data, y[0].nbytes, u[0].nbytes, rgba.ctypes.data, w * h * 4))
+        for i, f in enumerate(files):
+            _, _, ey, eu, ev = oracle.decode(f)
+            assert np.array_equal(y[i], ey) and np.array_equal(u[i], eu) and np.array_equal(v[i], ev), (w, h, i)
+            assert np.array_equal(rgba[i], oracle.build_nrgba(w, h, ey, eu, ev))
+    bad = rec.copy(); bad[0, 0, 768 + 8 + 16 + 1] = 9  # uv_mode out of range
+    assert L.wgpu_dec_reconstruct(gpu_ctx.handle, n, w, h, bad.ctypes.data, ftype.ctypes.data, 0) == native.ERR_INVALID
+
+
+def test_enc_stats_for_a_host_side_refresh(oracle, gpu_ctx):
+    """wgpu_enc_stats (collectAllStats with the not-yet-encoded macroblocks in their zero state, encode_proba.go:171,
+    encode_frame.go:35-57): with no macroblock encoded every one is I16, not skipped, without coefficients -> one EOB event
+    per block in context 0 (WHT block: type 1 band 0; 16 luma AC blocks: type 0 band 1; 8 chroma blocks: type 2 band 0); the
+    counts grow monotonically with the cut and the full-frame call is repeatable."""
+    w, h = 160, 112
+    imgs = np.stack([oracle.synth_image(w, h, i) for i in (1, 2)])
+    webp_b200.EncodeBatch(imgs, webp_b200.DefaultOptions(), gpu_ctx)
+    nmb = 10 * 7
+    L = native.lib()
+    def stats(cut):
+        st = np.zeros((2, 4, 8, 3, 11, 2), np.uint32)
+        gpu_ctx.check(L.wgpu_enc_stats(gpu_ctx.handle, cut, st.ctypes.data))
+        return st
+    z = stats(0)
+    exp = np.zeros_like(z)
+    exp[:, 1, 0, 0, 0, 0] = nmb; exp[:, 0, 1, 0, 0, 0] = 16 * nmb; exp[:, 2, 0, 0, 0, 0] = 8 * nmb
+    assert np.array_equal(z, exp)
+    full = stats(nmb)
+    assert np.array_equal(full, stats(nmb)) and not np.array_equal(full, z)
+    half = stats(nmb // 2)
+    assert int(half.sum()) >= int(z.sum()) and int(full.sum()) >= int(half.sum())
+    assert L.wgpu_enc_stats(gpu_ctx.handle, nmb + 1, z.ctypes.data) == native.ERR_INVALID

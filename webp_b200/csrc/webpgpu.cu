@@ -1282,6 +1282,28 @@ int wgpu_encode_batch(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int 
   return wgpu_enc_finish(ctx, out, out_stride, out_sizes);
 }
 
+int wgpu_enc_stats(wgpu_ctx* ctx, int upto_mb, uint32_t* stats) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->e_done) FAIL(WGPU_ERR_INVALID, "wgpu_enc_stats needs a completed wgpu_enc_device / wgpu_enc_search");
+  const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
+  if (!stats || upto_mb < 0 || upto_mb > nmb) FAIL(WGPU_ERR_INVALID, "wgpu_enc_stats: bad arguments");
+  CK(cudaSetDevice(ctx->dev));
+  const size_t bytes = (size_t)n * wg::STATS_SIZE * 4;
+  RESERVE(ctx->stats_cuts, bytes);
+  wg::AllStatsParams A;
+  A.hdr = ctx->hdr.as<uint8_t>(); A.coeffs = ctx->coeffs.as<int16_t>(); A.stats = ctx->stats_cuts.as<unsigned int>();
+  A.n_images = n; A.mb_w = ctx->e_mbw; A.mb_h = ctx->e_mbh; A.cut = upto_mb; A.hdr_prev = nullptr; A.coeffs_prev = nullptr;
+  CK(cudaMemsetAsync(A.stats, 0, bytes, ctx->stream));
+  wg::collect_all_stats_kernel<<<(unsigned)(((long long)n * nmb + 127) / 128), 128, 0, ctx->stream>>>(A);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(stats, A.stats, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->xfer_d2h += (uint64_t)bytes;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WGPU_OK;
+}
+
 int wgpu_transfer_bytes(wgpu_ctx* ctx, uint64_t* h2d, uint64_t* d2h, int reset) {
   if (!ctx) return WGPU_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1524,6 +1546,55 @@ int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* l
   if (width_out) *width_out = width;
   if (height_out) *height_out = height;
   return WGPU_OK;
+}
+
+int wgpu_dec_device(wgpu_ctx* ctx, int want_nrgba);
+int wgpu_dec_reconstruct(wgpu_ctx* ctx, int n, int width, int height, const wgpu_mb_data* mbs, const uint8_t* filter_type, int want_nrgba) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!mbs || !filter_type || n <= 0 || width <= 0 || height <= 0 || width > 16383 || height > 16383) FAIL(WGPU_ERR_INVALID, "wgpu_dec_reconstruct: bad arguments");
+    static_assert(sizeof(wgpu_mb_data) == 768 + sizeof(wgh::MBMetaH), "wgpu_mb_data = Coeffs + the 32-byte side record");
+    CK(cudaSetDevice(ctx->dev));
+    ctx->d_ready = false;
+    const int mbw = (width + 15) >> 4, mbh = (height + 15) >> 4;
+    const size_t nmb = (size_t)mbw * mbh;
+    RESERVE(ctx->hd_coeffs, (size_t)n * nmb * 768);
+    RESERVE(ctx->hd_meta, (size_t)n * nmb * sizeof(wgh::MBMetaH));
+    RESERVE(ctx->hd_ftype, (size_t)n);
+    RESERVE(ctx->d_coeffs, (size_t)n * nmb * 768);
+    RESERVE(ctx->d_meta, (size_t)n * nmb * sizeof(wg::MBMeta));
+    RESERVE(ctx->d_ftype, (size_t)n);
+    RESERVE(ctx->dy, (size_t)n * nmb * 256); RESERVE(ctx->du, (size_t)n * nmb * 64); RESERVE(ctx->dv, (size_t)n * nmb * 64);
+    // array of records -> the two arrays the kernels read (coefficients, side data), into the pinned staging buffers
+    int16_t* hc = ctx->hd_coeffs.as<int16_t>();
+    wgh::MBMetaH* hm = ctx->hd_meta.as<wgh::MBMetaH>();
+    std::atomic<int> bad(-1);
+    parallel_for(n, threads_of(ctx), [&](int i) {
+      if (filter_type[i] > 2) { bad.store(i); return; }
+      for (size_t k = 0; k < nmb; ++k) {
+        const wgpu_mb_data& m = mbs[(size_t)i * nmb + k];
+        memcpy(hc + ((size_t)i * nmb + k) * 384, m.coeffs, 768);
+        memcpy(&hm[(size_t)i * nmb + k], &m.non_zero_y, sizeof(wgh::MBMetaH));
+        if (m.uv_mode > 3 || (m.is_i4x4 ? false : m.imodes[0] > 3)) bad.store(i);
+        if (m.is_i4x4) for (int b = 0; b < 16; ++b) if (m.imodes[b] > 9) bad.store(i);
+      }
+      ctx->hd_ftype.as<uint8_t>()[i] = filter_type[i];
+    });
+    if (bad.load() >= 0) FAIL(WGPU_ERR_INVALID, std::string("image ") + std::to_string(bad.load()) + ": prediction mode or filter type out of range");
+    CK(cudaMemcpyAsync(ctx->d_coeffs.p, ctx->hd_coeffs.p, (size_t)n * nmb * 768, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)((size_t)n * nmb * 768);
+    CK(cudaMemcpyAsync(ctx->d_meta.p, ctx->hd_meta.p, (size_t)n * nmb * sizeof(wg::MBMeta), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)((size_t)n * nmb * sizeof(wg::MBMeta));
+    CK(cudaMemcpyAsync(ctx->d_ftype.p, ctx->hd_ftype.p, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)((size_t)n);
+    ctx->d_any_filter = false;
+    for (int i = 0; i < n; ++i) ctx->d_any_filter |= filter_type[i] > 0;
+    ctx->d_dev_parsed = false;
+    ctx->d_n = n; ctx->d_w = width; ctx->d_h = height; ctx->d_mbw = mbw; ctx->d_mbh = mbh;
+    ctx->d_ready = true;
+  }
+  return wgpu_dec_device(ctx, want_nrgba);
 }
 
 int wgpu_dec_device(wgpu_ctx* ctx, int want_nrgba) {
