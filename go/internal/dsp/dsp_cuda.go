@@ -60,3 +60,39 @@ func CleanupTransparentAreaCUDA(ctx unsafe.Pointer, nrgba []byte, n, w, h, strid
 	return int(C.wgpu_cleanup_transparent((*C.wgpu_ctx)(ctx), (*C.uint8_t)(&nrgba[0]), C.int(n), C.int(w), C.int(h), C.int(stride),
 		C.size_t(imageStride), (*C.uint8_t)(&out[0])))
 }
+
+// The rest of the surface (include/webpgpu.h): 16x16 metrics, DequantCoeffs, decoder transforms, the loop-filter set on
+// 24x24 tiles, UpsampleLinePair (RGB) / UpsampleLinePairNRGBA.
+func SSE16x16BatchCUDA(ctx unsafe.Pointer, a, b []byte, out []int32) int {
+	return int(C.wgpu_dsp_sse16x16_batch((*C.wgpu_ctx)(ctx), C.int(len(out)), (*C.uint8_t)(&a[0]), (*C.uint8_t)(&b[0]), (*C.int32_t)(&out[0])))
+}
+func TDisto16x16BatchCUDA(ctx unsafe.Pointer, a, b []byte, out []int32) int {
+	return int(C.wgpu_dsp_tdisto16x16_batch((*C.wgpu_ctx)(ctx), C.int(len(out)), (*C.uint8_t)(&a[0]), (*C.uint8_t)(&b[0]), (*C.int32_t)(&out[0])))
+}
+func DequantCoeffsBatchCUDA(ctx unsafe.Pointer, in []int16, dcQ, acQ int, out []int16) int {
+	return int(C.wgpu_dsp_dequant_batch((*C.wgpu_ctx)(ctx), C.int(len(out)/16), (*C.int16_t)(&in[0]), C.int(dcQ), C.int(acQ), (*C.int16_t)(&out[0])))
+}
+
+// kind: 0 Transform, 1 TransformDC, 2 TransformAC3 (4x4 blocks), 3 TransformUV, 4 TransformDCUV (8x8 tiles) -- transforms.go:37-216.
+func DecTransformBatchCUDA(ctx unsafe.Pointer, n, kind int, in []int16, ref, dst []byte) int {
+	return int(C.wgpu_dsp_dec_transform_batch((*C.wgpu_ctx)(ctx), C.int(n), C.int(kind), (*C.int16_t)(&in[0]), (*C.uint8_t)(&ref[0]), (*C.uint8_t)(&dst[0])))
+}
+
+// kind: 0 SimpleVFilter16 ... 11 HFilter8i in the order of filter.go:93-242; tiles are 24x24 with the block at (4, 4).
+func FilterBatchCUDA(ctx unsafe.Pointer, n, kind int, tilesIn []byte, thresh, ithresh, hevThresh int, tilesOut []byte) int {
+	return int(C.wgpu_dsp_filter_batch((*C.wgpu_ctx)(ctx), C.int(n), C.int(kind), (*C.uint8_t)(&tilesIn[0]), C.int(thresh), C.int(ithresh),
+		C.int(hevThresh), (*C.uint8_t)(&tilesOut[0])))
+}
+
+// channels = 3: UpsampleLinePair (upsample.go:45); 4: UpsampleLinePairNRGBA (:130).  botY == nil: last row of an odd height.
+func UpsampleLinePairBatchCUDA(ctx unsafe.Pointer, n, width int, topY, botY, topU, topV, botU, botV, alphaTop, alphaBot []byte, channels int,
+	topDst, botDst []byte) int {
+	p := func(b []byte) *C.uint8_t {
+		if len(b) == 0 {
+			return nil
+		}
+		return (*C.uint8_t)(&b[0])
+	}
+	return int(C.wgpu_dsp_upsample_line_pair_batch((*C.wgpu_ctx)(ctx), C.int(n), C.int(width), p(topY), p(botY), p(topU), p(topV), p(botU), p(botV),
+		p(alphaTop), p(alphaBot), C.int(channels), p(topDst), p(botDst)))
+}

@@ -8,6 +8,7 @@ package lossy
 
 /*
 #cgo LDFLAGS: -lwebpgpu
+#include <stdlib.h>
 #include "webpgpu.h"
 */
 import "C"
@@ -20,9 +21,12 @@ import (
 
 // DecodeBatchCUDA decodes n lossy streams of identical dimensions.  y/u/v receive macroblock-padded planes
 // (stride 16*mbW / 8*mbW, as dec.cacheY/U/V); nrgba, when non-nil, receives buildNRGBA output (webp.go:379).
-// The library restates the host parser; the Go parser can be used instead through wgpu_dec_* once a
-// "pre-parsed MBData" entry point is added (SURVEY.md 8b) -- both produce the same MBData by construction.
+// This form lets the library parse the streams itself (on the host or on the GPU); ReconstructBatchCUDA below is the form
+// SURVEY.md 8b describes, with the Go parser kept.
 func DecodeBatchCUDA(streams [][]byte, y, u, v, nrgba []byte, yPlane, uvPlane, nrgbaImage int) error {
+	if len(streams) == 0 {
+		return nil
+	}
 	dev, err := pool.GetDevice(0)
 	if err != nil {
 		return err
@@ -47,4 +51,58 @@ func DecodeBatchCUDA(streams [][]byte, y, u, v, nrgba []byte, yPlane, uvPlane, n
 		return dev.Err("decode")
 	}
 	return nil
+}
+
+// ReconstructBatchCUDA is DecodeFrame's pixel half for a batch (decode.go:209-241 minus the parsing): the caller has run
+// parseHeaders and, for every macroblock row, parseIntraModeRow + decodeMB + precomputeFilterStrengths exactly as today, but
+// kept every row's MBData and FInfo (frame-sized slices instead of the one-row dec.mbData / dec.fInfo, decode.go:463-468).
+// frames[i] holds image i's mbW*mbH macroblocks in raster order; filterType[i] is dec.filterType (decode.go:399).
+func ReconstructBatchCUDA(frames [][]MBData, finfo [][]FInfo, filterType []uint8, width, height int, y, u, v, nrgba []byte,
+	yPlane, uvPlane, nrgbaImage int) error {
+	n := len(frames)
+	if n == 0 {
+		return nil
+	}
+	dev, err := pool.GetDevice(0)
+	if err != nil {
+		return err
+	}
+	ctx := (*C.wgpu_ctx)(dev.Ctx())
+	nmb := len(frames[0])
+	recs := make([]C.wgpu_mb_data, n*nmb)
+	for i := range frames {
+		for k := range frames[i] {
+			m, f, r := &frames[i][k], &finfo[i][k], &recs[i*nmb+k]
+			for c := range m.Coeffs {
+				r.coeffs[c] = C.int16_t(m.Coeffs[c])
+			}
+			r.non_zero_y, r.non_zero_uv = C.uint32_t(m.NonZeroY), C.uint32_t(m.NonZeroUV)
+			for b := range m.IModes {
+				r.imodes[b] = C.uint8_t(m.IModes[b])
+			}
+			r.is_i4x4, r.skip, r.f_inner = b2u(m.IsI4x4), b2u(m.Skip), b2u(f.FInner)
+			r.uv_mode, r.segment = C.uint8_t(m.UVMode), C.uint8_t(m.Segment)
+			r.f_limit, r.f_ilevel, r.hev_thresh = C.uint8_t(f.FLimit), C.uint8_t(f.FILevel), C.uint8_t(f.HevThresh)
+		}
+	}
+	want := 0
+	var pn *C.uint8_t
+	if nrgba != nil {
+		want, pn = 1, (*C.uint8_t)(&nrgba[0])
+	}
+	if rc := C.wgpu_dec_reconstruct(ctx, C.int(n), C.int(width), C.int(height), &recs[0], (*C.uint8_t)(&filterType[0]), C.int(want)); rc != 0 {
+		return dev.Err("reconstruct")
+	}
+	if rc := C.wgpu_dec_fetch(ctx, (*C.uint8_t)(&y[0]), (*C.uint8_t)(&u[0]), (*C.uint8_t)(&v[0]), C.size_t(yPlane), C.size_t(uvPlane),
+		pn, C.size_t(nrgbaImage)); rc != 0 {
+		return dev.Err("fetch")
+	}
+	return nil
+}
+
+func b2u(b bool) C.uint8_t {
+	if b {
+		return 1
+	}
+	return 0
 }

@@ -64,6 +64,9 @@ func EncodeBatchCUDA(encs []*VP8Encoder, rgba []byte, stride int) error {
 	if err != nil {
 		return err
 	}
+	if len(encs) == 0 || len(rgba) == 0 {
+		return nil
+	}
 	ctx := (*C.wgpu_ctx)(dev.Ctx())
 	n, w, h := len(encs), encs[0].width, encs[0].height
 	nmb := encs[0].mbW * encs[0].mbH

@@ -38,3 +38,20 @@ def synth_batch(n, w, h, distinct=24, first_index=0):
     base = np.stack([synth_image(w, h, first_index + i) for i in range(d)])
     reps = (n + d - 1) // d
     return np.concatenate([base] * reps)[:n]
+
+
+def synth_formula(w, h, kind):
+    """RNG-free pictures (integer formulas only) that a Go program reproduces bit for bit (go/cmd/refdump): kind 0 = the
+    gradient of richTestImage (root encode_test.go:1496), 1 = noisyImage without its random term (race_test.go:78), 2 = both
+    in alternating 32x32 tiles (hard edges).  Opaque RGBA uint8 [h][w][4]."""
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.int64)
+    grad = (xx * 255 // w, yy * 255 // h, (xx + yy) * 255 // (w + h))
+    noisy = ((xx * 7 + yy * 13) % 256, (xx * 3 + yy * 5) % 256, (xx ^ yy) % 256)
+    if kind == 0:
+        r, g, b = grad
+    elif kind == 1:
+        r, g, b = noisy
+    else:
+        sel = (((xx >> 5) + (yy >> 5)) & 1) == 0
+        r, g, b = [np.where(sel, a, c) for a, c in zip(grad, noisy)]
+    return np.stack([r, g, b, np.full_like(r, 255)], axis=-1).astype(np.uint8)
