@@ -24,6 +24,12 @@ struct EncKernelParams {
   const uint16_t* lc_img;       // [n][LC_SIZE] per-image folded level costs (serial path with probability refreshes), or null
   const uint16_t* eob_img;      // [n][EOB_SIZE]
   int serial_gpw;               // encode_serial_tab_kernel: macroblock groups (images) per warp actually used, 1..32/G (0 = all)
+  // Serial RD path split by plane (refresh route): luma runs as left/top/top-right waves over the macroblocks [mb_begin, mb_end) of a
+  // refresh segment (serial_wave = 1: `wave` is x + 2y and tasks are (image, row) pairs), chroma as one raster-order chain per image
+  // (its DC error diffusion carries leftDerr from macroblock to macroblock, encode_frame.go:529-566).  ctx_uv receives the chroma half
+  // of the NZ context words; serial_merge_kernel joins the halves and sets the skip flag.
+  int serial_wave, mb_begin, mb_end;
+  uint32_t* ctx_uv;             // [n][nmb]
   uint32_t* ctx2;               // [n][nmb] Method < 3 / serial RD: trial 4x4 modes of the bottom row / right column (mode-cost context)
 #ifdef WG_PHASE_CLOCK
   unsigned long long* phase_clock;  // profiling build: CTA `clock_cta` timestamps its phase boundaries

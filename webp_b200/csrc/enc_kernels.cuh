@@ -164,11 +164,13 @@ __device__ __forceinline__ void stat_block_dev(const LevT* lev, int n_coeffs, in
 
 // Loads of data another macroblock produced (reconstruction borders, NZ context words, neighbour modes): they come through a
 // kernel boundary (one launch per wave / macroblock index), so plain loads see them.
-template <class Tp>
-__device__ __forceinline__ Tp ldn(const Tp* p) { return *p; }
+// CG: the raster-order chroma chain keeps running inside one launch, so what the previous macroblock wrote is read past L1.
+template <bool CG = false, class Tp>
+__device__ __forceinline__ Tp ldn(const Tp* p) { return CG ? __ldcg(p) : *p; }
 
 // The mode search of MPW = 32/G macroblocks by one warp: macroblock `task_base + lane/G` of wave `wave`.
-template <int G, bool FAST, bool SERIAL = false>
+// PART (serial RD path only): 0 = the whole macroblock, 1 = luma only, 2 = chroma only (see EncKernelParams::serial_wave).
+template <int G, bool FAST, bool SERIAL = false, int PART = 0>
 __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wave, long long task_base, MBShared* s_mb_warp,
                                                 const CostTabs& T_launch, const uint16_t* s_i4cost) {
   const int lane = threadIdx.x & 31;
@@ -176,21 +178,23 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   // rows on this wave: x = wave - 2y in [0, mb_w)
   const int y_lo = max(0, (wave - (P.mb_w - 1) + 1) >> 1), y_hi = min(P.mb_h - 1, wave >> 1);
   const int rows = y_hi - y_lo + 1;
-  const long long total = SERIAL ? (long long)P.n_images : (long long)rows * P.n_images;
+  const bool wave_map = !SERIAL || (PART == 1 && P.serial_wave != 0);  // tasks are (image, row of the wave) pairs, else images
+  const long long total = wave_map ? (long long)rows * P.n_images : (long long)P.n_images;
   const long long task = task_base + g;
   // SERIAL (the reference's serial encodeFrame order): `wave` is the raster macroblock index, one macroblock per image per
   // launch.  Rate-control passes (adjustQuantForTarget) re-encode only the images that have not converged: bit 8 of
   // seg[0].flags parks an image, bits 0-7 carry its own getMaxI4RDModes (its quality moves with the search).
   const bool in_range = task < total && (!SERIAL || P.serial_gpw == 0 || g < P.serial_gpw);
-  const int img_flags = ((SERIAL || FAST) && in_range) ? P.img[SERIAL ? (int)task : (int)(task / rows)].seg[0].flags : 0;
-  const bool active = task < total && !(img_flags & 0x100) && (!SERIAL || P.serial_gpw == 0 || g < P.serial_gpw);
+  const int img_flags = ((SERIAL || FAST) && in_range) ? P.img[wave_map ? (int)(task / rows) : (int)task].seg[0].flags : 0;
+  const bool active0 = task < total && !(img_flags & 0x100) && (!SERIAL || P.serial_gpw == 0 || g < P.serial_gpw);
   const int max_i4_modes = (img_flags & 0xff) ? (img_flags & 0xff) : P.max_i4_modes;
-  const int img = active ? (SERIAL ? (int)task : (int)(task / rows)) : 0;
+  const int img = active0 ? (wave_map ? (int)(task / rows) : (int)task) : 0;
   const CostTabs& T = T_launch;  // launch-wide tables, or this macroblock's image's own (encode_serial_tab_kernel)
-  const int my = active ? (SERIAL ? wave / P.mb_w : y_lo + (int)(task % rows)) : 0;
-  const int mx = active ? (SERIAL ? wave - my * P.mb_w : wave - 2 * my) : 0;
+  const int my = active0 ? (wave_map ? y_lo + (int)(task % rows) : wave / P.mb_w) : 0;
+  const int mx = active0 ? (wave_map ? wave - 2 * my : wave - my * P.mb_w) : 0;
   const int nmb = P.mb_w * P.mb_h;
   const int mb_idx = my * P.mb_w + mx;
+  const bool active = active0 && (!(SERIAL && PART == 1 && P.serial_wave != 0) || (mb_idx >= P.mb_begin && mb_idx < P.mb_end));
   MBShared& S = s_mb_warp[g];
 
   const int y_stride = P.mb_w * 16, uv_stride = P.mb_w * 8;
@@ -200,7 +204,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   uint8_t* rec_y = P.rec_y + (size_t)img * P.y_plane;
   uint8_t* rec_u = P.rec_u + (size_t)img * P.uv_plane;
   uint8_t* rec_v = P.rec_v + (size_t)img * P.uv_plane;
-  uint32_t* ctxw = P.ctx + (size_t)img * nmb;
+  uint32_t* ctxw = (PART == 2 ? P.ctx_uv : P.ctx) + (size_t)img * nmb;  // the chroma chain keeps its half of the NZ context apart
   uint8_t* hdr = P.out_hdr + ((size_t)img * nmb + mb_idx) * 48;
   int16_t* oc = P.out_coeffs + ((size_t)img * nmb + mb_idx) * 400;
   const int segment = active ? P.segment[(size_t)img * nmb + mb_idx] : 0;
@@ -236,23 +240,23 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       int v = 127;
       if (my > 0) {
         const int xx = (i < 16 || mx < P.mb_w - 1) ? x0 + i : x0 + 15;
-        v = ldn(&rec_y[(size_t)(y0 - 1) * y_stride + xx]);
+        v = ldn<PART == 2>(&rec_y[(size_t)(y0 - 1) * y_stride + xx]);
       }
       o[Y_OFF - BPS + i] = (uint8_t)v;
     }
-    for (int j = gl; j < 16; j += G) o[Y_OFF - 1 + j * BPS] = mx > 0 ? ldn(&rec_y[(size_t)(y0 + j) * y_stride + x0 - 1]) : 129;
+    for (int j = gl; j < 16; j += G) o[Y_OFF - 1 + j * BPS] = mx > 0 ? ldn<PART == 2>(&rec_y[(size_t)(y0 + j) * y_stride + x0 - 1]) : 129;
     for (int i = gl; i < 16; i += G) {
       const int pl = i >> 3, c = i & 7;
       const uint8_t* rp = pl ? rec_v : rec_u;
       const int off = pl ? V_OFF : U_OFF;
-      o[off - BPS + c] = my > 0 ? ldn(&rp[(size_t)(my * 8 - 1) * uv_stride + mx * 8 + c]) : 127;
-      o[off - 1 + c * BPS] = mx > 0 ? ldn(&rp[(size_t)(my * 8 + c) * uv_stride + mx * 8 - 1]) : 129;
+      o[off - BPS + c] = my > 0 ? ldn<PART == 2>(&rp[(size_t)(my * 8 - 1) * uv_stride + mx * 8 + c]) : 127;
+      o[off - 1 + c * BPS] = mx > 0 ? ldn<PART == 2>(&rp[(size_t)(my * 8 + c) * uv_stride + mx * 8 - 1]) : 129;
     }
     if (gl == 0) {
       const bool both = mx > 0 && my > 0;
-      o[Y_OFF - BPS - 1] = both ? ldn(&rec_y[(size_t)(y0 - 1) * y_stride + x0 - 1]) : (my > 0 ? 129 : 127);
-      o[U_OFF - BPS - 1] = both ? ldn(&rec_u[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1]) : (my > 0 ? 129 : 127);
-      o[V_OFF - BPS - 1] = both ? ldn(&rec_v[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1]) : (my > 0 ? 129 : 127);
+      o[Y_OFF - BPS - 1] = both ? ldn<PART == 2>(&rec_y[(size_t)(y0 - 1) * y_stride + x0 - 1]) : (my > 0 ? 129 : 127);
+      o[U_OFF - BPS - 1] = both ? ldn<PART == 2>(&rec_u[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1]) : (my > 0 ? 129 : 127);
+      o[V_OFF - BPS - 1] = both ? ldn<PART == 2>(&rec_v[(size_t)(my * 8 - 1) * uv_stride + mx * 8 - 1]) : (my > 0 ? 129 : 127);
     }
   }
   __syncwarp();
@@ -268,30 +272,34 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   int top_modes[4] = {0, 0, 0, 0}, left_modes[4] = {0, 0, 0, 0};
   if (active) {
     if (my > 0) {
-      const uint32_t cw = ldn(&ctxw[mb_idx - P.mb_w]);
+      const uint32_t cw = ldn<PART == 2>(&ctxw[mb_idx - P.mb_w]);
       top_nz = cw & 0xff;
       top_nz_dc = (cw >> 16) & 1;
       const uint8_t* th = hdr - (size_t)P.mb_w * 48;
       if (FAST || SERIAL) {
-        const uint32_t tm = ldn(&P.ctx2[(size_t)img * nmb + mb_idx - P.mb_w]);
+        const uint32_t tm = ldn<PART == 2>(&P.ctx2[(size_t)img * nmb + mb_idx - P.mb_w]);
         for (int i = 0; i < 4; ++i) top_modes[i] = (tm >> (4 * i)) & 15;
-      } else if (ldn(&th[0]) == 1) { top_modes[0] = ldn(&th[8 + 12]); top_modes[1] = ldn(&th[8 + 13]); top_modes[2] = ldn(&th[8 + 14]); top_modes[3] = ldn(&th[8 + 15]); }
+      } else if (ldn<PART == 2>(&th[0]) == 1) { top_modes[0] = ldn<PART == 2>(&th[8 + 12]); top_modes[1] = ldn<PART == 2>(&th[8 + 13]); top_modes[2] = ldn<PART == 2>(&th[8 + 14]); top_modes[3] = ldn<PART == 2>(&th[8 + 15]); }
     }
     if (mx > 0) {
-      const uint32_t cw = ldn(&ctxw[mb_idx - 1]);
+      const uint32_t cw = ldn<PART == 2>(&ctxw[mb_idx - 1]);
       left_nz = (cw >> 8) & 0xff;
       left_nz_dc = (cw >> 17) & 1;
       const uint8_t* lh = hdr - 48;
       if (FAST || SERIAL) {
-        const uint32_t lm = ldn(&P.ctx2[(size_t)img * nmb + mb_idx - 1]);
+        const uint32_t lm = ldn<PART == 2>(&P.ctx2[(size_t)img * nmb + mb_idx - 1]);
         for (int i = 0; i < 4; ++i) left_modes[i] = (lm >> (16 + 4 * i)) & 15;
-      } else if (ldn(&lh[0]) == 1) { left_modes[0] = ldn(&lh[8 + 3]); left_modes[1] = ldn(&lh[8 + 7]); left_modes[2] = ldn(&lh[8 + 11]); left_modes[3] = ldn(&lh[8 + 15]); }
+      } else if (ldn<PART == 2>(&lh[0]) == 1) { left_modes[0] = ldn<PART == 2>(&lh[8 + 3]); left_modes[1] = ldn<PART == 2>(&lh[8 + 7]); left_modes[2] = ldn<PART == 2>(&lh[8 + 11]); left_modes[3] = ldn<PART == 2>(&lh[8 + 15]); }
     }
   }
   __syncwarp();
 
   int best16 = 0;
   unsigned long long score16 = 0;
+  unsigned long long score4 = ~0ull;
+  uint32_t i4_nzmask = 0;
+  uint32_t trial_modes = 0;  // FAST: bottom-row (bits 0-15) and right-column (16-31) trial modes for the neighbours
+  if constexpr (PART != 2) {
   if constexpr (!FAST) {  // ---- 3a. I16 RD search (encode_parallel.go:624-735)
     int rate16 = 0, disto16 = 0;
     unsigned long long best_score = ~0ull;
@@ -417,9 +425,6 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
     }
   }
 
-  unsigned long long score4 = ~0ull;
-  uint32_t i4_nzmask = 0;
-  uint32_t trial_modes = 0;  // FAST: bottom-row (bits 0-15) and right-column (16-31) trial modes for the neighbours
   if constexpr (!FAST) {  // ---- 3b. I4 RD search (encode_parallel.go:738-1027)
     if (active) for (int i = gl; i < YUV_SIZE / 4; i += G) reinterpret_cast<uint32_t*>(S.out2)[i] = reinterpret_cast<const uint32_t*>(S.out)[i];
     __syncwarp();
@@ -672,15 +677,20 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
     S.misc[0] = use_i4;
     S.misc[3] = (int)modes_lo; S.misc[2] = (int)modes_hi;  // for the residual pass below
   }
+  }
   __syncwarp();
-  const bool use_i4 = S.misc[0] != 0;
+  const bool use_i4 = PART != 2 && S.misc[0] != 0;
 
   int best_uv = 0;
-  if constexpr (!FAST) {  // ---- 3c. UV RD search (encode_parallel.go:1030-1116)
+  if constexpr (PART == 1) {
+  } else if constexpr (!FAST) {  // ---- 3c. UV RD search (encode_parallel.go:1030-1116)
     unsigned long long best_score = ~0ull;
-    if (active)
-      for (int i = gl; i < (YUV_SIZE - U_OFF) / 4; i += G)
-        reinterpret_cast<uint32_t*>(S.out2 + U_OFF)[i] = reinterpret_cast<const uint32_t*>(S.out + U_OFF)[i];
+    if (active) {
+      // the chroma-only pass has no luma search before it that left the whole work buffer (borders included) in out2
+      const int from = PART == 2 ? 0 : U_OFF;
+      for (int i = gl; i < (YUV_SIZE - from) / 4; i += G)
+        reinterpret_cast<uint32_t*>(S.out2 + from)[i] = reinterpret_cast<const uint32_t*>(S.out + from)[i];
+    }
     __syncwarp();
     for (int mode = 0; mode < 4; ++mode) {
       const bool allowed = active && !((mode == 2 && my == 0) || (mode == 3 && mx == 0) || (mode == 1 && (mx == 0 || my == 0)));
@@ -767,6 +777,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   // ---- 4. final residuals + 6. reconstruction (encode_parallel.go:1164-1407)
   uint32_t nzy_flags = 0;  // 16 bits: Y block has nz>0 (i16: AC), bit 24: DC block
   int nz_dc = 0;
+  if constexpr (PART != 2) {
   if (active && !use_i4) {
     // I16: forward transform all blocks against the cached prediction in S.out
     for (int b = gl; b < 16; b += G) {
@@ -873,6 +884,8 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
     nzy_flags = i4_nzmask;
     for (int i = gl; i < 16; i += G) oc[384 + i] = 0;  // no WHT block on I4 macroblocks
   }
+  }
+  if constexpr (PART != 1) {
   // UV: predict with the winner, transform, quantise, reconstruct
   if (active) {
     const int am = check_mode(mx, my, best_uv);
@@ -950,11 +963,12 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   }
   __syncwarp();
 
+  }
   // ---- 6b. token statistics for the final probability optimisation (collectMBStats, encode_parallel.go:1606-1707;
   // collectCoeffStats, encode_proba.go:10-113).  Contexts are the ones this kernel already holds: a skipped MB
   // contributes nothing and leaves all-zero flags behind, exactly like the reset in recordAllTokens.
   uint32_t nzuv_all = 0;
-  if (active) for (int b = 0; b < 8; ++b) nzuv_all |= (uint32_t)(S.nz[16 + b] > 0) << b;
+  if (PART != 1 && active) for (int b = 0; b < 8; ++b) nzuv_all |= (uint32_t)(S.nz[16 + b] > 0) << b;
   const bool mb_skip = active && (nzy_flags == 0) && (use_i4 || nz_dc == 0) && nzuv_all == 0;
   if (active && !mb_skip && P.stats != nullptr) {
     unsigned int* st = P.stats + (size_t)img * STATS_SIZE;
@@ -980,30 +994,34 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   // ---- 7. export: reconstruction planes, header, NZ context (encode_parallel.go:341-428,1410-1496)
   if (active) {
     const int x0 = mx * 16, y0 = my * 16;
-    for (int i = gl; i < 64; i += G) {
-      const int r = i >> 2, c4 = (i & 3) * 4;
-      *reinterpret_cast<uint32_t*>(rec_y + (size_t)(y0 + r) * y_stride + x0 + c4) =
-          *reinterpret_cast<const uint32_t*>(S.out + Y_OFF + r * BPS + c4);
-    }
-    for (int i = gl; i < 32; i += G) {
-      const int pl = i >> 4, r = (i >> 1) & 7, c4 = (i & 1) * 4;
-      uint8_t* rp = pl ? rec_v : rec_u;
-      *reinterpret_cast<uint32_t*>(rp + (size_t)(my * 8 + r) * uv_stride + mx * 8 + c4) =
-          *reinterpret_cast<const uint32_t*>(S.out + (pl ? V_OFF : U_OFF) + r * BPS + c4);
-    }
+    if (PART != 2)
+      for (int i = gl; i < 64; i += G) {
+        const int r = i >> 2, c4 = (i & 3) * 4;
+        *reinterpret_cast<uint32_t*>(rec_y + (size_t)(y0 + r) * y_stride + x0 + c4) =
+            *reinterpret_cast<const uint32_t*>(S.out + Y_OFF + r * BPS + c4);
+      }
+    if (PART != 1)
+      for (int i = gl; i < 32; i += G) {
+        const int pl = i >> 4, r = (i >> 1) & 7, c4 = (i & 1) * 4;
+        uint8_t* rp = pl ? rec_v : rec_u;
+        *reinterpret_cast<uint32_t*>(rp + (size_t)(my * 8 + r) * uv_stride + mx * 8 + c4) =
+            *reinterpret_cast<const uint32_t*>(S.out + (pl ? V_OFF : U_OFF) + r * BPS + c4);
+      }
     if (gl == 0) {
       const uint32_t nzuv = nzuv_all;
       const bool i16 = !use_i4;
       const int dcflag = nz_dc > 0;
       const bool skip = mb_skip;
-      hdr[0] = use_i4 ? 1 : 0;
-      hdr[1] = (uint8_t)(i16 ? best16 : 0);
-      hdr[2] = (uint8_t)best_uv;
-      hdr[3] = (uint8_t)segment;
-      hdr[4] = skip ? 1 : 0;
-      hdr[5] = (uint8_t)(i16 ? nz_dc : 0);
-      hdr[6] = 0; hdr[7] = 0;
-      // NZ context words (bottom row / right column flags)
+      if (PART != 2) {
+        hdr[0] = use_i4 ? 1 : 0;
+        hdr[1] = (uint8_t)(i16 ? best16 : 0);
+        hdr[3] = (uint8_t)segment;
+        hdr[5] = (uint8_t)(i16 ? nz_dc : 0);
+        hdr[6] = 0; hdr[7] = 0;
+      }
+      if (PART != 1) hdr[2] = (uint8_t)best_uv;
+      if (PART == 0) hdr[4] = skip ? 1 : 0;  // split by plane: serial_merge_kernel sets it once both halves are there
+      // NZ context words (bottom row / right column flags); a plane-split pass writes its half into its own array
       const uint32_t out_t = ((nzy_flags >> 12) & 0xf) | (((nzuv >> 2) & 3) << 4) | (((nzuv >> 6) & 3) << 6);
       const uint32_t yl = ((nzy_flags >> 3) & 1) | (((nzy_flags >> 7) & 1) << 1) | (((nzy_flags >> 11) & 1) << 2) | (((nzy_flags >> 15) & 1) << 3);
       const uint32_t ul = ((nzuv >> 1) & 1) | (((nzuv >> 3) & 1) << 1);
@@ -1011,9 +1029,29 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
       const uint32_t out_l = yl | (ul << 4) | (vl << 6);
       const int tdc = i16 ? dcflag : top_nz_dc, ldc = i16 ? dcflag : left_nz_dc;
       ctxw[mb_idx] = pack_ctx(out_t, out_l, tdc, ldc);
-      if (FAST || SERIAL) P.ctx2[(size_t)img * nmb + mb_idx] = trial_modes;
+      if ((FAST || SERIAL) && PART != 2) P.ctx2[(size_t)img * nmb + mb_idx] = trial_modes;
     }
   }
+}
+
+// Joins the halves a plane-split serial pass left behind for the macroblocks [mb_begin, mb_end) of every image that is not
+// parked: NZ context word = luma bits of ctx | chroma bits of ctx_uv, skip flag from the nz counts of both planes.
+struct SerialMergeParams {
+  uint8_t* hdr; uint32_t* ctx; const uint32_t* ctx_uv; const ImageParams* img;
+  int n_images, nmb, mb_begin, mb_end;
+};
+__global__ void __launch_bounds__(256) serial_merge_kernel(const SerialMergeParams P) {
+  const int per = P.mb_end - P.mb_begin;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)per * P.n_images) return;
+  const int img = (int)(t / per), mb = P.mb_begin + (int)(t % per);
+  if (P.img[img].seg[0].flags & 0x100) return;
+  uint8_t* h = P.hdr + ((size_t)img * P.nmb + mb) * 48;
+  bool any = false;
+  for (int b = 0; b < 24; ++b) any |= h[24 + b] > 0;
+  h[4] = (!any && (h[0] == 1 || h[5] == 0)) ? 1 : 0;
+  const size_t k = (size_t)img * P.nmb + mb;
+  P.ctx[k] = (P.ctx[k] & 0x00030f0fu) | (P.ctx_uv[k] & 0x0000f0f0u);
 }
 
 #define WG_STAGE_TABLES(NT)                                                                                                        \
@@ -1219,6 +1257,64 @@ __global__ void __launch_bounds__(32, 2) encode_serial_tab_kernel(const EncKerne
   Tg.lc = s_tabs + (size_t)g * (LC_SIZE + EOB_SIZE);
   Tg.eob = Tg.lc + LC_SIZE;
   encode_mb_group<G, false, true>(P, mb_index, task_base, s_mb, Tg, s_i4cost);
+}
+
+// The same serial RD path split by plane, for frames long enough to refresh their probabilities (config: 3840x2160, rate
+// control): inside a refresh segment the luma decisions of a macroblock depend on its left / top / top-right neighbours only,
+// so luma runs as x + 2y waves over the segment (tasks = (image, row) pairs of the wave that fall inside [mb_begin, mb_end));
+// what forces raster order is the chroma DC error diffusion (leftDerr carries from the end of a row into the next one,
+// encode_frame.go:529-566), and chroma depends on nothing in luma -- so chroma runs beside the waves as ONE launch per
+// segment in which a group of lanes walks its image's macroblocks in raster order.  A segment thus costs ~mb_w + 2 * rows
+// dependent luma steps instead of mb_w * rows whole-macroblock steps.
+template <int G>
+__global__ void __launch_bounds__(32, 2) encode_serial_luma_wave_kernel(const EncKernelParams P, int wave) {
+  const int gpw = P.serial_gpw;
+  WG_STAGE_TABLES(32);
+  uint16_t* s_tabs = reinterpret_cast<uint16_t*>(s_mb + 32 / G);
+  const int y_lo = max(0, (wave - (P.mb_w - 1) + 1) >> 1), y_hi = min(P.mb_h - 1, wave >> 1);
+  const int rows = max(y_hi - y_lo + 1, 1);
+  const long long task_base = (long long)blockIdx.x * gpw, total = (long long)rows * P.n_images;
+  for (int g = 0; g < gpw; ++g) {  // each group's image has its own probability state, hence its own folded cost tables
+    if (task_base + g >= total) break;
+    const long long img = (task_base + g) / rows;
+    uint4* dst = reinterpret_cast<uint4*>(s_tabs + (size_t)g * (LC_SIZE + EOB_SIZE));
+    const uint4* a = reinterpret_cast<const uint4*>(P.lc_img + (size_t)img * LC_SIZE);
+    const uint4* b = reinterpret_cast<const uint4*>(P.eob_img + (size_t)img * EOB_SIZE);
+    for (int i = threadIdx.x; i < LC_SIZE / 8; i += 32) dst[i] = a[i];
+    for (int i = threadIdx.x; i < EOB_SIZE / 8; i += 32) dst[LC_SIZE / 8 + i] = b[i];
+  }
+  __syncwarp();
+  CostTabs Tg = T;
+  const int g = min((int)(threadIdx.x & 31) / G, gpw - 1);
+  Tg.lc = s_tabs + (size_t)g * (LC_SIZE + EOB_SIZE);
+  Tg.eob = Tg.lc + LC_SIZE;
+  encode_mb_group<G, false, true, 1>(P, wave, task_base, s_mb, Tg, s_i4cost);
+}
+template <int G>
+__global__ void __launch_bounds__(32, 2) encode_serial_chroma_chain_kernel(const EncKernelParams P) {
+  const int gpw = P.serial_gpw;
+  WG_STAGE_TABLES(32);
+  uint16_t* s_tabs = reinterpret_cast<uint16_t*>(s_mb + 32 / G);
+  const long long task_base = (long long)blockIdx.x * gpw;
+  for (int g = 0; g < gpw; ++g) {
+    const long long img = task_base + g;
+    if (img >= P.n_images) break;
+    uint4* dst = reinterpret_cast<uint4*>(s_tabs + (size_t)g * (LC_SIZE + EOB_SIZE));
+    const uint4* a = reinterpret_cast<const uint4*>(P.lc_img + (size_t)img * LC_SIZE);
+    const uint4* b = reinterpret_cast<const uint4*>(P.eob_img + (size_t)img * EOB_SIZE);
+    for (int i = threadIdx.x; i < LC_SIZE / 8; i += 32) dst[i] = a[i];
+    for (int i = threadIdx.x; i < EOB_SIZE / 8; i += 32) dst[LC_SIZE / 8 + i] = b[i];
+  }
+  __syncwarp();
+  CostTabs Tg = T;
+  const int g = min((int)(threadIdx.x & 31) / G, gpw - 1);
+  Tg.lc = s_tabs + (size_t)g * (LC_SIZE + EOB_SIZE);
+  Tg.eob = Tg.lc + LC_SIZE;
+#pragma unroll 1
+  for (int mb = P.mb_begin; mb < P.mb_end; ++mb) {
+    encode_mb_group<G, false, true, 2>(P, mb, task_base, s_mb, Tg, s_i4cost);
+    __syncwarp();  // the next macroblock reads (past L1) the chroma borders, context half and diffusion state written here
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -73,8 +73,8 @@ void parallel_for(int n, int threads, F f) {
 struct wgpu_ctx {
   int dev = 0;
   int sm_count = 148;  // of this context's device
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_hdr = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: the chroma chains of the plane-split serial RD path
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_hdr = nullptr, ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   uint64_t launches = 0;
   uint64_t xfer_h2d = 0, xfer_d2h = 0;  // bytes copied by this context since the last wgpu_transfer_bytes(reset)
@@ -83,7 +83,7 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, derr, dither_y, dither_uv, hdr, coeffs, stats, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, ctxw_uv, derr, dither_y, dither_uv, hdr, coeffs, stats, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
   DevBuf sharp_best_y, sharp_target_y, sharp_best_uv, sharp_target_uv, t_sharp;  // SharpYUV import working planes + gamma tables
   PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
@@ -191,6 +191,9 @@ int wgpu_ctx_create(int device_ordinal, wgpu_ctx** out) {
   if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&ctx->ev_hdr, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   // tables
   static uint16_t i4costs[1000];
   wgh::compute_i4_costs(i4costs);
@@ -228,7 +231,7 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->derr, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
+  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->ctxw_uv, &ctx->derr, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_streams, &ctx->d_hdrs, &ctx->d_perr, &ctx->t_bmodes, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
@@ -241,6 +244,9 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_hdr) cudaEventDestroy(ctx->ev_hdr);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->d_graph) cudaGraphExecDestroy(ctx->d_graph);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -387,6 +393,56 @@ int launch_enc_serial_tab(wgpu_ctx* ctx, wg::EncKernelParams& P, int mb_begin, i
     wg::encode_serial_tab_kernel<G><<<grid, 32, smem, ctx->stream>>>(P, i);
     ctx->launches++;
   }
+  return WGPU_OK;
+}
+// Serial RD path with refreshes, split by plane (enc_kernels.cuh): luma waves over the macroblocks [mb_begin, mb_end) on the
+// context's stream, the chroma chains of the same segment on its second stream, then the merge of the two halves.
+int launch_enc_serial_split(wgpu_ctx* ctx, wg::EncKernelParams& P, int mb_begin, int mb_end) {
+  constexpr int G = 8;
+  const int mbw = P.mb_w, mbh = P.mb_h, nmb = mbw * mbh, n = P.n_images;
+  const size_t max_smem = sizeof(wg::MBShared) * 4 + (size_t)4 * (wg::LC_SIZE + wg::EOB_SIZE) * 2;
+  cudaError_t e = cudaFuncSetAttribute(wg::encode_serial_luma_wave_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(wg::encode_serial_chroma_chain_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+  if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
+  P.mb_begin = mb_begin; P.mb_end = mb_end;
+  // chroma: everything queued on the main stream so far (the cost tables of this segment) comes first
+  CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+  {
+    wg::EncKernelParams C = P;
+    C.serial_wave = 0;
+    C.serial_gpw = n <= 8 * ctx->sm_count ? 1 : (n <= 24 * ctx->sm_count ? 2 : 4);
+    const size_t smem = sizeof(wg::MBShared) * (32 / G) + (size_t)C.serial_gpw * (wg::LC_SIZE + wg::EOB_SIZE) * 2;
+    wg::encode_serial_chroma_chain_kernel<G><<<(unsigned)((n + C.serial_gpw - 1) / C.serial_gpw), 32, smem, ctx->stream2>>>(C);
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev_join, ctx->stream2));
+  }
+  // luma: the waves that hold a macroblock of the segment
+  const int y_first = mb_begin / mbw, y_last = (mb_end - 1) / mbw;
+  for (int w = 0; w < mbw + 2 * (mbh - 1); ++w) {
+    const int rows = wave_rows(w, mbw, mbh);
+    if (rows <= 0) continue;
+    const int y_lo = std::max(0, (w - (mbw - 1) + 1) >> 1), y_hi = std::min(mbh - 1, w >> 1);
+    bool any = false;
+    for (int y = std::max(y_lo, y_first); y <= std::min(y_hi, y_last) && !any; ++y) {
+      const int idx = y * mbw + (w - 2 * y);
+      any = idx >= mb_begin && idx < mb_end;
+    }
+    if (!any) continue;
+    wg::EncKernelParams L = P;
+    L.serial_wave = 1;
+    const long long tasks = (long long)rows * n;
+    L.serial_gpw = tasks <= 8LL * ctx->sm_count ? 1 : (tasks <= 24LL * ctx->sm_count ? 2 : 4);
+    const size_t smem = sizeof(wg::MBShared) * (32 / G) + (size_t)L.serial_gpw * (wg::LC_SIZE + wg::EOB_SIZE) * 2;
+    wg::encode_serial_luma_wave_kernel<G><<<(unsigned)((tasks + L.serial_gpw - 1) / L.serial_gpw), 32, smem, ctx->stream>>>(L, w);
+    ctx->launches++;
+  }
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  wg::SerialMergeParams M;
+  M.hdr = P.out_hdr; M.ctx = P.ctx; M.ctx_uv = P.ctx_uv; M.img = P.img; M.n_images = n; M.nmb = nmb; M.mb_begin = mb_begin; M.mb_end = mb_end;
+  wg::serial_merge_kernel<<<(unsigned)(((long long)(mb_end - mb_begin) * n + 255) / 256), 256, 0, ctx->stream>>>(M);
+  ctx->launches++;
+  CK(cudaGetLastError());
   return WGPU_OK;
 }
 // Row-parallel RD path: the phase-synchronous kernel (enc_phased.cuh).  M macroblocks per CTA, 16 threads per macroblock;
@@ -577,6 +633,7 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.max_i4_modes = ctx->e_opt.quality < 50 ? 2 : 3;  // getMaxI4RDModes (encode_parallel.go:931)
   P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
   P.top_derr = nullptr; P.left_derr = nullptr; P.lc_img = nullptr; P.eob_img = nullptr; P.serial_gpw = 0;
+  P.serial_wave = 0; P.mb_begin = 0; P.mb_end = nmb; P.ctx_uv = nullptr;
   int rc;
   const bool do_search = ctx->e_opt.target_size > 0 || ctx->e_opt.target_psnr > 0.f;
   if (ctx->e_opt.method >= 3 && (mbh < 4 || do_search)) {  // useParallel == false (encode.go:1356)
@@ -603,6 +660,8 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
       CK(cudaMemsetAsync(ctx->hdr.p, 0, (size_t)n * nmb * 48, ctx->stream));
     }
     P.stats = nullptr;  // statistics are taken by collect_all_stats_kernel, over the whole array
+    RESERVE(ctx->ctxw_uv, (size_t)n * nmb * 4);
+    P.ctx_uv = ctx->ctxw_uv.as<uint32_t>();
     RESERVE(ctx->lc_img, (size_t)n * wg::LC_SIZE * 2); RESERVE(ctx->eob_img, (size_t)n * wg::EOB_SIZE * 2);
     RESERVE(ctx->h_lc_img, (size_t)n * (wg::LC_SIZE + wg::EOB_SIZE) * 2);
     RESERVE(ctx->h_stats, (size_t)n * wg::STATS_SIZE * 4);
@@ -637,7 +696,9 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
     int start = 0;
     for (int k = 1;; ++k) {
       const int end = std::min(k * max_count + (k - 1), nmb);
-      if ((rc = launch_enc_serial_tab(ctx, P, start, end))) return rc;
+      // WGPU_SERIAL_SPLIT=0 keeps the whole-macroblock raster chain (one launch per macroblock index), for comparison
+      static const bool split = getenv_int("WGPU_SERIAL_SPLIT", 1) != 0;
+      if ((rc = split ? launch_enc_serial_split(ctx, P, start, end) : launch_enc_serial_tab(ctx, P, start, end))) return rc;
       if (end >= nmb) break;
       if ((rc = all_stats())) return rc;
       CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->stats.p, (size_t)n * wg::STATS_SIZE * 4, cudaMemcpyDeviceToHost, ctx->stream));
