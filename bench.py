@@ -39,7 +39,7 @@ METRIC = "lossy encode & decode Mpix/s (1536x1024 q75 m4), bit-exact"
 CONFIGS = {
     2: dict(w=1536, h=1024, quality=75, method=4, target_psnr=0.0, batch=256, distinct=24, steps=12, e2e_workers=5, value_contexts=2, decode=True,
             metric=METRIC, workload="synthetic 1536x1024 RGBA lossy encode q75 method 4, batch of %d images per GPU (BASELINE configs[1])"),
-    4: dict(w=3840, h=2160, quality=75, method=6, target_psnr=42.0, batch=16, distinct=8, steps=3, e2e_workers=2, value_contexts=1, decode=False,
+    4: dict(w=3840, h=2160, quality=75, method=6, target_psnr=42.0, batch=48, distinct=8, steps=3, e2e_workers=2, value_contexts=1, decode=False,
             metric="lossy encode Mpix/s (3840x2160 m6 TargetPSNR 42), bit-exact",
             workload="synthetic 3840x2160 RGBA lossy encode method 6, TargetPSNR 42 (three serial RD passes), batch of %d images per GPU (BASELINE configs[3])"),
     5: dict(w=256, h=256, quality=80, method=2, target_psnr=0.0, batch=2500, distinct=48, steps=8, e2e_workers=3, value_contexts=2, decode=False,
@@ -63,6 +63,62 @@ def committed_traffic():
         return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"]), t.get("launch")
     except Exception:
         return None, None
+
+
+def _parse_cpulist(text):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_host_cores(local, local_world):
+    """Multi-rank runs: pin this rank (and every pinned buffer it first-touches afterwards) to its share of the host cores on the
+    NUMA node its GPU hangs off, so that the D2H of one rank's NRGBA does not cross the socket interconnect and the ranks do not
+    migrate over each other.  Falls back to an even split of the allowed cores when sysfs shows no NUMA placement."""
+    info = {"mode": "none"}
+    if local_world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return info
+    allowed = sorted(os.sched_getaffinity(0))
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus  # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        info["pci"] = bus
+        info["numa_node"] = node
+    except Exception:
+        node = -1
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+    except Exception:
+        nodes = []
+    info["numa_nodes"] = len(nodes)
+    mine = None
+    if node >= 0 and len(nodes) > 1:
+        try:
+            node_cpus = [c for c in _parse_cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read()) if c in allowed]
+            # the ranks whose GPUs share this node split its cores; without knowing the others' placement assume an even spread
+            per_node = max(1, local_world // len(nodes))
+            slot = local % per_node
+            share = max(1, len(node_cpus) // per_node)
+            mine = node_cpus[slot * share:(slot + 1) * share] or node_cpus
+            info["mode"] = "numa-local"
+        except Exception:
+            mine = None
+    if mine is None:
+        share = max(1, len(allowed) // local_world)
+        mine = allowed[local * share:(local + 1) * share] or allowed
+        info["mode"] = "even-split"
+    try:
+        os.sched_setaffinity(0, mine)
+        info["cpus"] = len(mine)
+    except Exception as e:
+        info = {"mode": "none", "error": str(e)}
+    return info
 
 
 class ClockSampler:
@@ -164,6 +220,7 @@ def main():
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the benchmarked outputs (profiling runs only)")
+    ap.add_argument("--no-affinity", action="store_true", help="multi-rank runs: do not pin the rank to the host cores next to its GPU")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     args.steps = args.steps or cfg["steps"]
@@ -200,6 +257,7 @@ def main():
     W, H = cfg["w"], cfg["h"]
     L = native.lib()
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    affinity = {"mode": "none"} if args.no_affinity else bind_host_cores(local, local_world)  # before any pinned allocation
     host_threads = args.host_threads or max(1, (os.cpu_count() or 1) // max(1, local_world))
     ctx = native.Context(local, host_threads=host_threads)
     n, K = args.batch, args.steps
@@ -448,6 +506,40 @@ def main():
         barrier()
         ds = max_over_ranks(time.perf_counter() - t0)
         dxfer = [wk.ctx.transfer_bytes() for wk in dworkers]
+        # the same leg at the lossy.DecodeFrame boundary (internal/lossy/decode.go:107-131: Y, U, V planes out, 1.5 B/px instead
+        # of 4): what the e2e figure becomes when the D2H volume, the multi-GPU limiter (tools/d2h_scale_probe.py), shrinks
+        mbw_, mbh_ = (W + 15) >> 4, (H + 15) >> 4
+        ysz, uvsz = mbw_ * 16 * mbh_ * 16, mbw_ * 8 * mbh_ * 8
+
+        def decode_planes_e2e(wk, buf):
+            h = wk.ctx.handle
+            wk.ctx.check(L.wgpu_dec_parse(h, ptrs, lens, n, None, None))
+            wk.ctx.check(L.wgpu_dec_device(h, 0))
+            wk.ctx.check(L.wgpu_sync(h))
+            with gpu_stage:
+                wk.ctx.check(L.wgpu_dec_fetch(h, buf, buf + n * ysz, buf + n * (ysz + uvsz), ysz, uvsz, None, 0))
+        pcounter = iter(range(K))
+        plock = threading.Lock()
+
+        def prun(wk, buf):
+            while True:
+                with plock:
+                    if next(pcounter, None) is None:
+                        return
+                decode_planes_e2e(wk, buf)
+        barrier()
+        t0 = time.perf_counter()
+        ths = [threading.Thread(target=prun, args=(wk, buf)) for wk, buf in zip(dworkers, dec_bufs)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        barrier()
+        dps = max_over_ranks(time.perf_counter() - t0)
+        # leave every context with a full NRGBA decode behind it again (the parity check below reads the buffers)
+        for wk, buf in zip(dworkers, dec_bufs):
+            if wk.batches or wk is dworkers[0]:
+                wk.ctx.check(L.wgpu_decode_batch(wk.ctx.handle, ptrs, lens, n, None, None, None, 0, 0, buf, W * H * 4))
         t1 = time.perf_counter()
         ctx.check(L.wgpu_decode_batch(ctx.handle, ptrs, lens, n, None, None, None, 0, 0, h_rgba, W * H * 4))
         dec_one_shot_s = time.perf_counter() - t1
@@ -471,6 +563,9 @@ def main():
                             "e2e": {"value": px_step * K * world / ds / 1e6, "unit": "Mpix/s", "ms_per_step": ds / K * 1e3,
                                     "h2d_bytes_per_step": sum(x[0] for x in dxfer) // K, "d2h_bytes_per_step": sum(x[1] for x in dxfer) // K,
                                     "macroblock_parser": "gpu" if device_parser else "host", "workers_per_gpu": len(dworkers),
+                                    "planes_out": {"value": px_step * K * world / dps / 1e6, "unit": "Mpix/s", "ms_per_step": dps / K * 1e3,
+                                                   "d2h_bytes_per_step": n * (ysz + 2 * uvsz),
+                                                   "api": "same stages, Y/U/V planes out (the lossy.DecodeFrame boundary) instead of NRGBA"},
                                     "one_shot": {"value": px_step / dec_one_shot_s / 1e6, "unit": "Mpix/s", "ms": dec_one_shot_s * 1e3,
                                                  "api": "one wgpu_decode_batch call on one context, nothing overlapped"}},
                             "config": {"workload": "decode of the %d streams above -> recon + loop filter + fancy upsampling to NRGBA (BASELINE configs[2])" % n},
@@ -478,6 +573,8 @@ def main():
                                          "achieved": dec_gbs, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": dec_gbs / peak}}
         L.wgpu_host_free(ctx.handle, h_rgba)
     result["clocks"] = clock_rec
+    if world > 1:
+        result["host_affinity"] = affinity
     # ---- roofline of the dominant kernel (the mode search): integer issue, SURVEY.md 8(d).  Operations are COUNTED by the oracle
     # built with its per-stage counters (oracle/vp8_common.h OpStage) over the distinct images of this rank's batch, weighted by how
     # often each one occurs in it; peak = SMs x 128 lanes x the SM clock observed during the timed region.
@@ -503,7 +600,7 @@ def main():
     t_two = dev_ms / K * 1e-3                      # per step with `batches_in_flight` sequences side by side (the value leg; import + analysis inside)
     t_one = stage_ms.get("mode_search", 0.0) * 1e-3  # one batch's wave sequence alone
     roofline = {"bound": "int_issue", "kernel": "encode_phased_kernel (one launch per wave, %d per step)" % ((W + 15) // 16 + 2 * ((H + 15) // 16 - 1))
-                if cfg["method"] >= 3 and not do_search else ("encode_serial_tab_kernel (serial RD passes)" if do_search else "encode_fast_wave_kernel"),
+                if cfg["method"] >= 3 and not do_search else ("encode_serial_luma_wave_kernel + encode_serial_chroma_chain_kernel (serial RD passes, split by plane)" if do_search else "encode_fast_wave_kernel"),
                 "unit": "Tiop/s", "peak": peak_ops / 1e12, "peak_kind": "%d SMs x 128 lanes x %.0f MHz observed" % (sm_count, sm_mhz),
                 "ops_per_macroblock": ops_step / (n * nmb) if ops_step else None,
                 "ops_by_stage_per_macroblock": {k: round(v / (n * nmb), 1) for k, v in ops_by_stage.items()} if ops_by_stage else None,

@@ -155,7 +155,7 @@ struct DecParseParams {
   const uint8_t* streams;    // packed VP8 frames
   const DecHeader* hdr;      // [n]
   const uint8_t* bmodes;     // kBModesProba [10][10][9]
-  int16_t* coeffs;           // [n][nmb][384], zeroed before the launch
+  int16_t* coeffs;           // [n][nmb][384]; written for macroblocks with a non-zero transform code only (nothing else is read)
   MBMeta* meta;              // [n][nmb]
   int* err;                  // [n] 0 ok, 1 premature end of data
   int n_images, mb_w, mb_h;
@@ -165,6 +165,8 @@ struct DecParseParams {
 // the per-column contexts (4 top modes + NZ flags + DC flag per macroblock column) and the token-partition decoder states.
 __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ __align__(16) int16_t s_co[384];  // the macroblock being parsed: zero between macroblocks
+  uint4* s_co4 = reinterpret_cast<uint4*>(s_co);
   DecHeader* H = reinterpret_cast<DecHeader*>(s_dyn);
   uint4* s_prob = reinterpret_cast<uint4*>(s_dyn + ((sizeof(DecHeader) + 15) & ~(size_t)15));  // [4][8][3] rows of 11 (+5) bytes
   uint8_t* s_bmodes = reinterpret_cast<uint8_t*>(s_prob + 96);
@@ -185,13 +187,17 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
     }
     for (int i = lane; i < 6 * P.mb_w; i += 32) top_modes[i] = 0;
   }
+  for (int i = lane; i < 48; i += 32) s_co4[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
-  if (lane != 0) return;
+  // Lane 0 walks the boolean decoders (every bit decides the next instruction: a chain by construction); the other lanes
+  // only help to move a finished macroblock's coefficients out of shared memory in whole sectors.
   const uint8_t* frame = P.streams + H->stream_off;
   DBoolDec br;
   br.adopt(frame + H->br_pos, frame + H->br_end, H->br_value, H->br_range, H->br_bits, H->br_eof != 0);
   const int last = H->last_part;
-  for (int p = 0; p <= last; ++p) parts[p].init(frame + H->part_off[p], H->part_len[p]);
+  if (lane == 0)
+    for (int p = 0; p <= last; ++p) parts[p].init(frame + H->part_off[p], H->part_len[p]);
+  __syncwarp();
   const int mb_w = P.mb_w, mb_h = P.mb_h;
   const size_t nmb = (size_t)mb_w * mb_h;
   const bool update_map = H->update_map, use_skip = H->use_skip;
@@ -199,6 +205,7 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
   for (int my = 0; my < mb_h; ++my) {
     uint8_t left_modes[4] = {0, 0, 0, 0};
     MBMeta* row = P.meta + (size_t)img * nmb + (size_t)my * mb_w;
+    if (lane == 0)
     for (int mx = 0; mx < mb_w; ++mx) {  // parseIntraModeRow (decode_tree.go:35)
       MBMeta m;
       uint8_t* top = top_modes + 4 * mx;
@@ -230,13 +237,15 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
       m.f_limit = m.f_ilevel = m.f_inner = m.hev_thresh = 0;
       row[mx] = m;
     }
-    if (br.eof) { P.err[img] = 1; return; }
+    if (__shfl_sync(0xffffffffu, (int)br.eof, 0)) { if (lane == 0) P.err[img] = 1; return; }
     DBoolDec tb = parts[my & last];
     uint8_t left_nz = 0, left_dc = 0;
     for (int mx = 0; mx < mb_w; ++mx) {
+      uint32_t any_nz = 0;  // some block of this macroblock has a non-zero transform code: its coefficients will be read
+      if (lane == 0) {
       MBMeta& m = row[mx];
       const int is_i4 = m.is_i4, segment = m.segment & 3;
-      int16_t* dst = P.coeffs + ((size_t)img * nmb + (size_t)my * mb_w + mx) * 384;
+      int16_t* dst = s_co;
       const bool skip = use_skip && m.skip;
       uint32_t nzy = 0, nzuv = 0;
       if (skip) {
@@ -311,9 +320,21 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
       const uint8_t* f = H->fs[segment][is_i4];
       m.f_limit = f[0]; m.f_ilevel = f[1]; m.hev_thresh = f[3];
       m.f_inner = (uint8_t)(f[2] || !skip);  // FInner |= !skip (decode_mb.go:291)
-      if (tb.eof) { P.err[img] = 1; return; }
+      any_nz = nzy | nzuv;
+      }
+      any_nz = __shfl_sync(0xffffffffu, any_nz, 0);
+      if (__shfl_sync(0xffffffffu, (int)tb.eof, 0)) { if (lane == 0) P.err[img] = 1; return; }
+      if (any_nz) {
+        __syncwarp();
+        // the reconstruction reads the coefficients of blocks with a non-zero code only (recon_wave_kernel), so an all-zero
+        // macroblock leaves nothing behind and the array needs no zero fill: 768 B per coded macroblock, written once
+        uint4* dst4 = reinterpret_cast<uint4*>(P.coeffs + ((size_t)img * nmb + (size_t)my * mb_w + mx) * 384);
+        for (int i = lane; i < 48; i += 32) { dst4[i] = s_co4[i]; s_co4[i] = make_uint4(0, 0, 0, 0); }
+        __syncwarp();
+      }
     }
-    parts[my & last] = tb;
+    if (lane == 0) parts[my & last] = tb;
+    __syncwarp();
   }
 }
 

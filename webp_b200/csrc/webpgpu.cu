@@ -1559,7 +1559,7 @@ int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* l
     ctx->xfer_h2d += (uint64_t)((size_t)n * sizeof(wgh::DecHeaderH));
     CK(cudaMemcpyAsync(ctx->d_ftype.p, ctx->hd_ftype.p, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     ctx->xfer_h2d += (uint64_t)((size_t)n);
-    CK(cudaMemsetAsync(ctx->d_coeffs.p, 0, (size_t)n * nmb * 768, ctx->stream));
+    // no zero fill of d_coeffs: the parser writes the macroblocks with a non-zero transform code, the reconstruction reads no others
     CK(cudaMemsetAsync(ctx->d_perr.p, 0, (size_t)n * 4, ctx->stream));
     // a truncated partition makes the parser stop early: what it did not reach must not be stale or uninitialised memory
     CK(cudaMemsetAsync(ctx->d_meta.p, 0, (size_t)n * nmb * sizeof(wg::MBMeta), ctx->stream));
@@ -1567,9 +1567,10 @@ int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* l
     DP.streams = ctx->d_streams.as<uint8_t>(); DP.hdr = ctx->d_hdrs.as<wg::DecHeader>(); DP.bmodes = ctx->t_bmodes.as<uint8_t>();
     DP.coeffs = ctx->d_coeffs.as<int16_t>(); DP.meta = ctx->d_meta.as<wg::MBMeta>(); DP.err = ctx->d_perr.as<int>();
     DP.n_images = n; DP.mb_w = mbw; DP.mb_h = mbh;
-    // one warp per image; 24 KB of shared memory per block keeps the block scheduler from stacking dozens of these
-    // single-lane latency chains on one SM
-    const size_t smem = std::max(wg::dec_parse_smem(mbw), (size_t)24 * 1024);
+    // one warp per image, one lane of it on the chain: a chain issues an instruction every ~4.4 cycles, so an SM's four
+    // schedulers carry ~16 of them at full speed; 14 KB of shared memory per block caps the stacking there (the parsers of
+    // several contexts in flight share the GPU: 8 x 256 images in bench.py's decode leg)
+    const size_t smem = std::max(wg::dec_parse_smem(mbw), (size_t)14 * 1024);
     wg::dec_parse_kernel<<<n, 32, smem, ctx->stream>>>(DP);
     ctx->launches++;
     CK(cudaGetLastError());
