@@ -331,14 +331,16 @@ __device__ __forceinline__ uint32_t ups_px(uint32_t y24, uint32_t uv, uint32_t a
   asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(px) : "r"(g), "r"(r), "r"(ba));        // r | g << 8 | b << 16 | a << 24
   return px;
 }
-__global__ void __launch_bounds__(256) upsample_nrgba_kernel(const UpsampleParams P) {
+// blockDim = (bx, 256 / bx): thread (tx, ty) takes pixel group blockIdx.x * bx + tx of line pair blockIdx.y * by + ty of image
+// blockIdx.z -- no index divisions.
+template <bool HAS_ALPHA>
+__global__ void __launch_bounds__(256, 4) upsample_nrgba_kernel(const UpsampleParams P) {
   const int gw = (P.width + 15) >> 4, npairs = (P.height >> 1) + 1;
   const int ch = (P.height + 1) >> 1, half_w = (P.width + 1) >> 1;
-  const long long per_img = (long long)gw * npairs, total = per_img * P.n;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int img = (int)(t / per_img);
-    const int rem = (int)(t - (long long)img * per_img);
-    const int p = rem / gw, x0 = (rem - p * gw) * 16;
+  {
+    const int img = blockIdx.z, p = blockIdx.y * blockDim.y + threadIdx.y, gx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gx >= gw || p >= npairs) return;
+    const int x0 = gx * 16;
     const int rt = 2 * p - 1, rb = 2 * p;
     const bool has_top = p >= 1, has_bot = rb < P.height;
     const int ca = max(p - 1, 0), cb = min(p, ch - 1);
@@ -386,8 +388,8 @@ __global__ void __launch_bounds__(256) upsample_nrgba_kernel(const UpsampleParam
         yb[i >> 2] |= (uint32_t)ybr[xx] << (8 * (i & 3));
       }
     }
-    const uint8_t* at = P.alpha ? P.alpha + (size_t)img * P.alpha_plane + (size_t)max(rt, 0) * P.width + x0 : nullptr;
-    const uint8_t* ab = P.alpha ? P.alpha + (size_t)img * P.alpha_plane + (size_t)min(rb, P.height - 1) * P.width + x0 : nullptr;
+    const uint8_t* at = HAS_ALPHA ? P.alpha + (size_t)img * P.alpha_plane + (size_t)max(rt, 0) * P.width + x0 : nullptr;
+    const uint8_t* ab = HAS_ALPHA ? P.alpha + (size_t)img * P.alpha_plane + (size_t)min(rb, P.height - 1) * P.width + x0 : nullptr;
     uint8_t* dt = P.out + (size_t)img * P.out_image + ((size_t)max(rt, 0) * P.width + x0) * 4;
     uint8_t* db = P.out + (size_t)img * P.out_image + ((size_t)min(rb, P.height - 1) * P.width + x0) * 4;
     const bool vec = full && (((uintptr_t)dt | (uintptr_t)db) & 15) == 0;
@@ -398,18 +400,20 @@ __global__ void __launch_bounds__(256) upsample_nrgba_kernel(const UpsampleParam
       uint32_t pt[4], pb[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int i = 4 * g4 + k, x = x0 + i, j = (i + 1) >> 1;
+        const int i = 4 * g4 + k, j = (i + 1) >> 1;
         const uint32_t tl = A[j], tt = A[j + 1], l = B[j], cur = B[j + 1];
         const uint32_t avg = tl + tt + l + cur + 0x00080008u;
         const uint32_t diag12 = (avg + 2 * (tt + l)) >> 3, diag03 = (avg + 2 * (tl + cur)) >> 3;
         uint32_t uvt = (i & 1) ? (diag12 + tl) >> 1 : (diag03 + tt) >> 1;
         uint32_t uvb = (i & 1) ? (diag03 + l) >> 1 : (diag12 + cur) >> 1;
-        if (x == 0) { uvt = (3 * tt + cur + 0x00020002u) >> 2; uvb = (3 * cur + tt + 0x00020002u) >> 2; }      // samples 0 of both rows (j + 1 == 1)
-        else if ((x & 1) && ((x + 1) >> 1) >= half_w) { uvt = (3 * tl + l + 0x00020002u) >> 2; uvb = (3 * l + tl + 0x00020002u) >> 2; }  // sample (x - 1) / 2
+        // x == 0 and the last pixel of an even width have no horizontal neighbour (upsample.go:74-107: (3 * a + b + 2) >> 2);
+        // their missing sample is the clamped replica in A / B, and with tl == tt, l == cur (or tt == tl, cur == l) the
+        // diamond IS that formula: ((a + b + 2) >> 1 + a) >> 1 == (3 * a + b + 2) >> 2 -- no special case
         const uint32_t ytv = __byte_perm(yt[g4], 0, (k << 12) | 0x444), ybv = __byte_perm(yb[g4], 0, (k << 12) | 0x444);  // luma << 24
-        const int xa = min(i, P.width - 1 - x0);
-        pt[k] = ups_px(ytv, uvt, at ? at[xa] : 255u);
-        pb[k] = ups_px(ybv, uvb, ab ? ab[xa] : 255u);
+        uint32_t alt = 255u, alb = 255u;
+        if (HAS_ALPHA) { const int xa = min(i, P.width - 1 - x0); alt = at[xa]; alb = ab[xa]; }
+        pt[k] = ups_px(ytv, uvt, alt);
+        pb[k] = ups_px(ybv, uvb, alb);
       }
       if (vec) {
         if (has_top) *reinterpret_cast<uint4*>(dt + 16 * g4) = make_uint4(pt[0], pt[1], pt[2], pt[3]);

@@ -1335,7 +1335,6 @@ struct ImportParams {
   const uint16_t* dither_y;   // [pad_h][pad_w]      RandomBits(rg, 16)
   const uint32_t* dither_uv;  // [pad_h/2][pad_w/2][2] RandomBits(rg, 18) for U then V
 };
-__device__ __forceinline__ int rgb_to_y(int r, int g, int b) { return (16839 * r + 33059 * g + 6420 * b + (1 << 15) + (16 << 16)) >> 16; }
 __device__ __forceinline__ int clip_uv(int uv, int rounding) {  // VP8ClipUV (yuv.go:138); rounding = 1<<17 unless dithering
   uv = (uv + rounding + (128 << 18)) >> 18;
   return min(max(uv, 0), 255);
@@ -1346,84 +1345,81 @@ __device__ __forceinline__ int lin2gamma(uint32_t v, const uint16_t* l2g) {  // 
   const int yv = l2g[tab_pos + 1] * x + l2g[tab_pos] * (512 - x);
   return (yv + 64) >> 7;
 }
+// RGBToY (yuv.go:151) as two byte dot products: 16839 = 65 * 256 + 199, 33059 = 129 * 256 + 35, 6420 = 25 * 256 + 20, so
+// Y = (256 * dot(rgb, {65, 129, 25}) + dot(rgb, {199, 35, 20}) + rounding + (16 << 16)) >> 16 -- the same integer, 4 instructions.
+__device__ __forceinline__ uint32_t rgb_to_y_px(uint32_t p, uint32_t rounding) {
+  const uint32_t lo = __dp4a(p, 0x001423c7u, rounding + (16u << 16));
+  return (__dp4a(p, 0x00198141u, 0u) * 256u + lo) >> 16;
+}
+// blockDim = (64, 4): a thread takes 4 x 2 source pixels at quad column blockIdx.x * 64 + threadIdx.x, row pair
+// blockIdx.y * 4 + threadIdx.y of image blockIdx.z -- no index divisions.
+template <bool ALPHA, bool DITHER>
 __global__ void __launch_bounds__(256) import_rgba_kernel(const ImportParams P) {
   __shared__ uint16_t s_g2l[256];
   __shared__ uint16_t s_l2g[34];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_g2l[i] = P.gamma_to_linear[i];
-  if (threadIdx.x < 34) s_l2g[threadIdx.x] = P.linear_to_gamma[threadIdx.x];
+  const int tid = threadIdx.y * 64 + threadIdx.x;
+  s_g2l[tid] = P.gamma_to_linear[tid];
+  if (tid < 34) s_l2g[tid] = P.linear_to_gamma[tid];
   __syncthreads();
   const int qw = P.pad_w >> 2, qh = P.pad_h >> 1;
-  const long long per_img = (long long)qw * qh;
-  const long long total = per_img * P.n;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int img = (int)(t / per_img);
-    const int rem = (int)(t - (long long)img * per_img);
-    const int cy = rem / qw, cx = rem - cy * qw;
-    const int x0 = cx * 4, y0 = cy * 2;
-    const uint8_t* base = P.rgba + (size_t)img * P.image_stride;
-    uint32_t px[2][4];
+  const int cx = blockIdx.x * 64 + threadIdx.x, cy = blockIdx.y * 4 + threadIdx.y, img = blockIdx.z;
+  if (cx >= qw || cy >= qh) return;
+  const int x0 = cx * 4, y0 = cy * 2;
+  const uint8_t* base = P.rgba + (size_t)img * P.image_stride;
+  uint32_t px[2][4];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const uint8_t* row = base + (size_t)min(y0 + r, P.height - 1) * P.stride;
-      if (x0 + 3 < P.width) {
-        const uint4 q = *reinterpret_cast<const uint4*>(row + 4 * x0);
-        px[r][0] = q.x; px[r][1] = q.y; px[r][2] = q.z; px[r][3] = q.w;
-      } else {
+  for (int r = 0; r < 2; ++r) {
+    const uint8_t* row = base + (size_t)min(y0 + r, P.height - 1) * P.stride;
+    if (x0 + 3 < P.width) {
+      const uint4 q = *reinterpret_cast<const uint4*>(row + 4 * x0);
+      px[r][0] = q.x; px[r][1] = q.y; px[r][2] = q.z; px[r][3] = q.w;
+    } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) px[r][i] = *reinterpret_cast<const uint32_t*>(row + 4 * min(x0 + i, P.width - 1));
-      }
+      for (int i = 0; i < 4; ++i) px[r][i] = *reinterpret_cast<const uint32_t*>(row + 4 * min(x0 + i, P.width - 1));
     }
-    uint8_t* yp = P.y + (size_t)img * P.y_plane;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      uint32_t w = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t p = px[r][i];
-        int yv;
-        if (P.dither_y) {  // RGBToYRounding (yuv.go:159)
-          const int rnd = P.dither_y[(size_t)(y0 + r) * P.pad_w + x0 + i];
-          yv = (16839 * (int)(p & 0xff) + 33059 * (int)((p >> 8) & 0xff) + 6420 * (int)((p >> 16) & 0xff) + rnd + (16 << 16)) >> 16;
-        } else {
-          yv = rgb_to_y(p & 0xff, (p >> 8) & 0xff, (p >> 16) & 0xff);
-        }
-        w |= (uint32_t)yv << (8 * i);
-      }
-      *reinterpret_cast<uint32_t*>(yp + (size_t)(y0 + r) * P.pad_w + x0) = w;
-    }
-    uint32_t uu = 0, vv = 0;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const uint32_t p0 = px[0][2 * k], p1 = px[0][2 * k + 1], p2 = px[1][2 * k], p3 = px[1][2 * k + 1];
-      uint32_t a0 = 255, a1 = 255, a2 = 255, a3 = 255;
-      if (P.has_alpha) { a0 = p0 >> 24; a1 = p1 >> 24; a2 = p2 >> 24; a3 = p3 >> 24; }
-      const uint32_t ta = a0 + a1 + a2 + a3;
-      int c[3];
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        const int sh = 8 * ch;
-        const uint32_t l0 = s_g2l[(p0 >> sh) & 0xff], l1 = s_g2l[(p1 >> sh) & 0xff];
-        const uint32_t l2 = s_g2l[(p2 >> sh) & 0xff], l3 = s_g2l[(p3 >> sh) & 0xff];
-        if (ta == 4 * 255 || ta == 0) {
-          c[ch] = lin2gamma(l0 + l1 + l2 + l3, s_l2g);
-        } else {  // LinearToGammaWeighted (yuv.go:466); kInvAlpha[a] = (1<<19)/a
-          const uint32_t sum = a0 * l0 + a1 * l1 + a2 * l2 + a3 * l3;
-          c[ch] = lin2gamma((sum * ((1u << 19) / ta)) >> (19 - 2), s_l2g);
-        }
-        c[ch] &= 0xffff;
-      }
-      int ru = 1 << 17, rv = 1 << 17;
-      if (P.dither_uv) {
-        const size_t di = ((size_t)cy * (P.pad_w >> 1) + (x0 >> 1) + k) * 2;
-        ru = (int)P.dither_uv[di]; rv = (int)P.dither_uv[di + 1];
-      }
-      uu |= (uint32_t)clip_uv(-9719 * c[0] - 19081 * c[1] + 28800 * c[2], ru) << (8 * k);
-      vv |= (uint32_t)clip_uv(28800 * c[0] - 24116 * c[1] - 4684 * c[2], rv) << (8 * k);
-    }
-    const size_t uvo = (size_t)img * P.uv_plane + (size_t)cy * (P.pad_w >> 1) + (x0 >> 1);
-    *reinterpret_cast<uint16_t*>(P.u + uvo) = (uint16_t)uu;
-    *reinterpret_cast<uint16_t*>(P.v + uvo) = (uint16_t)vv;
   }
+  uint8_t* yp = P.y + (size_t)img * P.y_plane;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    uint32_t yv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)  // RGBToYRounding (yuv.go:159) with the drawn term, else the fixed 1 << 15
+      yv[i] = rgb_to_y_px(px[r][i], DITHER ? (uint32_t)P.dither_y[(size_t)(y0 + r) * P.pad_w + x0 + i] : (1u << 15));
+    *reinterpret_cast<uint32_t*>(yp + (size_t)(y0 + r) * P.pad_w + x0) =
+        __byte_perm(__byte_perm(yv[0], yv[1], 0x0040), __byte_perm(yv[2], yv[3], 0x0040), 0x5410);
+  }
+  uint32_t uu = 0, vv = 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t p0 = px[0][2 * k], p1 = px[0][2 * k + 1], p2 = px[1][2 * k], p3 = px[1][2 * k + 1];
+    uint32_t a0 = 255, a1 = 255, a2 = 255, a3 = 255;
+    if (ALPHA) { a0 = p0 >> 24; a1 = p1 >> 24; a2 = p2 >> 24; a3 = p3 >> 24; }
+    const uint32_t ta = a0 + a1 + a2 + a3;
+    int c[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const int sh = 8 * ch;
+      const uint32_t l0 = s_g2l[(p0 >> sh) & 0xff], l1 = s_g2l[(p1 >> sh) & 0xff];
+      const uint32_t l2 = s_g2l[(p2 >> sh) & 0xff], l3 = s_g2l[(p3 >> sh) & 0xff];
+      if (!ALPHA || ta == 4 * 255 || ta == 0) {
+        c[ch] = lin2gamma(l0 + l1 + l2 + l3, s_l2g);
+      } else {  // LinearToGammaWeighted (yuv.go:466); kInvAlpha[a] = (1<<19)/a
+        const uint32_t sum = a0 * l0 + a1 * l1 + a2 * l2 + a3 * l3;
+        c[ch] = lin2gamma((sum * ((1u << 19) / ta)) >> (19 - 2), s_l2g);
+      }
+      c[ch] &= 0xffff;
+    }
+    int ru = 1 << 17, rv = 1 << 17;
+    if (DITHER) {
+      const size_t di = ((size_t)cy * (P.pad_w >> 1) + (x0 >> 1) + k) * 2;
+      ru = (int)P.dither_uv[di]; rv = (int)P.dither_uv[di + 1];
+    }
+    uu |= (uint32_t)clip_uv(-9719 * c[0] - 19081 * c[1] + 28800 * c[2], ru) << (8 * k);
+    vv |= (uint32_t)clip_uv(28800 * c[0] - 24116 * c[1] - 4684 * c[2], rv) << (8 * k);
+  }
+  const size_t uvo = (size_t)img * P.uv_plane + (size_t)cy * (P.pad_w >> 1) + (x0 >> 1);
+  *reinterpret_cast<uint16_t*>(P.u + uvo) = (uint16_t)uu;
+  *reinterpret_cast<uint16_t*>(P.v + uvo) = (uint16_t)vv;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1449,7 +1445,9 @@ __device__ __forceinline__ int histo_alpha16(int* hist, int gl) {  // alpha from
   }
   if (last < 0) last = 1;
   int alpha = 0;
-  if (mx > 1) alpha = 2 * 255 * last / mx;
+  // 2 * 255 * last / mx: numerator < 2^14 and denominator <= 512, so the IEEE single quotient truncates to the exact integer one
+  // (an exact quotient is representable; otherwise it lies >= 1 / mx from the integers, the rounding error is < 2^-10 of that)
+  if (mx > 1) alpha = (int)__fdiv_rn((float)(2 * 255 * last), (float)mx);
   return min(alpha, 255);
 }
 __device__ __forceinline__ void histo_add16(const int* c, int* hist) {
@@ -1461,12 +1459,11 @@ __global__ void __launch_bounds__(128) analysis_kernel(const AnalysisParams P) {
   const int lane = threadIdx.x & 31, gl = lane & 15;
   const int grp = threadIdx.x >> 4;  // 8 macroblocks per CTA
   const int nmb = P.mb_w * P.mb_h;
-  const long long total = (long long)nmb * P.n;
-  const long long task = (long long)blockIdx.x * 8 + grp;
-  const bool active = task < total;
-  const int img = active ? (int)(task / nmb) : 0;
-  const int mb = active ? (int)(task - (long long)img * nmb) : 0;
-  const int my = mb / P.mb_w, mx = mb - my * P.mb_w;
+  // grid = (ceil(mb_w / 8), mb_h, n): no index divisions
+  const bool active = (int)blockIdx.x * 8 + grp < P.mb_w;
+  const int img = active ? (int)blockIdx.z : 0;
+  const int my = active ? (int)blockIdx.y : 0, mx = active ? (int)blockIdx.x * 8 + grp : 0;
+  const int mb = my * P.mb_w + mx;
   const int ys = P.mb_w * 16, uvs = P.mb_w * 8;
   const uint8_t* yp = P.y + (size_t)img * P.y_plane + (size_t)my * 16 * ys + mx * 16;
   int* hist = s_hist[grp];
@@ -1489,7 +1486,7 @@ __global__ void __launch_bounds__(128) analysis_kernel(const AnalysisParams P) {
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
   const int count = (my > 0 ? 16 : 0) + (mx > 0 ? 16 : 0);
-  const int dc_val = count > 0 ? (s + count / 2) / count : 128;
+  const int dc_val = count == 32 ? (s + 16) >> 5 : (count == 16 ? (s + 8) >> 4 : 128);  // (s + count / 2) / count
   int best_alpha = 256;
   int pred[16], c[16];
   {
@@ -1534,7 +1531,7 @@ __global__ void __launch_bounds__(128) analysis_kernel(const AnalysisParams P) {
 #pragma unroll
   for (int o = 4; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o, 8);
   const int ccount = (my > 0 ? 8 : 0) + (mx > 0 ? 8 : 0);
-  const int cdc = ccount > 0 ? (cs + ccount / 2) / ccount : 128;
+  const int cdc = ccount == 16 ? (cs + 8) >> 4 : (ccount == 8 ? (cs + 4) >> 3 : 128);  // (cs + ccount / 2) / ccount
   const int dc_u = __shfl_sync(0xffffffffu, cdc, 0, 16), dc_v = __shfl_sync(0xffffffffu, cdc, 8, 16);
   hist[gl] = 0; hist[gl + 16] = 0;
   __syncwarp();

@@ -593,9 +593,15 @@ static int enc_launch_import(wgpu_ctx* ctx) {
     }
     ip.dither_y = ctx->dither_y.as<uint16_t>(); ip.dither_uv = ctx->dither_uv.as<uint32_t>();
   }
-  const long long total = (long long)(pad_w / 4) * (pad_h / 2) * n;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
-  wg::import_rgba_kernel<<<blocks, 256, 0, ctx->stream>>>(ip);
+  const dim3 block(64, 4), grid((unsigned)((pad_w / 4 + 63) / 64), (unsigned)((pad_h / 2 + 3) / 4), (unsigned)n);
+  const bool dither = ip.dither_y != nullptr;
+  if (ip.has_alpha) {
+    if (dither) wg::import_rgba_kernel<true, true><<<grid, block, 0, ctx->stream>>>(ip);
+    else wg::import_rgba_kernel<true, false><<<grid, block, 0, ctx->stream>>>(ip);
+  } else {
+    if (dither) wg::import_rgba_kernel<false, true><<<grid, block, 0, ctx->stream>>>(ip);
+    else wg::import_rgba_kernel<false, false><<<grid, block, 0, ctx->stream>>>(ip);
+  }
   ctx->launches++;
   CK(cudaGetLastError());
   return WGPU_OK;
@@ -607,8 +613,8 @@ static int enc_launch_analysis(wgpu_ctx* ctx) {
   ap.y_plane = (size_t)nmb * 256; ap.uv_plane = (size_t)nmb * 64;
   ap.n = n; ap.mb_w = ctx->e_mbw; ap.mb_h = ctx->e_mbh; ap.width = ctx->e_w; ap.height = ctx->e_h;
   ap.alpha = ctx->alpha.as<uint8_t>(); ap.uv_alpha = ctx->uv_alpha.as<uint8_t>();
-  const long long total = (long long)nmb * n;
-  wg::analysis_kernel<<<(unsigned)((total + 7) / 8), 128, 0, ctx->stream>>>(ap);
+  (void)nmb;
+  wg::analysis_kernel<<<dim3((unsigned)((ctx->e_mbw + 7) / 8), (unsigned)ctx->e_mbh, (unsigned)n), 128, 0, ctx->stream>>>(ap);
   ctx->launches++;
   CK(cudaGetLastError());
   return WGPU_OK;
@@ -1483,9 +1489,11 @@ static int launch_upsample(wgpu_ctx* ctx, int n, int width, int height, const ui
   up.y = y; up.u = u; up.v = v; up.alpha = alpha;
   up.y_plane = y_plane; up.uv_plane = uv_plane; up.alpha_plane = (size_t)width * height; up.out_image = (size_t)width * height * 4;
   up.y_stride = ys; up.uv_stride = uvs; up.width = width; up.height = height; up.n = n; up.out = out;
-  const long long total = (long long)((width + 15) / 16) * (height / 2 + 1) * n;  // 16 pixels of a line pair per thread
-  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 64);
-  wg::upsample_nrgba_kernel<<<blocks, 256, 0, ctx->stream>>>(up);
+  // 16 pixels of a line pair per thread
+  const int gw = (width + 15) / 16, bx = gw <= 8 ? 8 : (gw <= 16 ? 16 : 32), by = 256 / bx;
+  const dim3 block(bx, by), grid((unsigned)((gw + bx - 1) / bx), (unsigned)((height / 2 + 1 + by - 1) / by), (unsigned)n);
+  if (alpha) wg::upsample_nrgba_kernel<true><<<grid, block, 0, ctx->stream>>>(up);
+  else wg::upsample_nrgba_kernel<false><<<grid, block, 0, ctx->stream>>>(up);
   ctx->launches++;
   CK(cudaGetLastError());
   return WGPU_OK;
