@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 ALG_BYTES_PER_PX = {"mode_search": 6.44, "import": 5.5, "analysis": 1.5, "recon": 4.66, "filter": 3.0, "upsample": 5.5}
 METRIC = "lossy encode & decode Mpix/s (1536x1024 q75 m4), bit-exact"
 CONFIGS = {
-    2: dict(w=1536, h=1024, quality=75, method=4, target_psnr=0.0, batch=256, distinct=24, steps=12, e2e_workers=5, value_contexts=2, decode=True,
+    2: dict(w=1536, h=1024, quality=75, method=4, target_psnr=0.0, batch=256, distinct=24, steps=12, e2e_workers=3, value_contexts=2, decode=True,
             metric=METRIC, workload="synthetic 1536x1024 RGBA lossy encode q75 method 4, batch of %d images per GPU (BASELINE configs[1])"),
     4: dict(w=3840, h=2160, quality=75, method=6, target_psnr=42.0, batch=48, distinct=8, steps=3, e2e_workers=2, value_contexts=1, decode=False,
             metric="lossy encode Mpix/s (3840x2160 m6 TargetPSNR 42), bit-exact",

@@ -79,6 +79,26 @@ long orc_encode(const uint8_t* rgba, int stride, int w, int h, const OrcEncCfg* 
   return ret;
 }
 
+// The final token stream of the (single) token partition, bit | prob << 8 per token as recordAllTokens leaves it
+// (encode_token.go:20,304), and the partition it codes to.  Test infrastructure for the device boolean coder: returns the
+// token count (tokens may be null to size the buffer); *part_len / part receive the coded partition (emitTokenPartition).
+long orc_encode_tokens(const uint8_t* rgba, int stride, int w, int h, const OrcEncCfg* cfg, uint16_t* tokens, long cap,
+                       uint8_t* part, long part_cap, long* part_len) {
+  if (((w + 15) >> 4) > 1024) return -1;
+  Encoder* enc = new Encoder();
+  enc->init(rgba, stride, w, h, to_cfg(cfg), cfg->has_alpha);
+  (void)enc->encode_frame();
+  const long n = (long)enc->tokens.size();
+  if (tokens && n <= cap) memcpy(tokens, enc->tokens.data(), (size_t)n * 2);
+  if (part_len) {
+    std::vector<uint8_t> p = enc->emit_token_partition(0);
+    *part_len = (long)p.size();
+    if (part && (long)p.size() <= part_cap) memcpy(part, p.data(), p.size());
+  }
+  delete enc;
+  return n;
+}
+
 // Encode n same-size images on `threads` host threads (bench cpu_baseline / --impl reference).
 // sizes[i] receives each RIFF size; returns total bytes or <0.
 long orc_encode_batch(const uint8_t* rgba, int n, int stride, int w, int h, const OrcEncCfg* cfg, int threads,

@@ -10,6 +10,7 @@
 #include <random>
 #include <chrono>
 
+#include "../webp_b200/csrc/boolcode_par.cuh"
 extern "C" {
 struct OrcEncCfg2 {
   int quality, method, sns_strength, filter_strength, filter_sharpness, filter_type, partitions, segments, preprocessing, has_alpha, passes, dither_amp;
@@ -301,5 +302,67 @@ int hostcheck_modesearch(const uint8_t* rgba, int stride, int w, int h, const Or
   for (int i = 0; i < nmb; ++i) seg_bad += segmap[i] != enc->mb_info[i].segment;
   delete enc;
   return bad + seg_bad;
+}
+
+// ---- chunk-parallel boolean coder (webp_b200/csrc/boolcode_par.cuh) run on the CPU: the kernels' per-chunk functions in a
+// shuffled order per launch, rounds until the relaxation reports no change.  tokens = the partitions back to back (totals[i]
+// tokens each); partition i is written to out + i * out_stride, its size to sizes[i]; returns the number of relaxation rounds.
+int hostcheck_boolcode_par(const uint16_t* tokens, const unsigned long long* totals, int n, uint8_t* out, long out_stride,
+                           unsigned* sizes, unsigned order_seed) {
+  std::vector<unsigned long long> base(n), obase(n);
+  std::vector<uint32_t> first(n + 1);
+  unsigned long long all = 0;
+  uint32_t nchunks = 0;
+  for (int i = 0; i < n; ++i) {
+    base[i] = all; all += (totals[i] + 7) & ~7ull;
+    obase[i] = (unsigned long long)i * (unsigned long long)out_stride;
+    first[i] = nchunks; nchunks += wg::bcp_chunks_of(totals[i]);
+  }
+  first[n] = nchunks;
+  std::vector<uint16_t> tk(all + 8, 0);
+  unsigned long long src = 0;
+  for (int i = 0; i < n; ++i) { memcpy(&tk[base[i]], tokens + src, (size_t)totals[i] * 2); src += totals[i]; }
+  std::vector<uint8_t> entry(nchunks, 0), walked(nchunks, 0);
+  std::vector<uint32_t> shift(nchunks, 0), bitpos(nchunks, 0), head(nchunks, 0), hcarry(nchunks, 0);
+  std::vector<uint16_t> tail(nchunks, 0);
+  std::vector<unsigned> changed(4096, 0);
+  wg::BcpParams P;
+  P.tokens = tk.data(); P.img_base = base.data(); P.img_total = totals; P.chunk_first = first.data(); P.n_images = n; P.n_chunks = nchunks;
+  P.entry = entry.data(); P.walked = walked.data(); P.shift_total = shift.data(); P.chunk_bit = bitpos.data(); P.head = head.data();
+  P.head_carry = hcarry.data(); P.tail = tail.data(); P.changed = changed.data(); P.round = 0; P.out = out; P.out_base = obase.data();
+  P.out_size = sizes;
+  std::vector<uint32_t> order(nchunks);
+  for (uint32_t k = 0; k < nchunks; ++k) order[k] = k;
+  unsigned rng = order_seed * 2654435761u + 12345u;
+  auto shuffle = [&]() {
+    if (!order_seed) return;
+    for (uint32_t k = nchunks; k > 1; --k) { rng = rng * 1664525u + 1013904223u; std::swap(order[k - 1], order[(rng >> 8) % k]); }
+  };
+  int rounds = 0;
+  for (;; ++rounds) {
+    if (rounds >= 4096) return -1;
+    P.round = rounds;
+    shuffle();
+    for (uint32_t k = 0; k < nchunks; ++k) wg::bcp_state_chunk(P, order[k]);
+    if (rounds > 0 && changed[rounds] == 0) break;
+  }
+  for (int i = 0; i < n; ++i) {
+    uint32_t run = 0;
+    for (uint32_t k = first[i]; k < first[i + 1]; ++k) { bitpos[k] = run; run += shift[k]; }
+  }
+  shuffle();
+  for (uint32_t k = 0; k < nchunks; ++k) wg::bcp_bytes_chunk(P, order[k]);
+  for (int i = n - 1; i >= 0; --i) wg::bcp_join_image(P, i);
+  return rounds + 1;
+}
+
+// the reference-order coder over one flat token array (oracle BoolWriter = bitio/writer_bool.go): what the chunked coder must equal
+long hostcheck_boolcode_serial(const uint16_t* tokens, unsigned long long n, uint8_t* out, long cap) {
+  orc::BoolWriter bw;
+  for (unsigned long long i = 0; i < n; ++i) bw.put_bit(tokens[i] & 1, tokens[i] >> 8);
+  std::vector<uint8_t> r = bw.finish();
+  if ((long)r.size() > cap) return -1;
+  memcpy(out, r.data(), r.size());
+  return (long)r.size();
 }
 }

@@ -105,6 +105,25 @@ def encode_ops(rgba, cfg=None):
     return {_OPS_LIB.orc_op_name(i).decode(): int(cnt[i]) * int(wt[i]) for i in range(n)}
 
 
+def encode_tokens(rgba, cfg=None):
+    """(tokens uint16 [n] = bit | prob << 8, coded token partition bytes) of one encode: the input and the expected output of the
+    device boolean coder (oracle/capi.cc orc_encode_tokens)."""
+    L = lib()
+    L.orc_encode_tokens.restype = C.c_long
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = rgba.shape[:2]
+    cfg = cfg or default_cfg()
+    plen = C.c_long(0)
+    cap = w * h * 4 + (1 << 16)
+    toks = np.empty(cap, np.uint16)
+    part = np.empty(cap, np.uint8)
+    n = L.orc_encode_tokens(_p(rgba), C.c_int(rgba.strides[0]), w, h, C.byref(cfg), toks.ctypes.data_as(C.c_void_p), C.c_long(cap),
+                            part.ctypes.data_as(C.c_void_p), C.c_long(cap), C.byref(plen))
+    if n < 0 or n > cap or plen.value > cap:
+        raise RuntimeError("orc_encode_tokens failed: %d" % n)
+    return toks[:n].copy(), part[:plen.value].copy()
+
+
 def encode_batch(rgba_batch, cfg=None, threads=1):
     """rgba_batch uint8 [n][h][w][4]; returns total compressed bytes (timing leg)."""
     rgba_batch = np.ascontiguousarray(rgba_batch, dtype=np.uint8)

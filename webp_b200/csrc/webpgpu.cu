@@ -15,6 +15,7 @@
 #include "../../include/webpgpu.h"
 #include "misc_kernels.cuh"
 #include "token_kernels.cuh"
+#include "boolcode_par.cuh"
 #include "enc_phased.cuh"
 #include "dec_parse.cuh"
 #include "sharp_kernels.cuh"
@@ -83,9 +84,9 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, ctxw_uv, derr, dither_y, dither_uv, hdr, coeffs, stats, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, ctxw_uv, derr, dither_y, dither_uv, hdr, coeffs, stats, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, bcp_work, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
   DevBuf sharp_best_y, sharp_target_y, sharp_best_uv, sharp_target_uv, t_sharp;  // SharpYUV import working planes + gamma tables
-  PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens;
+  PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens, h_bcp;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false, e_keep_derr = false, e_keep_stats = false;
   int dither_w = 0, dither_h = 0, dither_amp_cached = 0;  // what the device dither tables currently hold
@@ -231,14 +232,14 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->ctxw_uv, &ctx->derr, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
+  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->ctxw_uv, &ctx->derr, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->bcp_work, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_streams, &ctx->d_hdrs, &ctx->d_perr, &ctx->t_bmodes, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
                   &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
                   &ctx->m_sse, &ctx->m_ssim};
   for (DevBuf* b : db) b->release();
-  PinBuf* pb[] = {&ctx->h_stats_cuts, &ctx->hd_streams, &ctx->hd_hdrs, &ctx->hd_perr, &ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
+  PinBuf* pb[] = {&ctx->h_stats_cuts, &ctx->hd_streams, &ctx->hd_hdrs, &ctx->hd_perr, &ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_bcp, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
                   &ctx->hd_meta, &ctx->hd_ftype, &ctx->hd_planes, &ctx->hd_nrgba};
   for (PinBuf* b : pb) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -752,6 +753,77 @@ static int enc_reserve(wgpu_ctx* ctx) {
   return WGPU_OK;
 }
 
+// Chunk-parallel boolean coder (boolcode_par.cuh): plan on the host from the per-partition token counts, then the usual number
+// of relaxation rounds, the prefix sums, the byte pass and the joins, queued without a host round trip.  The per-round change
+// counters come back with the coded sizes; finish_boolcode_par checks the last one.
+constexpr int kBcpRounds = 8;
+static int launch_bcp_tail(wgpu_ctx* ctx, const wg::BcpParams& BP) {
+  const unsigned cb = (BP.n_chunks + 127) / 128;
+  wg::bcp_scan_kernel<<<(unsigned)((BP.n_images * 32 + 127) / 128), 128, 0, ctx->stream>>>(BP);
+  wg::bcp_bytes_kernel<<<cb, 128, 0, ctx->stream>>>(BP);
+  wg::bcp_join_kernel<<<(unsigned)((BP.n_images + 63) / 64), 64, 0, ctx->stream>>>(BP);
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  return WGPU_OK;
+}
+static int launch_boolcode_par(wgpu_ctx* ctx, const wg::BoolCodeParams& B, const unsigned long long* totals, size_t n, wg::BcpParams* out) {
+  RESERVE(ctx->h_bcp, (n + 1) * 4 + 64 * 4);
+  uint32_t* first = ctx->h_bcp.as<uint32_t>();
+  uint32_t nchunks = 0;
+  for (size_t i = 0; i < n; ++i) { first[i] = nchunks; nchunks += wg::bcp_chunks_of(totals[i]); }
+  first[n] = nchunks;
+  // device work area: chunk_first [n + 1] | changed [64] | shift, bit, head, head_carry [chunks] x 4 B | tail x 2 B | entry, walked x 1 B
+  const size_t head_words = n + 1 + 64;
+  RESERVE(ctx->bcp_work, head_words * 4 + (size_t)nchunks * (16 + 2 + 2) + 64);
+  uint32_t* w = ctx->bcp_work.as<uint32_t>();
+  CK(cudaMemcpyAsync(w, first, (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->xfer_h2d += (uint64_t)((n + 1) * 4);
+  CK(cudaMemsetAsync(w + n + 1, 0, 64 * 4, ctx->stream));
+  wg::BcpParams BP;
+  BP.tokens = B.tokens; BP.img_base = B.img_base; BP.img_total = B.img_total; BP.chunk_first = w; BP.n_images = (int)n; BP.n_chunks = nchunks;
+  BP.changed = w + n + 1;
+  BP.shift_total = w + head_words; BP.chunk_bit = BP.shift_total + nchunks; BP.head = BP.chunk_bit + nchunks; BP.head_carry = BP.head + nchunks;
+  BP.tail = reinterpret_cast<uint16_t*>(BP.head_carry + nchunks);
+  BP.entry = reinterpret_cast<uint8_t*>(BP.tail + nchunks); BP.walked = BP.entry + nchunks;
+  BP.out = B.out; BP.out_base = B.out_base; BP.out_size = B.out_size;
+  const unsigned cb = (nchunks + 127) / 128;
+  for (int r = 0; r < kBcpRounds; ++r) {
+    BP.round = r;
+    wg::bcp_state_kernel<<<cb, 128, 0, ctx->stream>>>(BP);
+    ctx->launches++;
+  }
+  int rc = launch_bcp_tail(ctx, BP);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(first + n + 1, BP.changed, 64 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->xfer_d2h += 64 * 4;
+  *out = BP;
+  return WGPU_OK;
+}
+// After the stream has drained: if the last queued round still changed an entry state (token streams whose range states
+// merge slowly), keep relaxing -- a round that changes nothing is the exact fixed point -- and redo the passes behind it.
+static int finish_boolcode_par(wgpu_ctx* ctx, wg::BcpParams& BP) {
+  uint32_t* changed = ctx->h_bcp.as<uint32_t>() + BP.n_images + 1;
+  int last = kBcpRounds - 1;
+  if (changed[last] == 0) return WGPU_OK;
+  const unsigned cb = (BP.n_chunks + 127) / 128;
+  for (int guard = 0; guard < (1 << 20); ++guard) {
+    CK(cudaMemsetAsync(BP.changed, 0, 64 * 4, ctx->stream));
+    for (int r = 1; r <= 32; ++r) {  // round numbers > 0: walk only what changed
+      BP.round = r;
+      wg::bcp_state_kernel<<<cb, 128, 0, ctx->stream>>>(BP);
+      ctx->launches++;
+    }
+    CK(cudaMemcpyAsync(changed, BP.changed, 64 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (changed[32] == 0) break;
+  }
+  int rc = launch_bcp_tail(ctx, BP);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, (size_t)BP.n_images * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return WGPU_OK;
+}
+
 static wg::TokenParams token_params(wgpu_ctx* ctx) {
   wg::TokenParams T;
   T.hdr = ctx->hdr.as<uint8_t>(); T.coeffs = ctx->coeffs.as<int16_t>(); T.ctxw = ctx->ctxw.as<uint32_t>();
@@ -1199,14 +1271,17 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     B.tokens = ctx->tokens.as<uint16_t>(); B.img_base = ctx->img_base.as<unsigned long long>(); B.img_total = ctx->img_total.as<unsigned long long>();
     B.out = ctx->coded.as<uint8_t>(); B.out_base = ctx->img_base.as<unsigned long long>() + n; B.out_size = ctx->coded_size.as<unsigned int>();
     B.n_images = (int)n;
-    {
-      // The coder runs for 100-200 ms (the serial chain of the longest partition) beside the NEXT batch's mode-search waves
-      // (another context's stream).  Its blocks (32 partitions each, one per lane) ask for 200 KB of shared memory: that
-      // forces the same L1/shared split as the mode-search CTAs (a kernel with a small footprint gets a different split from
-      // the driver and cannot share an SM with them at all -- it then piles onto the few free SMs and stalls both: 540 ms vs
-      // 140 ms), and it gives each block an SM of its own, where the tight coder loops keep the instruction cache (216 ms
-      // vs 280 ms beside mode-search warps).  Cost to the waves: 8 of 148 SMs while the coder runs (packing more warp pairs
-      // per block, WGPU_CODER_PAIRS, frees SMs but slows the chains: 2639 vs 2790 Mpix/s end to end at 4 pairs).
+    // WGPU_CODER=chain keeps the one-lane-per-partition coder (a 100-200 ms dependency chain per batch), for comparison
+    static const bool chain_coder = [] { const char* e = getenv("WGPU_CODER"); return e && !strcmp(e, "chain"); }();
+    wg::BcpParams BP;
+    bool par_coder = !chain_coder;
+    if (par_coder) {
+      const int rc_par = launch_boolcode_par(ctx, B, totals, n, &BP);
+      if (rc_par) return rc_par;
+    } else {
+      // Its blocks (32 partitions each, one per lane) ask for 200 KB of shared memory: that forces the same L1/shared split as
+      // the mode-search CTAs (a kernel with a small footprint gets a different split from the driver and cannot share an SM
+      // with them at all), and it gives each block an SM of its own, where the tight coder loops keep the instruction cache.
       static const int coder_pairs = std::min((int)wg::BOOLCODE_MAX_PAIRS, std::max(1, getenv_int("WGPU_CODER_PAIRS", 1)));
       const size_t coder_smem = std::max((size_t)200 * 1024, (size_t)wg::BOOLCODE_SMEM * wg::BOOLCODE_MAX_PAIRS);
       // per device, so on every call (contexts of one process may sit on different GPUs)
@@ -1219,8 +1294,8 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       B.order = reinterpret_cast<const int*>(ctx->img_base.as<unsigned long long>() + 2 * n);
       const int per_block = 32 * coder_pairs;
       wg::boolcode_kernel<<<(unsigned)((n + per_block - 1) / per_block), 64 * coder_pairs, coder_smem, ctx->stream>>>(B);
+      ctx->launches++;
     }
-    ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->xfer_d2h += (uint64_t)(n * 4);
@@ -1233,6 +1308,10 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     });
     const double t3 = now_ms();
     CK(cudaStreamSynchronize(ctx->stream));
+    if (par_coder) {  // more relaxation rounds if the usual ones were not enough
+      const int rc_par = finish_boolcode_par(ctx, BP);
+      if (rc_par) return rc_par;
+    }
     const double t4 = now_ms();
     const unsigned int* csz = ctx->h_coded_size.as<unsigned int>();
     for (size_t i = 0; i < n; ++i) {  // token partitions go straight to their place in the caller's buffer
