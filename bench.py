@@ -271,9 +271,8 @@ def main():
         opt.target_psnr = cfg["target_psnr"]
     do_search = cfg["target_psnr"] > 0
 
-    # the library codes the token partitions on the GPU for batches of at least 32 images (webpgpu.cu device_coder_wanted)
-    env_coder = os.environ.get("WGPU_DEVICE_CODER", "")
-    device_coder = ((env_coder != "0") if env_coder else n >= 32) and not do_search
+    # the library codes the token partitions on the GPU (webpgpu.cu device_coder_wanted; WGPU_DEVICE_CODER=0 forces the host coder)
+    device_coder = os.environ.get("WGPU_DEVICE_CODER", "") != "0" and not do_search
     finish_slots = args.finish_slots or (3 if device_coder else 1)
     upload_stage, gpu_stage, host_stage = threading.Lock(), threading.BoundedSemaphore(max(1, args.gpu_slots)), threading.BoundedSemaphore(finish_slots)
     first_index = rank * cfg["distinct"]

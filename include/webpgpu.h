@@ -206,6 +206,12 @@ int wgpu_dsp_token_cost_batch(wgpu_ctx* ctx, int n, const int16_t* levels, const
  *   UpsampleLinePair (upsample.go:45, channels = 3) / UpsampleLinePairNRGBA (:130, channels = 4) on n line pairs:
  *     top_y / bot_y [n][width] (bot_y NULL = last row of an odd height), *_u / *_v [n][(width + 1) / 2], alpha rows optional,
  *     top_dst / bot_dst [n][width][channels] */
+/* VP8BitWriter (internal/bitio/writer_bool.go:58-150: PutBit per token, Flush, Finish) over n flat token arrays, the way the
+ * encoder codes its token partitions on the device (chunk-parallel).  tokens = the arrays back to back, bit | prob << 8 per token
+ * (encode_token.go:20 Token{Bit, Prob}), totals[i] tokens each; partition i goes to out + i * out_stride, sizes[i] bytes
+ * (out_stride >= totals[i] / 8 + 4).  *rounds (may be NULL) receives how many state-relaxation rounds the batch needed. */
+int wgpu_dsp_boolcode_batch(wgpu_ctx* ctx, int n, const uint16_t* tokens, const unsigned long long* totals, uint8_t* out,
+                            size_t out_stride, unsigned int* sizes, int* rounds);
 int wgpu_dsp_sse16x16_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int32_t* out);
 int wgpu_dsp_tdisto16x16_batch(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int32_t* out);
 int wgpu_dsp_dequant_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, int ac_q, int16_t* out);

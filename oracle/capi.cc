@@ -99,6 +99,16 @@ long orc_encode_tokens(const uint8_t* rgba, int stride, int w, int h, const OrcE
   return n;
 }
 
+// VP8BitWriter over one flat token array (bit | prob << 8): PutBit per token, then Finish (bitio/writer_bool.go:58-150).
+long orc_boolcode(const uint16_t* tokens, unsigned long long n, uint8_t* out, long cap) {
+  BoolWriter bw;
+  for (unsigned long long i = 0; i < n; ++i) bw.put_bit(tokens[i] & 1, tokens[i] >> 8);
+  std::vector<uint8_t> r = bw.finish();
+  if ((long)r.size() > cap) return -1;
+  memcpy(out, r.data(), r.size());
+  return (long)r.size();
+}
+
 // Encode n same-size images on `threads` host threads (bench cpu_baseline / --impl reference).
 // sizes[i] receives each RIFF size; returns total bytes or <0.
 long orc_encode_batch(const uint8_t* rgba, int n, int stride, int w, int h, const OrcEncCfg* cfg, int threads,

@@ -124,6 +124,37 @@ def encode_tokens(rgba, cfg=None):
     return toks[:n].copy(), part[:plen.value].copy()
 
 
+def boolcode(tokens):
+    """VP8BitWriter over a flat token array (uint16 bit | prob << 8): the coded bytes (oracle/capi.cc orc_boolcode)."""
+    L = lib()
+    L.orc_boolcode.restype = C.c_long
+    t = np.ascontiguousarray(tokens, dtype=np.uint16)
+    out = np.empty(len(t) + 64, np.uint8)
+    m = L.orc_boolcode(t.ctypes.data_as(C.c_void_p), C.c_ulonglong(len(t)), out.ctypes.data_as(C.c_void_p), C.c_long(len(out)))
+    if m < 0:
+        raise RuntimeError("orc_boolcode failed")
+    return out[:m].copy()
+
+
+def adversarial_tokens(rng, n, mode):
+    """Token streams that stress the boolean coder beyond what an encoder emits: 0 bits follow the probabilities, 1 improbable bits
+    and extreme probabilities (carries, big shifts, probability 0), 2 long runs of near-certain zeros (few shifts), 3 all ones against
+    tiny probabilities (0xff runs), 4 near-certain zeros only (range states merge slowly: many relaxation rounds), 5 uniform."""
+    if mode == 0:
+        p = rng.integers(1, 256, n); b = (rng.random(n) * 256 >= p)
+    elif mode == 1:
+        p = rng.choice([1, 2, 254, 255, 128, 0], n); b = rng.integers(0, 2, n)
+    elif mode == 2:
+        p = np.full(n, 255); b = rng.random(n) < 0.002
+    elif mode == 3:
+        p = rng.integers(1, 4, n); b = np.ones(n)
+    elif mode == 4:
+        p = rng.integers(250, 256, n); b = np.zeros(n)
+    else:
+        p = rng.integers(0, 256, n); b = rng.integers(0, 2, n)
+    return (np.asarray(b).astype(np.uint16) | (np.asarray(p).astype(np.uint16) << 8)).astype(np.uint16)
+
+
 def encode_batch(rgba_batch, cfg=None, threads=1):
     """rgba_batch uint8 [n][h][w][4]; returns total compressed bytes (timing leg)."""
     rgba_batch = np.ascontiguousarray(rgba_batch, dtype=np.uint8)

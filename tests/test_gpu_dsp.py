@@ -197,3 +197,32 @@ def test_upsample_line_pair(oracle, gpu_ctx, width, channels):
             assert np.array_equal(gt, et)
             if with_bot:
                 assert np.array_equal(gb, eb)
+
+
+def test_boolean_coder_real_and_adversarial_streams(oracle, gpu_ctx):
+    """wgpu_dsp_boolcode_batch (the encoder's chunk-parallel device coder) vs VP8BitWriter over the same tokens: real token partitions,
+    then streams built to break it (probability 0 / 255, carries through 0xff runs, slow-merging range states that need extra
+    relaxation rounds, lengths around the chunk size, an empty partition)."""
+    rng = np.random.default_rng(11)
+    streams = [oracle.encode_tokens(oracle.synth_image(352, 288, 7, kind=2))[0], oracle.encode_tokens(oracle.synth_image(64, 48, 8, kind=1))[0]]
+    for n in (0, 1, 9, 4095, 4096, 8191, 8192, 8193, 20000, 100000):
+        t = oracle.adversarial_tokens(rng, n, int(rng.integers(0, 6)))
+        if n > 9000:
+            cut = int(rng.integers(1, n))
+            t[cut:] = oracle.adversarial_tokens(rng, n - cut, int(rng.integers(0, 6)))
+        streams.append(t)
+    streams.append(oracle.adversarial_tokens(rng, 300000, 4))  # near-certain zeros only: the range states barely merge
+    streams.append(oracle.adversarial_tokens(rng, 200000, 3))
+    got, rounds = dsp.BoolCodeBatch(streams, gpu_ctx)
+    for i, (g, t) in enumerate(zip(got, streams)):
+        assert np.array_equal(g, oracle.boolcode(t)), "stream %d (%d tokens)" % (i, len(t))
+    assert rounds >= 1
+
+
+def test_boolean_coder_many_partitions(oracle, gpu_ctx):
+    rng = np.random.default_rng(12)
+    streams = [oracle.adversarial_tokens(rng, int(rng.integers(0, 40000)), int(rng.integers(0, 6))) for _ in range(300)]
+    got, _ = dsp.BoolCodeBatch(streams, gpu_ctx)
+    for i, (g, t) in enumerate(zip(got, streams)):
+        assert np.array_equal(g, oracle.boolcode(t)), "stream %d (%d tokens)" % (i, len(t))
+

@@ -359,3 +359,57 @@ def test_phased_mode_search_code_on_cpu_matches_oracle(oracle):
         fb = (C.c_int * 4)()
         bad = L.hostcheck_modesearch(img.ctypes.data_as(C.c_void_p), C.c_int(img.strides[0]), w, h, C.byref(cfg), C.c_uint(seed), m, fb)
         assert bad == 0, (w, h, idx, kw, seed, m, list(fb))
+
+
+def _hostcheck():
+    import ctypes as C
+    return C.CDLL(os.path.join(os.path.dirname(DATA), "..", "oracle", "_build", "libhostcheck.so"))
+
+
+def _chunked_boolcode_on_cpu(token_arrays, seed):
+    import ctypes as C
+    L = _hostcheck()
+    totals = np.array([len(t) for t in token_arrays], np.uint64)
+    flat = np.concatenate(list(token_arrays) + [np.zeros(1, np.uint16)]).astype(np.uint16)
+    stride = int(totals.max()) + 64
+    out = np.zeros((len(token_arrays), stride), np.uint8); sizes = np.zeros(len(token_arrays), np.uint32)
+    rounds = L.hostcheck_boolcode_par(flat.ctypes.data_as(C.c_void_p), totals.ctypes.data_as(C.c_void_p), len(token_arrays),
+                                      out.ctypes.data_as(C.c_void_p), C.c_long(stride), sizes.ctypes.data_as(C.c_void_p), C.c_uint(seed))
+    assert rounds > 0
+    return [out[i, :int(sizes[i])] for i in range(len(token_arrays))], rounds
+
+
+def test_chunk_parallel_boolean_coder_code_on_cpu_real_streams(oracle):
+    """webp_b200/csrc/boolcode_par.cuh (the kernels' per-chunk functions, run on the CPU in shuffled chunk order) against the
+    oracle's own token partitions: entry-state relaxation, shift prefix sums, byte pass and boundary joins give the bytes of
+    VP8BitWriter (bitio/writer_bool.go) over the same tokens."""
+    streams, parts = [], []
+    for kind, (w, h) in [(0, (256, 256)), (1, (320, 240)), (2, (352, 288)), (2, (48, 48)), (1, (16, 16))]:
+        t, part = oracle.encode_tokens(oracle.synth_image(w, h, 5 + kind, kind=kind))
+        assert np.array_equal(oracle.boolcode(t), part)  # the flat-array coder is the partition coder
+        streams.append(t); parts.append(part)
+    assert max(len(t) for t in streams) > 3 * 4096  # several chunks in at least one partition
+    for seed in (0, 3):
+        got, _ = _chunked_boolcode_on_cpu(streams, seed)
+        for g, e in zip(got, parts):
+            assert np.array_equal(g, e)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_chunk_parallel_boolean_coder_code_on_cpu_adversarial_streams(oracle, seed):
+    """Streams no encoder emits: probability 0 / 255, improbable bits (carries rippling through 0xff runs across chunk boundaries),
+    near-certain zeros only (range states that merge slowly: many relaxation rounds), lengths around the chunk size."""
+    rng = np.random.default_rng(seed)
+    streams = []
+    for n in (0, 1, 7, 4095, 4096, 8191, 8192, 8193, 12288, 30000, 70000):
+        t = oracle.adversarial_tokens(rng, n, int(rng.integers(0, 6)))
+        if n > 9000:
+            cut = int(rng.integers(1, n))
+            t[cut:] = oracle.adversarial_tokens(rng, n - cut, int(rng.integers(0, 6)))
+        streams.append(t)
+    streams.append(oracle.adversarial_tokens(rng, 50000, 4))
+    streams.append(oracle.adversarial_tokens(rng, 50000, 3))
+    got, rounds = _chunked_boolcode_on_cpu(streams, seed)
+    for g, t in zip(got, streams):
+        assert np.array_equal(g, oracle.boolcode(t))
+

@@ -1,7 +1,8 @@
 // Decoder macroblock parser on the device (sm_100a): intra modes from partition 0 and coefficient tokens from the token
 // partitions, i.e. parseIntraModeRow (internal/lossy/decode_tree.go:35) and parseResiduals / getCoeffs
-// (decode_mb.go:111-313) over the boolean decoder of internal/bitio/reader_bool.go -- SURVEY 8(f) rank 2, the mirror of
-// boolcode_kernel.  The frame HEADERS stay on the host (host_dec.h::parse_frame: a few hundred bits per image); the host
+// (decode_mb.go:111-313) over the boolean decoder of internal/bitio/reader_bool.go -- SURVEY 8(f) rank 2, the mirror of the
+// encoder's boolean coder (whose range recurrence depends on the tokens only and so runs chunk-parallel, boolcode_par.cuh;
+// the decoder's depends on the bits it has yet to decode).  The frame HEADERS stay on the host (host_dec.h::parse_frame: a few hundred bits per image); the host
 // hands over the partition-0 decoder state right after them plus the tables they define (DecHeader).
 //
 // Boolean decoding is a serial chain per partition with data-dependent control flow at every bit, so there is nothing for

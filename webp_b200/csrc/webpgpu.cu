@@ -129,16 +129,14 @@ struct wgpu_ctx {
 
 static int threads_of(const wgpu_ctx* ctx);
 static int getenv_int(const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
-// Where the token partition is boolean-coded.  The coder is one serial chain per partition.  On the GPU the batch's
-// partitions run one per lane on a few dedicated SMs and the batch waits for its longest partition (~40 ns per token); on
-// the host a thread codes ~4 ns per token.  For a batch of at least a warp of partitions the GPU route matches 16 host
-// threads (2336 vs 2339 Mpix/s end to end) and does not depend on the host at all (2365 Mpix/s with 2 threads per context,
-// where host coding gives 443); small batches keep the host's lower latency.  WGPU_DEVICE_CODER=0/1 forces either.
+// Where the token partition is boolean-coded.  On the GPU the coder is chunk-parallel (boolcode_par.cuh: ~4.5 ms for the 480 M
+// tokens of a 256-image batch, 0.3 ms for one 1536x1024 frame), so it is the route for every batch size; the host coder (a
+// thread codes ~4 ns per token) stays for multi-partition frames and as the cross-check WGPU_DEVICE_CODER=0 selects.
 static bool device_coder_wanted(const wgpu_ctx* ctx, size_t n_images) {
   const char* e = getenv("WGPU_DEVICE_CODER");  // read per call: tests flip it
   if (e && *e) return atoi(e) != 0;
-  (void)ctx;
-  return n_images >= 32;  // a full warp of partitions: the GPU coder then matches 16 host threads and leaves the host free
+  (void)ctx; (void)n_images;
+  return true;
 }
 // Where the macroblock data of the decoder is parsed (intra modes + coefficient tokens; the frame headers always on the
 // host).  On the GPU: one warp per image (dec_parse_kernel), 46 MB of compressed bytes up instead of 1.26 GB of
@@ -801,7 +799,8 @@ static int launch_boolcode_par(wgpu_ctx* ctx, const wg::BoolCodeParams& B, const
 }
 // After the stream has drained: if the last queued round still changed an entry state (token streams whose range states
 // merge slowly), keep relaxing -- a round that changes nothing is the exact fixed point -- and redo the passes behind it.
-static int finish_boolcode_par(wgpu_ctx* ctx, wg::BcpParams& BP) {
+static int finish_boolcode_par(wgpu_ctx* ctx, wg::BcpParams& BP, bool* redone) {
+  *redone = false;
   uint32_t* changed = ctx->h_bcp.as<uint32_t>() + BP.n_images + 1;
   int last = kBcpRounds - 1;
   if (changed[last] == 0) return WGPU_OK;
@@ -817,11 +816,8 @@ static int finish_boolcode_par(wgpu_ctx* ctx, wg::BcpParams& BP) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (changed[32] == 0) break;
   }
-  int rc = launch_bcp_tail(ctx, BP);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, (size_t)BP.n_images * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  return WGPU_OK;
+  *redone = true;  // the caller fetches out_size again
+  return launch_bcp_tail(ctx, BP);
 }
 
 static wg::TokenParams token_params(wgpu_ctx* ctx) {
@@ -1244,7 +1240,7 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
     });
   } else if (ctx->e_token_route && device_coder_wanted(ctx, n)) {
-    // ---- single partition: tokens are generated AND boolean-coded on the GPU (token_kernel, boolcode_kernel); the host
+    // ---- single partition: tokens are generated AND boolean-coded on the GPU (token_kernel, boolcode_par.cuh); the host
     // emits partition 0 (modes, a few bits per macroblock) while the coder runs, then lays the frames out
     CK(cudaStreamSynchronize(ctx->stream));  // waves + token pre-pass done, per-image totals on the host
     const double t1 = now_ms();
@@ -1271,30 +1267,10 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     B.tokens = ctx->tokens.as<uint16_t>(); B.img_base = ctx->img_base.as<unsigned long long>(); B.img_total = ctx->img_total.as<unsigned long long>();
     B.out = ctx->coded.as<uint8_t>(); B.out_base = ctx->img_base.as<unsigned long long>() + n; B.out_size = ctx->coded_size.as<unsigned int>();
     B.n_images = (int)n;
-    // WGPU_CODER=chain keeps the one-lane-per-partition coder (a 100-200 ms dependency chain per batch), for comparison
-    static const bool chain_coder = [] { const char* e = getenv("WGPU_CODER"); return e && !strcmp(e, "chain"); }();
     wg::BcpParams BP;
-    bool par_coder = !chain_coder;
-    if (par_coder) {
+    {
       const int rc_par = launch_boolcode_par(ctx, B, totals, n, &BP);
       if (rc_par) return rc_par;
-    } else {
-      // Its blocks (32 partitions each, one per lane) ask for 200 KB of shared memory: that forces the same L1/shared split as
-      // the mode-search CTAs (a kernel with a small footprint gets a different split from the driver and cannot share an SM
-      // with them at all), and it gives each block an SM of its own, where the tight coder loops keep the instruction cache.
-      static const int coder_pairs = std::min((int)wg::BOOLCODE_MAX_PAIRS, std::max(1, getenv_int("WGPU_CODER_PAIRS", 1)));
-      const size_t coder_smem = std::max((size_t)200 * 1024, (size_t)wg::BOOLCODE_SMEM * wg::BOOLCODE_MAX_PAIRS);
-      // per device, so on every call (contexts of one process may sit on different GPUs)
-      CK(cudaFuncSetAttribute(wg::boolcode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coder_smem));
-      int* order = reinterpret_cast<int*>(bases + 2 * n);  // longest first, so that the lanes of a warp finish together
-      for (size_t i = 0; i < n; ++i) order[i] = (int)i;
-      std::sort(order, order + n, [&](int a, int b) { return totals[a] > totals[b] || (totals[a] == totals[b] && a < b); });
-      CK(cudaMemcpyAsync(ctx->img_base.as<unsigned long long>() + 2 * n, order, n * 4, cudaMemcpyHostToDevice, ctx->stream));
-      ctx->xfer_h2d += (uint64_t)(n * 4);
-      B.order = reinterpret_cast<const int*>(ctx->img_base.as<unsigned long long>() + 2 * n);
-      const int per_block = 32 * coder_pairs;
-      wg::boolcode_kernel<<<(unsigned)((n + per_block - 1) / per_block), 64 * coder_pairs, coder_smem, ctx->stream>>>(B);
-      ctx->launches++;
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1308,9 +1284,14 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
     });
     const double t3 = now_ms();
     CK(cudaStreamSynchronize(ctx->stream));
-    if (par_coder) {  // more relaxation rounds if the usual ones were not enough
-      const int rc_par = finish_boolcode_par(ctx, BP);
+    {  // more relaxation rounds if the usual ones were not enough
+      bool redone = false;
+      const int rc_par = finish_boolcode_par(ctx, BP, &redone);
       if (rc_par) return rc_par;
+      if (redone) {
+        CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+      }
     }
     const double t4 = now_ms();
     const unsigned int* csz = ctx->h_coded_size.as<unsigned int>();
@@ -2125,6 +2106,58 @@ int wgpu_dsp_dequant_batch(wgpu_ctx* ctx, int n, const int16_t* in, int dc_q, in
   sq.quant = ac_q; sq.dc_quant = dc_q;
   wg::dsp_dequant_kernel<<<grid, 128, 0, ctx->stream>>>(n, d_in, sq, d_out);
   DSP_END(d_out, out, (size_t)n * 32);
+  DSP_SYNC;
+}
+int wgpu_dsp_boolcode_batch(wgpu_ctx* ctx, int n, const uint16_t* tokens, const unsigned long long* totals, uint8_t* out, size_t out_stride,
+                            unsigned int* sizes, int* rounds) {
+  DSP_BEGIN;
+  (void)grid;
+  if (!tokens || !totals || !out || !sizes) FAIL(WGPU_ERR_INVALID, "wgpu_dsp_boolcode_batch: null argument");
+  std::vector<unsigned long long> bases(2 * (size_t)n);
+  unsigned long long all = 0, oall = 0, src = 0;
+  for (int i = 0; i < n; ++i) {
+    if (totals[i] + 32 > out_stride * 8ull) FAIL(WGPU_ERR_TOO_SMALL, "wgpu_dsp_boolcode_batch: out_stride below a partition's worst case");
+    bases[i] = all; all += (totals[i] + 7) & ~7ull;
+    bases[n + i] = oall; oall += (totals[i] + 16 + 15) & ~15ull;
+  }
+  uint16_t* d_tok = reinterpret_cast<uint16_t*>(S.get((size_t)(all + 512) * 2));
+  uint8_t* d_out = reinterpret_cast<uint8_t*>(S.get((size_t)oall + 64));
+  unsigned long long* d_base = reinterpret_cast<unsigned long long*>(S.get((size_t)n * 24));
+  unsigned int* d_size = reinterpret_cast<unsigned int*>(S.get((size_t)n * 4));
+  if (!d_tok || !d_out || !d_base || !d_size) FAIL(WGPU_ERR_NOMEM, "dsp batch: device allocation failed");
+  for (int i = 0; i < n; ++i) {
+    if (totals[i]) CK(cudaMemcpyAsync(d_tok + bases[i], tokens + src, (size_t)totals[i] * 2, cudaMemcpyHostToDevice, ctx->stream));
+    src += totals[i];
+  }
+  CK(cudaMemcpyAsync(d_base, bases.data(), (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_base + 2 * n, totals, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  wg::BoolCodeParams B;
+  B.tokens = d_tok; B.img_base = d_base; B.img_total = d_base + 2 * n; B.out = d_out; B.out_base = d_base + n; B.out_size = d_size; B.n_images = n;
+  wg::BcpParams BP;
+  int rc = launch_boolcode_par(ctx, B, totals, (size_t)n, &BP);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(sizes, d_size, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int extra = 0;
+  {
+    const uint32_t* changed = ctx->h_bcp.as<uint32_t>() + n + 1;
+    int used = 0;
+    for (int r = 0; r < kBcpRounds; ++r) if (changed[r]) used = r + 1;
+    extra = used;
+    const unsigned launches0 = (unsigned)ctx->launches;
+    bool redone = false;
+    if ((rc = finish_boolcode_par(ctx, BP, &redone))) return rc;
+    if (redone) {
+      extra = kBcpRounds + (int)(ctx->launches - launches0) - 3;
+      CK(cudaMemcpyAsync(sizes, d_size, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  if (rounds) *rounds = extra;
+  for (int i = 0; i < n; ++i) {
+    if (sizes[i] > out_stride) FAIL(WGPU_ERR_TOO_SMALL, "wgpu_dsp_boolcode_batch: out_stride too small");
+    if (sizes[i]) CK(cudaMemcpyAsync(out + (size_t)i * out_stride, d_out + bases[n + i], sizes[i], cudaMemcpyDeviceToHost, ctx->stream));
+  }
   DSP_SYNC;
 }
 int wgpu_dsp_ftransform2_batch(wgpu_ctx* ctx, int n, const uint8_t* src, const uint8_t* ref, int16_t* out) {

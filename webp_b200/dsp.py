@@ -207,3 +207,19 @@ def UpsampleLinePairBatch(top_y, bot_y, top_u, top_v, bot_u, bot_v, channels=3, 
     ctx.check(native.lib().wgpu_dsp_upsample_line_pair_batch(ctx.handle, n, width, top_y.ctypes.data, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4],
                                                              ptr[5], ptr[6], channels, td.ctypes.data, bd.ctypes.data))
     return td, (bd if bot_y is not None else None)
+
+
+def BoolCodeBatch(token_arrays, ctx=None):
+    """bitio VP8BitWriter (writer_bool.go:58-150) over n flat token arrays (uint16 bit | prob << 8, encode_token.go:20): PutBit per
+    token + Finish, coded chunk-parallel on the device.  Returns (list of coded partitions, relaxation rounds used)."""
+    ctx = _ctx(ctx)
+    arrs = [_c(a, np.uint16) for a in token_arrays]
+    n = len(arrs)
+    totals = np.array([len(a) for a in arrs], np.uint64)
+    flat = np.concatenate(arrs + [np.zeros(1, np.uint16)])
+    stride = int(totals.max()) + 64
+    out = np.zeros((n, stride), np.uint8); sizes = np.zeros(n, np.uint32)
+    rounds = C.c_int(0)
+    ctx.check(native.lib().wgpu_dsp_boolcode_batch(ctx.handle, n, flat.ctypes.data, totals.ctypes.data, out.ctypes.data, stride, sizes.ctypes.data,
+                                                   C.byref(rounds)))
+    return [out[i, :int(sizes[i])].copy() for i in range(n)], int(rounds.value)

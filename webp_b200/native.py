@@ -102,6 +102,7 @@ def lib():
         L.wgpu_dsp_dec_transform_batch.argtypes = [vp, C.c_int, C.c_int, i16p, u8p, u8p]
         L.wgpu_dsp_filter_batch.argtypes = [vp, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p]
         L.wgpu_dsp_upsample_line_pair_batch.argtypes = [vp, C.c_int, C.c_int] + [u8p] * 8 + [C.c_int, u8p, u8p]
+        L.wgpu_dsp_boolcode_batch.argtypes = [vp, C.c_int, vp, vp, u8p, sz, vp, C.POINTER(C.c_int)]
         L.wgpu_dec_reconstruct.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, u8p, C.c_int]
         L.wgpu_enc_stats.argtypes = [vp, C.c_int, vp]
         L.wgpu_cleanup_transparent.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, sz, u8p]
