@@ -16,6 +16,7 @@
 #include "misc_kernels.cuh"
 #include "token_kernels.cuh"
 #include "boolcode_par.cuh"
+#include "part0_kernels.cuh"
 #include "enc_phased.cuh"
 #include "dec_parse.cuh"
 #include "sharp_kernels.cuh"
@@ -84,9 +85,9 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, ctxw_uv, derr, dither_y, dither_uv, hdr, coeffs, stats, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, bcp_work, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, ctxw_uv, derr, dither_y, dither_uv, hdr, coeffs, stats, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, bcp_work, p0_plan, p0_info, p0_mb_tokens, p0_mb_offset, p0_total, t_i4paths, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
   DevBuf sharp_best_y, sharp_target_y, sharp_best_uv, sharp_target_uv, t_sharp;  // SharpYUV import working planes + gamma tables
-  PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens, h_bcp;
+  PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens, h_bcp, h_p0;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false, e_keep_derr = false, e_keep_stats = false;
   int dither_w = 0, dither_h = 0, dither_amp_cached = 0;  // what the device dither tables currently hold
@@ -216,6 +217,8 @@ int wgpu_ctx_create(int device_ordinal, wgpu_ctx** out) {
   rc |= upload_table(ctx, ctx->t_lfc, wgh::kLevelFixedCosts, sizeof(wgh::kLevelFixedCosts));
   rc |= upload_table(ctx, ctx->t_proba0, wgh::kCoeffsProba0, sizeof(wgh::kCoeffsProba0));
   rc |= upload_table(ctx, ctx->t_bmodes, wgh::kBModesProba, sizeof(wgh::kBModesProba));
+  static_assert(sizeof(wg::I4PathDev) == sizeof(wgh::I4Path), "I4Path layout");
+  rc |= upload_table(ctx, ctx->t_i4paths, wgh::i4_paths(), 10 * sizeof(wgh::I4Path));
   rc |= upload_table(ctx, ctx->t_upd, wgh::kCoeffsUpdateProba, sizeof(wgh::kCoeffsUpdateProba));
   rc |= upload_table(ctx, ctx->t_ecost, wgh::kEntropyCost, sizeof(wgh::kEntropyCost));
   rc |= upload_table(ctx, ctx->t_i4cost, i4costs, sizeof(i4costs));
@@ -230,14 +233,14 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->ctxw_uv, &ctx->derr, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->bcp_work, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
+  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->ctxw_uv, &ctx->derr, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->bcp_work, &ctx->p0_plan, &ctx->p0_info, &ctx->p0_mb_tokens, &ctx->p0_mb_offset, &ctx->p0_total, &ctx->t_i4paths, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_streams, &ctx->d_hdrs, &ctx->d_perr, &ctx->t_bmodes, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
                   &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
                   &ctx->m_sse, &ctx->m_ssim};
   for (DevBuf* b : db) b->release();
-  PinBuf* pb[] = {&ctx->h_stats_cuts, &ctx->hd_streams, &ctx->hd_hdrs, &ctx->hd_perr, &ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_bcp, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
+  PinBuf* pb[] = {&ctx->h_stats_cuts, &ctx->hd_streams, &ctx->hd_hdrs, &ctx->hd_perr, &ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_bcp, &ctx->h_p0, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
                   &ctx->hd_meta, &ctx->hd_ftype, &ctx->hd_planes, &ctx->hd_nrgba};
   for (PinBuf* b : pb) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -744,7 +747,7 @@ static int enc_reserve(wgpu_ctx* ctx) {
   RESERVE(ctx->stats, n * wg::STATS_SIZE * 4); RESERVE(ctx->h_stats, n * wg::STATS_SIZE * 4);
   RESERVE(ctx->proba, n * 1056); RESERVE(ctx->h_proba, n * 1056);
   RESERVE(ctx->mb_tokens, n * nmb * 4); RESERVE(ctx->mb_offset, n * nmb * 8);
-  RESERVE(ctx->img_total, n * 8); RESERVE(ctx->img_base, 3 * n * 8); RESERVE(ctx->h_totals, n * 8); RESERVE(ctx->h_bases, 3 * n * 8);
+  RESERVE(ctx->img_total, n * 8); RESERVE(ctx->img_base, 6 * n * 8); RESERVE(ctx->h_totals, n * 8); RESERVE(ctx->h_bases, 6 * n * 8);
   RESERVE(ctx->coded_size, n * 4); RESERVE(ctx->h_coded_size, n * 4);
   RESERVE(ctx->h_alpha, n * nmb); RESERVE(ctx->h_uv_alpha, n * nmb); RESERVE(ctx->h_segment, n * nmb);
   RESERVE(ctx->h_params, n * sizeof(wg::ImageParams));
@@ -829,6 +832,16 @@ static wg::TokenParams token_params(wgpu_ctx* ctx) {
   T.n_images = ctx->e_n; T.mb_w = ctx->e_mbw; T.mb_h = ctx->e_mbh;
   return T;
 }
+static wg::P0Params p0_params(wgpu_ctx* ctx) {
+  wg::P0Params Q;
+  Q.hdr = ctx->hdr.as<uint8_t>(); Q.segment = ctx->segment.as<uint8_t>(); Q.proba = ctx->proba.as<uint8_t>();
+  Q.proba0 = ctx->t_proba0.as<uint8_t>(); Q.update = ctx->t_upd.as<uint8_t>(); Q.bmodes = ctx->t_bmodes.as<uint8_t>();
+  Q.i4paths = ctx->t_i4paths.as<wg::I4PathDev>(); Q.plan = ctx->p0_plan.as<wg::P0Plan>(); Q.info = ctx->p0_info.as<uint32_t>();
+  Q.mb_tokens = ctx->p0_mb_tokens.as<uint32_t>(); Q.mb_offset = ctx->p0_mb_offset.as<unsigned long long>();
+  Q.img_base = ctx->img_base.as<unsigned long long>() + ctx->e_n; Q.tokens = ctx->tokens.as<uint16_t>();
+  Q.n_images = ctx->e_n; Q.mb_w = ctx->e_mbw; Q.mb_h = ctx->e_mbh;
+  return Q;
+}
 // Single-partition route, device part 1 (queued right behind the waves): final probabilities from the token statistics,
 // tokens per macroblock, per-image prefix sums and totals.
 static int enc_launch_token_prepass(wgpu_ctx* ctx, bool run_optimize = true) {
@@ -848,6 +861,39 @@ static int enc_launch_token_prepass(wgpu_ctx* ctx, bool run_optimize = true) {
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ctx->h_totals.p, ctx->img_total.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   ctx->xfer_d2h += (uint64_t)((size_t)n * 8);
+  // partition 0 as tokens (part0_kernels.cuh): counts now, so that their totals reach the host with the others
+  if (ctx->plans.size() == (size_t)n) {
+    RESERVE(ctx->p0_plan, (size_t)n * sizeof(wg::P0Plan)); RESERVE(ctx->p0_info, (size_t)n * 16);
+    RESERVE(ctx->p0_mb_tokens, (size_t)n * nmb * 4); RESERVE(ctx->p0_mb_offset, (size_t)n * nmb * 8); RESERVE(ctx->p0_total, (size_t)n * 8);
+    RESERVE(ctx->h_p0, (size_t)n * (sizeof(wg::P0Plan) + 16 + 8));
+    wg::P0Plan* hp = ctx->h_p0.as<wg::P0Plan>();
+    for (int i = 0; i < n; ++i) {
+      const wgh::FramePlan& fp = ctx->plans[i];
+      wg::P0Plan& d = hp[i];
+      memset(&d, 0, sizeof(d));
+      d.seg_use = fp.seg_use; d.seg_update_map = fp.seg_update_map; d.f_simple = fp.f_simple; d.f_level = (uint8_t)fp.f_level;
+      d.f_sharpness = (uint8_t)fp.f_sharpness; d.parts_code = (uint8_t)(fp.num_parts == 8 ? 3 : fp.num_parts == 4 ? 2 : fp.num_parts == 2 ? 1 : 0);
+      d.base_quant = (uint8_t)fp.seg[0].quant;
+      for (int k = 0; k < 4; ++k) { d.seg_quantizer[k] = fp.seg_quantizer[k]; d.seg_fstrength[k] = fp.seg_fstrength[k]; }
+      for (int k = 0; k < 3; ++k) d.seg_proba[k] = fp.seg_proba[k];
+      d.dq_uv_dc = (int16_t)fp.dq_uv_dc; d.dq_uv_ac = (int16_t)fp.dq_uv_ac;
+    }
+    CK(cudaMemcpyAsync(ctx->p0_plan.p, hp, (size_t)n * sizeof(wg::P0Plan), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)((size_t)n * sizeof(wg::P0Plan));
+    const wg::P0Params Q = p0_params(ctx);
+    wg::p0_info_kernel<<<n, 256, 0, ctx->stream>>>(Q);
+    wg::p0_mb_kernel<false><<<dim3((unsigned)((nmb + 127) / 128), (unsigned)n), 128, 0, ctx->stream>>>(Q);
+    wg::TokenParams S = T;  // the same scan over the partition-0 counts
+    S.mb_tokens = ctx->p0_mb_tokens.as<uint32_t>(); S.mb_offset = ctx->p0_mb_offset.as<unsigned long long>();
+    S.img_total = ctx->p0_total.as<unsigned long long>();
+    wg::token_scan_kernel<<<n, 256, 0, ctx->stream>>>(S);
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    uint8_t* hb = ctx->h_p0.as<uint8_t>() + (size_t)n * sizeof(wg::P0Plan);
+    CK(cudaMemcpyAsync(hb, ctx->p0_info.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hb + (size_t)n * 16, ctx->p0_total.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)((size_t)n * 24);
+  }
   return WGPU_OK;
 }
 
@@ -1240,80 +1286,70 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       memcpy(out + (size_t)i * out_stride, riff.data(), riff.size());
     });
   } else if (ctx->e_token_route && device_coder_wanted(ctx, n)) {
-    // ---- single partition: tokens are generated AND boolean-coded on the GPU (token_kernel, boolcode_par.cuh); the host
-    // emits partition 0 (modes, a few bits per macroblock) while the coder runs, then lays the frames out
+    // ---- single token partition: the tokens of BOTH partitions of a frame are generated and boolean-coded on the GPU
+    // (token_kernel, part0_kernels.cuh, boolcode_par.cuh); the host only lays the frames out around the coded partitions
     CK(cudaStreamSynchronize(ctx->stream));  // waves + token pre-pass done, per-image totals on the host
     const double t1 = now_ms();
-    const unsigned long long* totals = ctx->h_totals.as<unsigned long long>();
-    unsigned long long* bases = ctx->h_bases.as<unsigned long long>();  // [0, n): token offsets, [n, 2n): coded byte offsets, [2n, ..): order
+    const unsigned long long* main_totals = ctx->h_totals.as<unsigned long long>();
+    const uint32_t* p0_info = reinterpret_cast<const uint32_t*>(ctx->h_p0.as<uint8_t>() + n * sizeof(wg::P0Plan));
+    const unsigned long long* p0_mb_total = reinterpret_cast<const unsigned long long*>(ctx->h_p0.as<uint8_t>() + n * (sizeof(wg::P0Plan) + 16));
+    // coder partitions: [0, n) the token partition of image i, [n, 2n) partition 0 of image i - n
+    unsigned long long* bases = ctx->h_bases.as<unsigned long long>();  // [0, 2n) token offsets, [2n, 4n) coded byte offsets, [4n, 6n) totals
+    unsigned long long* totals = bases + 4 * n;
     unsigned long long all = 0, oall = 0;
-    for (size_t i = 0; i < n; ++i) {
-      bases[i] = all; all += (totals[i] + 7) & ~7ull;                    // 128-bit aligned token runs
-      bases[n + i] = oall; oall += (totals[i] + 16 + 15) & ~15ull;        // <= 7 bits out per token + the closing flush
+    for (size_t k = 0; k < 2 * n; ++k) {
+      totals[k] = k < n ? main_totals[k] : (unsigned long long)p0_info[(k - n) * 4 + 2] + p0_mb_total[k - n];
+      bases[k] = all; all += (totals[k] + 7) & ~7ull;                        // 128-bit aligned token runs
+      bases[2 * n + k] = oall; oall += (totals[k] + 16 + 15) & ~15ull;        // <= 7 bits out per token + the closing flush
     }
     RESERVE(ctx->tokens, (size_t)(all + 512) * 2);
     RESERVE(ctx->coded, (size_t)oall);
-    CK(cudaMemcpyAsync(ctx->h_hdr.p, ctx->hdr.p, n * nmb * 48, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->xfer_d2h += (uint64_t)(n * nmb * 48);
-    CK(cudaMemcpyAsync(ctx->h_proba.p, ctx->proba.p, n * 1056, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->xfer_d2h += (uint64_t)(n * 1056);
-    CK(cudaEventRecord(ctx->ev_hdr, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->img_base.p, bases, 2 * n * 8, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->xfer_h2d += (uint64_t)(2 * n * 8);
+    RESERVE(ctx->coded_size, 2 * n * 4); RESERVE(ctx->h_coded_size, 2 * n * 4);
+    CK(cudaMemcpyAsync(ctx->img_base.p, bases, 6 * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)(6 * n * 8);
     const wg::TokenParams T = token_params(ctx);
     wg::token_kernel<true><<<(unsigned)((n * nmb + 15) / 16), 128, 0, ctx->stream>>>(T);
-    ctx->launches++;
+    const wg::P0Params Q = p0_params(ctx);
+    wg::p0_mb_kernel<true><<<dim3((unsigned)((nmb + 127) / 128), (unsigned)n), 128, 0, ctx->stream>>>(Q);
+    ctx->launches += 2;
     wg::BoolCodeParams B;
-    B.tokens = ctx->tokens.as<uint16_t>(); B.img_base = ctx->img_base.as<unsigned long long>(); B.img_total = ctx->img_total.as<unsigned long long>();
-    B.out = ctx->coded.as<uint8_t>(); B.out_base = ctx->img_base.as<unsigned long long>() + n; B.out_size = ctx->coded_size.as<unsigned int>();
-    B.n_images = (int)n;
+    B.tokens = ctx->tokens.as<uint16_t>(); B.img_base = ctx->img_base.as<unsigned long long>(); B.img_total = ctx->img_base.as<unsigned long long>() + 4 * n;
+    B.out = ctx->coded.as<uint8_t>(); B.out_base = ctx->img_base.as<unsigned long long>() + 2 * n; B.out_size = ctx->coded_size.as<unsigned int>();
+    B.n_images = (int)(2 * n);
     wg::BcpParams BP;
     {
-      const int rc_par = launch_boolcode_par(ctx, B, totals, n, &BP);
+      const int rc_par = launch_boolcode_par(ctx, B, totals, 2 * n, &BP);
       if (rc_par) return rc_par;
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->xfer_d2h += (uint64_t)(n * 4);
-    CK(cudaEventSynchronize(ctx->ev_hdr));
-    const double t2 = now_ms();
-    std::vector<std::vector<uint8_t>> part0(n);
-    parallel_for((int)n, threads_of(ctx), [&](int i) {
-      wgh::emit_partition0_of(ctx->plans[i], ctx->h_hdr.as<uint8_t>() + (size_t)i * nmb * 48, ctx->h_segment.as<uint8_t>() + (size_t)i * nmb,
-                              ctx->h_proba.as<uint8_t>() + (size_t)i * 1056, &part0[i]);
-    });
-    const double t3 = now_ms();
+    CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, 2 * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)(2 * n * 4);
     CK(cudaStreamSynchronize(ctx->stream));
     {  // more relaxation rounds if the usual ones were not enough
       bool redone = false;
       const int rc_par = finish_boolcode_par(ctx, BP, &redone);
       if (rc_par) return rc_par;
       if (redone) {
-        CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, 2 * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
       }
     }
     const double t4 = now_ms();
     const unsigned int* csz = ctx->h_coded_size.as<unsigned int>();
-    for (size_t i = 0; i < n; ++i) {  // token partitions go straight to their place in the caller's buffer
-      out_sizes[i] = wgh::frame_file_size(part0[i].size(), csz[i]);
+    for (size_t i = 0; i < n; ++i) {  // both partitions go straight to their place in the caller's buffer
+      const size_t p0 = csz[n + i];
+      out_sizes[i] = wgh::frame_file_size(p0, csz[i]);
       if (out_sizes[i] > out_stride) { too_small.store(1); continue; }
-      if (csz[i]) {
-        CK(cudaMemcpyAsync(out + i * out_stride + 30 + part0[i].size(), ctx->coded.as<uint8_t>() + bases[n + i], csz[i], cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->xfer_d2h += (uint64_t)(csz[i]);
-      }
+      CK(cudaMemcpyAsync(out + i * out_stride + 30, ctx->coded.as<uint8_t>() + bases[2 * n + n + i], p0, cudaMemcpyDeviceToHost, ctx->stream));
+      if (csz[i]) CK(cudaMemcpyAsync(out + i * out_stride + 30 + p0, ctx->coded.as<uint8_t>() + bases[2 * n + i], csz[i], cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->xfer_d2h += (uint64_t)(p0 + csz[i]);
     }
-    parallel_for((int)n, threads_of(ctx), [&](int i) {
-      if (out_sizes[i] > out_stride) return;
-      uint8_t* dst = out + (size_t)i * out_stride;
-      memcpy(dst + 30, part0[i].data(), part0[i].size());
-      wgh::write_frame_headers(ctx->plans[i], dst, part0[i].size(), csz[i]);
-    });
     CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < n; ++i)
+      if (out_sizes[i] <= out_stride) wgh::write_frame_headers(ctx->plans[i], out + i * out_stride, csz[n + i], csz[i]);
     if (trace_on())
-      fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, hdr D2H %.2f ms, partition 0 on host %.2f ms (%d threads), wait coder %.2f ms (%.1f M tokens, longest partition %.2f M), "
-              "frames D2H %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, threads_of(ctx), t4 - t3, (double)all / 1e6,
-              (double)*std::max_element(totals, totals + n) / 1e6, now_ms() - t4);
+      fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, tokens + coder %.2f ms (%.1f M tokens, longest partition %.2f M), frames D2H + headers %.2f ms\n",
+              t1 - t0, t4 - t1, (double)all / 1e6, (double)*std::max_element(totals, totals + 2 * n) / 1e6, now_ms() - t4);
   } else if (ctx->e_token_route) {
     // ---- single partition: tokens are generated on the GPU, the host only boolean-codes flat arrays
     CK(cudaStreamSynchronize(ctx->stream));  // waves + token pre-pass done, per-image totals on the host
