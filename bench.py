@@ -5,8 +5,9 @@
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch of synthetic images:
-  value : encode throughput with the RGBA batch already resident in HBM (import + analysis + host segment plan + mode
-          search; per-macroblock modes/levels left in HBM), CUDA events on the library's stream
+  value : encode throughput with the RGBA batch already resident in HBM: wgpu_enc_device + wgpu_enc_finish, i.e. import +
+          analysis + host segment plan + mode search + token generation + boolean coding of both partitions on the GPU and
+          the WebP files laid out in pinned host memory; CUDA events on the library's stream around the whole sequence
   e2e   : the same batch through the reference-facing call wgpu_encode_batch (webp.Encode's batch twin), spelled as its
           three public stages: pinned host RGBA in, H2D, kernels, coded partitions back, WebP files out
   decode: the streams produced above through wgpu_dec_* / wgpu_decode_batch (parse, recon + loop filter + fancy
@@ -350,7 +351,10 @@ def main():
         go.wait()
         wk.ctx.check(L.wgpu_timer_begin(wk.ctx.handle))
         for _ in range(shares[i]):
+            # the whole job from HBM-resident RGBA to WebP files: mode search, token generation and boolean coding of both
+            # partitions on the device, the coded partitions laid out as files in (pinned) host memory
             wk.ctx.check(L.wgpu_enc_device(wk.ctx.handle, C.byref(opt)))
+            wk.ctx.check(L.wgpu_enc_finish(wk.ctx.handle, wk.h_out, cap, wk.sizes.ctypes.data))
         wk.ctx.check(L.wgpu_timer_end(wk.ctx.handle, C.byref(m)))
         v_ms[i] = m.value
     barrier()
@@ -413,7 +417,8 @@ def main():
               "config": {"workload": cfg["workload"] % n,
                          "batch_per_gpu": n, "l2": "inputs (%.0f MB RGBA per step) exceed the 126 MB L2" % (in_bytes / 1e6),
                          "parallelism": "images sharded across %d GPU(s), no collective" % world,
-                         "batches_in_flight": len(vws)},
+                         "batches_in_flight": len(vws),
+                         "value_region": "wgpu_enc_device + wgpu_enc_finish per step (RGBA resident in HBM -> WebP files in pinned host memory)"},
               "e2e": {"value": e2e, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / K * 1e3,
                       "compressed_bytes_per_step": int(sizes.sum()), "workers_per_gpu": len(workers), "host_threads_per_worker": host_threads,
                       "token_partition_coder": "gpu" if device_coder else "host", "finish_slots": finish_slots, "gpu_slots": args.gpu_slots,
@@ -608,12 +613,15 @@ def main():
                 "stages_ms": stage_ms,
                 "stages_gbs": {k: ALG_BYTES_PER_PX[k] * px_step / (v * 1e-3) / 1e9 for k, v in stage_ms.items()},
                 "hbm_peak_gbs": peak, "hbm_peak_kind": peak_kind}
-    if ops_step:
-        roofline["achieved"] = ops_step / t_two / 1e12
+    if ops_step and t_one > 0:
+        # the kernel's own time: CUDA events around the wave launches of one batch (wgpu_enc_stage_time), nothing else on the GPU
+        roofline["achieved"] = ops_step / t_one / 1e12
         roofline["frac"] = roofline["achieved"] / roofline["peak"]
-        roofline["regime"] = "%d batches' wave sequences in flight (the `value` leg, %.1f ms per step)" % (len(vws), t_two * 1e3)
-        if t_one > 0:
-            roofline["one_batch"] = {"achieved": ops_step / t_one / 1e12, "frac": ops_step / t_one / peak_ops, "ms_per_step": t_one * 1e3}
+        roofline["kernel_ms_per_step"] = t_one * 1e3
+        roofline["avg_launch_us"] = t_one * 1e6 / ((W + 15) // 16 + 2 * ((H + 15) // 16 - 1))
+        # for scale: the same operations over the whole step of the `value` leg (every other kernel, the coder and the file layout inside)
+        roofline["value_leg"] = {"achieved": ops_step / t_two / 1e12, "frac": ops_step / t_two / peak_ops, "ms_per_step": t_two * 1e3,
+                                 "batches_in_flight": len(vws)}
     else:
         roofline["achieved"] = roofline["frac"] = None
         roofline["note"] = "operations not counted for the rate-controlled workload by default (BENCH_COUNT_OPS=1 counts them: three CPU passes per image)"
