@@ -1,6 +1,6 @@
 """Device time and achieved HBM bandwidth of the streaming kernels on the bench workload (CUDA events on the library's stream):
 import (5.5 B/px), analysis (1.5 B/px), SSE+SSIM (2 B/px), fancy upsampling to NRGBA (5.5 B/px).  SURVEY.md 8(d) byte counts.
-  python tools/prof_stream.py [n] [w] [h]"""
+  python tools/prof_stream.py [n] [w] [h] [reps]"""
 import ctypes as C, json, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,6 +10,7 @@ from webp_b200.synth import synth_batch
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 w = int(sys.argv[2]) if len(sys.argv) > 2 else 1536
 h = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
+reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 L = native.lib(); ctx = native.Context(0)
 imgs = synth_batch(n, w, h, distinct=min(n, 12))
 cap = w * h + 65536
@@ -27,6 +28,6 @@ ms = C.c_float()
 mbw, mbh = (w + 15) // 16, (h + 15) // 16
 for sid, name, bpp, px in ((0, "import_rgba_kernel", 5.5, n * w * h), (1, "analysis_kernel", 1.5, n * mbw * mbh * 256), (3, "metrics_kernel SSE+SSIM", 2.0, n * mbw * mbh * 256), (5, "sse_kernel (PSNR only)", 2.0, n * mbw * mbh * 256),
                            (4, "upsample_nrgba_kernel", 5.5, n * w * h)):
-    ctx.check(L.wgpu_enc_stage_time(ctx.handle, C.byref(opt), sid, 5, C.byref(ms)))
+    ctx.check(L.wgpu_enc_stage_time(ctx.handle, C.byref(opt), sid, reps, C.byref(ms)))
     gbs = bpp * px / (ms.value * 1e-3) / 1e9
     print("%-26s %.3f ms  %.0f GB/s algorithmic = %.1f %% of the measured %.0f GB/s  (%.1f Gpix/s)" % (name, ms.value, gbs, 100 * gbs / peak, peak, px / ms.value / 1e6))
