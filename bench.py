@@ -40,7 +40,7 @@ METRIC = "lossy encode & decode Mpix/s (1536x1024 q75 m4), bit-exact"
 CONFIGS = {
     2: dict(w=1536, h=1024, quality=75, method=4, target_psnr=0.0, batch=256, distinct=24, steps=12, e2e_workers=3, value_contexts=2, decode=True,
             metric=METRIC, workload="synthetic 1536x1024 RGBA lossy encode q75 method 4, batch of %d images per GPU (BASELINE configs[1])"),
-    4: dict(w=3840, h=2160, quality=75, method=6, target_psnr=42.0, batch=48, distinct=8, steps=3, e2e_workers=2, value_contexts=1, decode=False,
+    4: dict(w=3840, h=2160, quality=75, method=6, target_psnr=42.0, batch=128, distinct=8, steps=3, e2e_workers=2, value_contexts=1, decode=False,
             metric="lossy encode Mpix/s (3840x2160 m6 TargetPSNR 42), bit-exact",
             workload="synthetic 3840x2160 RGBA lossy encode method 6, TargetPSNR 42 (three serial RD passes), batch of %d images per GPU (BASELINE configs[3])"),
     5: dict(w=256, h=256, quality=80, method=2, target_psnr=0.0, batch=2500, distinct=48, steps=8, e2e_workers=3, value_contexts=2, decode=False,
@@ -182,7 +182,7 @@ def run_reference(args, cfg, rank):
     W, H = cfg["w"], cfg["h"]
     cores = os.cpu_count() or 1
     # images per step: at least one per thread, sized for ~5-20 s per step on this workload
-    sample = {2: max(cores, 8), 4: max(cores // 4, 2), 5: max(16 * cores, 256)}[args.config]
+    sample = {2: max(cores, 8), 4: max(cores, 2), 5: max(16 * cores, 256)}[args.config]
     imgs = synth_batch(sample, W, H, distinct=min(sample, cfg["distinct"]))
     oc = oracle_cfg(cfg)
     for _ in range(1 if args.warmup else 0):
@@ -657,7 +657,7 @@ def main():
     # ---- CPU baseline beside it: the oracle port on this box's host cores, bounded sample, rank 0 at N=1 only
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = {2: max(cores, 8), 4: max(cores // 4, 2), 5: max(16 * cores, 256)}[args.config]
+        sample = {2: max(cores, 8), 4: max(cores, 2), 5: max(16 * cores, 256)}[args.config]
         sub = np.ascontiguousarray(imgs[:sample] if sample <= n else synth_batch(sample, W, H, distinct=cfg["distinct"]))
         t0 = time.perf_counter()
         oracle_lib.encode_batch(sub, oc, threads=cores)
