@@ -163,7 +163,7 @@ def test_encode_bytes_and_decisions(oracle, gpu_ctx, w, h, idxs, kw):
 @pytest.mark.parametrize("w,h,idxs,kw", [(128, 96, [0, 1, 2], {}), (768, 576, [1, 2], {}), (100, 70, [2], dict(Quality=98, Method=6)),
                                           (64, 48, [0, 1], {}), (320, 240, [0, 1, 2, 4, 5, 7, 8], dict(Quality=20))])
 def test_token_partition_coder_routes(oracle, gpu_ctx, monkeypatch, device_coder, w, h, idxs, kw):
-    """The token partition is boolean-coded either on the host (code_token_streams) or on the GPU (boolcode_kernel:
+    """The token partition is boolean-coded either on the host (code_token_streams) or on the GPU (boolcode_par.cuh:
     VP8BitWriter PutBit / Flush / Finish, internal/bitio/writer_bool.go:58-150); both must give the oracle's bytes."""
     monkeypatch.setenv("WGPU_DEVICE_CODER", device_coder)
     o = _opts(**kw)
@@ -458,7 +458,7 @@ def test_round_trip_at_full_size(oracle, gpu_ctx, parser_route):
 
 def test_two_contexts_concurrently_at_bench_size(oracle, monkeypatch):
     """What bench.py times, checked: 64 images 1536x1024 with DEFAULT options (FilterStrength 60, 4 segments, Method 4) through
-    TWO contexts running at the same time on one GPU, token partitions coded on the GPU (boolcode_kernel of one context beside
+    TWO contexts running at the same time on one GPU, token partitions coded on the GPU (the coder kernels of one context beside
     the other context's mode-search waves); then the streams decoded concurrently on both contexts, one per macroblock-parser
     route, with the complex loop filter on.  Files, planes and NRGBA against the oracle."""
     import concurrent.futures as cf

@@ -595,7 +595,7 @@ static inline int count_skips(const uint8_t* mb_hdr, int total) {
   return n;
 }
 
-// Device-coded route: the token partition arrives already boolean-coded (boolcode_kernel); the host emits partition 0
+// Host partition 0 for the routes that do not generate it on the device (part0_kernels.cuh); the host emits partition 0
 // and writes RIFF(20) + frame header(10) around [partition 0][token partition] laid out in place at `dst`.
 static inline void emit_partition0_of(const FramePlan& fp, const uint8_t* mb_hdr, const uint8_t* segment_map, const uint8_t* proba /*[1056]*/,
                                       std::vector<uint8_t>* part0) {
@@ -694,7 +694,7 @@ static inline void serialize_frame(const FramePlan& fp, const uint8_t* mb_hdr /*
                                    const int16_t* mb_coeffs /*[nmb][400]*/, const uint8_t* segment_map,
                                    const uint32_t* stats /*[4][8][3][11][2]*/, std::vector<uint8_t>* riff) {
   const int mb_w = fp.mb_w, mb_h = fp.mb_h, total = mb_w * mb_h;
-  // statistics come from the GPU (encode_wave_kernel step 6b == collectMBStats); only the skip count is taken here
+  // statistics come from the GPU (mb_stats_kernel == collectMBStats); only the skip count is taken here
   const int (*st)[8][3][11][2] = reinterpret_cast<const int (*)[8][3][11][2]>(stats);
   std::vector<uint32_t> top_nz(mb_w);
   std::vector<uint8_t> top_dc(mb_w);
