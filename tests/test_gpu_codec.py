@@ -584,3 +584,36 @@ def test_enc_stats_for_a_host_side_refresh(oracle, gpu_ctx):
     half = stats(nmb // 2)
     assert int(half.sum()) >= int(z.sum()) and int(full.sum()) >= int(half.sum())
     assert L.wgpu_enc_stats(gpu_ctx.handle, nmb + 1, z.ctypes.data) == native.ERR_INVALID
+
+
+def test_context_on_second_device(oracle):
+    """ADVICE: contexts of one process on different GPUs (function attributes and tables are per device).  Needs two GPUs."""
+    import ctypes as C
+    from webp_b200 import native
+    count = C.c_int(0)
+    cudart = None
+    for name in ("libcudart.so", "libcudart.so.12"):
+        try:
+            cudart = C.CDLL(name); break
+        except OSError:
+            continue
+    if cudart is None or cudart.cudaGetDeviceCount(C.byref(count)) != 0 or count.value < 2:
+        pytest.skip("one GPU visible")
+    c0, c1 = native.Context(0), native.Context(1)
+    try:
+        imgs = np.stack([oracle.synth_image(320, 240, i) for i in (0, 1, 2)])
+        o = _opts()
+        f1 = webp_b200.EncodeBatch(imgs, o, c1)
+        f0 = webp_b200.EncodeBatch(imgs, o, c0)
+        o2 = _opts(TargetSize=4000)
+        r1 = webp_b200.EncodeBatch(imgs, o2, c1)
+        for k in range(3):
+            assert f1[k] == f0[k] == oracle.encode(imgs[k], _ocfg(oracle, o))
+            assert r1[k] == oracle.encode(imgs[k], _ocfg(oracle, o2))
+        w, h, y, u, v, rgba = webp_b200.webp.decode_padded(f1, nrgba=True, ctx=c1)
+        for k in range(3):
+            _, _, ey, eu, ev = oracle.decode(f1[k])
+            assert np.array_equal(y[k], ey) and np.array_equal(rgba[k], oracle.build_nrgba(w, h, ey, eu, ev))
+    finally:
+        c0.close(); c1.close()
+

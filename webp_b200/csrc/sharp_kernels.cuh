@@ -9,7 +9,8 @@
 // frame top to bottom and every row pair reads the chroma row above AFTER its update, so row pairs are a serial chain; the
 // samples of one row pair are independent and go across the CTA's threads), sharp_finish (one thread per padded 2x2 block).
 // sharp_refine_ring_kernel is the same sweep with the step's independent operands fetched one row pair ahead and the residual
-// rows in a shared-memory ring (WGPU_SHARP_VARIANT=1; bit-exact, not yet timed).
+// rows in a shared-memory ring: the one the library launches (11.2 vs 17.6 ms per 256 x 1536x1024); sharp_refine_kernel<1024>
+// stays for rows wider than the ring.
 // The per-sample code is host+device so that a CPU test harness can run the same functions in the kernels' schedule.
 #pragma once
 #include <stdint.h>
@@ -155,7 +156,7 @@ WG_SHD bool sharp_stop(int iter, unsigned long long sum, unsigned long long prev
   return iter > 0 && (sum < threshold || sum > prev_sum);
 }
 
-// ---- phase 2, pipelined variant (WGPU_SHARP_VARIANT=1): the operands of a row pair that do not depend on the row pair above it
+// ---- phase 2, pipelined (the default for rows of up to 256 * SHARP_ITEMS chroma samples): the operands of a row pair that do not depend on the row pair above it
 // (its W and target samples, its target residuals, the residual row two below) are fetched one step ahead, and the residual rows
 // live in a 4-slot ring in shared memory (slot = row & 3), so the dependent path of a step has no global-memory round trip.
 struct SharpOperands {

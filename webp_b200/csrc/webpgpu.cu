@@ -536,8 +536,9 @@ static int enc_launch_import_sharp(wgpu_ctx* ctx) {
   P.iterations = nullptr;
   const long long blocks2 = (long long)P.uv_w * P.uv_h * n;
   wg::sharp_init_kernel<<<(unsigned)std::min<long long>((blocks2 + 255) / 256, 148LL * 64), 256, 0, ctx->stream>>>(P);
-  static const int variant = getenv_int("WGPU_SHARP_VARIANT", 0);  // 1: operands fetched a row pair ahead, residual rows in a shared-memory ring (experimental)
-  if (variant == 1 && P.uv_w <= 256 * wg::SHARP_ITEMS) {
+  // refinement: operands fetched a row pair ahead, residual rows in a shared-memory ring (11.2 ms per 256 x 1536x1024 against 17.6 ms
+  // for the plain row-pair sweep, 3.5 vs 5.3 ms for one image); rows wider than the ring take the plain sweep with 1024 threads
+  if (P.uv_w <= 256 * wg::SHARP_ITEMS) {
     const int items = (P.uv_w + 255) / 256;
     if (items <= 1) launch_sharp_ring<1>(P, n, ctx->stream);
     else if (items == 2) launch_sharp_ring<2>(P, n, ctx->stream);
@@ -545,7 +546,7 @@ static int enc_launch_import_sharp(wgpu_ctx* ctx) {
     else if (items == 4) launch_sharp_ring<4>(P, n, ctx->stream);
     else if (items <= 6) launch_sharp_ring<6>(P, n, ctx->stream);
     else launch_sharp_ring<8>(P, n, ctx->stream);
-  } else if (P.uv_w <= 256 * wg::SHARP_ITEMS) wg::sharp_refine_kernel<256><<<(unsigned)n, 256, 0, ctx->stream>>>(P);
+  }
   else wg::sharp_refine_kernel<1024><<<(unsigned)n, 1024, 0, ctx->stream>>>(P);  // up to 8192 chroma samples per row: any WebP width
   const long long blocks3 = (long long)(pad_w / 2) * (pad_h / 2) * n;
   wg::sharp_finish_kernel<<<(unsigned)std::min<long long>((blocks3 + 255) / 256, 148LL * 64), 256, 0, ctx->stream>>>(P);
