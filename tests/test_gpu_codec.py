@@ -277,6 +277,23 @@ def test_rate_control_passes(oracle, gpu_ctx, w, h, idxs, kw):
         assert files[k] == exp, "image %d: bitstream differs (%d vs %d bytes)" % (i, len(files[k]), len(exp))
 
 
+@pytest.mark.parametrize("device_coder", ["0", "1"])
+@pytest.mark.parametrize("w,h,idxs,kw", [
+    (81, 47, [10, 11], dict(Quality=20, TargetSize=8000, Preprocessing=3, SNSStrength=0, FilterStrength=60, FilterSharpness=3, FilterType=0, Pass=1)),
+    (94, 155, [6, 8], dict(Quality=49, Method=5, TargetSize=300, Preprocessing=1, SNSStrength=100, FilterStrength=100, Segments=4)),
+    (100, 70, [5, 7, 2], dict(Quality=20, Method=5, TargetSize=8000, Preprocessing=2, SNSStrength=0, FilterStrength=60, FilterType=0, Segments=4, Pass=1))])
+def test_rate_control_unconverged_last_pass_header(oracle, gpu_ctx, monkeypatch, device_coder, w, h, idxs, kw):
+    """A search that has not converged after its last pass re-derives the segment parameters, and the frame header (partition 0)
+    is written from THAT state while the macroblocks keep the last pass's data.  Found by tools/fuzz_parity.py (seed 7) when
+    partition 0 moved to the device: its segment map has to be the host's final one.  Both coder routes, bytes == oracle."""
+    monkeypatch.setenv("WGPU_DEVICE_CODER", device_coder)
+    o = _opts(**kw)
+    imgs = np.stack([oracle.synth_image(w, h, i) for i in idxs])
+    files = webp_b200.EncodeBatch(imgs, o, gpu_ctx)
+    for k in range(len(idxs)):
+        assert files[k] == oracle.encode(imgs[k], _ocfg(oracle, o)), "image %d" % idxs[k]
+
+
 def test_config4_4k_target_psnr_method6(oracle, gpu_ctx):
     """BASELINE configs[3]: 3840x2160, Method 6, TargetPSNR multi-pass -- three serial RD passes (Q, Q-10, Q-10: the
     reference's PSNR reading is always 99 dB) of 32 400 macroblocks with seven probability refreshes each."""

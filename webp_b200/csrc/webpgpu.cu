@@ -881,6 +881,12 @@ static int enc_launch_token_prepass(wgpu_ctx* ctx, bool run_optimize = true) {
     }
     CK(cudaMemcpyAsync(ctx->p0_plan.p, hp, (size_t)n * sizeof(wg::P0Plan), cudaMemcpyHostToDevice, ctx->stream));
     ctx->xfer_h2d += (uint64_t)((size_t)n * sizeof(wg::P0Plan));
+    if (ctx->e_opt.target_size > 0 || ctx->e_opt.target_psnr > 0.f) {
+      // the rate-control loop re-derives the segment parameters (and with them the map the header codes) after its last pass:
+      // partition 0 is written from the host's final map, as emit_partition0 would
+      CK(cudaMemcpyAsync(ctx->segment.p, ctx->h_segment.p, (size_t)n * nmb, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->xfer_h2d += (uint64_t)((size_t)n * nmb);
+    }
     const wg::P0Params Q = p0_params(ctx);
     wg::p0_info_kernel<<<n, 256, 0, ctx->stream>>>(Q);
     wg::p0_mb_kernel<false><<<dim3((unsigned)((nmb + 127) / 128), (unsigned)n), 128, 0, ctx->stream>>>(Q);
