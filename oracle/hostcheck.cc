@@ -10,8 +10,11 @@
 #include <random>
 #include <chrono>
 
+static long g_bcp_parked = 0;
+#define BCP_NOTE_PARKED() (++g_bcp_parked)
 #include "../webp_b200/csrc/boolcode_par.cuh"
 extern "C" {
+long hostcheck_boolcode_parked() { return g_bcp_parked; }
 struct OrcEncCfg2 {
   int quality, method, sns_strength, filter_strength, filter_sharpness, filter_type, partitions, segments, preprocessing, has_alpha, passes, dither_amp;
 };
@@ -326,10 +329,11 @@ int hostcheck_boolcode_par(const uint16_t* tokens, const unsigned long long* tot
   std::vector<uint32_t> shift(nchunks, 0), bitpos(nchunks, 0), head(nchunks, 0), hcarry(nchunks, 0);
   std::vector<uint16_t> tail(nchunks, 0);
   std::vector<unsigned> changed(4096, 0);
+  std::vector<uint32_t> pending(nchunks, 0xffffffffu), any_pending(n, 0);
   wg::BcpParams P;
   P.tokens = tk.data(); P.img_base = base.data(); P.img_total = totals; P.chunk_first = first.data(); P.n_images = n; P.n_chunks = nchunks;
   P.entry = entry.data(); P.walked = walked.data(); P.shift_total = shift.data(); P.chunk_bit = bitpos.data(); P.head = head.data();
-  P.head_carry = hcarry.data(); P.tail = tail.data(); P.changed = changed.data(); P.round = 0; P.out = out; P.out_base = obase.data();
+  P.head_carry = hcarry.data(); P.tail = tail.data(); P.changed = changed.data(); P.pending = pending.data(); P.any_pending = any_pending.data(); P.round = 0; P.out = out; P.out_base = obase.data();
   P.out_size = sizes;
   std::vector<uint32_t> order(nchunks);
   for (uint32_t k = 0; k < nchunks; ++k) order[k] = k;
@@ -352,7 +356,9 @@ int hostcheck_boolcode_par(const uint16_t* tokens, const unsigned long long* tot
   }
   shuffle();
   for (uint32_t k = 0; k < nchunks; ++k) wg::bcp_bytes_chunk(P, order[k]);
-  for (int i = n - 1; i >= 0; --i) wg::bcp_join_image(P, i);
+  shuffle();
+  for (uint32_t k = 0; k < nchunks; ++k) wg::bcp_join_boundary(P, order[k]);
+  for (int i = 0; i < n; ++i) wg::bcp_join_fix_image(P, i);
   return rounds + 1;
 }
 
@@ -364,5 +370,23 @@ long hostcheck_boolcode_serial(const uint16_t* tokens, unsigned long long n, uin
   if ((long)r.size() > cap) return -1;
   memcpy(out, r.data(), r.size());
   return (long)r.size();
+}
+
+// The boundary join of boolcode_par.cuh on hand-made records (one partition of nch chunks starting at stream bits chunk_bit[]):
+// every boundary in the given order, then the parked ripples.  out holds the bytes the chunks wrote themselves.
+long hostcheck_bcp_join(int nch, const uint32_t* chunk_bit, uint32_t* head, uint32_t* head_carry, const uint16_t* tail, uint8_t* out,
+                        const uint32_t* order) {
+  uint32_t first[2] = {0, (uint32_t)nch};
+  unsigned long long obase = 0, total = 0, tbase = 0;
+  std::vector<uint32_t> pending(nch, 0xffffffffu), any(1, 0);
+  wg::BcpParams P;
+  memset(&P, 0, sizeof(P));
+  P.chunk_first = first; P.n_images = 1; P.n_chunks = (uint32_t)nch; P.img_total = &total; P.img_base = &tbase; P.chunk_bit = const_cast<uint32_t*>(chunk_bit);
+  P.head = head; P.head_carry = head_carry; P.tail = const_cast<uint16_t*>(tail); P.pending = pending.data(); P.any_pending = any.data();
+  P.out = out; P.out_base = &obase;
+  const long parked0 = g_bcp_parked;
+  for (int k = 0; k < nch; ++k) wg::bcp_join_boundary(P, order[k]);
+  wg::bcp_join_fix_image(P, 0);
+  return g_bcp_parked - parked0;
 }
 }

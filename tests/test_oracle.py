@@ -413,3 +413,45 @@ def test_chunk_parallel_boolean_coder_code_on_cpu_adversarial_streams(oracle, se
     for g, t in zip(got, streams):
         assert np.array_equal(g, oracle.boolcode(t))
 
+
+def test_chunk_boundary_join_with_ripples_through_whole_chunks(oracle):
+    """bcp_join_boundary / bcp_join_fix_image (boolcode_par.cuh) on hand-made boundary records: short chunks whose bytes are mostly
+    0xff, so that carries out of a boundary run through a whole chunk into the next boundary zone (the parked-ripple path no real
+    token stream reaches).  Model: the partition is one big integer, the join must write its sum."""
+    import ctypes as C
+    L = _hostcheck()
+    L.hostcheck_bcp_join.restype = C.c_long
+    rng = np.random.default_rng(9)
+    parked_total = 0
+    for trial in range(300):
+        nch = int(rng.integers(2, 12))
+        adv = rng.integers(32, 80, nch)                       # stream bits per chunk (>= 32: what a full chunk guarantees)
+        bits = np.concatenate([[0], np.cumsum(adv)[:-1]]).astype(np.uint32)
+        F = [0 if g == 0 else (int(g) - 8 - (((int(g) - 1) & 7) - 7)) >> 3 for g in bits]
+        nbytes = F[-1] + 6
+        out = np.where(rng.random(nbytes) < 0.8, 0xff, rng.integers(0, 256, nbytes)).astype(np.uint8)
+        out[0] = 0                                           # room for the carries at the top
+        head = np.zeros(nch, np.uint32); hcarry = np.zeros(nch, np.uint32); tail = np.zeros(nch, np.uint16)
+        model = 0
+        zone = set()
+        for c in range(1, nch):
+            zone.update((F[c], F[c] + 1))
+        for j in range(nbytes):
+            if j not in zone:
+                model += int(out[j]) << (8 * (nbytes - 1 - j))
+        for c in range(1, nch):
+            h0, h1 = int(rng.integers(0, 256)), int(rng.integers(0, 256))
+            t0, t1 = int(rng.integers(0, 256)), int(rng.integers(0, 256))
+            hc = int(rng.integers(0, 2))
+            if rng.random() < 0.5:
+                h0, h1, t0, t1 = 0xff, 0xff, 0, 1             # a carry out of the zone with nothing left behind
+            head[c] = h0 | (h1 << 16); hcarry[c] = hc; tail[c - 1] = t0 | (t1 << 8)
+            model += ((hc << 16) + ((h0 + t0) << 8) + h1 + t1) << (8 * (nbytes - 2 - F[c]))
+        order = rng.permutation(nch).astype(np.uint32)
+        got = out.copy()
+        parked_total += L.hostcheck_bcp_join(nch, bits.ctypes.data_as(C.c_void_p), head.ctypes.data_as(C.c_void_p), hcarry.ctypes.data_as(C.c_void_p),
+                                             tail.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), order.ctypes.data_as(C.c_void_p))
+        assert model < (1 << (8 * nbytes))
+        assert int.from_bytes(got.tobytes(), "big") == model, "trial %d" % trial
+    assert parked_total > 20  # the rare path did run
+

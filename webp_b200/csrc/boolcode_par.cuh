@@ -16,7 +16,8 @@
 //                         the bytes only it contributes to; the two bytes it shares with its predecessor's tail (an addend
 //                         is 8 bits wide) and the carry out of its first byte go to a boundary record, as do the two tail
 //                         bytes it leaves in its successor's first bytes.  The last chunk runs Finish.
-//   4. bcp_join_kernel    per partition, last boundary first: tail + head (+ carries), ripple into the bytes above.
+//   4. bcp_join_kernel    every chunk boundary: tail + head (+ carries), ripple into the bytes above; bcp_join_fix_kernel
+//                         applies the rare ripples that ran through a whole chunk.
 // One lane per chunk everywhere: a 256-image batch of 1536x1024 frames is ~220k chunks, i.e. the whole GPU for a few hundred
 // microseconds instead of one 160 ms dependency chain per partition.  BCP_L >= 127 * 32 guarantees that a full chunk shifts
 // by >= 32 bits (the range shrinks with every token until it renormalises, so at most 127 tokens pass without a shift):
@@ -30,6 +31,10 @@
 #define BCP_HD __host__ __device__ __forceinline__
 #else
 #define BCP_HD inline
+#endif
+
+#if !defined(BCP_NOTE_PARKED)
+#define BCP_NOTE_PARKED() ((void)0)  // the CPU test harness counts how often the rare path runs
 #endif
 
 namespace wg {
@@ -52,6 +57,8 @@ struct BcpParams {
   uint32_t* head_carry;                 // [chunks] carries out of the chunk's first byte
   uint16_t* tail;                       // [chunks] t0 | t1 << 8: what the chunk leaves in the first two bytes of the next
   unsigned int* changed;                // [rounds] entries changed in each relaxation round
+  uint32_t* pending;                    // [chunks] a ripple parked at the chunk's boundary zone: byte index << 2 | carry
+  uint32_t* any_pending;                // [n] the partition has parked ripples (zeroed with `changed`)
   int round;
   uint8_t* out;                         // coded partitions
   const unsigned long long* out_base;   // [n] byte offset of each partition in `out`
@@ -101,19 +108,31 @@ BCP_HD void bcp_grid_at(uint32_t G, int* nb_bits, uint32_t* flushed) {
   *flushed = (uint32_t)(((long long)G - 8 - *nb_bits) >> 3);
 }
 
-// walk tokens [lo, hi) of a partition from R: exit state and total shift
+// eight tokens (one 128-bit load on the device)
+struct BcpGroup { uint32_t x, y, z, w; };
+BCP_HD BcpGroup bcp_load8(const uint16_t* tk, unsigned long long i) {
+  BcpGroup q;
+#if defined(__CUDA_ARCH__)
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(tk + i));
+  q.x = v.x; q.y = v.y; q.z = v.z; q.w = v.w;
+#else
+  q.x = tk[i] | ((uint32_t)tk[i + 1] << 16); q.y = tk[i + 2] | ((uint32_t)tk[i + 3] << 16);
+  q.z = tk[i + 4] | ((uint32_t)tk[i + 5] << 16); q.w = tk[i + 6] | ((uint32_t)tk[i + 7] << 16);
+#endif
+  return q;
+}
+// walk tokens [lo, hi) of a partition from R: exit state and total shift.  lo is a multiple of 8; the group after the one
+// being walked is already in flight (a lane's loads are 8 KB apart from its neighbours': nothing coalesces, latency is all)
 BCP_HD void bcp_walk(const uint16_t* tk, unsigned long long lo, unsigned long long hi, int* R_io, uint32_t* shift_out) {
   int R = *R_io;
   uint32_t S = 0;
   unsigned long long i = lo;
-  for (; i + 8 <= hi && (i & 7) == 0; i += 8) {
-#if defined(__CUDA_ARCH__)
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(tk + i));
-#else
-    struct { uint32_t x, y, z, w; } q;
-    q.x = tk[i] | ((uint32_t)tk[i + 1] << 16); q.y = tk[i + 2] | ((uint32_t)tk[i + 3] << 16);
-    q.z = tk[i + 4] | ((uint32_t)tk[i + 5] << 16); q.w = tk[i + 6] | ((uint32_t)tk[i + 7] << 16);
-#endif
+  const unsigned long long full = lo + ((hi - lo) & ~7ull);
+  BcpGroup nxt = {0, 0, 0, 0};
+  if (i < full) nxt = bcp_load8(tk, i);
+  for (; i < full; i += 8) {
+    const BcpGroup q = nxt;
+    if (i + 8 < full) nxt = bcp_load8(tk, i + 8);
     S += bcp_step(R, q.x & 0xffffu, nullptr); S += bcp_step(R, q.x >> 16, nullptr);
     S += bcp_step(R, q.y & 0xffffu, nullptr); S += bcp_step(R, q.y >> 16, nullptr);
     S += bcp_step(R, q.z & 0xffffu, nullptr); S += bcp_step(R, q.z >> 16, nullptr);
@@ -212,14 +231,12 @@ BCP_HD void bcp_bytes_chunk(const BcpParams& P, uint32_t ck) {
   W.out = P.out + P.out_base[img];
   int R = c > 0 ? (int)P.entry[ck] : 255;
   unsigned long long i = lo;
-  for (; i + 8 <= hi && (i & 7) == 0; i += 8) {
-#if defined(__CUDA_ARCH__)
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(tk + i));
-#else
-    struct { uint32_t x, y, z, w; } q;
-    q.x = tk[i] | ((uint32_t)tk[i + 1] << 16); q.y = tk[i + 2] | ((uint32_t)tk[i + 3] << 16);
-    q.z = tk[i + 4] | ((uint32_t)tk[i + 5] << 16); q.w = tk[i + 6] | ((uint32_t)tk[i + 7] << 16);
-#endif
+  const unsigned long long full = lo + ((hi - lo) & ~7ull);
+  BcpGroup nxt = {0, 0, 0, 0};
+  if (i < full) nxt = bcp_load8(tk, i);
+  for (; i < full; i += 8) {
+    const BcpGroup q = nxt;
+    if (i + 8 < full) nxt = bcp_load8(tk, i + 8);
     uint32_t a; int s;
     s = bcp_step(R, q.x & 0xffffu, &a); W.put(a, s); s = bcp_step(R, q.x >> 16, &a); W.put(a, s);
     s = bcp_step(R, q.y & 0xffffu, &a); W.put(a, s); s = bcp_step(R, q.y >> 16, &a); W.put(a, s);
@@ -247,30 +264,48 @@ BCP_HD void bcp_bytes_chunk(const BcpParams& P, uint32_t ck) {
   P.head_carry[ck] = W.head_carry;
 }
 
-// ---- 4. boundaries of one partition, last first
-BCP_HD void bcp_join_image(const BcpParams& P, int img) {
+// ---- 4. the boundary between chunk ck - 1 and chunk ck (ck is not the first chunk of its partition): tail + head + carries
+// give the two shared bytes; what is left over ripples into the bytes above, which belong to chunk ck - 1 alone down to ITS
+// boundary zone -- a ripple that gets that far (a chunk-long run of 0xff) is parked in pending[ck - 1] and applied once every
+// boundary byte is in memory (bcp_join_fix_image), so that all boundaries can be resolved side by side.
+BCP_HD void bcp_join_boundary(const BcpParams& P, uint32_t ck) {
+  const int img = bcp_image_of(P.chunk_first, P.n_images, ck);
+  const uint32_t first = P.chunk_first[img], c = ck - first;
+  if (c == 0) return;
+  uint8_t* out = P.out + P.out_base[img];
+  int nb; uint32_t F;
+  bcp_grid_at(P.chunk_bit[ck], &nb, &F);
+  const uint32_t hd = P.head[ck], tl = P.tail[ck - 1];
+  const uint32_t x1 = (tl >> 8) + (hd >> 16);
+  const uint32_t x0 = (tl & 0xffu) + (hd & 0xffffu) + (x1 >> 8);
+  uint32_t cy = (x0 >> 8) + P.head_carry[ck];
+  out[F] = (uint8_t)x0;
+  out[F + 1] = (uint8_t)x1;
+  uint32_t lo_zone = 0;
+  const bool zone = c - 1 > 0;
+  if (zone) { int nb2; bcp_grid_at(P.chunk_bit[ck - 1], &nb2, &lo_zone); }
+  uint32_t p = F - 1, parked = 0;
+  while (cy) {
+    if (zone && p < lo_zone + 2) { parked = (p << 2) | cy; BCP_NOTE_PARKED(); break; }
+    const uint32_t b = out[p] + cy;
+    out[p] = (uint8_t)b;
+    cy = b >> 8;
+    if (p == 0) break;
+    --p;
+  }
+  P.pending[ck - 1] = parked;
+  if (parked) P.any_pending[img] = 1u;
+}
+// the parked ripples of one partition: plain big-number carries now that every byte is in memory
+BCP_HD void bcp_join_fix_image(const BcpParams& P, int img) {
+  if (!P.any_pending[img]) return;
   const uint32_t first = P.chunk_first[img], nch = P.chunk_first[img + 1] - first;
   uint8_t* out = P.out + P.out_base[img];
-  for (uint32_t c = nch - 1; c >= 1; --c) {
-    const uint32_t ck = first + c;
-    int nb; uint32_t F;
-    bcp_grid_at(P.chunk_bit[ck], &nb, &F);
-    const uint32_t hd = P.head[ck], tl = P.tail[ck - 1];
-    const uint32_t x1 = (tl >> 8) + (hd >> 16);
-    const uint32_t x0 = (tl & 0xffu) + (hd & 0xffffu) + (x1 >> 8);
-    uint32_t cy = (x0 >> 8) + P.head_carry[ck];
-    out[F] = (uint8_t)x0;
-    out[F + 1] = (uint8_t)x1;
-    // ripple into the bytes above: memory down to the head zone of the chunk above, whose record takes the rest
-    uint32_t lo_zone = 0;
-    const bool zone = c - 1 > 0;
-    if (zone) { int nb2; bcp_grid_at(P.chunk_bit[ck - 1], &nb2, &lo_zone); }
-    uint32_t p = F - 1;
+  for (uint32_t c = nch - 1; c-- > 1;) {  // chunks nch - 2 .. 1 can hold a parked ripple
+    const uint32_t v = P.pending[first + c];
+    if (!v) continue;
+    uint32_t p = v >> 2, cy = v & 3u;
     while (cy) {
-      if (zone && p < lo_zone + 2) {
-        if (p >= lo_zone) P.head[ck - 1] += cy << (16 * (p - lo_zone)); else P.head_carry[ck - 1] += cy;
-        break;
-      }
       const uint32_t b = out[p] + cy;
       out[p] = (uint8_t)b;
       cy = b >> 8;
@@ -305,9 +340,13 @@ __global__ void __launch_bounds__(128) bcp_bytes_kernel(const BcpParams P) {
   const uint32_t ck = blockIdx.x * blockDim.x + threadIdx.x;
   if (ck < P.n_chunks) bcp_bytes_chunk(P, ck);
 }
-__global__ void __launch_bounds__(64) bcp_join_kernel(const BcpParams P) {
+__global__ void __launch_bounds__(128) bcp_join_kernel(const BcpParams P) {
+  const uint32_t ck = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ck < P.n_chunks) bcp_join_boundary(P, ck);
+}
+__global__ void __launch_bounds__(64) bcp_join_fix_kernel(const BcpParams P) {
   const int img = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (img < P.n_images) bcp_join_image(P, img);
+  if (img < P.n_images) bcp_join_fix_image(P, img);
 }
 #endif
 

@@ -763,8 +763,9 @@ static int launch_bcp_tail(wgpu_ctx* ctx, const wg::BcpParams& BP) {
   const unsigned cb = (BP.n_chunks + 127) / 128;
   wg::bcp_scan_kernel<<<(unsigned)((BP.n_images * 32 + 127) / 128), 128, 0, ctx->stream>>>(BP);
   wg::bcp_bytes_kernel<<<cb, 128, 0, ctx->stream>>>(BP);
-  wg::bcp_join_kernel<<<(unsigned)((BP.n_images + 63) / 64), 64, 0, ctx->stream>>>(BP);
-  ctx->launches += 3;
+  wg::bcp_join_kernel<<<cb, 128, 0, ctx->stream>>>(BP);
+  wg::bcp_join_fix_kernel<<<(unsigned)((BP.n_images + 63) / 64), 64, 0, ctx->stream>>>(BP);
+  ctx->launches += 4;
   CK(cudaGetLastError());
   return WGPU_OK;
 }
@@ -774,18 +775,20 @@ static int launch_boolcode_par(wgpu_ctx* ctx, const wg::BoolCodeParams& B, const
   uint32_t nchunks = 0;
   for (size_t i = 0; i < n; ++i) { first[i] = nchunks; nchunks += wg::bcp_chunks_of(totals[i]); }
   first[n] = nchunks;
-  // device work area: chunk_first [n + 1] | changed [64] | shift, bit, head, head_carry [chunks] x 4 B | tail x 2 B | entry, walked x 1 B
-  const size_t head_words = n + 1 + 64;
-  RESERVE(ctx->bcp_work, head_words * 4 + (size_t)nchunks * (16 + 2 + 2) + 64);
+  // device work area: chunk_first [n + 1] | changed [64] | any_pending [n] | shift, bit, head, head_carry, pending [chunks] x 4 B |
+  // tail x 2 B | entry, walked x 1 B
+  const size_t head_words = n + 1 + 64 + n;
+  RESERVE(ctx->bcp_work, head_words * 4 + (size_t)nchunks * (20 + 2 + 2) + 64);
   uint32_t* w = ctx->bcp_work.as<uint32_t>();
   CK(cudaMemcpyAsync(w, first, (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   ctx->xfer_h2d += (uint64_t)((n + 1) * 4);
-  CK(cudaMemsetAsync(w + n + 1, 0, 64 * 4, ctx->stream));
+  CK(cudaMemsetAsync(w + n + 1, 0, (64 + n) * 4, ctx->stream));
   wg::BcpParams BP;
   BP.tokens = B.tokens; BP.img_base = B.img_base; BP.img_total = B.img_total; BP.chunk_first = w; BP.n_images = (int)n; BP.n_chunks = nchunks;
-  BP.changed = w + n + 1;
+  BP.changed = w + n + 1; BP.any_pending = w + n + 1 + 64;
   BP.shift_total = w + head_words; BP.chunk_bit = BP.shift_total + nchunks; BP.head = BP.chunk_bit + nchunks; BP.head_carry = BP.head + nchunks;
-  BP.tail = reinterpret_cast<uint16_t*>(BP.head_carry + nchunks);
+  BP.pending = BP.head_carry + nchunks;
+  BP.tail = reinterpret_cast<uint16_t*>(BP.pending + nchunks);
   BP.entry = reinterpret_cast<uint8_t*>(BP.tail + nchunks); BP.walked = BP.entry + nchunks;
   BP.out = B.out; BP.out_base = B.out_base; BP.out_size = B.out_size;
   const unsigned cb = (nchunks + 127) / 128;
