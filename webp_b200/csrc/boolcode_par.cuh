@@ -348,6 +348,39 @@ __global__ void __launch_bounds__(64) bcp_join_fix_kernel(const BcpParams P) {
   const int img = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (img < P.n_images) bcp_join_fix_image(P, img);
 }
+// Frames for the host: [partition 0][token partition] of image 0, of image 1, ... back to back, so that one copy brings a
+// batch's coded bytes over.  sizes[k] / in_base[k]: k < n the token partition of image k, k >= n partition 0 of image k - n.
+struct FramePackParams {
+  const uint8_t* coded; const unsigned long long* in_base; const unsigned int* sizes; uint8_t* packed; unsigned long long* offsets; int n;
+};
+// one block: exclusive prefix of size(p0_i) + size(tok_i) over the images
+__global__ void __launch_bounds__(1024) frame_pack_scan_kernel(const FramePackParams P) {
+  __shared__ unsigned long long s_part[1024];
+  const int per = (P.n + 1023) / 1024, lo = min((int)threadIdx.x * per, P.n), hi = min(lo + per, P.n);
+  unsigned long long sum = 0;
+  for (int i = lo; i < hi; ++i) sum += (unsigned long long)P.sizes[i] + P.sizes[P.n + i];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < 1024; ++i) { const unsigned long long v = s_part[i]; s_part[i] = run; run += v; }
+  }
+  __syncthreads();
+  unsigned long long run = s_part[threadIdx.x];
+  for (int i = lo; i < hi; ++i) { P.offsets[i] = run; run += (unsigned long long)P.sizes[i] + P.sizes[P.n + i]; }
+}
+// grid = (n, chunks of 16 KB)
+__global__ void __launch_bounds__(256) frame_pack_copy_kernel(const FramePackParams P) {
+  const int img = blockIdx.x;
+  const unsigned int p0 = P.sizes[P.n + img], tk = P.sizes[img], total = p0 + tk;
+  const unsigned int begin = blockIdx.y * 16384u;
+  if (begin >= total) return;
+  const unsigned int end = min(begin + 16384u, total);
+  const uint8_t* a = P.coded + P.in_base[P.n + img];
+  const uint8_t* b = P.coded + P.in_base[img];
+  uint8_t* dst = P.packed + P.offsets[img];
+  for (unsigned int i = begin + threadIdx.x; i < end; i += 256) dst[i] = i < p0 ? a[i] : b[i - p0];
+}
 #endif
 
 }  // namespace wg

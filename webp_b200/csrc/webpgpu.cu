@@ -85,9 +85,9 @@ struct wgpu_ctx {
   // constant tables
   DevBuf t_lc, t_eob, t_lfc, t_i4cost, t_g2l, t_l2g, t_proba0, t_upd, t_ecost;
   // encoder state (device)
-  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, ctxw_uv, derr, dither_y, dither_uv, hdr, coeffs, stats, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, bcp_work, p0_plan, p0_info, p0_mb_tokens, p0_mb_offset, p0_total, t_i4paths, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
+  DevBuf rgba, sy, su, sv, ry, ru, rv, alpha, uv_alpha, segment, img_params, ctxw, ctxw2, ctxw_uv, derr, dither_y, dither_uv, hdr, coeffs, stats, proba, mb_tokens, mb_offset, img_total, img_base, tokens, coded, coded_size, coded_packed, pack_offsets, bcp_work, p0_plan, p0_info, p0_mb_tokens, p0_mb_offset, p0_total, t_i4paths, lc_img, eob_img, stats_cuts, hdr_prev, coeffs_prev;
   DevBuf sharp_best_y, sharp_target_y, sharp_best_uv, sharp_target_uv, t_sharp;  // SharpYUV import working planes + gamma tables
-  PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens, h_bcp, h_p0;
+  PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens, h_bcp, h_p0, h_packed;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
   bool e_uploaded = false, e_analyzed = false, e_done = false, e_keep_derr = false, e_keep_stats = false;
   int dither_w = 0, dither_h = 0, dither_amp_cached = 0;  // what the device dither tables currently hold
@@ -233,14 +233,14 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->ctxw_uv, &ctx->derr, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->bcp_work, &ctx->p0_plan, &ctx->p0_info, &ctx->p0_mb_tokens, &ctx->p0_mb_offset, &ctx->p0_total, &ctx->t_i4paths, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
+  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->ctxw_uv, &ctx->derr, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->coded_packed, &ctx->pack_offsets, &ctx->bcp_work, &ctx->p0_plan, &ctx->p0_info, &ctx->p0_mb_tokens, &ctx->p0_mb_offset, &ctx->p0_total, &ctx->t_i4paths, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
                   &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
                   &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
                   &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_streams, &ctx->d_hdrs, &ctx->d_perr, &ctx->t_bmodes, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
                   &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
                   &ctx->m_sse, &ctx->m_ssim};
   for (DevBuf* b : db) b->release();
-  PinBuf* pb[] = {&ctx->h_stats_cuts, &ctx->hd_streams, &ctx->hd_hdrs, &ctx->hd_perr, &ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_bcp, &ctx->h_p0, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
+  PinBuf* pb[] = {&ctx->h_stats_cuts, &ctx->hd_streams, &ctx->hd_hdrs, &ctx->hd_perr, &ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_bcp, &ctx->h_p0, &ctx->h_packed, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
                   &ctx->hd_meta, &ctx->hd_ftype, &ctx->hd_planes, &ctx->hd_nrgba};
   for (PinBuf* b : pb) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1332,33 +1332,51 @@ int wgpu_enc_finish(wgpu_ctx* ctx, uint8_t* out, size_t out_stride, size_t* out_
       if (rc_par) return rc_par;
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, 2 * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->xfer_d2h += (uint64_t)(2 * n * 4);
+    // frames packed back to back on the device ([partition 0][token partition] per image): one copy brings the batch over
+    RESERVE(ctx->coded_packed, (size_t)oall); RESERVE(ctx->pack_offsets, n * 8);
+    wg::FramePackParams FP;
+    FP.coded = ctx->coded.as<uint8_t>(); FP.in_base = ctx->img_base.as<unsigned long long>() + 2 * n; FP.sizes = ctx->coded_size.as<unsigned int>();
+    FP.packed = ctx->coded_packed.as<uint8_t>(); FP.offsets = ctx->pack_offsets.as<unsigned long long>(); FP.n = (int)n;
+    unsigned long long max_cap = 0;
+    for (size_t i = 0; i < n; ++i) max_cap = std::max(max_cap, totals[i] + totals[n + i] + 64);
+    auto launch_pack = [&]() -> int {
+      wg::frame_pack_scan_kernel<<<1, 1024, 0, ctx->stream>>>(FP);
+      wg::frame_pack_copy_kernel<<<dim3((unsigned)n, (unsigned)((max_cap + 16383) / 16384)), 256, 0, ctx->stream>>>(FP);
+      ctx->launches += 2;
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, 2 * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->xfer_d2h += (uint64_t)(2 * n * 4);
+      return WGPU_OK;
+    };
+    if (int rc_pack = launch_pack()) return rc_pack;
     CK(cudaStreamSynchronize(ctx->stream));
     {  // more relaxation rounds if the usual ones were not enough
       bool redone = false;
       const int rc_par = finish_boolcode_par(ctx, BP, &redone);
       if (rc_par) return rc_par;
       if (redone) {
-        CK(cudaMemcpyAsync(ctx->h_coded_size.p, ctx->coded_size.p, 2 * n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (int rc_pack = launch_pack()) return rc_pack;
         CK(cudaStreamSynchronize(ctx->stream));
       }
     }
     const double t4 = now_ms();
     const unsigned int* csz = ctx->h_coded_size.as<unsigned int>();
-    for (size_t i = 0; i < n; ++i) {  // both partitions go straight to their place in the caller's buffer
-      const size_t p0 = csz[n + i];
-      out_sizes[i] = wgh::frame_file_size(p0, csz[i]);
-      if (out_sizes[i] > out_stride) { too_small.store(1); continue; }
-      CK(cudaMemcpyAsync(out + i * out_stride + 30, ctx->coded.as<uint8_t>() + bases[2 * n + n + i], p0, cudaMemcpyDeviceToHost, ctx->stream));
-      if (csz[i]) CK(cudaMemcpyAsync(out + i * out_stride + 30 + p0, ctx->coded.as<uint8_t>() + bases[2 * n + i], csz[i], cudaMemcpyDeviceToHost, ctx->stream));
-      ctx->xfer_d2h += (uint64_t)(p0 + csz[i]);
-    }
+    std::vector<unsigned long long> offs(n + 1);
+    offs[0] = 0;
+    for (size_t i = 0; i < n; ++i) offs[i + 1] = offs[i] + csz[i] + csz[n + i];  // the same prefix frame_pack_scan_kernel took
+    RESERVE(ctx->h_packed, (size_t)offs[n] + 16);
+    CK(cudaMemcpyAsync(ctx->h_packed.p, ctx->coded_packed.p, (size_t)offs[n], cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->xfer_d2h += (uint64_t)offs[n];
     CK(cudaStreamSynchronize(ctx->stream));
-    for (size_t i = 0; i < n; ++i)
-      if (out_sizes[i] <= out_stride) wgh::write_frame_headers(ctx->plans[i], out + i * out_stride, csz[n + i], csz[i]);
+    parallel_for((int)n, threads_of(ctx), [&](int i) {
+      out_sizes[i] = wgh::frame_file_size(csz[n + i], csz[i]);
+      if (out_sizes[i] > out_stride) { too_small.store(1); return; }
+      uint8_t* dst = out + (size_t)i * out_stride;
+      memcpy(dst + 30, ctx->h_packed.as<uint8_t>() + offs[i], (size_t)(offs[i + 1] - offs[i]));
+      wgh::write_frame_headers(ctx->plans[i], dst, csz[n + i], csz[i]);
+    });
     if (trace_on())
-      fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, tokens + coder %.2f ms (%.1f M tokens, longest partition %.2f M), frames D2H + headers %.2f ms\n",
+      fprintf(stderr, "[wgpu] enc_finish: wait device %.2f ms, tokens + coder + pack %.2f ms (%.1f M tokens, longest partition %.2f M), frames D2H + layout %.2f ms\n",
               t1 - t0, t4 - t1, (double)all / 1e6, (double)*std::max_element(totals, totals + 2 * n) / 1e6, now_ms() - t4);
   } else if (ctx->e_token_route) {
     // ---- single partition: tokens are generated on the GPU, the host only boolean-codes flat arrays
