@@ -96,3 +96,13 @@ func UpsampleLinePairBatchCUDA(ctx unsafe.Pointer, n, width int, topY, botY, top
 	return int(C.wgpu_dsp_upsample_line_pair_batch((*C.wgpu_ctx)(ctx), C.int(n), C.int(width), p(topY), p(botY), p(topU), p(topV), p(botU), p(botV),
 		p(alphaTop), p(alphaBot), C.int(channels), p(topDst), p(botDst)))
 }
+
+// VP8BitWriter (internal/bitio/writer_bool.go:58-150) over n flat token arrays, bit | prob << 8 per token (encode_token.go:20): the
+// encoder's chunk-parallel device coder.  tokens holds the arrays back to back, totals[i] tokens each; partition i is written to
+// out[i*outStride:], sizes[i] bytes.  Returns the status and the number of state-relaxation rounds the batch needed.
+func BoolCodeBatchCUDA(ctx unsafe.Pointer, tokens []uint16, totals []uint64, out []byte, outStride int, sizes []uint32) (int, int) {
+	var rounds C.int
+	rc := C.wgpu_dsp_boolcode_batch((*C.wgpu_ctx)(ctx), C.int(len(totals)), (*C.uint16_t)(&tokens[0]), (*C.ulonglong)(&totals[0]),
+		(*C.uint8_t)(&out[0]), C.size_t(outStride), (*C.uint)(&sizes[0]), &rounds)
+	return int(rc), int(rounds)
+}
