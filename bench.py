@@ -547,6 +547,20 @@ def main():
         t1 = time.perf_counter()
         ctx.check(L.wgpu_decode_batch(ctx.handle, ptrs, lens, n, None, None, None, 0, 0, h_rgba, W * H * 4))
         dec_one_shot_s = time.perf_counter() - t1
+        # the same call with the macroblocks parsed by the host's threads (WGPU_DEVICE_PARSER=0, read per call): one context alone on
+        # a host with many cores finishes sooner that way; the GPU parser is the default because it needs no host cores and scales
+        # with the number of contexts in flight
+        saved_parser = os.environ.get("WGPU_DEVICE_PARSER")
+        os.environ["WGPU_DEVICE_PARSER"] = "0"
+        ctx.check(L.wgpu_decode_batch(ctx.handle, ptrs, lens, n, None, None, None, 0, 0, h_rgba, W * H * 4))  # warm-up: staging buffers
+        t1 = time.perf_counter()
+        ctx.check(L.wgpu_decode_batch(ctx.handle, ptrs, lens, n, None, None, None, 0, 0, h_rgba, W * H * 4))
+        dec_one_shot_host_s = time.perf_counter() - t1
+        if saved_parser is None:
+            os.environ.pop("WGPU_DEVICE_PARSER", None)
+        else:
+            os.environ["WGPU_DEVICE_PARSER"] = saved_parser
+        ctx.check(L.wgpu_decode_batch(ctx.handle, ptrs, lens, n, None, None, None, 0, 0, h_rgba, W * H * 4))  # back on the default route
         clock_rec = clocks.stop()
         # what the oracle comparison below looks at: NRGBA of every decode context that ran, planes of the first one
         mbw, mbh = (W + 15) >> 4, (H + 15) >> 4
@@ -571,7 +585,9 @@ def main():
                                                    "d2h_bytes_per_step": n * (ysz + 2 * uvsz),
                                                    "api": "same stages, Y/U/V planes out (the lossy.DecodeFrame boundary) instead of NRGBA"},
                                     "one_shot": {"value": px_step / dec_one_shot_s / 1e6, "unit": "Mpix/s", "ms": dec_one_shot_s * 1e3,
-                                                 "api": "one wgpu_decode_batch call on one context, nothing overlapped"}},
+                                                 "api": "one wgpu_decode_batch call on one context, nothing overlapped",
+                                                 "host_parser": {"value": px_step / dec_one_shot_host_s / 1e6, "unit": "Mpix/s", "ms": dec_one_shot_host_s * 1e3,
+                                                                 "threads": host_threads, "how": "WGPU_DEVICE_PARSER=0"}}},
                             "config": {"workload": "decode of the %d streams above -> recon + loop filter + fancy upsampling to NRGBA (BASELINE configs[2])" % n},
                             "roofline": {"bound": "hbm", "kernel": "recon_wave + filter_wave + upsample_nrgba (whole device step)",
                                          "achieved": dec_gbs, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": dec_gbs / peak}}
