@@ -23,7 +23,7 @@ struct EncKernelParams {
   int8_t* left_derr;            // [n][2][2] (enc.leftDerr)
   const uint16_t* lc_img;       // [n][LC_SIZE] per-image folded level costs (serial path with probability refreshes), or null
   const uint16_t* eob_img;      // [n][EOB_SIZE]
-  int serial_gpw;               // encode_serial_tab_kernel: macroblock groups (images) per warp actually used, 1..32/G (0 = all)
+  int serial_gpw;               // serial RD kernels with per-image tables: macroblock groups (images) per warp actually used, 1..32/G (0 = all)
   // Serial RD path split by plane (refresh route): luma runs as left/top/top-right waves over the macroblocks [mb_begin, mb_end) of a
   // refresh segment (serial_wave = 1: `wave` is x + 2y and tasks are (image, row) pairs), chroma as one raster-order chain per image
   // (its DC error diffusion carries leftDerr from macroblock to macroblock, encode_frame.go:529-566).  ctx_uv receives the chroma half

@@ -189,7 +189,7 @@ __device__ __forceinline__ void encode_mb_group(const EncKernelParams& P, int wa
   const bool active0 = task < total && !(img_flags & 0x100) && (!SERIAL || P.serial_gpw == 0 || g < P.serial_gpw);
   const int max_i4_modes = (img_flags & 0xff) ? (img_flags & 0xff) : P.max_i4_modes;
   const int img = active0 ? (wave_map ? (int)(task / rows) : (int)task) : 0;
-  const CostTabs& T = T_launch;  // launch-wide tables, or this macroblock's image's own (encode_serial_tab_kernel)
+  const CostTabs& T = T_launch;  // launch-wide tables, or this macroblock's image's own (the plane-split serial kernels)
   const int my = active0 ? (wave_map ? y_lo + (int)(task % rows) : wave / P.mb_w) : 0;
   const int mx = active0 ? (wave_map ? wave - 2 * my : wave - my * P.mb_w) : 0;
   const int nmb = P.mb_w * P.mb_h;
@@ -1231,35 +1231,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) encode_serial_kernel(const E
 // Serial RD path with mid-stream probability refreshes (encode_frame.go:35-57): the RD costs follow each image's own
 // probability state, so every macroblock group works from ITS image's folded cost tables (rebuilt by the host at each
 // refresh, P.lc_img / P.eob_img), staged into shared memory next to the group's work buffers -- the Viterbi reads them a
-// dozen times per coefficient position, and from HBM/L2 that latency dominated the pass (380 us per macroblock step).
-// One warp per CTA: 4 macroblocks = 4 images = 4 x 13.4 KB of tables.
-template <int G>
-__global__ void __launch_bounds__(32, 2) encode_serial_tab_kernel(const EncKernelParams P, int mb_index) {
-  // Macroblocks that share a warp run their data-dependent control flow one after the other (a step takes ~130 us for one
-  // group per warp, ~310 us for four), and this path is a chain of 3 x mbW x mbH such steps with the GPU nearly empty: the
-  // host picks P.serial_gpw = 1 group per warp while the batch leaves SMs to spare.
-  const int gpw = P.serial_gpw;
-  WG_STAGE_TABLES(32);
-  uint16_t* s_tabs = reinterpret_cast<uint16_t*>(s_mb + 32 / G);  // [gpw][LC_SIZE + EOB_SIZE], after a work buffer for every group slot
-  const long long task_base = (long long)blockIdx.x * gpw;
-  for (int g = 0; g < gpw; ++g) {
-    const long long img = task_base + g;
-    if (img >= P.n_images) break;
-    uint4* dst = reinterpret_cast<uint4*>(s_tabs + (size_t)g * (LC_SIZE + EOB_SIZE));
-    const uint4* a = reinterpret_cast<const uint4*>(P.lc_img + (size_t)img * LC_SIZE);
-    const uint4* b = reinterpret_cast<const uint4*>(P.eob_img + (size_t)img * EOB_SIZE);
-    for (int i = threadIdx.x; i < LC_SIZE / 8; i += 32) dst[i] = a[i];
-    for (int i = threadIdx.x; i < EOB_SIZE / 8; i += 32) dst[LC_SIZE / 8 + i] = b[i];
-  }
-  __syncwarp();
-  CostTabs Tg = T;
-  const int g = min((int)(threadIdx.x & 31) / G, gpw - 1);
-  Tg.lc = s_tabs + (size_t)g * (LC_SIZE + EOB_SIZE);
-  Tg.eob = Tg.lc + LC_SIZE;
-  encode_mb_group<G, false, true>(P, mb_index, task_base, s_mb, Tg, s_i4cost);
-}
-
-// The same serial RD path split by plane, for frames long enough to refresh their probabilities (config: 3840x2160, rate
+// dozen times per coefficient position.  One warp per CTA: up to 4 macroblock groups = 4 images = 4 x 13.4 KB of tables;
+// macroblocks that share a warp run their data-dependent control flow one after the other, so the host picks P.serial_gpw = 1
+// group per warp while the batch leaves SMs to spare.
+// The path is split by plane, for frames long enough to refresh their probabilities (config: 3840x2160, rate
 // control): inside a refresh segment the luma decisions of a macroblock depend on its left / top / top-right neighbours only,
 // so luma runs as x + 2y waves over the segment (tasks = (image, row) pairs of the wave that fall inside [mb_begin, mb_end));
 // what forces raster order is the chroma DC error diffusion (leftDerr carries from the end of a row into the next one,

@@ -377,26 +377,6 @@ int launch_enc_serial(wgpu_ctx* ctx, const wg::EncKernelParams& P, int mb_begin,
   }
   return WGPU_OK;
 }
-// Serial RD path with probability refreshes: as launch_enc_serial, each macroblock group with its image's own cost tables.
-int launch_enc_serial_tab(wgpu_ctx* ctx, wg::EncKernelParams& P, int mb_begin, int mb_end) {
-  constexpr int G = 8;
-  const int sm_count = ctx->sm_count;
-  // one macroblock group (image) per warp while the batch leaves SMs to spare, then 2, then 4 (see the kernel)
-  const int gpw = P.n_images <= 8 * sm_count ? 1 : (P.n_images <= 24 * sm_count ? 2 : 4);
-  P.serial_gpw = gpw;
-  const size_t smem = sizeof(wg::MBShared) * (32 / G) + (size_t)gpw * (wg::LC_SIZE + wg::EOB_SIZE) * 2;
-  {
-    const size_t max_smem = sizeof(wg::MBShared) * 4 + (size_t)4 * (wg::LC_SIZE + wg::EOB_SIZE) * 2;
-    cudaError_t e = cudaFuncSetAttribute(wg::encode_serial_tab_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-    if (e != cudaSuccess) { ctx->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return WGPU_ERR_CUDA; }
-  }
-  const unsigned grid = (unsigned)((P.n_images + gpw - 1) / gpw);
-  for (int i = mb_begin; i < mb_end; ++i) {
-    wg::encode_serial_tab_kernel<G><<<grid, 32, smem, ctx->stream>>>(P, i);
-    ctx->launches++;
-  }
-  return WGPU_OK;
-}
 // Serial RD path with refreshes, split by plane (enc_kernels.cuh): luma waves over the macroblocks [mb_begin, mb_end) on the
 // context's stream, the chroma chains of the same segment on its second stream, then the merge of the two halves.
 int launch_enc_serial_split(wgpu_ctx* ctx, wg::EncKernelParams& P, int mb_begin, int mb_end) {
@@ -705,9 +685,7 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
     int start = 0;
     for (int k = 1;; ++k) {
       const int end = std::min(k * max_count + (k - 1), nmb);
-      // WGPU_SERIAL_SPLIT=0 keeps the whole-macroblock raster chain (one launch per macroblock index), for comparison
-      static const bool split = getenv_int("WGPU_SERIAL_SPLIT", 1) != 0;
-      if ((rc = split ? launch_enc_serial_split(ctx, P, start, end) : launch_enc_serial_tab(ctx, P, start, end))) return rc;
+      if ((rc = launch_enc_serial_split(ctx, P, start, end))) return rc;
       if (end >= nmb) break;
       if ((rc = all_stats())) return rc;
       CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->stats.p, (size_t)n * wg::STATS_SIZE * 4, cudaMemcpyDeviceToHost, ctx->stream));
