@@ -5,6 +5,7 @@
 #include "../webp_b200/csrc/host_enc.h"
 #include "../webp_b200/csrc/host_dec.h"
 #include "../webp_b200/csrc/sharp_kernels.cuh"
+#include "../webp_b200/csrc/ssim_sep.cuh"
 #include "../webp_b200/csrc/enc_phased.cuh"
 #include <algorithm>
 #include <random>
@@ -388,5 +389,53 @@ long hostcheck_bcp_join(int nch, const uint32_t* chunk_bit, uint32_t* head, uint
   for (int k = 0; k < nch; ++k) wg::bcp_join_boundary(P, order[k]);
   wg::bcp_join_fix_image(P, 0);
   return g_bcp_parked - parked0;
+}
+// The PRODUCT's separable SSE / SSIM (webp_b200/csrc/ssim_sep.cuh) run on the CPU in the kernel's schedule: stage, hpass and
+// vpass of every tile, the threads / tasks of each phase in shuffled order (order_seed), a barrier where the kernel has one,
+// the tile partials added in the fixed order of metrics_reduce_kernel's input.  force_unaligned = 1 takes the byte path.
+int hostcheck_ssim(const uint8_t* a, const uint8_t* b, int stride, int width, int height, unsigned order_seed, int force_unaligned,
+                   unsigned long long* sse_out, double* ssim_out) {
+  std::mt19937 rng(order_seed);
+  auto shuffled = [&](int count) {
+    std::vector<int> o((size_t)count);
+    for (int i = 0; i < count; ++i) o[(size_t)i] = i;
+    if (order_seed) std::shuffle(o.begin(), o.end(), rng);
+    return o;
+  };
+  const int tiles_x = (width + wg::SS_TW - 1) / wg::SS_TW, tiles_y = (height + wg::SS_TH - 1) / wg::SS_TH;
+  const bool aligned = !force_unaligned && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)stride) & 3u) == 0;
+  std::vector<uint32_t> sa(wg::SS_ROWS * wg::SS_SW), sb(sa.size());
+  std::vector<wg::SsimH> sh((size_t)wg::SS_ROWS * wg::SS_TW);
+  unsigned long long sse = 0;
+  double ssim = 0.0;
+  for (int ty = 0; ty < tiles_y; ++ty)
+    for (int tx = 0; tx < tiles_x; ++tx) {
+      const int x0 = tx * wg::SS_TW, y0 = ty * wg::SS_TH;
+      for (auto& e : sh) e = wg::SsimH{0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu};
+      for (int i : shuffled(wg::SS_ROWS * wg::SS_SW)) wg::ssim_stage_word(a, b, stride, width, height, x0, y0, aligned, i, sa.data(), sb.data());
+      // __syncthreads()
+      unsigned long long tile_sse = 0;
+      for (int t : shuffled(wg::SS_HTASKS)) {
+        const int r = t >> 3, cg = t & 7;
+        const uint32_t d = wg::ssim_hpass(sa.data() + r * wg::SS_SW, sb.data() + r * wg::SS_SW, cg, sh.data() + (size_t)r * wg::SS_TW);
+        if (r >= 3 && r < 3 + wg::SS_TH) tile_sse += d;
+      }
+      // __syncthreads()
+      double lane_sum[256];
+      for (int t : shuffled(256)) lane_sum[t] = wg::ssim_vpass(sh.data(), t & 31, t >> 5, x0, y0, width, height);
+      double tile_ssim = 0.0;
+      for (int w = 0; w < 8; ++w) {  // shuffle-down tree of a warp, then warps in order
+        double v[32];
+        for (int l = 0; l < 32; ++l) v[l] = lane_sum[32 * w + l];
+        for (int o = 16; o > 0; o >>= 1)
+          for (int l = 0; l < o; ++l) v[l] += v[l + o];
+        tile_ssim += v[0];
+      }
+      sse += tile_sse;
+      ssim += tile_ssim;
+    }
+  *sse_out = sse;
+  *ssim_out = ssim;
+  return 0;
 }
 }

@@ -399,7 +399,7 @@ def test_upsample_nrgba(oracle, gpu_ctx, w, h):
         assert np.array_equal(got_a[i], oracle.build_nrgba(w, h, y[i], u[i], v[i], a[i]))
 
 
-@pytest.mark.parametrize("w,h", [(7, 7), (8, 3), (40, 56), (130, 71), (1536, 1024)])
+@pytest.mark.parametrize("w,h", [(1, 1), (7, 7), (8, 3), (40, 56), (33, 57), (130, 71), (257, 119), (768, 512), (1536, 1024)])
 def test_plane_metrics(oracle, gpu_ctx, w, h):
     rng = np.random.RandomState(w + h)
     a = rng.randint(0, 256, (2, h, w)).astype(np.uint8)

@@ -286,6 +286,36 @@ def test_sharpyuv_kernel_code_on_cpu_matches_oracle(oracle):
                 assert it[k] == oracle.sharp_yuv(imgs[k])[3]
 
 
+def test_ssim_kernel_code_on_cpu_matches_oracle(oracle):
+    """The product's separable SSE / SSIM (webp_b200/csrc/ssim_sep.cuh: row sums, column sums, ssimCalculation) run on the CPU in
+    the kernel's schedule with the tasks of each phase in shuffled order (oracle/hostcheck.cc hostcheck_ssim) vs the oracle's
+    direct 7x7 windows (internal/dsp/ssim.go:12-160): SSE exact, SSIM within 1e-12 relative (the order of the double sum)."""
+    import ctypes as C
+    L = C.CDLL(os.path.join(os.path.dirname(DATA), "..", "oracle", "_build", "libhostcheck.so"))
+    rng = np.random.default_rng(3)
+    for (w, h) in [(1, 1), (2, 3), (7, 7), (31, 5), (32, 56), (33, 57), (64, 112), (100, 75), (130, 61), (257, 119)]:
+        for kind in range(3):
+            a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            if kind == 0:
+                b = np.clip(a.astype(int) + rng.integers(-9, 10, (h, w)), 0, 255).astype(np.uint8)
+            elif kind == 1:
+                b = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            else:  # flat halves: the C3 shortcut and the largest cross terms
+                a = np.full((h, w), 3, np.uint8)
+                b = a.copy()
+                b[h // 2:, :] = 250
+            exp = oracle.plane_ssim(a, b)
+            for pad, force_bytes, seed in ((0, 0, 0), (3, 0, 5), (0, 1, 9)):  # odd stride and forced byte loads take the unaligned path
+                A = np.zeros((h, w + pad), np.uint8)
+                B = np.zeros_like(A)
+                A[:, :w] = a
+                B[:, :w] = b
+                sse, ss = C.c_ulonglong(), C.c_double()
+                L.hostcheck_ssim(A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), A.strides[0], w, h, C.c_uint(seed), force_bytes, C.byref(sse), C.byref(ss))
+                assert sse.value == oracle.plane_sse(a, b), (w, h, kind)
+                assert abs(ss.value - exp) <= 1e-12 * abs(exp), (w, h, kind, pad, force_bytes)
+
+
 def _cleanup_numpy(img):
     """cleanupTransparentAreaLossy (encode.go:788-890) restated once more in plain numpy, to cross-check the C++ oracle."""
     px = img.copy()

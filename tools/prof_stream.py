@@ -26,7 +26,7 @@ except Exception:
     peak = 6650.0
 ms = C.c_float()
 mbw, mbh = (w + 15) // 16, (h + 15) // 16
-for sid, name, bpp, px in ((0, "import_rgba_kernel", 5.5, n * w * h), (1, "analysis_kernel", 1.5, n * mbw * mbh * 256), (3, "metrics_kernel SSE+SSIM", 2.0, n * mbw * mbh * 256), (5, "sse_kernel (PSNR only)", 2.0, n * mbw * mbh * 256),
+for sid, name, bpp, px in ((0, "import_rgba_kernel", 5.5, n * w * h), (1, "analysis_kernel", 1.5, n * mbw * mbh * 256), (3, "ssim_sep_kernel SSE+SSIM", 2.0, n * mbw * mbh * 256), (5, "sse_kernel (PSNR only)", 2.0, n * mbw * mbh * 256),
                            (4, "upsample_nrgba_kernel", 5.5, n * w * h)):
     ctx.check(L.wgpu_enc_stage_time(ctx.handle, C.byref(opt), sid, reps, C.byref(ms)))
     gbs = bpp * px / (ms.value * 1e-3) / 1e9

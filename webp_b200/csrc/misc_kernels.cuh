@@ -5,8 +5,7 @@
 
 namespace wg {
 
-// ---- SSE + SSIM over whole plane pairs.  One CTA = a 32x8 tile of windows; both planes' tiles (with the
-// 3-pixel apron) are staged in shared memory so each source byte is read from HBM once (2 B/px algorithmic).
+// ---- SSE over whole plane pairs (the SSE + SSIM kernel is ssim_sep.cuh; metrics_reduce_kernel below adds its tile partials).
 struct MetricsParams {
   const uint8_t* a; const uint8_t* b;
   size_t plane_stride;
@@ -15,88 +14,6 @@ struct MetricsParams {
   unsigned long long* sse_part;  // [n][tiles]
   double* ssim_part;             // [n][tiles]
 };
-// ssimCalculation (ssim.go:48) on integer window statistics; the only floating-point op is the final divide.
-__device__ __forceinline__ double ssim_calc(uint32_t xm, uint32_t ym, uint32_t xxm, uint32_t xym, uint32_t yym, uint32_t N) {
-  const unsigned long long w2 = (unsigned long long)N * N;
-  const unsigned long long C1 = 20 * w2, C2 = 60 * w2, C3 = 64 * w2;
-  const unsigned long long xmxm = (unsigned long long)xm * xm, ymym = (unsigned long long)ym * ym;
-  if (xmxm + ymym < C3) return 1.0;
-  const long long xmym = (long long)xm * (long long)ym;
-  const long long sxy = (long long)xym * (long long)N - xmym;
-  const unsigned long long sxx = (unsigned long long)xxm * N - xmxm;
-  const unsigned long long syy = (unsigned long long)yym * N - ymym;
-  const unsigned long long sxy_pos = sxy > 0 ? (unsigned long long)sxy : 0ull;
-  const unsigned long long num_s = (2 * sxy_pos + C2) >> 8;
-  const unsigned long long den_s = (sxx + syy + C2) >> 8;
-  const unsigned long long fnum = (2 * (unsigned long long)xmym + C1) * num_s;
-  const unsigned long long fden = (xmxm + ymym + C1) * den_s;
-  if (fden == 0) return 1.0;
-  return (double)fnum / (double)fden;
-}
-enum { MET_TW = 32, MET_TH = 8 };  // windows per tile (one per thread)
-__global__ void __launch_bounds__(256) metrics_kernel(const MetricsParams P) {
-  constexpr int TW = 32, TH = 8, AW = TW + 6, AH = TH + 6;
-  __shared__ uint8_t sa[AH][AW + 2], sb[AH][AW + 2];
-  __shared__ unsigned long long s_sse[8];
-  __shared__ double s_ssim[8];
-  const int tiles = P.tiles_x * P.tiles_y;
-  const int img = blockIdx.x / tiles, tile = blockIdx.x - img * tiles;
-  const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
-  const int x0 = tx * TW, y0 = ty * TH;
-  const uint8_t* pa = P.a + (size_t)img * P.plane_stride;
-  const uint8_t* pb = P.b + (size_t)img * P.plane_stride;
-  for (int i = threadIdx.x; i < AW * AH; i += 256) {
-    const int r = i / AW, c = i - r * AW;
-    const int gx = x0 + c - 3, gy = y0 + r - 3;
-    uint8_t va = 0, vb = 0;
-    if (gx >= 0 && gx < P.width && gy >= 0 && gy < P.height) {
-      va = pa[(size_t)gy * P.stride + gx];
-      vb = pb[(size_t)gy * P.stride + gx];
-    }
-    sa[r][c] = va;
-    sb[r][c] = vb;
-  }
-  __syncthreads();
-  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-  const int gx = x0 + lx, gy = y0 + ly;
-  unsigned long long sse = 0;
-  double ssim = 0.0;
-  if (gx < P.width && gy < P.height) {
-    const int d = (int)sa[ly + 3][lx + 3] - (int)sb[ly + 3][lx + 3];
-    sse = (unsigned long long)(d * d);
-    uint32_t w = 0, xm = 0, ym = 0, xxm = 0, xym = 0, yym = 0;
-#pragma unroll
-    for (int dy = 0; dy < 7; ++dy) {
-      const int yy = gy + dy - 3;
-      if (yy < 0 || yy >= P.height) continue;
-      const uint32_t wy = dy < 4 ? dy + 1 : 7 - dy;
-#pragma unroll
-      for (int dx = 0; dx < 7; ++dx) {
-        const int xx = gx + dx - 3;
-        if (xx < 0 || xx >= P.width) continue;
-        const uint32_t ww = wy * (dx < 4 ? dx + 1 : 7 - dx);
-        const uint32_t x = sa[ly + dy][lx + dx], y = sb[ly + dy][lx + dx];
-        w += ww; xm += ww * x; ym += ww * y; xxm += ww * x * x; xym += ww * x * y; yym += ww * y * y;
-      }
-    }
-    ssim = ssim_calc(xm, ym, xxm, xym, yym, w);  // interior windows have w == 256 (SSIMGet), borders are SSIMGetClipped
-  }
-  // deterministic in-CTA reduction: lanes, then warps in order
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sse += __shfl_down_sync(0xffffffffu, sse, o);
-    ssim += __shfl_down_sync(0xffffffffu, ssim, o);
-  }
-  if (lx == 0) { s_sse[ly] = sse; s_ssim[ly] = ssim; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long ts = 0;
-    double tq = 0.0;
-    for (int i = 0; i < 8; ++i) { ts += s_sse[i]; tq += s_ssim[i]; }
-    P.sse_part[blockIdx.x] = ts;
-    P.ssim_part[blockIdx.x] = tq;
-  }
-}
 // SSE alone (dsp.SSE, ssim.go:172; PSNR for TargetPSNR): a pure stream, 2 B/px.  16 bytes of each plane per thread and step
 // (128-bit loads where the row allows), |a - b| per byte and the dot product of the differences with themselves (dp4a).
 __global__ void __launch_bounds__(256) sse_kernel(const MetricsParams P, unsigned long long* sse) {

@@ -20,6 +20,7 @@
 #include "enc_phased.cuh"
 #include "dec_parse.cuh"
 #include "sharp_kernels.cuh"
+#include "ssim_sep.cuh"
 #include "host_dec.h"
 
 namespace {
@@ -1941,7 +1942,7 @@ int wgpu_upsample_nrgba(wgpu_ctx* ctx, int n, int width, int height, const uint8
 static int launch_metrics(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t* b, int width, int height, int stride, size_t plane_stride, bool want_ssim) {
   wg::MetricsParams mp;
   mp.a = a; mp.b = b; mp.plane_stride = plane_stride; mp.stride = stride; mp.width = width; mp.height = height; mp.n = n;
-  mp.tiles_x = (width + wg::MET_TW - 1) / wg::MET_TW; mp.tiles_y = (height + wg::MET_TH - 1) / wg::MET_TH;
+  mp.tiles_x = (width + wg::SS_TW - 1) / wg::SS_TW; mp.tiles_y = (height + wg::SS_TH - 1) / wg::SS_TH;
   const int tiles = mp.tiles_x * mp.tiles_y;
   RESERVE(ctx->m_sse, (size_t)n * 8); RESERVE(ctx->m_ssim, (size_t)n * 8);
   if (!want_ssim) {  // SSE / PSNR only: the streaming kernel
@@ -1955,7 +1956,10 @@ static int launch_metrics(wgpu_ctx* ctx, int n, const uint8_t* a, const uint8_t*
   }
   RESERVE(ctx->m_sse_part, (size_t)n * tiles * 8); RESERVE(ctx->m_ssim_part, (size_t)n * tiles * 8);
   mp.sse_part = ctx->m_sse_part.as<unsigned long long>(); mp.ssim_part = ctx->m_ssim_part.as<double>();
-  wg::metrics_kernel<<<(unsigned)(n * tiles), 256, 0, ctx->stream>>>(mp);
+  wg::SsimSepParams sp;
+  sp.a = a; sp.b = b; sp.plane_stride = plane_stride; sp.stride = stride; sp.width = width; sp.height = height; sp.n = n;
+  sp.tiles_x = mp.tiles_x; sp.tiles_y = mp.tiles_y; sp.sse_part = mp.sse_part; sp.ssim_part = mp.ssim_part;
+  wg::ssim_sep_kernel<<<(unsigned)(n * tiles), 256, 0, ctx->stream>>>(sp);
   wg::metrics_reduce_kernel<<<n, 256, 0, ctx->stream>>>(mp.sse_part, mp.ssim_part, tiles, ctx->m_sse.as<unsigned long long>(), ctx->m_ssim.as<double>());
   ctx->launches += 2;
   CK(cudaGetLastError());
