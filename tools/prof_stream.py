@@ -28,6 +28,11 @@ ms = C.c_float()
 mbw, mbh = (w + 15) // 16, (h + 15) // 16
 for sid, name, bpp, px in ((0, "import_rgba_kernel", 5.5, n * w * h), (1, "analysis_kernel", 1.5, n * mbw * mbh * 256), (3, "ssim_sep_kernel SSE+SSIM", 2.0, n * mbw * mbh * 256), (5, "sse_kernel (PSNR only)", 2.0, n * mbw * mbh * 256),
                            (4, "upsample_nrgba_kernel", 5.5, n * w * h)):
+    ctx.check(L.wgpu_enc_stage_time(ctx.handle, C.byref(opt), sid, 1, C.byref(ms)))  # warm-up: first-use allocations stay outside the timing
     ctx.check(L.wgpu_enc_stage_time(ctx.handle, C.byref(opt), sid, reps, C.byref(ms)))
     gbs = bpp * px / (ms.value * 1e-3) / 1e9
     print("%-26s %.3f ms  %.0f GB/s algorithmic = %.1f %% of the measured %.0f GB/s  (%.1f Gpix/s)" % (name, ms.value, gbs, 100 * gbs / peak, peak, px / ms.value / 1e6))
+if os.environ.get("SSIM_REPEAT"):  # steadiness of the SSE+SSIM stage: SSIM_REPEAT=8 python tools/prof_stream.py
+    for k in range(int(os.environ["SSIM_REPEAT"])):
+        ctx.check(L.wgpu_enc_stage_time(ctx.handle, C.byref(opt), 3, 4, C.byref(ms)))
+        print("ssim repeat %d: %.3f ms" % (k, ms.value))

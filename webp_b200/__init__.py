@@ -5,4 +5,4 @@ webp_b200/_build/libwebpgpu.so); this package is the host-side mirror of the ref
 """
 from .webp import (Config, Decode, DecodeBatch, DecodeConfig, DefaultOptions, Encode, EncodeBatch, EncoderOptions,  # noqa: F401
                    Options, OptionsForPreset, WebPError, YCbCr, validateConfig)
-from . import dsp, native  # noqa: F401
+from . import animation, dsp, mux, native  # noqa: F401

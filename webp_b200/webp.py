@@ -3,8 +3,9 @@
 Names, argument meaning and error behaviour follow the Go package (paths relative to the reference):
   Encode / EncoderOptions / DefaultOptions / OptionsForPreset / validateConfig     encode.go:42-334,424
   Decode / DecodeConfig / buildYCbCr / buildNRGBA                                  webp.go:88-140,351-450
-Only the lossy pixel path is behind this boundary (BASELINE.json north_star); Lossless / alpha-plane /
-animation / metadata options are rejected with the same "webp: ..." error style instead of being emulated.
+Only the lossy pixel path is behind this boundary (BASELINE.json north_star); Lossless and alpha-plane options are
+rejected with the same "webp: ..." error style instead of being emulated.  Metadata (ICC / EXIF / XMP) puts the VP8X
+container of mux.py around the same bitstream; animations are animation.py.
 EncodeBatch / DecodeBatch are the additions a GPU backend needs: one image cannot fill a B200.
 """
 import ctypes as C
@@ -167,8 +168,6 @@ class WebPError(ValueError):
 def _unsupported(o):
     if o.Lossless:
         return "webp: Lossless (VP8L) is outside the GPU lossy path"
-    if o.ICC or o.EXIF or o.XMP:
-        return "webp: metadata chunks (VP8X container) are host-side container work outside this path"
     return None
 
 
@@ -204,7 +203,11 @@ def EncodeBatch(imgs, opts=None, ctx=None):
     sizes = np.zeros(n, np.uint64)
     ctx.check(native.lib().wgpu_encode_batch(ctx.handle, a.ctypes.data, n, w, h, w * 4, w * h * 4, C.byref(cfg), out.ctypes.data,
                                             cap, sizes.ctypes.data))
-    return [out[i, :int(sizes[i])].tobytes() for i in range(n)]
+    files = [out[i, :int(sizes[i])].tobytes() for i in range(n)]
+    if o.ICC or o.EXIF or o.XMP:  # writeRIFF (encode.go:955): metadata asks for the VP8X container around the same bitstream
+        from . import mux
+        files = [mux.writeRIFFExtended(mux.FourCCVP8, mux.riff_payload(f), None, w, h, bytes(o.ICC), bytes(o.EXIF), bytes(o.XMP)) for f in files]
+    return files
 
 
 def Encode(w, img, opts=None, ctx=None):
