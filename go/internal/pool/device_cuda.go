@@ -66,3 +66,21 @@ func (d *Device) FreePinned(b []byte) {
 		C.wgpu_host_free(d.ctx, unsafe.Pointer(&b[0]))
 	}
 }
+
+// MemInfo reports what the context's allocator holds: device bytes, pinned host bytes, live buffers (wgpu_ctx_mem_info).
+// Buffers are grow-only and sized in the classes of pool.go:14-40 up to 1 MiB, sixteenths of a power of two above.
+func (d *Device) MemInfo() (device, pinned uint64, buffers int) {
+	var dv, pv C.size_t
+	var n C.int
+	C.wgpu_ctx_mem_info(d.ctx, &dv, &pv, &n)
+	return uint64(dv), uint64(pv), int(n)
+}
+
+// Trim returns the working buffers to the driver, as draining the sync.Pool buckets does on the CPU side; constant tables
+// stay and the next call re-reserves (wgpu_ctx_trim).
+func (d *Device) Trim() error {
+	if rc := C.wgpu_ctx_trim(d.ctx); rc != 0 {
+		return d.Err("trim")
+	}
+	return nil
+}

@@ -74,6 +74,15 @@ int wgpu_set_host_threads(wgpu_ctx* ctx, int n);
 /* pinned host staging (device image-batch allocator; internal/pool analogue) */
 void* wgpu_host_alloc(wgpu_ctx* ctx, size_t bytes);
 void wgpu_host_free(wgpu_ctx* ctx, void* p);
+/* Device image-batch allocator -- replaces the bucketed byte pools of internal/pool/pool.go:14-71 (Get / Put, bucketIndex) and
+ * the encoder / decoder object pools of internal/lossy/encode.go:391 (resetForReuse) for the GPU side.  A context's device and
+ * pinned buffers are grow-only and sized in classes: wgpu_pool_bucket(bytes) = the reference's seven buckets up to 1 MiB, above
+ * that the next sixteenth of the enclosing power of two.  wgpu_ctx_mem_info reports the bytes a context holds and how many
+ * buffers are live; wgpu_ctx_trim returns the working buffers to the driver (constant tables stay) and forgets whatever picture
+ * state they held -- the next call re-reserves.  Results never depend on what a buffer held before (tests/test_gpu_codec.py). */
+size_t wgpu_pool_bucket(size_t bytes);
+int wgpu_ctx_mem_info(wgpu_ctx* ctx, size_t* device_bytes, size_t* pinned_bytes, int* buffers);
+int wgpu_ctx_trim(wgpu_ctx* ctx);
 
 /* ---- encoder: whole job --------------------------------------------------------------- */
 /* Encode n same-size RGBA images (4 B/px, `stride` bytes per row, image i at rgba + i*image_stride).

@@ -634,3 +634,42 @@ def test_context_on_second_device(oracle):
     finally:
         c0.close(); c1.close()
 
+
+def test_allocator_reuse_across_shapes_and_trim(oracle):
+    """Device image-batch allocator (include/webpgpu.h wgpu_ctx_mem_info / wgpu_ctx_trim; internal/pool/pool.go:14-71,
+    resetForReuse internal/lossy/encode.go:391): one context is driven through shapes, options and routes that leave every
+    kind of stale content behind (larger batch, other dimensions, rate control, Method 2, decode), and each result must be
+    what a fresh context gives = the oracle's bytes / planes.  Buffers only grow, in bucket sizes; trim gives the working set
+    back, keeps the constant tables and the next call starts from nothing."""
+    ctx = native.Context(0)
+    L = native.lib()
+    assert [L.wgpu_pool_bucket(n) for n in (1, 256, 257, 5000, 1 << 20, (1 << 20) + 1, 3 << 20, (5 << 20) + 7)] == [
+        256, 256, 1024, 16384, 1 << 20, (1 << 20) + (1 << 17), 3 << 20, (5 << 20) + (1 << 19)]
+    d0, h0, k0 = ctx.mem_info()
+    assert d0 > 0 and h0 == 0  # constant tables only
+    plan = [(4, 160, 112, {}), (1, 48, 48, {}), (2, 96, 144, dict(TargetSize=1500)), (3, 64, 64, dict(Method=2, Quality=80)),
+            (6, 160, 112, dict(Quality=30)), (1, 16, 16, {}), (2, 200, 40, dict(FilterStrength=0, Segments=1))]
+    grown = []
+    for n, w, h, kw in plan:
+        imgs = np.stack([oracle.synth_image(w, h, i, kind=i % 3) for i in range(n)])
+        o = _opts(**kw)
+        files = webp_b200.EncodeBatch(imgs, o, ctx)
+        exp = [oracle.encode(imgs[i], _ocfg(oracle, o)) for i in range(n)]
+        assert files == exp, (n, w, h, kw)
+        ys, rgba = webp_b200.DecodeBatch(files, nrgba=True, ctx=ctx)
+        for i in range(n):
+            _, _, y, u, v = oracle.decode(exp[i])
+            assert np.array_equal(ys[i].Y, y[:h, :w]) and np.array_equal(rgba[i], oracle.build_nrgba(w, h, y, u, v))
+        d, hp, k = ctx.mem_info()
+        grown.append(d)
+        assert d >= (grown[-2] if len(grown) > 1 else d0)  # grow-only
+    ctx.trim()
+    assert ctx.mem_info()[0] <= d0 + (1 << 20) and ctx.mem_info()[1] == 0  # tables (+ lazily built ones) stay, working set gone
+    n, w, h, kw = plan[0]
+    imgs = np.stack([oracle.synth_image(w, h, i, kind=i % 3) for i in range(n)])
+    assert webp_b200.EncodeBatch(imgs, _opts(), ctx) == [oracle.encode(imgs[i]) for i in range(n)]
+    files = [oracle.encode(imgs[i]) for i in range(n)]
+    ctx.trim()  # decode first on a trimmed context
+    ys = webp_b200.DecodeBatch(files, ctx=ctx)
+    assert all(np.array_equal(ys[i].Y, oracle.decode(files[i])[2][:h, :w]) for i in range(n))
+    ctx.close()

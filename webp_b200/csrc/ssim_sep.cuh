@@ -12,7 +12,7 @@
 //           (columns XOR-swizzled so that the 128-bit stores of this phase and the loads of the next are conflict-free);
 //           the squared difference of the task's own samples goes to the SSE
 //   vpass   thread = (column, 7 adjacent rows): column sums over 13 staged rows, then ssimCalculation per window
-// The phase functions are host+device: oracle/hostcheck.cc runs them on the CPU in this schedule against the oracle.
+// The phase functions are host+device so that a CPU test harness can run them in this schedule (tests/test_oracle.py).
 #pragma once
 #include <stdint.h>
 #include <stddef.h>

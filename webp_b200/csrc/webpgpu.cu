@@ -27,15 +27,43 @@ namespace {
 
 std::string g_create_error;
 
+// Device image-batch allocator (the GPU analogue of internal/pool/pool.go:14-71).  Every device / pinned buffer of a context
+// is grow-only and registers itself with its context; capacities come in size classes -- the reference's seven buckets up to
+// 1 MiB, above that sixteenths of the next power of two (at most 12.5 % slack) -- so a batch a little larger than the last
+// one reuses the buffer instead of reallocating.  wgpu_ctx_mem_info reports what a context holds, wgpu_ctx_trim gives the
+// working buffers back (constant tables stay) and resets every flag that described their contents.
+struct DevBuf;
+struct PinBuf;
+struct BufRegistry { std::vector<DevBuf*> dev; std::vector<PinBuf*> pin; };
+thread_local BufRegistry* g_reg = nullptr;  // set while a wgpu_ctx's members are being constructed
+
+inline size_t pool_bucket(size_t n) {
+  static const size_t classes[7] = {256, 1024, 4096, 16384, 65536, 262144, 1048576};  // pool.go:5-13
+  for (size_t c : classes) if (n <= c) return c;
+  size_t p = 1;
+  while (p < n) p <<= 1;
+  const size_t step = p >> 4;
+  return (n + step - 1) / step * step;
+}
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool table = false;  // constant table uploaded once (upload_table): survives wgpu_ctx_trim
+  DevBuf() { if (g_reg) g_reg->dev.push_back(this); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
   bool reserve(size_t n) {
     if (n <= cap) return true;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    if (cudaMalloc(&p, n) != cudaSuccess) return false;
-    cap = n;
+    size_t want = pool_bucket(n);
+    if (cudaMalloc(&p, want) != cudaSuccess) {  // the bucket's slack does not fit: take the exact size
+      cudaGetLastError();
+      want = n;
+      if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return false; }
+    }
+    cap = want;
     return true;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -44,12 +72,20 @@ struct DevBuf {
 struct PinBuf {
   void* p = nullptr;
   size_t cap = 0;
+  PinBuf() { if (g_reg) g_reg->pin.push_back(this); }
+  PinBuf(const PinBuf&) = delete;
+  PinBuf& operator=(const PinBuf&) = delete;
   bool reserve(size_t n) {
     if (n <= cap) return true;
     if (p) cudaFreeHost(p);
     p = nullptr; cap = 0;
-    if (cudaMallocHost(&p, n) != cudaSuccess) return false;
-    cap = n;
+    size_t want = pool_bucket(n);
+    if (cudaMallocHost(&p, want) != cudaSuccess) {
+      cudaGetLastError();
+      want = n;
+      if (cudaMallocHost(&p, want) != cudaSuccess) { p = nullptr; return false; }
+    }
+    cap = want;
     return true;
   }
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
@@ -74,6 +110,8 @@ void parallel_for(int n, int threads, F f) {
 }  // namespace
 
 struct wgpu_ctx {
+  BufRegistry reg;  // every DevBuf / PinBuf member below registers here (declaration order: reg_open first, reg_close last)
+  struct RegOpen { explicit RegOpen(BufRegistry* r) { g_reg = r; } } reg_open{&reg};
   int dev = 0;
   int sm_count = 148;  // of this context's device
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: the chroma chains of the plane-split serial RD path
@@ -113,6 +151,7 @@ struct wgpu_ctx {
   bool d_ready = false, d_any_filter = false, d_has_nrgba = false;
   // metrics
   DevBuf m_a, m_b, m_sse_part, m_ssim_part, m_sse, m_ssim;
+  struct RegClose { RegClose() { g_reg = nullptr; } } reg_close;
 };
 
 #define CK(call)                                                                                   \
@@ -166,6 +205,7 @@ void wgpu_enc_options_default(wgpu_enc_options* o, int quality) {
 
 static int upload_table(wgpu_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
   RESERVE(b, bytes);
+  b.table = true;
   CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->xfer_h2d += (uint64_t)(bytes);
   return 0;
@@ -234,16 +274,8 @@ void wgpu_ctx_destroy(wgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->dev);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* db[] = {&ctx->sharp_best_y, &ctx->sharp_target_y, &ctx->sharp_best_uv, &ctx->sharp_target_uv, &ctx->t_sharp, &ctx->dither_y, &ctx->dither_uv, &ctx->ctxw2, &ctx->ctxw_uv, &ctx->derr, &ctx->t_proba0, &ctx->t_upd, &ctx->t_ecost, &ctx->proba, &ctx->mb_tokens, &ctx->mb_offset, &ctx->img_total, &ctx->img_base, &ctx->tokens, &ctx->coded, &ctx->coded_size, &ctx->coded_packed, &ctx->pack_offsets, &ctx->bcp_work, &ctx->p0_plan, &ctx->p0_info, &ctx->p0_mb_tokens, &ctx->p0_mb_offset, &ctx->p0_total, &ctx->t_i4paths, &ctx->lc_img, &ctx->eob_img, &ctx->stats_cuts, &ctx->hdr_prev, &ctx->coeffs_prev,
-                  &ctx->t_lc, &ctx->t_eob, &ctx->t_lfc, &ctx->t_i4cost, &ctx->t_g2l, &ctx->t_l2g, &ctx->rgba,
-                  &ctx->sy, &ctx->su, &ctx->sv, &ctx->ry, &ctx->ru, &ctx->rv, &ctx->alpha, &ctx->uv_alpha, &ctx->segment,
-                  &ctx->img_params, &ctx->ctxw, &ctx->hdr, &ctx->coeffs, &ctx->stats, &ctx->d_streams, &ctx->d_hdrs, &ctx->d_perr, &ctx->t_bmodes, &ctx->d_coeffs, &ctx->d_meta, &ctx->d_ftype, &ctx->dy,
-                  &ctx->du, &ctx->dv, &ctx->d_nrgba, &ctx->d_alpha, &ctx->m_a, &ctx->m_b, &ctx->m_sse_part, &ctx->m_ssim_part,
-                  &ctx->m_sse, &ctx->m_ssim};
-  for (DevBuf* b : db) b->release();
-  PinBuf* pb[] = {&ctx->h_stats_cuts, &ctx->hd_streams, &ctx->hd_hdrs, &ctx->hd_perr, &ctx->h_lc_img, &ctx->h_coded_size, &ctx->h_proba, &ctx->h_totals, &ctx->h_bases, &ctx->h_tokens, &ctx->h_bcp, &ctx->h_p0, &ctx->h_packed, &ctx->h_stats, &ctx->h_alpha, &ctx->h_uv_alpha, &ctx->h_segment, &ctx->h_params, &ctx->h_hdr, &ctx->h_coeffs, &ctx->hd_coeffs,
-                  &ctx->hd_meta, &ctx->hd_ftype, &ctx->hd_planes, &ctx->hd_nrgba};
-  for (PinBuf* b : pb) b->release();
+  for (DevBuf* b : ctx->reg.dev) b->release();
+  for (PinBuf* b : ctx->reg.pin) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_hdr) cudaEventDestroy(ctx->ev_hdr);
@@ -261,6 +293,37 @@ int wgpu_sync(wgpu_ctx* ctx) {
   if (!ctx) return WGPU_ERR_INVALID;
   CK(cudaSetDevice(ctx->dev));
   CK(cudaStreamSynchronize(ctx->stream));
+  return WGPU_OK;
+}
+size_t wgpu_pool_bucket(size_t bytes) { return pool_bucket(bytes); }
+int wgpu_ctx_mem_info(wgpu_ctx* ctx, size_t* device_bytes, size_t* pinned_bytes, int* buffers) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  size_t d = 0, h = 0;
+  int k = 0;
+  for (const DevBuf* b : ctx->reg.dev) { d += b->cap; k += b->p != nullptr; }
+  for (const PinBuf* b : ctx->reg.pin) { h += b->cap; k += b->p != nullptr; }
+  if (device_bytes) *device_bytes = d;
+  if (pinned_bytes) *pinned_bytes = h;
+  if (buffers) *buffers = k;
+  return WGPU_OK;
+}
+int wgpu_ctx_trim(wgpu_ctx* ctx) {
+  if (!ctx) return WGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->dev));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->stream2) CK(cudaStreamSynchronize(ctx->stream2));
+  if (ctx->d_graph) { cudaGraphExecDestroy(ctx->d_graph); ctx->d_graph = nullptr; }  // it holds the buffers' addresses
+  memset(ctx->d_graph_key, 0, sizeof(ctx->d_graph_key));
+  for (DevBuf* b : ctx->reg.dev) if (!b->table) b->release();
+  for (PinBuf* b : ctx->reg.pin) b->release();
+  // nothing on the device describes a picture any more
+  ctx->e_uploaded = ctx->e_analyzed = ctx->e_done = ctx->e_keep_derr = ctx->e_keep_stats = false;
+  ctx->e_n = 0;
+  ctx->dither_w = ctx->dither_h = ctx->dither_amp_cached = 0;
+  ctx->d_ready = ctx->d_has_nrgba = ctx->d_dev_parsed = false;
+  ctx->d_n = 0;
   return WGPU_OK;
 }
 int wgpu_set_host_threads(wgpu_ctx* ctx, int n) {

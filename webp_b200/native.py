@@ -64,6 +64,10 @@ def lib():
         L.wgpu_host_alloc.restype = vp
         L.wgpu_host_free.argtypes = [vp, vp]
         L.wgpu_host_free.restype = None
+        L.wgpu_pool_bucket.argtypes = [sz]
+        L.wgpu_pool_bucket.restype = sz
+        L.wgpu_ctx_mem_info.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(C.c_int)]
+        L.wgpu_ctx_trim.argtypes = [vp]
         L.wgpu_enc_options_default.argtypes = [C.POINTER(EncOptions), C.c_int]
         L.wgpu_enc_options_default.restype = None
         L.wgpu_encode_batch.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int, sz, C.POINTER(EncOptions), u8p, sz, vp]
@@ -144,6 +148,16 @@ class Context:
         a, b = C.c_uint64(), C.c_uint64()
         self.check(lib().wgpu_transfer_bytes(self._h, C.byref(a), C.byref(b), 1 if reset else 0))
         return int(a.value), int(b.value)
+
+    def mem_info(self):
+        """(device bytes, pinned host bytes, live buffers) this context's allocator holds (wgpu_ctx_mem_info)."""
+        d, h, k = C.c_size_t(), C.c_size_t(), C.c_int()
+        self.check(lib().wgpu_ctx_mem_info(self._h, C.byref(d), C.byref(h), C.byref(k)))
+        return int(d.value), int(h.value), int(k.value)
+
+    def trim(self):
+        """Give the working buffers back (wgpu_ctx_trim); the next call re-reserves."""
+        self.check(lib().wgpu_ctx_trim(self._h))
 
     def close(self):
         if self._h:
