@@ -6,8 +6,8 @@
 // hands over the partition-0 decoder state right after them plus the tables they define (DecHeader).
 //
 // Boolean decoding is a serial chain per partition with data-dependent control flow at every bit, so there is nothing for
-// SIMT to share inside an image: one warp per image, lane 0 walks the macroblocks in raster order, and the batch supplies
-// the parallelism (256 images = 256 warps = 3 % of the warp slots; several batches' parsers overlap on the GPU).  What it
+// SIMT to share inside an image: one single-thread block per image walks the macroblocks in raster order, and the batch
+// supplies the parallelism (256 images = 256 warps = 3 % of the warp slots; several batches' parsers overlap on the GPU).  What it
 // buys is the host: 768 B of dequantised coefficients per macroblock no longer cross PCIe (1.26 GB per 256-image batch ->
 // 46 MB of compressed bytes), and 32 host cores no longer parse for 8 GPUs.
 //
@@ -48,7 +48,7 @@ __device__ __constant__ uint8_t c_dcat6[12] = {254, 254, 243, 230, 196, 177, 153
 struct DBoolDec {
   const uint8_t* p; const uint8_t* end;
   uint32_t value;
-  uint32_t range;
+  uint32_t range;  // the reference's range - 1 form, normalised: 127 .. 254
   int bits;
   bool eof;
   __device__ __forceinline__ void init(const uint8_t* d, uint32_t n) { p = d; end = d + n; value = 0; range = 254; bits = -8; eof = false; refill(); }
@@ -75,47 +75,51 @@ struct DBoolDec {
       bits = 0;
     }
   }
-  __device__ __forceinline__ int get(int prob) {
-    uint32_t r = range;
+  // One decoded bit; p24 = probability << 24.  The dependent chain per bit is range -> split -> compare -> new range ->
+  // its leading zeros -> shift, and it is kept to six operations: split = (range * prob) >> 8 is the upper word of
+  // range * p24 (one IMAD.HI instead of multiply + shift), and the renormalised (r << shift) - 1 is one funnel shift of
+  // r - 1 with ones coming in from below (no separate decrement).
+  __device__ __forceinline__ int get24(uint32_t p24) {
     if (bits < 0) refill();
     const int pos = bits;
-    const uint32_t split = (r * (uint32_t)prob) >> 8;
+    const uint32_t split = __umulhi(range, p24);
     const uint32_t v = value >> pos;
-    int bit;
-    if (v > split) { r -= split; value -= (split + 1) << pos; bit = 1; }
-    else { r = split + 1; bit = 0; }
+    const bool bit = v > split;
+    const uint32_t r = bit ? range - split : split + 1;  // the new range + 1: what the shift is read from
+    if (bit) value -= (split + 1) << pos;
+    const uint32_t rm = r - 1;                            // the new range itself, before renormalisation (off the chain)
     const int shift = 7 ^ (31 - __clz(r));
-    r <<= shift;
+    range = __funnelshift_l(0xffffffffu, rm, shift);
     bits -= shift;
-    range = r - 1;
     return bit;
   }
+  __device__ __forceinline__ int get(int prob) { return get24((uint32_t)prob << 24); }
 };
 
 // getCoeffs (decode_mb.go:111): one block's tokens, dequantised into out[zigzag]; returns the position after the last
 // coefficient read.  P = probabilities of this block's type in shared memory, rows [band][ctx] padded to 16 bytes so that
 // a row is ONE 128-bit load into registers per coefficient instead of a dependent byte load per bit; *dc_nz = whether
 // out[0] was written non-zero (as the int16 it is stored as).
-#define WG_PB(row, i) (((i) < 4 ? (row).x >> (8 * (i)) : (i) < 8 ? (row).y >> (8 * ((i) - 4)) : (row).z >> (8 * ((i) - 8))) & 0xffu)
+#define WG_PB(row, i) __byte_perm((i) < 4 ? (row).x : (i) < 8 ? (row).y : (row).z, 0, ((((i) & 3)) << 12) | 0x444)  /* probability i << 24 */
 __device__ __forceinline__ int dread_block(DBoolDec& br, const uint4* P, int ctx, int dq_dc, int dq_ac, int n, int16_t* out, bool* dc_nz) {
   uint4 p = P[c_bands[n] * 3 + ctx];
   for (; n < 16; ++n) {
-    if (!br.get(WG_PB(p, 0))) return n;
-    while (!br.get(WG_PB(p, 1))) {
+    if (!br.get24(WG_PB(p, 0))) return n;
+    while (!br.get24(WG_PB(p, 1))) {
       p = P[c_bands[++n] * 3 + 0];
       if (n == 16) return 16;
     }
     const uint4* next = P + c_bands[n + 1] * 3;
     const uint4 n1 = next[1], n2 = next[2];  // both candidates for the next row, issued before the level is known
     int v;
-    if (!br.get(WG_PB(p, 2))) { v = 1; p = n1; }
+    if (!br.get24(WG_PB(p, 2))) { v = 1; p = n1; }
     else {
-      if (!br.get(WG_PB(p, 3))) { v = !br.get(WG_PB(p, 4)) ? 2 : 3 + br.get(WG_PB(p, 5)); }
-      else if (!br.get(WG_PB(p, 6))) {
-        if (!br.get(WG_PB(p, 7))) v = 5 + br.get(159);
+      if (!br.get24(WG_PB(p, 3))) { v = !br.get24(WG_PB(p, 4)) ? 2 : 3 + br.get24(WG_PB(p, 5)); }
+      else if (!br.get24(WG_PB(p, 6))) {
+        if (!br.get24(WG_PB(p, 7))) v = 5 + br.get(159);
         else { v = 7 + 2 * br.get(165); v += br.get(145); }
       } else {
-        const int b1 = br.get(WG_PB(p, 8)), b0 = br.get(b1 ? WG_PB(p, 10) : WG_PB(p, 9)), cat = 2 * b1 + b0;
+        const int b1 = br.get24(WG_PB(p, 8)), b0 = br.get24(b1 ? WG_PB(p, 10) : WG_PB(p, 9)), cat = 2 * b1 + b0;
         const uint8_t* t = cat == 0 ? c_dcat3 : cat == 1 ? c_dcat4 : cat == 2 ? c_dcat5 : c_dcat6;
         v = 0;
         for (; *t; ++t) v += v + br.get(*t);
@@ -164,7 +168,12 @@ struct DecParseParams {
 
 // Dynamic shared memory: the image's header (probabilities, quantisers, filter strengths), the intra-mode probabilities,
 // the per-column contexts (4 top modes + NZ flags + DC flag per macroblock column) and the token-partition decoder states.
-__global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
+// ONE thread per block.  The chain has nothing for a second lane to do, and a block that cannot diverge is compiled without
+// the convergence bookkeeping of a 32-lane warp: with __launch_bounds__(1) ptxas drops the BSSY / BSYNC pair around the refill
+// test of every decoded bit and makes the bit's own branch a uniform one (87 of them in this kernel; 149 -> 62 BSSY), which
+// is two to three instructions off a ~20-instruction dependent chain.  The thread also moves a coded macroblock out of shared
+// memory itself: 48 independent 128-bit stores against the ~400 decoded bits of such a macroblock.
+__global__ void __launch_bounds__(1) dec_parse_kernel(const DecParseParams P) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ __align__(16) int16_t s_co[384];  // the macroblock being parsed: zero between macroblocks
   uint4* s_co4 = reinterpret_cast<uint4*>(s_co);
@@ -175,30 +184,25 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
   uint8_t* top_nz = top_modes + 4 * P.mb_w;
   uint8_t* top_dc = top_nz + P.mb_w;
   DBoolDec* parts = reinterpret_cast<DBoolDec*>(s_dyn + ((((top_dc + P.mb_w) - s_dyn) + 15) & ~(size_t)15));
-  const int img = blockIdx.x, lane = threadIdx.x;
+  const int img = blockIdx.x;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(P.hdr + img);
     uint32_t* dst = reinterpret_cast<uint32_t*>(H);
-    for (int i = lane; i < (int)(sizeof(DecHeader) / 4); i += 32) dst[i] = src[i];
-    for (int i = lane; i < 900; i += 32) s_bmodes[i] = P.bmodes[i];
-    __syncwarp();
-    for (int r = lane; r < 96; r += 32) {
+    for (int i = 0; i < (int)(sizeof(DecHeader) / 4); ++i) dst[i] = src[i];
+    const uint32_t* bm = reinterpret_cast<const uint32_t*>(P.bmodes);  // 900 bytes, 4-byte aligned table
+    for (int i = 0; i < 225; ++i) reinterpret_cast<uint32_t*>(s_bmodes)[i] = bm[i];
+    for (int r = 0; r < 96; ++r) {
       uint8_t* d = reinterpret_cast<uint8_t*>(s_prob + r);
       for (int k = 0; k < 16; ++k) d[k] = k < 11 ? H->proba[r * 11 + k] : 0;
     }
-    for (int i = lane; i < 6 * P.mb_w; i += 32) top_modes[i] = 0;
+    for (int i = 0; i < 6 * P.mb_w; ++i) top_modes[i] = 0;
   }
-  for (int i = lane; i < 48; i += 32) s_co4[i] = make_uint4(0, 0, 0, 0);
-  __syncwarp();
-  // Lane 0 walks the boolean decoders (every bit decides the next instruction: a chain by construction); the other lanes
-  // only help to move a finished macroblock's coefficients out of shared memory in whole sectors.
+  for (int i = 0; i < 48; ++i) s_co4[i] = make_uint4(0, 0, 0, 0);
   const uint8_t* frame = P.streams + H->stream_off;
   DBoolDec br;
   br.adopt(frame + H->br_pos, frame + H->br_end, H->br_value, H->br_range, H->br_bits, H->br_eof != 0);
   const int last = H->last_part;
-  if (lane == 0)
-    for (int p = 0; p <= last; ++p) parts[p].init(frame + H->part_off[p], H->part_len[p]);
-  __syncwarp();
+  for (int p = 0; p <= last; ++p) parts[p].init(frame + H->part_off[p], H->part_len[p]);
   const int mb_w = P.mb_w, mb_h = P.mb_h;
   const size_t nmb = (size_t)mb_w * mb_h;
   const bool update_map = H->update_map, use_skip = H->use_skip;
@@ -206,7 +210,6 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
   for (int my = 0; my < mb_h; ++my) {
     uint8_t left_modes[4] = {0, 0, 0, 0};
     MBMeta* row = P.meta + (size_t)img * nmb + (size_t)my * mb_w;
-    if (lane == 0)
     for (int mx = 0; mx < mb_w; ++mx) {  // parseIntraModeRow (decode_tree.go:35)
       MBMeta m;
       uint8_t* top = top_modes + 4 * mx;
@@ -238,12 +241,10 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
       m.f_limit = m.f_ilevel = m.f_inner = m.hev_thresh = 0;
       row[mx] = m;
     }
-    if (__shfl_sync(0xffffffffu, (int)br.eof, 0)) { if (lane == 0) P.err[img] = 1; return; }
+    if (br.eof) { P.err[img] = 1; return; }
     DBoolDec tb = parts[my & last];
     uint8_t left_nz = 0, left_dc = 0;
     for (int mx = 0; mx < mb_w; ++mx) {
-      uint32_t any_nz = 0;  // some block of this macroblock has a non-zero transform code: its coefficients will be read
-      if (lane == 0) {
       MBMeta& m = row[mx];
       const int is_i4 = m.is_i4, segment = m.segment & 3;
       int16_t* dst = s_co;
@@ -321,21 +322,16 @@ __global__ void __launch_bounds__(32) dec_parse_kernel(const DecParseParams P) {
       const uint8_t* f = H->fs[segment][is_i4];
       m.f_limit = f[0]; m.f_ilevel = f[1]; m.hev_thresh = f[3];
       m.f_inner = (uint8_t)(f[2] || !skip);  // FInner |= !skip (decode_mb.go:291)
-      any_nz = nzy | nzuv;
-      }
-      any_nz = __shfl_sync(0xffffffffu, any_nz, 0);
-      if (__shfl_sync(0xffffffffu, (int)tb.eof, 0)) { if (lane == 0) P.err[img] = 1; return; }
-      if (any_nz) {
-        __syncwarp();
+      if (tb.eof) { P.err[img] = 1; return; }
+      if (nzy | nzuv) {
         // the reconstruction reads the coefficients of blocks with a non-zero code only (recon_wave_kernel), so an all-zero
         // macroblock leaves nothing behind and the array needs no zero fill: 768 B per coded macroblock, written once
         uint4* dst4 = reinterpret_cast<uint4*>(P.coeffs + ((size_t)img * nmb + (size_t)my * mb_w + mx) * 384);
-        for (int i = lane; i < 48; i += 32) { dst4[i] = s_co4[i]; s_co4[i] = make_uint4(0, 0, 0, 0); }
-        __syncwarp();
+#pragma unroll 8
+        for (int i = 0; i < 48; ++i) { dst4[i] = s_co4[i]; s_co4[i] = make_uint4(0, 0, 0, 0); }
       }
     }
-    if (lane == 0) parts[my & last] = tb;
-    __syncwarp();
+    parts[my & last] = tb;
   }
 }
 

@@ -1741,11 +1741,11 @@ int wgpu_dec_parse(wgpu_ctx* ctx, const uint8_t* const* streams, const size_t* l
     DP.streams = ctx->d_streams.as<uint8_t>(); DP.hdr = ctx->d_hdrs.as<wg::DecHeader>(); DP.bmodes = ctx->t_bmodes.as<uint8_t>();
     DP.coeffs = ctx->d_coeffs.as<int16_t>(); DP.meta = ctx->d_meta.as<wg::MBMeta>(); DP.err = ctx->d_perr.as<int>();
     DP.n_images = n; DP.mb_w = mbw; DP.mb_h = mbh;
-    // one warp per image, one lane of it on the chain: a chain issues an instruction every ~4.4 cycles, so an SM's four
-    // schedulers carry ~16 of them at full speed; 14 KB of shared memory per block caps the stacking there (the parsers of
-    // several contexts in flight share the GPU: 8 x 256 images in bench.py's decode leg)
+    // one single-thread block per image: a chain issues an instruction every ~4.4 cycles, so an SM's four schedulers carry
+    // ~16 of them at full speed; 14 KB of shared memory per block caps the stacking there (the parsers of several contexts
+    // in flight share the GPU: 8 x 256 images in bench.py's decode leg)
     const size_t smem = std::max(wg::dec_parse_smem(mbw), (size_t)14 * 1024);
-    wg::dec_parse_kernel<<<n, 32, smem, ctx->stream>>>(DP);
+    wg::dec_parse_kernel<<<n, 1, smem, ctx->stream>>>(DP);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(ctx->hd_perr.p, ctx->d_perr.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
