@@ -110,6 +110,63 @@ def test_muxer_anmf_layout_and_demux_round_trip():
         mux.Muxer().Assemble()
 
 
+def _vp8_keyframe(w, h):
+    """makeVP8Keyframe (mux/mux_test.go:104): frame tag, signature, dimensions."""
+    return b"\0\0\0\x9d\x01\x2a" + struct.pack("<HH", w, h)
+
+
+def test_reference_mux_cases():
+    """The cases the reference's own mux tests hold (mux/mux_test.go), transcribed: clamping of durations (:799-880) and loop
+    counts (:822), canvas size rules (:934-1010), demux of the two decode fixtures and of a hand-built extended file (:240),
+    the empty / missing frame errors (:610-625), bad RIFF (:409), frame index out of range (:416)."""
+    for dur, want in ((-1, 0), (0, 0), (100, 100), (0xFFFFFF, 0xFFFFFF), (0x1000000, 0xFFFFFF), (0x7FFFFFFF, 0xFFFFFF), (-50, 0)):
+        m = mux.Muxer()
+        m.AddFrame(_vp8_keyframe(10, 10), mux.FrameOptions(Duration=dur))
+        assert m.FrameDuration(0) == want
+        m.SetFrameDuration(0, dur)
+        assert m.FrameDuration(0) == want
+    for loops, want in ((-1, 0), (0, 0), (3, 3), (0xFFFF, 0xFFFF), (0x10000, 0xFFFF), (0x7FFFFFFF, 0xFFFF)):
+        m = mux.Muxer()
+        m.SetLoopCount(loops)
+        assert m.loopCount == want
+        m.AddFrame(_vp8_keyframe(4, 4), mux.FrameOptions(Duration=10))
+        assert mux.Demuxer(m.Assemble()).LoopCount() == want  # TestLoopCountRoundtrip (:883)
+    m = mux.Muxer(); m.SetICCProfile(b"\0"); m.SetCanvasSize(200, 160); m.AddFrame(_vp8_keyframe(100, 80))
+    d = mux.Demuxer(m.Assemble())
+    assert (d.Width, d.Height) == (200, 160)  # the explicit canvas wins (:934)
+    m = mux.Muxer(); m.SetICCProfile(b"\0"); m.AddFrame(_vp8_keyframe(100, 80))
+    d = mux.Demuxer(m.Assemble())
+    assert (d.Width, d.Height) == (100, 80) and d.HasICC and d.iccData == b"\0"  # fallback: the frame extent (:960)
+    m = mux.Muxer(); m.SetCanvasSize(50, 40)
+    assert m.canvasSize() == (50, 40)  # (:987)
+    m = mux.Muxer(); m.SetCanvasSize(100, 100)
+    m.AddFrame(_vp8_keyframe(50, 50), mux.FrameOptions(Duration=100))
+    m.AddFrame(_vp8_keyframe(50, 50), mux.FrameOptions(Duration=100, OffsetX=50, OffsetY=50))
+    d = mux.Demuxer(m.Assemble())
+    assert (d.Width, d.Height, d.NumFrames()) == (100, 100, 2) and (d.Frame(1).OffsetX, d.Frame(1).OffsetY) == (50, 50)  # (:1000)
+    assert d.Frame(0).IsKeyframe and not d.Frame(1).IsKeyframe
+    with pytest.raises(mux.MuxError):
+        d.Frame(2)
+    with pytest.raises(mux.MuxError):
+        mux.Muxer().AddFrame(b"")
+    with pytest.raises(mux.MuxError):
+        mux.Demuxer(b"not a riff file at all")
+    import os
+    data_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+    for name, dims in (("blue_16x16_lossy.webp", (16, 16)), ("red_4x4_lossy.webp", (4, 4))):  # the reference's decode fixtures (webp_test.go:148-188)
+        raw = open(os.path.join(data_dir, name), "rb").read()
+        d = mux.Demuxer(raw)
+        assert (d.Width, d.Height, d.NumFrames(), d.Format, d.HasAlpha, d.HasAnimation) == dims + (1, 1, False, False)
+        assert mux.writeRIFFSimple(mux.FourCCVP8, d.Frame(0).Data) == raw[:8 + struct.unpack_from("<I", raw, 4)[0]]
+        m = mux.Muxer(); m.AddFrame(d.Frame(0).Data)
+        assert m.Assemble() == mux.writeRIFFSimple(mux.FourCCVP8, d.Frame(0).Data)  # one frame, no metadata: the simple format (:437)
+    # VP8L frames pass through as opaque byte strings; their header's alpha bit raises the VP8X alpha flag (:691-800)
+    vp8l = bytes([0x2F]) + struct.pack("<I", (9) | (9 << 14) | (1 << 28))
+    m = mux.Muxer(); m.AddFrame(vp8l, mux.FrameOptions(Duration=5))
+    d = mux.Demuxer(m.Assemble())
+    assert d.HasAlpha and d.HasAnimation and d.Frame(0).HasAlpha and (d.Frame(0).Width, d.Frame(0).Height) == (10, 10)
+
+
 def test_keyframe_options_and_rect_helpers():
     """animation/animation.go:546 (sanitizeKeyframeOptions), :1019 findChangedRect against the reference's scan, :1099 snapToEven."""
     big = (1 << 63) - 1
