@@ -554,18 +554,6 @@ WG_HD long long wg_mad_wide(uint32_t a, uint32_t b, long long c) {  // a * b + c
   return c + (long long)((unsigned long long)a * b);
 #endif
 }
-// zigzag position of raster coefficient i (inverse of c_zigzag); constant-folded in unrolled loops
-WG_HD constexpr int trellis_zigzag_pos(int i) {
-  return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 5 : i == 3 ? 6 : i == 4 ? 2 : i == 5 ? 4 : i == 6 ? 7 : i == 7 ? 12 : i == 8 ? 3 : i == 9 ? 8 :
-         i == 10 ? 11 : i == 11 ? 13 : i == 12 ? 9 : i == 13 ? 10 : i == 14 ? 14 : 15;
-}
-WG_HD int wg_clz(uint32_t v) {
-#ifdef __CUDA_ARCH__
-  return __clz((int)v);
-#else
-  return v ? __builtin_clz(v) : 32;
-#endif
-}
 struct TrellisPos3 {  // what a position contributes, independent of the Viterbi state
   int L0;
   uint32_t flags;      // 1: level L0 exists, 2: level L0+1 exists
@@ -599,8 +587,6 @@ WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type,
   const int quant_ac = sq.quant, quant_dc = sq.dc_quant;
   const unsigned iq_ac = (unsigned)sq.iquant, iq_dc = (unsigned)sq.dc_iquant;
   uint32_t neg_mask = 0;  // bit i: raster coefficient i is negative
-  uint32_t cand_mask = 0;  // bit n: zigzag position n has a candidate level > 0
-  int n_end = 16;          // one past the last such position
   {
     bool non_zero = false;  // all-zero pre-scan with neutral bias (encode_trellis.go:39-98)
     int c0[16];
@@ -609,24 +595,14 @@ WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type,
       const int raw = io[i];
       c0[i] = max(abs(raw) + sq.sharpen[i], 0);
       neg_mask |= (raw < 0 ? 1u : 0u) << i;
-      const unsigned prod = (unsigned)c0[i] * (i > 0 ? iq_ac : iq_dc);
-      if (i > 0) non_zero |= (prod >> 17) > 0;
-      else non_zero |= first == 0 && (prod >> 17) > 0;
-      // thresh_level = (prod + 65536) >> 17 >= 1 (encode_trellis.go:179): the position has a non-zero candidate level at all.
-      // One without is coded as zero whatever its magnitude, so the magnitude is dropped here.
-      if ((i > 0 || first == 0) && prod >= 65536u) cand_mask |= 1u << trellis_zigzag_pos(i);
-      else c0[i] = 0;
+      if (i > 0) non_zero |= (((unsigned)c0[i] * iq_ac) >> 17) > 0;
+      else non_zero |= first == 0 && (((unsigned)c0[0] * iq_dc) >> 17) > 0;
     }
     if (!non_zero) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) io[i] = 0;
       return 0;
     }
-    // Past the last position with a candidate level only zeros can follow, and a zero offers no terminal (an EOB follows a
-    // non-zero coefficient): the best terminal, which is all the backtrack starts from, is final there.  The reference walks
-    // all sixteen positions (encode_trellis.go:149); stopping at n_end gives the same levels.  Positions never walked are
-    // zero in the result (their magnitudes were dropped above).
-    n_end = max(first, 32 - wg_clz(cand_mask));
 #pragma unroll
     for (int i = 0; i < 16; ++i) io[i] = (int16_t)c0[i];
   }
@@ -642,7 +618,7 @@ WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type,
   TrellisPos3 cur;
   trellis_prep3(io, first, quant_dc, quant_ac, iq_dc, iq_ac, T, lam64, cur);
 #pragma unroll 1
-  for (int n = first; n < n_end; ++n) {
+  for (int n = first; n < 16; ++n) {
     // this position's table costs: addresses known since the previous iteration, issued first ...
     const int band = c_bands[n + 1];  // sic: the next position's band (encode_trellis.go:151)
     const uint16_t* row = lc + band * 3 * LC_LEVELS;
@@ -685,7 +661,7 @@ WG_HD int trellis_block_v3(int16_t* io, const SegQuant& sq, int first, int type,
   int ctx = tag ? 1 + ((tag - 1) & 1) : -1, last = 0;
   if (first == 1) io[0] = 0;
 #pragma unroll 1
-  for (int n = n_end - 1; n >= first; --n) {
+  for (int n = 15; n >= first; --n) {
     const int zig = c_zigzag[n];
     const uint32_t ent = w0 & 0x3ffu;
     w0 = wg_fshr(w0, w1, 10); w1 = wg_fshr(w1, w2, 10); w2 = wg_fshr(w2, w3, 10); w3 = wg_fshr(w3, w4, 10); w4 >>= 10;
