@@ -43,6 +43,9 @@ struct EncKernelParams {
   int n_images, width, height, mb_w, mb_h;
   int method, max_i4_modes;
   size_t y_plane, uv_plane;     // bytes per image plane
+  // Row-parallel path: image slot s of a wave's task list holds image img_order[s] (null: the identity).  The host sorts the
+  // batch by expected cost, most expensive images first, so that a wave's longest CTAs start first instead of last.
+  const int* img_order;
 };
 
 // ctx word: bits 0-7 out_t (4 Y, 2 U, 2 V), 8-15 out_l, 16 top-DC carry, 17 left-DC carry

@@ -190,7 +190,8 @@ WG_HD bool ph_task_coords(const EncKernelParams& P, int wave, long long task, in
   const int y_lo = max(0, (wave - (P.mb_w - 1) + 1) >> 1), y_hi = min(P.mb_h - 1, wave >> 1);
   const int rows = y_hi - y_lo + 1;
   if (rows <= 0 || task >= (long long)rows * P.n_images) return false;
-  *img = (int)(task / rows);
+  const int slot = (int)(task / rows);
+  *img = P.img_order ? P.img_order[slot] : slot;
   *my = y_lo + (int)(task % rows);
   *mx = wave - 2 * *my;
   return true;

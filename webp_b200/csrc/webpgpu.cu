@@ -128,6 +128,9 @@ struct wgpu_ctx {
   DevBuf sharp_best_y, sharp_target_y, sharp_best_uv, sharp_target_uv, t_sharp;  // SharpYUV import working planes + gamma tables
   PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens, h_bcp, h_p0, h_packed;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
+  std::vector<long long> e_alpha_sum;  // per image: sum of the analysis alphas (low = busy picture); valid for the waves that follow wgpu_enc_device's plan
+  bool e_order_valid = false;
+  DevBuf img_order; PinBuf h_img_order;
   bool e_uploaded = false, e_analyzed = false, e_done = false, e_keep_derr = false, e_keep_stats = false;
   int dither_w = 0, dither_h = 0, dither_amp_cached = 0;  // what the device dither tables currently hold
   wgpu_enc_options e_opt;
@@ -319,7 +322,7 @@ int wgpu_ctx_trim(wgpu_ctx* ctx) {
   for (DevBuf* b : ctx->reg.dev) if (!b->table) b->release();
   for (PinBuf* b : ctx->reg.pin) b->release();
   // nothing on the device describes a picture any more
-  ctx->e_uploaded = ctx->e_analyzed = ctx->e_done = ctx->e_keep_derr = ctx->e_keep_stats = false;
+  ctx->e_uploaded = ctx->e_analyzed = ctx->e_done = ctx->e_keep_derr = ctx->e_keep_stats = ctx->e_order_valid = false;
   ctx->e_n = 0;
   ctx->dither_w = ctx->dither_h = ctx->dither_amp_cached = 0;
   ctx->d_ready = ctx->d_has_nrgba = ctx->d_dev_parsed = false;
@@ -395,7 +398,7 @@ int wgpu_enc_upload(wgpu_ctx* ctx, const uint8_t* rgba, int n, int width, int he
   }
   ctx->e_n = n; ctx->e_w = width; ctx->e_h = height; ctx->e_mbw = (width + 15) >> 4; ctx->e_mbh = (height + 15) >> 4;
   ctx->e_rgba_stride = dstride;
-  ctx->e_uploaded = true;
+  ctx->e_uploaded = true; ctx->e_order_valid = false;
   ctx->e_analyzed = false;
   ctx->e_done = false;
   return WGPU_OK;
@@ -686,7 +689,7 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
   P.max_i4_modes = ctx->e_opt.quality < 50 ? 2 : 3;  // getMaxI4RDModes (encode_parallel.go:931)
   P.y_plane = (size_t)nmb * 256; P.uv_plane = (size_t)nmb * 64;
   P.top_derr = nullptr; P.left_derr = nullptr; P.lc_img = nullptr; P.eob_img = nullptr; P.serial_gpw = 0;
-  P.serial_wave = 0; P.mb_begin = 0; P.mb_end = nmb; P.ctx_uv = nullptr;
+  P.serial_wave = 0; P.mb_begin = 0; P.mb_end = nmb; P.ctx_uv = nullptr; P.img_order = nullptr;
   int rc;
   const bool do_search = ctx->e_opt.target_size > 0 || ctx->e_opt.target_psnr > 0.f;
   if (ctx->e_opt.method >= 3 && (mbh < 4 || do_search)) {  // useParallel == false (encode.go:1356)
@@ -773,6 +776,19 @@ static int enc_launch_waves(wgpu_ctx* ctx) {
     if (rc) return rc;
     CK(cudaGetLastError());
     return WGPU_OK;
+  }
+  if (ctx->e_order_valid && (int)ctx->e_alpha_sum.size() == n && n > 1 && getenv_int("WGPU_WAVE_ORDER", 1) != 0) {
+    // A wave launch ends with its slowest CTAs, and those belong to the busiest pictures: give them the first slots of every
+    // wave's task list (longest first), the easy pictures fill in behind.  The analysis alpha is high for smooth macroblocks
+    // (finalAlphaValue, encode_analysis.go:237), so the lowest sum is the busiest picture.  Results do not depend on the order.
+    RESERVE(ctx->img_order, (size_t)n * 4); RESERVE(ctx->h_img_order, (size_t)n * 4);
+    int* ord = ctx->h_img_order.as<int>();
+    for (int i = 0; i < n; ++i) ord[i] = i;
+    const int sign = getenv_int("WGPU_WAVE_ORDER", 1) < 0 ? -1 : 1;
+    std::stable_sort(ord, ord + n, [&](int a, int b) { return sign * ctx->e_alpha_sum[a] < sign * ctx->e_alpha_sum[b]; });
+    CK(cudaMemcpyAsync(ctx->img_order.p, ord, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->xfer_h2d += (uint64_t)((size_t)n * 4);
+    P.img_order = ctx->img_order.as<int>();
   }
   rc = launch_enc_phased(ctx, P);
   if (rc) return rc;
@@ -1274,11 +1290,16 @@ int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
   const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
   // host: segment clustering + quantiser / lambda setup (microseconds per image; float64 pow as in the reference)
   ctx->plans.resize(n);
+  ctx->e_alpha_sum.assign(n, 0);
   static_assert(sizeof(wgh::SegParams) == sizeof(wg::SegParams), "SegParams layout");
   parallel_for(n, threads_of(ctx), [&](int i) {
     const uint8_t* ua = ctx->h_uv_alpha.as<uint8_t>() + (size_t)i * nmb;
     long long uv_sum = 0;
     for (int k = 0; k < nmb; ++k) uv_sum += ua[k];
+    const uint8_t* al = ctx->h_alpha.as<uint8_t>() + (size_t)i * nmb;
+    long long a_sum = 0;
+    for (int k = 0; k < nmb; ++k) a_sum += al[k];
+    ctx->e_alpha_sum[i] = a_sum;
     wgh::FramePlan& fp = ctx->plans[i];
     wgh::plan_frame(&fp, ctx->e_opt, ctx->e_w, ctx->e_h, ctx->h_alpha.as<uint8_t>() + (size_t)i * nmb, uv_sum,
                     ctx->h_segment.as<uint8_t>() + (size_t)i * nmb);
@@ -1286,6 +1307,7 @@ int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
     memcpy(ctx->h_params.as<uint8_t>() + (size_t)i * sizeof(wg::ImageParams), fp.dev, sizeof(wg::ImageParams));
   });
   const double t2 = now_ms();
+  ctx->e_order_valid = true;  // until the next upload: the alpha sums describe the pictures on the device
   if ((rc = enc_search_locked(ctx))) return rc;
   if (trace_on()) {
     const double t3 = now_ms();
