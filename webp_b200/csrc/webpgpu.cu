@@ -983,6 +983,15 @@ static int enc_analyze_locked(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
   ctx->xfer_d2h += (uint64_t)((size_t)n * nmb);
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->e_analyzed = true;
+  // per picture: the sum of its analysis alphas (low = busy), what the mode search orders its wave task lists by
+  ctx->e_alpha_sum.assign(n, 0);
+  parallel_for(n, threads_of(ctx), [&](int i) {
+    const uint8_t* al = ctx->h_alpha.as<uint8_t>() + (size_t)i * nmb;
+    long long a_sum = 0;
+    for (int k = 0; k < nmb; ++k) a_sum += al[k];
+    ctx->e_alpha_sum[i] = a_sum;
+  });
+  ctx->e_order_valid = true;  // until the next upload: the sums describe the pictures on the device
   return WGPU_OK;
 }
 // segment map + per-image parameters (already in the pinned staging buffers) -> device, then all waves
@@ -1290,16 +1299,11 @@ int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
   const int n = ctx->e_n, nmb = ctx->e_mbw * ctx->e_mbh;
   // host: segment clustering + quantiser / lambda setup (microseconds per image; float64 pow as in the reference)
   ctx->plans.resize(n);
-  ctx->e_alpha_sum.assign(n, 0);
   static_assert(sizeof(wgh::SegParams) == sizeof(wg::SegParams), "SegParams layout");
   parallel_for(n, threads_of(ctx), [&](int i) {
     const uint8_t* ua = ctx->h_uv_alpha.as<uint8_t>() + (size_t)i * nmb;
     long long uv_sum = 0;
     for (int k = 0; k < nmb; ++k) uv_sum += ua[k];
-    const uint8_t* al = ctx->h_alpha.as<uint8_t>() + (size_t)i * nmb;
-    long long a_sum = 0;
-    for (int k = 0; k < nmb; ++k) a_sum += al[k];
-    ctx->e_alpha_sum[i] = a_sum;
     wgh::FramePlan& fp = ctx->plans[i];
     wgh::plan_frame(&fp, ctx->e_opt, ctx->e_w, ctx->e_h, ctx->h_alpha.as<uint8_t>() + (size_t)i * nmb, uv_sum,
                     ctx->h_segment.as<uint8_t>() + (size_t)i * nmb);
@@ -1307,7 +1311,6 @@ int wgpu_enc_device(wgpu_ctx* ctx, const wgpu_enc_options* opt) {
     memcpy(ctx->h_params.as<uint8_t>() + (size_t)i * sizeof(wg::ImageParams), fp.dev, sizeof(wg::ImageParams));
   });
   const double t2 = now_ms();
-  ctx->e_order_valid = true;  // until the next upload: the alpha sums describe the pictures on the device
   if ((rc = enc_search_locked(ctx))) return rc;
   if (trace_on()) {
     const double t3 = now_ms();
