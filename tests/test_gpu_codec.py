@@ -673,3 +673,18 @@ def test_allocator_reuse_across_shapes_and_trim(oracle):
     ys = webp_b200.DecodeBatch(files, ctx=ctx)
     assert all(np.array_equal(ys[i].Y, oracle.decode(files[i])[2][:h, :w]) for i in range(n))
     ctx.close()
+
+
+def test_wave_order_does_not_change_the_bytes(oracle, gpu_ctx, monkeypatch):
+    """The mode search sorts every wave's task list by the pictures' analysis alpha sums, busiest first (EncKernelParams::img_order,
+    DESIGN.md 4a): a scheduling choice only.  A batch that mixes the three content classes must give the oracle's bytes in the
+    default order, in image order (WGPU_WAVE_ORDER=0) and in the reversed order (-1)."""
+    w, h, n = 208, 144, 13
+    imgs = np.stack([oracle.synth_image(w, h, i, kind=(i * 5) % 3) for i in range(n)])
+    exp = [oracle.encode(imgs[i]) for i in range(n)]
+    for order in (None, "0", "-1"):
+        if order is None:
+            monkeypatch.delenv("WGPU_WAVE_ORDER", raising=False)
+        else:
+            monkeypatch.setenv("WGPU_WAVE_ORDER", order)
+        assert webp_b200.EncodeBatch(imgs, webp_b200.DefaultOptions(), gpu_ctx) == exp, order
