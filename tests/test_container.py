@@ -257,6 +257,45 @@ def test_anim_encoder_files_read_by_libwebp(oracle, w, h, n, kmax, quality):
     assert not dec.HasNext()
 
 
+def test_anim_encoder_api_behaviour(oracle):
+    """animation/animation.go:590-640, 974-1016, 1157-1218: invalid canvas -> no encoder, closed encoder errors, smaller pictures sit
+    at (0, 0) of a full canvas, RGB input, AddRawFrame passes bitstreams through, metadata setters; what lies outside the lossy
+    path is refused with a message instead of being emulated."""
+    codec = _oracle_codec(oracle, 75)
+    for w, h in ((0, 10), (10, 0), (16384, 10), (10, 16384)):
+        with pytest.raises(animation.AnimError):
+            animation.AnimEncoder(io.BytesIO(), w, h)
+    for bad in (dict(Lossless=True), dict(AllowMixed=True)):
+        with pytest.raises(animation.AnimError, match="outside the GPU lossy path"):
+            animation.AnimEncoder(io.BytesIO(), 8, 8, animation.EncodeOptions(**bad), frame_encoder=codec)
+    buf = io.BytesIO()
+    enc = animation.AnimEncoder(buf, 40, 32, animation.EncodeOptions(Quality=75, LoopCount=70000), frame_encoder=codec)
+    assert enc.opts.LoopCount == 0xFFFF  # clampLoopCount
+    small = np.full((20, 24, 3), 200, np.uint8)  # RGB, smaller than the canvas
+    with pytest.raises(animation.AnimError, match="transparency"):  # the rest of the canvas would be transparent
+        enc.AddFrame(small, 40)
+    full = np.full((32, 40, 3), 90, np.uint8)
+    enc.AddFrame(full, 40)
+    moved = full.copy(); moved[4:12, 6:20] = 250
+    enc.AddFrame(moved, 60)
+    enc.AddFrame(moved, 25)  # identical: merged into the previous frame's duration
+    with pytest.raises(animation.AnimError, match="24 bits"):  # the reference would add a transparent 1x1 filler frame here
+        enc.AddFrame(moved, 0xFFFFFF)
+    raw = mux.riff_payload(oracle.encode(np.dstack([full, np.full((32, 40, 1), 255, np.uint8)])))
+    enc.AddRawFrame(raw, 15, 0, 0, animation.BlendNone, animation.DisposeNone)
+    enc.SetEXIF(b"Exif\0\0"); enc.SetICCProfile(b"icc"); enc.SetXMP(b"<x/>")
+    enc.Close()
+    enc.Close()  # a second Close is a no-op (animation.go:1191)
+    with pytest.raises(animation.AnimError, match="closed"):
+        enc.AddFrame(full, 10)
+    a = animation.DecodeBytes(buf.getvalue())
+    assert [f.Duration for f in a.Frames] == [40, 85, 15] and (a.ICC, a.EXIF, a.XMP) == (b"icc", b"Exif\0\0", b"<x/>")
+    assert a.LoopCount == 0xFFFF and (a.Frames[1].OffsetX, a.Frames[1].OffsetY) == (6, 4)
+    assert mux.parseVP8Dimensions(a.Frames[1].BitstreamData) == (14, 8)  # the changed rectangle, even offsets
+    shown, info = _pillow_canvases(buf.getvalue())
+    assert [d for _, d in shown] == [40, 85, 15] and info.get("icc_profile") == b"icc"
+
+
 def test_metadata_file_read_by_libwebp(oracle):
     """webp.Encode with ICC / EXIF / XMP (encode.go:955): VP8X container around the unchanged bitstream."""
     img = oracle.synth_image(40, 24, 3)
