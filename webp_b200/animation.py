@@ -12,7 +12,6 @@ batch, and DecodeFrames decodes every frame of a file in one batch per frame siz
 Outside this path (rejected, never emulated): Lossless / AllowMixed (VP8L), canvases with transparency and frames carrying
 an ALPH chunk (the alpha plane is VP8L work).
 """
-import io
 import math
 
 import numpy as np
