@@ -128,7 +128,7 @@ struct wgpu_ctx {
   DevBuf sharp_best_y, sharp_target_y, sharp_best_uv, sharp_target_uv, t_sharp;  // SharpYUV import working planes + gamma tables
   PinBuf h_stats_cuts, h_lc_img, h_coded_size, h_alpha, h_uv_alpha, h_segment, h_params, h_hdr, h_coeffs, h_stats, h_proba, h_totals, h_bases, h_tokens, h_bcp, h_p0, h_packed;
   int e_n = 0, e_w = 0, e_h = 0, e_mbw = 0, e_mbh = 0, e_rgba_stride = 0;
-  std::vector<long long> e_alpha_sum;  // per image: sum of the analysis alphas (low = busy picture); valid for the waves that follow wgpu_enc_device's plan
+  std::vector<long long> e_alpha_sum;  // per image: sum of the analysis alphas (low = busy picture), taken by enc_analyze_locked; e_order_valid until the next upload
   bool e_order_valid = false;
   DevBuf img_order; PinBuf h_img_order;
   bool e_uploaded = false, e_analyzed = false, e_done = false, e_keep_derr = false, e_keep_stats = false;
