@@ -286,6 +286,40 @@ def test_sharpyuv_kernel_code_on_cpu_matches_oracle(oracle):
                 assert it[k] == oracle.sharp_yuv(imgs[k])[3]
 
 
+def test_ssim_and_sse_pinned_to_libwebp_plane_distortion(oracle):
+    """libwebp 1.6.0's WebPPlaneDistortion (picture_psnr_enc.c: the sum of SSIMGet / SSIMGetClipped over every pixel,
+    which dsp.SSIM ports, internal/dsp/ssim.go:12-160) as the independent implementation behind the SSIM / SSE oracle.  libwebp
+    hands the sums back as float32, so SSIM agrees to float32 rounding (1e-6 relative is the north_star tolerance), SSE exactly
+    while it fits a float's 24 bits."""
+    import ctypes as C
+    import libwebp_ref
+    L = libwebp_ref.lib()
+    if L is None or not hasattr(L, "WebPPlaneDistortion"):
+        pytest.skip("libwebp not available")
+    L.WebPPlaneDistortion.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.c_int,
+                                      C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.WebPPlaneDistortion.restype = C.c_int
+    rng = np.random.default_rng(1)
+    for (w, h) in [(1, 1), (3, 2), (7, 7), (8, 3), (40, 56), (33, 57), (130, 71), (64, 64), (257, 119)]:
+        for kind in range(3):
+            a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            if kind == 0:
+                b = np.clip(a.astype(int) + rng.integers(-12, 13, (h, w)), 0, 255).astype(np.uint8)
+            elif kind == 1:
+                b = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            else:
+                a = np.full((h, w), 3, np.uint8)
+                b = a.copy()
+                b[h // 2:, :] = 250
+            d, r = C.c_float(), C.c_float()
+            assert L.WebPPlaneDistortion(a.ctypes.data, a.strides[0], b.ctypes.data, b.strides[0], w, h, 1, 1, C.byref(d), C.byref(r)) == 1
+            exp = oracle.plane_ssim(a, b)
+            assert abs(d.value - exp) <= 2e-7 * abs(exp) + 1e-6, (w, h, kind, d.value, exp)
+            assert L.WebPPlaneDistortion(a.ctypes.data, a.strides[0], b.ctypes.data, b.strides[0], w, h, 1, 0, C.byref(d), C.byref(r)) == 1
+            sse = oracle.plane_sse(a, b)
+            assert d.value == np.float32(sse), (w, h, kind)
+
+
 def test_ssim_kernel_code_on_cpu_matches_oracle(oracle):
     """The product's separable SSE / SSIM (webp_b200/csrc/ssim_sep.cuh: row sums, column sums, ssimCalculation) run on the CPU in
     the kernel's schedule with the tasks of each phase in shuffled order (oracle/hostcheck.cc hostcheck_ssim) vs the oracle's
